@@ -1,0 +1,406 @@
+/* sio_oracle.c -- CPU ORACLE for the collision-oracle hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * PARITY UNPINNED: the arithmetic of this path lives in Klampt 0.8.x / KrisLibrary (un-vendored,
+ * unpinned C++ dependency, README.md:54), absent from /root/reference and from this image; the
+ * reference holds no golden vector, known-answer test or fixture for it.  This file
+ * restates the published behaviour summarised in SURVEY.md Appendix A.2-A.4 and is pinned only
+ * by closed-form known answers (analytic SDFs) in tests/.  Every Klampt-side choice is a named
+ * constant below.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  The product (semiinfiniteoptimization_b200/) never does.
+ *
+ * What is restated (reference call site -> function here):
+ *   grid.distance_point(pt)           geometryopt.py:104-108,153   -> orc_query()
+ *   pc.distance_ext(grid, upperBound) geometryopt.py:117-127       -> orc_min_distance(), orc_under()
+ *   pose row [(R(pt-t)) x n, n]       geometryopt.py:413-418       -> orc_pose_rows()
+ *   robot.setConfig + getTransform    geometryopt.py:201-204,294   -> orc_fk()
+ *   Jp(local pt)^T n                  geometryopt.py:478-482       -> orc_chain_rows()
+ *
+ * Data: grid samples are float32 at CELL CENTRES, z fastest (geometryopt.py:25-28); cloud points
+ * are float32 xyz; transforms are row-major 3x4 float64.  Arithmetic is float64 throughout
+ * (orc_*_f32 variants exist only as the single-precision CPU timing baseline).
+ *
+ * Build: see oracle/Makefile  (-O3 -fopenmp -ffp-contract=off)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ---- named Klampt-side choices ------------------------------------ */
+#define ORC_CELL_CENTRED   1   /* A.1: samples at bmin + (i+1/2)h                                  */
+#define ORC_OUTSIDE_ADDS_BBOX_DISTANCE 1 /* A.2 step 2/4: d = v(clamp(p)) + |p - clamp(p)|        */
+
+typedef struct {
+    const float* v;       /* nx*ny*nz samples, z fastest */
+    int32_t nx, ny, nz;
+    double bmin[3], bmax[3];
+} orc_grid;
+
+int orc_version(void) { return 1; }
+int orc_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* A.2: distance and (optional) gradient w.r.t. the grid-local point p.
+ * gradient = masked trilinear derivative + outward unit vector of the bbox clamp. */
+static double query_local(const orc_grid* g, const double p[3], double* grad /*3 or NULL*/) {
+    const int dim[3] = {g->nx, g->ny, g->nz};
+    double o[3], f[3], h[3];
+    int i0[3], i1[3], interior[3];
+    double dout2 = 0;
+    for (int a = 0; a < 3; ++a) {
+        h[a] = (g->bmax[a] - g->bmin[a]) / (double)dim[a];
+        double c = p[a];
+        if (c < g->bmin[a]) c = g->bmin[a];
+        if (c > g->bmax[a]) c = g->bmax[a];
+        o[a] = p[a] - c;
+        dout2 += o[a] * o[a];
+        double u = (c - g->bmin[a]) / h[a] - 0.5;
+        interior[a] = (u > 0.0 && u < (double)(dim[a] - 1));
+        double uc = u;
+        if (uc < 0.0) uc = 0.0;
+        if (uc > (double)(dim[a] - 1)) uc = (double)(dim[a] - 1);
+        int i = (int)floor(uc);
+        if (i > dim[a] - 1) i = dim[a] - 1;
+        i0[a] = i;
+        i1[a] = (i + 1 < dim[a]) ? i + 1 : dim[a] - 1;
+        f[a] = uc - (double)i;
+    }
+    const size_t sy = (size_t)g->nz, sx = (size_t)g->ny * g->nz;
+#define V(I, J, K) ((double)g->v[(size_t)(I) * sx + (size_t)(J) * sy + (size_t)(K)])
+    double v000 = V(i0[0], i0[1], i0[2]), v001 = V(i0[0], i0[1], i1[2]);
+    double v010 = V(i0[0], i1[1], i0[2]), v011 = V(i0[0], i1[1], i1[2]);
+    double v100 = V(i1[0], i0[1], i0[2]), v101 = V(i1[0], i0[1], i1[2]);
+    double v110 = V(i1[0], i1[1], i0[2]), v111 = V(i1[0], i1[1], i1[2]);
+#undef V
+    /* z, then y, then x */
+    double dz00 = v001 - v000, dz01 = v011 - v010, dz10 = v101 - v100, dz11 = v111 - v110;
+    double a00 = v000 + f[2] * dz00, a01 = v010 + f[2] * dz01;
+    double a10 = v100 + f[2] * dz10, a11 = v110 + f[2] * dz11;
+    double dy0 = a01 - a00, dy1 = a11 - a10;
+    double b0 = a00 + f[1] * dy0, b1 = a10 + f[1] * dy1;
+    double dx = b1 - b0;
+    double val = b0 + f[0] * dx;
+    double dout = sqrt(dout2);
+    if (grad) {
+        double gz0 = dz00 + f[1] * (dz01 - dz00), gz1 = dz10 + f[1] * (dz11 - dz10);
+        double gf[3];
+        gf[0] = dx;
+        gf[1] = dy0 + f[0] * (dy1 - dy0);
+        gf[2] = gz0 + f[0] * (gz1 - gz0);
+        for (int a = 0; a < 3; ++a) {
+            double ga = interior[a] ? gf[a] / h[a] : 0.0;
+            if (dout > 0.0) ga += o[a] / dout;
+            grad[a] = ga;
+        }
+    }
+#if ORC_OUTSIDE_ADDS_BBOX_DISTANCE
+    return val + dout;
+#else
+    return val;
+#endif
+}
+
+static inline void xf_apply(const double* T, double x, double y, double z, double* p) {
+    p[0] = T[0] * x + T[1] * y + T[2] * z + T[3];
+    p[1] = T[4] * x + T[5] * y + T[6] * z + T[7];
+    p[2] = T[8] * x + T[9] * y + T[10] * z + T[11];
+}
+
+/* grid.distance_point for P points given in an input frame; T = grid-local <- input frame.
+ * grad (optional) is d(distance)/d(input point) = R^T * grad_local, normalised when `normalize`
+ * (A.2 step 5; zero vector stays zero). */
+void orc_query(const orc_grid* g, const double* T, const double* pts, int64_t P, int normalize,
+               double* d, double* grad) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < P; ++i) {
+        double p[3], gl[3];
+        xf_apply(T, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], p);
+        d[i] = query_local(g, p, grad ? gl : NULL);
+        if (grad) {
+            double gx = T[0] * gl[0] + T[4] * gl[1] + T[8] * gl[2];
+            double gy = T[1] * gl[0] + T[5] * gl[1] + T[9] * gl[2];
+            double gz = T[2] * gl[0] + T[6] * gl[1] + T[10] * gl[2];
+            if (normalize) {
+                double n = sqrt(gx * gx + gy * gy + gz * gz);
+                if (n > 0.0) { gx /= n; gy /= n; gz /= n; }
+            }
+            grad[3 * i] = gx; grad[3 * i + 1] = gy; grad[3 * i + 2] = gz;
+        }
+    }
+}
+
+/* the same over a float32 cloud and B transforms, per-point outputs (B*N) */
+void orc_cloud_query(const orc_grid* g, const float* cloud, int64_t N, const double* T, int64_t B,
+                     int normalize, double* d, double* grad) {
+#pragma omp parallel for schedule(static) collapse(2)
+    for (int64_t b = 0; b < B; ++b)
+        for (int64_t i = 0; i < N; ++i) {
+            const double* Tb = T + 12 * b;
+            double p[3], gl[3];
+            xf_apply(Tb, (double)cloud[3 * i], (double)cloud[3 * i + 1], (double)cloud[3 * i + 2], p);
+            d[b * N + i] = query_local(g, p, grad ? gl : NULL);
+            if (grad) {
+                double gx = Tb[0] * gl[0] + Tb[4] * gl[1] + Tb[8] * gl[2];
+                double gy = Tb[1] * gl[0] + Tb[5] * gl[1] + Tb[9] * gl[2];
+                double gz = Tb[2] * gl[0] + Tb[6] * gl[1] + Tb[10] * gl[2];
+                if (normalize) {
+                    double n = sqrt(gx * gx + gy * gy + gz * gz);
+                    if (n > 0.0) { gx /= n; gy /= n; gz /= n; }
+                }
+                double* o = grad + 3 * (b * N + i);
+                o[0] = gx; o[1] = gy; o[2] = gz;
+            }
+        }
+}
+
+/* pc.distance_ext(grid): brute-force min over the cloud (A.3), lowest index wins ties.
+ * grids[grid_of_b[b]] selects the grid of transform b (NULL -> grid 0).
+ * argmin = -1 when bound is finite and dmin >= bound (the wrapper's "[]", geometryopt.py:411). */
+void orc_min_distance(const orc_grid* grids, const int32_t* grid_of_b, const float* cloud, int64_t N,
+                      const double* T, const double* bound, int64_t B, double* dmin, int64_t* argmin) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t b = 0; b < B; ++b) {
+        const orc_grid* g = grids + (grid_of_b ? grid_of_b[b] : 0);
+        const double* Tb = T + 12 * b;
+        double best = INFINITY;
+        int64_t bi = -1;
+        for (int64_t i = 0; i < N; ++i) {
+            double p[3];
+            xf_apply(Tb, (double)cloud[3 * i], (double)cloud[3 * i + 1], (double)cloud[3 * i + 2], p);
+            double d = query_local(g, p, NULL);
+            if (d < best) { best = d; bi = i; }
+        }
+        dmin[b] = best;
+        if (bound && !(best < bound[b])) bi = -1;
+        argmin[b] = bi;
+    }
+}
+
+/* single-transform variant parallelised over points (B small, N large) */
+void orc_min_distance_1(const orc_grid* g, const float* cloud, int64_t N, const double* T,
+                        double* dmin, int64_t* argmin) {
+    double best = INFINITY;
+    int64_t bi = -1;
+#pragma omp parallel
+    {
+        double lb = INFINITY;
+        int64_t li = -1;
+#pragma omp for schedule(static) nowait
+        for (int64_t i = 0; i < N; ++i) {
+            double p[3];
+            xf_apply(T, (double)cloud[3 * i], (double)cloud[3 * i + 1], (double)cloud[3 * i + 2], p);
+            double d = query_local(g, p, NULL);
+            if (d < lb) { lb = d; li = i; }
+        }
+#pragma omp critical
+        {
+            if (lb < best || (lb == best && li >= 0 && (bi < 0 || li < bi))) { best = lb; bi = li; }
+        }
+    }
+    *dmin = best;
+    *argmin = bi;
+}
+
+/* all (b, i) with d < bound[b], in (b, i) order.  Returns the total count; writes at most cap. */
+int64_t orc_under(const orc_grid* grids, const int32_t* grid_of_b, const float* cloud, int64_t N,
+                  const double* T, const double* bound, int64_t B, int64_t cap,
+                  int64_t* out_b, int64_t* out_i, double* out_d) {
+    int64_t cnt = 0;
+    for (int64_t b = 0; b < B; ++b) {
+        const orc_grid* g = grids + (grid_of_b ? grid_of_b[b] : 0);
+        const double* Tb = T + 12 * b;
+        if (!(bound[b] < INFINITY)) continue;
+        for (int64_t i = 0; i < N; ++i) {
+            double p[3];
+            xf_apply(Tb, (double)cloud[3 * i], (double)cloud[3 * i + 1], (double)cloud[3 * i + 2], p);
+            double d = query_local(g, p, NULL);
+            if (d < bound[b]) {
+                if (cnt < cap) { out_b[cnt] = b; out_i[cnt] = i; out_d[cnt] = d; }
+                ++cnt;
+            }
+        }
+    }
+    return cnt;
+}
+
+/* ObjectCollisionConstraint.value + df_dx (geometryopt.py:407-408, 413-418) for P world points.
+ * Tpose = world <- object(grid) as row-major 3x4.  n = grad1 = -(gradient w.r.t. the world
+ * point); row = [ (R (pt - t)) x n , n ]  -- the lever arm is R(pt - t) exactly as written in the
+ * reference (Appendix B quirk). */
+void orc_pose_rows(const orc_grid* g, const double* Tpose, const double* pts, int64_t P, int normalize,
+                   double* d, double* rows) {
+    /* inverse transform: grid-local <- world */
+    double Ti[12];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) Ti[4 * r + c] = Tpose[4 * c + r];
+        Ti[4 * r + 3] = -(Tpose[0 + r] * Tpose[3] + Tpose[4 + r] * Tpose[7] + Tpose[8 + r] * Tpose[11]);
+    }
+    double* grad = (double*)malloc(sizeof(double) * 3 * (size_t)(P > 0 ? P : 1));
+    orc_query(g, Ti, pts, P, normalize, d, grad);
+    for (int64_t i = 0; i < P; ++i) {
+        double n[3] = {-grad[3 * i], -grad[3 * i + 1], -grad[3 * i + 2]};
+        double q[3] = {pts[3 * i] - Tpose[3], pts[3 * i + 1] - Tpose[7], pts[3 * i + 2] - Tpose[11]};
+        double r[3];
+        for (int a = 0; a < 3; ++a) r[a] = Tpose[4 * a] * q[0] + Tpose[4 * a + 1] * q[1] + Tpose[4 * a + 2] * q[2];
+        double* o = rows + 6 * i;
+        o[0] = r[1] * n[2] - r[2] * n[1];
+        o[1] = r[2] * n[0] - r[0] * n[2];
+        o[2] = r[0] * n[1] - r[1] * n[0];
+        o[3] = n[0]; o[4] = n[1]; o[5] = n[2];
+    }
+    free(grad);
+}
+
+/* ---- kinematics (Klampt RobotModel restated: serial/tree chain of revolute or prismatic links)
+ * T_link = T_parent * TParent_link * Joint(axis, q);  revolute: rotation about `axis` by q,
+ * prismatic: translation along `axis` by q.  All transforms row-major 3x4. */
+typedef struct {
+    int32_t n;
+    const int32_t* parent;   /* n, -1 for roots */
+    const int32_t* jtype;    /* n, 0 revolute, 1 prismatic */
+    const double* tparent;   /* n*12 */
+    const double* axis;      /* n*3, unit */
+} orc_robot;
+
+static void mat_mul34(const double* A, const double* B, double* C) {
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c)
+            C[4 * r + c] = A[4 * r] * B[c] + A[4 * r + 1] * B[4 + c] + A[4 * r + 2] * B[8 + c];
+        C[4 * r + 3] = A[4 * r] * B[3] + A[4 * r + 1] * B[7] + A[4 * r + 2] * B[11] + A[4 * r + 3];
+    }
+}
+
+static void joint_xform(const double* ax, int jtype, double q, double* J) {
+    if (jtype == 1) {
+        J[0] = 1; J[1] = 0; J[2] = 0; J[3] = ax[0] * q;
+        J[4] = 0; J[5] = 1; J[6] = 0; J[7] = ax[1] * q;
+        J[8] = 0; J[9] = 0; J[10] = 1; J[11] = ax[2] * q;
+        return;
+    }
+    double c = cos(q), s = sin(q), C = 1.0 - c;
+    double x = ax[0], y = ax[1], z = ax[2];
+    J[0] = c + x * x * C;     J[1] = x * y * C - z * s; J[2] = x * z * C + y * s; J[3] = 0;
+    J[4] = y * x * C + z * s; J[5] = c + y * y * C;     J[6] = y * z * C - x * s; J[7] = 0;
+    J[8] = z * x * C - y * s; J[9] = z * y * C + x * s; J[10] = c + z * z * C;    J[11] = 0;
+}
+
+/* q: B*n  ->  Tout: B*n*12 (world <- link) */
+void orc_fk(const orc_robot* R, const double* q, int64_t B, double* Tout) {
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < B; ++b) {
+        for (int l = 0; l < R->n; ++l) {
+            double J[12], L[12];
+            joint_xform(R->axis + 3 * l, R->jtype[l], q[b * R->n + l], J);
+            mat_mul34(R->tparent + 12 * l, J, L);
+            double* out = Tout + (b * R->n + l) * 12;
+            if (R->parent[l] < 0) memcpy(out, L, sizeof(L));
+            else mat_mul34(Tout + (b * R->n + R->parent[l]) * 12, L, out);
+        }
+    }
+}
+
+/* RobotLinkCollisionConstraint.value + df_dx (geometryopt.py:472-473, 478-482) at one config q:
+ * d = SDF_link(T_link^-1 pt);  n = grad1;  Jp column j (ancestor-or-self j of `link`):
+ *   revolute  w_j x (pt - o_j)   with w_j = R_j axis_j, o_j = origin of frame j (after the joint),
+ *   prismatic w_j;   row = Jp^T n  (n entries). */
+void orc_chain_rows(const orc_robot* R, int32_t link, const orc_grid* g, const double* q,
+                    const double* pts, int64_t P, int normalize, double* d, double* rows) {
+    double* Tl = (double*)malloc(sizeof(double) * 12 * (size_t)R->n);
+    orc_fk(R, q, 1, Tl);
+    const double* Tpose = Tl + 12 * link;
+    double Ti[12];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) Ti[4 * r + c] = Tpose[4 * c + r];
+        Ti[4 * r + 3] = -(Tpose[0 + r] * Tpose[3] + Tpose[4 + r] * Tpose[7] + Tpose[8 + r] * Tpose[11]);
+    }
+    double* grad = (double*)malloc(sizeof(double) * 3 * (size_t)(P > 0 ? P : 1));
+    orc_query(g, Ti, pts, P, normalize, d, grad);
+    for (int64_t i = 0; i < P; ++i) {
+        double n[3] = {-grad[3 * i], -grad[3 * i + 1], -grad[3 * i + 2]};
+        double* o = rows + (size_t)R->n * i;
+        for (int j = 0; j < R->n; ++j) o[j] = 0.0;
+        for (int j = link; j >= 0; j = R->parent[j]) {
+            const double* Tj = Tl + 12 * j;
+            const double* ax = R->axis + 3 * j;
+            double w[3];
+            for (int a = 0; a < 3; ++a) w[a] = Tj[4 * a] * ax[0] + Tj[4 * a + 1] * ax[1] + Tj[4 * a + 2] * ax[2];
+            if (R->jtype[j] == 1) {
+                o[j] = w[0] * n[0] + w[1] * n[1] + w[2] * n[2];
+            } else {
+                double r[3] = {pts[3 * i] - Tj[3], pts[3 * i + 1] - Tj[7], pts[3 * i + 2] - Tj[11]};
+                double cx = w[1] * r[2] - w[2] * r[1], cy = w[2] * r[0] - w[0] * r[2], cz = w[0] * r[1] - w[1] * r[0];
+                o[j] = cx * n[0] + cy * n[1] + cz * n[2];
+            }
+        }
+    }
+    free(grad);
+    free(Tl);
+}
+
+/* ---- single-precision brute force, used ONLY as a CPU timing baseline (bench.py) ---------- */
+static inline float query_local_f32(const orc_grid* g, const float* bminf, const float* invh, const float* hf,
+                                    float px, float py, float pz) {
+    const int dim[3] = {g->nx, g->ny, g->nz};
+    float p[3] = {px, py, pz}, f[3];
+    int i0[3], i1[3];
+    float dout2 = 0.f;
+    for (int a = 0; a < 3; ++a) {
+        float u = (p[a] - bminf[a]) * invh[a] - 0.5f;
+        float lo = -0.5f, hi = (float)dim[a] - 0.5f;
+        float ub = u < lo ? lo : (u > hi ? hi : u);
+        float o = (u - ub) * hf[a];
+        dout2 += o * o;
+        float uc = ub < 0.f ? 0.f : (ub > (float)(dim[a] - 1) ? (float)(dim[a] - 1) : ub);
+        int i = (int)uc;
+        i0[a] = i;
+        i1[a] = (i + 1 < dim[a]) ? i + 1 : dim[a] - 1;
+        f[a] = uc - (float)i;
+    }
+    const size_t sy = (size_t)g->nz, sx = (size_t)g->ny * g->nz;
+#define V(I, J, K) (g->v[(size_t)(I) * sx + (size_t)(J) * sy + (size_t)(K)])
+    float a00 = V(i0[0], i0[1], i0[2]) + f[2] * (V(i0[0], i0[1], i1[2]) - V(i0[0], i0[1], i0[2]));
+    float a01 = V(i0[0], i1[1], i0[2]) + f[2] * (V(i0[0], i1[1], i1[2]) - V(i0[0], i1[1], i0[2]));
+    float a10 = V(i1[0], i0[1], i0[2]) + f[2] * (V(i1[0], i0[1], i1[2]) - V(i1[0], i0[1], i0[2]));
+    float a11 = V(i1[0], i1[1], i0[2]) + f[2] * (V(i1[0], i1[1], i1[2]) - V(i1[0], i1[1], i0[2]));
+#undef V
+    float b0 = a00 + f[1] * (a01 - a00), b1 = a10 + f[1] * (a11 - a10);
+    float val = b0 + f[0] * (b1 - b0);
+    return dout2 > 0.f ? val + sqrtf(dout2) : val;
+}
+
+void orc_min_distance_f32(const orc_grid* g, const float* cloud, int64_t N, const double* T, int64_t B,
+                          float* dmin, int64_t* argmin) {
+    float bminf[3], invh[3], hf[3];
+    const int dim[3] = {g->nx, g->ny, g->nz};
+    for (int a = 0; a < 3; ++a) {
+        double h = (g->bmax[a] - g->bmin[a]) / dim[a];
+        bminf[a] = (float)g->bmin[a]; invh[a] = (float)(1.0 / h); hf[a] = (float)h;
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t b = 0; b < B; ++b) {
+        float M[12];
+        for (int k = 0; k < 12; ++k) M[k] = (float)T[12 * b + k];
+        float best = INFINITY;
+        int64_t bi = -1;
+        for (int64_t i = 0; i < N; ++i) {
+            float x = cloud[3 * i], y = cloud[3 * i + 1], z = cloud[3 * i + 2];
+            float px = M[0] * x + M[1] * y + M[2] * z + M[3];
+            float py = M[4] * x + M[5] * y + M[6] * z + M[7];
+            float pz = M[8] * x + M[9] * y + M[10] * z + M[11];
+            float d = query_local_f32(g, bminf, invh, hf, px, py, pz);
+            if (d < best) { best = d; bi = i; }
+        }
+        dmin[b] = best;
+        argmin[b] = bi;
+    }
+}
