@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the collision-oracle hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "C2"): the m1062 tree mesh as a signed distance grid at
+gridres 0.01 (68x98x105 cell-centred float32 samples) is the moving body; the static cloud is the
+declared synthetic 2^20-point upsample of bunny.pcd (point j = 4*(b[j mod 397] -
+centroid) + centre(bbox(m1062)) + N(0, 0.005^2 I), numpy default_rng(1)); 64 seeded poses per GPU
+(w ~ U(-0.3,0.3)^3, t ~ U(-0.1,0.1)^3).
+
+A STEP is one oracle sweep: the K2 call (transform + trilinear SDF query of every cloud point for
+every pose, minimum / arg-minimum / under-bound set with the float64 near-tie re-check) over
+64 x 2^20 = 67,108,864 point-queries per GPU.  With N > 1 every rank owns its own 64 poses (weak
+scaling; geometry replicated) and the compact per-pose results are all-gathered with NCCL.
+
+`value`  : point-queries/s, inputs resident in HBM, timed with CUDA events on the launching stream,
+           max over ranks; L2 is flushed between timed steps.
+`e2e`    : the same sweep through the host-pointer C-ABI call a user of the Python API makes
+           (poses + bounds H2D, results D2H inside the timed region, wall clock).
+`roofline`: the dominant kernel k_min_f32 against the measured HBM copy peak using the
+           ALGORITHMIC 48 B/query of SURVEY.md 8d, and (extra key `gather`) its 32 B/query of corner
+           gathers against an L2 gather peak measured here.
+`cpu_baseline`: the CPU oracle (oracle/, float64 brute force, all host threads) on a bounded
+           sample of the same sweep, rank 0 / N=1 only.
+
+--impl reference times that CPU oracle port as the reference arm (the reference itself is
+Python 2 on absent Klampt/OSQP and cannot run).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+POSES_PER_GPU = 64
+CLOUD_N = 1 << 20
+GRIDRES = 0.01
+BYTES_PER_QUERY = 48          # 16 B float4 point + 8 x 4 B corners
+GATHER_BYTES_PER_QUERY = 32
+METRIC = "sdf_oracle_point_queries_per_s"
+UNIT = "queries/s"
+
+
+def build_workload(rank=0):
+    from semiinfiniteoptimization_b200._host.geometry import fixture_geometry
+    from semiinfiniteoptimization_b200._host import se3, so3
+    tree = fixture_geometry("m1062")
+    vg = tree.convert("VolumeGrid", GRIDRES).getVolumeGrid()
+    b = fixture_geometry("bunny").getPointCloud().points
+    rng = np.random.default_rng(1)
+    lo, hi = tree.data.bbox()
+    centre = 0.5 * (lo + hi)
+    j = np.arange(CLOUD_N) % len(b)
+    cloud = 4.0 * (b[j] - b.mean(0)) + centre + rng.normal(0.0, 0.005, (CLOUD_N, 3))
+    cloud = cloud.astype(np.float32)
+    # poses of the moving body (world <- grid); cloud frame = world.  T_rel = pose^-1
+    prng = np.random.default_rng(1000 + rank)
+    T_rel = np.empty((POSES_PER_GPU, 12))
+    for i in range(POSES_PER_GPU):
+        w = prng.uniform(-0.3, 0.3, 3)
+        t = prng.uniform(-0.1, 0.1, 3)
+        # rotate about the body centre so the pose set stays in contact with the cloud
+        R = so3.from_rotation_vector(w)
+        tt = [float(v) for v in (centre - so3.matrix(R) @ centre + t)]
+        T_rel[i] = se3.to_rowmajor12(se3.inv((R, tt)))
+    bound = np.zeros(POSES_PER_GPU)       # SIP's discovery bound min(0, min depths) (sip.py:215-219)
+    return vg, cloud, T_rel, bound
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for l in self.proc.stdout:
+            self.lines.append(l.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, smax, reasons = [], None, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(vg, cloud, T_rel, budget_s=12.0, native=True):
+    """CPU oracle port on a bounded sample: float64 brute force, all host threads."""
+    from oracle import oracle as O
+    L = None
+    if native:
+        try:
+            O.build(native=True)          # tune for the GPU box's host CPU when gcc is there
+            L = O.lib(prefer_native=True)
+        except Exception:
+            L = None
+    L = L or O.lib()
+    G = O.Grid(vg.values, vg.bmin, vg.bmax)
+    threads = L.orc_max_threads()
+    npose = max(1, min(len(T_rel), threads))
+    # calibrate on a slice, then size the sample for ~budget_s
+    n0 = 1 << 16
+    t0 = time.perf_counter()
+    O.min_distance(G, cloud[:n0], T_rel[:npose], L=L)
+    rate = npose * n0 / (time.perf_counter() - t0)
+    npts = int(min(len(cloud), max(n0, rate * budget_s / npose)))
+    t0 = time.perf_counter()
+    O.min_distance(G, cloud[:npts], T_rel[:npose], L=L)
+    dt = time.perf_counter() - t0
+    return {"value": npose * npts / dt, "unit": UNIT, "cores": int(threads), "kind": "port",
+            "sample": "%d poses x %d cloud points of the same sweep, float64 brute force (no hierarchy pruning), %.1f s"
+                      % (npose, npts, dt)}
+
+
+def run_reference(args):
+    """Reference arm: the CPU oracle port timed on the host cores, same config/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    try:
+        O.build(native=True)
+        L = O.lib(prefer_native=True)
+    except Exception:
+        L = O.lib()
+    vg, cloud, T_rel, bound = build_workload(0)
+    G = O.Grid(vg.values, vg.bmin, vg.bmax)
+    threads = L.orc_max_threads()
+    npose = max(1, min(POSES_PER_GPU, threads))
+    # per step: npose poses x a slice of the cloud sized for ~2 s
+    n0 = 1 << 15
+    t0 = time.perf_counter()
+    O.min_distance(G, cloud[:n0], T_rel[:npose], L=L)
+    rate = npose * n0 / (time.perf_counter() - t0)
+    npts = int(min(CLOUD_N, max(n0, rate * 2.0 / npose)))
+    for _ in range(args.warmup):
+        O.min_distance(G, cloud[:npts], T_rel[:npose], L=L)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.min_distance(G, cloud[:npts], T_rel[:npose], L=L)
+    dt = time.perf_counter() - t0
+    val = args.steps * npose * npts / dt
+    sample = "%d poses x %d cloud points per step (bounded sample of the 64 x 2^20 sweep), float64 brute force" % (npose, npts)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": int(threads), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference is Python 2 on Klampt/OSQP (absent, un-vendored): its path cannot run; this arm is the CPU "
+                    "oracle port (oracle/sio_oracle.c) on the host cores"}
+    print(json.dumps(line))
+
+
+def workload_config(ngpu):
+    return {"workload": "C2 bunny-vs-m1062 fine grid: m1062 SDF gridres 0.01 (68x98x105 f32), synthetic 2^20-point bunny "
+                        "upsample (seed 1), 64 seeded poses per GPU, one K2 min/arg-min/under-bound sweep per step",
+            "poses_per_gpu": POSES_PER_GPU, "cloud_points": CLOUD_N, "queries_per_step_per_gpu": POSES_PER_GPU * CLOUD_N,
+            "sharding": "poses across ranks (geometry replicated), NCCL all_gather of per-pose results" if ngpu > 1 else "single GPU",
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from semiinfiniteoptimization_b200 import _abi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the collision oracle has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    vg, cloud, T_rel, bound = build_workload(rank)
+    ctx = _abi.Context(local)
+    g = ctx.grid_create(vg.values, vg.bmin, vg.bmax)
+    c = ctx.cloud_create(cloud)
+    B = POSES_PER_GPU
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    dT = torch.from_numpy(T_rel).cuda()
+    dbound = torch.from_numpy(bound).cuda()
+    ddmin = torch.empty(B, dtype=torch.float64, device="cuda")
+    darg = torch.empty(B, dtype=torch.int64, device="cuda")
+    gathered = [torch.empty(B * 2, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.min_distance_dev([g], c, dT.data_ptr(), dbound.data_ptr(), B, _abi.SIO_F32, ddmin.data_ptr(), darg.data_ptr())
+        if world > 1:
+            with torch.cuda.stream(stream):
+                packed = torch.cat([ddmin, darg.to(torch.float64)])
+                dist.all_gather(gathered, packed)
+
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    bulk_ms = []
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()                       # evict L2 (126 MB) between timed steps
+        ev[k][0].record(stream)
+        step()
+        ev[k][1].record(stream)
+        bulk_ms.append(None)
+        ev[k][1].synchronize()
+        bulk_ms[k] = ctx.last_bulk_ms()
+    ctx.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches - launches0
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(ms_steps))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    queries_per_step = B * CLOUD_N * world
+    value = queries_per_step * args.steps / (total_ms * 1e-3)
+
+    # end to end through the host-pointer call (what PenetrationDepthGeometry.distance(other) issues)
+    for _ in range(2):
+        ctx.min_distance(g, c, T_rel, bound=bound)
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dmin_h, arg_h, nu_h = ctx.min_distance(g, c, T_rel, bound=bound)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    n_under = int(nu_h.sum())
+    e2e = {"value": queries_per_step * args.steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(B * (96 + 8)), "d2h_bytes_per_step": int(B * 16 + 4 + n_under * 16),
+           "call": "sio_min_distance (host pointers): poses+bounds H2D, dmin/argmin/under-list D2H; geometry resident as in "
+                   "the reference API (PenetrationDepthGeometry builds grid+cloud once)"}
+
+    if rank == 0:
+        bulk = float(np.mean(bulk_ms))
+        q1 = B * CLOUD_N
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = q1 * BYTES_PER_QUERY / (bulk * 1e-3) / 1e9
+        gather_peak = ctx.bench_gather(int(np.prod(vg.dims)), 1 << 26, iters=5)
+        roofline = {"bound": "hbm", "kernel": "k_min_f32", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
+                    "bytes_per_query": BYTES_PER_QUERY, "kernel_ms": bulk,
+                    "gather": {"achieved": q1 * GATHER_BYTES_PER_QUERY / (bulk * 1e-3) / 1e9, "peak": gather_peak, "unit": "GB/s",
+                               "frac": q1 * GATHER_BYTES_PER_QUERY / (bulk * 1e-3) / 1e9 / gather_peak,
+                               "peak_source": "sio_bench_gather: random 4 B loads over an L2-resident array of the grid's size"}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
+                "check": {"dmin_first": float(dmin_h[0]), "argmin_first": int(arg_h[0]), "n_under_total": n_under}}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(vg, cloud, T_rel)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

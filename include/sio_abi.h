@@ -1,0 +1,156 @@
+/* sio_abi.h -- C-ABI of the B200 collision oracle (libsio_b200.so).
+ *
+ * This is the drop-in boundary for the collision-oracle hot path of
+ * krishauser/SemiInfiniteOptimization.  The reference reaches that path through Klampt's SWIG
+ * bindings; each entry point below names the reference call site(s) (file:line under
+ * /root/reference) whose work it replaces.  The Python classes that keep the reference's names
+ * (`PenetrationDepthGeometry`, `ObjectCollisionConstraint`, ... in
+ * semiinfiniteoptimization_b200/geometryopt.py) bind these symbols with ctypes; INTEGRATION.md
+ * shows the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions cross the boundary.  Every function returns
+ *     SIO_OK (0) or a negative status; sio_last_error() gives the message (thread-local).
+ *   - rigid transforms are row-major 3x4 double[12] = [R | t]  (Klampt's se3 (R,t) has R
+ *     column-major; the Python shim converts).
+ *   - grid samples: float32, values at CELL CENTRES, flat order (i*ny + j)*nz + k (z fastest) --
+ *     the order geometryopt.py:25-28 reads a Klampt VolumeGrid in.
+ *   - cloud points: float32 xyz[N*3].  Indices returned are indices into THAT array (the
+ *     library's internal Morton reordering is invisible).
+ *   - precision: SIO_F32 = float32 arithmetic for the bulk pass + float64 re-evaluation of every
+ *     near-tie, so minima / arg-minima / under-bound sets equal the float64 oracle's;
+ *     SIO_F64 = float64 arithmetic everywhere (validation mode).
+ *   - "host" entry points take host pointers and copy in/out on the context's stream; "_dev"
+ *     entry points take device pointers, enqueue on the context's stream and do not synchronise.
+ */
+#ifndef SIO_ABI_H
+#define SIO_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIO_ABI_VERSION 1
+
+/* status codes */
+#define SIO_OK               0
+#define SIO_ERR_INVALID     -1   /* bad argument / handle                       */
+#define SIO_ERR_CUDA        -2   /* CUDA runtime error (message has the detail) */
+#define SIO_ERR_NOMEM       -3
+#define SIO_ERR_NODEVICE    -4   /* no usable CUDA device: the product has no CPU fallback */
+#define SIO_ERR_OVERFLOW    -5   /* an output capacity was too small; counts are still exact */
+
+/* flags */
+#define SIO_F32             0x0
+#define SIO_F64             0x1
+#define SIO_NO_NORMALIZE    0x2   /* return the raw analytic gradient instead of the unit one */
+#define SIO_WANT_GRAD       0x4
+
+typedef struct sio_ctx sio_ctx;
+typedef int32_t sio_handle;
+
+int         sio_abi_version(void);
+const char* sio_last_error(void);
+
+/* ---- context: one per device, owns a stream, scratch arenas and all handles --------------- */
+int   sio_ctx_create(int device, sio_ctx** out);
+int   sio_ctx_destroy(sio_ctx* ctx);
+int   sio_ctx_sync(sio_ctx* ctx);
+void* sio_ctx_stream(sio_ctx* ctx);                 /* the cudaStream_t kernels are launched on */
+int   sio_ctx_set_tau(sio_ctx* ctx, double tau);    /* near-tie window (metres) of the f64 re-check; <=0 -> automatic */
+int   sio_ctx_num_sms(sio_ctx* ctx);
+int64_t sio_ctx_kernel_launches(sio_ctx* ctx);      /* kernels launched by this context so far */
+
+/* ---- resident geometry ----------------------------------------------------------------------
+ * replaces: Geometry3D.convert(...) results being handed to Klampt's collision data structures,
+ * geometryopt.py:58-66 (PenetrationDepthGeometry.__init__).  Built once, immutable. */
+int sio_grid_create(sio_ctx* ctx, const float* values, const int32_t dims[3],
+                    const double bmin[3], const double bmax[3], sio_handle* out);
+int sio_grid_destroy(sio_ctx* ctx, sio_handle grid);
+int sio_cloud_create(sio_ctx* ctx, const float* xyz, int64_t n, sio_handle* out);
+int sio_cloud_destroy(sio_ctx* ctx, sio_handle cloud);
+int64_t sio_cloud_size(sio_ctx* ctx, sio_handle cloud);
+
+/* ---- K1: point queries ----------------------------------------------------------------------
+ * replaces: grid.distance_point(pt[,settings]) -- geometryopt.py:104-108 (PDG.distance(point)),
+ * :139, :153 (PDG.normal).  T_grid_from_in maps the frame the points are given in (normally
+ * world) to grid-local, i.e. it is the INVERSE of the pose set by setTransform (gopt:85-88).
+ * d[P]; grad[P*3] = d(distance)/d(input point) (Klampt's grad1 is its negative), may be NULL. */
+int sio_query(sio_ctx* ctx, sio_handle grid, const double T_grid_from_in[12],
+              const double* pts, int64_t P, int flags, double* d, double* grad);
+
+/* the same over a resident cloud and B transforms, outputs stay on the device:
+ * out_d[B*N] float (and out_g[B*N] float4 = (gx,gy,gz,d) when non-NULL); SIO_F32 only.
+ * Point order is the cloud's INTERNAL order (throughput mode; use sio_cloud_perm to map). */
+int sio_cloud_query_dev(sio_ctx* ctx, sio_handle grid, sio_handle cloud, const double* dT_rel,
+                        int64_t B, int flags, float* out_d, float* out_g4);
+int sio_cloud_perm(sio_ctx* ctx, sio_handle cloud, int32_t* perm_out /* internal -> caller index */);
+
+/* ---- K2: cloud-vs-grid minimum + active set -------------------------------------------------
+ * replaces: pc.distance_ext(grid, settings{upperBound}) -- geometryopt.py:117-127, called from
+ * ObjectCollisionConstraint.minvalue (gopt:409-412), RobotLinkCollisionConstraint.minvalue
+ * (gopt:474-477) and the milestone / bisection sweeps of the trajectory constraints
+ * (gopt:610, 640, 748, 822, 896).  Batched over B transforms:
+ *   T_rel[b]   grid-local <- cloud-local of query b  (= T_grid(b)^-1 * T_cloud)
+ *   grid_of_b  index into grids[] per query (NULL: all use grids[0])
+ *   bound[b]   Klampt's upperBound; +inf or bound==NULL means none
+ * outputs per b:  dmin[b] (exact float64 value of the winner), argmin[b] (cloud index, lowest
+ * index on exact ties; -1 when bound is finite and dmin >= bound, the wrapper's "[]" case,
+ * gopt:411/476), n_under[b] = #{i : d(b,i) < bound[b]} (0 for an infinite bound).
+ * The compact under-bound list (b, i, d) sorted by (b, i) is fetched with sio_under_fetch. */
+int sio_min_distance(sio_ctx* ctx, const sio_handle* grids, int32_t n_grids, const int32_t* grid_of_b,
+                     sio_handle cloud, const double* T_rel, const double* bound, int64_t B, int flags,
+                     double* dmin, int64_t* argmin, int32_t* n_under);
+int sio_min_distance_dev(sio_ctx* ctx, const sio_handle* grids, int32_t n_grids, const int32_t* d_grid_of_b,
+                         sio_handle cloud, const double* dT_rel, const double* d_bound, int64_t B, int flags,
+                         double* d_dmin, int64_t* d_argmin);
+/* under-bound list of the LAST sio_min_distance[_dev] call on this context (synchronises).
+ * *total = exact number of entries; at most `capacity` are written. */
+int sio_under_fetch(sio_ctx* ctx, int64_t capacity, int64_t* b_out, int64_t* idx_out, double* d_out,
+                    int64_t* total);
+
+/* ---- K3: Jacobian rows ----------------------------------------------------------------------
+ * replaces: ObjectCollisionConstraint.value + df_dx -- geometryopt.py:407-408, 413-418.
+ * Batched over `nprob` independent poses; problem p owns points [offsets[p], offsets[p+1]).
+ * T_pose[p] = world <- object(grid).  d[i]; rows[i*6] = [ (R(pt - t)) x n , n ], n = grad1. */
+int sio_pose_rows(sio_ctx* ctx, sio_handle grid, const double* T_pose, const int64_t* offsets,
+                  int64_t nprob, const double* pts, int flags, double* d, double* rows);
+
+/* ---- K4: kinematics -------------------------------------------------------------------------
+ * replaces: RobotModel.setConfig + RobotModelLink.getTransform -- geometryopt.py:201-204, 294-295,
+ * 636-637, 658-659, 893-895; link.getLocalPosition / getPositionJacobian -- gopt:479-482, 670-672,
+ * 923-925.  jtype: 0 revolute, 1 prismatic.  tparent: n*12 row-major, axis: n*3. */
+int sio_robot_create(sio_ctx* ctx, int32_t n_links, const int32_t* parent, const int32_t* jtype,
+                     const double* tparent, const double* axis, sio_handle* out);
+int sio_robot_destroy(sio_ctx* ctx, sio_handle robot);
+int sio_fk(sio_ctx* ctx, sio_handle robot, const double* q, int64_t B, double* T_out /* B*n*12 */);
+/* RobotLinkCollisionConstraint / RobotTrajectoryCollisionConstraint value + df_dx
+ * (gopt:472-473, 478-482, 704-722, 906-925): point i is attached to link[i] with grid
+ * grids[link_grid[link[i]]] at configuration q[cfg[i]]; rows[i*n] = Jp^T n. */
+int sio_chain_rows(sio_ctx* ctx, sio_handle robot, const sio_handle* link_grids /* n_links, -1 = none */,
+                   const double* q, int64_t n_cfg, const int32_t* cfg_of_pt, const int32_t* link_of_pt,
+                   const double* pts, int64_t P, int flags, double* d, double* rows);
+
+/* fused FK -> relative transforms -> K2 for robot links against one static cloud (pose sweeps and
+ * trajectory time-sample sweeps, gopt:736-759, 802-858 batched).  Query (s, l) uses configuration
+ * q[s], link links[l], grid link_grids[links[l]]; T_cloud = world <- cloud.  Outputs are
+ * [S*n_sel] in (s, l) order; the under-bound list uses b = s*n_sel + l. */
+int sio_robot_min_distance(sio_ctx* ctx, sio_handle robot, const sio_handle* link_grids,
+                           const int32_t* links, int32_t n_sel, sio_handle cloud, const double T_cloud[12],
+                           const double* q, int64_t S, const double* bound /* S*n_sel or NULL */, int flags,
+                           double* dmin, int64_t* argmin, int32_t* n_under);
+
+/* ---- measurement helpers (bench.py only) ---------------------------------------------------- */
+/* device time (ms, CUDA events on the context's stream) of the fp32 bulk kernel launches
+ * (k_min_f32) of the LAST sio_min_distance[_dev] call; synchronises on that call's end event. */
+int sio_ctx_last_bulk_ms(sio_ctx* ctx, double* ms);
+/* random 4-byte gathers over an L2-resident float array of `n_elems`: returns achieved GB/s of
+ * gathered bytes (32 B sectors are NOT counted, only the 4 B used) in *gbps. */
+int sio_bench_gather(sio_ctx* ctx, int64_t n_elems, int64_t n_gathers, int iters, double* gbps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIO_ABI_H */

@@ -1,0 +1,295 @@
+"""ctypes binding of the C-ABI in include/sio_abi.h (libsio_b200.so).
+
+This is the only door from the Python mirror of the reference's API to the device.  There is no
+CPU implementation behind it: if the library is missing, or no sm_100 device is usable,
+`Context()` raises -- the oracle path never silently falls back (SURVEY.md 8b "Errors").
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libsio_b200.so")
+
+SIO_OK = 0
+SIO_ERR_OVERFLOW = -5
+SIO_F32 = 0x0
+SIO_F64 = 0x1
+SIO_NO_NORMALIZE = 0x2
+
+# every symbol include/sio_abi.h declares (tests check the built library exports each of them)
+ABI_SYMBOLS = (
+    "sio_abi_version", "sio_last_error",
+    "sio_ctx_create", "sio_ctx_destroy", "sio_ctx_sync", "sio_ctx_stream", "sio_ctx_set_tau", "sio_ctx_num_sms",
+    "sio_ctx_kernel_launches",
+    "sio_grid_create", "sio_grid_destroy", "sio_cloud_create", "sio_cloud_destroy", "sio_cloud_size",
+    "sio_query", "sio_cloud_query_dev", "sio_cloud_perm",
+    "sio_min_distance", "sio_min_distance_dev", "sio_under_fetch",
+    "sio_pose_rows",
+    "sio_robot_create", "sio_robot_destroy", "sio_fk", "sio_chain_rows", "sio_robot_min_distance",
+    "sio_bench_gather", "sio_ctx_last_bulk_ms",
+)
+
+_lib = None
+
+
+class SioError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "sio error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load_library():
+    """dlopen libsio_b200.so and declare prototypes.  Raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the collision oracle has no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    P, I32, I64, D = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.sio_abi_version.restype = C.c_int
+    L.sio_last_error.restype = C.c_char_p
+    L.sio_ctx_create.argtypes = [C.c_int, C.POINTER(P)]
+    L.sio_ctx_destroy.argtypes = [P]
+    L.sio_ctx_sync.argtypes = [P]
+    L.sio_ctx_stream.argtypes = [P]
+    L.sio_ctx_stream.restype = P
+    L.sio_ctx_set_tau.argtypes = [P, D]
+    L.sio_ctx_num_sms.argtypes = [P]
+    L.sio_ctx_kernel_launches.argtypes = [P]
+    L.sio_ctx_kernel_launches.restype = I64
+    L.sio_grid_create.argtypes = [P, P, P, P, P, C.POINTER(I32)]
+    L.sio_grid_destroy.argtypes = [P, I32]
+    L.sio_cloud_create.argtypes = [P, P, I64, C.POINTER(I32)]
+    L.sio_cloud_destroy.argtypes = [P, I32]
+    L.sio_cloud_size.argtypes = [P, I32]
+    L.sio_cloud_size.restype = I64
+    L.sio_query.argtypes = [P, I32, P, P, I64, C.c_int, P, P]
+    L.sio_cloud_query_dev.argtypes = [P, I32, I32, P, I64, C.c_int, P, P]
+    L.sio_cloud_perm.argtypes = [P, I32, P]
+    L.sio_min_distance.argtypes = [P, P, I32, P, I32, P, P, I64, C.c_int, P, P, P]
+    L.sio_min_distance_dev.argtypes = [P, P, I32, P, I32, P, P, I64, C.c_int, P, P]
+    L.sio_under_fetch.argtypes = [P, I64, P, P, P, C.POINTER(I64)]
+    L.sio_pose_rows.argtypes = [P, I32, P, P, I64, P, C.c_int, P, P]
+    L.sio_robot_create.argtypes = [P, I32, P, P, P, P, C.POINTER(I32)]
+    L.sio_robot_destroy.argtypes = [P, I32]
+    L.sio_fk.argtypes = [P, I32, P, I64, P]
+    L.sio_chain_rows.argtypes = [P, I32, P, P, I64, P, P, P, I64, C.c_int, P, P]
+    L.sio_robot_min_distance.argtypes = [P, I32, P, P, I32, I32, P, P, I64, P, C.c_int, P, P, P]
+    L.sio_bench_gather.argtypes = [P, I64, I64, C.c_int, C.POINTER(D)]
+    L.sio_ctx_last_bulk_ms.argtypes = [P, C.POINTER(D)]
+    _lib = L
+    return L
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One device context (stream + scratch + resident handles).  Calls are serialised on its stream."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.sio_ctx_create(int(device), C.byref(h))
+        if rc != SIO_OK:
+            raise SioError(rc, self.L.sio_last_error().decode())
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sio_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != SIO_OK:
+            raise SioError(rc, self.L.sio_last_error().decode())
+
+    # -- context --
+    def sync(self):
+        self._ck(self.L.sio_ctx_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.L.sio_ctx_stream(self.h)
+
+    def set_tau(self, tau):
+        self._ck(self.L.sio_ctx_set_tau(self.h, float(tau)))
+
+    @property
+    def num_sms(self):
+        return self.L.sio_ctx_num_sms(self.h)
+
+    @property
+    def kernel_launches(self):
+        return int(self.L.sio_ctx_kernel_launches(self.h))
+
+    # -- geometry --
+    def grid_create(self, values, bmin, bmax):
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        if v.ndim != 3:
+            raise ValueError("grid values must be a 3-D array (nx,ny,nz), z fastest")
+        dims = np.array(v.shape, dtype=np.int32)
+        bmin, bmax = _f64(bmin), _f64(bmax)
+        out = C.c_int32(-1)
+        self._ck(self.L.sio_grid_create(self.h, v.ctypes.data, dims.ctypes.data, bmin.ctypes.data, bmax.ctypes.data, C.byref(out)))
+        return out.value
+
+    def grid_destroy(self, g):
+        self._ck(self.L.sio_grid_destroy(self.h, g))
+
+    def cloud_create(self, xyz):
+        p = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        out = C.c_int32(-1)
+        self._ck(self.L.sio_cloud_create(self.h, p.ctypes.data, len(p), C.byref(out)))
+        return out.value
+
+    def cloud_destroy(self, c):
+        self._ck(self.L.sio_cloud_destroy(self.h, c))
+
+    def cloud_size(self, c):
+        return int(self.L.sio_cloud_size(self.h, c))
+
+    def cloud_perm(self, c):
+        out = np.empty(self.cloud_size(c), dtype=np.int32)
+        self._ck(self.L.sio_cloud_perm(self.h, c, out.ctypes.data))
+        return out
+
+    # -- K1 --
+    def query(self, grid, T_grid_from_in, pts, flags=SIO_F64, want_grad=True):
+        T = _f64(T_grid_from_in).reshape(12)
+        p = _f64(pts).reshape(-1, 3)
+        d = np.empty(len(p))
+        g = np.empty((len(p), 3)) if want_grad else None
+        self._ck(self.L.sio_query(self.h, grid, T.ctypes.data, p.ctypes.data, len(p), int(flags), d.ctypes.data, _ptr(g)))
+        return (d, g) if want_grad else d
+
+    def cloud_query_dev(self, grid, cloud, dT_rel_ptr, B, flags, out_d_ptr, out_g4_ptr):
+        self._ck(self.L.sio_cloud_query_dev(self.h, grid, cloud, dT_rel_ptr, int(B), int(flags), out_d_ptr, out_g4_ptr))
+
+    # -- K2 --
+    def min_distance(self, grids, cloud, T_rel, bound=None, grid_of_b=None, flags=SIO_F32, want_under=True):
+        """Returns dmin[B], argmin[B], n_under[B]; the under-bound list comes from under_fetch()."""
+        if np.isscalar(grids):
+            grids = [grids]
+        ga = np.ascontiguousarray(grids, dtype=np.int32)
+        T = _f64(T_rel).reshape(-1, 12)
+        B = len(T)
+        bnd = None if bound is None else _f64(np.broadcast_to(bound, (B,)))
+        gob = None if grid_of_b is None else np.ascontiguousarray(grid_of_b, dtype=np.int32)
+        dmin = np.empty(B)
+        arg = np.empty(B, dtype=np.int64)
+        nu = np.zeros(B, dtype=np.int32) if want_under else None
+        self._ck(self.L.sio_min_distance(self.h, ga.ctypes.data, len(ga), _ptr(gob), cloud, T.ctypes.data, _ptr(bnd), B,
+                                         int(flags), dmin.ctypes.data, arg.ctypes.data, _ptr(nu)))
+        return dmin, arg, nu
+
+    def min_distance_dev(self, grids, cloud, dT_rel_ptr, d_bound_ptr, B, flags, d_dmin_ptr, d_argmin_ptr, d_gob_ptr=None):
+        ga = np.ascontiguousarray(grids, dtype=np.int32)
+        self._ck(self.L.sio_min_distance_dev(self.h, ga.ctypes.data, len(ga), d_gob_ptr, cloud, dT_rel_ptr, d_bound_ptr, int(B),
+                                             int(flags), d_dmin_ptr, d_argmin_ptr))
+
+    def under_fetch(self, capacity=1 << 20):
+        b = np.empty(capacity, dtype=np.int64)
+        i = np.empty(capacity, dtype=np.int64)
+        d = np.empty(capacity)
+        tot = C.c_int64(0)
+        self._ck(self.L.sio_under_fetch(self.h, capacity, b.ctypes.data, i.ctypes.data, d.ctypes.data, C.byref(tot)))
+        n = tot.value
+        return b[:n], i[:n], d[:n]
+
+    # -- K3 --
+    def pose_rows(self, grid, T_pose, offsets, pts, flags=SIO_F64, want_rows=True):
+        T = _f64(T_pose).reshape(-1, 12)
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        p = _f64(pts).reshape(-1, 3)
+        assert len(off) == len(T) + 1 and off[-1] == len(p)
+        d = np.empty(len(p))
+        rows = np.empty((len(p), 6)) if want_rows else None
+        self._ck(self.L.sio_pose_rows(self.h, grid, T.ctypes.data, off.ctypes.data, len(T), p.ctypes.data, int(flags),
+                                      d.ctypes.data, _ptr(rows)))
+        return d, rows
+
+    # -- K4 --
+    def robot_create(self, parent, tparent, axis, jtype=None):
+        par = np.ascontiguousarray(parent, dtype=np.int32)
+        n = len(par)
+        tp = _f64(tparent).reshape(n, 12)
+        ax = _f64(axis).reshape(n, 3)
+        jt = None if jtype is None else np.ascontiguousarray(jtype, dtype=np.int32)
+        out = C.c_int32(-1)
+        self._ck(self.L.sio_robot_create(self.h, n, par.ctypes.data, _ptr(jt), tp.ctypes.data, ax.ctypes.data, C.byref(out)))
+        return out.value
+
+    def robot_destroy(self, r):
+        self._ck(self.L.sio_robot_destroy(self.h, r))
+
+    def fk(self, robot, q, n_links):
+        q = _f64(q).reshape(-1, n_links)
+        out = np.empty((len(q), n_links, 12))
+        self._ck(self.L.sio_fk(self.h, robot, q.ctypes.data, len(q), out.ctypes.data))
+        return out
+
+    def chain_rows(self, robot, n_links, link_grids, q, link_of_pt, pts, cfg_of_pt=None, flags=SIO_F64, want_rows=True):
+        lg = np.ascontiguousarray(link_grids, dtype=np.int32)
+        q = _f64(q).reshape(-1, n_links)
+        p = _f64(pts).reshape(-1, 3)
+        lop = np.ascontiguousarray(np.broadcast_to(link_of_pt, (len(p),)), dtype=np.int32)
+        cop = None if cfg_of_pt is None else np.ascontiguousarray(cfg_of_pt, dtype=np.int32)
+        d = np.empty(len(p))
+        rows = np.empty((len(p), n_links)) if want_rows else None
+        self._ck(self.L.sio_chain_rows(self.h, robot, lg.ctypes.data, q.ctypes.data, len(q), _ptr(cop), lop.ctypes.data,
+                                       p.ctypes.data, len(p), int(flags), d.ctypes.data, _ptr(rows)))
+        return d, rows
+
+    def robot_min_distance(self, robot, n_links, link_grids, links, cloud, T_cloud, q, bound=None, flags=SIO_F32):
+        lg = np.ascontiguousarray(link_grids, dtype=np.int32)
+        ls = np.ascontiguousarray(links, dtype=np.int32)
+        q = _f64(q).reshape(-1, n_links)
+        S, nsel = len(q), len(ls)
+        Tc = _f64(T_cloud).reshape(12)
+        bnd = None if bound is None else _f64(np.broadcast_to(bound, (S, nsel)))
+        dmin = np.empty((S, nsel))
+        arg = np.empty((S, nsel), dtype=np.int64)
+        nu = np.zeros((S, nsel), dtype=np.int32)
+        self._ck(self.L.sio_robot_min_distance(self.h, robot, lg.ctypes.data, ls.ctypes.data, nsel, cloud, Tc.ctypes.data,
+                                               q.ctypes.data, S, _ptr(bnd), int(flags), dmin.ctypes.data, arg.ctypes.data,
+                                               nu.ctypes.data))
+        return dmin, arg, nu
+
+    def last_bulk_ms(self):
+        out = C.c_double(0)
+        self._ck(self.L.sio_ctx_last_bulk_ms(self.h, C.byref(out)))
+        return out.value
+
+    def bench_gather(self, n_elems, n_gathers, iters=10):
+        out = C.c_double(0)
+        self._ck(self.L.sio_bench_gather(self.h, int(n_elems), int(n_gathers), int(iters), C.byref(out)))
+        return out.value
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    """Process-wide context per device (created on first use)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("SIO_DEVICE_FROM_RANK") else 0
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

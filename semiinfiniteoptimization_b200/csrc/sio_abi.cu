@@ -1,0 +1,780 @@
+// sio_abi.cu -- host side of the C-ABI declared in include/sio_abi.h: context, resident handles,
+// scratch arenas and the launch sequences of the oracle calls.  No CPU implementation of any query
+// exists here: without a CUDA device sio_ctx_create fails with SIO_ERR_NODEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sio_abi.h"
+#include "sio_common.cuh"
+
+using namespace sio;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? SIO_ERR_NOMEM : SIO_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                               \
+    } while (0)
+
+// grow-only device / pinned-host buffers
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(bytes, (size_t)256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(bytes, (size_t)256);
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct GridH {
+    bool live = false;
+    float* d_v = nullptr;
+    GridDev meta{};
+    GridDev* d_meta = nullptr;     // single-element device copy (K1 kernels take a pointer)
+};
+struct CloudH {
+    bool live = false;
+    int64_t n = 0;
+    float4* d_pts = nullptr;       // Morton-sorted
+    int32_t* d_perm = nullptr;     // internal -> caller index
+    std::vector<int32_t> perm;
+};
+struct RobotH {
+    bool live = false;
+    int32_t n = 0;
+    int32_t *d_parent = nullptr, *d_jtype = nullptr;
+    double *d_tparent = nullptr, *d_axis = nullptr;
+    RobotDev dev() const { return RobotDev{n, d_parent, d_jtype, d_tparent, d_axis}; }
+};
+
+struct UnderEntry { int64_t b, idx; double d; };
+
+}  // namespace
+
+struct sio_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_bulk0 = nullptr, ev_bulk1 = nullptr;   // bracket the fp32 bulk launches of the last K2 call
+    bool bulk_timed = false;
+    double tau = 0.0;                 // <= 0: automatic
+    int64_t launches = 0;
+    std::vector<GridH> grids;
+    std::vector<CloudH> clouds;
+    std::vector<RobotH> robots;
+    // scratch
+    DevBuf s_xf, s_keys, s_gridtab, s_cand, s_cnt, s_in0, s_in1, s_in2, s_in3, s_out0, s_out1, s_out2, s_tlinks, s_trel, s_gob;
+    HostBuf h_a, h_b, h_c;
+    uint32_t cand_cap = 1u << 20;
+    // state of the last min-distance call (for sio_under_fetch)
+    bool under_valid = false, under_pending = false, under_final = false;
+    std::vector<UnderEntry> under;
+};
+
+namespace {
+
+bool grid_ok(sio_ctx* c, sio_handle h) { return h >= 0 && (size_t)h < c->grids.size() && c->grids[h].live; }
+bool cloud_ok(sio_ctx* c, sio_handle h) { return h >= 0 && (size_t)h < c->clouds.size() && c->clouds[h].live; }
+bool robot_ok(sio_ctx* c, sio_handle h) { return h >= 0 && (size_t)h < c->robots.size() && c->robots[h].live; }
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// the automatic near-tie window: generous multiple of the fp32 evaluation error, which scales with the
+// magnitude of the samples and of the coordinates (DESIGN.md "Exactness")
+double auto_tau(const GridDev* g, int n) {
+    double scale = 1.0;
+    for (int i = 0; i < n; ++i) {
+        double diag = 0;
+        for (int a = 0; a < 3; ++a) diag += (g[i].bmax[a] - g[i].bmin[a]) * (g[i].bmax[a] - g[i].bmin[a]);
+        scale = std::max(scale, std::sqrt(diag) + std::max(std::fabs((double)g[i].vmin), std::fabs((double)g[i].vmax)));
+    }
+    return 1e-5 * scale;
+}
+
+uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) {   // 21 bits per axis
+    auto spread = [](uint64_t v) {
+        v &= 0x1fffffULL;
+        v = (v | v << 32) & 0x1f00000000ffffULL;
+        v = (v | v << 16) & 0x1f0000ff0000ffULL;
+        v = (v | v << 8) & 0x100f00f00f00f00fULL;
+        v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+        v = (v | v << 2) & 0x1249249249249249ULL;
+        return v;
+    };
+    return spread(x) | (spread(y) << 1) | (spread(z) << 2);
+}
+
+}  // namespace
+
+extern "C" {
+
+int sio_abi_version(void) { return SIO_ABI_VERSION; }
+const char* sio_last_error(void) { return g_err.c_str(); }
+
+int sio_ctx_create(int device, sio_ctx** out) {
+    if (!out) return fail(SIO_ERR_INVALID, "sio_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SIO_ERR_NODEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(SIO_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(SIO_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    sio_ctx* c = new sio_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(SIO_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    cudaEventCreate(&c->ev_bulk0);
+    cudaEventCreate(&c->ev_bulk1);
+    *out = c;
+    return SIO_OK;
+}
+
+int sio_ctx_destroy(sio_ctx* c) {
+    if (!c) return SIO_OK;
+    DeviceGuard guard(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& g : c->grids) if (g.live) { cudaFree(g.d_v); cudaFree(g.d_meta); }
+    for (auto& p : c->clouds) if (p.live) { cudaFree(p.d_pts); cudaFree(p.d_perm); }
+    for (auto& r : c->robots) if (r.live) { cudaFree(r.d_parent); cudaFree(r.d_jtype); cudaFree(r.d_tparent); cudaFree(r.d_axis); }
+    DevBuf* bufs[] = {&c->s_xf, &c->s_keys, &c->s_gridtab, &c->s_cand, &c->s_cnt, &c->s_in0, &c->s_in1, &c->s_in2, &c->s_in3,
+                      &c->s_out0, &c->s_out1, &c->s_out2, &c->s_tlinks, &c->s_trel, &c->s_gob};
+    for (auto* b : bufs) b->release();
+    c->h_a.release(); c->h_b.release(); c->h_c.release();
+    cudaEventDestroy(c->ev_bulk0); cudaEventDestroy(c->ev_bulk1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return SIO_OK;
+}
+
+int sio_ctx_sync(sio_ctx* c) {
+    if (!c) return fail(SIO_ERR_INVALID, "null context");
+    DeviceGuard guard(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    return SIO_OK;
+}
+void* sio_ctx_stream(sio_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int sio_ctx_set_tau(sio_ctx* c, double tau) { if (!c) return fail(SIO_ERR_INVALID, "null context"); c->tau = tau; return SIO_OK; }
+int sio_ctx_num_sms(sio_ctx* c) { return c ? c->num_sms : 0; }
+int64_t sio_ctx_kernel_launches(sio_ctx* c) { return c ? c->launches : 0; }
+
+// ---- geometry --------------------------------------------------------------------------------------
+int sio_grid_create(sio_ctx* c, const float* values, const int32_t dims[3], const double bmin[3],
+                    const double bmax[3], sio_handle* out) {
+    if (!c || !values || !dims || !bmin || !bmax || !out) return fail(SIO_ERR_INVALID, "sio_grid_create: null argument");
+    for (int a = 0; a < 3; ++a) {
+        if (dims[a] < 1) return fail(SIO_ERR_INVALID, "sio_grid_create: dims[%d]=%d", a, dims[a]);
+        if (!(bmax[a] > bmin[a])) return fail(SIO_ERR_INVALID, "sio_grid_create: empty bbox on axis %d", a);
+    }
+    if ((int64_t)(dims[0] + 1) * (dims[1] + 1) * (dims[2] + 1) >= (1LL << 31))
+        return fail(SIO_ERR_INVALID, "sio_grid_create: grid too large for 32-bit cell indexing");
+    DeviceGuard guard(c->device);
+    const int nx = dims[0], ny = dims[1], nz = dims[2];
+    const int px = nx + 1, py = ny + 1, pz = nz + 1;
+    // padded copy: the extra far layer in each axis replicates the last sample
+    std::vector<float> pad((size_t)px * py * pz);
+    float vmin = std::numeric_limits<float>::infinity(), vmax = -vmin;
+    for (int i = 0; i < px; ++i) {
+        int si = std::min(i, nx - 1);
+        for (int j = 0; j < py; ++j) {
+            int sj = std::min(j, ny - 1);
+            const float* src = values + ((size_t)si * ny + sj) * nz;
+            float* dst = pad.data() + ((size_t)i * py + j) * pz;
+            std::memcpy(dst, src, sizeof(float) * nz);
+            dst[nz] = src[nz - 1];
+        }
+    }
+    for (size_t k = 0, n = (size_t)nx * ny * nz; k < n; ++k) {
+        float v = values[k];
+        if (!(v == v)) return fail(SIO_ERR_INVALID, "sio_grid_create: NaN sample at flat index %zu", k);
+        vmin = std::min(vmin, v); vmax = std::max(vmax, v);
+    }
+    GridH g;
+    CU(cudaMalloc(&g.d_v, pad.size() * sizeof(float)));
+    CU(cudaMemcpyAsync(g.d_v, pad.data(), pad.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    g.meta.v = g.d_v;
+    g.meta.nx = nx; g.meta.ny = ny; g.meta.nz = nz;
+    g.meta.sy = pz; g.meta.sx = py * pz;
+    for (int a = 0; a < 3; ++a) {
+        g.meta.bmin[a] = bmin[a]; g.meta.bmax[a] = bmax[a];
+        g.meta.h[a] = (bmax[a] - bmin[a]) / (double)dims[a];
+    }
+    g.meta.vmin = vmin; g.meta.vmax = vmax;
+    CU(cudaMalloc(&g.d_meta, sizeof(GridDev)));
+    CU(cudaMemcpyAsync(g.d_meta, &g.meta, sizeof(GridDev), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    g.live = true;
+    c->grids.push_back(g);
+    *out = (sio_handle)(c->grids.size() - 1);
+    return SIO_OK;
+}
+
+int sio_grid_destroy(sio_ctx* c, sio_handle h) {
+    if (!c || !grid_ok(c, h)) return fail(SIO_ERR_INVALID, "sio_grid_destroy: bad handle %d", h);
+    DeviceGuard guard(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->grids[h].d_v); cudaFree(c->grids[h].d_meta);
+    c->grids[h] = GridH();
+    return SIO_OK;
+}
+
+int sio_cloud_create(sio_ctx* c, const float* xyz, int64_t n, sio_handle* out) {
+    if (!c || !out || n < 0 || (n > 0 && !xyz)) return fail(SIO_ERR_INVALID, "sio_cloud_create: bad argument");
+    if (n >= (1LL << 31) - kTile) return fail(SIO_ERR_INVALID, "sio_cloud_create: more than 2^31 points");
+    DeviceGuard guard(c->device);
+    CloudH p;
+    p.n = n;
+    // Morton order (one-off, host): warps of the bulk kernels then touch spatially coherent cells
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) {
+            float v = xyz[3 * i + a];
+            if (!std::isfinite(v)) return fail(SIO_ERR_INVALID, "sio_cloud_create: non-finite coordinate at point %lld", (long long)i);
+            lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v);
+        }
+    std::vector<std::pair<uint64_t, int32_t>> keys((size_t)n);
+    float span = 0.f;
+    for (int a = 0; a < 3; ++a) span = std::max(span, hi[a] - lo[a]);
+    const double sc = span > 0 ? 2097151.0 / span : 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t q[3];
+        for (int a = 0; a < 3; ++a) q[a] = (uint32_t)std::min(2097151.0, std::max(0.0, (xyz[3 * i + a] - lo[a]) * sc));
+        keys[i] = {morton3(q[0], q[1], q[2]), (int32_t)i};
+    }
+    std::sort(keys.begin(), keys.end());
+    const int64_t npad = ((n + kTile - 1) / kTile) * kTile;
+    std::vector<float4> pts((size_t)std::max<int64_t>(npad, 1));
+    p.perm.resize((size_t)std::max<int64_t>(npad, 1), -1);
+    for (int64_t i = 0; i < n; ++i) {
+        int32_t s = keys[i].second;
+        pts[i] = make_float4(xyz[3 * s], xyz[3 * s + 1], xyz[3 * s + 2], 0.f);
+        p.perm[i] = s;
+    }
+    for (int64_t i = n; i < npad; ++i) pts[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    CU(cudaMalloc(&p.d_pts, pts.size() * sizeof(float4)));
+    CU(cudaMalloc(&p.d_perm, p.perm.size() * sizeof(int32_t)));
+    CU(cudaMemcpyAsync(p.d_pts, pts.data(), pts.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(p.d_perm, p.perm.data(), p.perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    p.live = true;
+    c->clouds.push_back(std::move(p));
+    *out = (sio_handle)(c->clouds.size() - 1);
+    return SIO_OK;
+}
+
+int sio_cloud_destroy(sio_ctx* c, sio_handle h) {
+    if (!c || !cloud_ok(c, h)) return fail(SIO_ERR_INVALID, "sio_cloud_destroy: bad handle %d", h);
+    DeviceGuard guard(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->clouds[h].d_pts); cudaFree(c->clouds[h].d_perm);
+    c->clouds[h] = CloudH();
+    return SIO_OK;
+}
+
+int64_t sio_cloud_size(sio_ctx* c, sio_handle h) { return (c && cloud_ok(c, h)) ? c->clouds[h].n : -1; }
+
+int sio_cloud_perm(sio_ctx* c, sio_handle h, int32_t* perm_out) {
+    if (!c || !cloud_ok(c, h) || !perm_out) return fail(SIO_ERR_INVALID, "sio_cloud_perm: bad argument");
+    std::memcpy(perm_out, c->clouds[h].perm.data(), sizeof(int32_t) * (size_t)c->clouds[h].n);
+    return SIO_OK;
+}
+
+// ---- K1 ----------------------------------------------------------------------------------------------
+int sio_query(sio_ctx* c, sio_handle grid, const double T[12], const double* pts, int64_t P, int flags,
+              double* d, double* grad) {
+    if (!c || !grid_ok(c, grid) || !T || P < 0 || (P > 0 && (!pts || !d)))
+        return fail(SIO_ERR_INVALID, "sio_query: bad argument");
+    if (P == 0) return SIO_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    CU(c->s_in0.ensure(12 * sizeof(double)));
+    CU(c->s_in1.ensure((size_t)P * 3 * sizeof(double)));
+    CU(c->s_out0.ensure((size_t)P * sizeof(double)));
+    CU(c->s_out1.ensure((size_t)P * 3 * sizeof(double)));
+    CU(cudaMemcpyAsync(c->s_in0.p, T, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->s_in1.p, pts, (size_t)P * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int normalize = (flags & SIO_NO_NORMALIZE) ? 0 : 1;
+    double* dg = grad ? c->s_out1.as<double>() : nullptr;
+    if (flags & SIO_F64)
+        launch_query_f64(c->grids[grid].d_meta, c->s_in0.as<double>(), c->s_in1.as<double>(), P, normalize, c->s_out0.as<double>(), dg, st);
+    else
+        launch_query_f32(c->grids[grid].d_meta, c->s_in0.as<double>(), c->s_in1.as<double>(), P, normalize, c->s_out0.as<double>(), dg, st);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(d, c->s_out0.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (grad) CU(cudaMemcpyAsync(grad, c->s_out1.p, (size_t)P * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SIO_OK;
+}
+
+// builds the device grid table for a call; returns the automatic tau through *tau
+static int stage_grid_table(sio_ctx* c, const sio_handle* grids, int32_t n_grids, double* tau) {
+    if (n_grids <= 0 || !grids) return fail(SIO_ERR_INVALID, "no grids given");
+    std::vector<GridDev> tab((size_t)n_grids);
+    for (int i = 0; i < n_grids; ++i) {
+        if (!grid_ok(c, grids[i])) return fail(SIO_ERR_INVALID, "bad grid handle %d at position %d", grids[i], i);
+        tab[i] = c->grids[grids[i]].meta;
+    }
+    CU(c->s_gridtab.ensure(tab.size() * sizeof(GridDev)));
+    // pageable -> device copy of a stack/vector object: synchronous w.r.t. the host, so `tab` may die
+    CU(cudaMemcpyAsync(c->s_gridtab.p, tab.data(), tab.size() * sizeof(GridDev), cudaMemcpyHostToDevice, c->stream));
+    *tau = c->tau > 0 ? c->tau : auto_tau(tab.data(), n_grids);
+    return SIO_OK;
+}
+
+int sio_cloud_query_dev(sio_ctx* c, sio_handle grid, sio_handle cloud, const double* dT_rel, int64_t B, int flags,
+                        float* out_d, float* out_g4) {
+    if (!c || !grid_ok(c, grid) || !cloud_ok(c, cloud) || B < 0 || (B > 0 && !dT_rel) || (!out_d && !out_g4))
+        return fail(SIO_ERR_INVALID, "sio_cloud_query_dev: bad argument");
+    if (flags & SIO_F64) return fail(SIO_ERR_INVALID, "sio_cloud_query_dev: SIO_F32 only");
+    if (B == 0) return SIO_OK;
+    DeviceGuard guard(c->device);
+    double tau;
+    int rc = stage_grid_table(c, &grid, 1, &tau);
+    if (rc) return rc;
+    CU(c->s_xf.ensure((size_t)B * sizeof(XfRec)));
+    MinArgs a{};
+    a.grids = c->s_gridtab.as<GridDev>(); a.grid_of_b = nullptr; a.T_rel = dT_rel; a.bound = nullptr;
+    a.B = B; a.tau = tau; a.xf = c->s_xf.as<XfRec>();
+    launch_prep_xf(a, c->stream);
+    const CloudH& p = c->clouds[cloud];
+    launch_cloud_query_f32(p.d_pts, p.n, a.xf, B, (flags & SIO_NO_NORMALIZE) ? 0 : 1, out_g4 ? nullptr : out_d,
+                           reinterpret_cast<float4*>(out_g4), c->stream);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return SIO_OK;
+}
+
+// ---- K2 ----------------------------------------------------------------------------------------------
+int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, const int32_t* d_grid_of_b,
+                         sio_handle cloud, const double* dT_rel, const double* d_bound, int64_t B, int flags,
+                         double* d_dmin, int64_t* d_argmin) {
+    if (!c || !cloud_ok(c, cloud) || B < 0 || (B > 0 && (!dT_rel || !d_dmin || !d_argmin)))
+        return fail(SIO_ERR_INVALID, "sio_min_distance_dev: bad argument");
+    if (B >= (1LL << 31)) return fail(SIO_ERR_INVALID, "sio_min_distance_dev: B too large");
+    DeviceGuard guard(c->device);
+    c->under.clear(); c->under_valid = false; c->under_pending = false;
+    if (B == 0) { c->under_valid = true; return SIO_OK; }
+    double tau;
+    int rc = stage_grid_table(c, grids, n_grids, &tau);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    const CloudH& p = c->clouds[cloud];
+    const bool f64 = (flags & SIO_F64) != 0;
+    const int32_t ntiles = (int32_t)((p.n + kTile - 1) / kTile);
+    const int64_t nsub = (int64_t)ntiles * (kThreads / 32);
+    // bound the sub-tile key scratch to ~256 MB by sweeping the transforms in batches
+    int64_t Bc = B;
+    if (!f64 && nsub > 0) {
+        int64_t maxb = (int64_t)(256u << 20) / (nsub * 4);
+        maxb = std::max<int64_t>(kXfChunk, (maxb / kXfChunk) * kXfChunk);
+        Bc = std::min(B, maxb);
+    }
+    CU(c->s_cnt.ensure(sizeof(uint32_t)));
+    CU(c->s_cand.ensure((size_t)c->cand_cap * sizeof(Cand)));
+    CU(cudaMemsetAsync(c->s_cnt.p, 0, sizeof(uint32_t), st));
+    MinArgs a{};
+    a.pts = p.d_pts; a.perm = p.d_perm; a.N = p.n;
+    a.grids = c->s_gridtab.as<GridDev>(); a.grid_of_b = d_grid_of_b;
+    a.T_rel = dT_rel; a.bound = d_bound; a.B = B; a.tau = tau; a.ntiles = ntiles;
+    a.cand = c->s_cand.as<Cand>(); a.cand_count = c->s_cnt.as<uint32_t>(); a.cand_cap = c->cand_cap;
+    a.dmin = d_dmin; a.argmin = d_argmin;
+    if (!f64) {
+        CU(c->s_xf.ensure((size_t)B * sizeof(XfRec)));
+        CU(c->s_keys.ensure((size_t)std::max<int64_t>(1, Bc * nsub) * sizeof(uint32_t)));
+        a.xf = c->s_xf.as<XfRec>(); a.subkeys = c->s_keys.as<uint32_t>();
+        launch_prep_xf(a, st);
+        c->launches += 1;
+    }
+    c->bulk_timed = false;
+    const bool one_batch = Bc >= B;
+    for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+        a.b_begin = b0; a.Bc = std::min(Bc, B - b0);
+        if (!f64) {
+            if (one_batch) cudaEventRecord(c->ev_bulk0, st);
+            launch_min_f32(a, st);
+            if (one_batch) { cudaEventRecord(c->ev_bulk1, st); c->bulk_timed = true; }
+            c->launches += (p.n > 0);
+        }
+        launch_finalize(a, /*all_tiles=*/f64, /*emit_under=*/f64, st);
+        c->launches += 1;
+    }
+    if (!f64 && d_bound) { launch_recheck(a, st); c->launches += 1; }
+    CU(cudaGetLastError());
+    c->under_pending = d_bound != nullptr;
+    c->under_final = f64;
+    c->under_valid = !c->under_pending;
+    return SIO_OK;
+}
+
+// pulls the candidate records of the last call, filters and sorts them into ctx->under
+static int collect_under(sio_ctx* c) {
+    if (c->under_valid) return SIO_OK;
+    cudaStream_t st = c->stream;
+    CU(c->h_c.ensure(sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(c->h_c.p, c->s_cnt.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    uint32_t n = *c->h_c.as<uint32_t>();
+    if (n > c->cand_cap)
+        return fail(SIO_ERR_OVERFLOW, "under-bound candidate buffer overflow: %u candidates, capacity %u", n, c->cand_cap);
+    c->under.clear();
+    if (n > 0) {
+        std::vector<Cand> recs(n);
+        CU(cudaMemcpy(recs.data(), c->s_cand.p, (size_t)n * sizeof(Cand), cudaMemcpyDeviceToHost));
+        c->under.reserve(n);
+        for (const Cand& r : recs) if (r.b >= 0) c->under.push_back({r.b, r.idx, r.d});
+        std::sort(c->under.begin(), c->under.end(), [](const UnderEntry& x, const UnderEntry& y) {
+            return x.b != y.b ? x.b < y.b : x.idx < y.idx;
+        });
+    }
+    c->under_valid = true; c->under_pending = false;
+    return SIO_OK;
+}
+
+int sio_under_fetch(sio_ctx* c, int64_t capacity, int64_t* b_out, int64_t* idx_out, double* d_out, int64_t* total) {
+    if (!c || !total) return fail(SIO_ERR_INVALID, "sio_under_fetch: bad argument");
+    DeviceGuard guard(c->device);
+    int rc = collect_under(c);
+    if (rc) return rc;
+    *total = (int64_t)c->under.size();
+    int64_t m = std::min<int64_t>(capacity, *total);
+    for (int64_t i = 0; i < m; ++i) {
+        if (b_out) b_out[i] = c->under[i].b;
+        if (idx_out) idx_out[i] = c->under[i].idx;
+        if (d_out) d_out[i] = c->under[i].d;
+    }
+    return (*total > capacity && capacity > 0) ? fail(SIO_ERR_OVERFLOW, "under list has %lld entries, capacity %lld", (long long)*total, (long long)capacity) : SIO_OK;
+}
+
+int sio_min_distance(sio_ctx* c, const sio_handle* grids, int32_t n_grids, const int32_t* grid_of_b, sio_handle cloud,
+                     const double* T_rel, const double* bound, int64_t B, int flags, double* dmin, int64_t* argmin,
+                     int32_t* n_under) {
+    if (!c || B < 0 || (B > 0 && (!T_rel || !dmin || !argmin))) return fail(SIO_ERR_INVALID, "sio_min_distance: bad argument");
+    DeviceGuard guard(c->device);
+    if (B == 0) { c->under.clear(); c->under_valid = true; return SIO_OK; }
+    cudaStream_t st = c->stream;
+    CU(c->s_in0.ensure((size_t)B * 12 * sizeof(double)));
+    CU(c->s_out0.ensure((size_t)B * sizeof(double)));
+    CU(c->s_out1.ensure((size_t)B * sizeof(int64_t)));
+    CU(cudaMemcpyAsync(c->s_in0.p, T_rel, (size_t)B * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+    const double* d_bound = nullptr;
+    if (bound) {
+        CU(c->s_in1.ensure((size_t)B * sizeof(double)));
+        CU(cudaMemcpyAsync(c->s_in1.p, bound, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st));
+        d_bound = c->s_in1.as<double>();
+    }
+    const int32_t* d_gob = nullptr;
+    if (grid_of_b) {
+        for (int64_t b = 0; b < B; ++b)
+            if (grid_of_b[b] < 0 || grid_of_b[b] >= n_grids) return fail(SIO_ERR_INVALID, "grid_of_b[%lld]=%d out of range", (long long)b, grid_of_b[b]);
+        CU(c->s_in2.ensure((size_t)B * sizeof(int32_t)));
+        CU(cudaMemcpyAsync(c->s_in2.p, grid_of_b, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        d_gob = c->s_in2.as<int32_t>();
+    }
+    int rc = sio_min_distance_dev(c, grids, n_grids, d_gob, cloud, c->s_in0.as<double>(), d_bound, B, flags,
+                                  c->s_out0.as<double>(), c->s_out1.as<int64_t>());
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dmin, c->s_out0.p, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(argmin, c->s_out1.p, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_under) {
+        std::memset(n_under, 0, sizeof(int32_t) * (size_t)B);
+        if (bound) {
+            rc = collect_under(c);
+            if (rc) return rc;
+            for (const auto& u : c->under) n_under[u.b] += 1;
+        }
+    }
+    return SIO_OK;
+}
+
+// ---- K3 ----------------------------------------------------------------------------------------------
+int sio_pose_rows(sio_ctx* c, sio_handle grid, const double* T_pose, const int64_t* offsets, int64_t nprob,
+                  const double* pts, int flags, double* d, double* rows) {
+    if (!c || !grid_ok(c, grid) || nprob < 0 || (nprob > 0 && (!T_pose || !offsets)))
+        return fail(SIO_ERR_INVALID, "sio_pose_rows: bad argument");
+    if (nprob == 0) return SIO_OK;
+    const int64_t total = offsets[nprob];
+    if (offsets[0] != 0 || total < 0) return fail(SIO_ERR_INVALID, "sio_pose_rows: offsets must start at 0 and be non-decreasing");
+    for (int64_t p = 0; p < nprob; ++p)
+        if (offsets[p + 1] < offsets[p]) return fail(SIO_ERR_INVALID, "sio_pose_rows: offsets decrease at %lld", (long long)p);
+    if (total == 0) return SIO_OK;
+    if (!pts || !d) return fail(SIO_ERR_INVALID, "sio_pose_rows: null pts/d");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    CU(c->s_in0.ensure((size_t)nprob * 12 * sizeof(double)));
+    CU(c->s_in1.ensure((size_t)total * 3 * sizeof(double)));
+    CU(c->s_in2.ensure((size_t)(nprob + 1) * sizeof(int64_t)));
+    CU(c->s_out0.ensure((size_t)total * sizeof(double)));
+    CU(c->s_out1.ensure((size_t)total * 6 * sizeof(double)));
+    CU(cudaMemcpyAsync(c->s_in0.p, T_pose, (size_t)nprob * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->s_in1.p, pts, (size_t)total * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->s_in2.p, offsets, (size_t)(nprob + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    launch_pose_rows(c->grids[grid].d_meta, c->s_in0.as<double>(), c->s_in2.as<int64_t>(), nprob, c->s_in1.as<double>(), total,
+                     (flags & SIO_NO_NORMALIZE) ? 0 : 1, c->s_out0.as<double>(), rows ? c->s_out1.as<double>() : nullptr, st);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(d, c->s_out0.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (rows) CU(cudaMemcpyAsync(rows, c->s_out1.p, (size_t)total * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SIO_OK;
+}
+
+// ---- K4 ----------------------------------------------------------------------------------------------
+int sio_robot_create(sio_ctx* c, int32_t n, const int32_t* parent, const int32_t* jtype, const double* tparent,
+                     const double* axis, sio_handle* out) {
+    if (!c || n <= 0 || !parent || !tparent || !axis || !out) return fail(SIO_ERR_INVALID, "sio_robot_create: bad argument");
+    for (int i = 0; i < n; ++i)
+        if (parent[i] >= i) return fail(SIO_ERR_INVALID, "sio_robot_create: parent[%d]=%d must precede its child", i, parent[i]);
+    DeviceGuard guard(c->device);
+    RobotH r;
+    r.n = n;
+    std::vector<int32_t> jt(n, 0);
+    if (jtype) jt.assign(jtype, jtype + n);
+    CU(cudaMalloc(&r.d_parent, n * sizeof(int32_t)));
+    CU(cudaMalloc(&r.d_jtype, n * sizeof(int32_t)));
+    CU(cudaMalloc(&r.d_tparent, (size_t)n * 12 * sizeof(double)));
+    CU(cudaMalloc(&r.d_axis, (size_t)n * 3 * sizeof(double)));
+    CU(cudaMemcpy(r.d_parent, parent, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(r.d_jtype, jt.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(r.d_tparent, tparent, (size_t)n * 12 * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(r.d_axis, axis, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    r.live = true;
+    c->robots.push_back(r);
+    *out = (sio_handle)(c->robots.size() - 1);
+    return SIO_OK;
+}
+
+int sio_robot_destroy(sio_ctx* c, sio_handle h) {
+    if (!c || !robot_ok(c, h)) return fail(SIO_ERR_INVALID, "sio_robot_destroy: bad handle %d", h);
+    DeviceGuard guard(c->device);
+    cudaStreamSynchronize(c->stream);
+    RobotH& r = c->robots[h];
+    cudaFree(r.d_parent); cudaFree(r.d_jtype); cudaFree(r.d_tparent); cudaFree(r.d_axis);
+    r = RobotH();
+    return SIO_OK;
+}
+
+int sio_fk(sio_ctx* c, sio_handle robot, const double* q, int64_t B, double* T_out) {
+    if (!c || !robot_ok(c, robot) || B < 0 || (B > 0 && (!q || !T_out))) return fail(SIO_ERR_INVALID, "sio_fk: bad argument");
+    if (B == 0) return SIO_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    const RobotH& r = c->robots[robot];
+    CU(c->s_in0.ensure((size_t)B * r.n * sizeof(double)));
+    CU(c->s_tlinks.ensure((size_t)B * r.n * 12 * sizeof(double)));
+    CU(cudaMemcpyAsync(c->s_in0.p, q, (size_t)B * r.n * sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_fk(r.dev(), c->s_in0.as<double>(), B, c->s_tlinks.as<double>(), st);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(T_out, c->s_tlinks.p, (size_t)B * r.n * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SIO_OK;
+}
+
+int sio_chain_rows(sio_ctx* c, sio_handle robot, const sio_handle* link_grids, const double* q, int64_t n_cfg,
+                   const int32_t* cfg_of_pt, const int32_t* link_of_pt, const double* pts, int64_t P, int flags,
+                   double* d, double* rows) {
+    if (!c || !robot_ok(c, robot) || !link_grids || n_cfg <= 0 || !q || P < 0 || (P > 0 && (!link_of_pt || !pts || !d)))
+        return fail(SIO_ERR_INVALID, "sio_chain_rows: bad argument");
+    if (P == 0) return SIO_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    const RobotH& r = c->robots[robot];
+    // grid table over the links that have one; link_grid[l] = slot or -1
+    std::vector<GridDev> tab;
+    std::vector<int32_t> slot(r.n, -1);
+    for (int l = 0; l < r.n; ++l)
+        if (link_grids[l] >= 0) {
+            if (!grid_ok(c, link_grids[l])) return fail(SIO_ERR_INVALID, "sio_chain_rows: bad grid handle for link %d", l);
+            slot[l] = (int32_t)tab.size();
+            tab.push_back(c->grids[link_grids[l]].meta);
+        }
+    for (int64_t i = 0; i < P; ++i) {
+        int l = link_of_pt[i];
+        if (l < 0 || l >= r.n || slot[l] < 0) return fail(SIO_ERR_INVALID, "sio_chain_rows: point %lld on link %d which has no grid", (long long)i, l);
+        if (cfg_of_pt && (cfg_of_pt[i] < 0 || cfg_of_pt[i] >= n_cfg)) return fail(SIO_ERR_INVALID, "sio_chain_rows: cfg_of_pt[%lld] out of range", (long long)i);
+    }
+    CU(c->s_gridtab.ensure(tab.size() * sizeof(GridDev)));
+    CU(cudaMemcpyAsync(c->s_gridtab.p, tab.data(), tab.size() * sizeof(GridDev), cudaMemcpyHostToDevice, st));
+    CU(c->s_gob.ensure((size_t)r.n * sizeof(int32_t)));
+    CU(cudaMemcpyAsync(c->s_gob.p, slot.data(), (size_t)r.n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(c->s_in0.ensure((size_t)n_cfg * r.n * sizeof(double)));
+    CU(cudaMemcpyAsync(c->s_in0.p, q, (size_t)n_cfg * r.n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(c->s_tlinks.ensure((size_t)n_cfg * r.n * 12 * sizeof(double)));
+    launch_fk(r.dev(), c->s_in0.as<double>(), n_cfg, c->s_tlinks.as<double>(), st);
+    CU(c->s_in1.ensure((size_t)P * 3 * sizeof(double)));
+    CU(cudaMemcpyAsync(c->s_in1.p, pts, (size_t)P * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(c->s_in2.ensure((size_t)P * sizeof(int32_t)));
+    CU(cudaMemcpyAsync(c->s_in2.p, link_of_pt, (size_t)P * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    const int32_t* d_cfg = nullptr;
+    if (cfg_of_pt) {
+        CU(c->s_in3.ensure((size_t)P * sizeof(int32_t)));
+        CU(cudaMemcpyAsync(c->s_in3.p, cfg_of_pt, (size_t)P * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        d_cfg = c->s_in3.as<int32_t>();
+    }
+    CU(c->s_out0.ensure((size_t)P * sizeof(double)));
+    CU(c->s_out1.ensure((size_t)P * r.n * sizeof(double)));
+    launch_chain_rows(r.dev(), c->s_gridtab.as<GridDev>(), c->s_gob.as<int32_t>(), c->s_tlinks.as<double>(), d_cfg,
+                      c->s_in2.as<int32_t>(), c->s_in1.as<double>(), P, (flags & SIO_NO_NORMALIZE) ? 0 : 1,
+                      c->s_out0.as<double>(), rows ? c->s_out1.as<double>() : nullptr, st);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(d, c->s_out0.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (rows) CU(cudaMemcpyAsync(rows, c->s_out1.p, (size_t)P * r.n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SIO_OK;
+}
+
+int sio_robot_min_distance(sio_ctx* c, sio_handle robot, const sio_handle* link_grids, const int32_t* links, int32_t n_sel,
+                           sio_handle cloud, const double T_cloud[12], const double* q, int64_t S, const double* bound,
+                           int flags, double* dmin, int64_t* argmin, int32_t* n_under) {
+    if (!c || !robot_ok(c, robot) || !link_grids || !links || n_sel <= 0 || !cloud_ok(c, cloud) || !T_cloud || S < 0 ||
+        (S > 0 && (!q || !dmin || !argmin)))
+        return fail(SIO_ERR_INVALID, "sio_robot_min_distance: bad argument");
+    if (S == 0) { c->under.clear(); c->under_valid = true; return SIO_OK; }
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    const RobotH& r = c->robots[robot];
+    std::vector<sio_handle> sel((size_t)n_sel);
+    for (int l = 0; l < n_sel; ++l) {
+        if (links[l] < 0 || links[l] >= r.n) return fail(SIO_ERR_INVALID, "sio_robot_min_distance: link %d out of range", links[l]);
+        sel[l] = link_grids[links[l]];
+        if (!grid_ok(c, sel[l])) return fail(SIO_ERR_INVALID, "sio_robot_min_distance: link %d has no grid", links[l]);
+    }
+    const int64_t B = S * n_sel;
+    CU(c->s_in0.ensure((size_t)S * r.n * sizeof(double)));
+    CU(cudaMemcpyAsync(c->s_in0.p, q, (size_t)S * r.n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(c->s_tlinks.ensure((size_t)S * r.n * 12 * sizeof(double)));
+    launch_fk(r.dev(), c->s_in0.as<double>(), S, c->s_tlinks.as<double>(), st);
+    CU(c->s_in2.ensure((size_t)n_sel * sizeof(int32_t) + 12 * sizeof(double) + 16));
+    // [links | pad | T_cloud] in one staging buffer
+    int32_t* d_links = c->s_in2.as<int32_t>();
+    double* d_Tc = reinterpret_cast<double*>(reinterpret_cast<char*>(c->s_in2.p) + (((size_t)n_sel * sizeof(int32_t) + 15) / 16) * 16);
+    CU(cudaMemcpyAsync(d_links, links, (size_t)n_sel * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_Tc, T_cloud, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(c->s_trel.ensure((size_t)B * 12 * sizeof(double)));
+    CU(c->s_gob.ensure((size_t)B * sizeof(int32_t)));
+    launch_link_rel(c->s_tlinks.as<double>(), r.n, d_links, n_sel, S, d_Tc, c->s_trel.as<double>(), c->s_gob.as<int32_t>(), st);
+    c->launches += 2;
+    const double* d_bound = nullptr;
+    if (bound) {
+        CU(c->s_in1.ensure((size_t)B * sizeof(double)));
+        CU(cudaMemcpyAsync(c->s_in1.p, bound, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st));
+        d_bound = c->s_in1.as<double>();
+    }
+    CU(c->s_out0.ensure((size_t)B * sizeof(double)));
+    CU(c->s_out1.ensure((size_t)B * sizeof(int64_t)));
+    int rc = sio_min_distance_dev(c, sel.data(), n_sel, c->s_gob.as<int32_t>(), cloud, c->s_trel.as<double>(), d_bound, B, flags,
+                                  c->s_out0.as<double>(), c->s_out1.as<int64_t>());
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dmin, c->s_out0.p, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(argmin, c->s_out1.p, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_under) {
+        std::memset(n_under, 0, sizeof(int32_t) * (size_t)B);
+        if (bound) {
+            rc = collect_under(c);
+            if (rc) return rc;
+            for (const auto& u : c->under) n_under[u.b] += 1;
+        }
+    }
+    return SIO_OK;
+}
+
+// ---- measurement helpers --------------------------------------------------------------------------------
+int sio_ctx_last_bulk_ms(sio_ctx* c, double* ms) {
+    if (!c || !ms) return fail(SIO_ERR_INVALID, "sio_ctx_last_bulk_ms: bad argument");
+    if (!c->bulk_timed) return fail(SIO_ERR_INVALID, "sio_ctx_last_bulk_ms: the last call had no single-batch fp32 bulk launch");
+    DeviceGuard guard(c->device);
+    CU(cudaEventSynchronize(c->ev_bulk1));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, c->ev_bulk0, c->ev_bulk1));
+    *ms = (double)f;
+    return SIO_OK;
+}
+
+int sio_bench_gather(sio_ctx* c, int64_t n_elems, int64_t n_gathers, int iters, double* gbps) {
+    if (!c || n_elems <= 0 || n_gathers <= 0 || iters <= 0 || !gbps) return fail(SIO_ERR_INVALID, "sio_bench_gather: bad argument");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    float* arr = nullptr; uint32_t* idx = nullptr; float* sink = nullptr;
+    CU(cudaMalloc(&arr, (size_t)n_elems * sizeof(float)));
+    CU(cudaMalloc(&idx, (size_t)n_gathers * sizeof(uint32_t)));
+    CU(cudaMalloc(&sink, sizeof(float)));
+    CU(cudaMemsetAsync(arr, 0, (size_t)n_elems * sizeof(float), st));
+    std::vector<uint32_t> h((size_t)n_gathers);
+    uint64_t s = 0x9E3779B97F4A7C15ULL;
+    for (auto& v : h) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; v = (uint32_t)(s % (uint64_t)n_elems); }
+    CU(cudaMemcpy(idx, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    for (int w = 0; w < 3; ++w) launch_gather_bench(arr, n_elems, idx, n_gathers, sink, st);
+    CU(cudaEventRecord(e0, st));
+    for (int it = 0; it < iters; ++it) launch_gather_bench(arr, n_elems, idx, n_gathers, sink, st);
+    CU(cudaEventRecord(e1, st));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    c->launches += iters + 3;
+    *gbps = (double)n_gathers * 4.0 * iters / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(arr); cudaFree(idx); cudaFree(sink);
+    return SIO_OK;
+}
+
+}  // extern "C"

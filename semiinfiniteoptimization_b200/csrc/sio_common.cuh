@@ -1,0 +1,108 @@
+// sio_common.cuh -- device-side records shared by the fp32 bulk kernels (sio_kernels.cu), the
+// fp64 kernels (sio_fp64.cu) and the C-ABI host code (sio_abi.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sio {
+
+constexpr int kThreads = 256;        // CTA size of the bulk kernels
+constexpr int kPtsPerThread = 4;     // points held in registers per thread
+constexpr int kTile = kThreads * kPtsPerThread;   // points per tile (1024)
+constexpr int kXfChunk = 32;         // transforms processed per CTA of the min kernel
+
+// One resident SDF grid.  `v` is a PADDED copy: (nx+1)*(ny+1)*(nz+1) samples whose last layer in
+// every axis replicates the one before it, so corner i0+1 is always addressable and equals the
+// clamped corner of Appendix A.2 step 3.
+struct GridDev {
+    const float* v;
+    int32_t nx, ny, nz;
+    int32_t sx, sy;              // element strides of the padded copy: sy = nz+1, sx = (ny+1)*(nz+1)
+    double bmin[3], bmax[3], h[3];
+    float vmin, vmax;            // range of the samples
+};
+
+// fp32 transform record of one query b: cloud-local point -> dual-lattice cell coordinates
+// u = M p + t  (grid affine (p - bmin)/h - 1/2 folded in), plus what the inner loop needs.
+struct __align__(16) XfRec {
+    float m[12];                 // rows of [M | t]
+    float hx, hy, hz;            // cell size (bbox-overshoot distance is measured in metres)
+    float thr;                   // candidate threshold: bound + tau (+inf: no under-bound list)
+    float hix, hiy, hiz;         // dim-1 (upper clamp of the interpolation coordinate)
+    int32_t sx;                  // padded strides
+    const float* v;              // grid samples
+    int32_t sy;
+    int32_t pad;
+};
+static_assert(sizeof(XfRec) == 96, "XfRec layout");
+
+// candidate / under-bound record.  The fp32 pass writes (b, internal index, float d); the fp64
+// re-check rewrites it in place to (b or -1, caller index, exact d).
+struct __align__(16) Cand {
+    int32_t b;
+    int32_t idx;
+    double d;
+};
+
+// order-preserving map float -> uint32 (min on the key == min on the float, -0 < +0)
+__host__ __device__ inline uint32_t fkey(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float fkey_inv(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+
+// ---- launchers implemented in the .cu files (all enqueue on `st`, none synchronises) --------
+struct MinArgs {
+    const float4* pts; const int32_t* perm; int64_t N;
+    const GridDev* grids; const int32_t* grid_of_b;   // device
+    const double* T_rel; const double* bound;          // device; bound may be null
+    int64_t B;                                          // total transforms (xf, T_rel, bound, outputs are [B])
+    int64_t b_begin, Bc;                                // the batch [b_begin, b_begin+Bc) this launch covers
+    double tau;
+    uint32_t* subkeys; int32_t ntiles;                  // scratch [Bc * ntiles*8]: one key per 128-point sub-tile
+    XfRec* xf;                                          // scratch [B]
+    Cand* cand; uint32_t* cand_count; uint32_t cand_cap;
+    double* dmin; int64_t* argmin;                      // device outputs
+    int normalize;
+};
+void launch_prep_xf(const MinArgs& a, cudaStream_t st);
+void launch_min_f32(const MinArgs& a, cudaStream_t st);
+void launch_finalize(const MinArgs& a, bool all_tiles, bool emit_under, cudaStream_t st);
+void launch_recheck(const MinArgs& a, cudaStream_t st);
+
+void launch_cloud_query_f32(const float4* pts, int64_t N, const XfRec* xf, int64_t B, int normalize,
+                            float* out_d, float4* out_g, cudaStream_t st);
+void launch_query_f64(const GridDev* grid, const double* T /*12, device*/, const double* pts, int64_t P,
+                      int normalize, double* d, double* grad, cudaStream_t st);
+void launch_query_f32(const GridDev* grid, const double* T, const double* pts, int64_t P,
+                      int normalize, double* d, double* grad, cudaStream_t st);
+void launch_pose_rows(const GridDev* grid, const double* T_pose, const int64_t* offsets, int64_t nprob,
+                      const double* pts, int64_t total, int normalize, double* d, double* rows, cudaStream_t st);
+
+struct RobotDev {
+    int32_t n;
+    const int32_t* parent; const int32_t* jtype;
+    const double* tparent; const double* axis;
+};
+void launch_fk(RobotDev r, const double* q, int64_t B, double* T_out, cudaStream_t st);
+// T_rel[(s*n_sel + l)] = T_link(s, links[l])^-1 * T_cloud ; grid_of_b[(s*n_sel+l)] = l
+void launch_link_rel(const double* T_links, int32_t n_links, const int32_t* links, int32_t n_sel, int64_t S,
+                     const double* T_cloud, double* T_rel, int32_t* grid_of_b, cudaStream_t st);
+void launch_chain_rows(RobotDev r, const GridDev* grids, const int32_t* link_grid, const double* T_links,
+                       const int32_t* cfg_of_pt, const int32_t* link_of_pt, const double* pts, int64_t P,
+                       int normalize, double* d, double* rows, cudaStream_t st);
+void launch_gather_bench(const float* arr, int64_t n_elems, const uint32_t* idx, int64_t n_gathers,
+                         float* sink, cudaStream_t st);
+
+}  // namespace sio

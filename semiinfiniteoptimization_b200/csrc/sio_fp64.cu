@@ -1,0 +1,411 @@
+// sio_fp64.cu -- float64 kernels of the collision oracle (sm_100a), compiled with --fmad=false so
+// the arithmetic is the plain IEEE sequence of SURVEY.md Appendix A.2 (no contraction).
+//
+//   k_finalize   exact (d, index) minimum per transform from the fp32 pass's sub-tile keys
+//   k_recheck    exact re-evaluation of the fp32 pass's under-bound candidates
+//   k_query_f64  K1 in float64 (PenetrationDepthGeometry.distance / normal, gopt:104-108, 153)
+//   k_pose_rows  K3 pose rows  [ (R(pt-t)) x n , n ]            (gopt:413-418)
+//   k_fk / k_link_rel / k_chain_rows  K4 kinematics + link rows   (gopt:201-204, 479-482)
+#include "sio_common.cuh"
+
+namespace sio {
+
+// Appendix A.2 in float64.  p = grid-local point.  gl (optional) = gradient w.r.t. p.
+__device__ __forceinline__ double eval64(const GridDev& g, const double p[3], double* gl) {
+    const int dim[3] = {g.nx, g.ny, g.nz};
+    double o[3], f[3], u[3];
+    int i0[3];
+    double dout2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double c = fmin(fmax(p[a], g.bmin[a]), g.bmax[a]);
+        o[a] = p[a] - c;
+        dout2 += o[a] * o[a];
+        double h = (g.bmax[a] - g.bmin[a]) / (double)dim[a];
+        u[a] = (c - g.bmin[a]) / h - 0.5;
+        double uc = fmin(fmax(u[a], 0.0), (double)(dim[a] - 1));
+        double fl = floor(uc);
+        i0[a] = (int)fl;
+        f[a] = uc - fl;
+    }
+    const float* b0 = g.v + ((size_t)i0[0] * g.sx + (size_t)i0[1] * g.sy + i0[2]);
+    const float* b1 = b0 + g.sy;
+    const float* b2 = b0 + g.sx;
+    const float* b3 = b2 + g.sy;
+    double v000 = __ldg(b0), v001 = __ldg(b0 + 1), v010 = __ldg(b1), v011 = __ldg(b1 + 1);
+    double v100 = __ldg(b2), v101 = __ldg(b2 + 1), v110 = __ldg(b3), v111 = __ldg(b3 + 1);
+    double dz00 = v001 - v000, dz01 = v011 - v010, dz10 = v101 - v100, dz11 = v111 - v110;
+    double a00 = v000 + f[2] * dz00, a01 = v010 + f[2] * dz01;
+    double a10 = v100 + f[2] * dz10, a11 = v110 + f[2] * dz11;
+    double dy0 = a01 - a00, dy1 = a11 - a10;
+    double c0 = a00 + f[1] * dy0, c1 = a10 + f[1] * dy1;
+    double dx = c1 - c0;
+    double val = c0 + f[0] * dx;
+    double dout = sqrt(dout2);
+    if (gl) {
+        double gz0 = dz00 + f[1] * (dz01 - dz00), gz1 = dz10 + f[1] * (dz11 - dz10);
+        double gf[3] = {dx, dy0 + f[0] * (dy1 - dy0), gz0 + f[0] * (gz1 - gz0)};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double h = (g.bmax[a] - g.bmin[a]) / (double)dim[a];
+            double ga = (u[a] > 0.0 && u[a] < (double)(dim[a] - 1)) ? gf[a] / h : 0.0;
+            if (dout > 0.0) ga += o[a] / dout;
+            gl[a] = ga;
+        }
+    }
+    return val + dout;
+}
+
+__device__ __forceinline__ void xf64(const double* T, double x, double y, double z, double* p) {
+    p[0] = T[0] * x + T[1] * y + T[2] * z + T[3];
+    p[1] = T[4] * x + T[5] * y + T[6] * z + T[7];
+    p[2] = T[8] * x + T[9] * y + T[10] * z + T[11];
+}
+
+// gradient w.r.t. the input point: R^T gl, optionally normalised
+__device__ __forceinline__ void grad_to_input(const double* T, const double* gl, int normalize, double* g) {
+    double gx = T[0] * gl[0] + T[4] * gl[1] + T[8] * gl[2];
+    double gy = T[1] * gl[0] + T[5] * gl[1] + T[9] * gl[2];
+    double gz = T[2] * gl[0] + T[6] * gl[1] + T[10] * gl[2];
+    if (normalize) {
+        double n = sqrt(gx * gx + gy * gy + gz * gz);
+        if (n > 0.0) { gx /= n; gy /= n; gz /= n; }
+    }
+    g[0] = gx; g[1] = gy; g[2] = gz;
+}
+
+// ---- finalize: one CTA (128 threads) per transform ------------------------------------------------
+constexpr int kFinThreads = 128;
+constexpr int kSubPts = 32 * kPtsPerThread;      // points per sub-tile (128)
+constexpr int kMaxList = 512;
+
+__device__ __forceinline__ bool lex_less(double d1, int64_t i1, double d2, int64_t i2) {
+    return d1 < d2 || (d1 == d2 && i1 >= 0 && (i2 < 0 || i1 < i2));
+}
+
+__global__ void __launch_bounds__(kFinThreads)
+k_finalize(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int64_t N,
+           const GridDev* __restrict__ grids, const int32_t* __restrict__ grid_of_b,
+           const double* __restrict__ T_rel, const double* __restrict__ bound, double tau, int64_t b_begin,
+           const uint32_t* __restrict__ subkeys, int64_t nsub, int all_tiles, int emit_under,
+           Cand* __restrict__ cand, uint32_t* __restrict__ cand_count, uint32_t cand_cap,
+           double* __restrict__ dmin, int64_t* __restrict__ argmin) {
+    __shared__ uint32_t s_key[kFinThreads];
+    __shared__ int32_t s_list[kMaxList];
+    __shared__ int32_t s_nlist;
+    __shared__ double s_d[kFinThreads];
+    __shared__ int64_t s_i[kFinThreads];
+    __shared__ GridDev s_g;
+    __shared__ double s_T[12];
+    const int tid = threadIdx.x;
+    const int64_t bl = blockIdx.x;                 // batch-local (indexes subkeys)
+    const int64_t b = b_begin + bl;                // global (indexes T_rel, bound, outputs)
+    if (tid == 0) { s_g = grids[grid_of_b ? grid_of_b[b] : 0]; s_nlist = 0; }
+    if (tid < 12) s_T[tid] = T_rel[12 * b + tid];
+    __syncthreads();
+    bool scan_all = all_tiles != 0;
+    if (!scan_all) {
+        // 1) fp32 minimum over the sub-tile keys
+        uint32_t k = 0xffffffffu;
+        for (int64_t s = tid; s < nsub; s += kFinThreads) k = min(k, subkeys[bl * nsub + s]);
+        s_key[tid] = k;
+        __syncthreads();
+        for (int w = kFinThreads / 2; w > 0; w >>= 1) {
+            if (tid < w) s_key[tid] = min(s_key[tid], s_key[tid + w]);
+            __syncthreads();
+        }
+        const float m32 = fkey_inv(s_key[0]);
+        // 2) sub-tiles that may hold the exact minimum: key <= m32 + tau  (fp32 error << tau)
+        const uint32_t kthr = fkey(__double2float_ru((double)m32 + tau));
+        for (int64_t s = tid; s < nsub; s += kFinThreads) {
+            if (subkeys[bl * nsub + s] <= kthr) {
+                int slot = atomicAdd(&s_nlist, 1);
+                if (slot < kMaxList) s_list[slot] = (int32_t)s;
+            }
+        }
+        __syncthreads();
+        if (s_nlist > kMaxList) scan_all = true;     // degenerate (flat field): fall back to every sub-tile
+    }
+    // 3) exact evaluation
+    double best = INFINITY;
+    int64_t besti = -1;
+    const double bnd = (emit_under && bound) ? bound[b] : -INFINITY;
+    const int64_t nloop = scan_all ? nsub : (int64_t)s_nlist;
+    for (int64_t l = 0; l < nloop; ++l) {
+        const int64_t s = scan_all ? l : (int64_t)s_list[l];
+        const int64_t i = s * kSubPts + tid;
+        if (i < N) {
+            float4 q = __ldg(pts + i);
+            double p[3];
+            xf64(s_T, (double)q.x, (double)q.y, (double)q.z, p);
+            double d = eval64(s_g, p, nullptr);
+            int64_t oi = perm[i];
+            if (lex_less(d, oi, best, besti)) { best = d; besti = oi; }
+            if (d < bnd && bnd < (double)INFINITY) {        // fp64 mode: final under-bound entries
+                uint32_t slot = atomicAdd(cand_count, 1u);
+                if (slot < cand_cap) { Cand c; c.b = (int32_t)b; c.idx = (int32_t)oi; c.d = d; cand[slot] = c; }
+            }
+        }
+    }
+    s_d[tid] = best; s_i[tid] = besti;
+    __syncthreads();
+    for (int w = kFinThreads / 2; w > 0; w >>= 1) {
+        if (tid < w && lex_less(s_d[tid + w], s_i[tid + w], s_d[tid], s_i[tid])) {
+            s_d[tid] = s_d[tid + w]; s_i[tid] = s_i[tid + w];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double dm = s_d[0];
+        int64_t am = s_i[0];
+        if (bound && !(dm < bound[b])) am = -1;          // "[]": nothing under Klampt's upperBound
+        dmin[b] = dm;
+        argmin[b] = am;
+    }
+}
+
+void launch_finalize(const MinArgs& a, bool all_tiles, bool emit_under, cudaStream_t st) {
+    if (a.Bc <= 0) return;
+    int64_t nsub = (int64_t)a.ntiles * (kThreads / 32);
+    k_finalize<<<(unsigned)a.Bc, kFinThreads, 0, st>>>(a.pts, a.perm, a.N, a.grids, a.grid_of_b, a.T_rel, a.bound,
+                                                      a.tau, a.b_begin, a.subkeys, nsub, all_tiles ? 1 : 0, emit_under ? 1 : 0,
+                                                      a.cand, a.cand_count, a.cand_cap, a.dmin, a.argmin);
+}
+
+// ---- exact re-check of the fp32 pass's under-bound candidates ------------------------------------------
+__global__ void k_recheck(const float4* __restrict__ pts, const int32_t* __restrict__ perm,
+                          const GridDev* __restrict__ grids, const int32_t* __restrict__ grid_of_b,
+                          const double* __restrict__ T_rel, const double* __restrict__ bound,
+                          Cand* __restrict__ cand, const uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
+    uint32_t n = min(*cand_count, cand_cap);
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    Cand r = cand[c];
+    const GridDev g = grids[grid_of_b ? grid_of_b[r.b] : 0];
+    float4 q = __ldg(pts + r.idx);
+    double p[3];
+    xf64(T_rel + 12 * (int64_t)r.b, (double)q.x, (double)q.y, (double)q.z, p);
+    double d = eval64(g, p, nullptr);
+    Cand o;
+    o.b = (d < bound[r.b]) ? r.b : -1;
+    o.idx = perm[r.idx];
+    o.d = d;
+    cand[c] = o;
+}
+
+void launch_recheck(const MinArgs& a, cudaStream_t st) {
+    // the count lives on the device; launch for the capacity in modest blocks and let threads exit
+    if (!a.bound || a.B <= 0) return;
+    uint32_t threads = 128;
+    // upper bound on work: cand_cap entries.  A launch of cap/128 idle CTAs is cheap, but avoid it when
+    // the cap is large by bounding the grid; the host loops if the count exceeded it (see sio_abi.cu).
+    uint32_t blocks = (a.cand_cap + threads - 1) / threads;
+    k_recheck<<<blocks, threads, 0, st>>>(a.pts, a.perm, a.grids, a.grid_of_b, a.T_rel, a.bound, a.cand,
+                                          a.cand_count, a.cand_cap);
+}
+
+// ---- K1 float64 ---------------------------------------------------------------------------------------
+__global__ void k_query_f64(const GridDev* __restrict__ grid, const double* __restrict__ T,
+                            const double* __restrict__ pts, int64_t P, int normalize,
+                            double* __restrict__ d, double* __restrict__ grad) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const GridDev g = *grid;
+    double p[3], gl[3];
+    xf64(T, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], p);
+    d[i] = eval64(g, p, grad ? gl : nullptr);
+    if (grad) grad_to_input(T, gl, normalize, grad + 3 * i);
+}
+
+void launch_query_f64(const GridDev* grid, const double* T, const double* pts, int64_t P, int normalize,
+                      double* d, double* grad, cudaStream_t st) {
+    if (P <= 0) return;
+    int threads = 128;
+    k_query_f64<<<(unsigned)((P + threads - 1) / threads), threads, 0, st>>>(grid, T, pts, P, normalize, d, grad);
+}
+
+// ---- K3 pose rows ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void invert34(const double* T, double* Ti) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Ti[4 * r + c] = T[4 * c + r];
+        Ti[4 * r + 3] = -(T[0 + r] * T[3] + T[4 + r] * T[7] + T[8 + r] * T[11]);
+    }
+}
+
+__global__ void k_pose_rows(const GridDev* __restrict__ grid, const double* __restrict__ T_pose,
+                            const int64_t* __restrict__ offsets, int64_t nprob, const double* __restrict__ pts,
+                            int64_t total, int normalize, double* __restrict__ d, double* __restrict__ rows) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    // owning problem: largest p with offsets[p] <= i
+    int64_t lo = 0, hi = nprob - 1;
+    while (lo < hi) {
+        int64_t mid = (lo + hi + 1) >> 1;
+        if (offsets[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const double* T = T_pose + 12 * lo;
+    double Ti[12];
+    invert34(T, Ti);
+    const GridDev g = *grid;
+    double p[3], gl[3], gw[3];
+    const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    xf64(Ti, x, y, z, p);
+    d[i] = eval64(g, p, gl);
+    if (!rows) return;
+    grad_to_input(Ti, gl, normalize, gw);
+    const double n0 = -gw[0], n1 = -gw[1], n2 = -gw[2];            // grad1
+    const double q0 = x - T[3], q1 = y - T[7], q2 = z - T[11];
+    // lever arm R (pt - t), exactly as the reference writes it (gopt:415)
+    const double r0 = T[0] * q0 + T[1] * q1 + T[2] * q2;
+    const double r1 = T[4] * q0 + T[5] * q1 + T[6] * q2;
+    const double r2 = T[8] * q0 + T[9] * q1 + T[10] * q2;
+    double* o = rows + 6 * i;
+    o[0] = r1 * n2 - r2 * n1;
+    o[1] = r2 * n0 - r0 * n2;
+    o[2] = r0 * n1 - r1 * n0;
+    o[3] = n0; o[4] = n1; o[5] = n2;
+}
+
+void launch_pose_rows(const GridDev* grid, const double* T_pose, const int64_t* offsets, int64_t nprob,
+                      const double* pts, int64_t total, int normalize, double* d, double* rows, cudaStream_t st) {
+    if (total <= 0) return;
+    int threads = 128;
+    k_pose_rows<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(grid, T_pose, offsets, nprob, pts,
+                                                                                 total, normalize, d, rows);
+}
+
+// ---- K4 kinematics -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void mul34(const double* A, const double* B, double* C) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            C[4 * r + c] = A[4 * r] * B[c] + A[4 * r + 1] * B[4 + c] + A[4 * r + 2] * B[8 + c];
+        C[4 * r + 3] = A[4 * r] * B[3] + A[4 * r + 1] * B[7] + A[4 * r + 2] * B[11] + A[4 * r + 3];
+    }
+}
+
+__device__ __forceinline__ void joint34(const double* ax, int jt, double q, double* J) {
+    if (jt == 1) {
+        J[0] = 1; J[1] = 0; J[2] = 0; J[3] = ax[0] * q;
+        J[4] = 0; J[5] = 1; J[6] = 0; J[7] = ax[1] * q;
+        J[8] = 0; J[9] = 0; J[10] = 1; J[11] = ax[2] * q;
+        return;
+    }
+    double s, c;
+    sincos(q, &s, &c);
+    const double C = 1.0 - c, x = ax[0], y = ax[1], z = ax[2];
+    J[0] = c + x * x * C;     J[1] = x * y * C - z * s; J[2] = x * z * C + y * s; J[3] = 0;
+    J[4] = y * x * C + z * s; J[5] = c + y * y * C;     J[6] = y * z * C - x * s; J[7] = 0;
+    J[8] = z * x * C - y * s; J[9] = z * y * C + x * s; J[10] = c + z * z * C;    J[11] = 0;
+}
+
+// one thread per configuration; links are visited in index order (parents precede children)
+__global__ void k_fk(RobotDev r, const double* __restrict__ q, int64_t B, double* __restrict__ T_out) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    for (int l = 0; l < r.n; ++l) {
+        double J[12], L[12], W[12];
+        joint34(r.axis + 3 * l, r.jtype[l], q[b * r.n + l], J);
+        mul34(r.tparent + 12 * l, J, L);
+        double* out = T_out + (b * r.n + l) * 12;
+        if (r.parent[l] < 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) out[k] = L[k];
+        } else {
+            const double* Pm = T_out + (b * r.n + r.parent[l]) * 12;
+            double Pl[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) Pl[k] = Pm[k];
+            mul34(Pl, L, W);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) out[k] = W[k];
+        }
+    }
+}
+
+void launch_fk(RobotDev r, const double* q, int64_t B, double* T_out, cudaStream_t st) {
+    if (B <= 0) return;
+    int threads = 64;
+    k_fk<<<(unsigned)((B + threads - 1) / threads), threads, 0, st>>>(r, q, B, T_out);
+}
+
+__global__ void k_link_rel(const double* __restrict__ T_links, int32_t n_links, const int32_t* __restrict__ links,
+                           int32_t n_sel, int64_t S, const double* __restrict__ T_cloud,
+                           double* __restrict__ T_rel, int32_t* __restrict__ grid_of_b) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= S * n_sel) return;
+    int64_t s = b / n_sel;
+    int l = (int)(b - s * n_sel);
+    const double* T = T_links + (s * n_links + links[l]) * 12;
+    double Tl[12], Ti[12], Tc[12], R[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { Tl[k] = T[k]; Tc[k] = T_cloud[k]; }
+    invert34(Tl, Ti);
+    mul34(Ti, Tc, R);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T_rel[12 * b + k] = R[k];
+    grid_of_b[b] = l;
+}
+
+void launch_link_rel(const double* T_links, int32_t n_links, const int32_t* links, int32_t n_sel, int64_t S,
+                     const double* T_cloud, double* T_rel, int32_t* grid_of_b, cudaStream_t st) {
+    int64_t n = S * n_sel;
+    if (n <= 0) return;
+    int threads = 128;
+    k_link_rel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(T_links, n_links, links, n_sel, S, T_cloud,
+                                                                            T_rel, grid_of_b);
+}
+
+// value + Jp^T n for points attached to links (gopt:478-482).  One thread per point.
+__global__ void k_chain_rows(RobotDev r, const GridDev* __restrict__ grids, const int32_t* __restrict__ link_grid,
+                             const double* __restrict__ T_links, const int32_t* __restrict__ cfg_of_pt,
+                             const int32_t* __restrict__ link_of_pt, const double* __restrict__ pts, int64_t P,
+                             int normalize, double* __restrict__ d, double* __restrict__ rows) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int link = link_of_pt[i];
+    const int64_t cfg = cfg_of_pt ? cfg_of_pt[i] : 0;
+    const double* Tl = T_links + cfg * r.n * 12;
+    double T[12], Ti[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = Tl[12 * link + k];
+    invert34(T, Ti);
+    const GridDev g = grids[link_grid[link]];
+    const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    double p[3], gl[3], gw[3];
+    xf64(Ti, x, y, z, p);
+    d[i] = eval64(g, p, gl);
+    if (!rows) return;
+    grad_to_input(Ti, gl, normalize, gw);
+    const double n0 = -gw[0], n1 = -gw[1], n2 = -gw[2];
+    double* o = rows + (size_t)r.n * i;
+    for (int j = 0; j < r.n; ++j) o[j] = 0.0;
+    for (int j = link; j >= 0; j = r.parent[j]) {
+        const double* Tj = Tl + 12 * j;
+        const double* ax = r.axis + 3 * j;
+        const double w0 = Tj[0] * ax[0] + Tj[1] * ax[1] + Tj[2] * ax[2];
+        const double w1 = Tj[4] * ax[0] + Tj[5] * ax[1] + Tj[6] * ax[2];
+        const double w2 = Tj[8] * ax[0] + Tj[9] * ax[1] + Tj[10] * ax[2];
+        if (r.jtype[j] == 1) {
+            o[j] = w0 * n0 + w1 * n1 + w2 * n2;
+        } else {
+            const double a0 = x - Tj[3], a1 = y - Tj[7], a2 = z - Tj[11];
+            const double c0 = w1 * a2 - w2 * a1, c1 = w2 * a0 - w0 * a2, c2 = w0 * a1 - w1 * a0;
+            o[j] = c0 * n0 + c1 * n1 + c2 * n2;
+        }
+    }
+}
+
+void launch_chain_rows(RobotDev r, const GridDev* grids, const int32_t* link_grid, const double* T_links,
+                       const int32_t* cfg_of_pt, const int32_t* link_of_pt, const double* pts, int64_t P,
+                       int normalize, double* d, double* rows, cudaStream_t st) {
+    if (P <= 0) return;
+    int threads = 64;
+    k_chain_rows<<<(unsigned)((P + threads - 1) / threads), threads, 0, st>>>(r, grids, link_grid, T_links, cfg_of_pt,
+                                                                              link_of_pt, pts, P, normalize, d, rows);
+}
+
+}  // namespace sio

@@ -1,0 +1,183 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerances (BASELINE.md / SURVEY.md 8d): float32 kernels vs the float64 oracle |dd| <= 2e-6 m,
+|dgrad|_inf <= 1e-4; float64 mode <= 1e-12; minima / arg-minima / under-bound sets IDENTICAL in both
+modes (the float32 mode re-evaluates near-ties in float64)."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+F32, F64, NONORM = 0, 1, 2
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def _mk(ctx, O, vg):
+    return ctx.grid_create(vg.values, vg.bmin, vg.bmax), O.Grid(vg.values, vg.bmin, vg.bmax)
+
+
+@pytest.mark.parametrize("gridname", ["sphere", "random"])
+def test_query_f64_matches_oracle(ctx, O, gridname):
+    vg = util.sphere_grid() if gridname == "sphere" else util.random_grid(1)
+    g, G = _mk(ctx, O, vg)
+    rng = np.random.default_rng(2)
+    span = vg.bmax - vg.bmin
+    pts = vg.bmin - 0.3 * span + rng.uniform(0, 1, (20000, 3)) * 1.6 * span     # inside and outside the bbox
+    for T in util.random_poses(3, 3, rot=0.8, trans=0.2):
+        for norm in (True, False):
+            d, gr = ctx.query(g, T, pts, flags=F64 | (0 if norm else NONORM))
+            d0, g0 = O.query(G, T, pts, normalize=norm)
+            assert np.abs(d - d0).max() <= 1e-12
+            assert np.abs(gr - g0).max() <= 1e-10
+    ctx.grid_destroy(g)
+
+
+def test_query_f32_within_tolerance(ctx, O):
+    geom = util.fixture_geometry("m1062")
+    vg = geom.convert("VolumeGrid", 0.02).getVolumeGrid()
+    g, G = _mk(ctx, O, vg)
+    rng = np.random.default_rng(4)
+    pts = vg.bmin + rng.uniform(0, 1, (50000, 3)) * (vg.bmax - vg.bmin)
+    T = util.random_poses(5, 1, rot=0.3, trans=0.05)[0]
+    d, gr = ctx.query(g, T, pts, flags=F32 | NONORM)
+    d0, g0 = O.query(G, T, pts, normalize=False)
+    assert np.abs(d - d0).max() <= 2e-6
+    # the gradient is discontinuous across cell faces: compare away from them
+    ok = np.abs(gr - g0).max(axis=1) <= 1e-4
+    assert ok.mean() > 0.999
+    ctx.grid_destroy(g)
+
+
+def test_known_answer_sphere(ctx):
+    """Closed form: |p| - r sampled on a fine grid; trilinear error is O(h^2)."""
+    vg = util.sphere_grid(r=0.7, n=96)
+    g = ctx.grid_create(vg.values, vg.bmin, vg.bmax)
+    rng = np.random.default_rng(6)
+    pts = rng.uniform(-0.9, 0.9, (4000, 3))
+    pts = pts[np.linalg.norm(pts, axis=1) > 0.2]
+    d, gr = ctx.query(g, np.eye(4)[:3].reshape(12), pts, flags=F64)
+    assert np.abs(d - (np.linalg.norm(pts, axis=1) - 0.7)).max() < 2e-3
+    n = pts / np.linalg.norm(pts, axis=1, keepdims=True)
+    assert np.abs(gr - n).max() < 5e-2
+    ctx.grid_destroy(g)
+
+
+@pytest.mark.parametrize("flags", [F32, F64])
+@pytest.mark.parametrize("N", [0, 1, 31, 1000, 4097, 70001])
+def test_min_distance_matches_oracle(ctx, O, flags, N):
+    vg = util.random_grid(7, dims=(21, 18, 25))
+    g, G = _mk(ctx, O, vg)
+    rng = np.random.default_rng(8 + N)
+    cloud = (vg.bmin - 0.2 + rng.uniform(0, 1, (N, 3)) * (vg.bmax - vg.bmin + 0.4)).astype(np.float32)
+    c = ctx.cloud_create(cloud)
+    T = util.random_poses(9, 37, rot=0.5, trans=0.2)
+    dmin, arg, nu = ctx.min_distance(g, c, T, flags=flags)
+    d0, a0 = O.min_distance(G, cloud, T)
+    if N == 0:
+        assert np.all(np.isinf(dmin)) and np.all(arg == -1)
+    else:
+        assert np.array_equal(arg, a0)
+        assert np.abs(dmin - d0).max() <= 1e-12
+    ctx.cloud_destroy(c)
+    ctx.grid_destroy(g)
+
+
+@pytest.mark.parametrize("flags", [F32, F64])
+def test_under_bound_sets_identical(ctx, O, flags):
+    geom = util.fixture_geometry("cube")
+    vg = geom.convert("VolumeGrid", 0.05).getVolumeGrid()
+    g, G = _mk(ctx, O, vg)
+    env = util.fixture_geometry("m797").convert("PointCloud", 0.02).getPointCloud().points
+    cloud = (env + np.array([0.3, 0.0, 0.0])).astype(np.float32)
+    c = ctx.cloud_create(cloud)
+    T = util.invert12(util.random_poses(10, 24, rot=0.3, trans=0.3, center=(0.2, 0.2, 0.2)))
+    bound = np.linspace(-0.05, 0.02, len(T))
+    bound[::5] = np.inf
+    dmin, arg, nu = ctx.min_distance(g, c, T, bound=bound, flags=flags)
+    ub, ui, ud = ctx.under_fetch()
+    d0, a0 = O.min_distance(G, cloud, T, bound=bound)
+    n0, ob, oi, od = O.under(G, cloud, T, bound)
+    assert np.array_equal(arg, a0)
+    assert np.abs(dmin - d0).max() <= 1e-12
+    assert n0 == len(ub) and n0 > 0
+    assert np.array_equal(ub, ob) and np.array_equal(ui, oi)
+    assert np.abs(ud - od).max() <= 1e-12
+    assert np.array_equal(nu, np.bincount(ob, minlength=len(T)))
+    ctx.cloud_destroy(c)
+    ctx.grid_destroy(g)
+
+
+def test_min_distance_multi_grid(ctx, O):
+    vgs = [util.random_grid(20 + k, dims=(9 + 3 * k, 11, 8 + k)) for k in range(3)]
+    pairs = [_mk(ctx, O, vg) for vg in vgs]
+    rng = np.random.default_rng(21)
+    cloud = rng.uniform(-0.5, 1.5, (5000, 3)).astype(np.float32)
+    c = ctx.cloud_create(cloud)
+    T = util.random_poses(22, 50, rot=0.6, trans=0.3)
+    gob = rng.integers(0, 3, len(T)).astype(np.int32)
+    dmin, arg, _ = ctx.min_distance([p[0] for p in pairs], c, T, grid_of_b=gob)
+    d0, a0 = O.min_distance([p[1] for p in pairs], cloud, T, grid_of_b=gob)
+    assert np.array_equal(arg, a0) and np.abs(dmin - d0).max() <= 1e-12
+
+
+def test_exact_ties_lowest_index(ctx, O):
+    """Duplicated points: the oracle keeps the first; so must the device path."""
+    vg = util.sphere_grid(n=32)
+    g, G = _mk(ctx, O, vg)
+    rng = np.random.default_rng(30)
+    base = rng.uniform(-0.9, 0.9, (500, 3)).astype(np.float32)
+    cloud = np.vstack([base, base, base[::-1]])
+    c = ctx.cloud_create(cloud)
+    T = util.random_poses(31, 16, rot=0.4, trans=0.1)
+    for flags in (F32, F64):
+        dmin, arg, _ = ctx.min_distance(g, c, T, flags=flags)
+        d0, a0 = O.min_distance(G, cloud, T)
+        assert np.array_equal(arg, a0)
+        assert np.array_equal(dmin, d0) or np.abs(dmin - d0).max() <= 1e-12
+
+
+def test_pose_rows_match_oracle(ctx, O):
+    geom = util.fixture_geometry("cube")
+    vg = geom.convert("VolumeGrid", 0.05).getVolumeGrid()
+    g, G = _mk(ctx, O, vg)
+    rng = np.random.default_rng(40)
+    poses = util.random_poses(41, 5, rot=0.5, trans=0.3)
+    counts = [0, 3, 1, 7, 2]
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    pts = rng.uniform(-0.3, 1.3, (offs[-1], 3))
+    d, rows = ctx.pose_rows(g, poses, offs, pts)
+    for p in range(5):
+        sl = slice(offs[p], offs[p + 1])
+        d0, r0 = O.pose_rows(G, poses[p], pts[sl])
+        assert np.abs(d[sl] - d0).max(initial=0) <= 1e-12
+        assert np.abs(rows[sl] - r0).max(initial=0) <= 1e-10
+
+
+def test_cloud_query_dev_layout(ctx, O):
+    import torch
+    vg = util.sphere_grid(r=0.6, n=40)       # a true SDF (|grad| = 1): the 2e-6 m tolerance is stated for those
+    g, G = _mk(ctx, O, vg)
+    rng = np.random.default_rng(51)
+    cloud = rng.uniform(-1.3, 1.3, (3000, 3)).astype(np.float32)
+    c = ctx.cloud_create(cloud)
+    perm = ctx.cloud_perm(c)
+    T = util.random_poses(52, 5, rot=0.5, trans=0.2)
+    dT = torch.from_numpy(T).cuda()
+    out = torch.empty((5, 3000, 4), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.cloud_query_dev(g, c, dT.data_ptr(), 5, F32, None, out.data_ptr())
+    ctx.sync()
+    res = out.cpu().numpy()
+    d0, g0 = O.cloud_query(G, cloud, T)
+    assert np.abs(res[:, :, 3] - d0[:, perm]).max() <= 2e-6
+    outd = torch.empty((5, 3000), dtype=torch.float32, device="cuda")
+    ctx.cloud_query_dev(g, c, dT.data_ptr(), 5, F32, outd.data_ptr(), None)
+    ctx.sync()
+    assert np.abs(outd.cpu().numpy() - d0[:, perm]).max() <= 2e-6
