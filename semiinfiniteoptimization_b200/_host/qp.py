@@ -1,0 +1,193 @@
+"""Host QP solver for the SIP step (the role OSQP plays for the reference, sip.py:294-378).
+
+OSQP is not available to this build, so its published algorithm (Stellato et al., "OSQP: an
+operator splitting solver for quadratic programs") is restated here: ADMM on
+
+    min 1/2 x'Px + q'x   s.t.  l <= Ax <= u
+
+with the indirect KKT system [[P + sigma I, A'], [A, -1/rho]], over-relaxation alpha, adaptive
+rho, the standard primal/dual residual test and the primal-infeasibility certificate, followed by
+an optional polish (equality-constrained solve on the identified active set).  The QP is small
+(n = 6 / 7 / 455 variables) and stays on the host per BASELINE.json's north_star.
+
+`solve_qp` handles one problem (dense or sparse); `solve_qp_batch` runs many small dense problems
+of identical shape in lock-step with numpy (the C5 batch).
+"""
+import numpy as np
+import scipy.linalg
+import scipy.sparse
+import scipy.sparse.linalg
+
+INF = 1e20
+
+
+class QPResult:
+    def __init__(self, x, y, status, iters, pri_res, dua_res):
+        self.x = x
+        self.y = y
+        self.status = status          # 'solved' | 'primal infeasible' | 'max iterations'
+        self.iters = iters
+        self.pri_res = pri_res
+        self.dua_res = dua_res
+
+
+def _kkt_solver(P, A, sigma, rho_vec, sparse):
+    n = P.shape[0]
+    if sparse:
+        K = scipy.sparse.bmat([[P + sigma * scipy.sparse.identity(n, format="csc"), A.T],
+                               [A, -scipy.sparse.diags(1.0 / rho_vec)]], format="csc")
+        lu = scipy.sparse.linalg.splu(K)
+        return lu.solve
+    m = A.shape[0]
+    K = np.zeros((n + m, n + m))
+    K[:n, :n] = P + sigma * np.eye(n)
+    K[:n, n:] = A.T
+    K[n:, :n] = A
+    K[n:, n:] = -np.diag(1.0 / rho_vec)
+    lu = scipy.linalg.lu_factor(K)
+    return lambda b: scipy.linalg.lu_solve(lu, b)
+
+
+def solve_qp(P, q, A, l, u, eps_abs=1e-5, eps_rel=1e-5, max_iter=20000, rho=0.1, sigma=1e-6, alpha=1.6,
+             polish=True, check_every=10, adapt_every=50):
+    sparse = scipy.sparse.issparse(P) or scipy.sparse.issparse(A)
+    if sparse:
+        P = scipy.sparse.csc_matrix(P)
+        A = scipy.sparse.csc_matrix(A)
+    else:
+        P = np.asarray(P, dtype=np.float64)
+        A = np.asarray(A, dtype=np.float64)
+    q = np.asarray(q, dtype=np.float64)
+    l = np.maximum(np.asarray(l, dtype=np.float64), -INF)
+    u = np.minimum(np.asarray(u, dtype=np.float64), INF)
+    n, m = len(q), len(l)
+    eq = (u - l) < 1e-12
+
+    def rho_vector(r):
+        v = np.full(m, r)
+        v[eq] = 1e3 * r
+        return v
+
+    rho_vec = rho_vector(rho)
+    solve = _kkt_solver(P, A, sigma, rho_vec, sparse)
+    x = np.zeros(n)
+    z = np.zeros(m)
+    y = np.zeros(m)
+    status = "max iterations"
+    r_prim = r_dual = np.inf
+    it = 0
+    for it in range(1, max_iter + 1):
+        rhs = np.concatenate([sigma * x - q, z - y / rho_vec])
+        sol = solve(rhs)
+        xt, nu = sol[:n], sol[n:]
+        zt = z + (nu - y) / rho_vec
+        x_new = alpha * xt + (1 - alpha) * x
+        zr = alpha * zt + (1 - alpha) * z
+        z_new = np.clip(zr + y / rho_vec, l, u)
+        y_new = y + rho_vec * (zr - z_new)
+        dy = y_new - y
+        x, z, y = x_new, z_new, y_new
+        if it % check_every and it != max_iter:
+            continue
+        Ax = A @ x
+        Px = P @ x
+        Aty = A.T @ y
+        r_prim = np.abs(Ax - z).max() if m else 0.0
+        r_dual = np.abs(Px + q + Aty).max()
+        nAx = max(np.abs(Ax).max() if m else 0.0, np.abs(z).max() if m else 0.0)
+        nd = max(np.abs(Px).max(), np.abs(Aty).max() if m else 0.0, np.abs(q).max())
+        if r_prim <= eps_abs + eps_rel * nAx and r_dual <= eps_abs + eps_rel * nd:
+            status = "solved"
+            break
+        # primal infeasibility certificate (OSQP paper, sec. 3.4)
+        ndy = np.abs(dy).max() if m else 0.0
+        if ndy > 1e-12:
+            dyn = dy / ndy
+            if np.abs(A.T @ dyn).max() <= 1e-4 and (u @ np.maximum(dyn, 0) + l @ np.minimum(dyn, 0)) < -1e-4:
+                status = "primal infeasible"
+                break
+        if it % adapt_every == 0 and r_prim > 0 and r_dual > 0:
+            scale = np.sqrt((r_prim / max(nAx, 1e-12)) / (r_dual / max(nd, 1e-12)))
+            if scale > 5 or scale < 0.2:
+                rho = float(np.clip(rho * scale, 1e-6, 1e6))
+                rho_vec = rho_vector(rho)
+                solve = _kkt_solver(P, A, sigma, rho_vec, sparse)
+    if status == "solved" and polish and m:
+        xp = _polish(P, q, A, l, u, x, y, sparse)
+        if xp is not None:
+            x = xp
+    return QPResult(x if status != "primal infeasible" else None, y, status, it, r_prim, r_dual)
+
+
+def _polish(P, q, A, l, u, x, y, sparse, delta=1e-7, tol=1e-7):
+    """Solve the equality-constrained QP on the active set the ADMM iterate identifies; keep the
+    result only if it is feasible and no worse."""
+    Ax = A @ x
+    lo = (y < -1e-9) | (Ax - l < 1e-7)
+    up = (y > 1e-9) | (u - Ax < 1e-7)
+    lo &= l > -INF / 2
+    up &= u < INF / 2
+    act = np.nonzero(lo | up)[0]
+    if len(act) == 0:
+        return None
+    rhs_c = np.where(lo[act], l[act], u[act])
+    n = len(q)
+    try:
+        if sparse:
+            Aa = A[act]
+            K = scipy.sparse.bmat([[P + delta * scipy.sparse.identity(n), Aa.T],
+                                   [Aa, -delta * scipy.sparse.identity(len(act))]], format="csc")
+            sol = scipy.sparse.linalg.splu(K).solve(np.concatenate([-q, rhs_c]))
+        else:
+            Aa = A[act]
+            K = np.block([[P + delta * np.eye(n), Aa.T], [Aa, -delta * np.eye(len(act))]])
+            sol = np.linalg.solve(K, np.concatenate([-q, rhs_c]))
+    except Exception:
+        return None
+    xp = sol[:n]
+    if not np.all(np.isfinite(xp)):
+        return None
+    Axp = A @ xp
+    if np.any(Axp < l - tol) or np.any(Axp > u + tol):
+        return None
+    f = lambda v: 0.5 * v @ (P @ v) + q @ v
+    if f(xp) > f(x) + 1e-9 * (1 + abs(f(x))):
+        return None
+    return xp
+
+
+def solve_qp_batch(P, q, A, l, u, nrows, iters=400, rho=0.1, sigma=1e-6, alpha=1.6):
+    """Lock-step ADMM for many small dense QPs of one padded shape.
+
+    P: (B,n,n), q: (B,n), A: (B,m,n), l/u: (B,m); rows >= nrows[b] of problem b are padding and
+    must be given as 0 <= 0*x <= 0-free rows (A row 0, l=-INF, u=INF).  Fixed iteration count;
+    returns x (B,n) and the final primal/dual residuals."""
+    P = np.asarray(P, dtype=np.float64)
+    A = np.asarray(A, dtype=np.float64)
+    B, m, n = A.shape
+    l = np.maximum(l, -INF)
+    u = np.minimum(u, INF)
+    K = np.zeros((B, n + m, n + m))
+    K[:, :n, :n] = P + sigma * np.eye(n)
+    K[:, :n, n:] = np.transpose(A, (0, 2, 1))
+    K[:, n:, :n] = A
+    idx = np.arange(m)
+    K[:, n + idx, n + idx] = -1.0 / rho
+    Kinv = np.linalg.inv(K)
+    x = np.zeros((B, n))
+    z = np.zeros((B, m))
+    y = np.zeros((B, m))
+    for _ in range(iters):
+        rhs = np.concatenate([sigma * x - q, z - y / rho], axis=1)
+        sol = np.einsum('bij,bj->bi', Kinv, rhs)
+        xt, nu = sol[:, :n], sol[:, n:]
+        zt = z + (nu - y) / rho
+        x = alpha * xt + (1 - alpha) * x
+        zr = alpha * zt + (1 - alpha) * z
+        z_new = np.clip(zr + y / rho, l, u)
+        y = y + rho * (zr - z_new)
+        z = z_new
+    Ax = np.einsum('bij,bj->bi', A, x)
+    r_prim = np.abs(Ax - z).max(axis=1)
+    r_dual = np.abs(np.einsum('bij,bj->bi', P, x) + q + np.einsum('bji,bj->bi', A, y)).max(axis=1)
+    return x, r_prim, r_dual

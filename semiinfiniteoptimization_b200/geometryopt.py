@@ -1,0 +1,952 @@
+"""Collision geometry wrapper, kinematics caches, collision constraints and front-ends.
+
+Keeps the names, call signatures and return conventions of the reference's
+semiinfinite/geometryopt.py so it drops in for the collision-oracle hot path:
+
+    PenetrationDepthGeometry                      gopt:38-168
+    RobotKinematicsCache / RobotTrajectoryCache   gopt:187-207 / 209-366
+    ObjectPoseObjective, RobotConfigObjective, TrajectoryLengthObjective   gopt:370-391, 444-455, 512-552
+    ObjectCollisionConstraint                     gopt:394-420
+    RobotLinkCollisionConstraint                  gopt:457-484
+    RobotLinkTrajectoryCollisionConstraint        gopt:565-675
+    RobotTrajectoryCollisionConstraint            gopt:678-956
+    makeCollisionConstraints, optimizeCollFree, optimizeCollFreeRobot, optimizeCollFreeTrajectory
+                                                  gopt:959-1036, 1039-1081, 1125-1225, 1227-1340
+
+What differs is underneath: every geometric query (`distance`, `normal`, `minvalue`, `df_dx`) is a
+call through the C-ABI (include/sio_abi.h) into sm_100a kernels on a resident SDF grid / point
+cloud; where the reference loops in Python around single Klampt calls (per parameter, per
+milestone, per bisection sample), these classes issue ONE batched launch (`value_batch`,
+`df_dx_batch`, the per-config link sweep of RobotKinematicsCache, the dense time sweep of the
+trajectory constraints).  There is no CPU path: constructing a PenetrationDepthGeometry needs the
+CUDA library and a B200.
+
+Host-side geometry objects (`Geometry3D`, robot model, trajectories) come from `_host/`, the
+stand-in for Klampt, which stays host-side for loading and one-off conversion exactly as in the
+reference.
+"""
+import math
+import random
+import time
+
+import numpy as np
+import scipy.sparse
+
+from . import _abi
+from ._host import se3, so3, vectorops
+from ._host.geometry import Geometry3D
+from ._host.robot import RigidObjectModel, RobotModel, RobotModelLink
+from ._host.trajectory import RobotTrajectory, Trajectory
+from .sip import *     # noqa: F401,F403   (the reference does `from sip import *`, gopt:5)
+from . import sip as _sip
+
+TEST_PYCCD = False            # pyccd convex path: out of scope (gopt:14)
+ADD_INTERIOR_POINTS = False
+USE_BALLS = False
+
+# precision of the bulk cloud-vs-grid pass: float32 arithmetic + float64 re-evaluation of every
+# near-tie (results equal the float64 oracle's) or float64 everywhere (validation mode)
+BULK_FLAGS = _abi.SIO_F32
+# single-point / per-parameter queries are launch-bound, so they always run in float64
+POINT_FLAGS = _abi.SIO_F64
+
+_I12 = np.eye(4)[:3].reshape(12)
+
+
+def set_validation_mode(on=True):
+    """fp64 validation mode of BASELINE.json's north_star: every kernel computes in float64."""
+    global BULK_FLAGS
+    BULK_FLAGS = _abi.SIO_F64 if on else _abi.SIO_F32
+
+
+def _inv12(T12):
+    T = np.asarray(T12, dtype=np.float64).reshape(3, 4)
+    out = np.empty((3, 4))
+    out[:, :3] = T[:, :3].T
+    out[:, 3] = -T[:, :3].T @ T[:, 3]
+    return out.reshape(12)
+
+
+def _mul12(A12, B12):
+    A = np.asarray(A12, dtype=np.float64).reshape(3, 4)
+    B = np.asarray(B12, dtype=np.float64).reshape(3, 4)
+    out = np.empty((3, 4))
+    out[:, :3] = A[:, :3] @ B[:, :3]
+    out[:, 3] = A[:, :3] @ B[:, 3] + A[:, 3]
+    return out.reshape(12)
+
+
+class _DeviceGeometry:
+    """Resident grid / cloud handles shared by every PenetrationDepthGeometry copy of one geometry
+    (the reference's copy constructor aliases grid and pc the same way, gopt:44-50)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.grid_h = -1
+        self.cloud_h = -1
+        self.cloud32 = None      # host float32 copy: arg-min index -> closest point
+
+    def upload_grid(self, vg):
+        self.grid_h = self.ctx.grid_create(vg.values, vg.bmin, vg.bmax)
+
+    def upload_cloud(self, pts):
+        self.cloud32 = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 3)
+        self.cloud_h = self.ctx.cloud_create(self.cloud32)
+
+
+class PenetrationDepthGeometry:
+    def __init__(self, geom, gridres=0, pcres=0, context=None):
+        """geom: a Geometry3D or another PenetrationDepthGeometry (copy: shares grid and cloud).
+        gridres / pcres: conversion resolutions; None disables that representation, 0 = automatic
+        (gopt:39-84)."""
+        if isinstance(geom, PenetrationDepthGeometry):
+            self.geom = geom.geom
+            self.pc = geom.pc
+            self.pcdata = geom.pcdata
+            self.grid = geom.grid
+            self.polyhedron = geom.polyhedron
+            self._dev = geom._dev
+            self._T12 = geom._T12.copy()
+        else:
+            assert isinstance(geom, Geometry3D), "geom must be a Geometry3D or PenetrationDepthGeometry"
+            self.geom = geom
+            self.pc = None
+            self.pcdata = None
+            self.grid = None
+            self.polyhedron = None
+            self._dev = _DeviceGeometry(context or _abi.default_context())
+            self._T12 = se3.to_rowmajor12(geom.getCurrentTransform())
+            if gridres is not None:
+                try:
+                    self.grid = geom.convert('VolumeGrid', gridres)
+                except Exception as e:
+                    print("WARNING: could not convert geometry to VolumeGrid, exception", e)
+                    print("May have problems performing normal and distance estimation")
+                if self.grid is not None:
+                    self._dev.upload_grid(self.grid.getVolumeGrid())
+            if pcres is not None:
+                self.pc = geom.convert('PointCloud', pcres)
+                self.pcdata = self.pc.getPointCloud()
+                self._dev.upload_cloud(self.pcdata.points)
+
+    # -- transforms (gopt:85-94) --
+    def setTransform(self, T):
+        self.geom.setCurrentTransform(*T)
+        if self.pc is not None:
+            self.pc.setCurrentTransform(*T)
+        if self.grid is not None:
+            self.grid.setCurrentTransform(*T)
+        self._T12 = se3.to_rowmajor12(T)
+
+    def setTransform12(self, T12):
+        """Row-major 3x4 variant used by the batched paths (no list conversions)."""
+        self._T12 = np.asarray(T12, dtype=np.float64).reshape(12).copy()
+        T = se3.from_rowmajor12(self._T12)
+        self.geom.setCurrentTransform(*T)
+        if self.pc is not None:
+            self.pc.setCurrentTransform(*T)
+        if self.grid is not None:
+            self.grid.setCurrentTransform(*T)
+
+    def getTransform(self):
+        return self.geom.getCurrentTransform()
+
+    @property
+    def context(self):
+        return self._dev.ctx
+
+    # -- queries --
+    def distance(self, other, bound=None):
+        """Returns (distance, closestpoint_self, closestpoint_other) (gopt:95-147).
+
+        other = point: SDF of this geometry's grid at the world point (K1).
+        other = PenetrationDepthGeometry: min over THIS geometry's cloud of `other`'s SDF (K2),
+        cp1 = arg-min cloud point in world coordinates; zeros when bound prunes everything."""
+        if isinstance(other, (list, tuple, np.ndarray)):
+            assert self.grid is not None, "Need a VolumeGrid for geometry-point distance"
+            pt = [float(v) for v in other[:3]]
+            d, g = self._dev.ctx.query(self._dev.grid_h, _inv12(self._T12), [pt], flags=POINT_FLAGS)
+            d = float(d[0])
+            cp1 = [pt[k] - g[0, k] * d for k in range(3)]      # surface point along the unit gradient
+            return d, cp1, pt
+        assert isinstance(other, PenetrationDepthGeometry)
+        if other.grid is None:
+            assert self.grid is not None, "Can't compute fast distance without a signed distance field VolumeGrid / PointCloud"
+            assert other.pc is not None, "Can't compute fast distance without a signed distance field VolumeGrid / PointCloud"
+            d, cp_other, cp_self = other._cloud_vs_grid(self, bound)
+            return d, cp_self, cp_other
+        return self._cloud_vs_grid(other, bound)
+
+    def _cloud_vs_grid(self, other, bound, want_cp2=True):
+        """min_i SDF_other(T_other^-1 T_self p_i) over this cloud; (d, cp on this cloud, cp on other)."""
+        assert self.pc is not None, "Need a PointCloud for geometry-geometry distance"
+        ctx = self._dev.ctx
+        T_rel = _mul12(_inv12(other._T12), self._T12)
+        bnd = None if bound is None else [float(bound)]
+        dmin, arg, _ = ctx.min_distance(other._dev.grid_h, self._dev.cloud_h, T_rel, bound=bnd, flags=BULK_FLAGS,
+                                        want_under=False)
+        d = float(dmin[0])
+        if arg[0] < 0 or (bound is not None and d >= bound):
+            return d, [0.0] * 3, [0.0] * 3
+        p = self._dev.cloud32[int(arg[0])].astype(np.float64)
+        T = self._T12.reshape(3, 4)
+        cp1 = [float(v) for v in T[:, :3] @ p + T[:, 3]]
+        cp2 = other.distance(cp1)[1] if want_cp2 else [0.0] * 3
+        return d, cp1, cp2
+
+    def normal(self, pt):
+        """grad1 of the SDF at the world point: d(distance)/d(translation of this geometry)
+        (gopt:148-168)."""
+        pt = [float(v) for v in pt[:3]]
+        d, g = self._dev.ctx.query(self._dev.grid_h, _inv12(self._T12), [pt], flags=POINT_FLAGS)
+        return [-float(v) for v in g[0]]
+
+    # -- batched extensions --
+    def distances(self, pts):
+        """SDF values at many world points in one launch."""
+        return self._dev.ctx.query(self._dev.grid_h, _inv12(self._T12), pts, flags=POINT_FLAGS, want_grad=False)
+
+    def normals(self, pts):
+        d, g = self._dev.ctx.query(self._dev.grid_h, _inv12(self._T12), pts, flags=POINT_FLAGS)
+        return -g
+
+
+class PenetrationGeometryDomain(DomainInterface):
+    def __init__(self, g):
+        self.g = g
+
+    def sample(self):
+        idx = random.randint(0, self.g.pcdata.numPoints() - 1)
+        return se3.apply(self.g.getTransform(), self.g.pcdata.getPoint(idx))
+
+    def extrema(self):
+        T = self.g.getTransform()
+        return [se3.apply(T, self.g.pcdata.getPoint(i)) for i in range(self.g.pcdata.numPoints())]
+
+
+# =================================================================================================
+# kinematics caches
+# =================================================================================================
+class RobotKinematicsCache:
+    """One PenetrationDepthGeometry per non-empty link; `set(q)` places them (gopt:187-207).
+
+    Device side: the kinematic chain is registered once (`sio_robot_create`); `link_min_distances`
+    sweeps EVERY geometric link against an environment cloud in one fused FK + K2 launch and
+    memoises the result until `clear()`, so the per-link constraints that share this cache pay for
+    one launch per configuration instead of one Klampt call each."""
+
+    def __init__(self, robot, gridres=0.05, pcres=0.02, context=None):
+        self.robot = robot
+        self.context = context or _abi.default_context()
+        self.geometry = []
+        for i in range(robot.numLinks()):
+            geom = robot.link(i).geometry()
+            if geom is None or geom.empty():
+                self.geometry.append(None)
+            else:
+                self.geometry.append(PenetrationDepthGeometry(geom, gridres, pcres, context=self.context))
+        self.dirty = True
+        self.q = None
+        self.robot_h = self.context.robot_create(robot.parents, robot.tparent, robot.axes, robot.jtypes)
+        self.link_grids = np.array([g._dev.grid_h if (g is not None and g.grid is not None) else -1 for g in self.geometry],
+                                   dtype=np.int32)
+        self.geom_links = [i for i, g in enumerate(self.geometry) if g is not None and g.grid is not None]
+        self._sweeps = {}
+
+    def set(self, q):
+        """Updates the robot configuration and PenetrationDepthGeometry transforms."""
+        if self.dirty:
+            self.robot.setConfig(q)
+            for i in range(self.robot.numLinks()):
+                if self.geometry[i] is None:
+                    continue
+                self.geometry[i].setTransform12(self.robot.link_T[i].reshape(12))
+            self.q = [float(v) for v in q]
+            self._sweeps = {}
+            self.dirty = False
+
+    def clear(self):
+        self.dirty = True
+
+    def link_min_distances(self, env):
+        """{link: (dmin, env cloud index)} for all geometric links at the current configuration."""
+        key = id(env._dev)
+        hit = self._sweeps.get(key)
+        if hit is not None and np.array_equal(hit[0], env._T12):
+            return hit[1]
+        dmin, arg, _ = self.context.robot_min_distance(self.robot_h, self.robot.numLinks(), self.link_grids, self.geom_links,
+                                                       env._dev.cloud_h, env._T12, [self.q], flags=BULK_FLAGS)
+        res = {l: (float(dmin[0, k]), int(arg[0, k])) for k, l in enumerate(self.geom_links)}
+        self._sweeps[key] = (env._T12.copy(), res)
+        return res
+
+
+class RobotTrajectoryCache:
+    """Decodes a RobotTrajectory from the optimisation vector and caches per-milestone link
+    transforms and Lipschitz workspace-motion bounds (gopt:209-366)."""
+
+    def __init__(self, robot, numPoints, times=False, qstart=None, qend=None):
+        if isinstance(robot, RobotKinematicsCache):
+            self.robot = robot.robot
+            self.kinematics = robot
+            robot = self.robot
+        else:
+            self.robot = robot
+            self.kinematics = RobotKinematicsCache(robot)
+        self.numPoints = numPoints
+        self.times = times
+        self.qstart = qstart
+        self.qend = qend
+        self.tstart = 0
+        self.tend = 1
+        self.trajectory = None
+        self.interMilestoneLipschitzBounds = []
+        self.linkTransforms = []
+        self.linkTransforms12 = None
+        n = self.robot.numLinks()
+        # K[i,j]: bound on the workspace motion of link j's geometry per unit motion of joint i
+        # (gopt:245-283): distance from joint i to link j's frame along the chain + the radius of
+        # link j's cloud about its own frame
+        self.lipschitzConstants = np.zeros((n, n))
+        radii = np.zeros((n, n))
+        ancestors = [[] for _ in range(n)]
+        for l in range(n):
+            p = self.robot.link(l).getParent()
+            if p >= 0:
+                ancestors[l] = [p] + ancestors[p]
+        for l in range(n):
+            link = self.robot.link(l)
+            p = link.getParent()
+            if p >= 0:
+                T = link.getParentTransform()
+                for a in ancestors[l]:
+                    radii[a, l] = radii[a, p] + vectorops.norm(T[1])
+                radii[p, l] += vectorops.norm(T[1])
+            axis = np.asarray(link.getAxis())
+            g = self.kinematics.geometry[l]
+            Kgeom = 0.0
+            if g is not None and g.pcdata is not None and g.pcdata.numPoints() > 0:
+                P = g.pcdata.points
+                if p < 0:
+                    Kgeom = float(np.linalg.norm(np.cross(P, axis), axis=1).max())
+                else:
+                    Kgeom = float(np.linalg.norm(P, axis=1).max())
+            for a in ancestors[l]:
+                self.lipschitzConstants[a, l] = radii[a, l] + Kgeom
+            self.lipschitzConstants[l, l] = Kgeom
+        self.dirty = True
+
+    def set(self, x):
+        if self.dirty:
+            self.trajectory = self.stateToTrajectory(x)
+            ms = np.asarray(self.trajectory.milestones, dtype=np.float64)
+            self.interMilestoneLipschitzBounds = [self.workspaceMovementBounds(ms[i], ms[i + 1]) for i in range(len(ms) - 1)]
+            # forward kinematics of every milestone in one device launch
+            T = self.kinematics.context.fk(self.kinematics.robot_h, ms, self.robot.numLinks())
+            self.linkTransforms12 = T
+            self.linkTransforms = [[se3.from_rowmajor12(T[i, j]) for j in range(T.shape[1])] for i in range(T.shape[0])]
+            self.dirty = False
+
+    def clear(self):
+        self.dirty = True
+
+    def workspaceMovementBounds(self, q1, q2):
+        dq = np.abs(self.robot.interpolateDeriv(q1, q2))
+        return np.dot(self.lipschitzConstants.T, dq)
+
+    def workspaceMovementBound(self, link, q1, q2):
+        if isinstance(link, RobotModelLink):
+            link = link.index
+        dq = np.abs(self.robot.interpolateDeriv(q1, q2)[:link + 1])
+        return np.dot(self.lipschitzConstants[:link + 1, link], dq)
+
+    def stateToTrajectory(self, x):
+        n = self.robot.numLinks()
+        m = self.numPoints
+        x = list(x)
+        times = []
+        milestones = []
+        timed = self.times is True or hasattr(self.times, '__iter__')
+        if self.qstart:
+            milestones.append(list(self.qstart))
+            if timed:
+                times.append(self.tstart)
+        k = 0
+        if self.times is True:
+            times += x[:m]
+            k = m
+        assert k + m * n == len(x), "state has %d entries, expected %d" % (len(x), k + m * n)
+        for _ in range(m):
+            milestones.append(list(x[k:k + n]))
+            k += n
+        if hasattr(self.times, '__iter__'):
+            times += list(self.times)
+        if self.qend:
+            milestones.append(list(self.qend))
+            if timed:
+                times.append(self.tend)
+        if self.times is False:
+            M = len(milestones)
+            times = [self.tstart + float(i) / (M - 1) * (self.tend - self.tstart) for i in range(M)]
+        return RobotTrajectory(self.robot, times, milestones)
+
+    def trajectoryToState(self, traj):
+        if self.qstart is not None:
+            assert list(traj.milestones[0]) == list(self.qstart), "Trajectory needs to match the start configuration"
+        if self.qend is not None:
+            assert list(traj.milestones[-1]) == list(self.qend), "Trajectory needs to match the end configuration"
+        sshift = 1 if self.qstart is not None else 0
+        eshift = 1 if self.qend is not None else 0
+        assert len(traj.milestones) == self.numPoints + sshift + eshift, \
+            "Trajectory needs exactly %d non-fixed milestones" % (self.numPoints,)
+        assert traj.times[0] == self.tstart, "Trajectory needs to match the start time"
+        assert traj.times[-1] == self.tend, "Trajectory needs to match the end time"
+        free = traj.milestones[sshift:len(traj.milestones) - eshift]
+        flat = [v for q in free for v in q]
+        if self.times is True:
+            return list(traj.times[sshift:len(traj.times) - eshift]) + flat
+        return flat
+
+    def straightLineState(self):
+        assert self.qstart is not None, "Need a start config for a straight line state"
+        qend = self.qend if self.qend is not None else self.qstart
+        sshift = 1
+        eshift = 1 if self.qend is not None else 0
+        us = [float(i + sshift) / (self.numPoints + sshift + eshift - 1) for i in range(self.numPoints)]
+        qs = [self.robot.interpolate(self.qstart, qend, u) for u in us]
+        ts = [] if self.times is not True else [self.tstart + u * (self.tend - self.tstart) for u in us]
+        return ts + [v for q in qs for v in q]
+
+
+# =================================================================================================
+# objectives (host arithmetic)
+# =================================================================================================
+class ObjectPoseObjective(ObjectiveFunctionInterface):
+    """f(T) = weight*||T.t - Tdes.t||^2 + rotationWeight^2 * weight * angle(T.R,Tdes.R)^2 (gopt:370-391)."""
+
+    def __init__(self, Tdes, weight=1.0, rotationWeight=1.0):
+        self.Tdes = Tdes
+        self.weight = weight
+        self.rotationWeight = rotationWeight
+
+    def value(self, T):
+        err = se3.error(self.Tdes, T)
+        return self.weight * (vectorops.normSquared(err[3:]) + self.rotationWeight ** 2 * vectorops.normSquared(err[0:3]))
+
+    def minstep(self, T):
+        return se3.error(self.Tdes, T)
+
+    def hessian(self, T):
+        w = self.weight
+        return np.array([w * self.rotationWeight ** 2] * 3 + [w] * 3)
+
+    def integrate(self, T, dT):
+        return (so3.mul(so3.from_rotation_vector(dT[:3]), T[0]), vectorops.add(T[1], dT[3:]))
+
+
+class RobotConfigObjective(ObjectiveFunctionInterface):
+    """f(q) = weight*||q - qdes||^2 (gopt:444-455)."""
+
+    def __init__(self, robot, qdes, weight=1.0):
+        self.robot = robot
+        self.qdes = qdes
+        self.weight = weight
+
+    def value(self, q):
+        return self.weight * self.robot.distance(q, self.qdes) ** 2
+
+    def minstep(self, q):
+        return self.robot.interpolateDeriv(q, self.qdes)
+
+
+class TrajectoryLengthObjective(ObjectiveFunctionInterface):
+    """Sum of squared milestone distances; block-tridiagonal Hessian (gopt:512-552)."""
+
+    def __init__(self, trajcache):
+        self.trajcache = trajcache
+        self.hessian_cache = None
+        self.xdes = np.asarray(self.trajcache.straightLineState())
+
+    def value(self, x):
+        traj = self.trajcache.stateToTrajectory(x)
+        ms = np.asarray(traj.milestones, dtype=np.float64)
+        return float(((ms[1:] - ms[:-1]) ** 2).sum())
+
+    def hessian(self, x):
+        if self.hessian_cache is None:
+            tc = self.trajcache
+            n = tc.robot.numLinks()
+            sshift = 1 if tc.qstart is not None else 0
+            eshift = 1 if tc.qend is not None else 0
+            nfree = tc.numPoints
+            nms = nfree + sshift + eshift
+            blocks = [[None] * nfree for _ in range(nfree)]
+            eye = scipy.sparse.identity(n)
+            for i in range(sshift, sshift + nfree):
+                k = i - sshift
+                if i == 0:
+                    blocks[k][k] = 2 * eye
+                    if k + 1 < nfree:
+                        blocks[k][k + 1] = -2 * eye
+                elif i + 1 == nms:
+                    blocks[k][k] = 2 * eye
+                    if k > 0:
+                        blocks[k][k - 1] = -2 * eye
+                else:
+                    blocks[k][k] = 4 * eye
+                    if k > 0:
+                        blocks[k][k - 1] = -2 * eye
+                    if k + 1 < nfree:
+                        blocks[k][k + 1] = -2 * eye
+            self.hessian_cache = scipy.sparse.bmat(blocks, format='csc')
+        return self.hessian_cache
+
+    def minstep(self, x):
+        return (self.xdes - np.asarray(x)) * 0.75
+
+
+# =================================================================================================
+# constraints
+# =================================================================================================
+class ObjectCollisionConstraint(SemiInfiniteConstraintInterface):
+    """signed-distance(T, pt): pt a world point on the environment's cloud, T in SE(3) the pose of
+    the object that owns the SDF (gopt:394-420)."""
+
+    def __init__(self, obj, env):
+        self.obj = obj
+        self.objgeom = PenetrationDepthGeometry(obj if isinstance(obj, (Geometry3D, PenetrationDepthGeometry)) else obj.geometry())
+        self.env = PenetrationDepthGeometry(env)
+
+    def setx(self, T):
+        self.objgeom.setTransform(T)
+
+    def value(self, T, pt):
+        return self.objgeom.distance(pt)[0]
+
+    def minvalue(self, T, bound=None):
+        dmin, cp1, cp2 = self.env._cloud_vs_grid(self.objgeom, bound, want_cp2=False)
+        if bound is not None and dmin >= bound:
+            return []
+        return dmin, cp1
+
+    def df_dx(self, T, pt):
+        return self.df_dx_batch(T, [pt])[0]
+
+    def domain(self):
+        return PenetrationGeometryDomain(self.env)
+
+    # batched protocol extension: one launch for all instantiated parameters
+    def value_batch(self, T, pts):
+        P = np.asarray(pts, dtype=np.float64).reshape(-1, 3)
+        d, _ = self.objgeom.context.pose_rows(self.objgeom._dev.grid_h, self.objgeom._T12, [0, len(P)], P,
+                                              flags=POINT_FLAGS, want_rows=False)
+        return d
+
+    def df_dx_batch(self, T, pts):
+        """rows [ (R(pt - t)) x n , n ] with n = grad1 (gopt:413-418), assembled on the device at
+        the pose given to setx."""
+        P = np.asarray(pts, dtype=np.float64).reshape(-1, 3)
+        _, rows = self.objgeom.context.pose_rows(self.objgeom._dev.grid_h, self.objgeom._T12, [0, len(P)], P, flags=POINT_FLAGS)
+        return rows
+
+
+class RobotLinkCollisionConstraint(SemiInfiniteConstraintInterface):
+    """Collisions between a single robot link and a single static geometry (gopt:457-484)."""
+
+    def __init__(self, link, env, robotcache=None):
+        self.link = link
+        self.robot = robotcache if robotcache is not None else RobotKinematicsCache(link.robot())
+        self.env = PenetrationDepthGeometry(env)
+
+    def setx(self, q):
+        self.robot.set(q)
+
+    def clearx(self):
+        self.robot.clear()
+
+    def value(self, q, pt):
+        return self.robot.geometry[self.link.index].distance(pt)[0]
+
+    def minvalue(self, q, bound=None):
+        # all links of the shared cache are swept against this environment in one launch
+        dmin, idx = self.robot.link_min_distances(self.env)[self.link.index]
+        if idx < 0 or (bound is not None and dmin >= bound):
+            return []
+        p = self.env._dev.cloud32[idx].astype(np.float64)
+        T = self.env._T12.reshape(3, 4)
+        return dmin, [float(v) for v in T[:, :3] @ p + T[:, 3]]
+
+    def df_dx(self, q, pt):
+        return self.df_dx_batch(q, [pt])[0]
+
+    def domain(self):
+        return PenetrationGeometryDomain(self.env)
+
+    def value_batch(self, q, pts):
+        c = self.robot
+        d, _ = c.context.chain_rows(c.robot_h, c.robot.numLinks(), c.link_grids, [c.q], self.link.index, pts,
+                                    flags=POINT_FLAGS, want_rows=False)
+        return d
+
+    def df_dx_batch(self, q, pts):
+        """rows Jp(link-local pt)^T grad1 (gopt:478-482), FK + Jacobian + SDF gradient on the device."""
+        c = self.robot
+        _, rows = c.context.chain_rows(c.robot_h, c.robot.numLinks(), c.link_grids, [c.q], self.link.index, pts,
+                                       flags=POINT_FLAGS)
+        return rows
+
+
+def intervalLipschitzMinimum(a, b, K):
+    """Lower bound over [0,1] of a K-Lipschitz f with f(0)=a, f(1)=b (gopt:554-563)."""
+    if K == 0:
+        return min(a, b)
+    u = (a - b + K) / (2 * K)
+    if u < 0 or u > 1:
+        return min(a - 0.5 * K, b - 0.5 * K)
+    return a - u * K
+
+
+def _dense_time_samples(traj, levels):
+    """Milestones plus, on every edge, the dyadic interior points k / 2^levels -- the finest sample
+    set the reference's time bisection can reach (gopt:802-858: halving stops once the halved
+    duration drops to epsilon = 1e-2, i.e. after 7 levels, k/128).  Returns
+    (q[S,n], t[S], is_milestone[S], edge[S], u[S]); milestones come first, in order."""
+    ms = np.asarray(traj.milestones, dtype=np.float64)
+    times = np.asarray(traj.times, dtype=np.float64)
+    M = len(ms)
+    K = 1 << levels
+    us = np.arange(1, K) / K
+    q_int = ms[:-1, None, :] + us[None, :, None] * (ms[1:, None, :] - ms[:-1, None, :])       # (M-1, K-1, n)
+    t_int = times[:-1, None] + us[None, :] * (times[1:, None] - times[:-1, None])
+    q = np.vstack([ms, q_int.reshape(-1, ms.shape[1])])
+    t = np.concatenate([times, t_int.reshape(-1)])
+    is_ms = np.zeros(len(q), dtype=bool)
+    is_ms[:M] = True
+    edge = np.concatenate([np.arange(M), np.repeat(np.arange(M - 1), K - 1)])
+    u = np.concatenate([np.zeros(M), np.tile(us, M - 1)])
+    return q, t, is_ms, edge, u
+
+
+class _TrajectorySweepMixin:
+    """Shared dense sweep: every (time sample, link) against every environment cloud in one fused
+    FK + K2 launch per environment."""
+
+    def _sweep(self, links, envs, levels):
+        tc = self.trajectory
+        kin = tc.kinematics
+        q, t, is_ms, edge, u = _dense_time_samples(tc.trajectory, levels)
+        best = None
+        for j, env in enumerate(envs):
+            dmin, arg, _ = kin.context.robot_min_distance(kin.robot_h, tc.robot.numLinks(), kin.link_grids, links,
+                                                          env._dev.cloud_h, env._T12, q, flags=BULK_FLAGS)
+            # tie-break like the reference's visiting order: milestones before interior samples
+            # (samples are already ordered that way), then the order of `links`
+            flat = int(np.argmin(dmin))          # first occurrence in (sample, link) order
+            s, k = divmod(flat, len(links))
+            cand = (float(dmin[s, k]), links[k], j, float(t[s]), int(arg[s, k]))
+            if best is None or cand[0] < best[0]:
+                best = cand
+        self.last_sweep_queries = len(q) * len(links) * sum(e._dev.ctx.cloud_size(e._dev.cloud_h) for e in envs)
+        return best
+
+    def _world_point(self, env, idx):
+        p = env._dev.cloud32[idx].astype(np.float64)
+        T = env._T12.reshape(3, 4)
+        return [float(v) for v in T[:, :3] @ p + T[:, 3]]
+
+
+class RobotLinkTrajectoryCollisionConstraint(SemiInfiniteConstraintInterface, _TrajectorySweepMixin):
+    """Collisions along a trajectory between a single link and a single static geometry; the
+    parameter is [t] + world point (gopt:565-675).  The reference's milestone sweep + Lipschitz
+    bisection (which halves down to u = k/64 here, gopt:639-645) is evaluated densely on the device."""
+    LEVELS = 6
+
+    def __init__(self, link, env, trajectorycache):
+        assert isinstance(trajectorycache, RobotTrajectoryCache)
+        self.link = link
+        self.env = env
+        self.trajectory = trajectorycache
+        self.verbose = 0
+
+    def setx(self, x):
+        self.trajectory.set(x)
+
+    def clearx(self):
+        self.trajectory.clear()
+
+    def _rows(self, ts, pts, want_rows):
+        tc = self.trajectory
+        kin = tc.kinematics
+        qs = [tc.trajectory.eval(t) for t in ts]
+        return kin.context.chain_rows(kin.robot_h, tc.robot.numLinks(), kin.link_grids, qs, self.link.index, pts,
+                                      cfg_of_pt=np.arange(len(ts), dtype=np.int32), flags=POINT_FLAGS, want_rows=want_rows)
+
+    def value(self, x, t_pt):
+        return float(self._rows([t_pt[0]], [t_pt[1:4]], False)[0][0])
+
+    def value_batch(self, x, ys):
+        return self._rows([y[0] for y in ys], [y[1:4] for y in ys], False)[0]
+
+    def minvalue(self, x, bound=None):
+        best = self._sweep([self.link.index], [self.env], self.LEVELS)
+        dmin, link, envidx, t, idx = best
+        if idx < 0 or (bound is not None and dmin >= bound):
+            return []
+        return dmin, (t,) + tuple(self._world_point(self.env, idx))
+
+    def df_dx(self, x, t_pt):
+        # the reference returns the configuration-space gradient here (gopt:662-672)
+        return self._rows([t_pt[0]], [t_pt[1:4]], True)[1][0]
+
+    def df_dx_batch(self, x, ys):
+        return list(self._rows([y[0] for y in ys], [y[1:4] for y in ys], True)[1])
+
+    def domain(self):
+        return CartesianProductDomain(IntervalDomain(self.trajectory.tstart, self.trajectory.tend),
+                                      PenetrationGeometryDomain(self.env))
+
+
+class RobotTrajectoryCollisionConstraint(SemiInfiniteConstraintInterface, _TrajectorySweepMixin):
+    """Collisions along a trajectory between the whole robot and one or more static geometries; the
+    6-parameter is [link, env, t] + world point (gopt:678-956).
+
+    minvalue: the reference visits milestones, then bisects time per edge with Lipschitz pruning
+    down to u = k/128; here ALL of those samples x active links are evaluated in one fused
+    FK + K2 launch per environment and reduced to the single deepest (link, env, t, point)."""
+    LEVELS = 7
+
+    def __init__(self, envs, trajectorycache):
+        assert isinstance(trajectorycache, RobotTrajectoryCache)
+        self.robot = trajectorycache.robot
+        self.envs = envs
+        self.trajectory = trajectorycache
+        self.verbose = 0
+        self.epsilon = 1e-2
+        self.activeLinks = []
+        qmin, qmax = self.trajectory.robot.getJointLimits()
+        for i in range(self.trajectory.robot.numLinks()):
+            if qmin[i] < qmax[i]:
+                self.activeLinks.append(i)
+            elif self.verbose:
+                print("RobotTrajectoryCollisionConstraint: ignoring link", i)
+
+    def setx(self, x):
+        self.trajectory.set(x)
+
+    def clearx(self):
+        self.trajectory.clear()
+
+    def _eval(self, ys, want_rows):
+        tc = self.trajectory
+        kin = tc.kinematics
+        qs = [tc.trajectory.eval(y[2]) for y in ys]
+        links = np.array([int(y[0]) for y in ys], dtype=np.int32)
+        pts = [y[3:6] for y in ys]
+        return kin.context.chain_rows(kin.robot_h, tc.robot.numLinks(), kin.link_grids, qs, links, pts,
+                                      cfg_of_pt=np.arange(len(ys), dtype=np.int32), flags=POINT_FLAGS, want_rows=want_rows)
+
+    def value(self, x, y):
+        return float(self._eval([y], False)[0][0])
+
+    def value_batch(self, x, ys):
+        return self._eval(ys, False)[0]
+
+    def minvalue(self, x, bound=None):
+        kin = self.trajectory.kinematics
+        # the reference walks activeLinks[::-1] (gopt:736); keep that order for tie-breaking
+        links = [l for l in self.activeLinks[::-1] if kin.link_grids[l] >= 0]
+        best = self._sweep(links, self.envs, self.LEVELS)
+        dmin, link, envidx, t, idx = best
+        if idx < 0 or (bound is not None and dmin >= bound):
+            return []
+        return dmin, (link, envidx, t) + tuple(self._world_point(self.envs[envidx], idx))
+
+    def _scatter(self, t, dq):
+        """Row of d value / d x for a sample at time t: (1-u) dq into the block of the segment's
+        first milestone, u dq into the next one; fixed endpoints own no block, and samples on the
+        FIRST segment get an all-zero row exactly as the reference computes it (gopt:926-949)."""
+        tc = self.trajectory
+        i, u = tc.trajectory.getSegment(t)
+        m = tc.numPoints
+        n = self.robot.numLinks()
+        sshift = 1 if tc.qstart is not None else 0
+        i -= sshift
+        vals, inds = [], []
+        if i >= 0 and i + 1 <= m:
+            vals.append((1 - u) * dq)
+            inds += list(range(i * n, i * n + n))
+        if i >= 0 and i + 1 < m:
+            vals.append(u * dq)
+            inds += list(range(i * n + n, i * n + 2 * n))
+        if len(vals) == 0:
+            return scipy.sparse.csr_matrix((1, m * n))
+        return scipy.sparse.csr_matrix((np.hstack(vals), inds, [0, len(inds)]), shape=(1, m * n))
+
+    def df_dx(self, x, y):
+        return self.df_dx_batch(x, [y])[0]
+
+    def df_dx_batch(self, x, ys):
+        _, dq = self._eval(ys, True)
+        return [self._scatter(y[2], dq[k]) for k, y in enumerate(ys)]
+
+    def domain(self):
+        return CartesianProductDomain(SetDomain(range(self.robot.numLinks())),
+                                      SetDomain(range(len(self.envs))),
+                                      IntervalDomain(self.trajectory.tstart, self.trajectory.tend),
+                                      UnionDomain([PenetrationGeometryDomain(e) for e in self.envs]))
+
+
+# =================================================================================================
+# front-ends
+# =================================================================================================
+def makeCollisionConstraints(obj, envs, gridres=0, pcres=0):
+    """Builds the collision constraints between obj (RobotModel, RobotKinematicsCache,
+    RobotModelLink, RigidObjectModel or Geometry3D) and one or more static geometries.
+    Returns (constraints, pairs) (gopt:959-1036)."""
+    if not hasattr(envs, '__iter__'):
+        envs = [envs]
+    envgeoms = [None] * len(envs)
+    for i, e in enumerate(envs):
+        if isinstance(e, PenetrationDepthGeometry):
+            envgeoms[i] = e
+        else:
+            g = e if isinstance(e, Geometry3D) else e.geometry()
+            envgeoms[i] = PenetrationDepthGeometry(g, gridres, pcres)
+    if isinstance(obj, RobotModel):
+        return makeCollisionConstraints(RobotKinematicsCache(obj, gridres, pcres), envgeoms, gridres, pcres)
+    if isinstance(obj, RobotKinematicsCache):
+        robot = obj.robot
+        res, pairs = [], []
+        for i in range(robot.numLinks()):
+            link = robot.link(i)
+            if link.geometry() is None or link.geometry().empty():
+                continue
+            res += [RobotLinkCollisionConstraint(link, e, obj) for e in envgeoms]
+            pairs += [(link, e) for e in envs]
+        return res, pairs
+    if isinstance(obj, RobotModelLink):
+        cache = RobotKinematicsCache(obj.robot(), gridres, pcres)
+        return [RobotLinkCollisionConstraint(obj, e, cache) for e in envgeoms], [(obj, e) for e in envs]
+    if isinstance(obj, RigidObjectModel):
+        geom = PenetrationDepthGeometry(obj.geometry(), gridres, pcres)
+        return [ObjectCollisionConstraint(geom, e) for e in envgeoms], [(obj, e) for e in envs]
+    assert isinstance(obj, (Geometry3D, PenetrationDepthGeometry)), "obj must be a robot, link, rigid object, or geometry"
+    geom = obj if isinstance(obj, PenetrationDepthGeometry) else PenetrationDepthGeometry(obj, gridres, pcres)
+    return [ObjectCollisionConstraint(geom, e) for e in envgeoms], [(obj, e) for e in envs]
+
+
+def _format(first, res, want_trace, want_times, want_constraints, trace=None, params=None):
+    if not want_trace and not want_times and not want_constraints:
+        return first
+    out = [first]
+    if want_trace:
+        out.append(res.trace if trace is None else trace)
+    if want_times:
+        out.append(res.trace_times)
+    if want_constraints:
+        out.append(res.instantiated_params if params is None else params)
+    return out
+
+
+def optimizeCollFree(obj, env, Tinit, Tdes=None, settings=None, verbose=1,
+                     want_trace=True, want_times=True, want_constraints=True):
+    """Optimises the pose of `obj` (owner of the SDF) so it is collision-free against `env` (owner
+    of the cloud) and as close as possible to Tdes (gopt:1039-1081).  Returns T, or
+    [T, trace, times, constraint points] according to the want_* flags."""
+    if Tdes is None:
+        Tdes = Tinit
+    objective = ObjectPoseObjective(Tdes)
+    constraint = ObjectCollisionConstraint(obj, env)
+    res = optimizeSemiInfinite(objective, [constraint], Tinit, verbose=verbose, settings=settings)
+    optimizeCollFree.last_result = res
+    return _format(res.x, res, want_trace, want_times, want_constraints, params=res.instantiated_params[0])
+
+
+def optimizeCollFreeRobot(robot, env, qdes=None, qinit=None, objective=None, constraints=None,
+                          settings=None, verbose=1, want_trace=True, want_times=True, want_constraints=True):
+    """Robot configuration closest to qdes that keeps every link collision-free (gopt:1125-1225)."""
+    if settings is None:
+        settings = SemiInfiniteOptimizationSettings()
+        settings.minimum_constraint_value = -0.02
+    if constraints is None:
+        constraints, pairs = makeCollisionConstraints(robot, env)
+    qmin, qmax = robot.getJointLimits()
+    if qinit is None:
+        qinit = robot.getConfig()
+    if qdes is None:
+        if isinstance(qinit, str):
+            raise ValueError("Must specify one of qdes or qinit")
+        qdes = qinit
+        if len(qinit) != robot.numLinks():
+            raise ValueError("Invalid size of initial configuration")
+    if objective is None:
+        objective = RobotConfigObjective(robot, qdes)
+    if isinstance(qinit, str) and qinit in ('random', 'random-collision-free'):
+        lower_bound = 0.0 if qinit == 'random-collision-free' else settings.minimum_constraint_value
+        qinit = [0.0] * robot.numLinks()
+        sampledFeasible = False
+        dbest = -float('inf')
+        qbest = qinit
+        maxSamples = 50
+        for sample in range(maxSamples):
+            rad = float(sample) / (maxSamples - 1)
+            for i in range(len(qdes)):
+                u = (random.uniform(-1, 1) ** 2 + 1) * 0.5
+                vmin = qdes[i] + rad * (qmin[i] - qdes[i])
+                vmax = qdes[i] + rad * (qmax[i] - qdes[i])
+                qinit[i] = vmin + u * (vmax - vmin)
+            gx = [c.eval_minimum(qinit) if isinstance(c, SemiInfiniteConstraintInterface) else c(qinit) for c in constraints]
+            dmin = min(gx)
+            if dmin >= lower_bound:
+                sampledFeasible = True
+                break
+            elif dmin > dbest:
+                dbest = dmin
+                qbest = qinit[:]
+        if not sampledFeasible:
+            if verbose >= 1:
+                print("optimizeCollFreeRobot: Could not generate an initial configuration that respects the minimum constraint value")
+            return qbest, [qbest], [[] for c in constraints]
+    res = optimizeSemiInfinite(objective, constraints, qinit, np.asarray(qmin), np.asarray(qmax), verbose=verbose, settings=settings)
+    optimizeCollFreeRobot.last_result = res
+    return _format(res.x, res, want_trace, want_times, want_constraints)
+
+
+def optimizeCollFreeTrajectory(trajcache, traj0, env, objective=None, constraints=None, greedyStart=False,
+                               settings=None, verbose=1, want_trace=True, want_times=True, want_constraints=True):
+    """Optimises a trajectory subject to collision-free constraints (gopt:1227-1340)."""
+    if settings is None:
+        settings = SemiInfiniteOptimizationSettings()
+        settings.minimum_constraint_value = -0.02
+    robot = trajcache.robot
+    qmin, qmax = robot.getJointLimits()
+    qmin = np.asarray(qmin)
+    qmax = np.asarray(qmax)
+    xinit = trajcache.trajectoryToState(traj0) if isinstance(traj0, Trajectory) else traj0
+    if greedyStart:
+        assert env is not None, "GreedyStart requires the environment to be given"
+        greedyconstraints, pairs = makeCollisionConstraints(trajcache.kinematics, env)
+        traj0 = trajcache.stateToTrajectory(xinit)
+        qlast = traj0.milestones[0]
+        first = 0 if trajcache.qstart is None else 1
+        last = len(traj0.milestones) - (0 if trajcache.qend is None else 1)
+        for i in range(first, last):
+            qobjective = RobotConfigObjective(robot, traj0.milestones[i])
+            r = optimizeSemiInfinite(qobjective, greedyconstraints, qlast, qmin, qmax, verbose=0, settings=settings)
+            traj0.milestones[i] = list(r.x)
+            qlast = list(r.x)
+        xinit = trajcache.trajectoryToState(traj0)
+    xmin = np.hstack([qmin] * trajcache.numPoints)
+    xmax = np.hstack([qmax] * trajcache.numPoints)
+    if objective is None:
+        objective = TrajectoryLengthObjective(trajcache)
+    if constraints is None:
+        if not hasattr(env, '__iter__'):
+            env = [env]
+        env = [e if isinstance(e, PenetrationDepthGeometry) else PenetrationDepthGeometry(e.geometry()) for e in env]
+        constraints = [RobotTrajectoryCollisionConstraint(env, trajcache)]
+    res = optimizeSemiInfinite(objective, constraints, np.asarray(xinit, dtype=np.float64), xmin, xmax, verbose=verbose, settings=settings)
+    optimizeCollFreeTrajectory.last_result = res
+    traj = trajcache.stateToTrajectory(res.x)
+    return _format(traj, res, want_trace, want_times, want_constraints,
+                   trace=[trajcache.stateToTrajectory(v) for v in res.trace] if want_trace else None)

@@ -1,0 +1,279 @@
+"""CPU suite: the oracle against closed-form answers and against its independent numpy restatement,
+the host substrate (so3/se3, trajectories, robot FK), the QP solver, the SIP loop driven by
+oracle-backed constraints, and the C-ABI surface (symbols only -- no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle
+    return oracle
+
+
+# ---- C-ABI surface ----------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol(built):
+    from semiinfiniteoptimization_b200 import _abi
+    hdr = open(os.path.join(ROOT, "include", "sio_abi.h")).read()
+    declared = set(re.findall(r"\b(sio_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_abi.ABI_SYMBOLS)
+    lib = ctypes.CDLL(_abi.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libsio_b200.so does not export %s" % name
+    assert lib.sio_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device(built):
+    """On a box without a GPU the product must fail loudly (SIO_ERR_NODEVICE), never compute."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from semiinfiniteoptimization_b200 import _abi
+    with pytest.raises(_abi.SioError) as e:
+        _abi.Context(0)
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "semiinfiniteoptimization_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+                src = open(os.path.join(dp, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+                assert "liboracle" not in src and "orc_" not in src, fn
+
+
+# ---- oracle: known answers and cross-restatement ----------------------------------------------------
+def test_oracle_c_equals_numpy(O):
+    vg = util.random_grid(3)
+    G = O.Grid(vg.values, vg.bmin, vg.bmax)
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-1, 2, (5000, 3))
+    for T in util.random_poses(1, 4, rot=1.0, trans=0.5):
+        for norm in (True, False):
+            d, g = O.query(G, T, pts, normalize=norm)
+            d2, g2 = O.np_query(vg.values, vg.bmin, vg.bmax, T, pts, normalize=norm)
+            assert np.abs(d - d2).max() < 1e-12
+            assert np.abs(g - g2).max() < 1e-9
+
+
+def test_oracle_sphere_known_answer(O):
+    vg = util.sphere_grid(r=0.7, n=96)
+    G = O.Grid(vg.values, vg.bmin, vg.bmax)
+    rng = np.random.default_rng(1)
+    pts = rng.uniform(-0.9, 0.9, (5000, 3))
+    pts = pts[np.linalg.norm(pts, axis=1) > 0.2]
+    d, g = O.query(G, np.eye(4)[:3].reshape(12), pts)
+    r = np.linalg.norm(pts, axis=1)
+    assert np.abs(d - (r - 0.7)).max() < 2e-3            # O(h^2) trilinear error, h = 2/96
+    assert np.abs(g - pts / r[:, None]).max() < 5e-2
+    # exact at sample positions
+    h = vg.cell
+    c = vg.bmin + (np.array([10, 20, 30]) + 0.5) * h
+    assert abs(O.query(G, np.eye(4)[:3].reshape(12), [c], want_grad=False)[0] - vg.values[10, 20, 30]) < 1e-12
+
+
+def test_oracle_outside_bbox_adds_distance(O):
+    """Appendix A.2 step 2/4: d = v(clamp(p)) + |p - clamp(p)|, gradient = outward unit vector there."""
+    from semiinfiniteoptimization_b200._host.geometry import analytic_sdf_grid
+    vg = analytic_sdf_grid(lambda P: np.zeros(P.shape[:-1]) + 0.25, [0, 0, 0], [1, 1, 1], (4, 4, 4))
+    G = O.Grid(vg.values, vg.bmin, vg.bmax)
+    d, g = O.query(G, np.eye(4)[:3].reshape(12), [[2.0, 0.5, 0.5], [0.5, 0.5, 0.5], [1.0 + 3, 1.0 + 4, 0.5]])
+    assert np.allclose(d, [1.25, 0.25, 5.25])
+    assert np.allclose(g[0], [1, 0, 0]) and np.allclose(g[1], 0) and np.allclose(g[2], [0.6, 0.8, 0])
+
+
+def test_oracle_gradient_matches_finite_differences(O):
+    """The reference's own gradient check (utils.py:39-51: h=1e-4, eps=1e-3), on the raw gradient."""
+    geom = util.fixture_geometry("m1062")
+    vg = geom.convert("VolumeGrid", 0.02).getVolumeGrid()
+    G = O.Grid(vg.values, vg.bmin, vg.bmax)
+    rng = np.random.default_rng(2)
+    pts = vg.bmin + rng.uniform(0.05, 0.95, (3000, 3)) * (vg.bmax - vg.bmin)
+    T = util.random_poses(3, 1, rot=0.4, trans=0.02)[0]
+    d, g = O.query(G, T, pts, normalize=False)
+    h = 1e-6
+    fd = np.stack([(O.query(G, T, pts + h * e, want_grad=False) - O.query(G, T, pts - h * e, want_grad=False)) / (2 * h)
+                   for e in np.eye(3)], axis=1)
+    err = np.abs(fd - g).max(axis=1)
+    assert np.quantile(err, 0.98) < 1e-3           # points straddling a cell face see a kink
+
+
+def test_oracle_min_distance_and_value_consistency(O):
+    """sip.py:223-230's (commented) probe: value(x, argmin) == dmin."""
+    vg = util.fixture_geometry("cube").convert("VolumeGrid", 0.05).getVolumeGrid()
+    G = O.Grid(vg.values, vg.bmin, vg.bmax)
+    cloud = util.fixture_geometry("m797").convert("PointCloud", 0.02).getPointCloud().points.astype(np.float32)
+    T = util.invert12(util.random_poses(4, 6, rot=0.3, trans=0.3, center=(0.2, 0.2, 0.2)))
+    dmin, arg = O.min_distance(G, cloud, T)
+    dn, an = O.np_min_distance(vg.values, vg.bmin, vg.bmax, cloud, T)
+    assert np.array_equal(arg, an) and np.abs(dmin - dn).max() < 1e-12
+    for b in range(len(T)):
+        v = O.query(G, T[b], [cloud[arg[b]].astype(np.float64)], want_grad=False)[0]
+        assert abs(v - dmin[b]) < 1e-12
+    # bound semantics: argmin = -1 iff dmin >= bound
+    bound = np.full(len(T), np.median(dmin))
+    d2, a2 = O.min_distance(G, cloud, T, bound=bound)
+    assert np.array_equal(a2 >= 0, dmin < bound) and np.array_equal(d2, dmin)
+
+
+def test_oracle_fk_and_chain_rows_vs_host_model(O):
+    from semiinfiniteoptimization_b200._host.robot import load_arc_robot
+    robot = load_arc_robot()
+    R = O.Robot(robot.parents, robot.tparent, robot.axes, robot.jtypes)
+    rng = np.random.default_rng(5)
+    qs = np.array([[rng.uniform(lo, hi) if hi > lo else lo for lo, hi in zip(robot.qmin, robot.qmax)] for _ in range(10)])
+    Tfk = O.fk(R, qs)
+    for k, q in enumerate(qs):
+        robot.setConfig(q)
+        assert np.abs(Tfk[k].reshape(7, 3, 4) - robot.link_T).max() < 1e-12
+    # Jacobian rows: oracle C vs the host model's getPositionJacobian
+    link = 5
+    vg = robot.link(link).geometry().convert("VolumeGrid", 0.02).getVolumeGrid()
+    G = O.Grid(vg.values, vg.bmin, vg.bmax)
+    q = qs[0]
+    robot.setConfig(q)
+    pts = np.array([robot.link(link).getWorldPosition(p) for p in rng.uniform(-0.2, 0.2, (20, 3))])
+    d, rows = O.chain_rows(R, link, G, q, pts)
+    Tl = robot.link_T[link]
+    Ti = np.concatenate([Tl[:, :3].T, (-Tl[:, :3].T @ Tl[:, 3])[:, None]], axis=1).reshape(12)
+    d0, g0 = O.query(G, Ti, pts)
+    assert np.abs(d - d0).max() < 1e-12
+    for i, p in enumerate(pts):
+        Jp = np.array(robot.link(link).getPositionJacobian(robot.link(link).getLocalPosition(p)))
+        assert np.abs(rows[i] - Jp.T @ (-g0[i])).max() < 1e-10
+    # finite-difference check of the kinematic Jacobian itself
+    lp = robot.link(link).getLocalPosition(pts[0])
+    Jp = np.array(robot.link(link).getPositionJacobian(lp))
+    for j in range(1, 7):
+        dq = np.zeros(7)
+        dq[j] = 1e-6
+        robot.setConfig(q + dq)
+        p1 = np.array(robot.link(link).getWorldPosition(lp))
+        robot.setConfig(q - dq)
+        p0 = np.array(robot.link(link).getWorldPosition(lp))
+        assert np.abs((p1 - p0) / 2e-6 - Jp[:, j]).max() < 1e-6
+
+
+# ---- host substrate -------------------------------------------------------------------------------------
+def test_so3_se3_conventions():
+    from semiinfiniteoptimization_b200._host import se3, so3
+    R = so3.from_rotation_vector([0.2, -0.4, 0.7])
+    M = so3.matrix(R)
+    assert np.allclose(M @ M.T, np.eye(3)) and np.isclose(np.linalg.det(M), 1)
+    assert np.allclose(so3.apply(R, [1, 2, 3]), M @ [1, 2, 3])          # column-major 9-list
+    assert np.allclose(so3.rotation_vector(R), [0.2, -0.4, 0.7])
+    T1 = (R, [0.1, 0.2, 0.3])
+    T2 = (so3.from_rotation_vector([-0.1, 0.3, 0.2]), [1, -1, 0.5])
+    e = se3.error(T1, T2)
+    assert np.allclose(so3.matrix(so3.from_rotation_vector(e[:3])) @ so3.matrix(T2[0]), M)   # exp(e) R2 = R1
+    assert np.allclose(e[3:], np.subtract(T1[1], T2[1]))
+    assert np.allclose(se3.apply(se3.inv(T1), se3.apply(T1, [3, 2, 1])), [3, 2, 1])
+    A = se3.to_rowmajor12(T1)
+    assert np.allclose(A.reshape(3, 4)[:, :3], M) and np.allclose(se3.to_rowmajor12(se3.from_rowmajor12(A)), A)
+
+
+def test_trajectory_segments_and_remesh():
+    from semiinfiniteoptimization_b200._host.trajectory import Trajectory
+    tr = Trajectory([0, 1, 3], [[0, 0], [1, 2], [3, 2]])
+    assert tr.eval(0.5) == [0.5, 1.0] and tr.eval(2) == [2.0, 2.0]
+    assert tr.eval(-1) == [0, 0] and tr.eval(9) == [3, 2]
+    assert tr.getSegment(0.25) == (0, 0.25) and tr.getSegment(3) == (2, 0)
+    tr2, idx = tr.remesh([0, 0.5, 1, 2, 3])
+    assert tr2.times == [0, 0.5, 1, 2, 3] and tr2.milestones[3] == [2.0, 2.0] and idx == [0, 1, 2, 3, 4]
+
+
+def test_mesh_conversions_are_deterministic_and_sane():
+    g = util.fixture_geometry("cube")
+    vg = g.convert("VolumeGrid", 0.05).getVolumeGrid()
+    assert vg.dims == (30, 30, 30) and np.allclose(vg.cell, 0.05)
+    # exact SDF of the unit cube at cell centres
+    ax = [vg.bmin[a] + (np.arange(30) + 0.5) * 0.05 for a in range(3)]
+    P = np.stack(np.meshgrid(*ax, indexing="ij"), -1)
+    assert np.abs(vg.values - util.box_sdf(P - 0.5, [0.5] * 3)).max() < 1e-6
+    pc = g.convert("PointCloud", 0.02).getPointCloud()
+    assert 14000 < pc.numPoints() < 17000
+    assert np.abs(util.box_sdf(pc.points - 0.5, [0.5] * 3)).max() < 1e-9            # samples lie on the surface
+    pc2 = util.fixture_geometry("cube").convert("PointCloud", 0.02).getPointCloud()
+    assert np.array_equal(pc.points, pc2.points)
+
+
+# ---- QP -------------------------------------------------------------------------------------------------------
+def test_qp_matches_kkt_on_random_problems():
+    from semiinfiniteoptimization_b200._host import qp
+    rng = np.random.default_rng(7)
+    for trial in range(20):
+        n, m = 6, rng.integers(1, 12)
+        W = rng.uniform(0.1, 2, n)
+        xdes = rng.normal(size=n)
+        A = rng.normal(size=(m, n))
+        b = rng.normal(size=m) * 0.3
+        P = np.diag(W + 1e-3)
+        q = -W * xdes
+        Afull = np.vstack([A, np.eye(n)])
+        l = np.concatenate([-b + 1e-3, -0.5 * np.ones(n)])
+        u = np.concatenate([np.full(m, np.inf), 0.5 * np.ones(n)])
+        r = qp.solve_qp(P, q, Afull, l, u)
+        if r.status != "solved":
+            continue
+        x = r.x
+        assert np.all(Afull @ x >= l - 1e-4) and np.all(Afull @ x <= u + 1e-4)
+        # optimality: no feasible descent direction found by projected random probing
+        f = lambda v: 0.5 * v @ P @ v + q @ v
+        for _ in range(200):
+            dxx = rng.normal(size=n) * 1e-3
+            xn = x + dxx
+            if np.all(Afull @ xn >= l) and np.all(Afull @ xn <= u):
+                assert f(xn) >= f(x) - 1e-7
+
+
+def test_qp_detects_infeasibility():
+    from semiinfiniteoptimization_b200._host import qp
+    P = np.eye(2)
+    r = qp.solve_qp(P, np.zeros(2), np.array([[1.0, 0], [1.0, 0]]), np.array([1.0, -np.inf]), np.array([np.inf, 0.0]))
+    assert r.status == "primal infeasible" and r.x is None
+
+
+# ---- SIP loop on oracle-backed constraints (host logic) -----------------------------------------------------------
+def test_sip_resolves_cube_vs_chair_penetration(O):
+    from oracle.ref_geometryopt import RefObjectCollisionConstraint, RefPDG
+    from semiinfiniteoptimization_b200 import sip
+    from semiinfiniteoptimization_b200._host import so3
+    from semiinfiniteoptimization_b200.geometryopt import ObjectPoseObjective
+    cube = RefPDG(util.fixture_geometry("cube"), 0.05, 0.02)
+    chair = RefPDG(util.fixture_geometry("m797"), 0.05, 0.02)
+    chair.setTransform((so3.identity(), [1.2, 0, 0]))
+    T = (so3.from_rotation_vector([0.1, -0.2, 0.15]), [0.7, 0.1, 0.2])
+    c = RefObjectCollisionConstraint(cube, chair)
+    assert c.eval_minimum(T) < -0.05                       # starts in deep penetration
+    res = sip.optimizeSemiInfinite(ObjectPoseObjective(T), [c], T, verbose=0)
+    assert min(res.gx) > -5e-3                             # the reference's own feasibility threshold (sip.py:1227)
+    assert c.eval_minimum(res.x) > -5e-3
+    assert len(res.trace) == len(res.trace_times) and res.trace[0] is T
+
+
+def test_sip_reference_quirks():
+    """No rows -> the QP returns xdes ignoring the trust region (sip.py:288); exclusion hash truncates toward zero."""
+    from semiinfiniteoptimization_b200 import sip
+    cd = sip.ConstraintGenerationData([object()])
+    assert np.array_equal(cd.solve_qp(1.0, np.array([5.0, -7.0]), [], [], np.array([-.5, -.5]), np.array([.5, .5])), [5.0, -7.0])
+    assert cd.instantiate(0, (0.0004, -0.0004, 1.0)) is True
+    assert cd.instantiate(0, (-0.0009, 0.0009, 1.0003)) is False       # int() truncation merges across zero
+    assert cd.instantiate(0, (0.0011, 0.0, 1.0)) is True
+
+
+def test_interval_lipschitz_minimum():
+    from oracle.ref_geometryopt import intervalLipschitzMinimum as f
+    assert f(1.0, 2.0, 0) == 1.0
+    assert np.isclose(f(1.0, 1.0, 2.0), 0.0)          # u = 1/2 -> a - K/2
+    assert np.isclose(f(0.0, 5.0, 1.0), -0.5)         # u outside [0,1]
