@@ -77,52 +77,68 @@ def build_workload(rank=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region.  Uses NVML (the library
+    nvidia-smi itself queries -- same counters as the B200_PROFILING.md clocks line) from a thread,
+    because an nvidia-smi subprocess polling every 100 ms was seen to stall CUDA calls."""
+    REASONS = {0x08: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x04: "sw_power_cap"}
 
-    def __init__(self, device):
-        self.device = device
-        self.proc = None
-        self.lines = []
+    def __init__(self, device, period_s=0.005):
+        self.device, self.period = device, period_s
+        self.sm, self.reasons, self.smax, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self.th = None
+        self.err = None
+
+    def _nvml_index(self, pynvml):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.device < len(ids) and ids[self.device].isdigit():
+                return int(ids[self.device])
+        return self.device
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index(pynvml))
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:
+            self.err = "nvml unavailable: %s" % e
+            return
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
 
-    def _read(self):
-        for l in self.proc.stdout:
-            self.lines.append(l.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, name in self.REASONS.items():
+            if r & bit:
+                self.reasons.add(name)
         try:
-            self.proc.wait(timeout=5)
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
         except Exception:
             pass
-        sm, smax, reasons = [], None, set()
-        for l in self.lines:
-            f = [x.strip() for x in l.split(",")]
-            if len(f) < 9:
-                continue
+
+    def _run(self):
+        while not self._stop.is_set():
             try:
-                sm.append(float(f[1]))
-                smax = float(f[2])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                self._sample()
+            except Exception as e:
+                self.err = str(e)
+                return
+            time.sleep(self.period)
+
+    def stop(self):
+        if self.th is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "not sampled"]}
+        self._stop.set()
+        self.th.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None}
 
 
 def cpu_baseline(vg, cloud, T_rel, budget_s=12.0, native=True):
@@ -139,18 +155,20 @@ def cpu_baseline(vg, cloud, T_rel, budget_s=12.0, native=True):
     G = O.Grid(vg.values, vg.bmin, vg.bmax)
     threads = L.orc_max_threads()
     npose = max(1, min(len(T_rel), threads))
-    # calibrate on a slice, then size the sample for ~budget_s
-    n0 = 1 << 16
-    t0 = time.perf_counter()
-    O.min_distance(G, cloud[:n0], T_rel[:npose], L=L)
-    rate = npose * n0 / (time.perf_counter() - t0)
-    npts = int(min(len(cloud), max(n0, rate * budget_s / npose)))
-    t0 = time.perf_counter()
-    O.min_distance(G, cloud[:npts], T_rel[:npose], L=L)
-    dt = time.perf_counter() - t0
-    return {"value": npose * npts / dt, "unit": UNIT, "cores": int(threads), "kind": "port",
-            "sample": "%d poses x %d cloud points of the same sweep, float64 brute force (no hierarchy pruning), %.1f s"
-                      % (npose, npts, dt)}
+    # one pose per thread over the whole cloud, repeated over successive pose groups until ~budget_s
+    O.min_distance(G, cloud[:1 << 14], T_rel[:npose], L=L)        # warm the pages / threads
+    done, t0, k = 0, time.perf_counter(), 0
+    while True:
+        sel = [(k * npose + i) % len(T_rel) for i in range(npose)]
+        O.min_distance(G, cloud, T_rel[sel], L=L)
+        done += npose * len(cloud)
+        k += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s:
+            break
+    return {"value": done / dt, "unit": UNIT, "cores": int(threads), "kind": "port",
+            "sample": "%d sweeps of %d poses x %d cloud points of the same workload, float64 brute force "
+                      "(no hierarchy pruning), %.1f s" % (k, npose, len(cloud), dt)}
 
 
 def run_reference(args):
@@ -204,7 +222,7 @@ def workload_config(ngpu):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -236,15 +254,17 @@ def main():
     dbound = torch.from_numpy(bound).cuda()
     ddmin = torch.empty(B, dtype=torch.float64, device="cuda")
     darg = torch.empty(B, dtype=torch.int64, device="cuda")
-    gathered = [torch.empty(B * 2, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
+    dnu = torch.empty(B, dtype=torch.int32, device="cuda")
+    gathered = [torch.empty(B * 3, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
 
     def step():
-        ctx.min_distance_dev([g], c, dT.data_ptr(), dbound.data_ptr(), B, _abi.SIO_F32, ddmin.data_ptr(), darg.data_ptr())
+        ctx.min_distance_dev([g], c, dT.data_ptr(), dbound.data_ptr(), B, _abi.SIO_F32, ddmin.data_ptr(), darg.data_ptr(),
+                             d_n_under_ptr=dnu.data_ptr())
         if world > 1:
             with torch.cuda.stream(stream):
-                packed = torch.cat([ddmin, darg.to(torch.float64)])
+                packed = torch.cat([ddmin, darg.to(torch.float64), dnu.to(torch.float64)])
                 dist.all_gather(gathered, packed)
 
     for _ in range(args.warmup):
@@ -300,9 +320,10 @@ def main():
         e2e_s = float(t.item())
     n_under = int(nu_h.sum())
     e2e = {"value": queries_per_step * args.steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(B * (96 + 8)), "d2h_bytes_per_step": int(B * 16 + 4 + n_under * 16),
-           "call": "sio_min_distance (host pointers): poses+bounds H2D, dmin/argmin/under-list D2H; geometry resident as in "
-                   "the reference API (PenetrationDepthGeometry builds grid+cloud once)"}
+           "h2d_bytes_per_step": int(B * (96 + 8)), "d2h_bytes_per_step": int(B * (8 + 8 + 4)),
+           "call": "sio_min_distance (host pointers): poses+bounds H2D from a pinned block, dmin/argmin/n_under D2H; geometry "
+                   "resident as in the reference API (PenetrationDepthGeometry builds grid+cloud once); the sorted under-bound "
+                   "list itself stays on the device until sio_under_fetch asks for it"}
 
     if rank == 0:
         bulk = float(np.mean(bulk_ms))

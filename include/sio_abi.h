@@ -105,7 +105,7 @@ int sio_min_distance(sio_ctx* ctx, const sio_handle* grids, int32_t n_grids, con
                      double* dmin, int64_t* argmin, int32_t* n_under);
 int sio_min_distance_dev(sio_ctx* ctx, const sio_handle* grids, int32_t n_grids, const int32_t* d_grid_of_b,
                          sio_handle cloud, const double* dT_rel, const double* d_bound, int64_t B, int flags,
-                         double* d_dmin, int64_t* d_argmin);
+                         double* d_dmin, int64_t* d_argmin, int32_t* d_n_under /* [B] or NULL */);
 /* under-bound list of the LAST sio_min_distance[_dev] call on this context (synchronises).
  * *total = exact number of entries; at most `capacity` are written. */
 int sio_under_fetch(sio_ctx* ctx, int64_t capacity, int64_t* b_out, int64_t* idx_out, double* d_out,

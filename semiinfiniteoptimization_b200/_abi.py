@@ -71,7 +71,7 @@ def load_library():
     L.sio_cloud_query_dev.argtypes = [P, I32, I32, P, I64, C.c_int, P, P]
     L.sio_cloud_perm.argtypes = [P, I32, P]
     L.sio_min_distance.argtypes = [P, P, I32, P, I32, P, P, I64, C.c_int, P, P, P]
-    L.sio_min_distance_dev.argtypes = [P, P, I32, P, I32, P, P, I64, C.c_int, P, P]
+    L.sio_min_distance_dev.argtypes = [P, P, I32, P, I32, P, P, I64, C.c_int, P, P, P]
     L.sio_under_fetch.argtypes = [P, I64, P, P, P, C.POINTER(I64)]
     L.sio_pose_rows.argtypes = [P, I32, P, P, I64, P, C.c_int, P, P]
     L.sio_robot_create.argtypes = [P, I32, P, P, P, P, C.POINTER(I32)]
@@ -199,10 +199,11 @@ class Context:
                                          int(flags), dmin.ctypes.data, arg.ctypes.data, _ptr(nu)))
         return dmin, arg, nu
 
-    def min_distance_dev(self, grids, cloud, dT_rel_ptr, d_bound_ptr, B, flags, d_dmin_ptr, d_argmin_ptr, d_gob_ptr=None):
+    def min_distance_dev(self, grids, cloud, dT_rel_ptr, d_bound_ptr, B, flags, d_dmin_ptr, d_argmin_ptr, d_gob_ptr=None,
+                         d_n_under_ptr=None):
         ga = np.ascontiguousarray(grids, dtype=np.int32)
         self._ck(self.L.sio_min_distance_dev(self.h, ga.ctypes.data, len(ga), d_gob_ptr, cloud, dT_rel_ptr, d_bound_ptr, int(B),
-                                             int(flags), d_dmin_ptr, d_argmin_ptr))
+                                             int(flags), d_dmin_ptr, d_argmin_ptr, d_n_under_ptr))
 
     def under_fetch(self, capacity=1 << 20):
         b = np.empty(capacity, dtype=np.int64)

@@ -73,6 +73,7 @@ struct HostBuf {
 struct GridH {
     bool live = false;
     float* d_v = nullptr;
+    float* d_brick = nullptr;
     GridDev meta{};
     GridDev* d_meta = nullptr;     // single-element device copy (K1 kernels take a pointer)
 };
@@ -110,6 +111,9 @@ struct sio_ctx {
     DevBuf s_xf, s_keys, s_gridtab, s_cand, s_cnt, s_in0, s_in1, s_in2, s_in3, s_out0, s_out1, s_out2, s_tlinks, s_trel, s_gob;
     HostBuf h_a, h_b, h_c;
     uint32_t cand_cap = 1u << 20;
+    GridDev single_grid_host{};       // host copy handed to the single-grid bulk kernel by value
+    std::vector<sio_handle> staged_grids;   // handles whose table currently sits in s_gridtab (grids are immutable)
+    double staged_tau = 0.0;
     // state of the last min-distance call (for sio_under_fetch)
     bool under_valid = false, under_pending = false, under_final = false;
     std::vector<UnderEntry> under;
@@ -188,7 +192,7 @@ int sio_ctx_destroy(sio_ctx* c) {
     if (!c) return SIO_OK;
     DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
-    for (auto& g : c->grids) if (g.live) { cudaFree(g.d_v); cudaFree(g.d_meta); }
+    for (auto& g : c->grids) if (g.live) { cudaFree(g.d_v); cudaFree(g.d_brick); cudaFree(g.d_meta); }
     for (auto& p : c->clouds) if (p.live) { cudaFree(p.d_pts); cudaFree(p.d_perm); }
     for (auto& r : c->robots) if (r.live) { cudaFree(r.d_parent); cudaFree(r.d_jtype); cudaFree(r.d_tparent); cudaFree(r.d_axis); }
     DevBuf* bufs[] = {&c->s_xf, &c->s_keys, &c->s_gridtab, &c->s_cand, &c->s_cnt, &c->s_in0, &c->s_in1, &c->s_in2, &c->s_in3,
@@ -243,15 +247,30 @@ int sio_grid_create(sio_ctx* c, const float* values, const int32_t dims[3], cons
         if (!(v == v)) return fail(SIO_ERR_INVALID, "sio_grid_create: NaN sample at flat index %zu", k);
         vmin = std::min(vmin, v); vmax = std::max(vmax, v);
     }
+    // 8-corner bricks: one 32-byte record per cell (i0 in [0, dim-1]; corner +1 comes from the padded copy)
+    std::vector<float> brick((size_t)nx * ny * nz * 8);
+    for (int i = 0; i < nx; ++i)
+        for (int j = 0; j < ny; ++j)
+            for (int k = 0; k < nz; ++k) {
+                float* dst = brick.data() + (((size_t)i * ny + j) * nz + k) * 8;
+                for (int di = 0; di < 2; ++di)
+                    for (int dj = 0; dj < 2; ++dj)
+                        for (int dk = 0; dk < 2; ++dk)
+                            dst[di * 4 + dj * 2 + dk] = pad[((size_t)(i + di) * py + (j + dj)) * pz + (k + dk)];
+            }
     GridH g;
     CU(cudaMalloc(&g.d_v, pad.size() * sizeof(float)));
     CU(cudaMemcpyAsync(g.d_v, pad.data(), pad.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMalloc(&g.d_brick, brick.size() * sizeof(float)));
+    CU(cudaMemcpyAsync(g.d_brick, brick.data(), brick.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     g.meta.v = g.d_v;
+    g.meta.brick = g.d_brick;
     g.meta.nx = nx; g.meta.ny = ny; g.meta.nz = nz;
     g.meta.sy = pz; g.meta.sx = py * pz;
     for (int a = 0; a < 3; ++a) {
         g.meta.bmin[a] = bmin[a]; g.meta.bmax[a] = bmax[a];
         g.meta.h[a] = (bmax[a] - bmin[a]) / (double)dims[a];
+        g.meta.ih[a] = 1.0 / g.meta.h[a];
     }
     g.meta.vmin = vmin; g.meta.vmax = vmax;
     CU(cudaMalloc(&g.d_meta, sizeof(GridDev)));
@@ -267,8 +286,9 @@ int sio_grid_destroy(sio_ctx* c, sio_handle h) {
     if (!c || !grid_ok(c, h)) return fail(SIO_ERR_INVALID, "sio_grid_destroy: bad handle %d", h);
     DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->grids[h].d_v); cudaFree(c->grids[h].d_meta);
+    cudaFree(c->grids[h].d_v); cudaFree(c->grids[h].d_brick); cudaFree(c->grids[h].d_meta);
     c->grids[h] = GridH();
+    c->staged_grids.clear();
     return SIO_OK;
 }
 
@@ -304,7 +324,9 @@ int sio_cloud_create(sio_ctx* c, const float* xyz, int64_t n, sio_handle* out) {
         pts[i] = make_float4(xyz[3 * s], xyz[3 * s + 1], xyz[3 * s + 2], 0.f);
         p.perm[i] = s;
     }
-    for (int64_t i = n; i < npad; ++i) pts[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // pad to a whole tile with copies of the last point: the bulk kernel needs no bounds test, a duplicate
+    // cannot lower a minimum, and the fp64 stages only ever look at indices < n
+    for (int64_t i = n; i < npad; ++i) pts[i] = n > 0 ? pts[n - 1] : make_float4(0.f, 0.f, 0.f, 0.f);
     CU(cudaMalloc(&p.d_pts, pts.size() * sizeof(float4)));
     CU(cudaMalloc(&p.d_perm, p.perm.size() * sizeof(int32_t)));
     CU(cudaMemcpyAsync(p.d_pts, pts.data(), pts.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
@@ -364,6 +386,11 @@ int sio_query(sio_ctx* c, sio_handle grid, const double T[12], const double* pts
 // builds the device grid table for a call; returns the automatic tau through *tau
 static int stage_grid_table(sio_ctx* c, const sio_handle* grids, int32_t n_grids, double* tau) {
     if (n_grids <= 0 || !grids) return fail(SIO_ERR_INVALID, "no grids given");
+    if ((int)c->staged_grids.size() == n_grids && std::equal(grids, grids + n_grids, c->staged_grids.begin())) {
+        *tau = c->tau > 0 ? c->tau : c->staged_tau;
+        return SIO_OK;                      // same table as the previous call: nothing to copy
+    }
+    c->staged_grids.clear();
     std::vector<GridDev> tab((size_t)n_grids);
     for (int i = 0; i < n_grids; ++i) {
         if (!grid_ok(c, grids[i])) return fail(SIO_ERR_INVALID, "bad grid handle %d at position %d", grids[i], i);
@@ -372,7 +399,9 @@ static int stage_grid_table(sio_ctx* c, const sio_handle* grids, int32_t n_grids
     CU(c->s_gridtab.ensure(tab.size() * sizeof(GridDev)));
     // pageable -> device copy of a stack/vector object: synchronous w.r.t. the host, so `tab` may die
     CU(cudaMemcpyAsync(c->s_gridtab.p, tab.data(), tab.size() * sizeof(GridDev), cudaMemcpyHostToDevice, c->stream));
-    *tau = c->tau > 0 ? c->tau : auto_tau(tab.data(), n_grids);
+    c->staged_tau = auto_tau(tab.data(), n_grids);
+    c->staged_grids.assign(grids, grids + n_grids);
+    *tau = c->tau > 0 ? c->tau : c->staged_tau;
     return SIO_OK;
 }
 
@@ -402,7 +431,7 @@ int sio_cloud_query_dev(sio_ctx* c, sio_handle grid, sio_handle cloud, const dou
 // ---- K2 ----------------------------------------------------------------------------------------------
 int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, const int32_t* d_grid_of_b,
                          sio_handle cloud, const double* dT_rel, const double* d_bound, int64_t B, int flags,
-                         double* d_dmin, int64_t* d_argmin) {
+                         double* d_dmin, int64_t* d_argmin, int32_t* d_n_under) {
     if (!c || !cloud_ok(c, cloud) || B < 0 || (B > 0 && (!dT_rel || !d_dmin || !d_argmin)))
         return fail(SIO_ERR_INVALID, "sio_min_distance_dev: bad argument");
     if (B >= (1LL << 31)) return fail(SIO_ERR_INVALID, "sio_min_distance_dev: B too large");
@@ -427,18 +456,19 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
     CU(c->s_cnt.ensure(sizeof(uint32_t)));
     CU(c->s_cand.ensure((size_t)c->cand_cap * sizeof(Cand)));
     CU(cudaMemsetAsync(c->s_cnt.p, 0, sizeof(uint32_t), st));
+    if (d_n_under) CU(cudaMemsetAsync(d_n_under, 0, (size_t)B * sizeof(int32_t), st));
     MinArgs a{};
     a.pts = p.d_pts; a.perm = p.d_perm; a.N = p.n;
     a.grids = c->s_gridtab.as<GridDev>(); a.grid_of_b = d_grid_of_b;
+    a.single_grid = nullptr;
+    if (n_grids == 1) { c->single_grid_host = c->grids[grids[0]].meta; a.single_grid = &c->single_grid_host; }
     a.T_rel = dT_rel; a.bound = d_bound; a.B = B; a.tau = tau; a.ntiles = ntiles;
     a.cand = c->s_cand.as<Cand>(); a.cand_count = c->s_cnt.as<uint32_t>(); a.cand_cap = c->cand_cap;
+    a.n_under = d_bound ? d_n_under : nullptr;
     a.dmin = d_dmin; a.argmin = d_argmin;
     if (!f64) {
-        CU(c->s_xf.ensure((size_t)B * sizeof(XfRec)));
         CU(c->s_keys.ensure((size_t)std::max<int64_t>(1, Bc * nsub) * sizeof(uint32_t)));
-        a.xf = c->s_xf.as<XfRec>(); a.subkeys = c->s_keys.as<uint32_t>();
-        launch_prep_xf(a, st);
-        c->launches += 1;
+        a.subkeys = c->s_keys.as<uint32_t>();
     }
     c->bulk_timed = false;
     const bool one_batch = Bc >= B;
@@ -500,46 +530,54 @@ int sio_under_fetch(sio_ctx* c, int64_t capacity, int64_t* b_out, int64_t* idx_o
     return (*total > capacity && capacity > 0) ? fail(SIO_ERR_OVERFLOW, "under list has %lld entries, capacity %lld", (long long)*total, (long long)capacity) : SIO_OK;
 }
 
+// host-pointer K2: inputs are packed into one pinned block and sent with ONE H2D copy; outputs come back
+// with ONE D2H copy:   in  = [T_rel B*12 f64 | bound B f64 | grid_of_b B i32]
+//                      out = [dmin B f64 | argmin B i64 | n_under B i32]
+static int min_distance_host(sio_ctx* c, const sio_handle* grids, int32_t n_grids, const int32_t* grid_of_b, sio_handle cloud,
+                             const double* T_rel, const double* bound, int64_t B, int flags, double* dmin, int64_t* argmin,
+                             int32_t* n_under) {
+    cudaStream_t st = c->stream;
+    const size_t oT = 0, oB = (size_t)B * 96, oG = oB + (size_t)B * 8, in_bytes = oG + (size_t)B * 4;
+    const size_t oD = 0, oA = (size_t)B * 8, oN = oA + (size_t)B * 8, out_bytes = oN + (size_t)B * 4;
+    CU(c->h_a.ensure(in_bytes));
+    CU(c->h_b.ensure(out_bytes));
+    CU(c->s_in0.ensure(in_bytes));
+    CU(c->s_out0.ensure(out_bytes));
+    char* hin = c->h_a.as<char>();
+    std::memcpy(hin + oT, T_rel, (size_t)B * 96);
+    if (bound) std::memcpy(hin + oB, bound, (size_t)B * 8);
+    if (grid_of_b) {
+        for (int64_t b = 0; b < B; ++b)
+            if (grid_of_b[b] < 0 || grid_of_b[b] >= n_grids) return fail(SIO_ERR_INVALID, "grid_of_b[%lld]=%d out of range", (long long)b, grid_of_b[b]);
+        std::memcpy(hin + oG, grid_of_b, (size_t)B * 4);
+    }
+    CU(cudaMemcpyAsync(c->s_in0.p, hin, in_bytes, cudaMemcpyHostToDevice, st));
+    char* din = c->s_in0.as<char>();
+    char* dout = c->s_out0.as<char>();
+    int rc = sio_min_distance_dev(c, grids, n_grids, grid_of_b ? reinterpret_cast<const int32_t*>(din + oG) : nullptr, cloud,
+                                  reinterpret_cast<const double*>(din + oT), bound ? reinterpret_cast<const double*>(din + oB) : nullptr,
+                                  B, flags, reinterpret_cast<double*>(dout + oD), reinterpret_cast<int64_t*>(dout + oA),
+                                  reinterpret_cast<int32_t*>(dout + oN));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_b.p, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const char* hout = c->h_b.as<char>();
+    std::memcpy(dmin, hout + oD, (size_t)B * 8);
+    std::memcpy(argmin, hout + oA, (size_t)B * 8);
+    if (n_under) {
+        if (bound) std::memcpy(n_under, hout + oN, (size_t)B * 4);
+        else std::memset(n_under, 0, (size_t)B * 4);
+    }
+    return SIO_OK;
+}
+
 int sio_min_distance(sio_ctx* c, const sio_handle* grids, int32_t n_grids, const int32_t* grid_of_b, sio_handle cloud,
                      const double* T_rel, const double* bound, int64_t B, int flags, double* dmin, int64_t* argmin,
                      int32_t* n_under) {
     if (!c || B < 0 || (B > 0 && (!T_rel || !dmin || !argmin))) return fail(SIO_ERR_INVALID, "sio_min_distance: bad argument");
     DeviceGuard guard(c->device);
     if (B == 0) { c->under.clear(); c->under_valid = true; return SIO_OK; }
-    cudaStream_t st = c->stream;
-    CU(c->s_in0.ensure((size_t)B * 12 * sizeof(double)));
-    CU(c->s_out0.ensure((size_t)B * sizeof(double)));
-    CU(c->s_out1.ensure((size_t)B * sizeof(int64_t)));
-    CU(cudaMemcpyAsync(c->s_in0.p, T_rel, (size_t)B * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
-    const double* d_bound = nullptr;
-    if (bound) {
-        CU(c->s_in1.ensure((size_t)B * sizeof(double)));
-        CU(cudaMemcpyAsync(c->s_in1.p, bound, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st));
-        d_bound = c->s_in1.as<double>();
-    }
-    const int32_t* d_gob = nullptr;
-    if (grid_of_b) {
-        for (int64_t b = 0; b < B; ++b)
-            if (grid_of_b[b] < 0 || grid_of_b[b] >= n_grids) return fail(SIO_ERR_INVALID, "grid_of_b[%lld]=%d out of range", (long long)b, grid_of_b[b]);
-        CU(c->s_in2.ensure((size_t)B * sizeof(int32_t)));
-        CU(cudaMemcpyAsync(c->s_in2.p, grid_of_b, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        d_gob = c->s_in2.as<int32_t>();
-    }
-    int rc = sio_min_distance_dev(c, grids, n_grids, d_gob, cloud, c->s_in0.as<double>(), d_bound, B, flags,
-                                  c->s_out0.as<double>(), c->s_out1.as<int64_t>());
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(dmin, c->s_out0.p, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(argmin, c->s_out1.p, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (n_under) {
-        std::memset(n_under, 0, sizeof(int32_t) * (size_t)B);
-        if (bound) {
-            rc = collect_under(c);
-            if (rc) return rc;
-            for (const auto& u : c->under) n_under[u.b] += 1;
-        }
-    }
-    return SIO_OK;
+    return min_distance_host(c, grids, n_grids, grid_of_b, cloud, T_rel, bound, B, flags, dmin, argmin, n_under);
 }
 
 // ---- K3 ----------------------------------------------------------------------------------------------
@@ -649,6 +687,7 @@ int sio_chain_rows(sio_ctx* c, sio_handle robot, const sio_handle* link_grids, c
         if (l < 0 || l >= r.n || slot[l] < 0) return fail(SIO_ERR_INVALID, "sio_chain_rows: point %lld on link %d which has no grid", (long long)i, l);
         if (cfg_of_pt && (cfg_of_pt[i] < 0 || cfg_of_pt[i] >= n_cfg)) return fail(SIO_ERR_INVALID, "sio_chain_rows: cfg_of_pt[%lld] out of range", (long long)i);
     }
+    c->staged_grids.clear();
     CU(c->s_gridtab.ensure(tab.size() * sizeof(GridDev)));
     CU(cudaMemcpyAsync(c->s_gridtab.p, tab.data(), tab.size() * sizeof(GridDev), cudaMemcpyHostToDevice, st));
     CU(c->s_gob.ensure((size_t)r.n * sizeof(int32_t)));
@@ -719,20 +758,15 @@ int sio_robot_min_distance(sio_ctx* c, sio_handle robot, const sio_handle* link_
     }
     CU(c->s_out0.ensure((size_t)B * sizeof(double)));
     CU(c->s_out1.ensure((size_t)B * sizeof(int64_t)));
+    CU(c->s_out2.ensure((size_t)B * sizeof(int32_t)));
     int rc = sio_min_distance_dev(c, sel.data(), n_sel, c->s_gob.as<int32_t>(), cloud, c->s_trel.as<double>(), d_bound, B, flags,
-                                  c->s_out0.as<double>(), c->s_out1.as<int64_t>());
+                                  c->s_out0.as<double>(), c->s_out1.as<int64_t>(), c->s_out2.as<int32_t>());
     if (rc) return rc;
     CU(cudaMemcpyAsync(dmin, c->s_out0.p, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(argmin, c->s_out1.p, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (n_under && bound) CU(cudaMemcpyAsync(n_under, c->s_out2.p, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (n_under) {
-        std::memset(n_under, 0, sizeof(int32_t) * (size_t)B);
-        if (bound) {
-            rc = collect_under(c);
-            if (rc) return rc;
-            for (const auto& u : c->under) n_under[u.b] += 1;
-        }
-    }
+    if (n_under && !bound) std::memset(n_under, 0, sizeof(int32_t) * (size_t)B);
     return SIO_OK;
 }
 

@@ -16,9 +16,13 @@ constexpr int kXfChunk = 32;         // transforms processed per CTA of the min 
 // clamped corner of Appendix A.2 step 3.
 struct GridDev {
     const float* v;
+    // the same samples as 8-corner bricks: cell (i,j,k) -> 8 floats [v000 v001 v010 v011 v100 v101
+    // v110 v111] at ((i*ny + j)*nz + k)*8, 32-byte aligned, so one 256-bit load fetches a query's
+    // corners (the fp32 bulk kernels read this; the fp64 kernels read `v`)
+    const float* brick;
     int32_t nx, ny, nz;
     int32_t sx, sy;              // element strides of the padded copy: sy = nz+1, sx = (ny+1)*(nz+1)
-    double bmin[3], bmax[3], h[3];
+    double bmin[3], bmax[3], h[3], ih[3];   // ih = 1/h (host-computed: no fp64 divides on the device)
     float vmin, vmax;            // range of the samples
 };
 
@@ -29,9 +33,9 @@ struct __align__(16) XfRec {
     float hx, hy, hz;            // cell size (bbox-overshoot distance is measured in metres)
     float thr;                   // candidate threshold: bound + tau (+inf: no under-bound list)
     float hix, hiy, hiz;         // dim-1 (upper clamp of the interpolation coordinate)
-    int32_t sx;                  // padded strides
-    const float* v;              // grid samples
-    int32_t sy;
+    int32_t sx;                  // cell stride in x: ny*nz
+    const float* v;              // the grid's 8-corner bricks
+    int32_t sy;                  // cell stride in y: nz
     int32_t pad;
 };
 static_assert(sizeof(XfRec) == 96, "XfRec layout");
@@ -66,6 +70,7 @@ __host__ __device__ inline float fkey_inv(uint32_t k) {
 struct MinArgs {
     const float4* pts; const int32_t* perm; int64_t N;
     const GridDev* grids; const int32_t* grid_of_b;   // device
+    const GridDev* single_grid;                         // HOST copy when every transform uses one grid, else null
     const double* T_rel; const double* bound;          // device; bound may be null
     int64_t B;                                          // total transforms (xf, T_rel, bound, outputs are [B])
     int64_t b_begin, Bc;                                // the batch [b_begin, b_begin+Bc) this launch covers
@@ -73,6 +78,7 @@ struct MinArgs {
     uint32_t* subkeys; int32_t ntiles;                  // scratch [Bc * ntiles*8]: one key per 128-point sub-tile
     XfRec* xf;                                          // scratch [B]
     Cand* cand; uint32_t* cand_count; uint32_t cand_cap;
+    int32_t* n_under;                                   // device [B] counters of the exact under-bound set, or null
     double* dmin; int64_t* argmin;                      // device outputs
     int normalize;
 };

@@ -89,7 +89,7 @@ k_finalize(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int
            const double* __restrict__ T_rel, const double* __restrict__ bound, double tau, int64_t b_begin,
            const uint32_t* __restrict__ subkeys, int64_t nsub, int all_tiles, int emit_under,
            Cand* __restrict__ cand, uint32_t* __restrict__ cand_count, uint32_t cand_cap,
-           double* __restrict__ dmin, int64_t* __restrict__ argmin) {
+           int32_t* __restrict__ n_under, double* __restrict__ dmin, int64_t* __restrict__ argmin) {
     __shared__ uint32_t s_key[kFinThreads];
     __shared__ int32_t s_list[kMaxList];
     __shared__ int32_t s_nlist;
@@ -144,6 +144,7 @@ k_finalize(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int
             if (d < bnd && bnd < (double)INFINITY) {        // fp64 mode: final under-bound entries
                 uint32_t slot = atomicAdd(cand_count, 1u);
                 if (slot < cand_cap) { Cand c; c.b = (int32_t)b; c.idx = (int32_t)oi; c.d = d; cand[slot] = c; }
+                if (n_under) atomicAdd(n_under + b, 1);
             }
         }
     }
@@ -169,39 +170,39 @@ void launch_finalize(const MinArgs& a, bool all_tiles, bool emit_under, cudaStre
     int64_t nsub = (int64_t)a.ntiles * (kThreads / 32);
     k_finalize<<<(unsigned)a.Bc, kFinThreads, 0, st>>>(a.pts, a.perm, a.N, a.grids, a.grid_of_b, a.T_rel, a.bound,
                                                       a.tau, a.b_begin, a.subkeys, nsub, all_tiles ? 1 : 0, emit_under ? 1 : 0,
-                                                      a.cand, a.cand_count, a.cand_cap, a.dmin, a.argmin);
+                                                      a.cand, a.cand_count, a.cand_cap, a.n_under, a.dmin, a.argmin);
 }
 
 // ---- exact re-check of the fp32 pass's under-bound candidates ------------------------------------------
-__global__ void k_recheck(const float4* __restrict__ pts, const int32_t* __restrict__ perm,
+// grid-stride over the candidate records; kept entries are counted per transform in n_under
+__global__ void k_recheck(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int64_t N,
                           const GridDev* __restrict__ grids, const int32_t* __restrict__ grid_of_b,
                           const double* __restrict__ T_rel, const double* __restrict__ bound,
-                          Cand* __restrict__ cand, const uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
-    uint32_t n = min(*cand_count, cand_cap);
-    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    Cand r = cand[c];
-    const GridDev g = grids[grid_of_b ? grid_of_b[r.b] : 0];
-    float4 q = __ldg(pts + r.idx);
-    double p[3];
-    xf64(T_rel + 12 * (int64_t)r.b, (double)q.x, (double)q.y, (double)q.z, p);
-    double d = eval64(g, p, nullptr);
-    Cand o;
-    o.b = (d < bound[r.b]) ? r.b : -1;
-    o.idx = perm[r.idx];
-    o.d = d;
-    cand[c] = o;
+                          Cand* __restrict__ cand, const uint32_t* __restrict__ cand_count, uint32_t cand_cap,
+                          int32_t* __restrict__ n_under) {
+    const uint32_t n = min(*cand_count, cand_cap);
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        Cand r = cand[c];
+        if (r.idx >= N) { r.b = -1; cand[c] = r; continue; }        // a padding copy of the last point
+        const GridDev g = grids[grid_of_b ? grid_of_b[r.b] : 0];
+        float4 q = __ldg(pts + r.idx);
+        double p[3];
+        xf64(T_rel + 12 * (int64_t)r.b, (double)q.x, (double)q.y, (double)q.z, p);
+        double d = eval64(g, p, nullptr);
+        Cand o;
+        o.b = (d < bound[r.b]) ? r.b : -1;
+        o.idx = perm[r.idx];
+        o.d = d;
+        cand[c] = o;
+        if (o.b >= 0 && n_under) atomicAdd(n_under + o.b, 1);
+    }
 }
 
 void launch_recheck(const MinArgs& a, cudaStream_t st) {
-    // the count lives on the device; launch for the capacity in modest blocks and let threads exit
+    // the count lives on the device: a fixed, SM-sized grid strides over however many there are
     if (!a.bound || a.B <= 0) return;
-    uint32_t threads = 128;
-    // upper bound on work: cand_cap entries.  A launch of cap/128 idle CTAs is cheap, but avoid it when
-    // the cap is large by bounding the grid; the host loops if the count exceeded it (see sio_abi.cu).
-    uint32_t blocks = (a.cand_cap + threads - 1) / threads;
-    k_recheck<<<blocks, threads, 0, st>>>(a.pts, a.perm, a.grids, a.grid_of_b, a.T_rel, a.bound, a.cand,
-                                          a.cand_count, a.cand_cap);
+    k_recheck<<<148 * 4, 128, 0, st>>>(a.pts, a.perm, a.N, a.grids, a.grid_of_b, a.T_rel, a.bound, a.cand,
+                                       a.cand_count, a.cand_cap, a.n_under);
 }
 
 // ---- K1 float64 ---------------------------------------------------------------------------------------

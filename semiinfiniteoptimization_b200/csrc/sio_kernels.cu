@@ -6,16 +6,20 @@
 // Design (DESIGN.md "Kernels"): this is gather work on CUDA cores -- no tensor cores.  Each thread
 // keeps kPtsPerThread cloud points (float4, 128-bit coalesced loads of the Morton-sorted cloud) in
 // registers and walks a chunk of transforms staged in shared memory, so the cloud is read from HBM
-// once per chunk; the 8 trilinear corners come from the L1/L2-resident padded grid through the
-// read-only path.  Minima are reduced per warp with REDUX on order-preserving keys and written as
-// one 4-byte key per (transform, 128-point sub-tile); the float64 finalize kernel (sio_fp64.cu)
-// re-evaluates only the sub-tiles within tau of the minimum, which makes the final arg-min set
-// identical to the float64 oracle's.
+// once per chunk.  The grid is resident as 8-corner BRICKS (32 B per cell = one sector): a query's
+// eight trilinear corners arrive with ONE 256-bit read-only load (LDG.E.256) at one computed
+// address, instead of eight 4-byte gathers at four addresses.  The round-1 ncu profile of the
+// 8-gather version showed the kernel issue-bound (76 % issue-active, 101 instr/query, L1 hit 94 %),
+// so everything here is about instructions per query: bricks, FADD.RZ floor/fraction on the FMA
+// pipe (no F2I/I2F), 3-input FMNMX3 for the in-lattice test, a warp-uniform fast path that skips
+// the bbox-overshoot arithmetic, and one candidate test per 4 queries.
+// Minima are reduced per warp with REDUX on order-preserving keys and written as one 4-byte key
+// per (transform, 128-point sub-tile); the float64 finalize kernel (sio_fp64.cu) re-evaluates only
+// the sub-tiles within tau of the minimum, which makes the final arg-min identical to the float64
+// oracle's.
 #include "sio_common.cuh"
 
 namespace sio {
-
-__device__ __forceinline__ float ldg_f(const float* p) { return __ldg(p); }
 
 // floor + fraction of a clamped, non-negative coordinate with FADD.RZ (no F2I/I2F on the XU pipe)
 __device__ __forceinline__ void split_rz(float c, int& i, float& f) {
@@ -25,49 +29,73 @@ __device__ __forceinline__ void split_rz(float c, int& i, float& f) {
     f = c - (t - big);
 }
 
-struct Corners { float v000, v001, v010, v011, v100, v101, v110, v111; };
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
 
-__device__ __forceinline__ Corners gather8(const float* __restrict__ v, int sx, int sy, int ix, int iy, int iz) {
-    const float* b0 = v + (ix * sx + iy * sy + iz);
-    const float* b1 = b0 + sy;
-    const float* b2 = b0 + sx;
-    const float* b3 = b2 + sy;
-    Corners c;
-    c.v000 = ldg_f(b0); c.v001 = ldg_f(b0 + 1);
-    c.v010 = ldg_f(b1); c.v011 = ldg_f(b1 + 1);
-    c.v100 = ldg_f(b2); c.v101 = ldg_f(b2 + 1);
-    c.v110 = ldg_f(b3); c.v111 = ldg_f(b3 + 1);
+// the 8 corners of one cell: [v000 v001 v010 v011 v100 v101 v110 v111], 32-byte aligned
+struct Cell { float v[8]; };
+__device__ __forceinline__ Cell load_cell(const float* __restrict__ brick, int cell) {
+    Cell c;
+    const float* p = brick + (size_t)cell * 8;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(c.v[0]), "=f"(c.v[1]), "=f"(c.v[2]), "=f"(c.v[3]), "=f"(c.v[4]), "=f"(c.v[5]), "=f"(c.v[6]), "=f"(c.v[7])
+        : "l"(p));
     return c;
 }
 
-// value only.  r lives in shared memory (broadcast reads).
-__device__ __forceinline__ float eval32(const XfRec& r, float px, float py, float pz) {
-    float ux = fmaf(r.m[0], px, fmaf(r.m[1], py, fmaf(r.m[2], pz, r.m[3])));
-    float uy = fmaf(r.m[4], px, fmaf(r.m[5], py, fmaf(r.m[6], pz, r.m[7])));
-    float uz = fmaf(r.m[8], px, fmaf(r.m[9], py, fmaf(r.m[10], pz, r.m[11])));
-    // clamp to the bbox [-1/2, dim-1/2] (cell units) -> overshoot in metres
-    float bx = fminf(fmaxf(ux, -0.5f), r.hix + 0.5f);
-    float by = fminf(fmaxf(uy, -0.5f), r.hiy + 0.5f);
-    float bz = fminf(fmaxf(uz, -0.5f), r.hiz + 0.5f);
-    float ox = (ux - bx) * r.hx, oy = (uy - by) * r.hy, oz = (uz - bz) * r.hz;
-    float dout2 = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
-    // clamp to the sample lattice [0, dim-1]
-    float cx = fminf(fmaxf(ux, 0.0f), r.hix);
-    float cy = fminf(fmaxf(uy, 0.0f), r.hiy);
-    float cz = fminf(fmaxf(uz, 0.0f), r.hiz);
+// what the inner loop needs to know about the grid of the current transform
+struct GridK {
+    const float* brick;
+    int cx, cz;                  // cell strides: cell = ix*cx + iy*cz + iz   (cx = ny*nz, cz = nz)
+    float hx, hy, hz;            // cell size
+    float hix, hiy, hiz;         // dim-1
+};
+
+// trilinear value at lattice coordinates already inside [0, dim-1]
+__device__ __forceinline__ float lattice_value(const GridK& g, float cx, float cy, float cz) {
     int ix, iy, iz; float fx, fy, fz;
     split_rz(cx, ix, fx); split_rz(cy, iy, fy); split_rz(cz, iz, fz);
-    Corners c = gather8(r.v, r.sx, r.sy, ix, iy, iz);
-    float a00 = fmaf(fz, c.v001 - c.v000, c.v000);
-    float a01 = fmaf(fz, c.v011 - c.v010, c.v010);
-    float a10 = fmaf(fz, c.v101 - c.v100, c.v100);
-    float a11 = fmaf(fz, c.v111 - c.v110, c.v110);
+    Cell c = load_cell(g.brick, ix * g.cx + iy * g.cz + iz);
+    float a00 = fmaf(fz, c.v[1] - c.v[0], c.v[0]);
+    float a01 = fmaf(fz, c.v[3] - c.v[2], c.v[2]);
+    float a10 = fmaf(fz, c.v[5] - c.v[4], c.v[4]);
+    float a11 = fmaf(fz, c.v[7] - c.v[6], c.v[6]);
     float b0 = fmaf(fy, a01 - a00, a00);
     float b1 = fmaf(fy, a11 - a10, a10);
-    float val = fmaf(fx, b1 - b0, b0);
+    return fmaf(fx, b1 - b0, b0);
+}
+
+// general point: clamp to the lattice, add the distance to the bbox [-1/2, dim-1/2] (Appendix A.2)
+__device__ __forceinline__ float clamped_value(const GridK& g, float ux, float uy, float uz) {
+    float bx = fminf(fmaxf(ux, -0.5f), g.hix + 0.5f);
+    float by = fminf(fmaxf(uy, -0.5f), g.hiy + 0.5f);
+    float bz = fminf(fmaxf(uz, -0.5f), g.hiz + 0.5f);
+    float ox = (ux - bx) * g.hx, oy = (uy - by) * g.hy, oz = (uz - bz) * g.hz;
+    float dout2 = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
+    float cx = fminf(fmaxf(ux, 0.0f), g.hix);
+    float cy = fminf(fmaxf(uy, 0.0f), g.hiy);
+    float cz = fminf(fmaxf(uz, 0.0f), g.hiz);
+    float val = lattice_value(g, cx, cy, cz);
     float dout;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(dout) : "f"(dout2));
     return val + dout;
+}
+
+// >= 0 iff the lattice coordinate lies inside [0, hi] on all three axes
+__device__ __forceinline__ float inside_margin(const GridK& g, float ux, float uy, float uz) {
+    float t = min3(ux, g.hix - ux, uy);
+    t = min3(t, g.hiy - uy, uz);
+    return fminf(t, g.hiz - uz);
+}
+
+__device__ __forceinline__ GridK grid_of(const XfRec& r) {
+    GridK g;
+    g.brick = r.v; g.cx = r.sx; g.cz = r.sy;
+    g.hx = r.hx; g.hy = r.hy; g.hz = r.hz; g.hix = r.hix; g.hiy = r.hiy; g.hiz = r.hiz;
+    return g;
 }
 
 // value + gradient w.r.t. the input point (cloud-local), optionally normalised
@@ -86,10 +114,10 @@ __device__ __forceinline__ float eval32_grad(const XfRec& r, float px, float py,
     float cz = fminf(fmaxf(uz, 0.0f), r.hiz);
     int ix, iy, iz; float fx, fy, fz;
     split_rz(cx, ix, fx); split_rz(cy, iy, fy); split_rz(cz, iz, fz);
-    Corners c = gather8(r.v, r.sx, r.sy, ix, iy, iz);
-    float dz00 = c.v001 - c.v000, dz01 = c.v011 - c.v010, dz10 = c.v101 - c.v100, dz11 = c.v111 - c.v110;
-    float a00 = fmaf(fz, dz00, c.v000), a01 = fmaf(fz, dz01, c.v010);
-    float a10 = fmaf(fz, dz10, c.v100), a11 = fmaf(fz, dz11, c.v110);
+    Cell c = load_cell(r.v, ix * r.sx + iy * r.sy + iz);
+    float dz00 = c.v[1] - c.v[0], dz01 = c.v[3] - c.v[2], dz10 = c.v[5] - c.v[4], dz11 = c.v[7] - c.v[6];
+    float a00 = fmaf(fz, dz00, c.v[0]), a01 = fmaf(fz, dz01, c.v[2]);
+    float a10 = fmaf(fz, dz10, c.v[4]), a11 = fmaf(fz, dz11, c.v[6]);
     float dy0 = a01 - a00, dy1 = a11 - a10;
     float b0 = fmaf(fy, dy0, a00), b1 = fmaf(fy, dy1, a10);
     float dx = b1 - b0;
@@ -119,16 +147,10 @@ __device__ __forceinline__ float eval32_grad(const XfRec& r, float px, float py,
 }
 
 // ---- transform records ---------------------------------------------------------------------------
-__global__ void k_prep_xf(const GridDev* __restrict__ grids, const int32_t* __restrict__ grid_of_b,
-                          const double* __restrict__ T_rel, const double* __restrict__ bound, int64_t B,
-                          double tau, XfRec* __restrict__ xf) {
-    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const GridDev g = grids[grid_of_b ? grid_of_b[b] : 0];
-    const double* T = T_rel + 12 * b;
+__device__ __forceinline__ XfRec make_xf(const GridDev& g, const double* T, float thr) {
     XfRec r;
     for (int a = 0; a < 3; ++a) {
-        double ih = 1.0 / g.h[a];
+        double ih = g.ih[a];
         r.m[4 * a + 0] = (float)(T[4 * a + 0] * ih);
         r.m[4 * a + 1] = (float)(T[4 * a + 1] * ih);
         r.m[4 * a + 2] = (float)(T[4 * a + 2] * ih);
@@ -136,14 +158,22 @@ __global__ void k_prep_xf(const GridDev* __restrict__ grids, const int32_t* __re
     }
     r.hx = (float)g.h[0]; r.hy = (float)g.h[1]; r.hz = (float)g.h[2];
     r.hix = (float)(g.nx - 1); r.hiy = (float)(g.ny - 1); r.hiz = (float)(g.nz - 1);
-    r.sx = g.sx; r.sy = g.sy; r.v = g.v; r.pad = 0;
+    r.sx = g.ny * g.nz; r.sy = g.nz; r.v = g.brick; r.pad = 0;
+    r.thr = thr;
+    return r;
+}
+
+__global__ void k_prep_xf(const GridDev* __restrict__ grids, const int32_t* __restrict__ grid_of_b,
+                          const double* __restrict__ T_rel, const double* __restrict__ bound, int64_t B,
+                          double tau, XfRec* __restrict__ xf) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= B) return;
     float thr = -INFINITY;                         // no under-bound list unless the bound is finite
     if (bound) {
         double bd = bound[b];
         if (bd < (double)INFINITY) thr = __double2float_ru(bd + tau);
     }
-    r.thr = thr;
-    xf[b] = r;
+    xf[b] = make_xf(grids[grid_of_b ? grid_of_b[b] : 0], T_rel + 12 * b, thr);
 }
 
 void launch_prep_xf(const MinArgs& a, cudaStream_t st) {
@@ -155,33 +185,39 @@ void launch_prep_xf(const MinArgs& a, cudaStream_t st) {
 
 // ---- K2 bulk pass ---------------------------------------------------------------------------------
 // grid  = nchunks * ntiles CTAs (chunk-major: consecutive CTAs share the transform chunk)
-// output: tilekeys[b * nsub + (tile*8 + warp)] = fkey(min over the warp's 128 points)
+// output: subkeys[b_local * nsub + (tile*8 + warp)] = fkey(min over the warp's 128 points)
+// kMulti = false: every transform uses the one grid passed by value in `gk` (uniform registers);
+// kMulti = true : the grid comes with each transform record (robot links).
+// The cloud is padded to a whole tile with copies of its last point, so no per-point bounds test.
+template <bool kMulti>
 __global__ void __launch_bounds__(kThreads, 4)
-k_min_f32(const float4* __restrict__ pts, int64_t N, const XfRec* __restrict__ xf, int64_t b_begin, int64_t Bc,
-          int32_t ntiles, uint32_t* __restrict__ subkeys, Cand* __restrict__ cand,
-          uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
+k_min_f32(const float4* __restrict__ pts, const GridDev* __restrict__ grids, const int32_t* __restrict__ grid_of_b,
+          const double* __restrict__ T_rel, const double* __restrict__ bound, double tau,
+          int64_t b_begin, int64_t Bc, int32_t ntiles, uint32_t* __restrict__ subkeys, Cand* __restrict__ cand,
+          uint32_t* __restrict__ cand_count, uint32_t cand_cap, GridK gk) {
     __shared__ XfRec sxf[kXfChunk];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t chunk = blockIdx.x / ntiles;
     const int32_t tile = (int32_t)(blockIdx.x - chunk * ntiles);
     const int64_t b0 = chunk * kXfChunk;                 // batch-local index of the chunk's first transform
     const int nb = (int)min((int64_t)kXfChunk, Bc - b0);
-
-    // stage the chunk's transform records (96 B each) with 16-byte copies
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(xf + b_begin + b0);
-        uint4* dst = reinterpret_cast<uint4*>(sxf);
-        for (int i = tid; i < nb * (int)(sizeof(XfRec) / 16); i += kThreads) dst[i] = src[i];
+    if (tid < nb) {
+        // fold this chunk's float64 transforms into float32 records in the prologue (no separate
+        // launch): thread t builds the record of transform t
+        const int64_t b = b_begin + b0 + tid;
+        float thr = -INFINITY;                       // no under-bound list unless the bound is finite
+        if (bound) {
+            double bd = bound[b];
+            if (bd < (double)INFINITY) thr = __double2float_ru(bd + tau);
+        }
+        sxf[tid] = make_xf(grids[grid_of_b ? grid_of_b[b] : 0], T_rel + 12 * b, thr);
     }
     // this warp's 128 contiguous points: lane l holds base + j*32 + l
     const int64_t base = (int64_t)tile * kTile + warp * (32 * kPtsPerThread);
     float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
-    bool ok[kPtsPerThread];
 #pragma unroll
     for (int j = 0; j < kPtsPerThread; ++j) {
-        int64_t i = base + j * 32 + lane;
-        ok[j] = i < N;
-        float4 p = ok[j] ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 p = __ldg(pts + base + j * 32 + lane);
         px[j] = p.x; py[j] = p.y; pz[j] = p.z;
     }
     __syncthreads();
@@ -189,20 +225,34 @@ k_min_f32(const float4* __restrict__ pts, int64_t N, const XfRec* __restrict__ x
     const int64_t sub = (int64_t)tile * (kThreads / 32) + warp;
     for (int bl = 0; bl < nb; ++bl) {
         const XfRec& r = sxf[bl];
-        float d[kPtsPerThread];
-#pragma unroll
-        for (int j = 0; j < kPtsPerThread; ++j) d[j] = eval32(r, px[j], py[j], pz[j]);
-        float best = INFINITY;
-        const float thr = r.thr;
+        const GridK g = kMulti ? grid_of(r) : gk;
+        float ux[kPtsPerThread], uy[kPtsPerThread], uz[kPtsPerThread], d[kPtsPerThread];
+        float margin = INFINITY;
 #pragma unroll
         for (int j = 0; j < kPtsPerThread; ++j) {
-            float dj = ok[j] ? d[j] : INFINITY;
-            best = fminf(best, dj);
-            if (dj < thr) {                                   // rare: candidate for the under-bound set
-                uint32_t slot = atomicAdd(cand_count, 1u);
-                if (slot < cand_cap) {
-                    Cand c; c.b = (int32_t)(b_begin + b0 + bl); c.idx = (int32_t)(base + j * 32 + lane); c.d = (double)dj;
-                    cand[slot] = c;
+            ux[j] = fmaf(r.m[0], px[j], fmaf(r.m[1], py[j], fmaf(r.m[2], pz[j], r.m[3])));
+            uy[j] = fmaf(r.m[4], px[j], fmaf(r.m[5], py[j], fmaf(r.m[6], pz[j], r.m[7])));
+            uz[j] = fmaf(r.m[8], px[j], fmaf(r.m[9], py[j], fmaf(r.m[10], pz[j], r.m[11])));
+            margin = fminf(margin, inside_margin(g, ux[j], uy[j], uz[j]));
+        }
+        if (__all_sync(0xffffffffu, margin >= 0.0f)) {         // whole warp inside the sample lattice
+#pragma unroll
+            for (int j = 0; j < kPtsPerThread; ++j) d[j] = lattice_value(g, ux[j], uy[j], uz[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPtsPerThread; ++j) d[j] = clamped_value(g, ux[j], uy[j], uz[j]);
+        }
+        float best = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
+        static_assert(kPtsPerThread == 4, "min tree assumes 4 points per thread");
+        if (best < r.thr) {                                    // rare: candidates for the under-bound set
+#pragma unroll
+            for (int j = 0; j < kPtsPerThread; ++j) {
+                if (d[j] < r.thr) {
+                    uint32_t slot = atomicAdd(cand_count, 1u);
+                    if (slot < cand_cap) {
+                        Cand c; c.b = (int32_t)(b_begin + b0 + bl); c.idx = (int32_t)(base + j * 32 + lane); c.d = (double)d[j];
+                        cand[slot] = c;
+                    }
                 }
             }
         }
@@ -211,12 +261,27 @@ k_min_f32(const float4* __restrict__ pts, int64_t N, const XfRec* __restrict__ x
     }
 }
 
+static GridK host_gridk(const GridDev& g) {
+    GridK k;
+    k.brick = g.brick; k.cx = g.ny * g.nz; k.cz = g.nz;
+    k.hx = (float)g.h[0]; k.hy = (float)g.h[1]; k.hz = (float)g.h[2];
+    k.hix = (float)(g.nx - 1); k.hiy = (float)(g.ny - 1); k.hiz = (float)(g.nz - 1);
+    return k;
+}
+
 void launch_min_f32(const MinArgs& a, cudaStream_t st) {
     if (a.Bc <= 0 || a.N <= 0) return;
     int64_t nchunks = (a.Bc + kXfChunk - 1) / kXfChunk;
     int64_t blocks = nchunks * a.ntiles;
-    k_min_f32<<<(unsigned)blocks, kThreads, 0, st>>>(a.pts, a.N, a.xf, a.b_begin, a.Bc, a.ntiles,
-                                                     a.subkeys, a.cand, a.cand_count, a.cand_cap);
+    if (a.single_grid) {
+        k_min_f32<false><<<(unsigned)blocks, kThreads, 0, st>>>(a.pts, a.grids, a.grid_of_b, a.T_rel, a.bound, a.tau, a.b_begin,
+                                                                a.Bc, a.ntiles, a.subkeys, a.cand, a.cand_count, a.cand_cap,
+                                                                host_gridk(*a.single_grid));
+    } else {
+        GridK dummy{};
+        k_min_f32<true><<<(unsigned)blocks, kThreads, 0, st>>>(a.pts, a.grids, a.grid_of_b, a.T_rel, a.bound, a.tau, a.b_begin,
+                                                               a.Bc, a.ntiles, a.subkeys, a.cand, a.cand_count, a.cand_cap, dummy);
+    }
 }
 
 // ---- K1 over a resident cloud: per-point outputs ----------------------------------------------------
@@ -237,7 +302,7 @@ k_cloud_query_f32(const float4* __restrict__ pts, int64_t N, const XfRec* __rest
         for (int i = tid; i < nb * (int)(sizeof(XfRec) / 16); i += kThreads) dst[i] = src[i];
     }
     const int64_t i = tile * kThreads + tid;
-    float4 p = i < N ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 p = __ldg(pts + i);                      // the cloud is padded to a multiple of kTile
     __syncthreads();
     if (i >= N) return;
     if (out_g) {
@@ -248,8 +313,11 @@ k_cloud_query_f32(const float4* __restrict__ pts, int64_t N, const XfRec* __rest
         }
     } else {
         for (int bl = 0; bl < nb; ++bl) {
-            float d = eval32(sxf[bl], p.x, p.y, p.z);
-            __stcs(out_d + (b0 + bl) * N + i, d);
+            const XfRec& r = sxf[bl];
+            float ux = fmaf(r.m[0], p.x, fmaf(r.m[1], p.y, fmaf(r.m[2], p.z, r.m[3])));
+            float uy = fmaf(r.m[4], p.x, fmaf(r.m[5], p.y, fmaf(r.m[6], p.z, r.m[7])));
+            float uz = fmaf(r.m[8], p.x, fmaf(r.m[9], p.y, fmaf(r.m[10], p.z, r.m[11])));
+            __stcs(out_d + (b0 + bl) * N + i, clamped_value(grid_of(r), ux, uy, uz));
         }
     }
 }
@@ -267,30 +335,14 @@ __global__ void k_query_f32(const GridDev* __restrict__ grid, const double* __re
                             const double* __restrict__ pts, int64_t P, int normalize,
                             double* __restrict__ d, double* __restrict__ grad) {
     __shared__ XfRec r;
-    if (threadIdx.x == 0) {
-        const GridDev g = *grid;
-        for (int a = 0; a < 3; ++a) {
-            double ih = 1.0 / g.h[a];
-            r.m[4 * a + 0] = (float)(T[4 * a + 0] * ih);
-            r.m[4 * a + 1] = (float)(T[4 * a + 1] * ih);
-            r.m[4 * a + 2] = (float)(T[4 * a + 2] * ih);
-            r.m[4 * a + 3] = (float)((T[4 * a + 3] - g.bmin[a]) * ih - 0.5);
-        }
-        r.hx = (float)g.h[0]; r.hy = (float)g.h[1]; r.hz = (float)g.h[2];
-        r.hix = (float)(g.nx - 1); r.hiy = (float)(g.ny - 1); r.hiz = (float)(g.nz - 1);
-        r.sx = g.sx; r.sy = g.sy; r.v = g.v; r.thr = -INFINITY; r.pad = 0;
-    }
+    if (threadIdx.x == 0) r = make_xf(*grid, T, -INFINITY);
     __syncthreads();
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= P) return;
     float x = (float)pts[3 * i], y = (float)pts[3 * i + 1], z = (float)pts[3 * i + 2];
-    if (grad) {
-        float gx, gy, gz;
-        d[i] = (double)eval32_grad(r, x, y, z, normalize, gx, gy, gz);
-        grad[3 * i] = gx; grad[3 * i + 1] = gy; grad[3 * i + 2] = gz;
-    } else {
-        d[i] = (double)eval32(r, x, y, z);
-    }
+    float gx, gy, gz;
+    d[i] = (double)eval32_grad(r, x, y, z, normalize, gx, gy, gz);
+    if (grad) { grad[3 * i] = gx; grad[3 * i + 1] = gy; grad[3 * i + 2] = gz; }
 }
 
 void launch_query_f32(const GridDev* grid, const double* T, const double* pts, int64_t P, int normalize,
