@@ -1,0 +1,304 @@
+"""Lock-step solver for MANY independent object-pose problems (BASELINE.json config 5: 65,536
+cube-vs-scene `optimizeCollFree` problems).
+
+Every problem is exactly the reference's `optimizeCollFree(obj, env, Tinit, Tdes)` (gopt:1039-1081 on
+sip.py:795-1241, default flags); what changes is the execution order.  The reference would run the
+problems one after another, each issuing a handful of single Klampt calls per iteration.  Here all
+problems advance through the SAME outer iteration together, so each oracle request of an iteration
+becomes one batched device call over all live problems:
+
+    values + rows of every instantiated parameter of every problem   -> sio_pose_rows (1 launch)
+    minvalue of every problem (B poses x N cloud points)              -> sio_min_distance (K2 sweep)
+
+Problems are independent, so they shard across GPUs by contiguous blocks with no collective during
+the solve (dist.py gathers the per-problem records at the end).
+
+The per-problem arithmetic (trust region, merit score, weight schedule, exclusion hash, quirks) is
+the scalar solver's, statement for statement; tests run both and compare traces.  The QP is solved
+per problem on the host (`qp='scalar'`, bit-identical to the scalar solver) or, for throughput, for
+all problems of one size at once with the lock-step ADMM of _host/qp.py (`qp='batch'`).
+"""
+import math
+import time
+
+import numpy as np
+
+from . import _abi, dist
+from . import sip as _sip
+from ._host import qp as _qp
+from .geometryopt import BULK_FLAGS, POINT_FLAGS, PenetrationDepthGeometry, _inv12, _mul12
+
+
+def _log_so3_batch(M):
+    """Rotation vectors of a batch of rotation matrices (B,3,3), same branches as _host/so3."""
+    from ._host import so3
+    return np.array([so3.rotation_vector(so3.from_matrix(m)) for m in M])
+
+
+def _exp_so3_batch(W):
+    from ._host import so3
+    return np.array([so3.matrix(so3.from_rotation_vector(w)) for w in W])
+
+
+class BatchResult:
+    def __init__(self, B):
+        self.T = None                    # (B,12) final poses, row-major 3x4
+        self.status = ['not converged'] * B
+        self.num_iterations = np.zeros(B, dtype=np.int64)
+        self.fx = np.zeros(B)
+        self.gx = np.full(B, np.inf)
+        self.gx0 = np.full(B, np.inf)
+        self.instantiated_params = [[] for _ in range(B)]
+        self.trace = None
+        self.time = 0.0
+        self.time_cons = 0.0
+        self.time_qp = 0.0
+        self.outer_iterations = 0        # sum over problems of completed outer iterations
+        self.point_queries = 0           # (pose, cloud point) pairs evaluated by K2 sweeps
+
+    def records(self):
+        """Fixed-size per-problem records for the end-of-solve gather: pose(12) gx fx iters nparams."""
+        B = len(self.status)
+        rec = np.zeros((B, 16))
+        rec[:, :12] = self.T
+        rec[:, 12] = self.gx
+        rec[:, 13] = self.fx
+        rec[:, 14] = self.num_iterations
+        rec[:, 15] = [len(p) for p in self.instantiated_params]
+        return rec
+
+
+def optimizeCollFreeBatch(obj, env, Tinits, Tdess=None, settings=None, qp='scalar', keep_trace=False, context=None):
+    """Solves B independent `optimizeCollFree` problems in lock step.
+
+    obj / env: PenetrationDepthGeometry (obj owns the SDF grid and moves; env owns the cloud).
+    Tinits / Tdess: sequences of Klampt se3 poses (R column-major 9-list, t)."""
+    from ._host import se3, so3
+    assert isinstance(obj, PenetrationDepthGeometry) and isinstance(env, PenetrationDepthGeometry)
+    ctx = context or obj.context
+    settings = settings or _sip.SemiInfiniteOptimizationSettings()
+    B = len(Tinits)
+    if Tdess is None:
+        Tdess = Tinits
+    R = np.array([so3.matrix(T[0]) for T in Tinits])
+    t = np.array([T[1] for T in Tinits], dtype=np.float64)
+    Rdes = np.array([so3.matrix(T[0]) for T in Tdess])
+    tdes = np.array([T[1] for T in Tdess], dtype=np.float64)
+    Tenv = env._T12.reshape(3, 4)
+    cloud_world = env._dev.cloud32.astype(np.float64) @ Tenv[:, :3].T + Tenv[:, 3]
+    grid_h, cloud_h = obj._dev.grid_h, env._dev.cloud_h
+    N = len(cloud_world)
+
+    res = BatchResult(B)
+    params = res.instantiated_params
+    visited = [set() for _ in range(B)]
+    excl = settings.parameter_exclusion_distance
+    w = np.full(B, settings.initial_objective_score_weight)
+    trs = np.full(B, 0.5)
+    update_oracle = np.ones(B, dtype=bool)
+    live = np.ones(B, dtype=bool)
+    min_cv = np.full(B, settings.minimum_constraint_value)
+    xeps2 = settings.xepsilon ** 2 * 2          # len((R,t)) == 2 in the reference        # quirk
+    if keep_trace:
+        res.trace = [[(so3.from_matrix(R[p]), list(t[p]))] for p in range(B)]
+
+    def pose12(idx):
+        T = np.empty((len(idx), 3, 4))
+        T[:, :, :3] = R[idx]
+        T[:, :, 3] = t[idx]
+        return T.reshape(-1, 12)
+
+    def objective(idx, Rm, tm):
+        rv = _log_so3_batch(np.einsum('bij,bkj->bik', Rdes[idx], Rm))
+        dt = tdes[idx] - tm
+        return (dt * dt).sum(1) + (rv * rv).sum(1), np.hstack([rv, dt])
+
+    def key(y):
+        return tuple(int(v / excl) for v in y)
+
+    def instantiate(p, y):
+        k = key(y)
+        if k not in visited[p]:
+            params[p].append(y)
+            visited[p].add(k)
+            return True
+        return False
+
+    def values(idx, Rm, tm, want_rows):
+        """values (and rows) of every instantiated parameter of problems idx at poses (Rm, tm)."""
+        counts = [len(params[p]) for p in idx]
+        offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        if offs[-1] == 0:
+            return offs, np.zeros(0), np.zeros((0, 6))
+        pts = np.array([y for p in idx for y in params[p]], dtype=np.float64)
+        T = np.empty((len(idx), 3, 4))
+        T[:, :, :3] = Rm
+        T[:, :, 3] = tm
+        d, rows = ctx.pose_rows(grid_h, T.reshape(-1, 12), offs, pts, flags=POINT_FLAGS, want_rows=want_rows)
+        return offs, d, rows
+
+    def minvalue(idx, Rm, tm, bound):
+        """(dmin, arg) of every problem in idx: one K2 sweep of len(idx) poses x N points."""
+        T = np.empty((len(idx), 3, 4))
+        T[:, :, :3] = Rm
+        T[:, :, 3] = tm
+        Tinv = np.empty_like(T)
+        Tinv[:, :, :3] = np.transpose(Rm, (0, 2, 1))
+        Tinv[:, :, 3] = -np.einsum('bji,bj->bi', Rm, tm)
+        # T_rel = T_obj^-1 * T_env
+        Trel = np.empty_like(T)
+        Trel[:, :, :3] = Tinv[:, :, :3] @ Tenv[:, :3]
+        Trel[:, :, 3] = Tinv[:, :, :3] @ Tenv[:, 3] + Tinv[:, :, 3]
+        dmin, arg, _ = ctx.min_distance(grid_h, cloud_h, Trel.reshape(-1, 12), bound=bound, flags=BULK_FLAGS, want_under=False)
+        res.point_queries += len(idx) * N
+        return dmin, arg
+
+    fx0, _ = objective(np.arange(B), R, t)
+    res.fx = fx0.copy()
+    tstart = time.time()
+    for it in range(settings.max_iters):
+        idx = np.nonzero(live)[0]
+        if len(idx) == 0:
+            break
+        res.num_iterations[idx] = it
+        _, dxdes = objective(idx, R[idx], t[idx])
+        # ---- oracle at x (sip.py:193-276) ---------------------------------------------------
+        t0 = time.time()
+        offs, d, _ = values(idx, R[idx], t[idx], False)
+        depths = []
+        for k, p in enumerate(idx):
+            cd = list(d[offs[k]:offs[k + 1]])
+            if update_oracle[p]:
+                keep = [v < settings.constraint_drop_value for v in cd]
+                if not all(keep):
+                    params[p][:] = [y for kk, y in zip(keep, params[p]) if kk]
+                    cd = [v for kk, v in zip(keep, cd) if kk]
+                    visited[p] = set(key(y) for y in params[p])
+            depths.append(cd)
+        sel = [k for k, p in enumerate(idx) if update_oracle[p]]
+        if sel:
+            olddmin = np.array([0.0 if len(depths[k]) == 0 else min(0.0, min(depths[k])) for k in sel])
+            pi = idx[sel]
+            dmin, arg = minvalue(pi, R[pi], t[pi], olddmin)
+            for j, k in enumerate(sel):
+                if arg[j] >= 0 and dmin[j] < olddmin[j]:
+                    if instantiate(idx[k], list(cloud_world[arg[j]])):
+                        depths[k].append(float(dmin[j]))
+        update_oracle[idx] = (it % 100 == 0)
+        offs, _, rows = values(idx, R[idx], t[idx], True)
+        res.time_cons += time.time() - t0
+        gx = np.array([min(cd) if cd else np.inf for cd in depths])
+        if it == 0:
+            res.gx0[idx] = gx
+            low = gx < min_cv[idx]
+            min_cv[idx[low]] = gx[low]
+        # ---- QP step (sip.py:945-964) -----------------------------------------------------------
+        t0 = time.time()
+        dx = np.zeros((len(idx), 6))
+        cd_helper = _sip.ConstraintGenerationData([None])
+        cd_helper.constraint_inflation = settings.constraint_inflation
+        for k, p in enumerate(idx):
+            A = rows[offs[k]:offs[k + 1]]
+            if len(A) == 0:
+                dx[k] = dxdes[k]                     # no rows: xdes, trust region ignored        # quirk
+                continue
+            if qp == 'scalar':
+                dx[k] = cd_helper.solve_qp_osqp(w[p] * np.ones(6), dxdes[k], list(A), depths[k],
+                                                -np.ones(6) * trs[p], np.ones(6) * trs[p], **settings.qp_solver_params)
+        if qp == 'batch':
+            _solve_batch(dx, idx, rows, offs, depths, dxdes, w, trs, settings, cd_helper)
+        res.time_qp += time.time() - t0
+        dxn2 = (dx * dx).sum(1)
+        conv = dxn2 < xeps2
+        for k in np.nonzero(conv)[0]:
+            res.status[idx[k]] = 'local optimum'
+        live[idx[conv]] = False
+        res.gx[idx[conv]] = gx[conv]
+        go = ~conv
+        if not go.any():
+            continue
+        idx, dx, dxn2, gx = idx[go], dx[go], dxn2[go], gx[go]
+        depths = [cd for cd, g_ in zip(depths, go) if g_]
+        dxnorm = np.sqrt(dxn2)
+        # ---- proposed step and merit (sip.py:1146-1156, 134-172) ------------------------------------
+        Rn = np.einsum('bij,bjk->bik', _exp_so3_batch(dx[:, :3]), R[idx])
+        tn = t[idx] + dx[:, 3:]
+        sorig = np.array([_sip._score(res.fx[p], [cd], w[p]) for p, cd in zip(idx, depths)])
+        ninst0 = np.array([len(params[p]) for p in idx])
+        t0 = time.time()
+        fxn, _ = objective(idx, Rn, tn)
+        offs, d, _ = values(idx, Rn, tn, False)
+        gxn = np.array([d[offs[k]:offs[k + 1]].min() if offs[k + 1] > offs[k] else np.inf for k in range(len(idx))])
+        gneg = [[v for v in d[offs[k]:offs[k + 1]] if v < 0] for k in range(len(idx))]
+        dmin, arg = minvalue(idx, Rn, tn, gxn)
+        for k, p in enumerate(idx):
+            if arg[k] >= 0 and dmin[k] < gxn[k]:
+                gxn[k] = dmin[k]
+                if instantiate(p, list(cloud_world[arg[k]])) and dmin[k] < 0:
+                    gneg[k].append(float(dmin[k]))
+        res.time_cons += time.time() - t0
+        snew = np.array([(_sip.scoring_metric(g) if g else 0.0) for g in gneg]) + w[idx] * fxn
+        for k, p in enumerate(idx):
+            accept = not (snew[k] >= sorig[k])
+            if len(params[p]) > ninst0[k] and gxn[k] < 0:
+                update_oracle[p] = False
+                accept = False
+            if accept:
+                R[p], t[p] = Rn[k], tn[k]
+                res.fx[p], res.gx[p] = fxn[k], gxn[k]
+                trs[p] *= 2.5
+            else:
+                res.gx[p] = gx[k]
+                trs[p] *= 0.5
+                if trs[p] > dxnorm[k]:
+                    trs[p] = np.max(np.abs(dx[k])) * 0.5
+            if keep_trace:
+                res.trace[p].append((so3.from_matrix(R[p]), list(t[p])))
+            scale = 0.75 * ((math.atan(res.gx[p] * 3) * 2 / math.pi + 0.5) * 1.75 + 0.25)
+            w[p] = max(w[p] * scale, settings.minimum_objective_score_weight)
+            res.outer_iterations += 1
+    res.T = pose12(np.arange(B))
+    res.time = time.time() - tstart
+    return res
+
+
+def _solve_batch(dx, idx, rows, offs, depths, dxdes, w, trs, settings, cd_helper):
+    """All QPs of one row count at once with the lock-step ADMM; problems whose strict solution
+    trips the reference's slack criterion are re-solved individually."""
+    reg = settings.qp_solver_params.get('regularizationFactor', 1e-2)
+    counts = np.array([offs[k + 1] - offs[k] for k in range(len(idx))])
+    for m in np.unique(counts):
+        if m == 0:
+            continue
+        ks = np.nonzero(counts == m)[0]
+        nb = len(ks)
+        P = np.zeros((nb, 6, 6))
+        P[:, np.arange(6), np.arange(6)] = (w[idx[ks]] + reg)[:, None]
+        q = -w[idx[ks]][:, None] * dxdes[ks]
+        A = np.zeros((nb, m + 6, 6))
+        l = np.zeros((nb, m + 6))
+        u = np.full((nb, m + 6), _qp.INF)
+        for j, k in enumerate(ks):
+            A[j, :m] = rows[offs[k]:offs[k + 1]]
+            l[j, :m] = -np.asarray(depths[k]) + settings.constraint_inflation
+        A[:, m:, :] = np.eye(6)
+        l[:, m:] = -trs[idx[ks]][:, None]
+        u[:, m:] = trs[idx[ks]][:, None]
+        x, rp, rd = _qp.solve_qp_batch(P, q, A, l, u, None)
+        for j, k in enumerate(ks):
+            b = np.asarray(depths[k])
+            bnorm = np.linalg.norm(b[b < 0]) if (b < 0).any() else 1.0
+            if rp[j] > 1e-4 or rd[j] > 1e-4 or np.linalg.norm(x[j]) * reg > bnorm:
+                p = idx[k]
+                dx[k] = cd_helper.solve_qp_osqp(w[p] * np.ones(6), dxdes[k], list(rows[offs[k]:offs[k + 1]]), depths[k],
+                                                -np.ones(6) * trs[p], np.ones(6) * trs[p], **settings.qp_solver_params)
+            else:
+                dx[k] = x[j]
+
+
+def solve_sharded(obj, env, Tinits, Tdess=None, settings=None, qp='scalar'):
+    """C5 across ranks: contiguous blocks of problems per rank, no collective during the solve, one
+    gather of the fixed-size per-problem records at the end."""
+    lo, hi = dist.shard_range(len(Tinits))
+    local = optimizeCollFreeBatch(obj, env, Tinits[lo:hi], None if Tdess is None else Tdess[lo:hi], settings, qp)
+    return dist.gather_records(local.records(), n_total=len(Tinits)), local

@@ -1,0 +1,91 @@
+"""Multi-GPU plumbing: one process per GPU, `torch.distributed` (NCCL on the GPU box, gloo in the
+CPU tests) -- SURVEY.md 8e.
+
+The oracle path has NO data-path collective: independent problems (C5) or blocks of trajectory
+time samples (C4) are sharded across ranks with geometry replicated, every rank runs its own
+kernels, and only COMPACT results cross the links:
+
+  * `gather_records`   all-gather of fixed-size per-problem records (C5: pose + status + counts);
+  * `argmin_allreduce` the global (value, payload) minimum over ranks (C4: the deepest
+                       (link, env, t, point) over all time blocks), by gathering one small record
+                       per rank and reducing it on every rank identically (deterministic tie-break:
+                       value, then the integer payload in order).
+
+Payloads are tens of bytes per problem, so latency -- not NVLink bandwidth -- is what matters; no
+custom kernel is warranted here (the compute kernels have no collective to fuse with).
+"""
+import numpy as np
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+def world():
+    d = _dist()
+    return (d.get_rank(), d.get_world_size()) if d else (0, 1)
+
+
+def shard_range(n, rank=None, world_size=None):
+    """Contiguous block [lo, hi) of n units owned by `rank`; blocks differ in size by at most one."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    base, rem = divmod(int(n), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _device_for_backend():
+    import torch
+    d = _dist()
+    if d is not None and d.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def gather_records(local, n_total=None):
+    """All-gather a (n_local, k) float64 array of per-unit records from every rank, in rank order
+    (= unit order for `shard_range` blocks).  Ranks may own different counts."""
+    import torch
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    if local.ndim == 1:
+        local = local[:, None]
+    d = _dist()
+    if d is None:
+        return local.copy()
+    dev = _device_for_backend()
+    rank, ws = d.get_rank(), d.get_world_size()
+    counts = torch.zeros(ws, dtype=torch.int64, device=dev)
+    counts[rank] = local.shape[0]
+    d.all_reduce(counts)
+    counts = [int(c) for c in counts.cpu()]
+    k = local.shape[1]
+    nmax = max(counts) if counts else 0
+    buf = torch.zeros((nmax, k), dtype=torch.float64, device=dev)
+    if local.shape[0]:
+        buf[:local.shape[0]] = torch.from_numpy(local).to(dev)
+    out = [torch.empty_like(buf) for _ in range(ws)]
+    d.all_gather(out, buf)
+    res = np.concatenate([o[:c].cpu().numpy() for o, c in zip(out, counts)], axis=0)
+    if n_total is not None:
+        assert res.shape[0] == n_total, (res.shape, n_total)
+    return res
+
+
+def argmin_allreduce(value, payload):
+    """Global minimum over ranks of (value, payload): returns the winning (value, payload) on every
+    rank.  `payload` is a fixed-length sequence of floats (ids, time, point ...).  A rank with
+    nothing to offer passes value = +inf.  Ties on value break on the payload, lexicographically,
+    so every rank picks the same winner."""
+    rec = np.concatenate([[float(value)], np.asarray(payload, dtype=np.float64)])
+    allrec = gather_records(rec[None, :])
+    order = np.lexsort(tuple(allrec[:, c] for c in range(allrec.shape[1] - 1, -1, -1)))
+    best = allrec[order[0]]
+    return float(best[0]), best[1:]
+
+
+def barrier():
+    d = _dist()
+    if d is not None:
+        d.barrier()
