@@ -47,6 +47,7 @@ extern "C" {
 #define SIO_F64             0x1
 #define SIO_NO_NORMALIZE    0x2   /* return the raw analytic gradient instead of the unit one */
 #define SIO_WANT_GRAD       0x4
+#define SIO_PRUNE           0x8   /* K2: skip 128-point sub-tiles whose Lipschitz lower bound rules them out (results identical) */
 
 typedef struct sio_ctx sio_ctx;
 typedef int32_t sio_handle;
@@ -146,6 +147,8 @@ int sio_robot_min_distance(sio_ctx* ctx, sio_handle robot, const sio_handle* lin
 /* device time (ms, CUDA events on the context's stream) of the fp32 bulk kernel launches
  * (k_min_f32) of the LAST sio_min_distance[_dev] call; synchronises on that call's end event. */
 int sio_ctx_last_bulk_ms(sio_ctx* ctx, double* ms);
+/* SIO_PRUNE bookkeeping of the LAST K2 call: (transform, sub-tile) pairs evaluated vs total. */
+int sio_ctx_last_prune_stats(sio_ctx* ctx, int64_t* evaluated, int64_t* total);
 /* random 4-byte gathers over an L2-resident float array of `n_elems`: returns achieved GB/s of
  * gathered bytes (32 B sectors are NOT counted, only the 4 B used) in *gbps. */
 int sio_bench_gather(sio_ctx* ctx, int64_t n_elems, int64_t n_gathers, int iters, double* gbps);

@@ -17,6 +17,7 @@ SIO_ERR_OVERFLOW = -5
 SIO_F32 = 0x0
 SIO_F64 = 0x1
 SIO_NO_NORMALIZE = 0x2
+SIO_PRUNE = 0x8
 
 # every symbol include/sio_abi.h declares (tests check the built library exports each of them)
 ABI_SYMBOLS = (
@@ -28,7 +29,7 @@ ABI_SYMBOLS = (
     "sio_min_distance", "sio_min_distance_dev", "sio_under_fetch",
     "sio_pose_rows",
     "sio_robot_create", "sio_robot_destroy", "sio_fk", "sio_chain_rows", "sio_robot_min_distance",
-    "sio_bench_gather", "sio_ctx_last_bulk_ms",
+    "sio_bench_gather", "sio_ctx_last_bulk_ms", "sio_ctx_last_prune_stats",
 )
 
 _lib = None
@@ -81,6 +82,7 @@ def load_library():
     L.sio_robot_min_distance.argtypes = [P, I32, P, P, I32, I32, P, P, I64, P, C.c_int, P, P, P]
     L.sio_bench_gather.argtypes = [P, I64, I64, C.c_int, C.POINTER(D)]
     L.sio_ctx_last_bulk_ms.argtypes = [P, C.POINTER(D)]
+    L.sio_ctx_last_prune_stats.argtypes = [P, C.POINTER(I64), C.POINTER(I64)]
     _lib = L
     return L
 
@@ -277,6 +279,11 @@ class Context:
         out = C.c_double(0)
         self._ck(self.L.sio_ctx_last_bulk_ms(self.h, C.byref(out)))
         return out.value
+
+    def last_prune_stats(self):
+        ev, tot = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.sio_ctx_last_prune_stats(self.h, C.byref(ev), C.byref(tot)))
+        return ev.value, tot.value
 
     def bench_gather(self, n_elems, n_gathers, iters=10):
         out = C.c_double(0)

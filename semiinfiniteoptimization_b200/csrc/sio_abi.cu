@@ -81,6 +81,7 @@ struct CloudH {
     bool live = false;
     int64_t n = 0;
     float4* d_pts = nullptr;       // Morton-sorted
+    float4* d_rep = nullptr;       // per 128-point sub-tile: representative cloud point (xyz) + bounding radius (w)
     int32_t* d_perm = nullptr;     // internal -> caller index
     std::vector<int32_t> perm;
 };
@@ -108,6 +109,10 @@ struct sio_ctx {
     std::vector<CloudH> clouds;
     std::vector<RobotH> robots;
     // scratch
+    DevBuf s_lb, s_ub, s_items, s_icnt;
+    HostBuf h_icnt;
+    int n_icnt = 0;                   // batches of the last pruned call (their survivor counts sit in h_icnt)
+    int64_t prune_total = 0;          // (transform, sub-tile) pairs of the last pruned call
     DevBuf s_xf, s_keys, s_gridtab, s_cand, s_cnt, s_in0, s_in1, s_in2, s_in3, s_out0, s_out1, s_out2, s_tlinks, s_trel, s_gob;
     HostBuf h_a, h_b, h_c;
     uint32_t cand_cap = 1u << 20;
@@ -193,8 +198,9 @@ int sio_ctx_destroy(sio_ctx* c) {
     DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& g : c->grids) if (g.live) { cudaFree(g.d_v); cudaFree(g.d_brick); cudaFree(g.d_meta); }
-    for (auto& p : c->clouds) if (p.live) { cudaFree(p.d_pts); cudaFree(p.d_perm); }
+    for (auto& p : c->clouds) if (p.live) { cudaFree(p.d_pts); cudaFree(p.d_rep); cudaFree(p.d_perm); }
     for (auto& r : c->robots) if (r.live) { cudaFree(r.d_parent); cudaFree(r.d_jtype); cudaFree(r.d_tparent); cudaFree(r.d_axis); }
+    c->s_lb.release(); c->s_ub.release(); c->s_items.release(); c->s_icnt.release(); c->h_icnt.release();
     DevBuf* bufs[] = {&c->s_xf, &c->s_keys, &c->s_gridtab, &c->s_cand, &c->s_cnt, &c->s_in0, &c->s_in1, &c->s_in2, &c->s_in3,
                       &c->s_out0, &c->s_out1, &c->s_out2, &c->s_tlinks, &c->s_trel, &c->s_gob};
     for (auto* b : bufs) b->release();
@@ -258,7 +264,26 @@ int sio_grid_create(sio_ctx* c, const float* values, const int32_t dims[3], cons
                         for (int dk = 0; dk < 2; ++dk)
                             dst[di * 4 + dj * 2 + dk] = pad[((size_t)(i + di) * py + (j + dj)) * pz + (k + dk)];
             }
+    // Lipschitz constant of the trilinear interpolant: inside a cell |dv/dx| <= max over its four x-edges of
+    // |difference| / hx (likewise y, z), so sqrt of the sum of squares bounds the gradient norm there; take the
+    // maximum over cells.  Used only by the sub-tile culling (a valid bound keeps pruned results exact).
+    double lip = 0.0;
+    {
+        const double hx = (bmax[0] - bmin[0]) / nx, hy = (bmax[1] - bmin[1]) / ny, hz = (bmax[2] - bmin[2]) / nz;
+        for (size_t cidx = 0, nc = (size_t)nx * ny * nz; cidx < nc; ++cidx) {
+            const float* q = brick.data() + cidx * 8;
+            double ex = 0, ey = 0, ez = 0;
+            for (int m = 0; m < 4; ++m) {
+                ex = std::max(ex, (double)std::fabs(q[4 + m] - q[m]));                       // x-edges: (1,j,k)-(0,j,k)
+                ey = std::max(ey, (double)std::fabs(q[(m & 2) * 2 + 2 + (m & 1)] - q[(m & 2) * 2 + (m & 1)]));  // y-edges
+                ez = std::max(ez, (double)std::fabs(q[2 * m + 1] - q[2 * m]));               // z-edges
+            }
+            ex /= hx; ey /= hy; ez /= hz;
+            lip = std::max(lip, std::sqrt(ex * ex + ey * ey + ez * ez));
+        }
+    }
     GridH g;
+    g.meta.lip = (float)(lip * (1.0 + 1e-6)) + 1e-6f;
     CU(cudaMalloc(&g.d_v, pad.size() * sizeof(float)));
     CU(cudaMemcpyAsync(g.d_v, pad.data(), pad.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMalloc(&g.d_brick, brick.size() * sizeof(float)));
@@ -327,7 +352,31 @@ int sio_cloud_create(sio_ctx* c, const float* xyz, int64_t n, sio_handle* out) {
     // pad to a whole tile with copies of the last point: the bulk kernel needs no bounds test, a duplicate
     // cannot lower a minimum, and the fp64 stages only ever look at indices < n
     for (int64_t i = n; i < npad; ++i) pts[i] = n > 0 ? pts[n - 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+    // sub-tile culling data: for every 128 consecutive (Morton-ordered) points, the point nearest to their
+    // centroid and the radius of the sphere about it that contains all of them (rounded up)
+    const int64_t sub = 32 * kPtsPerThread;
+    const int64_t nsubt = std::max<int64_t>(npad / sub, 1);
+    std::vector<float4> reps((size_t)nsubt, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int64_t s = 0; s * sub < npad; ++s) {
+        const float4* q = pts.data() + s * sub;
+        double cx = 0, cy = 0, cz = 0;
+        for (int64_t i = 0; i < sub; ++i) { cx += q[i].x; cy += q[i].y; cz += q[i].z; }
+        cx /= sub; cy /= sub; cz /= sub;
+        int64_t best = 0; double bd = 1e300;
+        for (int64_t i = 0; i < sub; ++i) {
+            double d2 = (q[i].x - cx) * (q[i].x - cx) + (q[i].y - cy) * (q[i].y - cy) + (q[i].z - cz) * (q[i].z - cz);
+            if (d2 < bd) { bd = d2; best = i; }
+        }
+        double r2 = 0;
+        for (int64_t i = 0; i < sub; ++i) {
+            double dx = (double)q[i].x - q[best].x, dy = (double)q[i].y - q[best].y, dz = (double)q[i].z - q[best].z;
+            r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+        }
+        reps[s] = make_float4(q[best].x, q[best].y, q[best].z, (float)(std::sqrt(r2) * (1.0 + 1e-6)) + 1e-7f);
+    }
     CU(cudaMalloc(&p.d_pts, pts.size() * sizeof(float4)));
+    CU(cudaMalloc(&p.d_rep, reps.size() * sizeof(float4)));
+    CU(cudaMemcpyAsync(p.d_rep, reps.data(), reps.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMalloc(&p.d_perm, p.perm.size() * sizeof(int32_t)));
     CU(cudaMemcpyAsync(p.d_pts, pts.data(), pts.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(p.d_perm, p.perm.data(), p.perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -342,7 +391,7 @@ int sio_cloud_destroy(sio_ctx* c, sio_handle h) {
     if (!c || !cloud_ok(c, h)) return fail(SIO_ERR_INVALID, "sio_cloud_destroy: bad handle %d", h);
     DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->clouds[h].d_pts); cudaFree(c->clouds[h].d_perm);
+    cudaFree(c->clouds[h].d_pts); cudaFree(c->clouds[h].d_rep); cudaFree(c->clouds[h].d_perm);
     c->clouds[h] = CloudH();
     return SIO_OK;
 }
@@ -466,15 +515,41 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
     a.cand = c->s_cand.as<Cand>(); a.cand_count = c->s_cnt.as<uint32_t>(); a.cand_cap = c->cand_cap;
     a.n_under = d_bound ? d_n_under : nullptr;
     a.dmin = d_dmin; a.argmin = d_argmin;
+    const bool prune = !f64 && (flags & SIO_PRUNE) && p.n > 0;
+    const int max_batches = 4096;
     if (!f64) {
         CU(c->s_keys.ensure((size_t)std::max<int64_t>(1, Bc * nsub) * sizeof(uint32_t)));
         a.subkeys = c->s_keys.as<uint32_t>();
+    }
+    c->n_icnt = 0; c->prune_total = 0;
+    if (prune) {
+        if ((B + Bc - 1) / Bc > max_batches) return fail(SIO_ERR_INVALID, "sio_min_distance_dev: too many batches for SIO_PRUNE");
+        CU(c->s_xf.ensure((size_t)B * sizeof(XfRec)));
+        CU(c->s_lb.ensure((size_t)(Bc * nsub) * sizeof(float)));
+        CU(c->s_items.ensure((size_t)(Bc * nsub) * sizeof(uint32_t)));
+        CU(c->s_ub.ensure((size_t)B * sizeof(uint32_t)));
+        CU(c->s_icnt.ensure(sizeof(uint32_t) * max_batches));
+        CU(c->h_icnt.ensure(sizeof(uint32_t) * max_batches));
+        CU(cudaMemsetAsync(c->s_ub.p, 0xff, (size_t)B * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(c->s_icnt.p, 0, sizeof(uint32_t) * ((B + Bc - 1) / Bc), st));
+        a.xf = c->s_xf.as<XfRec>(); a.rep = p.d_rep; a.lb = c->s_lb.as<float>(); a.ub = c->s_ub.as<uint32_t>();
+        a.items = c->s_items.as<uint32_t>();
+        launch_prep_xf(a, st);
+        c->launches += 1;
+        c->prune_total = B * nsub;
     }
     c->bulk_timed = false;
     const bool one_batch = Bc >= B;
     for (int64_t b0 = 0; b0 < B; b0 += Bc) {
         a.b_begin = b0; a.Bc = std::min(Bc, B - b0);
-        if (!f64) {
+        if (prune) {
+            a.item_count = c->s_icnt.as<uint32_t>() + c->n_icnt;
+            if (one_batch) cudaEventRecord(c->ev_bulk0, st);
+            launch_min_pruned(a, st);
+            if (one_batch) { cudaEventRecord(c->ev_bulk1, st); c->bulk_timed = true; }
+            c->n_icnt += 1;
+            c->launches += 3;
+        } else if (!f64) {
             if (one_batch) cudaEventRecord(c->ev_bulk0, st);
             launch_min_f32(a, st);
             if (one_batch) { cudaEventRecord(c->ev_bulk1, st); c->bulk_timed = true; }
@@ -771,6 +846,18 @@ int sio_robot_min_distance(sio_ctx* c, sio_handle robot, const sio_handle* link_
 }
 
 // ---- measurement helpers --------------------------------------------------------------------------------
+int sio_ctx_last_prune_stats(sio_ctx* c, int64_t* evaluated, int64_t* total) {
+    if (!c || !evaluated || !total) return fail(SIO_ERR_INVALID, "sio_ctx_last_prune_stats: bad argument");
+    DeviceGuard guard(c->device);
+    *evaluated = 0; *total = c->prune_total;
+    if (c->n_icnt > 0) {
+        CU(cudaMemcpyAsync(c->h_icnt.p, c->s_icnt.p, sizeof(uint32_t) * c->n_icnt, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < c->n_icnt; ++i) *evaluated += c->h_icnt.as<uint32_t>()[i];
+    }
+    return SIO_OK;
+}
+
 int sio_ctx_last_bulk_ms(sio_ctx* c, double* ms) {
     if (!c || !ms) return fail(SIO_ERR_INVALID, "sio_ctx_last_bulk_ms: bad argument");
     if (!c->bulk_timed) return fail(SIO_ERR_INVALID, "sio_ctx_last_bulk_ms: the last call had no single-batch fp32 bulk launch");

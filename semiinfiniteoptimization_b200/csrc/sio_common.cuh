@@ -24,6 +24,7 @@ struct GridDev {
     int32_t sx, sy;              // element strides of the padded copy: sy = nz+1, sx = (ny+1)*(nz+1)
     double bmin[3], bmax[3], h[3], ih[3];   // ih = 1/h (host-computed: no fp64 divides on the device)
     float vmin, vmax;            // range of the samples
+    float lip;                   // Lipschitz constant of the trilinear interpolant w.r.t. local position
 };
 
 // fp32 transform record of one query b: cloud-local point -> dual-lattice cell coordinates
@@ -36,7 +37,7 @@ struct __align__(16) XfRec {
     int32_t sx;                  // cell stride in x: ny*nz
     const float* v;              // the grid's 8-corner bricks
     int32_t sy;                  // cell stride in y: nz
-    int32_t pad;
+    float lip;                   // Lipschitz constant of the grid's interpolant (sub-tile culling)
 };
 static_assert(sizeof(XfRec) == 96, "XfRec layout");
 
@@ -79,11 +80,14 @@ struct MinArgs {
     XfRec* xf;                                          // scratch [B]
     Cand* cand; uint32_t* cand_count; uint32_t cand_cap;
     int32_t* n_under;                                   // device [B] counters of the exact under-bound set, or null
+    // sub-tile culling (SIO_PRUNE): representative point + radius per sub-tile, lower bounds, upper bounds, work list
+    const float4* rep; float* lb; uint32_t* ub; uint32_t* items; uint32_t* item_count;
     double* dmin; int64_t* argmin;                      // device outputs
     int normalize;
 };
 void launch_prep_xf(const MinArgs& a, cudaStream_t st);
 void launch_min_f32(const MinArgs& a, cudaStream_t st);
+void launch_min_pruned(const MinArgs& a, cudaStream_t st);
 void launch_finalize(const MinArgs& a, bool all_tiles, bool emit_under, cudaStream_t st);
 void launch_recheck(const MinArgs& a, cudaStream_t st);
 

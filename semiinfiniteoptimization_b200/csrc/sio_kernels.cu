@@ -158,7 +158,7 @@ __device__ __forceinline__ XfRec make_xf(const GridDev& g, const double* T, floa
     }
     r.hx = (float)g.h[0]; r.hy = (float)g.h[1]; r.hz = (float)g.h[2];
     r.hix = (float)(g.nx - 1); r.hiy = (float)(g.ny - 1); r.hiz = (float)(g.nz - 1);
-    r.sx = g.ny * g.nz; r.sy = g.nz; r.v = g.brick; r.pad = 0;
+    r.sx = g.ny * g.nz; r.sy = g.nz; r.v = g.brick; r.lip = g.lip;
     r.thr = thr;
     return r;
 }
@@ -181,6 +181,45 @@ void launch_prep_xf(const MinArgs& a, cudaStream_t st) {
     int threads = 128;
     int64_t blocks = (a.B + threads - 1) / threads;
     k_prep_xf<<<(unsigned)blocks, threads, 0, st>>>(a.grids, a.grid_of_b, a.T_rel, a.bound, a.B, a.tau, a.xf);
+}
+
+// One warp, one transform, the warp's 128 points (4 per lane): trilinear values, candidates for the
+// under-bound set, and the order-preserving key of the warp's minimum (returned in every lane).
+__device__ __forceinline__ uint32_t warp_subtile_min(const XfRec& r, const GridK& g, const float (&px)[kPtsPerThread],
+                                                     const float (&py)[kPtsPerThread], const float (&pz)[kPtsPerThread],
+                                                     int32_t b, int32_t base, int lane, Cand* __restrict__ cand,
+                                                     uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
+    float ux[kPtsPerThread], uy[kPtsPerThread], uz[kPtsPerThread], d[kPtsPerThread];
+    float margin = INFINITY;
+#pragma unroll
+    for (int j = 0; j < kPtsPerThread; ++j) {
+        ux[j] = fmaf(r.m[0], px[j], fmaf(r.m[1], py[j], fmaf(r.m[2], pz[j], r.m[3])));
+        uy[j] = fmaf(r.m[4], px[j], fmaf(r.m[5], py[j], fmaf(r.m[6], pz[j], r.m[7])));
+        uz[j] = fmaf(r.m[8], px[j], fmaf(r.m[9], py[j], fmaf(r.m[10], pz[j], r.m[11])));
+        margin = fminf(margin, inside_margin(g, ux[j], uy[j], uz[j]));
+    }
+    if (__all_sync(0xffffffffu, margin >= 0.0f)) {         // whole warp inside the sample lattice
+#pragma unroll
+        for (int j = 0; j < kPtsPerThread; ++j) d[j] = lattice_value(g, ux[j], uy[j], uz[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kPtsPerThread; ++j) d[j] = clamped_value(g, ux[j], uy[j], uz[j]);
+    }
+    float best = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
+    static_assert(kPtsPerThread == 4, "min tree assumes 4 points per thread");
+    if (best < r.thr) {                                    // rare: candidates for the under-bound set
+#pragma unroll
+        for (int j = 0; j < kPtsPerThread; ++j) {
+            if (d[j] < r.thr) {
+                uint32_t slot = atomicAdd(cand_count, 1u);
+                if (slot < cand_cap) {
+                    Cand c; c.b = b; c.idx = base + j * 32 + lane; c.d = (double)d[j];
+                    cand[slot] = c;
+                }
+            }
+        }
+    }
+    return __reduce_min_sync(0xffffffffu, fkey(best));
 }
 
 // ---- K2 bulk pass ---------------------------------------------------------------------------------
@@ -226,37 +265,8 @@ k_min_f32(const float4* __restrict__ pts, const GridDev* __restrict__ grids, con
     for (int bl = 0; bl < nb; ++bl) {
         const XfRec& r = sxf[bl];
         const GridK g = kMulti ? grid_of(r) : gk;
-        float ux[kPtsPerThread], uy[kPtsPerThread], uz[kPtsPerThread], d[kPtsPerThread];
-        float margin = INFINITY;
-#pragma unroll
-        for (int j = 0; j < kPtsPerThread; ++j) {
-            ux[j] = fmaf(r.m[0], px[j], fmaf(r.m[1], py[j], fmaf(r.m[2], pz[j], r.m[3])));
-            uy[j] = fmaf(r.m[4], px[j], fmaf(r.m[5], py[j], fmaf(r.m[6], pz[j], r.m[7])));
-            uz[j] = fmaf(r.m[8], px[j], fmaf(r.m[9], py[j], fmaf(r.m[10], pz[j], r.m[11])));
-            margin = fminf(margin, inside_margin(g, ux[j], uy[j], uz[j]));
-        }
-        if (__all_sync(0xffffffffu, margin >= 0.0f)) {         // whole warp inside the sample lattice
-#pragma unroll
-            for (int j = 0; j < kPtsPerThread; ++j) d[j] = lattice_value(g, ux[j], uy[j], uz[j]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < kPtsPerThread; ++j) d[j] = clamped_value(g, ux[j], uy[j], uz[j]);
-        }
-        float best = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
-        static_assert(kPtsPerThread == 4, "min tree assumes 4 points per thread");
-        if (best < r.thr) {                                    // rare: candidates for the under-bound set
-#pragma unroll
-            for (int j = 0; j < kPtsPerThread; ++j) {
-                if (d[j] < r.thr) {
-                    uint32_t slot = atomicAdd(cand_count, 1u);
-                    if (slot < cand_cap) {
-                        Cand c; c.b = (int32_t)(b_begin + b0 + bl); c.idx = (int32_t)(base + j * 32 + lane); c.d = (double)d[j];
-                        cand[slot] = c;
-                    }
-                }
-            }
-        }
-        uint32_t k = __reduce_min_sync(0xffffffffu, fkey(best));
+        uint32_t k = warp_subtile_min(r, g, px, py, pz, (int32_t)(b_begin + b0 + bl), (int32_t)base, lane,
+                                      cand, cand_count, cand_cap);
         if (lane == 0) subkeys[(b0 + bl) * nsub + sub] = k;
     }
 }
@@ -282,6 +292,130 @@ void launch_min_f32(const MinArgs& a, cudaStream_t st) {
         k_min_f32<true><<<(unsigned)blocks, kThreads, 0, st>>>(a.pts, a.grids, a.grid_of_b, a.T_rel, a.bound, a.tau, a.b_begin,
                                                                a.Bc, a.ntiles, a.subkeys, a.cand, a.cand_count, a.cand_cap, dummy);
     }
+}
+
+// ---- K2 with sub-tile culling (SIO_PRUNE) -----------------------------------------------------------
+// The GPU counterpart of the bounding-hierarchy branch-and-bound inside Klampt's distance_ext: each
+// 128-point sub-tile has a representative cloud point and a bounding radius (built once with the
+// cloud).  With L a Lipschitz constant of the interpolated field (from the grid's own samples; +1
+// where the sphere leaves the bbox, because the bbox-overshoot term is 1-Lipschitz):
+//     every point of sub-tile s has  d(b, .) >= d(b, rep_s) - L r_s      (lower bound)
+//     min_i d(b, i)  <=  min_s d(b, rep_s)                               (upper bound: reps are cloud points)
+// so a sub-tile whose lower bound exceeds max(upper bound, bound_b) + 2 tau can contain neither the
+// minimum nor an under-bound point and is skipped; its key is set to +inf.  Results are identical to
+// the un-pruned sweep.
+//   k_prune_centres : lb[b][s] and ub[b]       (one query per (transform, sub-tile))
+//   k_prune_select  : survivors -> work items  (compaction)
+//   k_min_items     : one warp per surviving (transform, sub-tile), persistent grid
+__global__ void __launch_bounds__(kThreads)
+k_prune_centres(const float4* __restrict__ rep, int64_t nsub, const XfRec* __restrict__ xf, int64_t b_begin, int64_t Bc,
+                float* __restrict__ lb, uint32_t* __restrict__ ub) {
+    __shared__ XfRec sxf[kXfChunk];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t ntl = (nsub + kThreads - 1) / kThreads;
+    const int64_t chunk = blockIdx.x / ntl;
+    const int64_t tl = blockIdx.x - chunk * ntl;
+    const int64_t b0 = chunk * kXfChunk;
+    const int nb = (int)min((int64_t)kXfChunk, Bc - b0);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(xf + b_begin + b0);
+        uint4* dst = reinterpret_cast<uint4*>(sxf);
+        for (int i = tid; i < nb * (int)(sizeof(XfRec) / 16); i += kThreads) dst[i] = src[i];
+    }
+    const int64_t s = tl * kThreads + tid;
+    const bool ok = s < nsub;
+    float4 p = ok ? __ldg(rep + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    for (int bl = 0; bl < nb; ++bl) {
+        const XfRec& r = sxf[bl];
+        const GridK g = grid_of(r);
+        float ux = fmaf(r.m[0], p.x, fmaf(r.m[1], p.y, fmaf(r.m[2], p.z, r.m[3])));
+        float uy = fmaf(r.m[4], p.x, fmaf(r.m[5], p.y, fmaf(r.m[6], p.z, r.m[7])));
+        float uz = fmaf(r.m[8], p.x, fmaf(r.m[9], p.y, fmaf(r.m[10], p.z, r.m[11])));
+        float dc = clamped_value(g, ux, uy, uz);
+        // distance (metres) from the centre to the nearest bbox face, negative outside
+        float mx = fminf(ux + 0.5f, g.hix + 0.5f - ux) * g.hx;
+        float my = fminf(uy + 0.5f, g.hiy + 0.5f - uy) * g.hy;
+        float mz = fminf(uz + 0.5f, g.hiz + 0.5f - uz) * g.hz;
+        float L = r.lip + ((min3(mx, my, mz) >= p.w) ? 0.0f : 1.0f);
+        if (ok) lb[(b0 + bl) * nsub + s] = dc - L * p.w;
+        uint32_t k = __reduce_min_sync(0xffffffffu, ok ? fkey(dc) : 0xffffffffu);
+        if (lane == 0) atomicMin(ub + b_begin + b0 + bl, k);
+    }
+}
+
+// s-major enumeration: the threads of a warp look at ONE sub-tile under 32 consecutive transforms, so the
+// survivors they append (warp-aggregated atomic -> consecutive slots) form runs that share their points
+__global__ void k_prune_select(const float* __restrict__ lb, const uint32_t* __restrict__ ub, const double* __restrict__ bound,
+                               int64_t nsub, int64_t b_begin, int64_t Bc, float tau, uint32_t* __restrict__ subkeys,
+                               uint32_t* __restrict__ items, uint32_t* __restrict__ item_count) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t Bp = (Bc + 31) & ~(int64_t)31;            // transforms padded to whole warps
+    if (t >= Bp * nsub) return;
+    const int64_t s = t / Bp;
+    const int64_t bl = t - s * Bp;
+    if (bl >= Bc) return;
+    const int64_t b = b_begin + bl;
+    const int64_t e = bl * nsub + s;
+    float thr = fkey_inv(ub[b]);
+    if (bound) {
+        double bd = bound[b];
+        if (bd < (double)INFINITY) thr = fmaxf(thr, __double2float_ru(bd));
+    }
+    if (lb[e] <= thr + 2.0f * tau) items[atomicAdd(item_count, 1u)] = (uint32_t)e;
+    else subkeys[e] = 0xff800000u;               // fkey(+inf): the finalize pass never opens this sub-tile
+}
+
+constexpr int kItemRun = 8;      // consecutive work items taken by one warp (they mostly share a sub-tile)
+
+__global__ void __launch_bounds__(kThreads, 4)
+k_min_items(const float4* __restrict__ pts, const XfRec* __restrict__ xf, int64_t b_begin, int64_t nsub,
+            const uint32_t* __restrict__ items, const uint32_t* __restrict__ item_count, uint32_t* __restrict__ subkeys,
+            Cand* __restrict__ cand, uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
+    __shared__ XfRec sxf[kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n = *item_count;
+    const uint32_t nwarps = gridDim.x * (kThreads / 32);
+    float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
+    int64_t have = -1;                                     // sub-tile whose points sit in registers
+    for (uint32_t it0 = (blockIdx.x * (kThreads / 32) + warp) * kItemRun; it0 < n; it0 += nwarps * kItemRun) {
+        const uint32_t it1 = min(n, it0 + kItemRun);
+        for (uint32_t it = it0; it < it1; ++it) {
+            const uint32_t e = __ldg(items + it);
+            const int64_t bl = e / nsub;
+            const int64_t s = e - bl * nsub;
+            const int64_t b = b_begin + bl;
+            __syncwarp();
+            if (lane < (int)(sizeof(XfRec) / 16))
+                reinterpret_cast<uint4*>(&sxf[warp])[lane] = __ldg(reinterpret_cast<const uint4*>(xf + b) + lane);
+            __syncwarp();
+            const XfRec& r = sxf[warp];
+            const int64_t base = s * (32 * kPtsPerThread);
+            if (s != have) {
+#pragma unroll
+                for (int j = 0; j < kPtsPerThread; ++j) {
+                    float4 p = __ldg(pts + base + j * 32 + lane);
+                    px[j] = p.x; py[j] = p.y; pz[j] = p.z;
+                }
+                have = s;
+            }
+            uint32_t k = warp_subtile_min(r, grid_of(r), px, py, pz, (int32_t)b, (int32_t)base, lane, cand, cand_count, cand_cap);
+            if (lane == 0) subkeys[e] = k;
+        }
+    }
+}
+
+void launch_min_pruned(const MinArgs& a, cudaStream_t st) {
+    if (a.Bc <= 0 || a.N <= 0) return;
+    const int64_t nsub = (int64_t)a.ntiles * (kThreads / 32);
+    const int64_t ntl = (nsub + kThreads - 1) / kThreads;
+    const int64_t nchunks = (a.Bc + kXfChunk - 1) / kXfChunk;
+    k_prune_centres<<<(unsigned)(nchunks * ntl), kThreads, 0, st>>>(a.rep, nsub, a.xf, a.b_begin, a.Bc, a.lb, a.ub);
+    const int64_t ne = ((a.Bc + 31) & ~(int64_t)31) * nsub;
+    k_prune_select<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(a.lb, a.ub, a.bound, nsub, a.b_begin, a.Bc, (float)a.tau,
+                                                                  a.subkeys, a.items, a.item_count);
+    k_min_items<<<148 * 4, kThreads, 0, st>>>(a.pts, a.xf, a.b_begin, nsub, a.items, a.item_count, a.subkeys, a.cand,
+                                              a.cand_count, a.cand_cap);
 }
 
 // ---- K1 over a resident cloud: per-point outputs ----------------------------------------------------

@@ -631,23 +631,37 @@ class _TrajectorySweepMixin:
     """Shared dense sweep: every (time sample, link) against every environment cloud in one fused
     FK + K2 launch per environment."""
 
+    # set True (and initialise torch.distributed) to split the time samples into contiguous blocks
+    # across ranks; the deepest sample is then agreed on with dist.argmin_allreduce (SURVEY.md 8e, C4)
+    shard_time_blocks = False
+
     def _sweep(self, links, envs, levels):
+        from . import dist
         tc = self.trajectory
         kin = tc.kinematics
         q, t, is_ms, edge, u = _dense_time_samples(tc.trajectory, levels)
-        best = None
-        for j, env in enumerate(envs):
-            dmin, arg, _ = kin.context.robot_min_distance(kin.robot_h, tc.robot.numLinks(), kin.link_grids, links,
-                                                          env._dev.cloud_h, env._T12, q, flags=BULK_FLAGS)
-            # tie-break like the reference's visiting order: milestones before interior samples
-            # (samples are already ordered that way), then the order of `links`
-            flat = int(np.argmin(dmin))          # first occurrence in (sample, link) order
-            s, k = divmod(flat, len(links))
-            cand = (float(dmin[s, k]), links[k], j, float(t[s]), int(arg[s, k]))
-            if best is None or cand[0] < best[0]:
-                best = cand
-        self.last_sweep_queries = len(q) * len(links) * sum(e._dev.ctx.cloud_size(e._dev.cloud_h) for e in envs)
-        return best
+        lo, hi = dist.shard_range(len(q)) if self.shard_time_blocks else (0, len(q))
+        # candidates are ordered by (value, env, sample, link position): milestones come before
+        # interior samples and `links` keeps the reference's visiting order, so ties resolve the
+        # same way on one GPU and across ranks
+        best = (float('inf'), -1, -1, -1, -1)
+        if hi > lo:
+            for j, env in enumerate(envs):
+                dmin, arg, _ = kin.context.robot_min_distance(kin.robot_h, tc.robot.numLinks(), kin.link_grids, links,
+                                                              env._dev.cloud_h, env._T12, q[lo:hi], flags=BULK_FLAGS)
+                flat = int(np.argmin(dmin))          # first occurrence in (sample, link) order
+                s, k = divmod(flat, len(links))
+                cand = (float(dmin[s, k]), j, lo + s, k, int(arg[s, k]))
+                if cand[:4] < best[:4]:
+                    best = cand
+        self.last_sweep_queries = (hi - lo) * len(links) * sum(e._dev.ctx.cloud_size(e._dev.cloud_h) for e in envs)
+        if self.shard_time_blocks:
+            v, payload = dist.argmin_allreduce(best[0], best[1:])
+            best = (v,) + tuple(int(x) for x in payload)
+        dmin, j, s, k, idx = best
+        if idx < 0:
+            return (dmin, -1, -1, 0.0, -1)
+        return (dmin, links[k], j, float(t[s]), idx)
 
     def _world_point(self, env, idx):
         p = env._dev.cloud32[idx].astype(np.float64)

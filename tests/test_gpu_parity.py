@@ -181,3 +181,60 @@ def test_cloud_query_dev_layout(ctx, O):
     ctx.cloud_query_dev(g, c, dT.data_ptr(), 5, F32, outd.data_ptr(), None)
     ctx.sync()
     assert np.abs(outd.cpu().numpy() - d0[:, perm]).max() <= 2e-6
+
+
+# ---- sub-tile culling (SIO_PRUNE): identical results, fewer queries -----------------------------------------
+PRUNE = 8
+
+
+@pytest.mark.parametrize("case", ["cube_chair", "tree_bunny", "random_grid"])
+def test_pruned_sweep_is_exact(ctx, O, case):
+    rng = np.random.default_rng(60)
+    if case == "cube_chair":
+        vg = util.fixture_geometry("cube").convert("VolumeGrid", 0.05).getVolumeGrid()
+        cloud = (util.fixture_geometry("m797").convert("PointCloud", 0.01).getPointCloud().points + [0.3, 0, 0]).astype(np.float32)
+        T = util.invert12(util.random_poses(61, 40, rot=0.4, trans=0.5, center=(0.3, 0.2, 0.2)))
+    elif case == "tree_bunny":
+        tree = util.fixture_geometry("m1062")
+        vg = tree.convert("VolumeGrid", 0.02).getVolumeGrid()
+        b = util.fixture_geometry("bunny").getPointCloud().points
+        lo, hi = tree.data.bbox()
+        j = np.arange(1 << 16) % len(b)
+        cloud = (4.0 * (b[j] - b.mean(0)) + 0.5 * (lo + hi) + rng.normal(0, 0.005, (1 << 16, 3))).astype(np.float32)
+        T = util.invert12(util.random_poses(62, 24, rot=0.3, trans=0.1))
+    else:
+        vg = util.random_grid(63)          # not an SDF at all: the Lipschitz bound must still be valid
+        cloud = rng.uniform(-0.5, 1.6, (30000, 3)).astype(np.float32)
+        T = util.random_poses(64, 20, rot=0.6, trans=0.3)
+    g, G = _mk(ctx, O, vg)
+    c = ctx.cloud_create(cloud)
+    bound = np.where(np.arange(len(T)) % 3 == 0, np.inf, -0.01 + 0.03 * rng.uniform(size=len(T)))
+    d0, a0, n0 = ctx.min_distance(g, c, T, bound=bound, flags=F32)
+    u0 = ctx.under_fetch()
+    d1, a1, n1 = ctx.min_distance(g, c, T, bound=bound, flags=F32 | PRUNE)
+    u1 = ctx.under_fetch()
+    ev, tot = ctx.last_prune_stats()
+    assert np.array_equal(a0, a1) and np.array_equal(d0, d1) and np.array_equal(n0, n1)
+    for x, y in zip(u0, u1):
+        assert np.array_equal(x, y)
+    do, ao = O.min_distance(G, cloud, T, bound=bound)
+    assert np.array_equal(a1, ao) and np.abs(d1 - do).max() <= 1e-12
+    assert 0 < ev <= tot and tot == len(T) * ((len(cloud) + 1023) // 1024) * 8
+    print("prune", case, "evaluated %d of %d sub-tiles" % (ev, tot))
+    if case == "tree_bunny":
+        assert ev < 0.5 * tot, (ev, tot)          # a dense cloud against a true SDF prunes most sub-tiles
+    ctx.cloud_destroy(c)
+    ctx.grid_destroy(g)
+
+
+def test_pruned_multi_grid(ctx, O):
+    vgs = [util.sphere_grid(r=0.3 + 0.1 * k, n=24 + 4 * k, half=0.8) for k in range(3)]
+    pairs = [_mk(ctx, O, vg) for vg in vgs]
+    rng = np.random.default_rng(70)
+    cloud = rng.uniform(-1.5, 1.5, (20000, 3)).astype(np.float32)
+    c = ctx.cloud_create(cloud)
+    T = util.random_poses(71, 45, rot=0.6, trans=0.4)
+    gob = rng.integers(0, 3, len(T)).astype(np.int32)
+    dmin, arg, _ = ctx.min_distance([p[0] for p in pairs], c, T, grid_of_b=gob, flags=F32 | PRUNE)
+    d0, a0 = O.min_distance([p[1] for p in pairs], cloud, T, grid_of_b=gob)
+    assert np.array_equal(arg, a0) and np.abs(dmin - d0).max() <= 1e-12
