@@ -253,7 +253,8 @@ int sio_grid_create(sio_ctx* c, const float* values, const int32_t dims[3], cons
         if (!(v == v)) return fail(SIO_ERR_INVALID, "sio_grid_create: NaN sample at flat index %zu", k);
         vmin = std::min(vmin, v); vmax = std::max(vmax, v);
     }
-    // 8-corner bricks: one 32-byte record per cell (i0 in [0, dim-1]; corner +1 comes from the padded copy)
+    // bricks: one 32-byte record per cell (i0 in [0, dim-1]; corner +1 comes from the padded copy), first as the
+    // 8 corner samples [v000 v001 v010 v011 v100 v101 v110 v111], converted to monomial coefficients below
     std::vector<float> brick((size_t)nx * ny * nz * 8);
     for (int i = 0; i < nx; ++i)
         for (int j = 0; j < ny; ++j)
@@ -281,6 +282,16 @@ int sio_grid_create(sio_ctx* c, const float* values, const int32_t dims[3], cons
             ex /= hx; ey /= hy; ez /= hz;
             lip = std::max(lip, std::sqrt(ex * ex + ey * ey + ez * ez));
         }
+    }
+    // corner samples -> monomial coefficients (Moebius transform per axis bit, in float64)
+    for (size_t cidx = 0, nc = (size_t)nx * ny * nz; cidx < nc; ++cidx) {
+        float* q = brick.data() + cidx * 8;
+        double m[8];
+        for (int k = 0; k < 8; ++k) m[k] = q[k];
+        for (int bit = 1; bit < 8; bit <<= 1)
+            for (int k = 0; k < 8; ++k)
+                if (k & bit) m[k] -= m[k ^ bit];
+        for (int k = 0; k < 8; ++k) q[k] = (float)m[k];
     }
     GridH g;
     g.meta.lip = (float)(lip * (1.0 + 1e-6)) + 1e-6f;
@@ -507,7 +518,7 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
     CU(cudaMemsetAsync(c->s_cnt.p, 0, sizeof(uint32_t), st));
     if (d_n_under) CU(cudaMemsetAsync(d_n_under, 0, (size_t)B * sizeof(int32_t), st));
     MinArgs a{};
-    a.pts = p.d_pts; a.perm = p.d_perm; a.N = p.n;
+    a.pts = p.d_pts; a.perm = p.d_perm; a.N = p.n; a.rep = p.d_rep;
     a.grids = c->s_gridtab.as<GridDev>(); a.grid_of_b = d_grid_of_b;
     a.single_grid = nullptr;
     if (n_grids == 1) { c->single_grid_host = c->grids[grids[0]].meta; a.single_grid = &c->single_grid_host; }
@@ -532,7 +543,7 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
         CU(c->h_icnt.ensure(sizeof(uint32_t) * max_batches));
         CU(cudaMemsetAsync(c->s_ub.p, 0xff, (size_t)B * sizeof(uint32_t), st));
         CU(cudaMemsetAsync(c->s_icnt.p, 0, sizeof(uint32_t) * ((B + Bc - 1) / Bc), st));
-        a.xf = c->s_xf.as<XfRec>(); a.rep = p.d_rep; a.lb = c->s_lb.as<float>(); a.ub = c->s_ub.as<uint32_t>();
+        a.xf = c->s_xf.as<XfRec>(); a.lb = c->s_lb.as<float>(); a.ub = c->s_ub.as<uint32_t>();
         a.items = c->s_items.as<uint32_t>();
         launch_prep_xf(a, st);
         c->launches += 1;

@@ -16,9 +16,10 @@ constexpr int kXfChunk = 32;         // transforms processed per CTA of the min 
 // clamped corner of Appendix A.2 step 3.
 struct GridDev {
     const float* v;
-    // the same samples as 8-corner bricks: cell (i,j,k) -> 8 floats [v000 v001 v010 v011 v100 v101
-    // v110 v111] at ((i*ny + j)*nz + k)*8, 32-byte aligned, so one 256-bit load fetches a query's
-    // corners (the fp32 bulk kernels read this; the fp64 kernels read `v`)
+    // the same samples as 32-byte BRICKS: cell (i,j,k) -> the 8 monomial coefficients of its trilinear
+    // interpolant, c[4a+2b+c] multiplying fx^a fy^b fz^c (f = offset from the low corner in cell units,
+    // formed in float64 from the 8 corner samples), at ((i*ny + j)*nz + k)*8, 32-byte aligned: one 256-bit
+    // load fetches everything a query needs (the fp32 kernels read this; the fp64 kernels read `v`)
     const float* brick;
     int32_t nx, ny, nz;
     int32_t sx, sy;              // element strides of the padded copy: sy = nz+1, sx = (ny+1)*(nz+1)
@@ -35,7 +36,7 @@ struct __align__(16) XfRec {
     float thr;                   // candidate threshold: bound + tau (+inf: no under-bound list)
     float hix, hiy, hiz;         // dim-1 (upper clamp of the interpolation coordinate)
     int32_t sx;                  // cell stride in x: ny*nz
-    const float* v;              // the grid's 8-corner bricks
+    const float* v;              // the grid's bricks (monomial coefficients)
     int32_t sy;                  // cell stride in y: nz
     float lip;                   // Lipschitz constant of the grid's interpolant (sub-tile culling)
 };
@@ -58,6 +59,8 @@ __host__ __device__ inline uint32_t fkey(float f) {
 #endif
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+// the same key from the float's bit pattern (the bulk pass stores raw float bits per sub-tile)
+__host__ __device__ inline uint32_t fkey_bits(uint32_t u) { return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __host__ __device__ inline float fkey_inv(uint32_t k) {
     uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
 #ifdef __CUDA_ARCH__
@@ -76,12 +79,13 @@ struct MinArgs {
     int64_t B;                                          // total transforms (xf, T_rel, bound, outputs are [B])
     int64_t b_begin, Bc;                                // the batch [b_begin, b_begin+Bc) this launch covers
     double tau;
-    uint32_t* subkeys; int32_t ntiles;                  // scratch [Bc * ntiles*8]: one key per 128-point sub-tile
+    uint32_t* subkeys; int32_t ntiles;                  // scratch [Bc * ntiles*8]: float32 min (raw bits) per 128-point sub-tile
     XfRec* xf;                                          // scratch [B]
     Cand* cand; uint32_t* cand_count; uint32_t cand_cap;
     int32_t* n_under;                                   // device [B] counters of the exact under-bound set, or null
-    // sub-tile culling (SIO_PRUNE): representative point + radius per sub-tile, lower bounds, upper bounds, work list
-    const float4* rep; float* lb; uint32_t* ub; uint32_t* items; uint32_t* item_count;
+    const float4* rep;                                  // bounding sphere (a cloud point + radius) per 128-point sub-tile
+    // sub-tile culling (SIO_PRUNE): lower bounds, upper bounds, work list
+    float* lb; uint32_t* ub; uint32_t* items; uint32_t* item_count;
     double* dmin; int64_t* argmin;                      // device outputs
     int normalize;
 };

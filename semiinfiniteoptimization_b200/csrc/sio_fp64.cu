@@ -1,7 +1,7 @@
 // sio_fp64.cu -- float64 kernels of the collision oracle (sm_100a), compiled with --fmad=false so
 // the arithmetic is the plain IEEE sequence of SURVEY.md Appendix A.2 (no contraction).
 //
-//   k_finalize   exact (d, index) minimum per transform from the fp32 pass's sub-tile keys
+//   k_finalize   exact (d, index) minimum per transform from the fp32 pass's sub-tile minima
 //   k_recheck    exact re-evaluation of the fp32 pass's under-bound candidates
 //   k_query_f64  K1 in float64 (PenetrationDepthGeometry.distance / normal, gopt:104-108, 153)
 //   k_pose_rows  K3 pose rows  [ (R(pt-t)) x n , n ]            (gopt:413-418)
@@ -107,7 +107,7 @@ k_finalize(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int
     if (!scan_all) {
         // 1) fp32 minimum over the sub-tile keys
         uint32_t k = 0xffffffffu;
-        for (int64_t s = tid; s < nsub; s += kFinThreads) k = min(k, subkeys[bl * nsub + s]);
+        for (int64_t s = tid; s < nsub; s += kFinThreads) k = min(k, fkey_bits(subkeys[bl * nsub + s]));
         s_key[tid] = k;
         __syncthreads();
         for (int w = kFinThreads / 2; w > 0; w >>= 1) {
@@ -118,7 +118,7 @@ k_finalize(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int
         // 2) sub-tiles that may hold the exact minimum: key <= m32 + tau  (fp32 error << tau)
         const uint32_t kthr = fkey(__double2float_ru((double)m32 + tau));
         for (int64_t s = tid; s < nsub; s += kFinThreads) {
-            if (subkeys[bl * nsub + s] <= kthr) {
+            if (fkey_bits(subkeys[bl * nsub + s]) <= kthr) {
                 int slot = atomicAdd(&s_nlist, 1);
                 if (slot < kMaxList) s_list[slot] = (int32_t)s;
             }

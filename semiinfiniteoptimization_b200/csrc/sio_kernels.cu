@@ -18,14 +18,17 @@
 // the sub-tiles within tau of the minimum, which makes the final arg-min identical to the float64
 // oracle's.
 #include "sio_common.cuh"
+#include <cstdlib>
 
 namespace sio {
 
-// floor + fraction of a clamped, non-negative coordinate with FADD.RZ (no F2I/I2F on the XU pipe)
-__device__ __forceinline__ void split_rz(float c, int& i, float& f) {
-    const float big = 8388608.0f;                 // 2^23: c + 2^23 rounded toward zero = floor(c) + 2^23
+// floor + fraction of a non-negative lattice coordinate with FADD.RZ (no F2I/I2F on the XU pipe):
+// c + 2^23 rounded toward zero = floor(c) + 2^23, whose bit pattern is kFloorBias + floor(c).
+constexpr uint32_t kFloorBias = 0x4B000000u;
+__device__ __forceinline__ void split_rz(float c, uint32_t& bits, float& f) {
+    const float big = 8388608.0f;
     float t = __fadd_rz(c, big);
-    i = __float_as_int(t) - 0x4B000000;
+    bits = __float_as_uint(t);
     f = c - (t - big);
 }
 
@@ -35,37 +38,47 @@ __device__ __forceinline__ float min3(float a, float b, float c) {
     return r;
 }
 
-// the 8 corners of one cell: [v000 v001 v010 v011 v100 v101 v110 v111], 32-byte aligned
-struct Cell { float v[8]; };
-__device__ __forceinline__ Cell load_cell(const float* __restrict__ brick, int cell) {
-    Cell c;
+// warp-wide float minimum in one instruction (redux.sync on f32 is new with sm_100a)
+__device__ __forceinline__ float warp_min_f32(float v) {
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// One cell of the grid as the 8 MONOMIAL coefficients of its trilinear interpolant,
+//     v(fx,fy,fz) = sum_m c[m] fx^m2 fy^m1 fz^m0,   m = 4*m2 + 2*m1 + m0,
+// (f = offset from the cell's low corner in cell units), 32 bytes = one sector, fetched with ONE
+// 256-bit read-only load.  Horner evaluation is 7 FMAs (the corner form needs 7 FMAs + 7 subtractions)
+// and the analytic gradient reuses its partial sums.  Coefficients are formed in float64 on the host.
+struct Cell { float c[8]; };
+__device__ __forceinline__ Cell load_cell(const float* __restrict__ brick, uint32_t cell) {
+    Cell q;
     const float* p = brick + (size_t)cell * 8;
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(c.v[0]), "=f"(c.v[1]), "=f"(c.v[2]), "=f"(c.v[3]), "=f"(c.v[4]), "=f"(c.v[5]), "=f"(c.v[6]), "=f"(c.v[7])
+        : "=f"(q.c[0]), "=f"(q.c[1]), "=f"(q.c[2]), "=f"(q.c[3]), "=f"(q.c[4]), "=f"(q.c[5]), "=f"(q.c[6]), "=f"(q.c[7])
         : "l"(p));
-    return c;
+    return q;
 }
 
 // what the inner loop needs to know about the grid of the current transform
 struct GridK {
     const float* brick;
-    int cx, cz;                  // cell strides: cell = ix*cx + iy*cz + iz   (cx = ny*nz, cz = nz)
+    uint32_t cx, cz;             // cell strides: cell = ix*cx + iy*cz + iz   (cx = ny*nz, cz = nz)
+    uint32_t nbias;              // -kFloorBias*(cx+cz+1) mod 2^32: folds the three floor biases into the cell index
     float hx, hy, hz;            // cell size
     float hix, hiy, hiz;         // dim-1
 };
 
 // trilinear value at lattice coordinates already inside [0, dim-1]
 __device__ __forceinline__ float lattice_value(const GridK& g, float cx, float cy, float cz) {
-    int ix, iy, iz; float fx, fy, fz;
-    split_rz(cx, ix, fx); split_rz(cy, iy, fy); split_rz(cz, iz, fz);
-    Cell c = load_cell(g.brick, ix * g.cx + iy * g.cz + iz);
-    float a00 = fmaf(fz, c.v[1] - c.v[0], c.v[0]);
-    float a01 = fmaf(fz, c.v[3] - c.v[2], c.v[2]);
-    float a10 = fmaf(fz, c.v[5] - c.v[4], c.v[4]);
-    float a11 = fmaf(fz, c.v[7] - c.v[6], c.v[6]);
-    float b0 = fmaf(fy, a01 - a00, a00);
-    float b1 = fmaf(fy, a11 - a10, a10);
-    return fmaf(fx, b1 - b0, b0);
+    uint32_t bx, by, bz; float fx, fy, fz;
+    split_rz(cx, bx, fx); split_rz(cy, by, fy); split_rz(cz, bz, fz);
+    Cell q = load_cell(g.brick, bx * g.cx + (by * g.cz + (bz + g.nbias)));
+    float a = fmaf(q.c[7], fz, q.c[6]);          // coefficient of fx fy
+    float b = fmaf(q.c[5], fz, q.c[4]);          // coefficient of fx
+    float c = fmaf(q.c[3], fz, q.c[2]);          // coefficient of fy
+    float d = fmaf(q.c[1], fz, q.c[0]);
+    return fmaf(fmaf(a, fy, b), fx, fmaf(c, fy, d));
 }
 
 // general point: clamp to the lattice, add the distance to the bbox [-1/2, dim-1/2] (Appendix A.2)
@@ -84,18 +97,27 @@ __device__ __forceinline__ float clamped_value(const GridK& g, float ux, float u
     return val + dout;
 }
 
-// >= 0 iff the lattice coordinate lies inside [0, hi] on all three axes
-__device__ __forceinline__ float inside_margin(const GridK& g, float ux, float uy, float uz) {
-    float t = min3(ux, g.hix - ux, uy);
-    t = min3(t, g.hiy - uy, uz);
-    return fminf(t, g.hiz - uz);
-}
-
 __device__ __forceinline__ GridK grid_of(const XfRec& r) {
     GridK g;
-    g.brick = r.v; g.cx = r.sx; g.cz = r.sy;
+    g.brick = r.v; g.cx = (uint32_t)r.sx; g.cz = (uint32_t)r.sy;
+    g.nbias = 0u - kFloorBias * (g.cx + g.cz + 1u);
     g.hx = r.hx; g.hy = r.hy; g.hz = r.hz; g.hix = r.hix; g.hiy = r.hiy; g.hiz = r.hiz;
     return g;
+}
+
+// Is the bounding sphere (centre p, radius p.w, cloud-local) of a group of points, mapped by the
+// transform of record r, entirely inside the sample lattice [0, dim-1]^3?  Then every point of the
+// group takes the unclamped path.  Row a of M has norm 1/h_a, so the sphere spans r/h_a cells on axis a;
+// 1/64 cell of slack covers the float32 rounding of the lattice coordinates (~1e-5 cells).
+__device__ __forceinline__ bool sphere_in_lattice(const XfRec& r, float4 p) {
+    float ux = fmaf(r.m[0], p.x, fmaf(r.m[1], p.y, fmaf(r.m[2], p.z, r.m[3])));
+    float uy = fmaf(r.m[4], p.x, fmaf(r.m[5], p.y, fmaf(r.m[6], p.z, r.m[7])));
+    float uz = fmaf(r.m[8], p.x, fmaf(r.m[9], p.y, fmaf(r.m[10], p.z, r.m[11])));
+    float ex = __fdividef(p.w, r.hx) + 0.015625f, ey = __fdividef(p.w, r.hy) + 0.015625f, ez = __fdividef(p.w, r.hz) + 0.015625f;
+    float m = min3(ux - ex, r.hix - ux - ex, uy - ey);
+    m = min3(m, r.hiy - uy - ey, uz - ez);
+    m = fminf(m, r.hiz - uz - ez);
+    return m >= 0.0f;                 // false for NaN
 }
 
 // value + gradient w.r.t. the input point (cloud-local), optionally normalised
@@ -112,21 +134,20 @@ __device__ __forceinline__ float eval32_grad(const XfRec& r, float px, float py,
     float cx = fminf(fmaxf(ux, 0.0f), r.hix);
     float cy = fminf(fmaxf(uy, 0.0f), r.hiy);
     float cz = fminf(fmaxf(uz, 0.0f), r.hiz);
-    int ix, iy, iz; float fx, fy, fz;
-    split_rz(cx, ix, fx); split_rz(cy, iy, fy); split_rz(cz, iz, fz);
-    Cell c = load_cell(r.v, ix * r.sx + iy * r.sy + iz);
-    float dz00 = c.v[1] - c.v[0], dz01 = c.v[3] - c.v[2], dz10 = c.v[5] - c.v[4], dz11 = c.v[7] - c.v[6];
-    float a00 = fmaf(fz, dz00, c.v[0]), a01 = fmaf(fz, dz01, c.v[2]);
-    float a10 = fmaf(fz, dz10, c.v[4]), a11 = fmaf(fz, dz11, c.v[6]);
-    float dy0 = a01 - a00, dy1 = a11 - a10;
-    float b0 = fmaf(fy, dy0, a00), b1 = fmaf(fy, dy1, a10);
-    float dx = b1 - b0;
-    float val = fmaf(fx, dx, b0);
-    float gz0 = fmaf(fy, dz01 - dz00, dz00), gz1 = fmaf(fy, dz11 - dz10, dz10);
+    uint32_t bx_, by_, bz_; float fx, fy, fz;
+    split_rz(cx, bx_, fx); split_rz(cy, by_, fy); split_rz(cz, bz_, fz);
+    const uint32_t sx = (uint32_t)r.sx, sy = (uint32_t)r.sy;
+    Cell q = load_cell(r.v, bx_ * sx + (by_ * sy + (bz_ + (0u - kFloorBias * (sx + sy + 1u)))));
+    float a = fmaf(q.c[7], fz, q.c[6]);          // coefficient of fx fy
+    float b = fmaf(q.c[5], fz, q.c[4]);          // coefficient of fx
+    float c = fmaf(q.c[3], fz, q.c[2]);          // coefficient of fy
+    float d = fmaf(q.c[1], fz, q.c[0]);
+    float dx = fmaf(a, fy, b);                   // dv/dfx
+    float val = fmaf(dx, fx, fmaf(c, fy, d));
     // derivative w.r.t. the cell coordinate, zero on clamped axes (Appendix A.2 step 3/5)
     float gfx = (ux > 0.0f && ux < r.hix) ? dx : 0.0f;
-    float gfy = (uy > 0.0f && uy < r.hiy) ? fmaf(fx, dy1 - dy0, dy0) : 0.0f;
-    float gfz = (uz > 0.0f && uz < r.hiz) ? fmaf(fx, gz1 - gz0, gz0) : 0.0f;
+    float gfy = (uy > 0.0f && uy < r.hiy) ? fmaf(a, fx, c) : 0.0f;
+    float gfz = (uz > 0.0f && uz < r.hiz) ? fmaf(fmaf(q.c[7], fy, q.c[5]), fx, fmaf(q.c[3], fy, q.c[1])) : 0.0f;
     float dout = sqrtf(dout2);
     if (dout2 > 0.0f) {
         float inv = 1.0f / dout;
@@ -184,26 +205,22 @@ void launch_prep_xf(const MinArgs& a, cudaStream_t st) {
 }
 
 // One warp, one transform, the warp's 128 points (4 per lane): trilinear values, candidates for the
-// under-bound set, and the order-preserving key of the warp's minimum (returned in every lane).
-__device__ __forceinline__ uint32_t warp_subtile_min(const XfRec& r, const GridK& g, const float (&px)[kPtsPerThread],
-                                                     const float (&py)[kPtsPerThread], const float (&pz)[kPtsPerThread],
-                                                     int32_t b, int32_t base, int lane, Cand* __restrict__ cand,
-                                                     uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
-    float ux[kPtsPerThread], uy[kPtsPerThread], uz[kPtsPerThread], d[kPtsPerThread];
-    float margin = INFINITY;
+// under-bound set, and the warp's float32 minimum (returned in every lane).
+// kInside: the caller has shown that all 128 points lie inside the sample lattice, so neither the
+// clamps nor the bbox-overshoot distance are needed -- 9 FMA transform, 3 x (FADD.RZ, FADD, FADD)
+// floor/fraction, 4 integer ops of addressing, one LDG.256, 7 FMA Horner per query.
+template <bool kInside>
+__device__ __forceinline__ float warp_subtile_min(const XfRec& r, const GridK& g, const float (&px)[kPtsPerThread],
+                                                  const float (&py)[kPtsPerThread], const float (&pz)[kPtsPerThread],
+                                                  int32_t b, int32_t base, int lane, Cand* __restrict__ cand,
+                                                  uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
+    float d[kPtsPerThread];
 #pragma unroll
     for (int j = 0; j < kPtsPerThread; ++j) {
-        ux[j] = fmaf(r.m[0], px[j], fmaf(r.m[1], py[j], fmaf(r.m[2], pz[j], r.m[3])));
-        uy[j] = fmaf(r.m[4], px[j], fmaf(r.m[5], py[j], fmaf(r.m[6], pz[j], r.m[7])));
-        uz[j] = fmaf(r.m[8], px[j], fmaf(r.m[9], py[j], fmaf(r.m[10], pz[j], r.m[11])));
-        margin = fminf(margin, inside_margin(g, ux[j], uy[j], uz[j]));
-    }
-    if (__all_sync(0xffffffffu, margin >= 0.0f)) {         // whole warp inside the sample lattice
-#pragma unroll
-        for (int j = 0; j < kPtsPerThread; ++j) d[j] = lattice_value(g, ux[j], uy[j], uz[j]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < kPtsPerThread; ++j) d[j] = clamped_value(g, ux[j], uy[j], uz[j]);
+        float ux = fmaf(r.m[0], px[j], fmaf(r.m[1], py[j], fmaf(r.m[2], pz[j], r.m[3])));
+        float uy = fmaf(r.m[4], px[j], fmaf(r.m[5], py[j], fmaf(r.m[6], pz[j], r.m[7])));
+        float uz = fmaf(r.m[8], px[j], fmaf(r.m[9], py[j], fmaf(r.m[10], pz[j], r.m[11])));
+        d[j] = kInside ? lattice_value(g, ux, uy, uz) : clamped_value(g, ux, uy, uz);
     }
     float best = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
     static_assert(kPtsPerThread == 4, "min tree assumes 4 points per thread");
@@ -219,27 +236,30 @@ __device__ __forceinline__ uint32_t warp_subtile_min(const XfRec& r, const GridK
             }
         }
     }
-    return __reduce_min_sync(0xffffffffu, fkey(best));
+    return warp_min_f32(best);
 }
 
 // ---- K2 bulk pass ---------------------------------------------------------------------------------
-// grid  = nchunks * ntiles CTAs (chunk-major: consecutive CTAs share the transform chunk)
-// output: subkeys[b_local * nsub + (tile*8 + warp)] = fkey(min over the warp's 128 points)
+// grid  = nchunks * ntiles CTAs (chunk-major: consecutive CTAs share the transform chunk); a chunk is
+//         `xfchunk` <= 32 transforms, chosen by the launcher so that the CTA count is many waves
+// output: subkeys[b_local * nsub + (tile*8 + warp)] = bits of the float32 min over the warp's 128 points
 // kMulti = false: every transform uses the one grid passed by value in `gk` (uniform registers);
 // kMulti = true : the grid comes with each transform record (robot links).
 // The cloud is padded to a whole tile with copies of its last point, so no per-point bounds test.
+// Lane l of every warp tests the warp's bounding sphere (rep[sub]) against the lattice of transform l
+// of the chunk; the ballot is the per-transform choice between the unclamped and the general path.
 template <bool kMulti>
 __global__ void __launch_bounds__(kThreads, 4)
-k_min_f32(const float4* __restrict__ pts, const GridDev* __restrict__ grids, const int32_t* __restrict__ grid_of_b,
-          const double* __restrict__ T_rel, const double* __restrict__ bound, double tau,
-          int64_t b_begin, int64_t Bc, int32_t ntiles, uint32_t* __restrict__ subkeys, Cand* __restrict__ cand,
+k_min_f32(const float4* __restrict__ pts, const float4* __restrict__ rep, const GridDev* __restrict__ grids,
+          const int32_t* __restrict__ grid_of_b, const double* __restrict__ T_rel, const double* __restrict__ bound, double tau,
+          int64_t b_begin, int64_t Bc, int32_t ntiles, int32_t xfchunk, uint32_t* __restrict__ subkeys, Cand* __restrict__ cand,
           uint32_t* __restrict__ cand_count, uint32_t cand_cap, GridK gk) {
     __shared__ XfRec sxf[kXfChunk];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t chunk = blockIdx.x / ntiles;
     const int32_t tile = (int32_t)(blockIdx.x - chunk * ntiles);
-    const int64_t b0 = chunk * kXfChunk;                 // batch-local index of the chunk's first transform
-    const int nb = (int)min((int64_t)kXfChunk, Bc - b0);
+    const int64_t b0 = chunk * xfchunk;                  // batch-local index of the chunk's first transform
+    const int nb = (int)min((int64_t)xfchunk, Bc - b0);
     if (tid < nb) {
         // fold this chunk's float64 transforms into float32 records in the prologue (no separate
         // launch): thread t builds the record of transform t
@@ -252,45 +272,63 @@ k_min_f32(const float4* __restrict__ pts, const GridDev* __restrict__ grids, con
         sxf[tid] = make_xf(grids[grid_of_b ? grid_of_b[b] : 0], T_rel + 12 * b, thr);
     }
     // this warp's 128 contiguous points: lane l holds base + j*32 + l
-    const int64_t base = (int64_t)tile * kTile + warp * (32 * kPtsPerThread);
+    const int64_t sub = (int64_t)tile * (kThreads / 32) + warp;
+    const int64_t base = sub * (32 * kPtsPerThread);
     float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
 #pragma unroll
     for (int j = 0; j < kPtsPerThread; ++j) {
         float4 p = __ldg(pts + base + j * 32 + lane);
         px[j] = p.x; py[j] = p.y; pz[j] = p.z;
     }
+    const float4 sphere = __ldg(rep + sub);
     __syncthreads();
+    const uint32_t inmask = __ballot_sync(0xffffffffu, lane < nb && sphere_in_lattice(sxf[lane < nb ? lane : 0], sphere));
     const int64_t nsub = (int64_t)ntiles * (kThreads / 32);
-    const int64_t sub = (int64_t)tile * (kThreads / 32) + warp;
+    float mine = INFINITY;                               // lane l keeps the minimum under transform l of the chunk
     for (int bl = 0; bl < nb; ++bl) {
         const XfRec& r = sxf[bl];
         const GridK g = kMulti ? grid_of(r) : gk;
-        uint32_t k = warp_subtile_min(r, g, px, py, pz, (int32_t)(b_begin + b0 + bl), (int32_t)base, lane,
-                                      cand, cand_count, cand_cap);
-        if (lane == 0) subkeys[(b0 + bl) * nsub + sub] = k;
+        const int32_t b = (int32_t)(b_begin + b0 + bl);
+        float m;
+        if ((inmask >> bl) & 1u) m = warp_subtile_min<true>(r, g, px, py, pz, b, (int32_t)base, lane, cand, cand_count, cand_cap);
+        else m = warp_subtile_min<false>(r, g, px, py, pz, b, (int32_t)base, lane, cand, cand_count, cand_cap);
+        mine = (lane == bl) ? m : mine;
     }
+    if (lane < nb) subkeys[(b0 + lane) * nsub + sub] = __float_as_uint(mine);
 }
 
 static GridK host_gridk(const GridDev& g) {
     GridK k;
-    k.brick = g.brick; k.cx = g.ny * g.nz; k.cz = g.nz;
+    k.brick = g.brick; k.cx = (uint32_t)(g.ny * g.nz); k.cz = (uint32_t)g.nz;
+    k.nbias = 0u - kFloorBias * (k.cx + k.cz + 1u);
     k.hx = (float)g.h[0]; k.hy = (float)g.h[1]; k.hz = (float)g.h[2];
     k.hix = (float)(g.nx - 1); k.hiy = (float)(g.ny - 1); k.hiz = (float)(g.nz - 1);
     return k;
 }
 
+// transforms per CTA: as many as possible (the cloud tile is re-read once per chunk) while the launch
+// still has >= 6 waves of 148 SMs x 4 resident CTAs (measured best on the C2 sweep), so the last partial wave costs little
+int min_f32_chunk(int64_t Bc, int32_t ntiles) {
+    static const int forced = getenv("SIO_MIN_CHUNK") ? atoi(getenv("SIO_MIN_CHUNK")) : 0;   // tuning aid
+    if (forced > 0) return forced < kXfChunk ? forced : kXfChunk;
+    int chunk = kXfChunk;
+    while (chunk > 4 && ((Bc + chunk - 1) / chunk) * (int64_t)ntiles < 6 * 148 * 4) chunk >>= 1;
+    return chunk;
+}
+
 void launch_min_f32(const MinArgs& a, cudaStream_t st) {
     if (a.Bc <= 0 || a.N <= 0) return;
-    int64_t nchunks = (a.Bc + kXfChunk - 1) / kXfChunk;
+    const int chunk = min_f32_chunk(a.Bc, a.ntiles);
+    int64_t nchunks = (a.Bc + chunk - 1) / chunk;
     int64_t blocks = nchunks * a.ntiles;
     if (a.single_grid) {
-        k_min_f32<false><<<(unsigned)blocks, kThreads, 0, st>>>(a.pts, a.grids, a.grid_of_b, a.T_rel, a.bound, a.tau, a.b_begin,
-                                                                a.Bc, a.ntiles, a.subkeys, a.cand, a.cand_count, a.cand_cap,
+        k_min_f32<false><<<(unsigned)blocks, kThreads, 0, st>>>(a.pts, a.rep, a.grids, a.grid_of_b, a.T_rel, a.bound, a.tau, a.b_begin,
+                                                                a.Bc, a.ntiles, chunk, a.subkeys, a.cand, a.cand_count, a.cand_cap,
                                                                 host_gridk(*a.single_grid));
     } else {
         GridK dummy{};
-        k_min_f32<true><<<(unsigned)blocks, kThreads, 0, st>>>(a.pts, a.grids, a.grid_of_b, a.T_rel, a.bound, a.tau, a.b_begin,
-                                                               a.Bc, a.ntiles, a.subkeys, a.cand, a.cand_count, a.cand_cap, dummy);
+        k_min_f32<true><<<(unsigned)blocks, kThreads, 0, st>>>(a.pts, a.rep, a.grids, a.grid_of_b, a.T_rel, a.bound, a.tau, a.b_begin,
+                                                               a.Bc, a.ntiles, chunk, a.subkeys, a.cand, a.cand_count, a.cand_cap, dummy);
     }
 }
 
@@ -363,20 +401,21 @@ __global__ void k_prune_select(const float* __restrict__ lb, const uint32_t* __r
         if (bd < (double)INFINITY) thr = fmaxf(thr, __double2float_ru(bd));
     }
     if (lb[e] <= thr + 2.0f * tau) items[atomicAdd(item_count, 1u)] = (uint32_t)e;
-    else subkeys[e] = 0xff800000u;               // fkey(+inf): the finalize pass never opens this sub-tile
+    else subkeys[e] = 0x7f800000u;               // +inf: the finalize pass never opens this sub-tile
 }
 
 constexpr int kItemRun = 8;      // consecutive work items taken by one warp (they mostly share a sub-tile)
 
 __global__ void __launch_bounds__(kThreads, 4)
-k_min_items(const float4* __restrict__ pts, const XfRec* __restrict__ xf, int64_t b_begin, int64_t nsub,
-            const uint32_t* __restrict__ items, const uint32_t* __restrict__ item_count, uint32_t* __restrict__ subkeys,
-            Cand* __restrict__ cand, uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
+k_min_items(const float4* __restrict__ pts, const float4* __restrict__ rep, const XfRec* __restrict__ xf, int64_t b_begin,
+            int64_t nsub, const uint32_t* __restrict__ items, const uint32_t* __restrict__ item_count,
+            uint32_t* __restrict__ subkeys, Cand* __restrict__ cand, uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
     __shared__ XfRec sxf[kThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n = *item_count;
     const uint32_t nwarps = gridDim.x * (kThreads / 32);
     float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
+    float4 sphere = make_float4(0.f, 0.f, 0.f, 0.f);
     int64_t have = -1;                                     // sub-tile whose points sit in registers
     for (uint32_t it0 = (blockIdx.x * (kThreads / 32) + warp) * kItemRun; it0 < n; it0 += nwarps * kItemRun) {
         const uint32_t it1 = min(n, it0 + kItemRun);
@@ -397,10 +436,15 @@ k_min_items(const float4* __restrict__ pts, const XfRec* __restrict__ xf, int64_
                     float4 p = __ldg(pts + base + j * 32 + lane);
                     px[j] = p.x; py[j] = p.y; pz[j] = p.z;
                 }
+                sphere = __ldg(rep + s);
                 have = s;
             }
-            uint32_t k = warp_subtile_min(r, grid_of(r), px, py, pz, (int32_t)b, (int32_t)base, lane, cand, cand_count, cand_cap);
-            if (lane == 0) subkeys[e] = k;
+            float m;
+            if (sphere_in_lattice(r, sphere))      // warp-uniform: every lane tests the same sphere and record
+                m = warp_subtile_min<true>(r, grid_of(r), px, py, pz, (int32_t)b, (int32_t)base, lane, cand, cand_count, cand_cap);
+            else
+                m = warp_subtile_min<false>(r, grid_of(r), px, py, pz, (int32_t)b, (int32_t)base, lane, cand, cand_count, cand_cap);
+            if (lane == 0) subkeys[e] = __float_as_uint(m);
         }
     }
 }
@@ -414,7 +458,7 @@ void launch_min_pruned(const MinArgs& a, cudaStream_t st) {
     const int64_t ne = ((a.Bc + 31) & ~(int64_t)31) * nsub;
     k_prune_select<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(a.lb, a.ub, a.bound, nsub, a.b_begin, a.Bc, (float)a.tau,
                                                                   a.subkeys, a.items, a.item_count);
-    k_min_items<<<148 * 4, kThreads, 0, st>>>(a.pts, a.xf, a.b_begin, nsub, a.items, a.item_count, a.subkeys, a.cand,
+    k_min_items<<<148 * 4, kThreads, 0, st>>>(a.pts, a.rep, a.xf, a.b_begin, nsub, a.items, a.item_count, a.subkeys, a.cand,
                                               a.cand_count, a.cand_cap);
 }
 
