@@ -256,6 +256,17 @@ class RefRobotTrajectoryCache:
         times = [self.tstart + float(i) / (M - 1) * (self.tend - self.tstart) for i in range(M)]
         return RobotTrajectory(self.robot, times, milestones)
 
+    def straightLineState(self):
+        """gopt:357-366."""
+        assert self.qstart is not None, "Need a start config for a straight line state"
+        qend = self.qend if self.qend is not None else self.qstart
+        sshift = 1
+        eshift = 1 if self.qend is not None else 0
+        us = [float(i + sshift) / (self.numPoints + sshift + eshift - 1) for i in range(self.numPoints)]
+        qs = [self.robot.interpolate(self.qstart, qend, u) for u in us]
+        ts = [] if self.times is not True else [self.tstart + u * (self.tend - self.tstart) for u in us]
+        return ts + [v for q in qs for v in q]
+
 
 def intervalLipschitzMinimum(a, b, K):
     """gopt:554-563."""

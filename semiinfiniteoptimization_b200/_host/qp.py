@@ -19,6 +19,7 @@ import scipy.sparse
 import scipy.sparse.linalg
 
 INF = 1e20
+DENSE_MAX_VARS = 64          # callers factor the KKT system densely up to this many variables, sparsely above
 
 
 class QPResult:

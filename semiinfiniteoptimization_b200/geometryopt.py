@@ -85,6 +85,8 @@ class _DeviceGeometry:
         self.grid_h = -1
         self.cloud_h = -1
         self.cloud32 = None      # host float32 copy: arg-min index -> closest point
+        self.T12 = None          # current world transform, row-major 3x4: shared by the copies exactly as the
+                                 # reference's copies share the transform held by their common Geometry3D objects
 
     def upload_grid(self, vg):
         self.grid_h = self.ctx.grid_create(vg.values, vg.bmin, vg.bmax)
@@ -106,7 +108,6 @@ class PenetrationDepthGeometry:
             self.grid = geom.grid
             self.polyhedron = geom.polyhedron
             self._dev = geom._dev
-            self._T12 = geom._T12.copy()
         else:
             assert isinstance(geom, Geometry3D), "geom must be a Geometry3D or PenetrationDepthGeometry"
             self.geom = geom
@@ -128,6 +129,14 @@ class PenetrationDepthGeometry:
                 self.pc = geom.convert('PointCloud', pcres)
                 self.pcdata = self.pc.getPointCloud()
                 self._dev.upload_cloud(self.pcdata.points)
+
+    @property
+    def _T12(self):
+        return self._dev.T12
+
+    @_T12.setter
+    def _T12(self, T12):
+        self._dev.T12 = T12
 
     # -- transforms (gopt:85-94) --
     def setTransform(self, T):

@@ -219,7 +219,6 @@ class ConstraintGenerationData:
         xdes = np.asarray(xdes, dtype=np.float64)
         n = len(xdes)
         m = len(b)
-        big = n > 64
         if isinstance(W, (int, float)):
             P = scipy.sparse.diags([float(W)] * n, format='csc')
         elif scipy.sparse.issparse(W):
@@ -243,7 +242,7 @@ class ConstraintGenerationData:
             u = np.hstack((u, xmax))
 
         def run(Pm, qv, Am):
-            if big:
+            if Pm.shape[0] > _qp.DENSE_MAX_VARS:
                 return _qp.solve_qp(Pm, qv, Am, l, u, eps_abs=1e-5)
             return _qp.solve_qp(Pm.toarray(), qv, Am.toarray(), l, u, eps_abs=1e-5)
 

@@ -1,0 +1,185 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.json by running the REFERENCE's own Python (sip.py, geometryopt.py,
+constraint.py, objective.py from /root/reference, loaded by oracle/refrun with stand-in klampt / osqp
+modules) on BASELINE.json's configurations.  The Klampt-side queries underneath are the CPU oracle
+(a restatement: "parity unpinned" for that layer); every line of SIP / constraint logic above them is
+the reference's.  Needs /root/reference, so it runs in the build container only; the fixtures it writes
+are committed and are what the tests on the GPU box compare against.
+
+    python tools/make_golden.py [--only c1,c2,c3,c4,classes,oracle]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+warnings.simplefilter("ignore")
+
+from tests import scenes  # noqa: E402
+
+
+def _f(v):
+    """JSON-able copy: numpy scalars/arrays -> python floats/lists (repr round-trips float64 exactly)."""
+    if isinstance(v, (list, tuple)):
+        return [_f(x) for x in v]
+    if isinstance(v, np.ndarray):
+        return [_f(x) for x in v.tolist()]
+    if isinstance(v, (np.floating, float)):
+        return float(v)
+    if isinstance(v, (np.integer, int)):
+        return int(v)
+    return v
+
+
+def _quiet(fn, *a, **k):
+    """The reference prints progress unconditionally in a few places."""
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def write(name, obj):
+    os.makedirs(scenes.GOLDEN, exist_ok=True)
+    fn = os.path.join(scenes.GOLDEN, name)
+    obj = dict(obj)
+    obj["_generated_by"] = "tools/make_golden.py: the reference package (/root/reference/semiinfinite) executed via oracle/refrun"
+    json.dump(obj, open(fn, "w"))
+    print("wrote %s (%.1f kB)" % (fn, os.path.getsize(fn) / 1e3))
+
+
+def pose_cases(scene_fn, poses, settings_kw=None):
+    mod, g1, g2, con = scene_fn('reference')
+    sip = sys.modules[mod.__name__.rsplit('.', 1)[0] + '.sip']
+    cases = []
+    for T in poses:
+        st = sip.SemiInfiniteOptimizationSettings()
+        for k, v in (settings_kw or {}).items():
+            setattr(st, k, v)
+        out = _quiet(mod.optimizeCollFree, g1, g2, T, settings=st, verbose=0)
+        cases.append({"Tinit": _f(T), "T": _f(out[0]), "trace": _f(out[1]), "params": _f(out[3])})
+    return cases
+
+
+def gen_c1():
+    write("c1_pose.json", {"config": "C1 cube SDF@0.05 vs m797 cloud@0.02, optimizeCollFree defaults (gopt:1039-1081)",
+                           "cases": pose_cases(scenes.c1_scene, scenes.c1_poses(8, seed=0))})
+
+
+def gen_c2():
+    write("c2_pose.json", {"config": "C2 as shipped: m1062 SDF@0.01 vs bunny.pcd (397 points), optimizeCollFree, max_iters 20",
+                           "cases": pose_cases(scenes.c2_scene, scenes.c2_poses(6, seed=0), {"max_iters": 20})})
+
+
+def gen_c3():
+    mod, robot, cons = _quiet(scenes.c3_scene, 'reference')
+    sip = sys.modules[mod.__name__.rsplit('.', 1)[0] + '.sip']
+    cases = []
+    for qdes in scenes.c3_configs(robot, 6, seed=3):
+        st = sip.SemiInfiniteOptimizationSettings()
+        st.max_iters, st.minimum_constraint_value = 5, -0.02                 # robotposeopt.py:101-104
+        q, trace, times, params = _quiet(mod.optimizeCollFreeRobot, robot, None, qdes=qdes, qinit=[0.0] * 7, constraints=cons,
+                                         settings=st, verbose=0)
+        cases.append({"qdes": _f(qdes), "q": _f(q), "trace": _f(trace), "params": _f(params)})
+    write("c3_robot.json", {"config": "C3 tx90_geom_test3.xml (synthetic link boxes), 7 link constraints, max_iters 5, "
+                                      "minimum_constraint_value -0.02 (robotposeopt.py:101-104)", "cases": cases})
+
+
+def gen_c4():
+    mod, robot, tc, con, traj, x = _quiet(scenes.c4_scene, 'reference')
+    sip = sys.modules[mod.__name__.rsplit('.', 1)[0] + '.sip']
+    rng = np.random.default_rng(0)
+    probes = []
+    for trial in range(3):
+        xa = [float(v) for v in (np.asarray(x) + (rng.normal(0, 0.05, len(x)) if trial else 0))]
+        con.setx(xa)
+        mv = _quiet(con.minvalue, xa)
+        y = mv[1]
+        row = con.df_dx(xa, y).tocoo()
+        probes.append({"x": xa, "dmin": float(mv[0]), "param": _f(y), "value_at_param": float(con.value(xa, y)),
+                       "row_cols": _f(row.col), "row_vals": _f(row.data),
+                       "pruned_by_bound": _quiet(con.minvalue, xa, mv[0] - 1e-6) == []})
+        con.clearx()
+    st = sip.SemiInfiniteOptimizationSettings()
+    st.max_iters, st.minimum_constraint_value = 4, -0.02
+    out = _quiet(mod.optimizeCollFreeTrajectory, tc, traj, env=None, constraints=[con], settings=st, verbose=0)
+    trace = [[float(v) for q in t.milestones[1:-1] for v in q] for t in out[1]]
+    write("c4_traj.json", {"config": "C4 tx90_geom_test2.xml, chair moved to %s, 67 milestones (65 free), "
+                                     "RobotTrajectoryCollisionConstraint, max_iters 4" % (scenes.CHAIR_IN_PATH,),
+                           "x0": x, "minvalue_probes": probes, "trace": trace, "params": _f(out[3])})
+
+
+def gen_classes():
+    """Single calls of the reference's constraint classes: value / minvalue / df_dx (gopt:394-420, 457-484)."""
+    out = {}
+    mod, g1, g2, con = scenes.c1_scene('reference')
+    rng = np.random.default_rng(4)
+    rec = []
+    for T in scenes.c1_poses(5, seed=3):
+        con.setx(T)
+        mv = con.minvalue(T)
+        pts = [[float(v) for v in (np.asarray(mv[1]) + d)] for d in rng.normal(0, 0.02, (4, 3))]
+        rec.append({"T": _f(T), "dmin": float(mv[0]), "argmin_point": _f(mv[1]), "bound_prunes": con.minvalue(T, mv[0] - 1e-3) == [],
+                    "points": pts, "values": [float(con.value(T, p)) for p in pts], "rows": [_f(con.df_dx(T, p)) for p in pts],
+                    "pdg_distance": _f(g1.distance(pts[0])), "pdg_normal": _f(g1.normal(pts[0]))})
+        con.clearx()
+    out["object_constraint"] = rec
+    mod, robot, cons = _quiet(scenes.c3_scene, 'reference')
+    rec = []
+    for q in scenes.c3_configs(robot, 3, seed=2):
+        for c in cons:
+            c.setx(q)
+        per = []
+        for c in cons:
+            mv = c.minvalue(q)
+            pts = [[float(v) for v in (np.asarray(mv[1]) + d)] for d in rng.normal(0, 0.03, (2, 3))]
+            per.append({"dmin": float(mv[0]), "argmin_point": _f(mv[1]), "points": pts,
+                        "values": [float(c.value(q, p)) for p in pts], "rows": [_f(c.df_dx(q, p)) for p in pts]})
+        for c in cons:
+            c.clearx()
+        rec.append({"q": _f(q), "links": per})
+    out["robot_link_constraints"] = rec
+    write("classes.json", out)
+
+
+def gen_oracle():
+    """Known answers of the oracle itself on seeded arrays (regression pin for oracle/sio_oracle.c and for the
+    CUDA kernels): analytic linear field (trilinear interpolation is exact on it) + seeded random grid."""
+    from oracle import oracle as O
+    from tests import util
+    rng = np.random.default_rng(123)
+    vg = util.random_grid(7)
+    G = O.Grid(vg.values, vg.bmin, vg.bmax)
+    T = util.random_poses(8, 6, rot=0.5, trans=0.2)
+    pts = rng.uniform(-0.6, 1.6, (40, 3))
+    d, g = O.query(G, T[0], pts)
+    cloud = rng.uniform(-0.5, 1.5, (5000, 3)).astype(np.float32)
+    bound = np.array([np.inf, 0.0, -0.5, 0.3, np.inf, -1.0])
+    dmin, arg = O.min_distance(G, cloud, T, bound=bound)
+    _, ub, ui, ud = O.under(G, cloud, T, bound)
+    order = np.lexsort((ui, ub))
+    ub, ui, ud = ub[order], ui[order], ud[order]
+    rows_d, rows = O.pose_rows(G, T[1], pts[:9])
+    out = {"grid_seed": 7, "T": _f(T), "pts": _f(pts), "query_d": _f(d), "query_grad": _f(g),
+           "cloud_seed": 123, "bound": [None if not np.isfinite(b) else float(b) for b in bound],
+           "dmin": _f(dmin), "argmin": _f(arg), "under_b": _f(ub), "under_idx": _f(ui), "under_d": _f(ud),
+           "pose_rows_d": _f(rows_d), "pose_rows": _f(rows)}
+    write("oracle_kat.json", out)
+
+
+GENERATORS = {"c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "classes": gen_classes, "oracle": gen_oracle}
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=",".join(GENERATORS))
+    a = ap.parse_args()
+    for k in a.only.split(","):
+        t0 = time.time()
+        GENERATORS[k]()
+        print("  %s: %.1f s" % (k, time.time() - t0))
