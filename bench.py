@@ -51,27 +51,13 @@ UNIT = "queries/s"
 
 
 def build_workload(rank=0):
+    from semiinfiniteoptimization_b200 import workloads
     from semiinfiniteoptimization_b200._host.geometry import fixture_geometry
-    from semiinfiniteoptimization_b200._host import se3, so3
-    tree = fixture_geometry("m1062")
-    vg = tree.convert("VolumeGrid", GRIDRES).getVolumeGrid()
-    b = fixture_geometry("bunny").getPointCloud().points
-    rng = np.random.default_rng(1)
-    lo, hi = tree.data.bbox()
-    centre = 0.5 * (lo + hi)
-    j = np.arange(CLOUD_N) % len(b)
-    cloud = 4.0 * (b[j] - b.mean(0)) + centre + rng.normal(0.0, 0.005, (CLOUD_N, 3))
-    cloud = cloud.astype(np.float32)
-    # poses of the moving body (world <- grid); cloud frame = world.  T_rel = pose^-1
-    prng = np.random.default_rng(1000 + rank)
-    T_rel = np.empty((POSES_PER_GPU, 12))
-    for i in range(POSES_PER_GPU):
-        w = prng.uniform(-0.3, 0.3, 3)
-        t = prng.uniform(-0.1, 0.1, 3)
-        # rotate about the body centre so the pose set stays in contact with the cloud
-        R = so3.from_rotation_vector(w)
-        tt = [float(v) for v in (centre - so3.matrix(R) @ centre + t)]
-        T_rel[i] = se3.to_rowmajor12(se3.inv((R, tt)))
+    vg = fixture_geometry("m1062").convert("VolumeGrid", GRIDRES).getVolumeGrid()
+    cloud, centre = workloads.c2_throughput_cloud(CLOUD_N, seed=1)
+    # poses of the moving body (world <- grid) rotate about the body centre so the pose set stays in contact with the
+    # cloud; cloud frame = world, T_rel = pose^-1
+    T_rel = workloads.c2_throughput_poses(POSES_PER_GPU, centre, seed=1000 + rank)
     bound = np.zeros(POSES_PER_GPU)       # SIP's discovery bound min(0, min depths) (sip.py:215-219)
     return vg, cloud, T_rel, bound
 
@@ -152,6 +138,7 @@ def cpu_baseline(vg, cloud, T_rel, budget_s=12.0, native=True):
         except Exception:
             L = None
     L = L or O.lib()
+    L.orc_set_threads(0)                  # every host core, whatever OMP_NUM_THREADS says
     G = O.Grid(vg.values, vg.bmin, vg.bmax)
     threads = L.orc_max_threads()
     npose = max(1, min(len(T_rel), threads))
@@ -182,6 +169,7 @@ def run_reference(args):
         L = O.lib(prefer_native=True)
     except Exception:
         L = O.lib()
+    L.orc_set_threads(0)                  # torchrun sets OMP_NUM_THREADS=1 for its workers: use every host core
     vg, cloud, T_rel, bound = build_workload(0)
     G = O.Grid(vg.values, vg.bmin, vg.bmax)
     threads = L.orc_max_threads()

@@ -100,7 +100,9 @@ int sio_cloud_perm(sio_ctx* ctx, sio_handle cloud, int32_t* perm_out /* internal
  * outputs per b:  dmin[b] (exact float64 value of the winner), argmin[b] (cloud index, lowest
  * index on exact ties; -1 when bound is finite and dmin >= bound, the wrapper's "[]" case,
  * gopt:411/476), n_under[b] = #{i : d(b,i) < bound[b]} (0 for an infinite bound).
- * The compact under-bound list (b, i, d) sorted by (b, i) is fetched with sio_under_fetch. */
+ * The compact under-bound list (b, i, d) sorted by (b, i) is fetched with sio_under_fetch.
+ * n_under == NULL asks for the minimum / arg-minimum only (what the reference's minvalue consumes): no
+ * under-bound set is produced, sio_under_fetch then returns an empty list. */
 int sio_min_distance(sio_ctx* ctx, const sio_handle* grids, int32_t n_grids, const int32_t* grid_of_b,
                      sio_handle cloud, const double* T_rel, const double* bound, int64_t B, int flags,
                      double* dmin, int64_t* argmin, int32_t* n_under);

@@ -54,6 +54,8 @@ def lib(prefer_native=False):
     P = _c.c_void_p
     I64 = _c.c_int64
     L.orc_max_threads.restype = _c.c_int
+    L.orc_set_threads.argtypes = [_c.c_int]
+    L.orc_set_threads.restype = None
     L.orc_query.argtypes = [P, P, P, I64, _c.c_int, P, P]
     L.orc_cloud_query.argtypes = [P, P, I64, P, I64, _c.c_int, P, P]
     L.orc_min_distance.argtypes = [P, P, P, I64, P, P, I64, P, P]

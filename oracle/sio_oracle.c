@@ -42,6 +42,15 @@ typedef struct {
 } orc_grid;
 
 int orc_version(void) { return 1; }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm of bench.py asks for every host
+ * core explicitly.  n <= 0: all processors. */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+#else
+    (void)n;
+#endif
+}
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

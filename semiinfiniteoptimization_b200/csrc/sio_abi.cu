@@ -522,9 +522,11 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
     a.grids = c->s_gridtab.as<GridDev>(); a.grid_of_b = d_grid_of_b;
     a.single_grid = nullptr;
     if (n_grids == 1) { c->single_grid_host = c->grids[grids[0]].meta; a.single_grid = &c->single_grid_host; }
-    a.T_rel = dT_rel; a.bound = d_bound; a.B = B; a.tau = tau; a.ntiles = ntiles;
+    // no counter array = the caller wants the minimum only: no candidates are produced, no re-check runs
+    const bool want_under = d_bound && d_n_under;
+    a.T_rel = dT_rel; a.bound = d_bound; a.under_bound = want_under ? d_bound : nullptr; a.B = B; a.tau = tau; a.ntiles = ntiles;
     a.cand = c->s_cand.as<Cand>(); a.cand_count = c->s_cnt.as<uint32_t>(); a.cand_cap = c->cand_cap;
-    a.n_under = d_bound ? d_n_under : nullptr;
+    a.n_under = want_under ? d_n_under : nullptr;
     a.dmin = d_dmin; a.argmin = d_argmin;
     const bool prune = !f64 && (flags & SIO_PRUNE) && p.n > 0;
     const int max_batches = 4096;
@@ -566,12 +568,12 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
             if (one_batch) { cudaEventRecord(c->ev_bulk1, st); c->bulk_timed = true; }
             c->launches += (p.n > 0);
         }
-        launch_finalize(a, /*all_tiles=*/f64, /*emit_under=*/f64, st);
+        launch_finalize(a, /*all_tiles=*/f64, /*emit_under=*/f64 && want_under, st);
         c->launches += 1;
     }
-    if (!f64 && d_bound) { launch_recheck(a, st); c->launches += 1; }
+    if (!f64 && want_under) { launch_recheck(a, st); c->launches += 1; }
     CU(cudaGetLastError());
-    c->under_pending = d_bound != nullptr;
+    c->under_pending = want_under;
     c->under_final = f64;
     c->under_valid = !c->under_pending;
     return SIO_OK;
@@ -643,7 +645,7 @@ static int min_distance_host(sio_ctx* c, const sio_handle* grids, int32_t n_grid
     int rc = sio_min_distance_dev(c, grids, n_grids, grid_of_b ? reinterpret_cast<const int32_t*>(din + oG) : nullptr, cloud,
                                   reinterpret_cast<const double*>(din + oT), bound ? reinterpret_cast<const double*>(din + oB) : nullptr,
                                   B, flags, reinterpret_cast<double*>(dout + oD), reinterpret_cast<int64_t*>(dout + oA),
-                                  reinterpret_cast<int32_t*>(dout + oN));
+                                  n_under ? reinterpret_cast<int32_t*>(dout + oN) : nullptr);
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->h_b.p, dout, out_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -846,7 +848,7 @@ int sio_robot_min_distance(sio_ctx* c, sio_handle robot, const sio_handle* link_
     CU(c->s_out1.ensure((size_t)B * sizeof(int64_t)));
     CU(c->s_out2.ensure((size_t)B * sizeof(int32_t)));
     int rc = sio_min_distance_dev(c, sel.data(), n_sel, c->s_gob.as<int32_t>(), cloud, c->s_trel.as<double>(), d_bound, B, flags,
-                                  c->s_out0.as<double>(), c->s_out1.as<int64_t>(), c->s_out2.as<int32_t>());
+                                  c->s_out0.as<double>(), c->s_out1.as<int64_t>(), n_under ? c->s_out2.as<int32_t>() : nullptr);
     if (rc) return rc;
     CU(cudaMemcpyAsync(dmin, c->s_out0.p, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(argmin, c->s_out1.p, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, st));

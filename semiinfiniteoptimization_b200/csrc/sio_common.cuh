@@ -76,6 +76,7 @@ struct MinArgs {
     const GridDev* grids; const int32_t* grid_of_b;   // device
     const GridDev* single_grid;                         // HOST copy when every transform uses one grid, else null
     const double* T_rel; const double* bound;          // device; bound may be null
+    const double* under_bound;                          // = bound when the under-bound set is wanted, else null (minimum only)
     int64_t B;                                          // total transforms (xf, T_rel, bound, outputs are [B])
     int64_t b_begin, Bc;                                // the batch [b_begin, b_begin+Bc) this launch covers
     double tau;

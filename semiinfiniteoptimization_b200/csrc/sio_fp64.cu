@@ -200,7 +200,7 @@ __global__ void k_recheck(const float4* __restrict__ pts, const int32_t* __restr
 
 void launch_recheck(const MinArgs& a, cudaStream_t st) {
     // the count lives on the device: a fixed, SM-sized grid strides over however many there are
-    if (!a.bound || a.B <= 0) return;
+    if (!a.under_bound || a.B <= 0) return;
     k_recheck<<<148 * 4, 128, 0, st>>>(a.pts, a.perm, a.N, a.grids, a.grid_of_b, a.T_rel, a.bound, a.cand,
                                        a.cand_count, a.cand_cap, a.n_under);
 }

@@ -201,7 +201,7 @@ void launch_prep_xf(const MinArgs& a, cudaStream_t st) {
     if (a.B <= 0) return;
     int threads = 128;
     int64_t blocks = (a.B + threads - 1) / threads;
-    k_prep_xf<<<(unsigned)blocks, threads, 0, st>>>(a.grids, a.grid_of_b, a.T_rel, a.bound, a.B, a.tau, a.xf);
+    k_prep_xf<<<(unsigned)blocks, threads, 0, st>>>(a.grids, a.grid_of_b, a.T_rel, a.under_bound, a.B, a.tau, a.xf);
 }
 
 // One warp, one transform, the warp's 128 points (4 per lane): trilinear values, candidates for the
@@ -322,12 +322,12 @@ void launch_min_f32(const MinArgs& a, cudaStream_t st) {
     int64_t nchunks = (a.Bc + chunk - 1) / chunk;
     int64_t blocks = nchunks * a.ntiles;
     if (a.single_grid) {
-        k_min_f32<false><<<(unsigned)blocks, kThreads, 0, st>>>(a.pts, a.rep, a.grids, a.grid_of_b, a.T_rel, a.bound, a.tau, a.b_begin,
+        k_min_f32<false><<<(unsigned)blocks, kThreads, 0, st>>>(a.pts, a.rep, a.grids, a.grid_of_b, a.T_rel, a.under_bound, a.tau, a.b_begin,
                                                                 a.Bc, a.ntiles, chunk, a.subkeys, a.cand, a.cand_count, a.cand_cap,
                                                                 host_gridk(*a.single_grid));
     } else {
         GridK dummy{};
-        k_min_f32<true><<<(unsigned)blocks, kThreads, 0, st>>>(a.pts, a.rep, a.grids, a.grid_of_b, a.T_rel, a.bound, a.tau, a.b_begin,
+        k_min_f32<true><<<(unsigned)blocks, kThreads, 0, st>>>(a.pts, a.rep, a.grids, a.grid_of_b, a.T_rel, a.under_bound, a.tau, a.b_begin,
                                                                a.Bc, a.ntiles, chunk, a.subkeys, a.cand, a.cand_count, a.cand_cap, dummy);
     }
 }
@@ -456,7 +456,7 @@ void launch_min_pruned(const MinArgs& a, cudaStream_t st) {
     const int64_t nchunks = (a.Bc + kXfChunk - 1) / kXfChunk;
     k_prune_centres<<<(unsigned)(nchunks * ntl), kThreads, 0, st>>>(a.rep, nsub, a.xf, a.b_begin, a.Bc, a.lb, a.ub);
     const int64_t ne = ((a.Bc + 31) & ~(int64_t)31) * nsub;
-    k_prune_select<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(a.lb, a.ub, a.bound, nsub, a.b_begin, a.Bc, (float)a.tau,
+    k_prune_select<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(a.lb, a.ub, a.under_bound, nsub, a.b_begin, a.Bc, (float)a.tau,
                                                                   a.subkeys, a.items, a.item_count);
     k_min_items<<<148 * 4, kThreads, 0, st>>>(a.pts, a.rep, a.xf, a.b_begin, nsub, a.items, a.item_count, a.subkeys, a.cand,
                                               a.cand_count, a.cand_cap);

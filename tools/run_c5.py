@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""C5 (BASELINE.json configs[4]): 65,536 independent cube-vs-scene pose problems, sharded across the ranks.
+
+    python tools/run_c5.py [--problems 65536] [--sip-problems 1024] [--max-iters 10]
+    python -m torch.distributed.run --nproc-per-node N ... tools/run_c5.py ...
+
+Part 1  one oracle sweep of this rank's block of poses x the 262,144-point scene cloud, exhaustive and with
+        sub-tile culling (identical results), timed on the device (max over ranks).
+Part 2  the lock-step batch SIP driver on --sip-problems problems per rank: outer iterations/s, with the split
+        between oracle time, QP time and the rest.
+Prints one JSON line (rank 0)."""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--problems", type=int, default=65536)
+ap.add_argument("--sip-problems", type=int, default=1024)
+ap.add_argument("--max-iters", type=int, default=10)
+ap.add_argument("--qp", default="batch")
+a = ap.parse_args()
+
+rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+from semiinfiniteoptimization_b200 import _abi, batch, geometryopt as G, sip, workloads as W, dist as sdist
+from semiinfiniteoptimization_b200._host import se3
+
+ctx = _abi.default_context()
+cube = G.PenetrationDepthGeometry(W.c5_cube(), 0.05, None)
+from semiinfiniteoptimization_b200._host.geometry import Geometry3D, PointCloud
+scene = G.PenetrationDepthGeometry(Geometry3D(PointCloud(W.c5_scene_cloud())), None, 0.02)
+poses = W.c5_poses(a.problems, seed=3)
+lo, hi = sdist.shard_range(a.problems)
+mine = poses[lo:hi]
+N = ctx.cloud_size(scene._dev.cloud_h)
+
+# ---- part 1: one sweep ------------------------------------------------------------------------------------------
+T_rel = np.array([se3.to_rowmajor12(se3.inv(T)) for T in mine])          # scene frame = world
+dT = torch.from_numpy(T_rel).cuda(); B = len(T_rel)
+bound = torch.zeros(B, dtype=torch.float64, device="cuda")
+dd = torch.empty(B, dtype=torch.float64, device="cuda"); da = torch.empty(B, dtype=torch.int64, device="cuda"); dn = torch.empty(B, dtype=torch.int32, device="cuda")
+stream = torch.cuda.ExternalStream(ctx.stream)
+out = {}
+for name, flags in (("exhaustive", _abi.SIO_F32), ("pruned", _abi.SIO_F32 | _abi.SIO_PRUNE)):
+    ms = []
+    for it in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.min_distance_dev([cube._dev.grid_h], scene._dev.cloud_h, dT.data_ptr(), bound.data_ptr(), B, flags, dd.data_ptr(), da.data_ptr())      # minimum / arg-minimum only, as minvalue needs
+        e1.record(stream); ctx.sync(); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = torch.tensor([min(ms[1:])], dtype=torch.float64, device="cuda")
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out[name] = {"ms": float(t.item()), "queries_per_s": a.problems * N / (float(t.item()) * 1e-3)}
+    if name == "exhaustive":
+        ref = (dd.clone(), da.clone())
+    else:
+        out[name]["identical_to_exhaustive"] = bool(torch.equal(ref[0], dd) and torch.equal(ref[1], da))
+        ev, tot = ctx.last_prune_stats(); out[name]["fraction_evaluated"] = ev / max(tot, 1)
+out["in_collision_fraction"] = float((ref[0] < 0).double().mean().item())
+
+# ---- part 2: lock-step SIP ------------------------------------------------------------------------------------------
+nb = min(a.sip_problems, len(mine))
+if nb == 0:
+    if rank == 0:
+        print(json.dumps({"config": "C5 synthetic scene %d pts, %d problems, %d GPUs" % (N, a.problems, world), **out}))
+    sys.exit(0)
+st = sip.SemiInfiniteOptimizationSettings(); st.max_iters = a.max_iters
+t0 = time.time()
+res = batch.optimizeCollFreeBatch(cube, scene, mine[:nb], settings=st, qp=a.qp)
+wall = time.time() - t0
+rec = torch.tensor([res.outer_iterations, wall, res.time_cons, res.time_qp, res.point_queries, float((res.gx > -5e-3).sum()), nb], dtype=torch.float64, device="cuda")
+if world > 1:
+    mx = rec.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(rec, op=dist.ReduceOp.SUM)
+    wall = float(mx[1].item())
+if rank == 0:
+    out["sip"] = {"problems": int(rec[6].item()), "max_iters": a.max_iters, "qp": a.qp, "outer_iterations": int(rec[0].item()),
+                  "wall_s": wall, "iters_per_s": float(rec[0].item()) / wall, "oracle_s": float(rec[2].item()) / world,
+                  "qp_s": float(rec[3].item()) / world, "point_queries": int(rec[4].item()), "feasible": int(rec[5].item())}
+    print(json.dumps({"config": "C5 synthetic scene %d pts, %d problems, %d GPUs" % (N, a.problems, world), **out}))
+if world > 1:
+    dist.destroy_process_group()
