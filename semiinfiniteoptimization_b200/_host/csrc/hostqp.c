@@ -1,0 +1,339 @@
+/* hostqp.c -- batched host solver for the small QP of the SIP step.
+ *
+ * The reference solves one QP per outer iteration with OSQP (sip.py:294-378):
+ *
+ *     min (x - xdes)' W (x - xdes) + reg |x|^2   s.t.  A x + b >= inflation,  xmin <= x <= xmax
+ *
+ * and, when the strict problem is infeasible or its solution is out of scale, a second QP with one
+ * slack variable per row (sip.py:332-357).  With 65,536 problems in lock step (BASELINE.json configs[4])
+ * that is 65,536 QPs per outer iteration, so they are solved here natively, one OpenMP thread per problem.
+ *
+ * Algorithm = the one in _host/qp.py (OSQP's ADMM: over-relaxation alpha, adaptive rho, the same residual
+ * test every 10 iterations, the primal-infeasibility certificate, the active-set polish), restated for
+ * dense problems with a DIAGONAL quadratic term.  Because P is diagonal the KKT step is taken in its reduced
+ * form  (P + sigma I + A' diag(rho) A) x~ = sigma x - q + A'(rho z - y),  z~ = A x~  -- an n x n Cholesky
+ * instead of an (n+m) x (n+m) LU; same iterates up to rounding.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define HQP_INF 1e20
+enum { HQP_SOLVED = 0, HQP_MAXIT = 1, HQP_INFEASIBLE = 2 };
+
+typedef struct {
+    double eps_abs, eps_rel, rho, sigma, alpha;
+    int max_iter, check_every, adapt_every, polish;
+} hqp_opts;
+
+/* in-place Cholesky of the n x n SPD matrix K (row-major, lower part used); returns 0 on success */
+static int chol(double* K, int n) {
+    for (int j = 0; j < n; ++j) {
+        double d = K[j * n + j];
+        for (int k = 0; k < j; ++k) d -= K[j * n + k] * K[j * n + k];
+        if (!(d > 0.0)) return -1;
+        d = sqrt(d);
+        K[j * n + j] = d;
+        for (int i = j + 1; i < n; ++i) {
+            double s = K[i * n + j];
+            for (int k = 0; k < j; ++k) s -= K[i * n + k] * K[j * n + k];
+            K[i * n + j] = s / d;
+        }
+    }
+    return 0;
+}
+static void chol_solve(const double* L, int n, double* b) {
+    for (int i = 0; i < n; ++i) {
+        double s = b[i];
+        for (int k = 0; k < i; ++k) s -= L[i * n + k] * b[k];
+        b[i] = s / L[i * n + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        double s = b[i];
+        for (int k = i + 1; k < n; ++k) s -= L[k * n + i] * b[k];
+        b[i] = s / L[i * n + i];
+    }
+}
+/* Gaussian elimination with partial pivoting, N x N row-major, solves M x = b in place; 0 on success */
+static int lu_solve(double* M, double* b, int N) {
+    for (int c = 0; c < N; ++c) {
+        int p = c;
+        double best = fabs(M[c * N + c]);
+        for (int r = c + 1; r < N; ++r) if (fabs(M[r * N + c]) > best) { best = fabs(M[r * N + c]); p = r; }
+        if (!(best > 0.0)) return -1;
+        if (p != c) {
+            for (int k = 0; k < N; ++k) { double t = M[c * N + k]; M[c * N + k] = M[p * N + k]; M[p * N + k] = t; }
+            double t = b[c]; b[c] = b[p]; b[p] = t;
+        }
+        for (int r = c + 1; r < N; ++r) {
+            double f = M[r * N + c] / M[c * N + c];
+            if (f == 0.0) continue;
+            for (int k = c; k < N; ++k) M[r * N + k] -= f * M[c * N + k];
+            b[r] -= f * b[c];
+        }
+    }
+    for (int r = N - 1; r >= 0; --r) {
+        double s = b[r];
+        for (int k = r + 1; k < N; ++k) s -= M[r * N + k] * b[k];
+        b[r] = s / M[r * N + r];
+    }
+    return 0;
+}
+
+static void build_K(int n, int m, const double* Pd, const double* A, const double* rv, double sigma, double* K) {
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = (i == j) ? Pd[i] + sigma : 0.0;
+            for (int r = 0; r < m; ++r) s += rv[r] * A[r * n + i] * A[r * n + j];
+            K[i * n + j] = s;
+        }
+}
+
+/* work: doubles, at least n*n + 8*m + 4*n + (n+m)*(n+m+1) */
+static int admm(int n, int m, const double* Pd, const double* q, const double* A, const double* l0, const double* u0,
+                const hqp_opts* o, double* x, double* pri, double* dua, int* iters_out, double* work) {
+    double* K = work;               work += n * n;
+    double* l = work;               work += m;
+    double* u = work;               work += m;
+    double* z = work;               work += m;
+    double* y = work;               work += m;
+    double* rv = work;              work += m;
+    double* zt = work;              work += m;
+    double* dy = work;              work += m;
+    double* Ax = work;              work += m;
+    double* xt = work;              work += n;
+    double* Px = work;              work += n;
+    double* Aty = work;             work += n;
+    double* tmpn = work;            work += n;
+    double* kkt = work;             /* (n+m)*(n+m+1) for the polish */
+    double rho = o->rho;
+    for (int r = 0; r < m; ++r) {
+        l[r] = l0[r] > -HQP_INF ? l0[r] : -HQP_INF;
+        u[r] = u0[r] < HQP_INF ? u0[r] : HQP_INF;
+        rv[r] = (u[r] - l[r] < 1e-12) ? 1e3 * rho : rho;
+        z[r] = 0.0; y[r] = 0.0;
+    }
+    for (int i = 0; i < n; ++i) x[i] = 0.0;
+    build_K(n, m, Pd, A, rv, o->sigma, K);
+    if (chol(K, n)) return HQP_MAXIT;
+    int status = HQP_MAXIT, it = 0;
+    double r_prim = INFINITY, r_dual = INFINITY;
+    for (it = 1; it <= o->max_iter; ++it) {
+        for (int i = 0; i < n; ++i) xt[i] = o->sigma * x[i] - q[i];
+        for (int r = 0; r < m; ++r) {
+            double w = rv[r] * z[r] - y[r];
+            for (int i = 0; i < n; ++i) xt[i] += A[r * n + i] * w;
+        }
+        chol_solve(K, n, xt);
+        double ndy = 0.0;
+        for (int r = 0; r < m; ++r) {
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) s += A[r * n + i] * xt[i];
+            double zr = o->alpha * s + (1.0 - o->alpha) * z[r];
+            double c = zr + y[r] / rv[r];
+            double zn = c < l[r] ? l[r] : (c > u[r] ? u[r] : c);
+            double yn = y[r] + rv[r] * (zr - zn);
+            dy[r] = yn - y[r];
+            if (fabs(dy[r]) > ndy) ndy = fabs(dy[r]);
+            z[r] = zn; y[r] = yn;
+        }
+        for (int i = 0; i < n; ++i) x[i] = o->alpha * xt[i] + (1.0 - o->alpha) * x[i];
+        if ((it % o->check_every) && it != o->max_iter) continue;
+        double nAx = 0.0, nd = 0.0;
+        r_prim = 0.0; r_dual = 0.0;
+        for (int i = 0; i < n; ++i) { Px[i] = Pd[i] * x[i]; Aty[i] = 0.0; }
+        for (int r = 0; r < m; ++r) {
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) { s += A[r * n + i] * x[i]; Aty[i] += A[r * n + i] * y[r]; }
+            Ax[r] = s;
+            if (fabs(s - z[r]) > r_prim) r_prim = fabs(s - z[r]);
+            if (fabs(s) > nAx) nAx = fabs(s);
+            if (fabs(z[r]) > nAx) nAx = fabs(z[r]);
+        }
+        for (int i = 0; i < n; ++i) {
+            double g = Px[i] + q[i] + Aty[i];
+            if (fabs(g) > r_dual) r_dual = fabs(g);
+            if (fabs(Px[i]) > nd) nd = fabs(Px[i]);
+            if (fabs(Aty[i]) > nd) nd = fabs(Aty[i]);
+            if (fabs(q[i]) > nd) nd = fabs(q[i]);
+        }
+        if (r_prim <= o->eps_abs + o->eps_rel * nAx && r_dual <= o->eps_abs + o->eps_rel * nd) { status = HQP_SOLVED; break; }
+        if (ndy > 1e-12) {                       /* primal infeasibility certificate (OSQP paper, sec. 3.4) */
+            double nAt = 0.0, sup = 0.0;
+            for (int i = 0; i < n; ++i) tmpn[i] = 0.0;
+            for (int r = 0; r < m; ++r) {
+                double d = dy[r] / ndy;
+                for (int i = 0; i < n; ++i) tmpn[i] += A[r * n + i] * d;
+                sup += u[r] * (d > 0 ? d : 0.0) + l[r] * (d < 0 ? d : 0.0);
+            }
+            for (int i = 0; i < n; ++i) if (fabs(tmpn[i]) > nAt) nAt = fabs(tmpn[i]);
+            if (nAt <= 1e-4 && sup < -1e-4) { status = HQP_INFEASIBLE; break; }
+        }
+        if (it % o->adapt_every == 0 && r_prim > 0 && r_dual > 0) {
+            double scale = sqrt((r_prim / (nAx > 1e-12 ? nAx : 1e-12)) / (r_dual / (nd > 1e-12 ? nd : 1e-12)));
+            if (scale > 5 || scale < 0.2) {
+                rho *= scale;
+                if (rho < 1e-6) rho = 1e-6;
+                if (rho > 1e6) rho = 1e6;
+                for (int r = 0; r < m; ++r) rv[r] = (u[r] - l[r] < 1e-12) ? 1e3 * rho : rho;
+                build_K(n, m, Pd, A, rv, o->sigma, K);
+                if (chol(K, n)) break;
+            }
+        }
+    }
+    if (it > o->max_iter) it = o->max_iter;
+    if (status == HQP_SOLVED && o->polish && m > 0) {
+        /* active set: rows at (or pushed against) a finite bound; equality-constrained solve on it */
+        int na = 0;
+        int* act = (int*)dy;                     /* dy is free now: reuse as the index list (m ints fit in m doubles) */
+        double* rhs_c = zt;
+        for (int r = 0; r < m; ++r) {
+            int lo = ((y[r] < -1e-9) || (Ax[r] - l[r] < 1e-7)) && l[r] > -HQP_INF / 2;
+            int up = ((y[r] > 1e-9) || (u[r] - Ax[r] < 1e-7)) && u[r] < HQP_INF / 2;
+            if (lo || up) { act[na] = r; rhs_c[na] = lo ? l[r] : u[r]; ++na; }
+        }
+        if (na > 0) {
+            const double delta = 1e-7, tol = 1e-7;
+            int N = n + na;
+            double* M = kkt;
+            double* b = kkt + (size_t)N * N;
+            memset(M, 0, sizeof(double) * (size_t)N * N);
+            for (int i = 0; i < n; ++i) { M[i * N + i] = Pd[i] + delta; b[i] = -q[i]; }
+            for (int a = 0; a < na; ++a) {
+                for (int i = 0; i < n; ++i) { M[i * N + n + a] = A[act[a] * n + i]; M[(n + a) * N + i] = A[act[a] * n + i]; }
+                M[(n + a) * N + n + a] = -delta;
+                b[n + a] = rhs_c[a];
+            }
+            if (lu_solve(M, b, N) == 0) {
+                int ok = 1;
+                for (int i = 0; i < n; ++i) if (!isfinite(b[i])) ok = 0;
+                double f0 = 0.0, f1 = 0.0;
+                for (int i = 0; i < n && ok; ++i) { f0 += 0.5 * Pd[i] * x[i] * x[i] + q[i] * x[i]; f1 += 0.5 * Pd[i] * b[i] * b[i] + q[i] * b[i]; }
+                for (int r = 0; r < m && ok; ++r) {
+                    double s = 0.0;
+                    for (int i = 0; i < n; ++i) s += A[r * n + i] * b[i];
+                    if (s < l[r] - tol || s > u[r] + tol) ok = 0;
+                }
+                if (ok && !(f1 > f0 + 1e-9 * (1 + fabs(f0)))) for (int i = 0; i < n; ++i) x[i] = b[i];
+            }
+        }
+    }
+    *pri = r_prim; *dua = r_dual; *iters_out = it;
+    return status;
+}
+
+int hqp_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* The SIP step of `nprob` problems with n variables each (sip.py:294-378, default solver settings):
+ *   W, xdes, xmin, xmax : [nprob*n]     (diagonal weights; xmin/xmax = the trust-region box, may be NULL together)
+ *   offs [nprob+1]      : row ranges into rows [total*n] (row-major) and depths [total]
+ * For each problem:  P = W + reg,  q = -W xdes,  rows: A x >= -depth + inflation,  box rows xmin <= x <= xmax.
+ * Problems with no rows return xdes (sip.py:288).  If the strict solve is infeasible, or |x| reg > |negative
+ * depths|, the slack problem of sip.py:332-357 is solved instead (slack_penalty = 'auto').
+ * status[p]: 0 strict solution, 1 slack solution, 2 no rows, -1 failure (dx = 0).
+ * iters[p] (optional): ADMM iterations spent on the problem (strict + slack). */
+int hqp_sip_step_batch(int64_t nprob, int n, const double* W, const double* xdes, const double* xmin, const double* xmax,
+                       const int64_t* offs, const double* rows, const double* depths, double reg, double inflation,
+                       double eps_abs, int max_iter, double* dx, int32_t* status, int32_t* iters) {
+    if (nprob < 0 || n <= 0 || !W || !xdes || !offs || !dx) return -1;
+    int64_t maxrows = 0;
+    for (int64_t p = 0; p < nprob; ++p) if (offs[p + 1] - offs[p] > maxrows) maxrows = offs[p + 1] - offs[p];
+    const int box = xmin && xmax;
+    const int M = (int)maxrows + (box ? n : 0);          /* rows of the largest strict problem */
+    const int NS = n + (int)maxrows;                     /* variables of the largest slack problem */
+    const size_t wsz = (size_t)NS * NS + 8 * (size_t)M + 4 * (size_t)NS + (size_t)(NS + M) * (NS + M + 1)
+                     + (size_t)M * NS + 2 * (size_t)M + 3 * (size_t)NS + 64;
+    hqp_opts o = {eps_abs, 1e-5, 0.1, 1e-6, 1.6, max_iter > 0 ? max_iter : 20000, 10, 50, 1};
+    int fail = 0;
+#pragma omp parallel
+    {
+        double* buf = (double*)malloc(sizeof(double) * wsz);
+        if (!buf) {
+#pragma omp atomic write
+            fail = 1;
+        }
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t p = 0; p < nprob; ++p) {
+            if (!buf) continue;
+            const int k = (int)(offs[p + 1] - offs[p]);
+            const double* Wp = W + p * n;
+            const double* xd = xdes + p * n;
+            double* out = dx + p * n;
+            if (k == 0) {
+                for (int i = 0; i < n; ++i) out[i] = xd[i];
+                if (status) status[p] = 2;
+                if (iters) iters[p] = 0;
+                continue;
+            }
+            const double* Ar = rows + offs[p] * n;
+            const double* b = depths + offs[p];
+            const int m = k + (box ? n : 0);
+            double* A = buf;                        /* m x NS max */
+            double* l = A + (size_t)M * NS;
+            double* u = l + M;
+            double* Pd = u + M;
+            double* q = Pd + NS;
+            double* x = q + NS;
+            double* work = x + NS;
+            for (int r = 0; r < k; ++r) {
+                for (int i = 0; i < n; ++i) A[r * n + i] = Ar[r * n + i];
+                l[r] = -b[r] + inflation; u[r] = INFINITY;
+            }
+            if (box)
+                for (int i = 0; i < n; ++i) {
+                    for (int j = 0; j < n; ++j) A[(k + i) * n + j] = (i == j) ? 1.0 : 0.0;
+                    l[k + i] = xmin[p * n + i]; u[k + i] = xmax[p * n + i];
+                }
+            for (int i = 0; i < n; ++i) { Pd[i] = Wp[i] + reg; q[i] = -Wp[i] * xd[i]; }
+            double pri, dua;
+            int its;
+            int st = admm(n, m, Pd, q, A, l, u, &o, x, &pri, &dua, &its, work);
+            double bnorm = 1.0, neg2 = 0.0, bmin = INFINITY;
+            int nneg = 0;
+            for (int r = 0; r < k; ++r) { if (b[r] < 0) { neg2 += b[r] * b[r]; ++nneg; } if (b[r] < bmin) bmin = b[r]; }
+            if (nneg) bnorm = sqrt(neg2);
+            double xn = 0.0;
+            for (int i = 0; i < n; ++i) xn += x[i] * x[i];
+            xn = sqrt(xn);
+            if (st != HQP_INFEASIBLE && !(xn * reg > bnorm)) {
+                for (int i = 0; i < n; ++i) out[i] = x[i];
+                if (status) status[p] = 0;
+                if (iters) iters[p] = its;
+                continue;
+            }
+            const int its_strict = its;
+            /* slack problem: variables [x (n) | s (k)], rows A x + s >= ..., box rows on x only */
+            const double pen = (1.0 + nneg) / (fabs(bmin) + 1e-3);
+            const int ns = n + k;
+            for (int r = 0; r < k; ++r) {
+                for (int i = 0; i < n; ++i) A[r * ns + i] = Ar[r * n + i];
+                for (int j = 0; j < k; ++j) A[r * ns + n + j] = (j == r) ? 1.0 : 0.0;
+            }
+            if (box)
+                for (int i = 0; i < n; ++i)
+                    for (int j = 0; j < ns; ++j) A[(k + i) * ns + j] = (i == j) ? 1.0 : 0.0;
+            for (int j = 0; j < k; ++j) { Pd[n + j] = pen; q[n + j] = 0.0; }
+            st = admm(ns, m, Pd, q, A, l, u, &o, x, &pri, &dua, &its, work);
+            if (st == HQP_INFEASIBLE) {
+                for (int i = 0; i < n; ++i) out[i] = 0.0;
+                if (status) status[p] = -1;
+            } else {
+                for (int i = 0; i < n; ++i) out[i] = x[i];
+                if (status) status[p] = 1;
+            }
+            if (iters) iters[p] = its_strict + its;
+        }
+        free(buf);
+    }
+    return fail ? -2 : 0;
+}

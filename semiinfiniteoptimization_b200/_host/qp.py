@@ -192,3 +192,55 @@ def solve_qp_batch(P, q, A, l, u, nrows, iters=400, rho=0.1, sigma=1e-6, alpha=1
     r_prim = np.abs(Ax - z).max(axis=1)
     r_dual = np.abs(np.einsum('bij,bj->bi', P, x) + q + np.einsum('bji,bj->bi', A, y)).max(axis=1)
     return x, r_prim, r_dual
+
+
+# ---------------------------------------------------------------------------------------------
+# native batched SIP step (csrc/hostqp.c): every problem's QP, slack fallback included, in one call
+# ---------------------------------------------------------------------------------------------
+_native = None
+
+
+def _native_lib():
+    global _native
+    if _native is None:
+        import ctypes as C
+        import os
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libsio_hostqp.so")
+        if not os.path.exists(path):
+            from .. import build
+            build.build_hostqp()
+        L = C.CDLL(path)
+        P = C.c_void_p
+        L.hqp_sip_step_batch.argtypes = [C.c_int64, C.c_int, P, P, P, P, P, P, P, C.c_double, C.c_double, C.c_double, C.c_int, P, P, P]
+        L.hqp_sip_step_batch.restype = C.c_int
+        L.hqp_max_threads.restype = C.c_int
+        _native = L
+    return _native
+
+
+def sip_step_batch(W, xdes, offs, rows, depths, xmin=None, xmax=None, reg=1e-2, inflation=1e-3, eps_abs=1e-5, max_iter=20000,
+                   return_iters=False):
+    """dx of `len(W)` problems at once: min (x-xdes)'W(x-xdes) + reg|x|^2  s.t.  rows x + depths >= inflation,
+    xmin <= x <= xmax, with the reference's slack re-solve (sip.py:294-378).  W, xdes, xmin, xmax: (B,n);
+    offs: (B+1,) row ranges into rows (total,n) / depths (total,).  Returns dx (B,n), status (B,) int32
+    (0 strict, 1 slack, 2 no rows -> xdes, -1 failed)."""
+    W = np.ascontiguousarray(W, dtype=np.float64)
+    xdes = np.ascontiguousarray(xdes, dtype=np.float64)
+    B, n = W.shape
+    offs = np.ascontiguousarray(offs, dtype=np.int64)
+    rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, n)
+    depths = np.ascontiguousarray(depths, dtype=np.float64)
+    assert len(offs) == B + 1 and offs[-1] == len(rows) == len(depths)
+    if xmin is not None:
+        xmin = np.ascontiguousarray(xmin, dtype=np.float64)
+        xmax = np.ascontiguousarray(xmax, dtype=np.float64)
+    dx = np.empty((B, n))
+    status = np.empty(B, dtype=np.int32)
+    iters = np.empty(B, dtype=np.int32) if return_iters else None
+    rc = _native_lib().hqp_sip_step_batch(B, n, W.ctypes.data, xdes.ctypes.data, None if xmin is None else xmin.ctypes.data,
+                                          None if xmax is None else xmax.ctypes.data, offs.ctypes.data, rows.ctypes.data,
+                                          depths.ctypes.data, float(reg), float(inflation), float(eps_abs), int(max_iter),
+                                          dx.ctypes.data, status.ctypes.data, None if iters is None else iters.ctypes.data)
+    if rc:
+        raise RuntimeError("hqp_sip_step_batch failed with code %d" % rc)
+    return (dx, status, iters) if return_iters else (dx, status)

@@ -302,3 +302,242 @@ def solve_sharded(obj, env, Tinits, Tdess=None, settings=None, qp='scalar'):
     lo, hi = dist.shard_range(len(Tinits))
     local = optimizeCollFreeBatch(obj, env, Tinits[lo:hi], None if Tdess is None else Tdess[lo:hi], settings, qp)
     return dist.gather_records(local.records(), n_total=len(Tinits)), local
+
+
+# =================================================================================================
+# array-at-a-time lock-step driver: no per-problem Python, native batched QP
+# =================================================================================================
+def _log_so3_vec(M):
+    """Vectorised _host/so3.rotation_vector (same three branches) for a batch (B,3,3)."""
+    c = np.clip((np.trace(M, axis1=1, axis2=2) - 1.0) * 0.5, -1.0, 1.0)
+    th = np.arccos(c)
+    v = np.stack([M[:, 2, 1] - M[:, 1, 2], M[:, 0, 2] - M[:, 2, 0], M[:, 1, 0] - M[:, 0, 1]], axis=1)
+    out = np.empty_like(v)
+    small = th < 1e-8
+    nearpi = ~small & (np.abs(th - math.pi) < 1e-5)
+    gen = ~small & ~nearpi
+    out[small] = 0.5 * v[small]
+    out[gen] = v[gen] * (th[gen] / (2.0 * np.sin(th[gen])))[:, None]
+    for k in np.nonzero(nearpi)[0]:                      # measure-zero branch: scalar code
+        from ._host import so3
+        out[k] = so3.rotation_vector(so3.from_matrix(M[k]))
+    return out
+
+
+def _exp_so3_vec(W):
+    """Vectorised _host/so3.from_rotation_vector (Rodrigues) for a batch (B,3) -> (B,3,3)."""
+    th = np.linalg.norm(W, axis=1)
+    K = np.zeros((len(W), 3, 3))
+    K[:, 0, 1], K[:, 0, 2] = -W[:, 2], W[:, 1]
+    K[:, 1, 0], K[:, 1, 2] = W[:, 2], -W[:, 0]
+    K[:, 2, 0], K[:, 2, 1] = -W[:, 1], W[:, 0]
+    K2 = K @ K
+    small = th < 1e-12
+    ths = np.where(small, 1.0, th)
+    a = np.where(small, 1.0, np.sin(ths) / ths)
+    b = np.where(small, 0.5, (1 - np.cos(ths)) / (ths * ths))
+    return np.eye(3)[None] + a[:, None, None] * K + b[:, None, None] * K2
+
+
+def optimizeCollFreeBatchFast(obj, env, Tinits, Tdess=None, settings=None, context=None, flags=None, keep_trace=False):
+    """The same lock-step algorithm as optimizeCollFreeBatch, written array-at-a-time: instantiated
+    parameters live in padded (B, cap, 3) arrays, the exclusion hash is an integer key array, every
+    oracle request is one device call over all live problems and all QPs of an outer iteration are
+    solved by ONE call into the native batched solver (_host/csrc/hostqp.c, OpenMP).  Per-problem
+    arithmetic and quirks are those of sip.py:795-1241 / the scalar driver above; the QP answers differ
+    from the scalar path only in rounding (reduced n x n system instead of the KKT LU)."""
+    from ._host import se3, so3
+    assert isinstance(obj, PenetrationDepthGeometry) and isinstance(env, PenetrationDepthGeometry)
+    ctx = context or obj.context
+    settings = settings or _sip.SemiInfiniteOptimizationSettings()
+    if flags is None:
+        flags = BULK_FLAGS | _abi.SIO_PRUNE
+    B = len(Tinits)
+    if Tdess is None:
+        Tdess = Tinits
+    R = np.array([so3.matrix(T[0]) for T in Tinits])
+    t = np.array([T[1] for T in Tinits], dtype=np.float64)
+    Rdes = np.array([so3.matrix(T[0]) for T in Tdess])
+    tdes = np.array([T[1] for T in Tdess], dtype=np.float64)
+    Tenv = env._T12.reshape(3, 4)
+    cloud_world = env._dev.cloud32.astype(np.float64) @ Tenv[:, :3].T + Tenv[:, 3]
+    grid_h, cloud_h = obj._dev.grid_h, env._dev.cloud_h
+    N = len(cloud_world)
+    res = BatchResult(B)
+    cap = 8
+    P = np.zeros((B, cap, 3))
+    keys = np.zeros((B, cap, 3), dtype=np.int64)
+    cnt = np.zeros(B, dtype=np.int64)
+    excl = settings.parameter_exclusion_distance
+    w = np.full(B, settings.initial_objective_score_weight)
+    trs = np.full(B, 0.5)
+    update_oracle = np.ones(B, dtype=bool)
+    live = np.ones(B, dtype=bool)
+    min_cv = np.full(B, settings.minimum_constraint_value)
+    xeps2 = settings.xepsilon ** 2 * 2          # len((R,t)) == 2 in the reference        # quirk
+    reg = settings.qp_solver_params.get('regularizationFactor', 1e-2)
+    status = np.zeros(B, dtype=bool)             # True = 'local optimum'
+    if keep_trace:
+        res.trace = [[(so3.from_matrix(R[p]), list(t[p]))] for p in range(B)]
+
+    def objective(idx, Rm, tm):
+        rv = _log_so3_vec(np.einsum('bij,bkj->bik', Rdes[idx], Rm))
+        dt = tdes[idx] - tm
+        return (dt * dt).sum(1) + (rv * rv).sum(1), np.hstack([rv, dt])
+
+    def valid_mask(idx):
+        return np.arange(cap)[None, :] < cnt[idx][:, None]
+
+    def values(idx, Rm, tm, want_rows):
+        """flat values (and rows) of every instantiated parameter of problems idx, problem-major."""
+        mask = valid_mask(idx)
+        counts = cnt[idx]
+        offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        if offs[-1] == 0:
+            return mask, offs, np.zeros(0), np.zeros((0, 6))
+        T = np.empty((len(idx), 3, 4))
+        T[:, :, :3] = Rm
+        T[:, :, 3] = tm
+        d, rows = ctx.pose_rows(grid_h, T.reshape(-1, 12), offs, P[idx][mask], flags=POINT_FLAGS, want_rows=want_rows)
+        return mask, offs, d, rows
+
+    def padded(mask, d):
+        D = np.full(mask.shape, np.inf)
+        D[mask] = d
+        return D
+
+    def minvalue(idx, Rm, tm, bound):
+        Tinv_R = np.transpose(Rm, (0, 2, 1))
+        Trel = np.empty((len(idx), 3, 4))
+        Trel[:, :, :3] = Tinv_R @ Tenv[:, :3]
+        Trel[:, :, 3] = np.einsum('bij,j->bi', Tinv_R, Tenv[:, 3]) - np.einsum('bji,bj->bi', Rm, tm)
+        dmin, arg, _ = ctx.min_distance(grid_h, cloud_h, Trel.reshape(-1, 12), bound=bound, flags=flags, want_under=False)
+        res.point_queries += len(idx) * N
+        return dmin, arg
+
+    def instantiate(pidx, pts):
+        """appends pts[k] to problem pidx[k] unless its exclusion key is present; returns the added mask."""
+        nonlocal P, keys, cap
+        if len(pidx) == 0:
+            return np.zeros(0, dtype=bool)
+        k = np.trunc(pts / excl).astype(np.int64)                                   # int() truncates toward zero (sip.py:280)
+        seen = ((keys[pidx] == k[:, None, :]).all(-1) & valid_mask(pidx)).any(1)
+        add = ~seen
+        tgt = pidx[add]
+        if len(tgt) and cnt[tgt].max() >= cap:
+            P = np.concatenate([P, np.zeros_like(P)], axis=1)
+            keys = np.concatenate([keys, np.zeros_like(keys)], axis=1)
+            cap *= 2
+        P[tgt, cnt[tgt]] = pts[add]
+        keys[tgt, cnt[tgt]] = k[add]
+        cnt[tgt] += 1
+        return add
+
+    fx0, _ = objective(np.arange(B), R, t)
+    res.fx = fx0.copy()
+    tstart = time.time()
+    for it in range(settings.max_iters):
+        idx = np.nonzero(live)[0]
+        if len(idx) == 0:
+            break
+        res.num_iterations[idx] = it
+        _, dxdes = objective(idx, R[idx], t[idx])
+        # ---- oracle at x (sip.py:193-276) ---------------------------------------------------
+        t0 = time.time()
+        mask, offs, d, _ = values(idx, R[idx], t[idx], False)
+        D = padded(mask, d)
+        uo = update_oracle[idx]
+        drop = mask & (D >= settings.constraint_drop_value) & uo[:, None]
+        if drop.any():
+            rows_ = np.nonzero(drop.any(1))[0]
+            order = np.argsort(drop[rows_] | ~mask[rows_], axis=1, kind='stable')     # kept entries first, original order
+            pi = idx[rows_]
+            P[pi] = np.take_along_axis(P[pi], order[:, :, None], axis=1)
+            keys[pi] = np.take_along_axis(keys[pi], order[:, :, None], axis=1)
+            D[rows_] = np.take_along_axis(D[rows_], order, axis=1)
+            cnt[pi] -= drop[rows_].sum(1)
+            mask = valid_mask(idx)
+            D[~mask] = np.inf
+        sel = np.nonzero(uo)[0]
+        if len(sel):
+            olddmin = np.minimum(0.0, D[sel].min(1))
+            pi = idx[sel]
+            dmin, arg = minvalue(pi, R[pi], t[pi], olddmin)
+            cond = (arg >= 0) & (dmin < olddmin)
+            if cond.any():
+                slot = cnt[pi[cond]].copy()
+                added = instantiate(pi[cond], cloud_world[arg[cond]])
+                if cap > D.shape[1]:
+                    D = np.concatenate([D, np.full((len(D), cap - D.shape[1]), np.inf)], axis=1)
+                rr = sel[cond][added]
+                D[rr, slot[added]] = dmin[cond][added]
+        update_oracle[idx] = (it % 100 == 0)
+        mask, offs, _, rows = values(idx, R[idx], t[idx], True)
+        res.time_cons += time.time() - t0
+        gx = D.min(1)
+        if it == 0:
+            res.gx0[idx] = gx
+            low = gx < min_cv[idx]
+            min_cv[idx[low]] = gx[low]
+        # ---- QP step (sip.py:945-964): every problem in one native call -----------------------------
+        t0 = time.time()
+        ones6 = np.ones((len(idx), 6))
+        dx, _ = _qp.sip_step_batch(w[idx][:, None] * ones6, dxdes, offs, rows, D[mask], -trs[idx][:, None] * ones6,
+                                   trs[idx][:, None] * ones6, reg=reg, inflation=settings.constraint_inflation)
+        res.time_qp += time.time() - t0
+        dxn2 = (dx * dx).sum(1)
+        conv = dxn2 < xeps2
+        status[idx[conv]] = True
+        live[idx[conv]] = False
+        res.gx[idx[conv]] = gx[conv]
+        go = ~conv
+        if not go.any():
+            continue
+        idx, dx, dxn2, gx, D = idx[go], dx[go], dxn2[go], gx[go], D[go]
+        dxnorm = np.sqrt(dxn2)
+        # ---- proposed step and merit (sip.py:1146-1156, 134-172) ------------------------------------
+        Rn = _exp_so3_vec(dx[:, :3]) @ R[idx]
+        tn = t[idx] + dx[:, 3:]
+        sorig = np.maximum(0.0, -D.min(1)) + w[idx] * res.fx[idx]
+        ninst0 = cnt[idx].copy()
+        t0 = time.time()
+        fxn, _ = objective(idx, Rn, tn)
+        mask, offs, d, _ = values(idx, Rn, tn, False)
+        Dn = padded(mask, d)
+        gxn = Dn.min(1)
+        metric = np.maximum(0.0, -gxn)
+        dmin, arg = minvalue(idx, Rn, tn, gxn)
+        cond = (arg >= 0) & (dmin < gxn)
+        if cond.any():
+            gxn[cond] = dmin[cond]
+            added = instantiate(idx[cond], cloud_world[arg[cond]])
+            hit = np.nonzero(cond)[0][added & (dmin[cond] < 0)]
+            metric[hit] = np.maximum(metric[hit], -dmin[hit])
+        res.time_cons += time.time() - t0
+        snew = metric + w[idx] * fxn
+        accept = ~(snew >= sorig)
+        newcol = (cnt[idx] > ninst0) & (gxn < 0)
+        update_oracle[idx[newcol]] = False
+        accept &= ~newcol
+        ia, ir = idx[accept], idx[~accept]
+        R[ia], t[ia] = Rn[accept], tn[accept]
+        res.fx[ia], res.gx[ia] = fxn[accept], gxn[accept]
+        trs[ia] *= 2.5
+        res.gx[ir] = gx[~accept]
+        trs[ir] *= 0.5
+        shrink = trs[ir] > dxnorm[~accept]
+        trs[ir[shrink]] = np.max(np.abs(dx[~accept][shrink]), axis=1) * 0.5
+        if keep_trace:
+            for p in idx:
+                res.trace[p].append((so3.from_matrix(R[p]), list(t[p])))
+        scale = 0.75 * ((np.arctan(res.gx[idx] * 3) * 2 / math.pi + 0.5) * 1.75 + 0.25)
+        w[idx] = np.maximum(w[idx] * scale, settings.minimum_objective_score_weight)
+        res.outer_iterations += len(idx)
+    T = np.empty((B, 3, 4))
+    T[:, :, :3] = R
+    T[:, :, 3] = t
+    res.T = T.reshape(B, 12)
+    res.status = ['local optimum' if s else 'not converged' for s in status]
+    res.instantiated_params = [[list(P[p, k]) for k in range(cnt[p])] for p in range(B)]
+    res.time = time.time() - tstart
+    return res

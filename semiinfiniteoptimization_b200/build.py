@@ -2,6 +2,7 @@
 
   lib/libsio_b200.so      CUDA kernels + C-ABI (nvcc, sm_100a only, -lineinfo)
   lib/libsio_hostgeom.so  host-side mesh -> SDF preprocessing (gcc, OpenMP)
+  lib/libsio_hostqp.so    batched host QP of the SIP step (gcc, OpenMP)
 
 nvcc cross-compiles without a GPU.  Objects go to build/ (git-ignored); the .so files are
 git-ignored too but travel to the GPU box with the gpurun snapshot.
@@ -73,8 +74,19 @@ def build_hostgeom(force=False):
     return out
 
 
+def build_hostqp(force=False):
+    os.makedirs(_LIB, exist_ok=True)
+    src = os.path.join(_PKG, "_host", "csrc", "hostqp.c")
+    out = os.path.join(_LIB, "libsio_hostqp.so")
+    if force or _newer([src], out):
+        # -ffp-contract=off: the same float64 sequence on every host
+        subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-Wall",
+                               src, "-o", out, "-lm"])
+    return out
+
+
 def build_all(force=False, verbose=False):
-    return build_cuda(force, verbose), build_hostgeom(force)
+    return build_cuda(force, verbose), build_hostgeom(force), build_hostqp(force)
 
 
 if __name__ == "__main__":

@@ -58,3 +58,22 @@ def test_batch_qp_reaches_feasibility(scene):
     assert feasible >= 12
     rec = res.records()
     assert rec.shape == (16, 16) and np.allclose(rec[:, :12], res.T)
+
+
+def test_array_driver_equals_scalar_driver(scene):
+    """optimizeCollFreeBatchFast (padded arrays + native batched QP + pruned sweeps) walks every problem through the
+    same iterations as the per-problem driver; poses agree to the QP's rounding."""
+    from semiinfiniteoptimization_b200 import batch
+    G, cube, chair = scene
+    poses = c1_poses(48, seed=21)
+    ref = batch.optimizeCollFreeBatch(cube, chair, poses, qp='scalar', keep_trace=True)
+    fast = batch.optimizeCollFreeBatchFast(cube, chair, poses, keep_trace=True)
+    assert np.array_equal(ref.num_iterations, fast.num_iterations) and ref.status == fast.status
+    assert ref.outer_iterations == fast.outer_iterations > 200
+    assert np.abs(ref.T - fast.T).max() <= 1e-6
+    for p in range(len(poses)):
+        assert len(ref.trace[p]) == len(fast.trace[p])
+        assert [len(y) for y in ref.instantiated_params[p]] == [len(y) for y in fast.instantiated_params[p]]
+        assert np.allclose(np.array(ref.instantiated_params[p]).reshape(-1), np.array(fast.instantiated_params[p]).reshape(-1), atol=1e-12)
+    assert np.allclose(ref.gx, fast.gx, atol=1e-6) and np.allclose(ref.fx, fast.fx, atol=1e-6)
+    assert fast.time_qp > 0 and fast.point_queries == ref.point_queries

@@ -277,3 +277,30 @@ def test_interval_lipschitz_minimum():
     assert f(1.0, 2.0, 0) == 1.0
     assert np.isclose(f(1.0, 1.0, 2.0), 0.0)          # u = 1/2 -> a - K/2
     assert np.isclose(f(0.0, 5.0, 1.0), -0.5)         # u outside [0,1]
+
+
+def test_native_batched_qp_equals_scalar_qp():
+    """_host/csrc/hostqp.c (reduced n x n ADMM, OpenMP over problems) against the scalar solve_qp_osqp restatement
+    (sip.py:294-378) on random SIP-step problems, slack fallbacks and row-less problems included."""
+    from semiinfiniteoptimization_b200 import sip
+    from semiinfiniteoptimization_b200._host import qp
+    rng = np.random.default_rng(0)
+    B, n = 400, 6
+    W = rng.uniform(0.01, 1.0, (B, 1)) * np.ones((B, n))
+    xdes = rng.normal(0, 0.2, (B, n))
+    counts = rng.integers(0, 12, B)
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    rows = rng.normal(0, 1, (offs[-1], n))
+    depths = rng.normal(0.0, 0.05, offs[-1])
+    trs = rng.uniform(0.05, 0.5, (B, 1)) * np.ones((B, n))
+    dx, st, its = qp.sip_step_batch(W, xdes, offs, rows, depths, -trs, trs, reg=1e-3, return_iters=True)
+    assert set(np.unique(st)) <= {0, 1, 2} and (st == 1).sum() > 5 and (st == 2).sum() == (counts == 0).sum()
+    cd = sip.ConstraintGenerationData([None])
+    cd.constraint_inflation = 1e-3
+    for p in range(120):
+        if counts[p] == 0:
+            assert np.array_equal(dx[p], xdes[p])          # no rows: xdes, box ignored (sip.py:288)
+            continue
+        ref = cd.solve_qp_osqp(W[p], xdes[p], list(rows[offs[p]:offs[p + 1]]), list(depths[offs[p]:offs[p + 1]]), -trs[p], trs[p],
+                               regularizationFactor=1e-3)
+        assert np.abs(ref - dx[p]).max() <= 1e-8

@@ -17,9 +17,9 @@ import torch.distributed as dist
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--problems", type=int, default=65536)
-ap.add_argument("--sip-problems", type=int, default=1024)
+ap.add_argument("--sip-problems", type=int, default=65536)
 ap.add_argument("--max-iters", type=int, default=10)
-ap.add_argument("--qp", default="batch")
+ap.add_argument("--qp", default="native", help="native: array driver + hostqp.c; scalar/batch: per-problem driver")
 a = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -71,7 +71,10 @@ if nb == 0:
     sys.exit(0)
 st = sip.SemiInfiniteOptimizationSettings(); st.max_iters = a.max_iters
 t0 = time.time()
-res = batch.optimizeCollFreeBatch(cube, scene, mine[:nb], settings=st, qp=a.qp)
+if a.qp == "native":
+    res = batch.optimizeCollFreeBatchFast(cube, scene, mine[:nb], settings=st)
+else:
+    res = batch.optimizeCollFreeBatch(cube, scene, mine[:nb], settings=st, qp=a.qp)
 wall = time.time() - t0
 rec = torch.tensor([res.outer_iterations, wall, res.time_cons, res.time_qp, res.point_queries, float((res.gx > -5e-3).sum()), nb], dtype=torch.float64, device="cuda")
 if world > 1:
