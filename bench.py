@@ -25,6 +25,11 @@ scaling; geometry replicated) and the compact per-pose results are all-gathered 
 `cpu_baseline`: the CPU oracle (oracle/, float64 brute force, all host threads) on a bounded
            sample of the same sweep, rank 0 / N=1 only.
 
+`sip`     : BASELINE.json's second metric, SIP outer iterations/s, on configs[4] ("C5"): 65,536 independent
+           cube-vs-scene optimizeCollFree problems (declared synthetic scene, 262,144 points) sharded across the
+           ranks and solved in lock step (batch.optimizeCollFreeBatchFast), with the oracle / QP / other split; at
+           N=1 also the CPU path (restated SIP loop on the CPU oracle, one process per host core, bounded sample).
+
 --impl reference times that CPU oracle port as the reference arm (the reference itself is
 Python 2 on absent Klampt/OSQP and cannot run).
 """
@@ -46,6 +51,7 @@ CLOUD_N = 1 << 20
 GRIDRES = 0.01
 BYTES_PER_QUERY = 48          # 16 B float4 point + 8 x 4 B corners
 GATHER_BYTES_PER_QUERY = 32
+SIP_PROBLEMS = 65536
 METRIC = "sdf_oracle_point_queries_per_s"
 UNIT = "queries/s"
 
@@ -176,6 +182,7 @@ def run_reference(args):
     npose = max(1, min(POSES_PER_GPU, threads))
     # per step: npose poses x a slice of the cloud sized for ~2 s
     n0 = 1 << 15
+    O.min_distance(G, cloud[:n0], T_rel[:npose], L=L)                 # warm the threads and pages before sizing the step
     t0 = time.perf_counter()
     O.min_distance(G, cloud[:n0], T_rel[:npose], L=L)
     rate = npose * n0 / (time.perf_counter() - t0)
@@ -196,7 +203,84 @@ def run_reference(args):
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference is Python 2 on Klampt/OSQP (absent, un-vendored): its path cannot run; this arm is the CPU "
                     "oracle port (oracle/sio_oracle.c) on the host cores"}
+    if not args.no_sip:
+        line["sip"] = cpu_sip_baseline()
     print(json.dumps(line))
+
+
+def _cpu_sip_worker(args):
+    """one host process: scalar SIP (sip.py restated) on the CPU oracle for its share of C5 problems, until the budget."""
+    first, step, budget = args
+    import warnings
+    warnings.simplefilter("ignore")
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import ref_geometryopt as R
+    from semiinfiniteoptimization_b200 import geometryopt as G
+    from semiinfiniteoptimization_b200 import sip, workloads
+    from semiinfiniteoptimization_b200._host.geometry import Geometry3D, PointCloud
+    cube = R.RefPDG(workloads.c5_cube(), 0.05, None)
+    scene = R.RefPDG(Geometry3D(PointCloud(workloads.c5_scene_cloud())), None, 0.02)
+    con = R.RefObjectCollisionConstraint(cube, scene)
+    poses = workloads.c5_poses(SIP_PROBLEMS, seed=3)
+    iters, solved, t0 = 0, 0, time.perf_counter()
+    k = first
+    while time.perf_counter() - t0 < budget and k < len(poses):
+        res = sip.optimizeSemiInfinite(G.ObjectPoseObjective(poses[k]), [con], poses[k], verbose=0)
+        iters += res.num_iterations
+        solved += 1
+        k += step
+    return iters, solved, time.perf_counter() - t0
+
+
+def cpu_sip_baseline(budget_s=8.0):
+    import multiprocessing as mp
+    n = os.cpu_count() or 1
+    # spawn: the parent has live OpenMP (and, in the GPU arm, CUDA) state that must not be forked
+    with mp.get_context("spawn").Pool(n) as pool:
+        out = pool.map(_cpu_sip_worker, [(i, n, budget_s) for i in range(n)])
+    iters = sum(o[0] for o in out)
+    wall = max(o[2] for o in out)
+    return {"value": iters / wall, "unit": "SIP outer iterations/s", "cores": n, "kind": "port",
+            "sample": "%d of the 65,536 C5 problems (every %d-th), restated sip.py loop + CPU oracle port (float64 brute-force "
+                      "minvalue over 262,144 points) + host QP, one process per core, %.1f s" % (sum(o[1] for o in out), n, wall)}
+
+
+def sip_leg(ctx, rank, world, want_cpu):
+    """C5 in lock step on this rank's shard; returns the aggregated record on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from semiinfiniteoptimization_b200 import batch, geometryopt as G, sip, workloads
+    from semiinfiniteoptimization_b200 import dist as sdist
+    from semiinfiniteoptimization_b200._host.geometry import Geometry3D, PointCloud
+    cube = G.PenetrationDepthGeometry(workloads.c5_cube(), 0.05, None, context=ctx)
+    scene = G.PenetrationDepthGeometry(Geometry3D(PointCloud(workloads.c5_scene_cloud())), None, 0.02, context=ctx)
+    poses = workloads.c5_poses(SIP_PROBLEMS, seed=3)
+    lo, hi = sdist.shard_range(SIP_PROBLEMS)
+    batch.optimizeCollFreeBatchFast(cube, scene, poses[lo:lo + 64])            # warm-up (allocations, first launches)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res = batch.optimizeCollFreeBatchFast(cube, scene, poses[lo:hi])
+    wall = time.perf_counter() - t0
+    rec = torch.tensor([res.outer_iterations, wall, res.time_cons, res.time_qp, res.point_queries, float((res.gx > -5e-3).sum()),
+                        float((np.asarray(res.gx0) < 0).sum())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = rec.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rec, op=dist.ReduceOp.SUM)
+        wall = float(mx[1].item())
+    if rank != 0:
+        return None
+    out = {"value": float(rec[0].item()) / wall, "unit": "SIP outer iterations/s", "scaling": "strong",
+           "workload": "C5: %d independent optimizeCollFree problems (cube SDF@0.05 vs synthetic 262,144-point scene, seed 2; poses "
+                       "seed 3), reference default settings (max_iters 50), sharded over %d GPU(s), lock-step array driver" % (SIP_PROBLEMS, world),
+           "outer_iterations": int(rec[0].item()), "wall_s": wall, "oracle_s_per_rank": float(rec[2].item()) / world,
+           "qp_s_per_rank": float(rec[3].item()) / world, "other_s_per_rank": wall - float(rec[2].item() + rec[3].item()) / world,
+           "oracle_point_queries_resolved": int(rec[4].item()), "started_in_collision": int(rec[6].item()),
+           "ended_feasible(g>-5e-3)": int(rec[5].item())}
+    if want_cpu:
+        out["cpu_baseline"] = cpu_sip_baseline()
+    return out
 
 
 def workload_config(ngpu):
@@ -213,7 +297,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-sip", action="store_true", help="skip the C5 SIP iterations/s leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -342,6 +427,10 @@ def main():
                   "note": "SIO_PRUNE: Lipschitz lower bound per 128-point sub-tile (the GPU analogue of Klampt's bounding-hierarchy "
                           "search inside distance_ext); effective = all (pose, point) pairs resolved / time"}
 
+    sip_rec = None
+    if not args.no_sip:
+        sip_rec = sip_leg(ctx, rank, world, want_cpu=(world == 1 and not args.no_cpu))
+
     if rank == 0:
         bulk = float(np.mean(bulk_ms))
         q1 = B * CLOUD_N
@@ -353,19 +442,38 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = q1 * BYTES_PER_QUERY / (bulk * 1e-3) / 1e9
         gather_peak = ctx.bench_gather(int(np.prod(vg.dims)), 1 << 26, iters=5)
+        gathered = q1 * GATHER_BYTES_PER_QUERY / (bulk * 1e-3) / 1e9
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        l1_peak = n_sm * 128 * sm_mhz * 1e6 / 1e9
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic, traffic_src = tr["k_min_f32"]["dram_bytes_per_launch"], tr["k_min_f32"]["source"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": "k_min_f32", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None,
+                    "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "note": "frac > 1 against HBM is expected: the cloud is read once per transform chunk and the grid bricks are "
+                            "L1/L2-resident (DRAM traffic per launch is `traffic`, far below the 48 B/query algorithmic figure), so HBM "
+                            "does not bind.  ncu (profiles/) shows the binding unit is the L1 data pipe (one 32 B brick per query = 8 "
+                            "wavefronts per warp load): see `l1_data_pipe`",
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
                     "bytes_per_query": BYTES_PER_QUERY, "kernel_ms": bulk,
-                    "gather": {"achieved": q1 * GATHER_BYTES_PER_QUERY / (bulk * 1e-3) / 1e9, "peak": gather_peak, "unit": "GB/s",
-                               "frac": q1 * GATHER_BYTES_PER_QUERY / (bulk * 1e-3) / 1e9 / gather_peak,
-                               "peak_source": "sio_bench_gather: random 4 B loads over an L2-resident array of the grid's size"}}
+                    "l1_data_pipe": {"achieved": gathered, "peak": l1_peak, "unit": "GB/s", "frac": gathered / l1_peak,
+                                     "peak_source": "%d SMs x 128 B/clk x %.0f MHz (L1TEX data-stage width x the SM clock sampled during the "
+                                                    "timed region); achieved = 32 B brick per query delivered to registers; ncu "
+                                                    "l1tex__data_pipe_lsu_wavefronts is 72%% of peak for this kernel (bricks + cloud tiles + "
+                                                    "the shared-memory transform records)" % (n_sm, sm_mhz)},
+                    "l2_gather": {"achieved": gathered, "peak": gather_peak, "unit": "GB/s", "frac": gathered / gather_peak,
+                                  "peak_source": "sio_bench_gather: random 4 B loads over an L2-resident array of the grid's size; the "
+                                                 "kernel exceeds it because Morton-ordered queries reuse bricks in L1 (hit rate 54%)"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
                 "check": {"dmin_first": float(dmin_h[0]), "argmin_first": int(arg_h[0]), "n_under_total": n_under},
-                "pruned": pruned}
+                "pruned": pruned, "sip": sip_rec}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(vg, cloud, T_rel)
         print(json.dumps(line))
