@@ -146,6 +146,20 @@ int sio_robot_min_distance(sio_ctx* ctx, sio_handle robot, const sio_handle* lin
                            double* dmin, int64_t* argmin, int32_t* n_under);
 
 /* ---- measurement helpers (bench.py only) ---------------------------------------------------- */
+/* ---- the QPs of one lock-step SIP iteration ------------------------------------
+ * replaces: ConstraintGenerationData.solve_qp_osqp -> osqp.OSQP().setup/solve -- sip.py:294-331, one
+ * call per problem per outer iteration (sip.py:964), here for `nprob` problems at once, one warp each:
+ *     min (x - xdes)' diag(W) (x - xdes) + reg |x|^2   s.t.  rows x + depths >= inflation,  xmin <= x <= xmax
+ *   W, xdes, xmin, xmax [nprob*n] (xmin/xmax may both be NULL); offsets [nprob+1] into rows [total*n], depths [total]
+ *   n = 6 (pose problems) or 7 (TX90 configurations).
+ * status[p]: 0 = strict problem solved, 1 = solved by the reference's slack re-solve (strict problem infeasible or
+ * out of scale, sip.py:332-357), 2 = no rows (dx = xdes, sip.py:288), 3 = not handled on the device (more than 64
+ * rows, or a polish system larger than the kernel's scratch): the caller solves those on the host (hostqp.c),
+ * dx[p] is left untouched. */
+int sio_sip_step_qp(sio_ctx* ctx, int32_t n, int64_t nprob, const double* W, const double* xdes, const double* xmin,
+                    const double* xmax, const int64_t* offsets, const double* rows, const double* depths, double reg,
+                    double inflation, double eps_abs, int32_t max_iter, double* dx, int32_t* status);
+
 /* device time (ms, CUDA events on the context's stream) of the fp32 bulk kernel launches
  * (k_min_f32) of the LAST sio_min_distance[_dev] call; synchronises on that call's end event. */
 int sio_ctx_last_bulk_ms(sio_ctx* ctx, double* ms);

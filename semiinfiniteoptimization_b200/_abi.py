@@ -75,6 +75,7 @@ def load_library():
     L.sio_min_distance_dev.argtypes = [P, P, I32, P, I32, P, P, I64, C.c_int, P, P, P]
     L.sio_under_fetch.argtypes = [P, I64, P, P, P, C.POINTER(I64)]
     L.sio_pose_rows.argtypes = [P, I32, P, P, I64, P, C.c_int, P, P]
+    L.sio_sip_step_qp.argtypes = [P, I32, I64, P, P, P, P, P, P, P, D, D, D, I32, P, P]
     L.sio_robot_create.argtypes = [P, I32, P, P, P, P, C.POINTER(I32)]
     L.sio_robot_destroy.argtypes = [P, I32]
     L.sio_fk.argtypes = [P, I32, P, I64, P]
@@ -227,6 +228,25 @@ class Context:
         self._ck(self.L.sio_pose_rows(self.h, grid, T.ctypes.data, off.ctypes.data, len(T), p.ctypes.data, int(flags),
                                       d.ctypes.data, _ptr(rows)))
         return d, rows
+
+    # -- SIP-step QPs --
+    def sip_step_qp(self, W, xdes, offs, rows, depths, xmin=None, xmax=None, reg=1e-2, inflation=1e-3, eps_abs=1e-5, max_iter=20000):
+        """dx (B,n), status (B,) of one lock-step iteration's strict QPs; status 3 = solve on the host."""
+        W = _f64(W)
+        xdes = _f64(xdes)
+        B, n = W.shape
+        off = np.ascontiguousarray(offs, dtype=np.int64)
+        rows = _f64(rows).reshape(-1, n)
+        depths = _f64(depths)
+        assert len(off) == B + 1 and off[-1] == len(rows) == len(depths)
+        lo = None if xmin is None else _f64(xmin)
+        hi = None if xmax is None else _f64(xmax)
+        dx = np.zeros((B, n))
+        status = np.empty(B, dtype=np.int32)
+        self._ck(self.L.sio_sip_step_qp(self.h, n, B, W.ctypes.data, xdes.ctypes.data, _ptr(lo), _ptr(hi), off.ctypes.data,
+                                        rows.ctypes.data if len(rows) else None, depths.ctypes.data if len(depths) else None,
+                                        float(reg), float(inflation), float(eps_abs), int(max_iter), dx.ctypes.data, status.ctypes.data))
+        return dx, status
 
     # -- K4 --
     def robot_create(self, parent, tparent, axis, jtype=None):

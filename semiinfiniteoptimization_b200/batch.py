@@ -339,11 +339,12 @@ def _exp_so3_vec(W):
     return np.eye(3)[None] + a[:, None, None] * K + b[:, None, None] * K2
 
 
-def optimizeCollFreeBatchFast(obj, env, Tinits, Tdess=None, settings=None, context=None, flags=None, keep_trace=False):
+def optimizeCollFreeBatchFast(obj, env, Tinits, Tdess=None, settings=None, context=None, flags=None, keep_trace=False, qp='device'):
     """The same lock-step algorithm as optimizeCollFreeBatch, written array-at-a-time: instantiated
     parameters live in padded (B, cap, 3) arrays, the exclusion hash is an integer key array, every
     oracle request is one device call over all live problems and all QPs of an outer iteration are
-    solved by ONE call into the native batched solver (_host/csrc/hostqp.c, OpenMP).  Per-problem
+    solved by ONE call: qp='device' -> sio_sip_step_qp (one warp per problem; the few problems that need the
+    reference's slack re-solve go to the host solver), qp='host' -> _host/csrc/hostqp.c (OpenMP).  Per-problem
     arithmetic and quirks are those of sip.py:795-1241 / the scalar driver above; the QP answers differ
     from the scalar path only in rounding (reduced n x n system instead of the KKT LU)."""
     from ._host import se3, so3
@@ -482,8 +483,20 @@ def optimizeCollFreeBatchFast(obj, env, Tinits, Tdess=None, settings=None, conte
         # ---- QP step (sip.py:945-964): every problem in one native call -----------------------------
         t0 = time.time()
         ones6 = np.ones((len(idx), 6))
-        dx, _ = _qp.sip_step_batch(w[idx][:, None] * ones6, dxdes, offs, rows, D[mask], -trs[idx][:, None] * ones6,
-                                   trs[idx][:, None] * ones6, reg=reg, inflation=settings.constraint_inflation)
+        Wq, lo_q, hi_q, dep = w[idx][:, None] * ones6, -trs[idx][:, None] * ones6, trs[idx][:, None] * ones6, D[mask]
+        if qp == 'device':
+            dx, qst = ctx.sip_step_qp(Wq, dxdes, offs, rows, dep, lo_q, hi_q, reg=reg, inflation=settings.constraint_inflation)
+            res.time_qp_device = getattr(res, 'time_qp_device', 0.0) + time.time() - t0
+            todo = np.nonzero(qst == 3)[0]
+            if len(todo):                            # slack re-solve (sip.py:332-357) on the host
+                cn = (offs[1:] - offs[:-1])[todo]
+                sub = np.concatenate([[0], np.cumsum(cn)]).astype(np.int64)
+                take = np.concatenate([np.arange(offs[k], offs[k + 1]) for k in todo]) if sub[-1] else np.zeros(0, dtype=np.int64)
+                dx[todo], _ = _qp.sip_step_batch(Wq[todo], dxdes[todo], sub, rows[take], dep[take], lo_q[todo], hi_q[todo], reg=reg,
+                                                 inflation=settings.constraint_inflation)
+                res.qp_host_fallbacks = getattr(res, 'qp_host_fallbacks', 0) + len(todo)
+        else:
+            dx, _ = _qp.sip_step_batch(Wq, dxdes, offs, rows, dep, lo_q, hi_q, reg=reg, inflation=settings.constraint_inflation)
         res.time_qp += time.time() - t0
         dxn2 = (dx * dx).sum(1)
         conv = dxn2 < xeps2

@@ -24,6 +24,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 CUDA_UNITS = [
     ("sio_kernels.cu", []),
     ("sio_fp64.cu", ["--fmad=false"]),      # plain IEEE float64 sequence, no contraction
+    ("sio_qp.cu", ["--fmad=false"]),        # the same float64 sequence as the host solver
     ("sio_abi.cu", []),
 ]
 

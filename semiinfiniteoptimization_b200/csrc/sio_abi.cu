@@ -110,6 +110,7 @@ struct sio_ctx {
     std::vector<RobotH> robots;
     // scratch
     DevBuf s_lb, s_ub, s_items, s_icnt;
+    DevBuf s_qp;                     // per-warp polish scratch + work counter of the SIP-step QP kernel
     HostBuf h_icnt;
     int n_icnt = 0;                   // batches of the last pruned call (their survivor counts sit in h_icnt)
     int64_t prune_total = 0;          // (transform, sub-tile) pairs of the last pruned call
@@ -200,6 +201,7 @@ int sio_ctx_destroy(sio_ctx* c) {
     for (auto& g : c->grids) if (g.live) { cudaFree(g.d_v); cudaFree(g.d_brick); cudaFree(g.d_meta); }
     for (auto& p : c->clouds) if (p.live) { cudaFree(p.d_pts); cudaFree(p.d_rep); cudaFree(p.d_perm); }
     for (auto& r : c->robots) if (r.live) { cudaFree(r.d_parent); cudaFree(r.d_jtype); cudaFree(r.d_tparent); cudaFree(r.d_axis); }
+    c->s_qp.release();
     c->s_lb.release(); c->s_ub.release(); c->s_items.release(); c->s_icnt.release(); c->h_icnt.release();
     DevBuf* bufs[] = {&c->s_xf, &c->s_keys, &c->s_gridtab, &c->s_cand, &c->s_cnt, &c->s_in0, &c->s_in1, &c->s_in2, &c->s_in3,
                       &c->s_out0, &c->s_out1, &c->s_out2, &c->s_tlinks, &c->s_trel, &c->s_gob};
@@ -697,6 +699,52 @@ int sio_pose_rows(sio_ctx* c, sio_handle grid, const double* T_pose, const int64
     CU(cudaMemcpyAsync(d, c->s_out0.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (rows) CU(cudaMemcpyAsync(rows, c->s_out1.p, (size_t)total * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return SIO_OK;
+}
+
+// ---- SIP-step QPs ----------------------------------------------------------------------------------------
+int sio_sip_step_qp(sio_ctx* c, int32_t n, int64_t nprob, const double* W, const double* xdes, const double* xmin,
+                    const double* xmax, const int64_t* offsets, const double* rows, const double* depths, double reg,
+                    double inflation, double eps_abs, int32_t max_iter, double* dx, int32_t* status) {
+    if (!c || nprob < 0 || (nprob > 0 && (!W || !xdes || !offsets || !dx || !status)) || ((xmin == nullptr) != (xmax == nullptr)))
+        return fail(SIO_ERR_INVALID, "sio_sip_step_qp: bad argument");
+    if (n != 6 && n != 7) return fail(SIO_ERR_INVALID, "sio_sip_step_qp: n must be 6 or 7, got %d", n);
+    if (nprob == 0) return SIO_OK;
+    const int64_t total = offsets[nprob];
+    if (offsets[0] != 0 || total < 0 || (total > 0 && (!rows || !depths))) return fail(SIO_ERR_INVALID, "sio_sip_step_qp: bad offsets/rows");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    // one staging block: [W | xdes | xmin | xmax | depths | rows | offsets]
+    const size_t v = (size_t)nprob * n * sizeof(double);
+    const size_t oW = 0, oX = v, oLo = 2 * v, oHi = 3 * v, oD = 4 * v, oR = oD + (size_t)total * sizeof(double);
+    const size_t oO = oR + (size_t)total * n * sizeof(double), in_bytes = oO + (size_t)(nprob + 1) * sizeof(int64_t);
+    CU(c->h_a.ensure(in_bytes));
+    CU(c->s_in0.ensure(in_bytes));
+    char* h = c->h_a.as<char>();
+    std::memcpy(h + oW, W, v);
+    std::memcpy(h + oX, xdes, v);
+    if (xmin) { std::memcpy(h + oLo, xmin, v); std::memcpy(h + oHi, xmax, v); }
+    if (total > 0) { std::memcpy(h + oD, depths, (size_t)total * sizeof(double)); std::memcpy(h + oR, rows, (size_t)total * n * sizeof(double)); }
+    std::memcpy(h + oO, offsets, (size_t)(nprob + 1) * sizeof(int64_t));
+    CU(cudaMemcpyAsync(c->s_in0.p, h, in_bytes, cudaMemcpyHostToDevice, st));
+    const size_t out_bytes = v + (size_t)nprob * sizeof(int32_t);
+    CU(c->s_out0.ensure(out_bytes));
+    CU(c->h_b.ensure(out_bytes));
+    CU(c->s_qp.ensure(sip_qp_scratch_bytes(c->num_sms)));
+    char* d = c->s_in0.as<char>();
+    char* o = c->s_out0.as<char>();
+    if (launch_sip_qp(n, nprob, reinterpret_cast<double*>(d + oW), reinterpret_cast<double*>(d + oX),
+                      xmin ? reinterpret_cast<double*>(d + oLo) : nullptr, xmin ? reinterpret_cast<double*>(d + oHi) : nullptr,
+                      reinterpret_cast<int64_t*>(d + oO), reinterpret_cast<double*>(d + oR), reinterpret_cast<double*>(d + oD), reg,
+                      inflation, eps_abs, max_iter > 0 ? max_iter : 20000, reinterpret_cast<double*>(o),
+                      reinterpret_cast<int32_t*>(o + v), c->s_qp.p, c->num_sms, st))
+        return fail(SIO_ERR_INVALID, "sio_sip_step_qp: unsupported n");
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_b.p, o, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::memcpy(dx, c->h_b.p, v);
+    std::memcpy(status, c->h_b.as<char>() + v, (size_t)nprob * sizeof(int32_t));
     return SIO_OK;
 }
 

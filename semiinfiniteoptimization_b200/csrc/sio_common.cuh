@@ -117,6 +117,11 @@ void launch_link_rel(const double* T_links, int32_t n_links, const int32_t* link
 void launch_chain_rows(RobotDev r, const GridDev* grids, const int32_t* link_grid, const double* T_links,
                        const int32_t* cfg_of_pt, const int32_t* link_of_pt, const double* pts, int64_t P,
                        int normalize, double* d, double* rows, cudaStream_t st);
+// the strict QPs of one lock-step SIP iteration, one warp per problem (sio_qp.cu); returns -1 for an unsupported n
+size_t sip_qp_scratch_bytes(int num_sms);
+int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, const double* xmin, const double* xmax,
+                  const int64_t* offs, const double* rows, const double* depths, double reg, double inflation, double eps_abs,
+                  int max_iter, double* dx, int32_t* status, void* scratch, int num_sms, cudaStream_t st);
 void launch_gather_bench(const float* arr, int64_t n_elems, const uint32_t* idx, int64_t n_gathers,
                          float* sink, cudaStream_t st);
 

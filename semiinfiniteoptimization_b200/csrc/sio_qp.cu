@@ -1,0 +1,456 @@
+// sio_qp.cu -- the QPs of one lock-step SIP iteration on the device (sm_100a), one warp per problem.
+//
+// What it replaces: the OSQP solves of ConstraintGenerationData.solve_qp_osqp (sip.py:294-378), one call per
+// problem per outer iteration,
+//     min (x - xdes)' W (x - xdes) + reg |x|^2   s.t.  A x + b >= inflation,  xmin <= x <= xmax,
+// and, when that strict problem is infeasible or its solution out of scale, the slack problem of
+// sip.py:332-357 (one slack variable per row, penalty 'auto') -- for the 65,536 problems of BASELINE.json
+// configs[4] advancing together.  The algorithm is the one of _host/qp.py / _host/csrc/hostqp.c (OSQP's ADMM:
+// over-relaxation, adaptive rho, residual test every 10 iterations, primal-infeasibility certificate,
+// active-set polish), in float64 without FMA contraction.
+//
+// Mapping: lane r owns constraint rows r and r+32 (the k instantiated-parameter rows, then the n box rows) and, in
+// the slack problem, the slack variables of its rows; x lives replicated in every lane.  The quadratic term is
+// diagonal and every slack variable sits in exactly one row, so the ADMM linear system reduces (Schur complement
+// over the slack block) to an n x n Cholesky that every lane solves redundantly; A'(rho z - y) is n butterfly
+// reductions; everything else is lane-local.  The polish solves its KKT system (slack unknowns eliminated the same
+// way) with a warp-parallel Gaussian elimination in a per-warp scratch (L2-resident global memory: the ADMM loop
+// itself touches no memory).  Warps are persistent and draw problems from an atomic counter, because the ADMM
+// iteration count varies from tens to thousands between problems.
+// Problems with more than 64 rows are flagged for the host solver.
+#include "sio_common.cuh"
+
+namespace sio {
+
+constexpr int kQpWarps = 4;                 // warps per CTA
+constexpr int kQpMaxRows = 64;              // 2 rows per lane
+constexpr int kQpMaxVars = 8;
+constexpr int kQpMaxKkt = kQpMaxVars + kQpMaxRows;     // largest polish system (x + active rows)
+constexpr int kQpScratch = kQpMaxKkt * (kQpMaxKkt + 1);   // doubles per warp
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <int N>
+struct Chol {
+    double L[N * (N + 1) / 2];              // lower triangle, row-major packed
+    double inv[N];                          // 1 / L[i][i]
+    __device__ __forceinline__ double& at(int i, int j) { return L[i * (i + 1) / 2 + j]; }
+    __device__ __forceinline__ bool factor() {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double d = at(j, j);
+#pragma unroll
+            for (int k = 0; k < j; ++k) d -= at(j, k) * at(j, k);
+            if (!(d > 0.0)) return false;
+            d = sqrt(d);
+            at(j, j) = d;
+            inv[j] = 1.0 / d;
+#pragma unroll
+            for (int i = j + 1; i < N; ++i) {
+                double s = at(i, j);
+#pragma unroll
+                for (int k = 0; k < j; ++k) s -= at(i, k) * at(j, k);
+                at(i, j) = s * inv[j];
+            }
+        }
+        return true;
+    }
+    __device__ __forceinline__ void solve(double (&b)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double s = b[i];
+#pragma unroll
+            for (int k = 0; k < i; ++k) s -= at(i, k) * b[k];
+            b[i] = s * inv[i];
+        }
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+            double s = b[i];
+#pragma unroll
+            for (int k = i + 1; k < N; ++k) s -= at(k, i) * b[k];
+            b[i] = s * inv[i];
+        }
+    }
+};
+
+// Gaussian elimination with partial pivoting on the NN x NN row-major system M x = b in the warp's scratch, rows
+// spread over the lanes.  Pivot choice (first largest |entry|) and the per-row arithmetic are those of the
+// host's serial routine, so the answer is the same.  Returns false on a zero pivot.  Result in b.
+__device__ bool warp_lu_solve(double* M, double* b, int NN, int lane) {
+    for (int c = 0; c < NN; ++c) {
+        double best = -1.0;
+        int pv = NN;
+        for (int r = c + lane; r < NN; r += 32) {
+            const double v = fabs(M[r * NN + c]);
+            if (v > best) { best = v; pv = r; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int op = __shfl_xor_sync(0xffffffffu, pv, o);
+            if (ob > best || (ob == best && op < pv)) { best = ob; pv = op; }
+        }
+        if (!(best > 0.0)) return false;
+        if (pv != c) {
+            for (int kk = lane; kk < NN; kk += 32) { const double t = M[c * NN + kk]; M[c * NN + kk] = M[pv * NN + kk]; M[pv * NN + kk] = t; }
+            if (lane == 0) { const double t = b[c]; b[c] = b[pv]; b[pv] = t; }
+        }
+        __syncwarp();
+        const double piv = M[c * NN + c], bc = b[c];
+        for (int r = c + 1 + lane; r < NN; r += 32) {
+            const double f = M[r * NN + c] / piv;
+            if (f == 0.0) continue;
+            for (int kk = c; kk < NN; ++kk) M[r * NN + kk] -= f * M[c * NN + kk];
+            b[r] -= f * bc;
+        }
+        __syncwarp();
+    }
+    if (lane == 0)
+        for (int r = NN - 1; r >= 0; --r) {
+            double s = b[r];
+            for (int kk = r + 1; kk < NN; ++kk) s -= M[r * NN + kk] * b[kk];
+            b[r] = s / M[r * NN + r];
+        }
+    __syncwarp();
+    return true;
+}
+
+// one lane's share of a problem: two constraint rows (and, in the slack problem, their slack variables)
+template <int N>
+struct Rows {
+    double a[2][N], l[2], u[2];
+    bool have[2], slack[2];                 // row present; row has a slack variable (the k parameter rows)
+};
+
+enum { kAdmmSolved = 0, kAdmmMaxIter = 1, kAdmmInfeasible = 2 };
+
+// ADMM + polish.  SLACK = false: variables x (N).  SLACK = true: variables [x | one slack per parameter row],
+// the slack block carrying the quadratic weight `pen`.  x (and sv, the lane's slack values) hold the answer.
+template <int N, bool SLACK>
+__device__ int admm(const Rows<N>& R, const double (&Pd)[N], const double (&q)[N], double pen, int k, int m, double eps_abs,
+                    double eps_rel, int max_iter, double* kkt, int lane, double (&x)[N], double (&sv)[2]) {
+    constexpr double kInf = 1e20, sigma = 1e-6, alpha = 1.6;
+    constexpr int check_every = 10, adapt_every = 50;
+    double z[2] = {0.0, 0.0}, y[2] = {0.0, 0.0}, rv[2], dy[2] = {0.0, 0.0}, Ax[2] = {0.0, 0.0}, ds[2] = {1.0, 1.0};
+    double rho = 0.1;
+    Chol<N> K;
+    auto set_rho = [&]() {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            rv[s] = (R.u[s] - R.l[s] < 1e-12) ? 1e3 * rho : rho;
+            ds[s] = pen + sigma + rv[s];                  // diagonal of the slack block of the system matrix
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                double v = 0.0;
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+                    if (R.have[s]) {
+                        const double wgt = (SLACK && R.slack[s]) ? rv[s] - rv[s] * rv[s] / ds[s] : rv[s];   // Schur complement
+                        v += wgt * R.a[s][i] * R.a[s][j];
+                    }
+                v = warp_sum(v);
+                K.at(i, j) = v + ((i == j) ? Pd[i] + sigma : 0.0);
+            }
+        return K.factor();
+    };
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = 0.0;
+    sv[0] = sv[1] = 0.0;
+    if (!set_rho()) return kAdmmMaxIter;
+    int st = kAdmmMaxIter;
+    for (int it = 1; it <= max_iter; ++it) {
+        double xt[N], w[2], stl[2] = {0.0, 0.0};
+#pragma unroll
+        for (int s = 0; s < 2; ++s) w[s] = rv[s] * z[s] - y[s];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double v = 0.0;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                double ws = w[s];
+                if (SLACK && R.slack[s]) ws -= rv[s] * (sigma * sv[s] + w[s]) / ds[s];      // eliminate the slack unknown
+                v += R.a[s][i] * ws;                                                       // a = 0 on absent rows
+            }
+            xt[i] = warp_sum(v) + sigma * x[i] - q[i];
+        }
+        K.solve(xt);
+        double ndy = 0.0;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            double ax = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) ax += R.a[s][i] * xt[i];
+            double zs = ax;
+            if (SLACK && R.slack[s]) {
+                stl[s] = (sigma * sv[s] + w[s] - rv[s] * ax) / ds[s];
+                zs = ax + stl[s];
+            }
+            const double zr = alpha * zs + (1.0 - alpha) * z[s];
+            const double c = zr + y[s] / rv[s];
+            const double zn = c < R.l[s] ? R.l[s] : (c > R.u[s] ? R.u[s] : c);
+            const double yn = y[s] + rv[s] * (zr - zn);
+            dy[s] = R.have[s] ? yn - y[s] : 0.0;
+            ndy = fmax(ndy, fabs(dy[s]));
+            if (R.have[s]) { z[s] = zn; y[s] = yn; }
+            if (SLACK && R.slack[s]) sv[s] = alpha * stl[s] + (1.0 - alpha) * sv[s];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = alpha * xt[i] + (1.0 - alpha) * x[i];
+        if ((it % check_every) && it != max_iter) continue;
+        // residuals (qp.py solve_qp: every 10 iterations)
+        double r_prim = 0.0, nAx = 0.0, r_dual = 0.0, nd = 0.0;
+        double Aty[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) Aty[i] = 0.0;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            double v = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) { v += R.a[s][i] * x[i]; Aty[i] += R.a[s][i] * y[s]; }
+            if (SLACK && R.slack[s]) {
+                v += sv[s];
+                const double ps = pen * sv[s];                          // dual residual of the slack variable: pen s + y
+                r_dual = fmax(r_dual, fabs(ps + y[s]));
+                nd = fmax(nd, fmax(fabs(ps), fabs(y[s])));
+            }
+            Ax[s] = v;
+            if (R.have[s]) { r_prim = fmax(r_prim, fabs(v - z[s])); nAx = fmax(nAx, fmax(fabs(v), fabs(z[s]))); }
+        }
+        r_prim = warp_max(r_prim); nAx = warp_max(nAx);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double t = warp_sum(Aty[i]);
+            const double px = Pd[i] * x[i];
+            r_dual = fmax(r_dual, fabs(px + q[i] + t));
+            nd = fmax(nd, fmax(fabs(px), fmax(fabs(t), fabs(q[i]))));
+        }
+        r_dual = warp_max(r_dual); nd = warp_max(nd);
+        if (r_prim <= eps_abs + eps_rel * nAx && r_dual <= eps_abs + eps_rel * nd) { st = kAdmmSolved; break; }
+        ndy = warp_max(ndy);
+        if (ndy > 1e-12) {                                 // primal infeasibility certificate
+            double sup = 0.0, nAt = 0.0;
+            double t[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) t[i] = 0.0;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const double d = dy[s] / ndy;
+#pragma unroll
+                for (int i = 0; i < N; ++i) t[i] += R.a[s][i] * d;
+                if (SLACK && R.slack[s]) nAt = fmax(nAt, fabs(d));      // the slack column of A' dy
+                if (R.have[s]) sup += R.u[s] * fmax(d, 0.0) + R.l[s] * fmin(d, 0.0);
+            }
+            sup = warp_sum(sup);
+            nAt = warp_max(nAt);
+#pragma unroll
+            for (int i = 0; i < N; ++i) nAt = fmax(nAt, fabs(warp_sum(t[i])));
+            if (nAt <= 1e-4 && sup < -1e-4) { st = kAdmmInfeasible; break; }
+        }
+        if (it % adapt_every == 0 && r_prim > 0 && r_dual > 0) {
+            const double scale = sqrt((r_prim / fmax(nAx, 1e-12)) / (r_dual / fmax(nd, 1e-12)));
+            if (scale > 5 || scale < 0.2) {
+                rho = fmin(fmax(rho * scale, 1e-6), 1e6);
+                if (!set_rho()) break;
+            }
+        }
+    }
+    if (st != kAdmmSolved) return st;
+    // ---- polish on the active set (qp.py _polish): KKT system over [variables | active rows] ----------------
+    int flag[2];
+    double rhs[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const bool lo = R.have[s] && ((y[s] < -1e-9) || (Ax[s] - R.l[s] < 1e-7)) && R.l[s] > -kInf / 2;
+        const bool up = R.have[s] && ((y[s] > 1e-9) || (R.u[s] - Ax[s] < 1e-7)) && R.u[s] < kInf / 2;
+        flag[s] = lo || up;
+        rhs[s] = lo ? R.l[s] : R.u[s];
+    }
+    const unsigned m0 = __ballot_sync(0xffffffffu, flag[0]), m1 = __ballot_sync(0xffffffffu, flag[1]);
+    const int na = __popc(m0) + __popc(m1);
+    if (na == 0) return kAdmmSolved;
+    // Unknowns [x | multipliers of the active rows].  A slack variable s_r (weight pen + delta, one entry in its own
+    // row) is eliminated in closed form: s_r = -lambda_r / (pen + delta), which adds 1 / (pen + delta) to that row's
+    // -delta diagonal; slack variables of inactive rows are zero.
+    const int NN = N + na;
+    double* M = kkt;
+    double* bb = M + NN * NN;
+    for (int e = lane; e < NN * (NN + 1); e += 32) M[e] = 0.0;
+    __syncwarp();
+    const double delta = 1e-7;
+    if (lane < N) { M[lane * NN + lane] = Pd[lane] + delta; bb[lane] = -q[lane]; }
+    int idx[2] = {0, 0};
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        if (flag[s]) {                                     // active rows keep their row order
+            idx[s] = N + ((s == 0) ? __popc(m0 & ((1u << lane) - 1u)) : __popc(m0) + __popc(m1 & ((1u << lane) - 1u)));
+#pragma unroll
+            for (int i = 0; i < N; ++i) { M[i * NN + idx[s]] = R.a[s][i]; M[idx[s] * NN + i] = R.a[s][i]; }
+            M[idx[s] * NN + idx[s]] = -delta - ((SLACK && R.slack[s]) ? 1.0 / (pen + delta) : 0.0);
+            bb[idx[s]] = rhs[s];
+        }
+    }
+    __syncwarp();
+    if (!warp_lu_solve(M, bb, NN, lane)) return kAdmmSolved;
+    double xp[N], sp[2] = {0.0, 0.0};
+    double f0 = 0.0, f1 = 0.0, fs0 = 0.0, fs1 = 0.0;
+    int bad = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        xp[i] = bb[i];
+        if (!isfinite(xp[i])) bad = 1;
+        f0 += 0.5 * Pd[i] * x[i] * x[i] + q[i] * x[i];
+        f1 += 0.5 * Pd[i] * xp[i] * xp[i] + q[i] * xp[i];
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) v += R.a[s][i] * xp[i];
+        if (SLACK && R.slack[s]) {
+            sp[s] = flag[s] ? -bb[idx[s]] / (pen + delta) : 0.0;
+            if (!isfinite(sp[s])) bad = 1;
+            v += sp[s];
+            fs0 += 0.5 * pen * sv[s] * sv[s];
+            fs1 += 0.5 * pen * sp[s] * sp[s];
+        }
+        if (R.have[s] && (v < R.l[s] - 1e-7 || v > R.u[s] + 1e-7)) bad = 1;
+    }
+    if (SLACK) { f0 += warp_sum(fs0); f1 += warp_sum(fs1); }
+    bad = __any_sync(0xffffffffu, bad);
+    __syncwarp();
+    if (!bad && !(f1 > f0 + 1e-9 * (1 + fabs(f0)))) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = xp[i];
+        sv[0] = sp[0]; sv[1] = sp[1];
+    }
+    return kAdmmSolved;
+}
+
+// status codes written per problem
+enum { kQpStrict = 0, kQpSlack = 1, kQpNoRows = 2, kQpToHost = 3 };
+
+template <int N>
+__device__ void solve_problem(int64_t p, const double* __restrict__ W, const double* __restrict__ xdes, const double* __restrict__ xmin,
+                              const double* __restrict__ xmax, const int64_t* __restrict__ offs, const double* __restrict__ rows,
+                              const double* __restrict__ depths, double reg, double inflation, double eps_abs, double eps_rel,
+                              int max_iter, double* kkt, int lane, double* __restrict__ dx, int32_t* __restrict__ status) {
+    constexpr double kInf = 1e20;
+    const int k = (int)(offs[p + 1] - offs[p]);
+    const bool box = xmin != nullptr;
+    if (k == 0) {                                          // no rows: xdes, box ignored (sip.py:288)
+        if (lane < N) dx[p * N + lane] = xdes[p * N + lane];
+        if (lane == 0) status[p] = kQpNoRows;
+        return;
+    }
+    const int m = k + (box ? N : 0);
+    if (m > kQpMaxRows) { if (lane == 0) status[p] = kQpToHost; return; }
+    double Pd[N], q[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double w = W[p * N + i];
+        Pd[i] = w + reg;
+        q[i] = -w * xdes[p * N + i];
+    }
+    Rows<N> R;
+    double bneg2 = 0.0, bmin = INFINITY;
+    int nneg = 0;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int r = lane + 32 * s;
+        R.have[s] = r < m;
+        R.slack[s] = r < k;
+        R.l[s] = -kInf; R.u[s] = kInf;
+#pragma unroll
+        for (int i = 0; i < N; ++i) R.a[s][i] = 0.0;
+        if (r < k) {
+            const double* src = rows + (offs[p] + r) * N;
+#pragma unroll
+            for (int i = 0; i < N; ++i) R.a[s][i] = src[i];
+            const double b = depths[offs[p] + r];
+            R.l[s] = -b + inflation;
+            if (b < 0) { bneg2 += b * b; ++nneg; }
+            bmin = fmin(bmin, b);
+        } else if (r < m) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) R.a[s][i] = (i == r - k) ? 1.0 : 0.0;
+            R.l[s] = fmax(xmin[p * N + (r - k)], -kInf);
+            R.u[s] = fmin(xmax[p * N + (r - k)], kInf);
+        }
+    }
+    // |negative depths| is summed in row order on the host; a fixed butterfly order here differs only in rounding
+    bneg2 = warp_sum(bneg2);
+    nneg = __reduce_add_sync(0xffffffffu, nneg);
+    bmin = -warp_max(-bmin);
+    const double bnorm = nneg ? sqrt(bneg2) : 1.0;
+    double x[N], sv[2];
+    int st = admm<N, false>(R, Pd, q, 0.0, k, m, eps_abs, eps_rel, max_iter, kkt, lane, x, sv);
+    double xn = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) xn += x[i] * x[i];
+    int code = kQpStrict;
+    if (st == kAdmmInfeasible || sqrt(xn) * reg > bnorm) {
+        // the reference's slack re-solve (sip.py:332-357), slack_penalty = 'auto'
+        const double pen = (1.0 + nneg) / (fabs(bmin) + 1e-3);
+        st = admm<N, true>(R, Pd, q, pen, k, m, eps_abs, eps_rel, max_iter, kkt, lane, x, sv);
+        if (st == kAdmmInfeasible) { if (lane == 0) status[p] = kQpToHost; return; }
+        code = kQpSlack;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) if (lane == i) dx[p * N + i] = x[i];
+    if (lane == 0) status[p] = code;
+}
+
+// persistent warps: each draws the next problem from *counter (reset to 0 by the launcher)
+template <int N>
+__global__ void __launch_bounds__(kQpWarps * 32)
+k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__ xdes, const double* __restrict__ xmin,
+         const double* __restrict__ xmax, const int64_t* __restrict__ offs, const double* __restrict__ rows,
+         const double* __restrict__ depths, double reg, double inflation, double eps_abs, double eps_rel, int max_iter,
+         double* __restrict__ scratch, unsigned long long* __restrict__ counter, double* __restrict__ dx, int32_t* __restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    double* kkt = scratch + ((size_t)blockIdx.x * kQpWarps + (threadIdx.x >> 5)) * kQpScratch;
+    for (;;) {
+        unsigned long long p = 0;
+        if (lane == 0) p = atomicAdd(counter, 1ull);
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p >= (unsigned long long)nprob) return;
+        solve_problem<N>((int64_t)p, W, xdes, xmin, xmax, offs, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status);
+    }
+}
+
+int sip_qp_grid(int num_sms) { return num_sms * 2; }                      // CTAs: 8 resident warps per SM (register-limited)
+size_t sip_qp_scratch_bytes(int num_sms) { return (size_t)sip_qp_grid(num_sms) * kQpWarps * kQpScratch * sizeof(double) + 64; }
+
+// scratch: sip_qp_scratch_bytes(num_sms) bytes; its last 64 bytes hold the work counter
+int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, const double* xmin, const double* xmax,
+                  const int64_t* offs, const double* rows, const double* depths, double reg, double inflation, double eps_abs,
+                  int max_iter, double* dx, int32_t* status, void* scratch, int num_sms, cudaStream_t st) {
+    if (nprob <= 0) return 0;
+    const int blocks = sip_qp_grid(num_sms);
+    double* kkt = reinterpret_cast<double*>(scratch);
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + sip_qp_scratch_bytes(num_sms) - 64);
+    cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+    if (n == 6)
+        k_sip_qp<6><<<blocks, kQpWarps * 32, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, rows, depths, reg, inflation, eps_abs, 1e-5,
+                                                      max_iter, kkt, counter, dx, status);
+    else if (n == 7)
+        k_sip_qp<7><<<blocks, kQpWarps * 32, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, rows, depths, reg, inflation, eps_abs, 1e-5,
+                                                      max_iter, kkt, counter, dx, status);
+    else
+        return -1;
+    return 0;
+}
+
+}  // namespace sio

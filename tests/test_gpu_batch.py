@@ -67,7 +67,12 @@ def test_array_driver_equals_scalar_driver(scene):
     G, cube, chair = scene
     poses = c1_poses(48, seed=21)
     ref = batch.optimizeCollFreeBatch(cube, chair, poses, qp='scalar', keep_trace=True)
-    fast = batch.optimizeCollFreeBatchFast(cube, chair, poses, keep_trace=True)
+    for qp in ('device', 'host'):
+        fast = batch.optimizeCollFreeBatchFast(cube, chair, poses, keep_trace=True, qp=qp)
+        _same_runs(ref, fast, poses)
+
+
+def _same_runs(ref, fast, poses):
     assert np.array_equal(ref.num_iterations, fast.num_iterations) and ref.status == fast.status
     assert ref.outer_iterations == fast.outer_iterations > 200
     assert np.abs(ref.T - fast.T).max() <= 1e-6
@@ -77,3 +82,37 @@ def test_array_driver_equals_scalar_driver(scene):
         assert np.allclose(np.array(ref.instantiated_params[p]).reshape(-1), np.array(fast.instantiated_params[p]).reshape(-1), atol=1e-12)
     assert np.allclose(ref.gx, fast.gx, atol=1e-6) and np.allclose(ref.fx, fast.fx, atol=1e-6)
     assert fast.time_qp > 0 and fast.point_queries == ref.point_queries
+
+
+def test_device_qp_equals_host_qp(ctx):
+    """sio_sip_step_qp (one warp per problem) against _host/csrc/hostqp.c on random SIP-step problems: same answers,
+    the reference's slack re-solve taken for the same problems (status 3 = left to the host: too many rows, or a
+    polish system larger than the kernel's scratch)."""
+    from semiinfiniteoptimization_b200._host import qp
+    rng = np.random.default_rng(5)
+    B, n = 3000, 6
+    W = rng.uniform(0.01, 1.0, (B, 1)) * np.ones((B, n))
+    xdes = rng.normal(0, 0.2, (B, n))
+    counts = rng.integers(0, 14, B)
+    counts[:3] = [0, 70, 58]                     # no rows; too many rows for the device kernel; the largest it takes
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    rows = rng.normal(0, 1, (offs[-1], n))
+    depths = rng.normal(0.0, 0.05, offs[-1])
+    trs = rng.uniform(0.05, 0.5, (B, 1)) * np.ones((B, n))
+    depths[offs[40]:offs[400]] -= 0.3                # deep penetrations: the strict problems become infeasible
+    dh, sh = qp.sip_step_batch(W, xdes, offs, rows, depths, -trs, trs, reg=1e-3)
+    dd, sd = ctx.sip_step_qp(W, xdes, offs, rows, depths, -trs, trs, reg=1e-3)
+    assert sd[0] == 2 and np.array_equal(dd[0], xdes[0]) and sd[1] == 3
+    keep = np.ones(B, dtype=bool)
+    keep[1] = False
+    assert np.array_equal(sd[keep & (sh == 0)], np.zeros((keep & (sh == 0)).sum(), dtype=np.int32))
+    assert np.array_equal(sd[sh == 2], np.full((sh == 2).sum(), 2, dtype=np.int32))
+    slack = keep & (sh == 1)
+    assert slack.sum() > 50 and set(np.unique(sd[slack])) <= {1, 3} and (sd[slack] == 1).mean() > 0.9
+    same = keep & (sd == sh) & (sh != 2)
+    assert np.abs(dd[same] - dh[same]).max() <= 1e-7
+    # without the box rows
+    dh2, sh2 = qp.sip_step_batch(W[:200], xdes[:200], offs[:201], rows[:offs[200]], depths[:offs[200]], reg=1e-3)
+    dd2, sd2 = ctx.sip_step_qp(W[:200], xdes[:200], offs[:201], rows[:offs[200]], depths[:offs[200]], reg=1e-3)
+    ok = (sh2 == 0) & (sd2 == 0)
+    assert ok.sum() > 100 and np.abs(dd2[ok] - dh2[ok]).max() <= 1e-8
