@@ -27,7 +27,7 @@ ABI_SYMBOLS = (
     "sio_grid_create", "sio_grid_destroy", "sio_cloud_create", "sio_cloud_destroy", "sio_cloud_size",
     "sio_query", "sio_cloud_query_dev", "sio_cloud_perm",
     "sio_min_distance", "sio_min_distance_dev", "sio_under_fetch",
-    "sio_pose_rows",
+    "sio_pose_rows", "sio_sip_step_qp",
     "sio_robot_create", "sio_robot_destroy", "sio_fk", "sio_chain_rows", "sio_robot_min_distance",
     "sio_bench_gather", "sio_ctx_last_bulk_ms", "sio_ctx_last_prune_stats",
 )
