@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "sio_min_distance", "sio_min_distance_dev", "sio_under_fetch",
     "sio_pose_rows", "sio_sip_step_qp",
     "sio_robot_create", "sio_robot_destroy", "sio_fk", "sio_chain_rows", "sio_robot_min_distance",
-    "sio_bench_gather", "sio_ctx_last_bulk_ms", "sio_ctx_last_prune_stats",
+    "sio_bench_gather", "sio_ctx_last_bulk_ms", "sio_ctx_last_prune_stats", "sio_ctx_last_qp_iters",
 )
 
 _lib = None
@@ -84,6 +84,7 @@ def load_library():
     L.sio_bench_gather.argtypes = [P, I64, I64, C.c_int, C.POINTER(D)]
     L.sio_ctx_last_bulk_ms.argtypes = [P, C.POINTER(D)]
     L.sio_ctx_last_prune_stats.argtypes = [P, C.POINTER(I64), C.POINTER(I64)]
+    L.sio_ctx_last_qp_iters.argtypes = [P, C.POINTER(I64)]
     _lib = L
     return L
 
@@ -230,7 +231,7 @@ class Context:
         return d, rows
 
     # -- SIP-step QPs --
-    def sip_step_qp(self, W, xdes, offs, rows, depths, xmin=None, xmax=None, reg=1e-2, inflation=1e-3, eps_abs=1e-5, max_iter=20000):
+    def sip_step_qp(self, W, xdes, offs, rows, depths, xmin=None, xmax=None, reg=1e-2, inflation=1e-3, eps_abs=1e-5, max_iter=4000):
         """dx (B,n), status (B,) of one lock-step iteration's strict QPs; status 3 = solve on the host."""
         W = _f64(W)
         xdes = _f64(xdes)
@@ -247,6 +248,11 @@ class Context:
                                         rows.ctypes.data if len(rows) else None, depths.ctypes.data if len(depths) else None,
                                         float(reg), float(inflation), float(eps_abs), int(max_iter), dx.ctypes.data, status.ctypes.data))
         return dx, status
+
+    def last_qp_iters(self):
+        n = C.c_int64(0)
+        self._ck(self.L.sio_ctx_last_qp_iters(self.h, C.byref(n)))
+        return n.value
 
     # -- K4 --
     def robot_create(self, parent, tparent, axis, jtype=None):

@@ -253,7 +253,7 @@ int hqp_sip_step_batch(int64_t nprob, int n, const double* W, const double* xdes
     const int NS = n + (int)maxrows;                     /* variables of the largest slack problem */
     const size_t wsz = (size_t)NS * NS + 8 * (size_t)M + 4 * (size_t)NS + (size_t)(NS + M) * (NS + M + 1)
                      + (size_t)M * NS + 2 * (size_t)M + 3 * (size_t)NS + 64;
-    hqp_opts o = {eps_abs, 1e-5, 0.1, 1e-6, 1.6, max_iter > 0 ? max_iter : 20000, 10, 50, 1};
+    hqp_opts o = {eps_abs, 1e-5, 0.1, 1e-6, 1.6, max_iter > 0 ? max_iter : 4000, 10, 50, 1};
     int fail = 0;
 #pragma omp parallel
     {

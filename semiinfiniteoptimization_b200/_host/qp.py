@@ -10,6 +10,9 @@ rho, the standard primal/dual residual test and the primal-infeasibility certifi
 an optional polish (equality-constrained solve on the identified active set).  The QP is small
 (n = 6 / 7 / 455 variables) and stays on the host per BASELINE.json's north_star.
 
+Iteration limit 4000 = OSQP's default `max_iter` (the reference passes only `eps_abs=1e-5`, sip.py:327); a
+problem that reaches it returns the last iterate, as OSQP does.
+
 `solve_qp` handles one problem (dense or sparse); `solve_qp_batch` runs many small dense problems
 of identical shape in lock-step with numpy (the C5 batch).
 """
@@ -49,7 +52,7 @@ def _kkt_solver(P, A, sigma, rho_vec, sparse):
     return lambda b: scipy.linalg.lu_solve(lu, b)
 
 
-def solve_qp(P, q, A, l, u, eps_abs=1e-5, eps_rel=1e-5, max_iter=20000, rho=0.1, sigma=1e-6, alpha=1.6,
+def solve_qp(P, q, A, l, u, eps_abs=1e-5, eps_rel=1e-5, max_iter=4000, rho=0.1, sigma=1e-6, alpha=1.6,
              polish=True, check_every=10, adapt_every=50):
     sparse = scipy.sparse.issparse(P) or scipy.sparse.issparse(A)
     if sparse:
@@ -218,7 +221,7 @@ def _native_lib():
     return _native
 
 
-def sip_step_batch(W, xdes, offs, rows, depths, xmin=None, xmax=None, reg=1e-2, inflation=1e-3, eps_abs=1e-5, max_iter=20000,
+def sip_step_batch(W, xdes, offs, rows, depths, xmin=None, xmax=None, reg=1e-2, inflation=1e-3, eps_abs=1e-5, max_iter=4000,
                    return_iters=False):
     """dx of `len(W)` problems at once: min (x-xdes)'W(x-xdes) + reg|x|^2  s.t.  rows x + depths >= inflation,
     xmin <= x <= xmax, with the reference's slack re-solve (sip.py:294-378).  W, xdes, xmin, xmax: (B,n);

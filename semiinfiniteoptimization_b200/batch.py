@@ -436,6 +436,7 @@ def optimizeCollFreeBatchFast(obj, env, Tinits, Tdess=None, settings=None, conte
 
     fx0, _ = objective(np.arange(B), R, t)
     res.fx = fx0.copy()
+    res.iter_log = []                            # (iteration, live problems, QP rows, QP seconds)
     tstart = time.time()
     for it in range(settings.max_iters):
         idx = np.nonzero(live)[0]
@@ -487,6 +488,7 @@ def optimizeCollFreeBatchFast(obj, env, Tinits, Tdess=None, settings=None, conte
         if qp == 'device':
             dx, qst = ctx.sip_step_qp(Wq, dxdes, offs, rows, dep, lo_q, hi_q, reg=reg, inflation=settings.constraint_inflation)
             res.time_qp_device = getattr(res, 'time_qp_device', 0.0) + time.time() - t0
+            res.qp_admm_iterations = getattr(res, 'qp_admm_iterations', 0) + ctx.last_qp_iters()
             todo = np.nonzero(qst == 3)[0]
             if len(todo):                            # slack re-solve (sip.py:332-357) on the host
                 cn = (offs[1:] - offs[:-1])[todo]
@@ -498,6 +500,7 @@ def optimizeCollFreeBatchFast(obj, env, Tinits, Tdess=None, settings=None, conte
         else:
             dx, _ = _qp.sip_step_batch(Wq, dxdes, offs, rows, dep, lo_q, hi_q, reg=reg, inflation=settings.constraint_inflation)
         res.time_qp += time.time() - t0
+        res.iter_log.append((it, len(idx), int(offs[-1]), time.time() - t0))
         dxn2 = (dx * dx).sum(1)
         conv = dxn2 < xeps2
         status[idx[conv]] = True

@@ -110,6 +110,7 @@ struct sio_ctx {
     std::vector<RobotH> robots;
     // scratch
     DevBuf s_lb, s_ub, s_items, s_icnt;
+    int64_t qp_iters_total = 0;      // ADMM iterations of the last sio_sip_step_qp call, summed over problems
     DevBuf s_qp;                     // per-warp polish scratch + work counter of the SIP-step QP kernel
     HostBuf h_icnt;
     int n_icnt = 0;                   // batches of the last pruned call (their survivor counts sit in h_icnt)
@@ -736,7 +737,7 @@ int sio_sip_step_qp(sio_ctx* c, int32_t n, int64_t nprob, const double* W, const
     if (launch_sip_qp(n, nprob, reinterpret_cast<double*>(d + oW), reinterpret_cast<double*>(d + oX),
                       xmin ? reinterpret_cast<double*>(d + oLo) : nullptr, xmin ? reinterpret_cast<double*>(d + oHi) : nullptr,
                       reinterpret_cast<int64_t*>(d + oO), reinterpret_cast<double*>(d + oR), reinterpret_cast<double*>(d + oD), reg,
-                      inflation, eps_abs, max_iter > 0 ? max_iter : 20000, reinterpret_cast<double*>(o),
+                      inflation, eps_abs, max_iter > 0 ? max_iter : 4000, reinterpret_cast<double*>(o),
                       reinterpret_cast<int32_t*>(o + v), c->s_qp.p, c->num_sms, st))
         return fail(SIO_ERR_INVALID, "sio_sip_step_qp: unsupported n");
     c->launches += 1;
@@ -745,6 +746,8 @@ int sio_sip_step_qp(sio_ctx* c, int32_t n, int64_t nprob, const double* W, const
     CU(cudaStreamSynchronize(st));
     std::memcpy(dx, c->h_b.p, v);
     std::memcpy(status, c->h_b.as<char>() + v, (size_t)nprob * sizeof(int32_t));
+    c->qp_iters_total = 0;
+    for (int64_t i = 0; i < nprob; ++i) { c->qp_iters_total += status[i] >> 8; status[i] &= 0xff; }
     return SIO_OK;
 }
 
@@ -907,6 +910,12 @@ int sio_robot_min_distance(sio_ctx* c, sio_handle robot, const sio_handle* link_
 }
 
 // ---- measurement helpers --------------------------------------------------------------------------------
+int sio_ctx_last_qp_iters(sio_ctx* c, int64_t* iters) {
+    if (!c || !iters) return fail(SIO_ERR_INVALID, "sio_ctx_last_qp_iters: bad argument");
+    *iters = c->qp_iters_total;
+    return SIO_OK;
+}
+
 int sio_ctx_last_prune_stats(sio_ctx* c, int64_t* evaluated, int64_t* total) {
     if (!c || !evaluated || !total) return fail(SIO_ERR_INVALID, "sio_ctx_last_prune_stats: bad argument");
     DeviceGuard guard(c->device);

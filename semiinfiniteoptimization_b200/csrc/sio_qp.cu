@@ -12,7 +12,7 @@
 // Mapping: lane r owns constraint rows r and r+32 (the k instantiated-parameter rows, then the n box rows) and, in
 // the slack problem, the slack variables of its rows; x lives replicated in every lane.  The quadratic term is
 // diagonal and every slack variable sits in exactly one row, so the ADMM linear system reduces (Schur complement
-// over the slack block) to an n x n Cholesky that every lane solves redundantly; A'(rho z - y) is n butterfly
+// over the slack block) to an n x n system whose explicit inverse every lane applies redundantly; A'(rho z - y) is n butterfly
 // reductions; everything else is lane-local.  The polish solves its KKT system (slack unknowns eliminated the same
 // way) with a warp-parallel Gaussian elimination in a per-warp scratch (L2-resident global memory: the ADMM loop
 // itself touches no memory).  Warps are persistent and draw problems from an atomic counter, because the ADMM
@@ -39,14 +39,18 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// Symmetric positive definite N x N system matrix -> its explicit inverse (packed lower triangle, registers).
+// The ADMM loop applies the inverse as N independent dot products: a Cholesky forward/back substitution is a
+// serial dependency chain several times longer, and this kernel is bound by exactly that latency.
 template <int N>
-struct Chol {
-    double L[N * (N + 1) / 2];              // lower triangle, row-major packed
-    double inv[N];                          // 1 / L[i][i]
-    __device__ __forceinline__ double& at(int i, int j) { return L[i * (i + 1) / 2 + j]; }
-    __device__ __forceinline__ bool factor() {
+struct SpdInverse {
+    double A[N * (N + 1) / 2];              // in: lower triangle of the matrix; out: lower triangle of its inverse
+    __device__ __forceinline__ double& at(int i, int j) { return A[i * (i + 1) / 2 + j]; }
+    __device__ __forceinline__ double sym(int i, int j) const { return i >= j ? A[i * (i + 1) / 2 + j] : A[j * (j + 1) / 2 + i]; }
+    __device__ __forceinline__ bool invert() {
+        double inv[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
+        for (int j = 0; j < N; ++j) {                      // Cholesky, in place
             double d = at(j, j);
 #pragma unroll
             for (int k = 0; k < j; ++k) d -= at(j, k) * at(j, k);
@@ -62,23 +66,44 @@ struct Chol {
                 at(i, j) = s * inv[j];
             }
         }
+        double X[N][N];                                    // columns of the inverse: solve L L' X = I
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            double b[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k) s -= at(i, k) * b[k];
+                b[i] = s * inv[i];
+            }
+#pragma unroll
+            for (int i = N - 1; i >= 0; --i) {
+                double s = b[i];
+#pragma unroll
+                for (int k = i + 1; k < N; ++k) s -= at(k, i) * b[k];
+                b[i] = s * inv[i];
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) X[i][c] = b[i];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) at(i, j) = 0.5 * (X[i][j] + X[j][i]);
         return true;
     }
-    __device__ __forceinline__ void solve(double (&b)[N]) {
+    __device__ __forceinline__ void apply(double (&b)[N]) const {
+        double r[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            double s = b[i];
+            double s = 0.0;
 #pragma unroll
-            for (int k = 0; k < i; ++k) s -= at(i, k) * b[k];
-            b[i] = s * inv[i];
+            for (int j = 0; j < N; ++j) s += sym(i, j) * b[j];
+            r[i] = s;
         }
 #pragma unroll
-        for (int i = N - 1; i >= 0; --i) {
-            double s = b[i];
-#pragma unroll
-            for (int k = i + 1; k < N; ++k) s -= at(k, i) * b[k];
-            b[i] = s * inv[i];
-        }
+        for (int i = 0; i < N; ++i) b[i] = r[i];
     }
 };
 
@@ -135,19 +160,24 @@ enum { kAdmmSolved = 0, kAdmmMaxIter = 1, kAdmmInfeasible = 2 };
 
 // ADMM + polish.  SLACK = false: variables x (N).  SLACK = true: variables [x | one slack per parameter row],
 // the slack block carrying the quadratic weight `pen`.  x (and sv, the lane's slack values) hold the answer.
-template <int N, bool SLACK>
-__device__ int admm(const Rows<N>& R, const double (&Pd)[N], const double (&q)[N], double pen, int k, int m, double eps_abs,
-                    double eps_rel, int max_iter, double* kkt, int lane, double (&x)[N], double (&sv)[2]) {
+// One instantiation serves both (a runtime flag): the unrolled body is large and two copies thrash the
+// instruction cache (ncu r01_qp: 64 % of the stall samples were instruction fetch).
+template <int N>
+__device__ __noinline__ int admm(const bool SLACK, const Rows<N>& R, const double (&Pd)[N], const double (&q)[N], double pen, int k, int m, double eps_abs,
+                    double eps_rel, int max_iter, double* kkt, int lane, double (&x)[N], double (&sv)[2], int& iters) {
     constexpr double kInf = 1e20, sigma = 1e-6, alpha = 1.6;
     constexpr int check_every = 10, adapt_every = 50;
     double z[2] = {0.0, 0.0}, y[2] = {0.0, 0.0}, rv[2], dy[2] = {0.0, 0.0}, Ax[2] = {0.0, 0.0}, ds[2] = {1.0, 1.0};
     double rho = 0.1;
-    Chol<N> K;
+    SpdInverse<N> K;
+    double irv[2] = {1.0, 1.0}, ids[2] = {1.0, 1.0};          // reciprocals: no float64 divisions inside the loop
     auto set_rho = [&]() {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             rv[s] = (R.u[s] - R.l[s] < 1e-12) ? 1e3 * rho : rho;
             ds[s] = pen + sigma + rv[s];                  // diagonal of the slack block of the system matrix
+            irv[s] = 1.0 / rv[s];
+            ids[s] = 1.0 / ds[s];
         }
 #pragma unroll
         for (int i = 0; i < N; ++i)
@@ -157,13 +187,13 @@ __device__ int admm(const Rows<N>& R, const double (&Pd)[N], const double (&q)[N
 #pragma unroll
                 for (int s = 0; s < 2; ++s)
                     if (R.have[s]) {
-                        const double wgt = (SLACK && R.slack[s]) ? rv[s] - rv[s] * rv[s] / ds[s] : rv[s];   // Schur complement
+                        const double wgt = (SLACK && R.slack[s]) ? rv[s] - rv[s] * rv[s] * ids[s] : rv[s];   // Schur complement
                         v += wgt * R.a[s][i] * R.a[s][j];
                     }
                 v = warp_sum(v);
                 K.at(i, j) = v + ((i == j) ? Pd[i] + sigma : 0.0);
             }
-        return K.factor();
+        return K.invert();
     };
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = 0.0;
@@ -171,6 +201,7 @@ __device__ int admm(const Rows<N>& R, const double (&Pd)[N], const double (&q)[N
     if (!set_rho()) return kAdmmMaxIter;
     int st = kAdmmMaxIter;
     for (int it = 1; it <= max_iter; ++it) {
+        ++iters;
         double xt[N], w[2], stl[2] = {0.0, 0.0};
 #pragma unroll
         for (int s = 0; s < 2; ++s) w[s] = rv[s] * z[s] - y[s];
@@ -180,12 +211,12 @@ __device__ int admm(const Rows<N>& R, const double (&Pd)[N], const double (&q)[N
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 double ws = w[s];
-                if (SLACK && R.slack[s]) ws -= rv[s] * (sigma * sv[s] + w[s]) / ds[s];      // eliminate the slack unknown
+                if (SLACK && R.slack[s]) ws -= rv[s] * (sigma * sv[s] + w[s]) * ids[s];     // eliminate the slack unknown
                 v += R.a[s][i] * ws;                                                       // a = 0 on absent rows
             }
             xt[i] = warp_sum(v) + sigma * x[i] - q[i];
         }
-        K.solve(xt);
+        K.apply(xt);
         double ndy = 0.0;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -194,11 +225,11 @@ __device__ int admm(const Rows<N>& R, const double (&Pd)[N], const double (&q)[N
             for (int i = 0; i < N; ++i) ax += R.a[s][i] * xt[i];
             double zs = ax;
             if (SLACK && R.slack[s]) {
-                stl[s] = (sigma * sv[s] + w[s] - rv[s] * ax) / ds[s];
+                stl[s] = (sigma * sv[s] + w[s] - rv[s] * ax) * ids[s];
                 zs = ax + stl[s];
             }
             const double zr = alpha * zs + (1.0 - alpha) * z[s];
-            const double c = zr + y[s] / rv[s];
+            const double c = zr + y[s] * irv[s];
             const double zn = c < R.l[s] ? R.l[s] : (c > R.u[s] ? R.u[s] : c);
             const double yn = y[s] + rv[s] * (zr - zn);
             dy[s] = R.have[s] ? yn - y[s] : 0.0;
@@ -338,7 +369,7 @@ __device__ int admm(const Rows<N>& R, const double (&Pd)[N], const double (&q)[N
     return kAdmmSolved;
 }
 
-// status codes written per problem
+// status codes written per problem (low byte; the ADMM iteration count sits above it)
 enum { kQpStrict = 0, kQpSlack = 1, kQpNoRows = 2, kQpToHost = 3 };
 
 template <int N>
@@ -395,7 +426,8 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
     bmin = -warp_max(-bmin);
     const double bnorm = nneg ? sqrt(bneg2) : 1.0;
     double x[N], sv[2];
-    int st = admm<N, false>(R, Pd, q, 0.0, k, m, eps_abs, eps_rel, max_iter, kkt, lane, x, sv);
+    int iters = 0;
+    int st = admm<N>(false, R, Pd, q, 0.0, k, m, eps_abs, eps_rel, max_iter, kkt, lane, x, sv, iters);
     double xn = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) xn += x[i] * x[i];
@@ -403,13 +435,13 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
     if (st == kAdmmInfeasible || sqrt(xn) * reg > bnorm) {
         // the reference's slack re-solve (sip.py:332-357), slack_penalty = 'auto'
         const double pen = (1.0 + nneg) / (fabs(bmin) + 1e-3);
-        st = admm<N, true>(R, Pd, q, pen, k, m, eps_abs, eps_rel, max_iter, kkt, lane, x, sv);
+        st = admm<N>(true, R, Pd, q, pen, k, m, eps_abs, eps_rel, max_iter, kkt, lane, x, sv, iters);
         if (st == kAdmmInfeasible) { if (lane == 0) status[p] = kQpToHost; return; }
         code = kQpSlack;
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) if (lane == i) dx[p * N + i] = x[i];
-    if (lane == 0) status[p] = code;
+    if (lane == 0) status[p] = code | (iters << 8);        // ADMM iterations spent, for diagnostics
 }
 
 // persistent warps: each draws the next problem from *counter (reset to 0 by the launcher)
