@@ -38,15 +38,17 @@ int fail(int code, const char* fmt, ...) {
                         cudaGetErrorString(e_), __FILE__, __LINE__);                               \
     } while (0)
 
-// grow-only device / pinned-host buffers
+// grow-only device / pinned-host buffers; growth is geometric (a lock-step SIP run asks for a little more
+// every iteration, and cudaFree / cudaMalloc / cudaMallocHost each cost a device synchronisation and milliseconds)
+inline size_t grown(size_t bytes, size_t cap) { return std::max(std::max(bytes, (size_t)256), cap + cap / 2); }
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        size_t want = grown(bytes, cap);
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = std::max(bytes, (size_t)256);
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -59,9 +61,9 @@ struct HostBuf {
     size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        size_t want = grown(bytes, cap);
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
-        size_t want = std::max(bytes, (size_t)256);
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -685,21 +687,30 @@ int sio_pose_rows(sio_ctx* c, sio_handle grid, const double* T_pose, const int64
     if (!pts || !d) return fail(SIO_ERR_INVALID, "sio_pose_rows: null pts/d");
     DeviceGuard guard(c->device);
     cudaStream_t st = c->stream;
-    CU(c->s_in0.ensure((size_t)nprob * 12 * sizeof(double)));
-    CU(c->s_in1.ensure((size_t)total * 3 * sizeof(double)));
-    CU(c->s_in2.ensure((size_t)(nprob + 1) * sizeof(int64_t)));
-    CU(c->s_out0.ensure((size_t)total * sizeof(double)));
-    CU(c->s_out1.ensure((size_t)total * 6 * sizeof(double)));
-    CU(cudaMemcpyAsync(c->s_in0.p, T_pose, (size_t)nprob * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->s_in1.p, pts, (size_t)total * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->s_in2.p, offsets, (size_t)(nprob + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    launch_pose_rows(c->grids[grid].d_meta, c->s_in0.as<double>(), c->s_in2.as<int64_t>(), nprob, c->s_in1.as<double>(), total,
-                     (flags & SIO_NO_NORMALIZE) ? 0 : 1, c->s_out0.as<double>(), rows ? c->s_out1.as<double>() : nullptr, st);
+    // one pinned staging block each way: [T_pose | pts | offsets] -> device, [d | rows] <- device
+    const size_t oT = 0, oP = (size_t)nprob * 12 * sizeof(double), oO = oP + (size_t)total * 3 * sizeof(double);
+    const size_t in_bytes = oO + (size_t)(nprob + 1) * sizeof(int64_t);
+    const size_t oD = 0, oR = (size_t)total * sizeof(double), out_bytes = oR + (rows ? (size_t)total * 6 * sizeof(double) : 0);
+    CU(c->h_a.ensure(in_bytes));
+    CU(c->h_b.ensure(out_bytes));
+    CU(c->s_in0.ensure(in_bytes));
+    CU(c->s_out0.ensure(out_bytes));
+    char* h = c->h_a.as<char>();
+    std::memcpy(h + oT, T_pose, oP);
+    std::memcpy(h + oP, pts, (size_t)total * 3 * sizeof(double));
+    std::memcpy(h + oO, offsets, (size_t)(nprob + 1) * sizeof(int64_t));
+    CU(cudaMemcpyAsync(c->s_in0.p, h, in_bytes, cudaMemcpyHostToDevice, st));
+    char* din = c->s_in0.as<char>();
+    char* dout = c->s_out0.as<char>();
+    launch_pose_rows(c->grids[grid].d_meta, reinterpret_cast<double*>(din + oT), reinterpret_cast<int64_t*>(din + oO), nprob,
+                     reinterpret_cast<double*>(din + oP), total, (flags & SIO_NO_NORMALIZE) ? 0 : 1,
+                     reinterpret_cast<double*>(dout + oD), rows ? reinterpret_cast<double*>(dout + oR) : nullptr, st);
     c->launches += 1;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(d, c->s_out0.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (rows) CU(cudaMemcpyAsync(rows, c->s_out1.p, (size_t)total * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_b.p, dout, out_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    std::memcpy(d, c->h_b.as<char>() + oD, (size_t)total * sizeof(double));
+    if (rows) std::memcpy(rows, c->h_b.as<char>() + oR, (size_t)total * 6 * sizeof(double));
     return SIO_OK;
 }
 
