@@ -573,10 +573,11 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
             if (one_batch) { cudaEventRecord(c->ev_bulk1, st); c->bulk_timed = true; }
             c->launches += (p.n > 0);
         }
-        launch_finalize(a, /*all_tiles=*/f64, /*emit_under=*/f64 && want_under, st);
+        // the last batch's launch also carries the CTAs that re-check the float32 pass's under-bound candidates
+        const bool last = b0 + Bc >= B;
+        launch_finalize(a, /*all_tiles=*/f64, /*emit_under=*/f64 && want_under, (!f64 && want_under && last) ? c->num_sms : 0, st);
         c->launches += 1;
     }
-    if (!f64 && want_under) { launch_recheck(a, st); c->launches += 1; }
     CU(cudaGetLastError());
     c->under_pending = want_under;
     c->under_final = f64;

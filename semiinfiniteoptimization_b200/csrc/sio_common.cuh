@@ -93,8 +93,7 @@ struct MinArgs {
 void launch_prep_xf(const MinArgs& a, cudaStream_t st);
 void launch_min_f32(const MinArgs& a, cudaStream_t st);
 void launch_min_pruned(const MinArgs& a, cudaStream_t st);
-void launch_finalize(const MinArgs& a, bool all_tiles, bool emit_under, cudaStream_t st);
-void launch_recheck(const MinArgs& a, cudaStream_t st);
+void launch_finalize(const MinArgs& a, bool all_tiles, bool emit_under, int n_recheck, cudaStream_t st);
 
 void launch_cloud_query_f32(const float4* pts, int64_t N, const XfRec* xf, int64_t B, int normalize,
                             float* out_d, float4* out_g, cudaStream_t st);

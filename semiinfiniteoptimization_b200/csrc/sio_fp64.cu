@@ -2,7 +2,7 @@
 // the arithmetic is the plain IEEE sequence of SURVEY.md Appendix A.2 (no contraction).
 //
 //   k_finalize   exact (d, index) minimum per transform from the fp32 pass's sub-tile minima
-//   k_recheck    exact re-evaluation of the fp32 pass's under-bound candidates
+//                (extra CTAs of the same launch re-evaluate the fp32 pass's under-bound candidates exactly)
 //   k_query_f64  K1 in float64 (PenetrationDepthGeometry.distance / normal, gopt:104-108, 153)
 //   k_pose_rows  K3 pose rows  [ (R(pt-t)) x n , n ]            (gopt:413-418)
 //   k_fk / k_link_rel / k_chain_rows  K4 kinematics + link rows   (gopt:201-204, 479-482)
@@ -74,30 +74,64 @@ __device__ __forceinline__ void grad_to_input(const double* T, const double* gl,
     g[0] = gx; g[1] = gy; g[2] = gz;
 }
 
-// ---- finalize: one CTA (128 threads) per transform ------------------------------------------------
-constexpr int kFinThreads = 128;
+// ---- finalize: one CTA per transform (+ extra CTAs re-checking the under-bound candidates) -------------------
+constexpr int kFinThreads = 512;
 constexpr int kSubPts = 32 * kPtsPerThread;      // points per sub-tile (128)
+constexpr int kFinSubs = kFinThreads / kSubPts;  // sub-tiles evaluated per pass (4)
 constexpr int kMaxList = 512;
 
 __device__ __forceinline__ bool lex_less(double d1, int64_t i1, double d2, int64_t i2) {
     return d1 < d2 || (d1 == d2 && i1 >= 0 && (i2 < 0 || i1 < i2));
 }
 
+// exact re-evaluation of the fp32 pass's under-bound candidates, strided over the `nthreads` threads of the
+// re-check CTAs; kept entries are counted per transform in n_under
+__device__ void recheck_candidates(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int64_t N,
+                                   const GridDev* __restrict__ grids, const int32_t* __restrict__ grid_of_b,
+                                   const double* __restrict__ T_rel, const double* __restrict__ bound,
+                                   Cand* __restrict__ cand, const uint32_t* __restrict__ cand_count, uint32_t cand_cap,
+                                   int32_t* __restrict__ n_under, uint32_t first, uint32_t nthreads) {
+    const uint32_t n = min(*cand_count, cand_cap);
+    for (uint32_t c = first; c < n; c += nthreads) {
+        Cand r = cand[c];
+        if (r.idx >= N) { r.b = -1; cand[c] = r; continue; }        // a padding copy of the last point
+        const GridDev& g = grids[grid_of_b ? grid_of_b[r.b] : 0];
+        float4 q = __ldg(pts + r.idx);
+        double p[3];
+        xf64(T_rel + 12 * (int64_t)r.b, (double)q.x, (double)q.y, (double)q.z, p);
+        double d = eval64(g, p, nullptr);
+        Cand o;
+        o.b = (d < bound[r.b]) ? r.b : -1;
+        o.idx = perm[r.idx];
+        o.d = d;
+        cand[c] = o;
+        if (o.b >= 0 && n_under) atomicAdd(n_under + o.b, 1);
+    }
+}
+
+// blocks [0, Bc): exact (d, index) minimum of transform b_begin + blockIdx.x from the fp32 sub-tile minima;
+// blocks [Bc, Bc + n_recheck): candidate re-check (only launched with the last batch of a float32 call)
 __global__ void __launch_bounds__(kFinThreads)
 k_finalize(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int64_t N,
            const GridDev* __restrict__ grids, const int32_t* __restrict__ grid_of_b,
-           const double* __restrict__ T_rel, const double* __restrict__ bound, double tau, int64_t b_begin,
+           const double* __restrict__ T_rel, const double* __restrict__ bound, double tau, int64_t b_begin, int64_t Bc,
            const uint32_t* __restrict__ subkeys, int64_t nsub, int all_tiles, int emit_under,
            Cand* __restrict__ cand, uint32_t* __restrict__ cand_count, uint32_t cand_cap,
            int32_t* __restrict__ n_under, double* __restrict__ dmin, int64_t* __restrict__ argmin) {
-    __shared__ uint32_t s_key[kFinThreads];
+    const int tid = threadIdx.x;
+    if ((int64_t)blockIdx.x >= Bc) {
+        recheck_candidates(pts, perm, N, grids, grid_of_b, T_rel, bound, cand, cand_count, cand_cap, n_under,
+                           (uint32_t)((blockIdx.x - Bc) * kFinThreads + tid), (uint32_t)((gridDim.x - Bc) * kFinThreads));
+        return;
+    }
+    __shared__ uint32_t s_wkey[kFinThreads / 32];
     __shared__ int32_t s_list[kMaxList];
     __shared__ int32_t s_nlist;
-    __shared__ double s_d[kFinThreads];
-    __shared__ int64_t s_i[kFinThreads];
+    __shared__ double s_d[kFinThreads / 32];
+    __shared__ int64_t s_i[kFinThreads / 32];
     __shared__ GridDev s_g;
     __shared__ double s_T[12];
-    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const int64_t bl = blockIdx.x;                 // batch-local (indexes subkeys)
     const int64_t b = b_begin + bl;                // global (indexes T_rel, bound, outputs)
     if (tid == 0) { s_g = grids[grid_of_b ? grid_of_b[b] : 0]; s_nlist = 0; }
@@ -105,20 +139,20 @@ k_finalize(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int
     __syncthreads();
     bool scan_all = all_tiles != 0;
     if (!scan_all) {
-        // 1) fp32 minimum over the sub-tile keys
+        // 1) fp32 minimum over the sub-tile minima (kept in registers for pass 2)
+        const uint32_t* keys = subkeys + bl * nsub;
         uint32_t k = 0xffffffffu;
-        for (int64_t s = tid; s < nsub; s += kFinThreads) k = min(k, fkey_bits(subkeys[bl * nsub + s]));
-        s_key[tid] = k;
+        for (int64_t s = tid; s < nsub; s += kFinThreads) k = min(k, fkey_bits(__ldg(keys + s)));
+        k = __reduce_min_sync(0xffffffffu, k);
+        if (lane == 0) s_wkey[warp] = k;
         __syncthreads();
-        for (int w = kFinThreads / 2; w > 0; w >>= 1) {
-            if (tid < w) s_key[tid] = min(s_key[tid], s_key[tid + w]);
-            __syncthreads();
-        }
-        const float m32 = fkey_inv(s_key[0]);
-        // 2) sub-tiles that may hold the exact minimum: key <= m32 + tau  (fp32 error << tau)
+        k = s_wkey[lane < kFinThreads / 32 ? lane : 0];
+        k = __reduce_min_sync(0xffffffffu, k);
+        const float m32 = fkey_inv(k);
+        // 2) sub-tiles that may hold the exact minimum: min <= m32 + tau  (fp32 error << tau)
         const uint32_t kthr = fkey(__double2float_ru((double)m32 + tau));
         for (int64_t s = tid; s < nsub; s += kFinThreads) {
-            if (fkey_bits(subkeys[bl * nsub + s]) <= kthr) {
+            if (fkey_bits(__ldg(keys + s)) <= kthr) {
                 int slot = atomicAdd(&s_nlist, 1);
                 if (slot < kMaxList) s_list[slot] = (int32_t)s;
             }
@@ -126,14 +160,16 @@ k_finalize(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int
         __syncthreads();
         if (s_nlist > kMaxList) scan_all = true;     // degenerate (flat field): fall back to every sub-tile
     }
-    // 3) exact evaluation
+    // 3) exact evaluation, kFinSubs sub-tiles per pass
     double best = INFINITY;
     int64_t besti = -1;
     const double bnd = (emit_under && bound) ? bound[b] : -INFINITY;
     const int64_t nloop = scan_all ? nsub : (int64_t)s_nlist;
-    for (int64_t l = 0; l < nloop; ++l) {
+    for (int64_t l0 = 0; l0 < nloop; l0 += kFinSubs) {
+        const int64_t l = l0 + tid / kSubPts;
+        if (l >= nloop) continue;
         const int64_t s = scan_all ? l : (int64_t)s_list[l];
-        const int64_t i = s * kSubPts + tid;
+        const int64_t i = s * kSubPts + (tid % kSubPts);
         if (i < N) {
             float4 q = __ldg(pts + i);
             double p[3];
@@ -148,61 +184,33 @@ k_finalize(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int
             }
         }
     }
-    s_d[tid] = best; s_i[tid] = besti;
-    __syncthreads();
-    for (int w = kFinThreads / 2; w > 0; w >>= 1) {
-        if (tid < w && lex_less(s_d[tid + w], s_i[tid + w], s_d[tid], s_i[tid])) {
-            s_d[tid] = s_d[tid + w]; s_i[tid] = s_i[tid + w];
-        }
-        __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best, o);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (lex_less(od, oi, best, besti)) { best = od; besti = oi; }
     }
+    if (lane == 0) { s_d[warp] = best; s_i[warp] = besti; }
+    __syncthreads();
     if (tid == 0) {
         double dm = s_d[0];
         int64_t am = s_i[0];
+        for (int w = 1; w < kFinThreads / 32; ++w)
+            if (lex_less(s_d[w], s_i[w], dm, am)) { dm = s_d[w]; am = s_i[w]; }
         if (bound && !(dm < bound[b])) am = -1;          // "[]": nothing under Klampt's upperBound
         dmin[b] = dm;
         argmin[b] = am;
     }
 }
 
-void launch_finalize(const MinArgs& a, bool all_tiles, bool emit_under, cudaStream_t st) {
+// n_recheck > 0 appends that many candidate re-check CTAs to the launch (float32 calls that want the under-bound set)
+void launch_finalize(const MinArgs& a, bool all_tiles, bool emit_under, int n_recheck, cudaStream_t st) {
     if (a.Bc <= 0) return;
     int64_t nsub = (int64_t)a.ntiles * (kThreads / 32);
-    k_finalize<<<(unsigned)a.Bc, kFinThreads, 0, st>>>(a.pts, a.perm, a.N, a.grids, a.grid_of_b, a.T_rel, a.bound,
-                                                      a.tau, a.b_begin, a.subkeys, nsub, all_tiles ? 1 : 0, emit_under ? 1 : 0,
-                                                      a.cand, a.cand_count, a.cand_cap, a.n_under, a.dmin, a.argmin);
-}
-
-// ---- exact re-check of the fp32 pass's under-bound candidates ------------------------------------------
-// grid-stride over the candidate records; kept entries are counted per transform in n_under
-__global__ void k_recheck(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int64_t N,
-                          const GridDev* __restrict__ grids, const int32_t* __restrict__ grid_of_b,
-                          const double* __restrict__ T_rel, const double* __restrict__ bound,
-                          Cand* __restrict__ cand, const uint32_t* __restrict__ cand_count, uint32_t cand_cap,
-                          int32_t* __restrict__ n_under) {
-    const uint32_t n = min(*cand_count, cand_cap);
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
-        Cand r = cand[c];
-        if (r.idx >= N) { r.b = -1; cand[c] = r; continue; }        // a padding copy of the last point
-        const GridDev g = grids[grid_of_b ? grid_of_b[r.b] : 0];
-        float4 q = __ldg(pts + r.idx);
-        double p[3];
-        xf64(T_rel + 12 * (int64_t)r.b, (double)q.x, (double)q.y, (double)q.z, p);
-        double d = eval64(g, p, nullptr);
-        Cand o;
-        o.b = (d < bound[r.b]) ? r.b : -1;
-        o.idx = perm[r.idx];
-        o.d = d;
-        cand[c] = o;
-        if (o.b >= 0 && n_under) atomicAdd(n_under + o.b, 1);
-    }
-}
-
-void launch_recheck(const MinArgs& a, cudaStream_t st) {
-    // the count lives on the device: a fixed, SM-sized grid strides over however many there are
-    if (!a.under_bound || a.B <= 0) return;
-    k_recheck<<<148 * 4, 128, 0, st>>>(a.pts, a.perm, a.N, a.grids, a.grid_of_b, a.T_rel, a.bound, a.cand,
-                                       a.cand_count, a.cand_cap, a.n_under);
+    k_finalize<<<(unsigned)(a.Bc + n_recheck), kFinThreads, 0, st>>>(a.pts, a.perm, a.N, a.grids, a.grid_of_b, a.T_rel, a.bound,
+                                                                      a.tau, a.b_begin, a.Bc, a.subkeys, nsub, all_tiles ? 1 : 0,
+                                                                      emit_under ? 1 : 0, a.cand, a.cand_count, a.cand_cap, a.n_under,
+                                                                      a.dmin, a.argmin);
 }
 
 // ---- K1 float64 ---------------------------------------------------------------------------------------
