@@ -442,6 +442,36 @@ def main():
                   "note": "SIO_PRUNE: Lipschitz lower bound per 128-point sub-tile (the GPU analogue of Klampt's bounding-hierarchy "
                           "search inside distance_ext); effective = all (pose, point) pairs resolved / time"}
 
+    # SURVEY.md 8d also asks for the per-point output modes of the same sweep (value-only, value+gradient); these ARE
+    # HBM-bound (4 B / 16 B written per query), so the HBM roofline means something for them
+    modes = None
+    if rank == 0:
+        N_ = CLOUD_N
+        outg = torch.empty((B, N_, 4), dtype=torch.float32, device="cuda")
+        modes = {}
+        peak_hbm = 6650.0
+        try:
+            peak_hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+        except Exception:
+            pass
+        for name, ptrs, wbytes in (("value_only", (outg.data_ptr(), None), 4), ("value_and_gradient", (None, outg.data_ptr()), 16)):
+            ms_m = []
+            for _ in range(13):
+                with torch.cuda.stream(stream):
+                    flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                ctx.cloud_query_dev(g, c, dT.data_ptr(), B, _abi.SIO_F32, *ptrs)
+                e1.record(stream)
+                e1.synchronize()
+                ms_m.append(e0.elapsed_time(e1))
+            t_m = float(np.median(ms_m[3:]))
+            gbs = B * N_ * (wbytes + 16.0 / 32) / (t_m * 1e-3) / 1e9          # written bytes + the cloud read once per 32-pose chunk
+            modes[name] = {"queries_per_s": B * N_ / (t_m * 1e-3), "ms": t_m,
+                           "hbm": {"achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
+                                   "bytes_per_query": wbytes + 0.5}}
+        del outg
+
     sip_rec = None
     if not args.no_sip:
         sip_rec = sip_leg(ctx, rank, world, want_cpu=(world == 1 and not args.no_cpu))
@@ -488,7 +518,7 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
                 "check": {"dmin_first": float(dmin_h[0]), "argmin_first": int(arg_h[0]), "n_under_total": n_under},
-                "pruned": pruned, "sip": sip_rec}
+                "pruned": pruned, "modes": modes, "sip": sip_rec}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(vg, cloud, T_rel)
         print(json.dumps(line))

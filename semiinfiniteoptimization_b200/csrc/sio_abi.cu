@@ -486,7 +486,7 @@ int sio_cloud_query_dev(sio_ctx* c, sio_handle grid, sio_handle cloud, const dou
     a.B = B; a.tau = tau; a.xf = c->s_xf.as<XfRec>();
     launch_prep_xf(a, c->stream);
     const CloudH& p = c->clouds[cloud];
-    launch_cloud_query_f32(p.d_pts, p.n, a.xf, B, (flags & SIO_NO_NORMALIZE) ? 0 : 1, out_g4 ? nullptr : out_d,
+    launch_cloud_query_f32(p.d_pts, p.d_rep, p.n, a.xf, B, (flags & SIO_NO_NORMALIZE) ? 0 : 1, out_g4 ? nullptr : out_d,
                            reinterpret_cast<float4*>(out_g4), c->stream);
     c->launches += 2;
     CU(cudaGetLastError());

@@ -95,7 +95,7 @@ void launch_min_f32(const MinArgs& a, cudaStream_t st);
 void launch_min_pruned(const MinArgs& a, cudaStream_t st);
 void launch_finalize(const MinArgs& a, bool all_tiles, bool emit_under, int n_recheck, cudaStream_t st);
 
-void launch_cloud_query_f32(const float4* pts, int64_t N, const XfRec* xf, int64_t B, int normalize,
+void launch_cloud_query_f32(const float4* pts, const float4* rep, int64_t N, const XfRec* xf, int64_t B, int normalize,
                             float* out_d, float4* out_g, cudaStream_t st);
 void launch_query_f64(const GridDev* grid, const double* T /*12, device*/, const double* pts, int64_t P,
                       int normalize, double* d, double* grad, cudaStream_t st);

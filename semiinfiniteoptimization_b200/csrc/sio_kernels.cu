@@ -463,49 +463,102 @@ void launch_min_pruned(const MinArgs& a, cudaStream_t st) {
 }
 
 // ---- K1 over a resident cloud: per-point outputs ----------------------------------------------------
-// one thread per point, loops over transforms; out_d[b*N + i], out_g[b*N + i] = (gx,gy,gz,d)
+// out_d[b*N + i] = d, or out_g[b*N + i] = (gx, gy, gz, d); i = internal (Morton) index.
+// Same decomposition as the K2 bulk pass: a warp holds 128 points (4 per lane), walks the chunk's transforms, and
+// its bounding sphere decides per transform between the unclamped path (value: 7 FMA Horner; gradient: 3 more
+// dot products reusing the Horner partial sums, then M' g and one rsqrt) and the general path.  Stores are
+// streaming (st.global.cs): 4 B or 16 B per query, the kernel's HBM traffic.
+__device__ __forceinline__ float lattice_value_grad(const XfRec& r, const GridK& g, float ux, float uy, float uz, int normalize,
+                                                    float& gx, float& gy, float& gz) {
+    uint32_t bx, by, bz; float fx, fy, fz;
+    split_rz(ux, bx, fx); split_rz(uy, by, fy); split_rz(uz, bz, fz);
+    Cell q = load_cell(g.brick, bx * g.cx + (by * g.cz + (bz + g.nbias)));
+    float a = fmaf(q.c[7], fz, q.c[6]);
+    float b = fmaf(q.c[5], fz, q.c[4]);
+    float c = fmaf(q.c[3], fz, q.c[2]);
+    float d = fmaf(q.c[1], fz, q.c[0]);
+    float gfx = fmaf(a, fy, b);                                               // dv/dfx
+    float val = fmaf(gfx, fx, fmaf(c, fy, d));
+    float gfy = fmaf(a, fx, c);
+    float gfz = fmaf(fmaf(q.c[7], fy, q.c[5]), fx, fmaf(q.c[3], fy, q.c[1]));
+    // strictly inside the lattice: no clamped axis, no bbox term.  g_in = M' gf
+    gx = fmaf(r.m[0], gfx, fmaf(r.m[4], gfy, r.m[8] * gfz));
+    gy = fmaf(r.m[1], gfx, fmaf(r.m[5], gfy, r.m[9] * gfz));
+    gz = fmaf(r.m[2], gfx, fmaf(r.m[6], gfy, r.m[10] * gfz));
+    if (normalize) {
+        float n2 = fmaf(gx, gx, fmaf(gy, gy, gz * gz));
+        if (n2 > 0.0f) { float s = rsqrtf(n2); gx *= s; gy *= s; gz *= s; }
+    }
+    return val;
+}
+
+template <bool kGrad>
 __global__ void __launch_bounds__(kThreads, 4)
-k_cloud_query_f32(const float4* __restrict__ pts, int64_t N, const XfRec* __restrict__ xf, int64_t B,
-                  int normalize, float* __restrict__ out_d, float4* __restrict__ out_g) {
+k_cloud_query_f32(const float4* __restrict__ pts, const float4* __restrict__ rep, int64_t N, int32_t ntiles,
+                  const XfRec* __restrict__ xf, int64_t B, int32_t xfchunk, int normalize, float* __restrict__ out_d,
+                  float4* __restrict__ out_g) {
     __shared__ XfRec sxf[kXfChunk];
-    const int tid = threadIdx.x;
-    const int64_t ntiles = (N + kThreads - 1) / kThreads;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t chunk = blockIdx.x / ntiles;
-    const int64_t tile = blockIdx.x - chunk * ntiles;
-    const int64_t b0 = chunk * kXfChunk;
-    const int nb = (int)min((int64_t)kXfChunk, B - b0);
+    const int32_t tile = (int32_t)(blockIdx.x - chunk * ntiles);
+    const int64_t b0 = chunk * xfchunk;
+    const int nb = (int)min((int64_t)xfchunk, B - b0);
     {
         const uint4* src = reinterpret_cast<const uint4*>(xf + b0);
         uint4* dst = reinterpret_cast<uint4*>(sxf);
         for (int i = tid; i < nb * (int)(sizeof(XfRec) / 16); i += kThreads) dst[i] = src[i];
     }
-    const int64_t i = tile * kThreads + tid;
-    float4 p = __ldg(pts + i);                      // the cloud is padded to a multiple of kTile
+    const int64_t sub = (int64_t)tile * (kThreads / 32) + warp;
+    const int64_t base = sub * (32 * kPtsPerThread);       // the cloud is padded to a multiple of kTile
+    float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
+#pragma unroll
+    for (int j = 0; j < kPtsPerThread; ++j) {
+        float4 p = __ldg(pts + base + j * 32 + lane);
+        px[j] = p.x; py[j] = p.y; pz[j] = p.z;
+    }
+    const float4 sphere = __ldg(rep + sub);
     __syncthreads();
-    if (i >= N) return;
-    if (out_g) {
-        for (int bl = 0; bl < nb; ++bl) {
-            float gx, gy, gz;
-            float d = eval32_grad(sxf[bl], p.x, p.y, p.z, normalize, gx, gy, gz);
-            __stcs(out_g + (b0 + bl) * N + i, make_float4(gx, gy, gz, d));
-        }
-    } else {
-        for (int bl = 0; bl < nb; ++bl) {
-            const XfRec& r = sxf[bl];
-            float ux = fmaf(r.m[0], p.x, fmaf(r.m[1], p.y, fmaf(r.m[2], p.z, r.m[3])));
-            float uy = fmaf(r.m[4], p.x, fmaf(r.m[5], p.y, fmaf(r.m[6], p.z, r.m[7])));
-            float uz = fmaf(r.m[8], p.x, fmaf(r.m[9], p.y, fmaf(r.m[10], p.z, r.m[11])));
-            __stcs(out_d + (b0 + bl) * N + i, clamped_value(grid_of(r), ux, uy, uz));
+    const uint32_t inmask = __ballot_sync(0xffffffffu, lane < nb && sphere_in_lattice(sxf[lane < nb ? lane : 0], sphere));
+    for (int bl = 0; bl < nb; ++bl) {
+        const XfRec& r = sxf[bl];
+        const GridK g = grid_of(r);
+        const bool inside = (inmask >> bl) & 1u;
+        const int64_t row = (b0 + bl) * N;
+#pragma unroll
+        for (int j = 0; j < kPtsPerThread; ++j) {
+            const int64_t i = base + j * 32 + lane;
+            float gx = 0.f, gy = 0.f, gz = 0.f, d;
+            if (kGrad) {
+                if (inside) {
+                    float ux = fmaf(r.m[0], px[j], fmaf(r.m[1], py[j], fmaf(r.m[2], pz[j], r.m[3])));
+                    float uy = fmaf(r.m[4], px[j], fmaf(r.m[5], py[j], fmaf(r.m[6], pz[j], r.m[7])));
+                    float uz = fmaf(r.m[8], px[j], fmaf(r.m[9], py[j], fmaf(r.m[10], pz[j], r.m[11])));
+                    d = lattice_value_grad(r, g, ux, uy, uz, normalize, gx, gy, gz);
+                } else {
+                    d = eval32_grad(r, px[j], py[j], pz[j], normalize, gx, gy, gz);
+                }
+                if (i < N) __stcs(out_g + row + i, make_float4(gx, gy, gz, d));
+            } else {
+                float ux = fmaf(r.m[0], px[j], fmaf(r.m[1], py[j], fmaf(r.m[2], pz[j], r.m[3])));
+                float uy = fmaf(r.m[4], px[j], fmaf(r.m[5], py[j], fmaf(r.m[6], pz[j], r.m[7])));
+                float uz = fmaf(r.m[8], px[j], fmaf(r.m[9], py[j], fmaf(r.m[10], pz[j], r.m[11])));
+                d = inside ? lattice_value(g, ux, uy, uz) : clamped_value(g, ux, uy, uz);
+                if (i < N) __stcs(out_d + row + i, d);
+            }
         }
     }
 }
 
-void launch_cloud_query_f32(const float4* pts, int64_t N, const XfRec* xf, int64_t B, int normalize,
+void launch_cloud_query_f32(const float4* pts, const float4* rep, int64_t N, const XfRec* xf, int64_t B, int normalize,
                             float* out_d, float4* out_g, cudaStream_t st) {
     if (B <= 0 || N <= 0) return;
-    int64_t ntiles = (N + kThreads - 1) / kThreads;
-    int64_t nchunks = (B + kXfChunk - 1) / kXfChunk;
-    k_cloud_query_f32<<<(unsigned)(ntiles * nchunks), kThreads, 0, st>>>(pts, N, xf, B, normalize, out_d, out_g);
+    const int32_t ntiles = (int32_t)((N + kTile - 1) / kTile);
+    const int chunk = min_f32_chunk(B, ntiles);
+    const int64_t nchunks = (B + chunk - 1) / chunk;
+    if (out_g)
+        k_cloud_query_f32<true><<<(unsigned)(ntiles * nchunks), kThreads, 0, st>>>(pts, rep, N, ntiles, xf, B, chunk, normalize, nullptr, out_g);
+    else
+        k_cloud_query_f32<false><<<(unsigned)(ntiles * nchunks), kThreads, 0, st>>>(pts, rep, N, ntiles, xf, B, chunk, normalize, out_d, nullptr);
 }
 
 // ---- K1 for caller-supplied float64 points, float32 arithmetic --------------------------------------
