@@ -61,6 +61,9 @@ int   sio_ctx_destroy(sio_ctx* ctx);
 int   sio_ctx_sync(sio_ctx* ctx);
 void* sio_ctx_stream(sio_ctx* ctx);                 /* the cudaStream_t kernels are launched on */
 int   sio_ctx_set_tau(sio_ctx* ctx, double tau);    /* near-tie window (metres) of the f64 re-check; <=0 -> automatic */
+/* bytes of per-(transform, sub-tile) scratch a K2 call may hold at once; larger sweeps run in batches of transforms
+ * (default 256 MiB; <= 0 restores it).  Results do not depend on it. */
+int   sio_ctx_set_scratch_limit(sio_ctx* ctx, int64_t bytes);
 int   sio_ctx_num_sms(sio_ctx* ctx);
 int64_t sio_ctx_kernel_launches(sio_ctx* ctx);      /* kernels launched by this context so far */
 

@@ -22,7 +22,7 @@ SIO_PRUNE = 0x8
 # every symbol include/sio_abi.h declares (tests check the built library exports each of them)
 ABI_SYMBOLS = (
     "sio_abi_version", "sio_last_error",
-    "sio_ctx_create", "sio_ctx_destroy", "sio_ctx_sync", "sio_ctx_stream", "sio_ctx_set_tau", "sio_ctx_num_sms",
+    "sio_ctx_create", "sio_ctx_destroy", "sio_ctx_sync", "sio_ctx_stream", "sio_ctx_set_tau", "sio_ctx_set_scratch_limit", "sio_ctx_num_sms",
     "sio_ctx_kernel_launches",
     "sio_grid_create", "sio_grid_destroy", "sio_cloud_create", "sio_cloud_destroy", "sio_cloud_size",
     "sio_query", "sio_cloud_query_dev", "sio_cloud_perm",
@@ -59,6 +59,7 @@ def load_library():
     L.sio_ctx_stream.argtypes = [P]
     L.sio_ctx_stream.restype = P
     L.sio_ctx_set_tau.argtypes = [P, D]
+    L.sio_ctx_set_scratch_limit.argtypes = [P, I64]
     L.sio_ctx_num_sms.argtypes = [P]
     L.sio_ctx_kernel_launches.argtypes = [P]
     L.sio_ctx_kernel_launches.restype = I64
@@ -134,6 +135,9 @@ class Context:
 
     def set_tau(self, tau):
         self._ck(self.L.sio_ctx_set_tau(self.h, float(tau)))
+
+    def set_scratch_limit(self, nbytes):
+        self._ck(self.L.sio_ctx_set_scratch_limit(self.h, int(nbytes)))
 
     @property
     def num_sms(self):

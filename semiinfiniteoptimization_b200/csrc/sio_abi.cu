@@ -112,6 +112,7 @@ struct sio_ctx {
     std::vector<RobotH> robots;
     // scratch
     DevBuf s_lb, s_ub, s_items, s_icnt;
+    int64_t scratch_limit = (int64_t)(256u << 20);   // bytes of sub-tile minima kept per K2 batch (sio_ctx_set_scratch_limit)
     int64_t qp_iters_total = 0;      // ADMM iterations of the last sio_sip_step_qp call, summed over problems
     DevBuf s_qp;                     // per-warp polish scratch + work counter of the SIP-step QP kernel
     HostBuf h_icnt;
@@ -224,6 +225,11 @@ int sio_ctx_sync(sio_ctx* c) {
 }
 void* sio_ctx_stream(sio_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int sio_ctx_set_tau(sio_ctx* c, double tau) { if (!c) return fail(SIO_ERR_INVALID, "null context"); c->tau = tau; return SIO_OK; }
+int sio_ctx_set_scratch_limit(sio_ctx* c, int64_t bytes) {
+    if (!c) return fail(SIO_ERR_INVALID, "null context");
+    c->scratch_limit = bytes > 0 ? bytes : (int64_t)(256u << 20);
+    return SIO_OK;
+}
 int sio_ctx_num_sms(sio_ctx* c) { return c ? c->num_sms : 0; }
 int64_t sio_ctx_kernel_launches(sio_ctx* c) { return c ? c->launches : 0; }
 
@@ -514,7 +520,7 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
     // bound the sub-tile key scratch to ~256 MB by sweeping the transforms in batches
     int64_t Bc = B;
     if (!f64 && nsub > 0) {
-        int64_t maxb = (int64_t)(256u << 20) / (nsub * 4);
+        int64_t maxb = c->scratch_limit / (nsub * 4);
         maxb = std::max<int64_t>(kXfChunk, (maxb / kXfChunk) * kXfChunk);
         Bc = std::min(B, maxb);
     }

@@ -238,3 +238,109 @@ def test_pruned_multi_grid(ctx, O):
     dmin, arg, _ = ctx.min_distance([p[0] for p in pairs], c, T, grid_of_b=gob, flags=F32 | PRUNE)
     d0, a0 = O.min_distance([p[1] for p in pairs], cloud, T, grid_of_b=gob)
     assert np.array_equal(arg, a0) and np.abs(dmin - d0).max() <= 1e-12
+
+
+# ---- batching of large sweeps, degenerate shapes ------------------------------------------------------------
+@pytest.mark.parametrize("flags", [F32, F32 | PRUNE])
+def test_transform_batching_does_not_change_results(ctx, O, flags):
+    """A sweep whose sub-tile scratch exceeds the context's limit runs in batches of transforms (the 65,536-pose C5 sweep
+    does); force that at a small size and compare with the unbatched call and the oracle."""
+    vg = util.sphere_grid(r=0.5, n=28, half=0.9)
+    g, G = _mk(ctx, O, vg)
+    rng = np.random.default_rng(80)
+    cloud = rng.uniform(-1.2, 1.2, (9000, 3)).astype(np.float32)          # 9 tiles -> 72 sub-tiles
+    c = ctx.cloud_create(cloud)
+    T = util.random_poses(81, 150, rot=0.8, trans=0.5)
+    bound = np.where(np.arange(len(T)) % 4 == 0, np.inf, 0.05)
+    d0, a0, n0 = ctx.min_distance(g, c, T, bound=bound, flags=flags)
+    u0 = ctx.under_fetch()
+    ctx.set_scratch_limit(72 * 4 * 40)                                     # 40 transforms per batch -> 4 batches
+    try:
+        d1, a1, n1 = ctx.min_distance(g, c, T, bound=bound, flags=flags)
+        u1 = ctx.under_fetch()
+    finally:
+        ctx.set_scratch_limit(0)
+    assert np.array_equal(d0, d1) and np.array_equal(a0, a1) and np.array_equal(n0, n1)
+    for x, y in zip(u0, u1):
+        assert np.array_equal(x, y)
+    do, ao = O.min_distance(G, cloud, T, bound=bound)
+    assert np.array_equal(a1, ao) and np.abs(d1 - do).max() <= 1e-12
+    ctx.cloud_destroy(c)
+    ctx.grid_destroy(g)
+
+
+def test_degenerate_shapes(ctx, O):
+    """Zero transforms, a one-cell grid, and a cloud that lies entirely outside the grid's bounding box."""
+    from semiinfiniteoptimization_b200._host.geometry import VolumeGrid
+    rng = np.random.default_rng(90)
+    one = VolumeGrid(np.array([[[0.25]]], dtype=np.float32), [0, 0, 0], [1, 1, 1])
+    g, G = _mk(ctx, O, one)
+    cloud = rng.uniform(-2, 3, (500, 3)).astype(np.float32)
+    c = ctx.cloud_create(cloud)
+    T = util.random_poses(91, 7, rot=1.0, trans=1.0)
+    for flags in (F32, F64, F32 | PRUNE):
+        d, a, _ = ctx.min_distance(g, c, T, flags=flags)
+        do, ao = O.min_distance(G, cloud, T)
+        assert np.array_equal(a, ao) and np.abs(d - do).max() <= 1e-12
+    d, a, n = ctx.min_distance(g, c, np.zeros((0, 12)))
+    assert len(d) == 0 and len(a) == 0
+    dq, gq = ctx.query(g, T[0], cloud[:20].astype(np.float64), flags=F64)
+    d0, g0 = O.query(G, T[0], cloud[:20].astype(np.float64))
+    assert np.abs(dq - d0).max() <= 1e-12 and np.abs(gq - g0).max() <= 1e-9
+    far = (cloud + 50.0).astype(np.float32)                                # everything outside the box
+    cf = ctx.cloud_create(far)
+    vg = util.random_grid(92)
+    g2, G2 = _mk(ctx, O, vg)
+    for flags in (F32, F32 | PRUNE):
+        d, a, _ = ctx.min_distance(g2, cf, T, flags=flags)
+        do, ao = O.min_distance(G2, far, T)
+        assert np.array_equal(a, ao) and np.abs(d - do).max() <= 1e-9      # |d| ~ 80 m: float64 rounding of the transform
+    for h in (c, cf):
+        ctx.cloud_destroy(h)
+    ctx.grid_destroy(g)
+    ctx.grid_destroy(g2)
+
+
+def test_full_size_c2_sweep_equals_oracle(ctx, O):
+    """BASELINE.json configs[1] at full size: 64 poses x 2^20 points, every pose's (dmin, argmin, n_under) against the
+    oracle (float64, all host threads: 67 M queries take well under a second)."""
+    import bench
+    vg, cloud, T_rel, bound = bench.build_workload(0)
+    g, G = _mk(ctx, O, vg)
+    c = ctx.cloud_create(cloud)
+    do, ao = O.min_distance(G, cloud, T_rel, bound=bound)
+    nu_total, ub, ui, ud = O.under(G, cloud, T_rel, bound)
+    for flags in (F32, F32 | PRUNE):
+        d, a, nu = ctx.min_distance(g, c, T_rel, bound=bound, flags=flags)
+        assert np.array_equal(a, ao) and np.abs(d - do).max() <= 1e-12
+        assert nu.sum() == nu_total and np.array_equal(nu, np.bincount(ub, minlength=len(T_rel)))
+        b1, i1, d1 = ctx.under_fetch()
+        order = np.lexsort((ui, ub))
+        assert np.array_equal(b1, ub[order]) and np.array_equal(i1, ui[order]) and np.abs(d1 - ud[order]).max() <= 1e-12
+    ctx.cloud_destroy(c)
+    ctx.grid_destroy(g)
+
+
+def test_full_size_c5_sweep_sampled_against_oracle(ctx, O):
+    """BASELINE.json configs[4] at full size: one minimum-only sweep of 65,536 poses x 262,144 points on the device
+    (two scratch batches), exhaustive and pruned; 96 sampled poses against the oracle, all poses against each other."""
+    from semiinfiniteoptimization_b200 import workloads as W
+    from semiinfiniteoptimization_b200._host import se3
+    from semiinfiniteoptimization_b200._host.geometry import fixture_geometry
+    vg = fixture_geometry("cube").convert("VolumeGrid", 0.05).getVolumeGrid()
+    g, G = _mk(ctx, O, vg)
+    cloud = W.c5_scene_cloud()
+    c = ctx.cloud_create(cloud)
+    T = np.array([se3.to_rowmajor12(se3.inv(P)) for P in W.c5_poses(65536, seed=3)])
+    bound = np.zeros(len(T))
+    d0, a0, _ = ctx.min_distance(g, c, T, bound=bound, flags=F32, want_under=False)
+    d1, a1, _ = ctx.min_distance(g, c, T, bound=bound, flags=F32 | PRUNE, want_under=False)
+    assert np.array_equal(d0, d1) and np.array_equal(a0, a1)
+    ev, tot = ctx.last_prune_stats()
+    assert tot == 65536 * 2048 and ev < 0.2 * tot
+    sel = np.random.default_rng(5).choice(len(T), 96, replace=False)
+    do, ao = O.min_distance(G, cloud, T[sel], bound=bound[sel])
+    assert np.array_equal(a0[sel], ao) and np.abs(d0[sel] - do).max() <= 1e-12
+    assert (a0 >= 0).mean() > 0.5                     # most poses start in collision with the scene
+    ctx.cloud_destroy(c)
+    ctx.grid_destroy(g)
