@@ -79,6 +79,21 @@ def test_c4_trajectory_constraint_and_solution_equal_the_reference(ctx):
         assert list(row.col) == probe["row_cols"] and np.allclose(row.data, probe["row_vals"], atol=1e-9, rtol=0)
         assert (con.minvalue(xa, mv[0] - 1e-6) == []) == probe["pruned_by_bound"]
         con.clearx()
+    # single-link trajectory constraint (gopt:565-675): the dense device sweep covers the reference's k/64 bisection
+    for probe in golden["link_probes"]:
+        lc = mod.RobotLinkTrajectoryCollisionConstraint(robot.link(probe["link"]), con.envs[0], tc)
+        xa = probe["x"]
+        lc.setx(xa)
+        mv = lc.minvalue(xa)
+        assert (mv == []) == probe["empty"]
+        if not probe["empty"]:
+            assert abs(mv[0] - probe["dmin"]) <= 1e-9 and abs(mv[1][0] - probe["param"][0]) <= 1e-12
+            assert np.allclose(mv[1][1:], probe["param"][1:], atol=1e-9, rtol=0)
+            y = tuple(probe["param"])
+            assert abs(lc.value(xa, y) - probe["value_at_param"]) <= 1e-9
+            assert np.abs(np.asarray(lc.df_dx(xa, y)) - np.array(probe["row"])).max() <= 1e-9
+            assert (lc.minvalue(xa, mv[0] - 1e-6) == []) == probe["pruned_by_bound"]
+        lc.clearx()
     st = sip.SemiInfiniteOptimizationSettings()
     st.max_iters, st.minimum_constraint_value = 4, -0.02
     out = mod.optimizeCollFreeTrajectory(tc, traj, env=None, constraints=[con], settings=st, verbose=0)

@@ -110,7 +110,23 @@ def gen_c4():
     st.max_iters, st.minimum_constraint_value = 4, -0.02
     out = _quiet(mod.optimizeCollFreeTrajectory, tc, traj, env=None, constraints=[con], settings=st, verbose=0)
     trace = [[float(v) for q in t.milestones[1:-1] for v in q] for t in out[1]]
-    write("c4_traj.json", {"config": "C4 tx90_geom_test2.xml, chair moved to %s, 67 milestones (65 free), "
+    # a10: single link vs single environment along the trajectory (gopt:565-675)
+    link_probes = []
+    for li in (4, 6):
+        lc = mod.RobotLinkTrajectoryCollisionConstraint(robot.link(li), con.envs[0], tc)
+        for trial in range(2):
+            xa = [float(v) for v in (np.asarray(x) + (rng.normal(0, 0.05, len(x)) if trial else 0))]
+            lc.setx(xa)
+            mv = _quiet(lc.minvalue, xa)
+            rec = {"link": li, "x": xa, "empty": mv == []}
+            if mv != []:
+                y = mv[1]
+                # df_dx right after minvalue: the reference leaves the robot at q(t_min), which is what its df_dx reads
+                rec.update({"dmin": float(mv[0]), "param": _f(y), "row": _f(lc.df_dx(xa, y)), "value_at_param": float(lc.value(xa, y)),
+                            "pruned_by_bound": _quiet(lc.minvalue, xa, mv[0] - 1e-6) == []})
+            link_probes.append(rec)
+            lc.clearx()
+    write("c4_traj.json", {"link_probes": link_probes, "config": "C4 tx90_geom_test2.xml, chair moved to %s, 67 milestones (65 free), "
                                      "RobotTrajectoryCollisionConstraint, max_iters 4" % (scenes.CHAIR_IN_PATH,),
                            "x0": x, "minvalue_probes": probes, "trace": trace, "params": _f(out[3])})
 
