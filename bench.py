@@ -353,21 +353,37 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    # the bulk kernel's own launch time (roofline), from the events the ABI puts around it: a few plain steps
+    bulk_ms = []
+    for _ in range(8):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        step()
+        ctx.sync()
+        bulk_ms.append(ctx.last_bulk_ms())
+    # a step is a fixed launch sequence (2 memsets, bulk, finalize): capture it once into a CUDA graph and replay it,
+    # so that host launch jitter (8 ranks share the box's cores) stays out of the device-side timing
+    graph = torch.cuda.CUDAGraph()
+    launches_per_step = ctx.kernel_launches
+    with torch.cuda.graph(graph, stream=stream):
+        step()
+    launches_per_step = ctx.kernel_launches - launches_per_step
+    with torch.cuda.stream(stream):
+        graph.replay()
+    ctx.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = ctx.kernel_launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    bulk_ms = []
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         with torch.cuda.stream(stream):
             flush.zero_()                       # evict L2 (126 MB) between timed steps
-        ev[k][0].record(stream)
-        step()
-        ev[k][1].record(stream)
-        bulk_ms.append(None)
-        ev[k][1].synchronize()
-        bulk_ms[k] = ctx.last_bulk_ms()
+            ev[k][0].record(stream)
+            graph.replay()
+            ev[k][1].record(stream)
     gather_ms = 0.0
     if world > 1:
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -382,7 +398,7 @@ def main():
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
-    launches = ctx.kernel_launches - launches0
+    launches = launches_per_step * args.steps
     ms_steps = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(ms_steps)) + gather_ms          # K sweeps + the one gather of the interval
     if world > 1:
@@ -514,7 +530,8 @@ def main():
                                   "peak_source": "sio_bench_gather: random 4 B loads over an L2-resident array of the grid's size; the "
                                                  "kernel exceeds it because Morton-ordered queries reuse bricks in L1 (hit rate 54%)"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": total_ms / args.steps, "ms_per_step_median": float(np.median(ms_steps)), "gather_ms": gather_ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
                 "check": {"dmin_first": float(dmin_h[0]), "argmin_first": int(arg_h[0]), "n_under_total": n_under},

@@ -563,7 +563,10 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
         c->prune_total = B * nsub;
     }
     c->bulk_timed = false;
-    const bool one_batch = Bc >= B;
+    // the bulk launch is bracketed by timing events unless the caller is capturing the call into a CUDA graph
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    const bool one_batch = Bc >= B && cap == cudaStreamCaptureStatusNone;
     for (int64_t b0 = 0; b0 < B; b0 += Bc) {
         a.b_begin = b0; a.Bc = std::min(Bc, B - b0);
         if (prune) {
