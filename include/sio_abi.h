@@ -147,6 +147,14 @@ int sio_robot_min_distance(sio_ctx* ctx, sio_handle robot, const sio_handle* lin
                            const int32_t* links, int32_t n_sel, sio_handle cloud, const double T_cloud[12],
                            const double* q, int64_t S, const double* bound /* S*n_sel or NULL */, int flags,
                            double* dmin, int64_t* argmin, int32_t* n_under);
+/* the same for an explicit list of (configuration, link) PAIRS: query p uses configuration q[p] (n values) and link
+ * link_of_pair[p].  This is what the second phase of a Lipschitz-scheduled time sweep issues: only the interior time
+ * samples of the (edge, link) pairs whose lower bound (intervalLipschitzMinimum, gopt:554-563, 761-797) can still
+ * beat the best milestone value are evaluated. */
+int sio_robot_pairs_min_distance(sio_ctx* ctx, sio_handle robot, const sio_handle* link_grids, sio_handle cloud,
+                                 const double T_cloud[12], const double* q, const int32_t* link_of_pair, int64_t P,
+                                 const double* bound /* P or NULL */, int flags, double* dmin, int64_t* argmin,
+                                 int32_t* n_under);
 
 /* ---- measurement helpers (bench.py only) ---------------------------------------------------- */
 /* ---- the QPs of one lock-step SIP iteration ------------------------------------

@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "sio_query", "sio_cloud_query_dev", "sio_cloud_perm",
     "sio_min_distance", "sio_min_distance_dev", "sio_under_fetch",
     "sio_pose_rows", "sio_sip_step_qp",
-    "sio_robot_create", "sio_robot_destroy", "sio_fk", "sio_chain_rows", "sio_robot_min_distance",
+    "sio_robot_create", "sio_robot_destroy", "sio_fk", "sio_chain_rows", "sio_robot_min_distance", "sio_robot_pairs_min_distance",
     "sio_bench_gather", "sio_ctx_last_bulk_ms", "sio_ctx_last_prune_stats", "sio_ctx_last_qp_iters",
 )
 
@@ -82,6 +82,7 @@ def load_library():
     L.sio_fk.argtypes = [P, I32, P, I64, P]
     L.sio_chain_rows.argtypes = [P, I32, P, P, I64, P, P, P, I64, C.c_int, P, P]
     L.sio_robot_min_distance.argtypes = [P, I32, P, P, I32, I32, P, P, I64, P, C.c_int, P, P, P]
+    L.sio_robot_pairs_min_distance.argtypes = [P, I32, P, I32, P, P, P, I64, P, C.c_int, P, P, P]
     L.sio_bench_gather.argtypes = [P, I64, I64, C.c_int, C.POINTER(D)]
     L.sio_ctx_last_bulk_ms.argtypes = [P, C.POINTER(D)]
     L.sio_ctx_last_prune_stats.argtypes = [P, C.POINTER(I64), C.POINTER(I64)]
@@ -304,6 +305,21 @@ class Context:
                                                q.ctypes.data, S, _ptr(bnd), int(flags), dmin.ctypes.data, arg.ctypes.data,
                                                nu.ctypes.data))
         return dmin, arg, nu
+
+    def robot_pairs_min_distance(self, robot, n_links, link_grids, cloud, T_cloud, q, link_of_pair, bound=None, flags=SIO_F32):
+        """(dmin, argmin) of explicit (configuration, link) pairs: q (P, n_links), link_of_pair (P,)."""
+        lg = np.ascontiguousarray(link_grids, dtype=np.int32)
+        q = _f64(q).reshape(-1, n_links)
+        lp = np.ascontiguousarray(link_of_pair, dtype=np.int32)
+        assert len(lp) == len(q)
+        Tc = _f64(T_cloud).reshape(12)
+        bnd = None if bound is None else _f64(np.broadcast_to(bound, (len(q),)))
+        dmin = np.empty(len(q))
+        arg = np.empty(len(q), dtype=np.int64)
+        self._ck(self.L.sio_robot_pairs_min_distance(self.h, robot, lg.ctypes.data, cloud, Tc.ctypes.data, q.ctypes.data,
+                                                     lp.ctypes.data, len(q), _ptr(bnd), int(flags), dmin.ctypes.data,
+                                                     arg.ctypes.data, None))
+        return dmin, arg
 
     def last_bulk_ms(self):
         out = C.c_double(0)

@@ -949,6 +949,63 @@ int sio_ctx_last_prune_stats(sio_ctx* c, int64_t* evaluated, int64_t* total) {
     return SIO_OK;
 }
 
+int sio_robot_pairs_min_distance(sio_ctx* c, sio_handle robot, const sio_handle* link_grids, sio_handle cloud,
+                                 const double T_cloud[12], const double* q, const int32_t* link_of_pair, int64_t P,
+                                 const double* bound, int flags, double* dmin, int64_t* argmin, int32_t* n_under) {
+    if (!c || !robot_ok(c, robot) || !link_grids || !cloud_ok(c, cloud) || !T_cloud || P < 0 ||
+        (P > 0 && (!q || !link_of_pair || !dmin || !argmin)))
+        return fail(SIO_ERR_INVALID, "sio_robot_pairs_min_distance: bad argument");
+    if (P == 0) { c->under.clear(); c->under_valid = true; return SIO_OK; }
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    const RobotH& r = c->robots[robot];
+    // the grids of the links that occur, in link order; slot_of_link maps a link to its position in that list
+    std::vector<int32_t> slot((size_t)r.n, -1);
+    for (int64_t p = 0; p < P; ++p) {
+        const int l = link_of_pair[p];
+        if (l < 0 || l >= r.n) return fail(SIO_ERR_INVALID, "sio_robot_pairs_min_distance: link %d out of range", l);
+        if (!grid_ok(c, link_grids[l])) return fail(SIO_ERR_INVALID, "sio_robot_pairs_min_distance: link %d has no grid", l);
+        slot[l] = 0;
+    }
+    std::vector<sio_handle> sel;
+    for (int l = 0; l < r.n; ++l) if (slot[l] == 0) { slot[l] = (int32_t)sel.size(); sel.push_back(link_grids[l]); }
+    // staging: [q | link_of_pair | slot_of_link | T_cloud | bound]
+    const size_t oQ = 0, oL = (size_t)P * r.n * sizeof(double), oS = oL + (((size_t)P * 4 + 15) / 16) * 16;
+    const size_t oT = oS + (((size_t)r.n * 4 + 15) / 16) * 16, oB = oT + 12 * sizeof(double), in_bytes = oB + (bound ? (size_t)P * 8 : 0);
+    CU(c->h_a.ensure(in_bytes));
+    CU(c->s_in0.ensure(in_bytes));
+    char* h = c->h_a.as<char>();
+    std::memcpy(h + oQ, q, oL);
+    std::memcpy(h + oL, link_of_pair, (size_t)P * 4);
+    std::memcpy(h + oS, slot.data(), (size_t)r.n * 4);
+    std::memcpy(h + oT, T_cloud, 12 * sizeof(double));
+    if (bound) std::memcpy(h + oB, bound, (size_t)P * 8);
+    CU(cudaMemcpyAsync(c->s_in0.p, h, in_bytes, cudaMemcpyHostToDevice, st));
+    char* d = c->s_in0.as<char>();
+    CU(c->s_tlinks.ensure((size_t)P * r.n * 12 * sizeof(double)));
+    launch_fk(r.dev(), reinterpret_cast<double*>(d + oQ), P, c->s_tlinks.as<double>(), st);
+    CU(c->s_trel.ensure((size_t)P * 12 * sizeof(double)));
+    CU(c->s_gob.ensure((size_t)P * sizeof(int32_t)));
+    launch_pair_rel(c->s_tlinks.as<double>(), r.n, reinterpret_cast<int32_t*>(d + oL), reinterpret_cast<int32_t*>(d + oS), P,
+                    reinterpret_cast<double*>(d + oT), c->s_trel.as<double>(), c->s_gob.as<int32_t>(), st);
+    c->launches += 2;
+    const size_t oD = 0, oA = (size_t)P * 8, oN = oA + (size_t)P * 8, out_bytes = oN + (size_t)P * 4;
+    CU(c->s_out0.ensure(out_bytes));
+    CU(c->h_b.ensure(out_bytes));
+    char* o = c->s_out0.as<char>();
+    int rc = sio_min_distance_dev(c, sel.data(), (int32_t)sel.size(), c->s_gob.as<int32_t>(), cloud, c->s_trel.as<double>(),
+                                  bound ? reinterpret_cast<double*>(d + oB) : nullptr, P, flags, reinterpret_cast<double*>(o + oD),
+                                  reinterpret_cast<int64_t*>(o + oA), n_under ? reinterpret_cast<int32_t*>(o + oN) : nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_b.p, o, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const char* ho = c->h_b.as<char>();
+    std::memcpy(dmin, ho + oD, (size_t)P * 8);
+    std::memcpy(argmin, ho + oA, (size_t)P * 8);
+    if (n_under) { if (bound) std::memcpy(n_under, ho + oN, (size_t)P * 4); else std::memset(n_under, 0, (size_t)P * 4); }
+    return SIO_OK;
+}
+
 int sio_ctx_last_bulk_ms(sio_ctx* c, double* ms) {
     if (!c || !ms) return fail(SIO_ERR_INVALID, "sio_ctx_last_bulk_ms: bad argument");
     if (!c->bulk_timed) return fail(SIO_ERR_INVALID, "sio_ctx_last_bulk_ms: the last call had no single-batch fp32 bulk launch");

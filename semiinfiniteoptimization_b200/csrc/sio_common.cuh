@@ -113,6 +113,8 @@ void launch_fk(RobotDev r, const double* q, int64_t B, double* T_out, cudaStream
 // T_rel[(s*n_sel + l)] = T_link(s, links[l])^-1 * T_cloud ; grid_of_b[(s*n_sel+l)] = l
 void launch_link_rel(const double* T_links, int32_t n_links, const int32_t* links, int32_t n_sel, int64_t S,
                      const double* T_cloud, double* T_rel, int32_t* grid_of_b, cudaStream_t st);
+void launch_pair_rel(const double* T_links, int32_t n_links, const int32_t* link_of_pair, const int32_t* slot_of_link, int64_t P,
+                     const double* T_cloud, double* T_rel, int32_t* grid_of_b, cudaStream_t st);
 void launch_chain_rows(RobotDev r, const GridDev* grids, const int32_t* link_grid, const double* T_links,
                        const int32_t* cfg_of_pt, const int32_t* link_of_pt, const double* pts, int64_t P,
                        int normalize, double* d, double* rows, cudaStream_t st);

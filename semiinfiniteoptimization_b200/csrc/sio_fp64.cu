@@ -368,6 +368,32 @@ void launch_link_rel(const double* T_links, int32_t n_links, const int32_t* link
                                                                             T_rel, grid_of_b);
 }
 
+// pair p: T_rel[p] = T_link(p, link_of_pair[p])^-1 * T_cloud, grid_of_b[p] = slot_of_link[link_of_pair[p]]
+__global__ void k_pair_rel(const double* __restrict__ T_links, int32_t n_links, const int32_t* __restrict__ link_of_pair,
+                           const int32_t* __restrict__ slot_of_link, int64_t P, const double* __restrict__ T_cloud,
+                           double* __restrict__ T_rel, int32_t* __restrict__ grid_of_b) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int l = link_of_pair[p];
+    const double* T = T_links + (p * n_links + l) * 12;
+    double Tl[12], Ti[12], Tc[12], R[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { Tl[k] = T[k]; Tc[k] = T_cloud[k]; }
+    invert34(Tl, Ti);
+    mul34(Ti, Tc, R);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T_rel[12 * p + k] = R[k];
+    grid_of_b[p] = slot_of_link[l];
+}
+
+void launch_pair_rel(const double* T_links, int32_t n_links, const int32_t* link_of_pair, const int32_t* slot_of_link, int64_t P,
+                     const double* T_cloud, double* T_rel, int32_t* grid_of_b, cudaStream_t st) {
+    if (P <= 0) return;
+    int threads = 128;
+    k_pair_rel<<<(unsigned)((P + threads - 1) / threads), threads, 0, st>>>(T_links, n_links, link_of_pair, slot_of_link, P, T_cloud,
+                                                                            T_rel, grid_of_b);
+}
+
 // value + Jp^T n for points attached to links (gopt:478-482).  One thread per point.
 __global__ void k_chain_rows(RobotDev r, const GridDev* __restrict__ grids, const int32_t* __restrict__ link_grid,
                              const double* __restrict__ T_links, const int32_t* __restrict__ cfg_of_pt,

@@ -55,6 +55,11 @@ POINT_FLAGS = _abi.SIO_F64
 PRUNE_SWEEPS = False        # C4 (8k-point chair cloud, 65 coarse sub-tiles): measured no gain, 2.56 vs 2.35 ms
 
 
+# trajectory sweeps: evaluate interior time samples only where the Lipschitz lower bound of an (edge, link) pair allows a
+# new minimum (the reference's own pruning rule, gopt:761-797); False = every sample of every edge (one device call)
+LIPSCHITZ_SCHEDULE = True
+
+
 def _sweep_flags():
     return BULK_FLAGS | (_abi.SIO_PRUNE if PRUNE_SWEEPS else 0)
 
@@ -652,7 +657,14 @@ class _TrajectorySweepMixin:
     # across ranks; the deepest sample is then agreed on with dist.argmin_allreduce
     shard_time_blocks = False
 
-    def _sweep(self, links, envs, levels):
+    def _sweep(self, links, envs, levels, bound=None):
+        """Deepest (value, link, env index, time, cloud point index) over every milestone and every dyadic interior
+        sample k / 2^levels of every edge, for the given links and environments."""
+        if LIPSCHITZ_SCHEDULE and not self.shard_time_blocks:
+            return self._sweep_scheduled(links, envs, levels, bound)
+        return self._sweep_dense(links, envs, levels)
+
+    def _sweep_dense(self, links, envs, levels):
         from . import dist
         tc = self.trajectory
         kin = tc.kinematics
@@ -679,6 +691,66 @@ class _TrajectorySweepMixin:
         if idx < 0:
             return (dmin, -1, -1, 0.0, -1)
         return (dmin, links[k], j, float(t[s]), idx)
+
+    def _sweep_scheduled(self, links, envs, levels, bound=None):
+        """The same answer with the reference's work reduction (gopt:761-797): milestones first; an (edge, link) pair's
+        interior samples are evaluated only if the Lipschitz lower bound of the distance along that edge
+        (intervalLipschitzMinimum on the two milestone values and the edge's workspace-motion bound) can still beat
+        the best milestone value (and the caller's bound).  Two device calls per environment instead of one."""
+        tc = self.trajectory
+        kin = tc.kinematics
+        ctx = kin.context
+        traj = tc.trajectory
+        ms = np.asarray(traj.milestones, dtype=np.float64)
+        times = np.asarray(traj.times, dtype=np.float64)
+        M, L, nl = len(ms), len(links), tc.robot.numLinks()
+        Kc = 1 << levels
+        us = np.arange(1, Kc) / Kc
+        Kedge = np.asarray(tc.interMilestoneLipschitzBounds, dtype=np.float64)[:, links]          # (M-1, L)
+        best = (float('inf'), -1, -1, -1, -1)                # (value, env, dense sample index, link position, point)
+        queries = 0
+        for j, env in enumerate(envs):
+            N = env._dev.ctx.cloud_size(env._dev.cloud_h)
+            dm, am, _ = ctx.robot_min_distance(kin.robot_h, nl, kin.link_grids, links, env._dev.cloud_h, env._T12, ms,
+                                               flags=_sweep_flags())
+            queries += M * L * N
+            flat = int(np.argmin(dm))
+            s, k = divmod(flat, L)
+            cand = (float(dm[s, k]), j, s, k, int(am[s, k]))
+            if cand[:4] < best[:4]:
+                best = cand
+            thr = best[0] if bound is None else min(best[0], float(bound))
+            a, b = dm[:-1], dm[1:]
+            with np.errstate(divide='ignore', invalid='ignore'):
+                u = (a - b + Kedge) / (2 * Kedge)
+                dlow = np.where((u < 0) | (u > 1), np.minimum(a, b) - 0.5 * Kedge, a - u * Kedge)
+            dlow = np.where(Kedge == 0, np.minimum(a, b), dlow)
+            ei, ki = np.nonzero(dlow < thr)
+            if len(ei) == 0:
+                continue
+            # interior samples of the surviving (edge, link) pairs
+            qp = ms[ei][:, None, :] + us[None, :, None] * (ms[ei + 1] - ms[ei])[:, None, :]           # (P, Kc-1, n)
+            lp = np.repeat(np.asarray(links, dtype=np.int32)[ki], Kc - 1)
+            dp, ap = ctx.robot_pairs_min_distance(kin.robot_h, nl, kin.link_grids, env._dev.cloud_h, env._T12,
+                                                  qp.reshape(-1, nl), lp, flags=_sweep_flags())
+            queries += len(lp) * N
+            dense_idx = (M + ei[:, None] * (Kc - 1) + np.arange(Kc - 1)[None, :]).reshape(-1)        # _dense_time_samples order
+            kk = np.repeat(ki, Kc - 1)
+            order = np.lexsort((kk, dense_idx, dp))                                                   # (value, sample, link)
+            o = int(order[0])
+            cand = (float(dp[o]), j, int(dense_idx[o]), int(kk[o]), int(ap[o]))
+            if cand[:4] < best[:4]:
+                best = cand
+        self.last_sweep_queries = queries
+        dmin, j, s, k, idx = best
+        if idx < 0:
+            return (dmin, -1, -1, 0.0, -1)
+        if s < M:
+            t = float(times[s])
+        else:
+            e, r = divmod(s - M, Kc - 1)
+            t = float(times[e] + us[r] * (times[e + 1] - times[e]))
+        return (dmin, links[k], j, t, idx)
 
     def _world_point(self, env, idx):
         p = env._dev.cloud32[idx].astype(np.float64)
@@ -719,7 +791,7 @@ class RobotLinkTrajectoryCollisionConstraint(SemiInfiniteConstraintInterface, _T
         return self._rows([y[0] for y in ys], [y[1:4] for y in ys], False)[0]
 
     def minvalue(self, x, bound=None):
-        best = self._sweep([self.link.index], [self.env], self.LEVELS)
+        best = self._sweep([self.link.index], [self.env], self.LEVELS, bound)
         dmin, link, envidx, t, idx = best
         if idx < 0 or (bound is not None and dmin >= bound):
             return []
@@ -786,7 +858,7 @@ class RobotTrajectoryCollisionConstraint(SemiInfiniteConstraintInterface, _Traje
         kin = self.trajectory.kinematics
         # the reference walks activeLinks[::-1] (gopt:736); keep that order for tie-breaking
         links = [l for l in self.activeLinks[::-1] if kin.link_grids[l] >= 0]
-        best = self._sweep(links, self.envs, self.LEVELS)
+        best = self._sweep(links, self.envs, self.LEVELS, bound)
         dmin, link, envidx, t, idx = best
         if idx < 0 or (bound is not None and dmin >= bound):
             return []

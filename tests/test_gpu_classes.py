@@ -318,3 +318,31 @@ def test_c4_solutions_match(G, R, c4):
         assert np.allclose(a, b, atol=1e-6)
     assert len(out[0].milestones) == 67
     assert res.gx0[0] < -0.01 and len(res.trace) >= 3          # it really started in collision and moved
+
+
+@pytest.mark.parametrize("chair_pos", [None, CHAIR_IN_PATH])
+def test_lipschitz_scheduled_sweep_equals_dense_sweep(G, R, c4, chair_pos):
+    """Row f2: milestones first, interior samples only for (edge, link) pairs whose Lipschitz lower bound can still win
+    (sio_robot_pairs_min_distance) -- same (dmin, link, env, t, point) as the one-call dense sweep, far fewer queries."""
+    robot, tc, con, traj, x = c4(G, False, chair_pos)
+    rng = np.random.default_rng(3)
+    for trial in range(3):
+        xa = list(np.asarray(x) + (rng.normal(0, 0.05, len(x)) if trial else 0))
+        for levels in (7, 8):
+            con.LEVELS = levels
+            con.setx(xa)
+            G.LIPSCHITZ_SCHEDULE = True
+            a = con.minvalue(xa)
+            qa = con.last_sweep_queries
+            G.LIPSCHITZ_SCHEDULE = False
+            try:
+                b = con.minvalue(xa)
+                qb = con.last_sweep_queries
+            finally:
+                G.LIPSCHITZ_SCHEDULE = True
+            assert a == b, (a, b)
+            assert qa < 0.6 * qb
+            # the caller's bound prunes further and yields [] exactly when the minimum is not below it
+            assert con.minvalue(xa, a[0] - 1e-6) == [] and con.minvalue(xa, a[0] + 1e-6) == a
+            con.clearx()
+    con.LEVELS = 7
