@@ -399,7 +399,8 @@ def optimizeCollFreeBatchFast(obj, env, Tinits, Tdess=None, settings=None, conte
         T = np.empty((len(idx), 3, 4))
         T[:, :, :3] = Rm
         T[:, :, 3] = tm
-        d, rows = ctx.pose_rows(grid_h, T.reshape(-1, 12), offs, P[idx][mask], flags=POINT_FLAGS, want_rows=want_rows)
+        r_, c_ = np.nonzero(mask)                          # problem-major: gather only the live parameters
+        d, rows = ctx.pose_rows(grid_h, T.reshape(-1, 12), offs, P[idx[r_], c_], flags=POINT_FLAGS, want_rows=want_rows)
         return mask, offs, d, rows
 
     def padded(mask, d):

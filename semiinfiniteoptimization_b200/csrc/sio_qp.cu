@@ -426,18 +426,22 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
     bmin = -warp_max(-bmin);
     const double bnorm = nneg ? sqrt(bneg2) : 1.0;
     double x[N], sv[2];
-    int iters = 0;
-    int st = admm<N>(false, R, Pd, q, 0.0, k, m, eps_abs, eps_rel, max_iter, kkt, lane, x, sv, iters);
-    double xn = 0.0;
+    // strict problem first; if it is infeasible or its solution out of scale, the reference's slack re-solve
+    // (sip.py:332-357, slack_penalty = 'auto').  One call site in a loop: the unrolled solver body exists once.
+    int iters = 0, code = kQpStrict;
+    double pen = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int st = admm<N>(pass == 1, R, Pd, q, pen, k, m, eps_abs, eps_rel, max_iter, kkt, lane, x, sv, iters);
+        if (pass == 1) {
+            if (st == kAdmmInfeasible) { if (lane == 0) status[p] = kQpToHost; return; }
+            code = kQpSlack;
+            break;
+        }
+        double xn = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) xn += x[i] * x[i];
-    int code = kQpStrict;
-    if (st == kAdmmInfeasible || sqrt(xn) * reg > bnorm) {
-        // the reference's slack re-solve (sip.py:332-357), slack_penalty = 'auto'
-        const double pen = (1.0 + nneg) / (fabs(bmin) + 1e-3);
-        st = admm<N>(true, R, Pd, q, pen, k, m, eps_abs, eps_rel, max_iter, kkt, lane, x, sv, iters);
-        if (st == kAdmmInfeasible) { if (lane == 0) status[p] = kQpToHost; return; }
-        code = kQpSlack;
+        for (int i = 0; i < N; ++i) xn += x[i] * x[i];
+        if (!(st == kAdmmInfeasible || sqrt(xn) * reg > bnorm)) break;
+        pen = (1.0 + nneg) / (fabs(bmin) + 1e-3);
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) if (lane == i) dx[p * N + i] = x[i];
