@@ -157,6 +157,14 @@ int sio_robot_pairs_min_distance(sio_ctx* ctx, sio_handle robot, const sio_handl
                                  int32_t* n_under);
 
 /* ---- measurement helpers (bench.py only) ---------------------------------------------------- */
+/* ---- geometry preprocessing ------------------------------------------------
+ * replaces: the distance computation inside geom.convert('VolumeGrid', res) -- geometryopt.py:58-66.
+ * out_dist[(i*ny + j)*nz + k] = exact distance from the cell centre bmin + (i+.5, j+.5, k+.5) h to the triangle mesh
+ * (verts [nv*3] float64, tris [nt*3] int32).  The caller applies the inside/outside sign (host, winding number near
+ * the surface only) and narrows to float32; the values equal the host builder's bit for bit. */
+int sio_mesh_distance_grid(sio_ctx* ctx, const double* verts, int32_t nv, const int32_t* tris, int32_t nt,
+                           const double bmin[3], const double h[3], const int32_t dims[3], double* out_dist);
+
 /* ---- the QPs of one lock-step SIP iteration ------------------------------------
  * replaces: ConstraintGenerationData.solve_qp_osqp -> osqp.OSQP().setup/solve -- sip.py:294-331, one
  * call per problem per outer iteration (sip.py:964), here for `nprob` problems at once, one warp each:

@@ -27,7 +27,7 @@ ABI_SYMBOLS = (
     "sio_grid_create", "sio_grid_destroy", "sio_cloud_create", "sio_cloud_destroy", "sio_cloud_size",
     "sio_query", "sio_cloud_query_dev", "sio_cloud_perm",
     "sio_min_distance", "sio_min_distance_dev", "sio_under_fetch",
-    "sio_pose_rows", "sio_sip_step_qp",
+    "sio_pose_rows", "sio_sip_step_qp", "sio_mesh_distance_grid",
     "sio_robot_create", "sio_robot_destroy", "sio_fk", "sio_chain_rows", "sio_robot_min_distance", "sio_robot_pairs_min_distance",
     "sio_bench_gather", "sio_ctx_last_bulk_ms", "sio_ctx_last_prune_stats", "sio_ctx_last_qp_iters",
 )
@@ -77,6 +77,7 @@ def load_library():
     L.sio_under_fetch.argtypes = [P, I64, P, P, P, C.POINTER(I64)]
     L.sio_pose_rows.argtypes = [P, I32, P, P, I64, P, C.c_int, P, P]
     L.sio_sip_step_qp.argtypes = [P, I32, I64, P, P, P, P, P, P, P, D, D, D, I32, P, P]
+    L.sio_mesh_distance_grid.argtypes = [P, P, I32, P, I32, P, P, P, P]
     L.sio_robot_create.argtypes = [P, I32, P, P, P, P, C.POINTER(I32)]
     L.sio_robot_destroy.argtypes = [P, I32]
     L.sio_fk.argtypes = [P, I32, P, I64, P]
@@ -234,6 +235,18 @@ class Context:
         self._ck(self.L.sio_pose_rows(self.h, grid, T.ctypes.data, off.ctypes.data, len(T), p.ctypes.data, int(flags),
                                       d.ctypes.data, _ptr(rows)))
         return d, rows
+
+    # -- geometry preprocessing --
+    def mesh_distance_grid(self, verts, tris, bmin, h, dims):
+        """Unsigned distance from every cell centre to the mesh, float64 (nx, ny, nz)."""
+        V = _f64(verts).reshape(-1, 3)
+        T = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1, 3)
+        b, hh = _f64(bmin).reshape(3), _f64(h).reshape(3)
+        d3 = np.ascontiguousarray(dims, dtype=np.int32).reshape(3)
+        out = np.empty(tuple(int(v) for v in d3))
+        self._ck(self.L.sio_mesh_distance_grid(self.h, V.ctypes.data, len(V), T.ctypes.data, len(T), b.ctypes.data, hh.ctypes.data,
+                                               d3.ctypes.data, out.ctypes.data))
+        return out
 
     # -- SIP-step QPs --
     def sip_step_qp(self, W, xdes, offs, rows, depths, xmin=None, xmax=None, reg=1e-2, inflation=1e-3, eps_abs=1e-5, max_iter=4000):

@@ -120,6 +120,32 @@ int hg_mesh_sdf(const double* verts, int nv, const int32_t* tris, int nt,
     return 0;
 }
 
+/* sign pass alone: `dist` holds the exact unsigned distances of the cell centres (from the device builder,
+ * sio_mesh_distance_grid); the side is decided exactly as in hg_mesh_sdf.  returns 0 on success */
+int hg_sdf_sign_pass(const double* verts, const int32_t* tris, int nt, const double* bmin, const double* h, const int32_t* dims,
+                     const double* dist, float* out) {
+    const v3* V = (const v3*)verts;
+    const int nx = dims[0], ny = dims[1], nz = dims[2];
+#pragma omp parallel for collapse(2) schedule(dynamic, 4)
+    for (int i = 0; i < nx; ++i)
+        for (int j = 0; j < ny; ++j) {
+            double dprev = -1; int sprev = 0;
+            for (int k = 0; k < nz; ++k) {
+                const size_t c = ((size_t)i * ny + j) * nz + k;
+                const double d = dist[c];
+                int sgn;
+                if (dprev >= 0 && (dprev > 1.0001 * h[2] || d > 1.0001 * h[2])) sgn = sprev;
+                else {
+                    v3 p = {bmin[0] + (i + 0.5) * h[0], bmin[1] + (j + 0.5) * h[1], bmin[2] + (k + 0.5) * h[2]};
+                    sgn = (winding(p, V, tris, nt) > 0.5) ? -1 : 1;
+                }
+                out[c] = (float)(sgn * d);
+                dprev = d; sprev = sgn;
+            }
+        }
+    return 0;
+}
+
 /* squared distance + nearest triangle for a list of points (used by tests / surface checks) */
 int hg_points_mesh_dist(const double* verts, const int32_t* tris, int nt, const double* pts, int64_t np_, double* out) {
     const v3* V = (const v3*)verts;

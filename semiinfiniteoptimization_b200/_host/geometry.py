@@ -40,6 +40,9 @@ def _lib():
         lib.hg_mesh_sdf.restype = ctypes.c_int
         lib.hg_mesh_sdf.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.hg_sdf_sign_pass.restype = ctypes.c_int
+        lib.hg_sdf_sign_pass.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         lib.hg_points_mesh_dist.restype = ctypes.c_int
         lib.hg_points_mesh_dist.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
@@ -148,6 +151,16 @@ def sample_mesh_surface(mesh, res):
     return P[np.sort(first)]
 
 
+# optional accelerator for the distance part of mesh_to_sdf: fn(verts, tris, bmin, h, dims) -> float64 (nx,ny,nz)
+# unsigned distances (geometryopt installs the device builder, sio_mesh_distance_grid; values identical to the host's)
+_distance_grid_fn = None
+
+
+def set_distance_grid_builder(fn):
+    global _distance_grid_fn
+    _distance_grid_fn = fn
+
+
 def mesh_to_sdf(mesh, res, pad_cells=SDF_PAD_CELLS):
     lo, hi = mesh.bbox()
     dims = np.maximum(1, np.ceil((hi - lo) / res - 1e-9).astype(np.int64)) + 2 * pad_cells
@@ -157,10 +170,15 @@ def mesh_to_sdf(mesh, res, pad_cells=SDF_PAD_CELLS):
     out = np.empty(tuple(int(d) for d in dims), dtype=np.float32)
     dims32 = np.ascontiguousarray(dims, dtype=np.int32)
     bmin_c = np.ascontiguousarray(bmin)
-    rc = _lib().hg_mesh_sdf(mesh.verts.ctypes.data, len(mesh.verts), mesh.tris.ctypes.data, len(mesh.tris),
-                            bmin_c.ctypes.data, h.ctypes.data, dims32.ctypes.data, out.ctypes.data)
+    if _distance_grid_fn is not None:
+        dist = np.ascontiguousarray(_distance_grid_fn(mesh.verts, mesh.tris, bmin_c, h, dims32), dtype=np.float64)
+        rc = _lib().hg_sdf_sign_pass(mesh.verts.ctypes.data, mesh.tris.ctypes.data, len(mesh.tris), bmin_c.ctypes.data,
+                                     h.ctypes.data, dims32.ctypes.data, dist.ctypes.data, out.ctypes.data)
+    else:
+        rc = _lib().hg_mesh_sdf(mesh.verts.ctypes.data, len(mesh.verts), mesh.tris.ctypes.data, len(mesh.tris),
+                                bmin_c.ctypes.data, h.ctypes.data, dims32.ctypes.data, out.ctypes.data)
     if rc != 0:
-        raise RuntimeError("hg_mesh_sdf failed with status %d" % rc)
+        raise RuntimeError("mesh -> SDF failed with status %d" % rc)
     return VolumeGrid(out, bmin, bmax)
 
 

@@ -25,6 +25,7 @@ CUDA_UNITS = [
     ("sio_kernels.cu", []),
     ("sio_fp64.cu", ["--fmad=false"]),      # plain IEEE float64 sequence, no contraction
     ("sio_qp.cu", ["--fmad=false"]),        # the same float64 sequence as the host solver
+    ("sio_sdf.cu", ["--fmad=false"]),       # identical to hostgeom.c's float64 distances
     ("sio_abi.cu", []),
 ]
 
@@ -70,8 +71,9 @@ def build_hostgeom(force=False):
     src = os.path.join(_PKG, "_host", "csrc", "hostgeom.c")
     out = os.path.join(_LIB, "libsio_hostgeom.so")
     if force or _newer([src], out):
-        # x86-64-v3 (AVX2): the .so is built here and runs on the GPU box's host CPU
-        subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-shared", "-fPIC", src, "-o", out, "-lm"])
+        # x86-64-v3 (AVX2): the .so is built here and runs on the GPU box's host CPU.  -ffp-contract=off: the float64
+        # distances are then the plain IEEE sequence, which the device builder (sio_sdf.cu, --fmad=false) reproduces
+        subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", src, "-o", out, "-lm"])
     return out
 
 

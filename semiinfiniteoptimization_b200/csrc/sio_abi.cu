@@ -724,6 +724,33 @@ int sio_pose_rows(sio_ctx* c, sio_handle grid, const double* T_pose, const int64
     return SIO_OK;
 }
 
+// ---- mesh -> distance grid ----------------------------------------------------------------------------------
+int sio_mesh_distance_grid(sio_ctx* c, const double* verts, int32_t nv, const int32_t* tris, int32_t nt,
+                           const double bmin[3], const double h[3], const int32_t dims[3], double* out_dist) {
+    if (!c || !verts || !tris || !bmin || !h || !dims || !out_dist || nv <= 0 || nt <= 0)
+        return fail(SIO_ERR_INVALID, "sio_mesh_distance_grid: bad argument");
+    const int64_t ncell = (int64_t)dims[0] * dims[1] * dims[2];
+    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || ncell >= (1LL << 31)) return fail(SIO_ERR_INVALID, "sio_mesh_distance_grid: bad dims");
+    std::vector<double> tri((size_t)nt * 9);
+    for (int t = 0; t < nt; ++t)
+        for (int v = 0; v < 3; ++v) {
+            const int32_t idx = tris[3 * t + v];
+            if (idx < 0 || idx >= nv) return fail(SIO_ERR_INVALID, "sio_mesh_distance_grid: triangle %d refers to vertex %d", t, idx);
+            for (int a = 0; a < 3; ++a) tri[(size_t)t * 9 + v * 3 + a] = verts[3 * (size_t)idx + a];
+        }
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    CU(c->s_in0.ensure(tri.size() * sizeof(double)));
+    CU(c->s_out0.ensure((size_t)ncell * sizeof(double)));
+    CU(cudaMemcpyAsync(c->s_in0.p, tri.data(), tri.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_mesh_distance(c->s_in0.as<double>(), nt, bmin, h, dims, c->s_out0.as<double>(), st);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_dist, c->s_out0.p, (size_t)ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SIO_OK;
+}
+
 // ---- SIP-step QPs ----------------------------------------------------------------------------------------
 int sio_sip_step_qp(sio_ctx* c, int32_t n, int64_t nprob, const double* W, const double* xdes, const double* xmin,
                     const double* xmax, const int64_t* offsets, const double* rows, const double* depths, double reg,

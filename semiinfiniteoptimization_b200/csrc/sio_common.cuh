@@ -123,6 +123,9 @@ size_t sip_qp_scratch_bytes(int num_sms);
 int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, const double* xmin, const double* xmax,
                   const int64_t* offs, const double* rows, const double* depths, double reg, double inflation, double eps_abs,
                   int max_iter, double* dx, int32_t* status, void* scratch, int num_sms, cudaStream_t st);
+// mesh -> unsigned distance at every cell centre (sio_sdf.cu); tri = [nt][9] doubles
+void launch_mesh_distance(const double* tri, int32_t nt, const double bmin[3], const double h[3], const int32_t dims[3],
+                          double* out, cudaStream_t st);
 void launch_gather_bench(const float* arr, int64_t n_elems, const uint32_t* idx, int64_t n_gathers,
                          float* sink, cudaStream_t st);
 

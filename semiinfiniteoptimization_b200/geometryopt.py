@@ -34,6 +34,7 @@ import scipy.sparse
 
 from . import _abi
 from ._host import se3, so3, vectorops
+from ._host import geometry as _hostgeometry
 from ._host.geometry import Geometry3D
 from ._host.robot import RigidObjectModel, RobotModel, RobotModelLink
 from ._host.trajectory import RobotTrajectory, Trajectory
@@ -131,6 +132,9 @@ class PenetrationDepthGeometry:
             self._dev = _DeviceGeometry(context or _abi.default_context())
             self._T12 = se3.to_rowmajor12(geom.getCurrentTransform())
             if gridres is not None:
+                # mesh -> SDF: distances on the device (sio_mesh_distance_grid), signs on the host; same grid as the
+                # host-only builder, bit for bit
+                _hostgeometry.set_distance_grid_builder(self._dev.ctx.mesh_distance_grid)
                 try:
                     self.grid = geom.convert('VolumeGrid', gridres)
                 except Exception as e:

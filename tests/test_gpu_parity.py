@@ -344,3 +344,21 @@ def test_full_size_c5_sweep_sampled_against_oracle(ctx, O):
     assert (a0 >= 0).mean() > 0.5                     # most poses start in collision with the scene
     ctx.cloud_destroy(c)
     ctx.grid_destroy(g)
+
+
+# ---- row f3: mesh -> SDF, distances on the device ------------------------------------------------------------------
+@pytest.mark.parametrize("name,res", [("cube", 0.05), ("m797", 0.05), ("m1062", 0.02), ("sphere", 0.1)])
+def test_device_sdf_builder_equals_host_builder(ctx, name, res):
+    """sio_mesh_distance_grid + the host sign pass give the host builder's grid bit for bit (same float64 arithmetic)."""
+    from semiinfiniteoptimization_b200._host import geometry as HG
+    mesh = util.fixture_geometry(name).data
+    HG.set_distance_grid_builder(None)
+    host = HG.mesh_to_sdf(mesh, res)
+    HG.set_distance_grid_builder(ctx.mesh_distance_grid)
+    try:
+        dev = HG.mesh_to_sdf(mesh, res)
+    finally:
+        HG.set_distance_grid_builder(None)
+    assert dev.values.shape == host.values.shape and np.array_equal(dev.bmin, host.bmin)
+    assert np.array_equal(dev.values, host.values)
+    assert (host.values < 0).any() and (host.values > 0).any()
