@@ -447,9 +447,15 @@ def optimizeCollFreeBatchFast(obj, env, Tinits, Tdess=None, settings=None, conte
         _, dxdes = objective(idx, R[idx], t[idx])
         # ---- oracle at x (sip.py:193-276) ---------------------------------------------------
         t0 = time.time()
-        mask, offs, d, _ = values(idx, R[idx], t[idx], False)
-        D = padded(mask, d)
         uo = update_oracle[idx]
+        # the oracle only drops / discovers parameters on iterations 0, 1, 100k (sip.py:855-870): on every other
+        # iteration nothing changes between the values and the rows, so one device call returns both
+        rows = None
+        if uo.any():
+            mask, offs, d, _ = values(idx, R[idx], t[idx], False)
+        else:
+            mask, offs, d, rows = values(idx, R[idx], t[idx], True)
+        D = padded(mask, d)
         drop = mask & (D >= settings.constraint_drop_value) & uo[:, None]
         if drop.any():
             rows_ = np.nonzero(drop.any(1))[0]
@@ -475,7 +481,8 @@ def optimizeCollFreeBatchFast(obj, env, Tinits, Tdess=None, settings=None, conte
                 rr = sel[cond][added]
                 D[rr, slot[added]] = dmin[cond][added]
         update_oracle[idx] = (it % 100 == 0)
-        mask, offs, _, rows = values(idx, R[idx], t[idx], True)
+        if rows is None:
+            mask, offs, _, rows = values(idx, R[idx], t[idx], True)
         res.time_cons += time.time() - t0
         gx = D.min(1)
         if it == 0:
