@@ -362,3 +362,45 @@ def test_device_sdf_builder_equals_host_builder(ctx, name, res):
     assert dev.values.shape == host.values.shape and np.array_equal(dev.bmin, host.bmin)
     assert np.array_equal(dev.values, host.values)
     assert (host.values < 0).any() and (host.values > 0).any()
+
+
+# ---- error behaviour at the boundary (status codes + message, the shim raises) ----------------------
+def test_error_paths(ctx, O):
+    from semiinfiniteoptimization_b200 import _abi
+    vg = util.random_grid(95)
+    g, G = _mk(ctx, O, vg)
+    cloud = np.random.default_rng(96).uniform(-0.5, 1.5, (2000, 3)).astype(np.float32)
+    c = ctx.cloud_create(cloud)
+    T = util.random_poses(97, 4)
+    with pytest.raises(_abi.SioError):
+        ctx.min_distance(999, c, T)                                   # unknown grid handle
+    with pytest.raises(_abi.SioError):
+        ctx.min_distance(g, 999, T)                                   # unknown cloud handle
+    bad = vg.values.copy()
+    bad[1, 2, 3] = np.nan
+    with pytest.raises(_abi.SioError):
+        ctx.grid_create(bad, vg.bmin, vg.bmax)                        # NaN sample
+    with pytest.raises(_abi.SioError):
+        ctx.grid_create(vg.values, vg.bmax, vg.bmin)                  # empty bounding box
+    pts = cloud.copy()
+    pts[5, 1] = np.inf
+    with pytest.raises(_abi.SioError):
+        ctx.cloud_create(pts)                                         # non-finite point
+    with pytest.raises(_abi.SioError):
+        ctx.min_distance([g, g], c, T, grid_of_b=np.array([0, 1, 2, 0], dtype=np.int32))      # grid index out of range
+    # the under-bound list can outgrow the caller's capacity: exact total is still reported through the error
+    d, a, nu = ctx.min_distance(g, c, T, bound=np.full(len(T), 10.0))  # every point is under the bound
+    assert nu.sum() == len(T) * len(cloud)
+    with pytest.raises(_abi.SioError) as e:
+        ctx.under_fetch(capacity=100)
+    assert str(len(T) * len(cloud)) in str(e.value)
+    b, i, dd = ctx.under_fetch(capacity=1 << 16)
+    assert len(b) == len(T) * len(cloud)
+    # a context still works after errors
+    d2, a2, _ = ctx.min_distance(g, c, T)
+    do, ao = O.min_distance(G, cloud, T)
+    assert np.array_equal(a2, ao) and np.abs(d2 - do).max() <= 1e-12
+    ctx.cloud_destroy(c)
+    ctx.grid_destroy(g)
+    with pytest.raises(_abi.SioError):
+        ctx.min_distance(g, c, T)                                     # destroyed handles
