@@ -157,6 +157,33 @@ int sio_robot_pairs_min_distance(sio_ctx* ctx, sio_handle robot, const sio_handl
                                  int32_t* n_under);
 
 /* ---- measurement helpers (bench.py only) ---------------------------------------------------- */
+/* ---- B independent object-pose problems in lock step, entirely on the device --------------------------
+ * replaces: B runs of optimizeCollFree (geometryopt.py:1039-1081) = optimizeSemiInfinite (sip.py:795-1241, default
+ * flags) with one ObjectCollisionConstraint (gopt:394-420) each -- BASELINE.json configs[4].  The moving body owns
+ * `grid`, the environment owns `cloud` (pose T_env = world <- cloud; cloud_world [N*3] = its points in world
+ * coordinates, caller order).  T_init / T_des / T_out are row-major 3x4 poses of the moving body.
+ * Per problem: status (1 = 'local optimum', 0 = iteration limit), iterations, f(x), g(x) = min over instantiated
+ * parameters, g at the start, number of instantiated parameters and (optional) the parameters themselves
+ * [B*cap*3].  stats[0..3] = outer iterations, point queries resolved by the sweeps, QP ADMM iterations, parameters
+ * that did not fit into `cap` slots. */
+typedef struct {
+    int32_t max_iters;                     /* sip.py:65   (50) */
+    int32_t cap;                           /* parameter slots per problem (<= 58: the device QP takes 64 rows) */
+    double xepsilon;                       /* sip.py:66   (1e-4) */
+    double constraint_inflation;           /* sip.py:68   (1e-3) */
+    double constraint_drop_value;          /* sip.py:69   (0.1) */
+    double minimum_constraint_value;       /* sip.py:70   (-inf) */
+    double initial_objective_score_weight; /* sip.py:71   (0.1) */
+    double minimum_objective_score_weight; /* sip.py:73   (1e-5) */
+    double parameter_exclusion_distance;   /* sip.py:74   (1e-3) */
+    double qp_regularization;              /* sip.py:75   (1e-3) */
+    int32_t sweep_flags;                   /* SIO_F32 [| SIO_PRUNE] or SIO_F64 */
+} sio_lockstep_settings;
+int sio_lockstep_pose_solve(sio_ctx* ctx, sio_handle grid, sio_handle cloud, const double T_env[12], const double* cloud_world,
+                            int64_t B, const double* T_init, const double* T_des, const sio_lockstep_settings* settings,
+                            double* T_out, int32_t* status, int32_t* iterations, double* fx, double* gx, double* gx0,
+                            int32_t* n_params, double* params /* B*cap*3 or NULL */, int64_t stats[4]);
+
 /* ---- geometry preprocessing ------------------------------------------------
  * replaces: the distance computation inside geom.convert('VolumeGrid', res) -- geometryopt.py:58-66.
  * out_dist[(i*ny + j)*nz + k] = exact distance from the cell centre bmin + (i+.5, j+.5, k+.5) h to the triangle mesh

@@ -27,7 +27,7 @@ ABI_SYMBOLS = (
     "sio_grid_create", "sio_grid_destroy", "sio_cloud_create", "sio_cloud_destroy", "sio_cloud_size",
     "sio_query", "sio_cloud_query_dev", "sio_cloud_perm",
     "sio_min_distance", "sio_min_distance_dev", "sio_under_fetch",
-    "sio_pose_rows", "sio_sip_step_qp", "sio_mesh_distance_grid",
+    "sio_pose_rows", "sio_sip_step_qp", "sio_mesh_distance_grid", "sio_lockstep_pose_solve",
     "sio_robot_create", "sio_robot_destroy", "sio_fk", "sio_chain_rows", "sio_robot_min_distance", "sio_robot_pairs_min_distance",
     "sio_bench_gather", "sio_ctx_last_bulk_ms", "sio_ctx_last_prune_stats", "sio_ctx_last_qp_iters",
 )
@@ -78,6 +78,7 @@ def load_library():
     L.sio_pose_rows.argtypes = [P, I32, P, P, I64, P, C.c_int, P, P]
     L.sio_sip_step_qp.argtypes = [P, I32, I64, P, P, P, P, P, P, P, D, D, D, I32, P, P]
     L.sio_mesh_distance_grid.argtypes = [P, P, I32, P, I32, P, P, P, P]
+    L.sio_lockstep_pose_solve.argtypes = [P, I32, I32, P, P, I64, P, P, P, P, P, P, P, P, P, P, P, P]
     L.sio_robot_create.argtypes = [P, I32, P, P, P, P, C.POINTER(I32)]
     L.sio_robot_destroy.argtypes = [P, I32]
     L.sio_fk.argtypes = [P, I32, P, I64, P]
@@ -235,6 +236,39 @@ class Context:
         self._ck(self.L.sio_pose_rows(self.h, grid, T.ctypes.data, off.ctypes.data, len(T), p.ctypes.data, int(flags),
                                       d.ctypes.data, _ptr(rows)))
         return d, rows
+
+    # -- lock-step pose solver (device resident) --
+    def lockstep_pose_solve(self, grid, cloud, T_env, cloud_world, T_init, T_des, settings, cap=48, sweep_flags=SIO_F32 | SIO_PRUNE,
+                            want_params=True):
+        """B object-pose SIP problems in lock step on the device (sio_lockstep_pose_solve).  `settings`: a
+        SemiInfiniteOptimizationSettings.  Returns a dict of per-problem arrays and the stats."""
+        class _S(C.Structure):
+            _fields_ = [("max_iters", C.c_int32), ("cap", C.c_int32), ("xepsilon", C.c_double), ("constraint_inflation", C.c_double),
+                        ("constraint_drop_value", C.c_double), ("minimum_constraint_value", C.c_double),
+                        ("initial_objective_score_weight", C.c_double), ("minimum_objective_score_weight", C.c_double),
+                        ("parameter_exclusion_distance", C.c_double), ("qp_regularization", C.c_double), ("sweep_flags", C.c_int32)]
+        Ti = _f64(T_init).reshape(-1, 12)
+        Td = _f64(T_des).reshape(-1, 12)
+        B = len(Ti)
+        assert len(Td) == B
+        cw = _f64(cloud_world).reshape(-1, 3)
+        Te = _f64(T_env).reshape(12)
+        s = _S(int(settings.max_iters), int(cap), float(settings.xepsilon), float(settings.constraint_inflation),
+               float(settings.constraint_drop_value), float(settings.minimum_constraint_value),
+               float(settings.initial_objective_score_weight), float(settings.minimum_objective_score_weight),
+               float(settings.parameter_exclusion_distance), float(settings.qp_solver_params.get('regularizationFactor', 1e-2)),
+               int(sweep_flags))
+        out = {"T": np.empty((B, 12)), "status": np.empty(B, dtype=np.int32), "iterations": np.empty(B, dtype=np.int32),
+               "fx": np.empty(B), "gx": np.empty(B), "gx0": np.empty(B), "n_params": np.empty(B, dtype=np.int32),
+               "params": np.empty((B, cap, 3)) if want_params else None}
+        stats = np.zeros(4, dtype=np.int64)
+        self._ck(self.L.sio_lockstep_pose_solve(self.h, grid, cloud, Te.ctypes.data, cw.ctypes.data, B, Ti.ctypes.data, Td.ctypes.data,
+                                                C.byref(s), out["T"].ctypes.data, out["status"].ctypes.data,
+                                                out["iterations"].ctypes.data, out["fx"].ctypes.data, out["gx"].ctypes.data,
+                                                out["gx0"].ctypes.data, out["n_params"].ctypes.data, _ptr(out["params"]),
+                                                stats.ctypes.data))
+        out["stats"] = {"outer_iterations": int(stats[0]), "point_queries": int(stats[1]), "slot_overflows": int(stats[3])}
+        return out
 
     # -- geometry preprocessing --
     def mesh_distance_grid(self, verts, tris, bmin, h, dims):

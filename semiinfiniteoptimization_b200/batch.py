@@ -565,3 +565,36 @@ def optimizeCollFreeBatchFast(obj, env, Tinits, Tdess=None, settings=None, conte
     res.instantiated_params = [[list(P[p, k]) for k in range(cnt[p])] for p in range(B)]
     res.time = time.time() - tstart
     return res
+
+
+def optimizeCollFreeBatchDevice(obj, env, Tinits, Tdess=None, settings=None, context=None, flags=None, cap=48):
+    """The lock-step algorithm with ALL per-problem state on the device (sio_lockstep_pose_solve, csrc/sio_lockstep.cu):
+    the host sequences kernel launches and reads two counters per outer iteration.  Same iterations per problem as
+    optimizeCollFreeBatchFast (tests compare them); `cap` = parameter slots per problem (parameters beyond it are
+    counted in result.slot_overflows and not instantiated)."""
+    from ._host import se3, so3
+    assert isinstance(obj, PenetrationDepthGeometry) and isinstance(env, PenetrationDepthGeometry)
+    ctx = context or obj.context
+    settings = settings or _sip.SemiInfiniteOptimizationSettings()
+    if flags is None:
+        flags = BULK_FLAGS | _abi.SIO_PRUNE
+    B = len(Tinits)
+    if Tdess is None:
+        Tdess = Tinits
+    Ti = np.array([se3.to_rowmajor12(T) for T in Tinits]).reshape(B, 12)
+    Td = np.array([se3.to_rowmajor12(T) for T in Tdess]).reshape(B, 12)
+    Tenv = env._T12.reshape(3, 4)
+    cloud_world = env._dev.cloud32.astype(np.float64) @ Tenv[:, :3].T + Tenv[:, 3]
+    t0 = time.time()
+    out = ctx.lockstep_pose_solve(obj._dev.grid_h, env._dev.cloud_h, env._T12, cloud_world, Ti, Td, settings, cap=cap, sweep_flags=flags)
+    res = BatchResult(B)
+    res.time = time.time() - t0
+    res.T = out["T"]
+    res.status = ['local optimum' if s == 1 else 'not converged' for s in out["status"]]
+    res.num_iterations = out["iterations"].astype(np.int64)
+    res.fx, res.gx, res.gx0 = out["fx"], out["gx"], out["gx0"]
+    res.instantiated_params = [[list(out["params"][p, k]) for k in range(out["n_params"][p])] for p in range(B)]
+    res.outer_iterations = out["stats"]["outer_iterations"]
+    res.point_queries = out["stats"]["point_queries"]
+    res.slot_overflows = out["stats"]["slot_overflows"]
+    return res

@@ -25,6 +25,7 @@ CUDA_UNITS = [
     ("sio_kernels.cu", []),
     ("sio_fp64.cu", ["--fmad=false"]),      # plain IEEE float64 sequence, no contraction
     ("sio_qp.cu", ["--fmad=false"]),        # the same float64 sequence as the host solver
+    ("sio_lockstep.cu", ["--fmad=false"]),  # the host driver's float64 sequence
     ("sio_sdf.cu", ["--fmad=false"]),       # identical to hostgeom.c's float64 distances
     ("sio_abi.cu", []),
 ]
@@ -49,7 +50,7 @@ def build_cuda(force=False, verbose=False):
     os.makedirs(_LIB, exist_ok=True)
     os.makedirs(_OBJ, exist_ok=True)
     log = []
-    hdrs = [os.path.join(_CSRC, "sio_common.cuh"), os.path.join(_PKG, "..", "include", "sio_abi.h")]
+    hdrs = [os.path.join(_CSRC, "sio_common.cuh"), os.path.join(_CSRC, "sio_eval64.cuh"), os.path.join(_CSRC, "sio_lockstep.cuh"), os.path.join(_PKG, "..", "include", "sio_abi.h")]
     objs = []
     for src, extra in CUDA_UNITS:
         s = os.path.join(_CSRC, src)

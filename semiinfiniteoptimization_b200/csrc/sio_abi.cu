@@ -13,6 +13,7 @@
 
 #include "../../include/sio_abi.h"
 #include "sio_common.cuh"
+#include "sio_lockstep.cuh"
 
 using namespace sio;
 
@@ -724,6 +725,160 @@ int sio_pose_rows(sio_ctx* c, sio_handle grid, const double* T_pose, const int64
     return SIO_OK;
 }
 
+// ---- lock-step pose solver ----------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+// one device allocation carved into the solver's arrays; freed when it goes out of scope
+struct Arena {
+    char* base = nullptr; size_t used = 0, cap = 0;
+    ~Arena() { if (base) cudaFree(base); }
+    template <class T> T* take(size_t n) {
+        used = (used + 255) / 256 * 256;
+        T* p = reinterpret_cast<T*>(base + used);
+        used += n * sizeof(T);
+        return p;
+    }
+};
+template <class F> size_t carve(Arena& A, LsState& S, int64_t B, int cap, F&& extra) {
+    S.R = A.take<double>(9 * B); S.t = A.take<double>(3 * B); S.Rdes = A.take<double>(9 * B); S.tdes = A.take<double>(3 * B);
+    S.P = A.take<double>((size_t)B * cap * 3); S.key = A.take<long long>((size_t)B * cap * 3); S.cnt = A.take<int32_t>(B);
+    S.D = A.take<double>((size_t)B * cap); S.Dn = A.take<double>((size_t)B * cap); S.rows = A.take<double>((size_t)B * cap * 6);
+    S.w = A.take<double>(B); S.trs = A.take<double>(B); S.fx = A.take<double>(B); S.gx = A.take<double>(B);
+    S.gx0 = A.take<double>(B); S.min_cv = A.take<double>(B); S.gxc = A.take<double>(B);
+    S.upd = A.take<uint8_t>(B); S.live = A.take<uint8_t>(B); S.go = A.take<uint8_t>(B);
+    S.status = A.take<int32_t>(B); S.niter = A.take<int32_t>(B); S.ninst0 = A.take<int32_t>(B);
+    S.dxdes = A.take<double>(6 * B); S.dx = A.take<double>(6 * B); S.Rn = A.take<double>(9 * B); S.tn = A.take<double>(3 * B);
+    S.fxn = A.take<double>(B); S.gxn = A.take<double>(B); S.sorig = A.take<double>(B); S.metric = A.take<double>(B);
+    S.qW = A.take<double>(6 * B); S.qlo = A.take<double>(6 * B); S.qhi = A.take<double>(6 * B);
+    S.qk = A.take<int32_t>(B); S.qstatus = A.take<int32_t>(B);
+    S.list = A.take<int32_t>(B); S.counters = A.take<unsigned long long>(8);
+    S.T_rel = A.take<double>(12 * B); S.bound = A.take<double>(B); S.dmin = A.take<double>(B); S.arg = A.take<int64_t>(B);
+    extra();
+    return A.used;
+}
+}  // namespace
+extern "C" {
+
+int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const double T_env[12], const double* cloud_world,
+                            int64_t B, const double* T_init, const double* T_des, const sio_lockstep_settings* cfg,
+                            double* T_out, int32_t* status, int32_t* iterations, double* fx, double* gx, double* gx0,
+                            int32_t* n_params, double* params, int64_t stats[4]) {
+    if (!c || !grid_ok(c, grid) || !cloud_ok(c, cloud) || !T_env || !cloud_world || B < 0 || !cfg ||
+        (B > 0 && (!T_init || !T_des || !T_out)))
+        return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: bad argument");
+    if (cfg->cap < 1 || cfg->cap > 58) return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: cap must be in [1, 58], got %d", cfg->cap);
+    if (B >= (1LL << 31) / 64) return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: too many problems");
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (B == 0) return SIO_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    const int cap = cfg->cap;
+    const int64_t N = c->clouds[cloud].n;
+    LsState S{};
+    S.B = B; S.N = N; S.cap = cap;
+    for (int k = 0; k < 12; ++k) S.Tenv[k] = T_env[k];
+    double* d_cloud = nullptr;
+    Arena A;
+    {   // size pass on a null arena, then the real one
+        Arena probe; LsState tmp{};
+        size_t need = carve(probe, tmp, B, cap, [&] { probe.take<double>((size_t)N * 3); });
+        CU(cudaMalloc(&A.base, need + 4096));
+        A.cap = need + 4096;
+    }
+    carve(A, S, B, cap, [&] { d_cloud = A.take<double>((size_t)N * 3); });
+    S.cloud_world = d_cloud;
+    S.grid = c->grids[grid].d_meta;
+    CU(cudaMemcpyAsync(d_cloud, cloud_world, (size_t)N * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    // poses: row-major 3x4 -> R (3x3) and t
+    {
+        std::vector<double> hR((size_t)B * 9), ht((size_t)B * 3), hRd((size_t)B * 9), htd((size_t)B * 3);
+        for (int64_t p = 0; p < B; ++p)
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) { hR[9 * p + 3 * i + j] = T_init[12 * p + 4 * i + j]; hRd[9 * p + 3 * i + j] = T_des[12 * p + 4 * i + j]; }
+                ht[3 * p + i] = T_init[12 * p + 4 * i + 3]; htd[3 * p + i] = T_des[12 * p + 4 * i + 3];
+            }
+        CU(cudaMemcpyAsync(S.R, hR.data(), hR.size() * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(S.t, ht.data(), ht.size() * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(S.Rdes, hRd.data(), hRd.size() * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(S.tdes, htd.data(), htd.size() * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));                     // the staging vectors die here
+    }
+    LsSettings L{};
+    L.max_iters = cfg->max_iters; L.cap = cap;
+    L.xeps2 = cfg->xepsilon * cfg->xepsilon * 2;           // len((R,t)) == 2 in the reference (sip.py:836-837)     quirk
+    L.inflation = cfg->constraint_inflation; L.drop_value = cfg->constraint_drop_value; L.min_cv = cfg->minimum_constraint_value;
+    L.w0 = cfg->initial_objective_score_weight; L.w_min = cfg->minimum_objective_score_weight;
+    L.excl = cfg->parameter_exclusion_distance; L.reg = cfg->qp_regularization;
+    CU(cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(S.key, 0, (size_t)B * cap * 3 * sizeof(long long), st));
+    ls_launch_init(S, L, st);
+    CU(c->s_qp.ensure(sip_qp_scratch_bytes(c->num_sms)));
+    unsigned long long hc[4];
+    int64_t queries = 0;
+    auto read_counters = [&]() -> cudaError_t {
+        cudaError_t e = cudaMemcpyAsync(hc, S.counters, sizeof(hc), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return e;
+        return cudaStreamSynchronize(st);
+    };
+    auto sweep = [&](int64_t n) -> int {                   // K2 over the queued problems: minimum / arg-minimum only
+        queries += n * N;
+        return sio_min_distance_dev(c, &grid, 1, nullptr, cloud, S.T_rel, S.bound, n, cfg->sweep_flags, S.dmin, S.arg, nullptr);
+    };
+    for (int it = 0; it < cfg->max_iters; ++it) {
+        CU(cudaMemsetAsync(S.counters, 0, 2 * sizeof(unsigned long long), st));
+        ls_launch_begin(S, it, st);
+        const bool maybe_upd = (it == 0) || ((it - 1) % 100 == 0);         // sip.py:855-870
+        if (maybe_upd) {
+            ls_launch_values(S, 0, 0, 1, st);
+            ls_launch_oracle_pre(S, L, st);
+        } else {
+            ls_launch_values(S, 0, 1, 1, st);
+        }
+        CU(read_counters());
+        if (hc[1] == 0) break;                             // no live problem left
+        if (maybe_upd) {
+            const int64_t n = (int64_t)hc[0];
+            if (n > 0) { int rc = sweep(n); if (rc) return rc; }
+            ls_launch_oracle_post(S, L, n, st);
+            ls_launch_values(S, 0, 1, 0, st);              // rows only: the appended depths are the sweeps' exact minima
+        }
+        ls_launch_gx(S, L, it, st);
+        if (launch_sip_qp(6, B, S.qW, S.dxdes, S.qlo, S.qhi, nullptr, S.qk, cap, S.rows, S.D, L.reg, L.inflation, 1e-5, 4000, S.dx,
+                          S.qstatus, c->s_qp.p, c->num_sms, st))
+            return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: QP launch failed");
+        ls_launch_step(S, L, st);
+        ls_launch_values(S, 1, 0, 1, st);
+        CU(cudaMemsetAsync(S.counters, 0, sizeof(unsigned long long), st));
+        ls_launch_score_pre(S, st);
+        CU(read_counters());
+        const int64_t n = (int64_t)hc[0];
+        if (n > 0) { int rc = sweep(n); if (rc) return rc; }
+        ls_launch_score_post(S, L, n, st);
+        c->launches += 8;
+        CU(cudaGetLastError());
+    }
+    CU(read_counters());
+    // results
+    std::vector<double> hR((size_t)B * 9), ht((size_t)B * 3);
+    CU(cudaMemcpyAsync(hR.data(), S.R, hR.size() * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ht.data(), S.t, ht.size() * 8, cudaMemcpyDeviceToHost, st));
+    if (status) CU(cudaMemcpyAsync(status, S.status, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if (iterations) CU(cudaMemcpyAsync(iterations, S.niter, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if (fx) CU(cudaMemcpyAsync(fx, S.fx, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    if (gx) CU(cudaMemcpyAsync(gx, S.gx, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    if (gx0) CU(cudaMemcpyAsync(gx0, S.gx0, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    if (n_params) CU(cudaMemcpyAsync(n_params, S.cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if (params) CU(cudaMemcpyAsync(params, S.P, (size_t)B * cap * 3 * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int64_t p = 0; p < B; ++p)
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) T_out[12 * p + 4 * i + j] = hR[9 * p + 3 * i + j];
+            T_out[12 * p + 4 * i + 3] = ht[3 * p + i];
+        }
+    if (stats) { stats[0] = (int64_t)hc[2]; stats[1] = queries; stats[2] = 0; stats[3] = (int64_t)hc[3]; }
+    return SIO_OK;
+}
+
 // ---- mesh -> distance grid ----------------------------------------------------------------------------------
 int sio_mesh_distance_grid(sio_ctx* c, const double* verts, int32_t nv, const int32_t* tris, int32_t nt,
                            const double bmin[3], const double h[3], const int32_t dims[3], double* out_dist) {
@@ -784,7 +939,7 @@ int sio_sip_step_qp(sio_ctx* c, int32_t n, int64_t nprob, const double* W, const
     char* o = c->s_out0.as<char>();
     if (launch_sip_qp(n, nprob, reinterpret_cast<double*>(d + oW), reinterpret_cast<double*>(d + oX),
                       xmin ? reinterpret_cast<double*>(d + oLo) : nullptr, xmin ? reinterpret_cast<double*>(d + oHi) : nullptr,
-                      reinterpret_cast<int64_t*>(d + oO), reinterpret_cast<double*>(d + oR), reinterpret_cast<double*>(d + oD), reg,
+                      reinterpret_cast<int64_t*>(d + oO), nullptr, 0, reinterpret_cast<double*>(d + oR), reinterpret_cast<double*>(d + oD), reg,
                       inflation, eps_abs, max_iter > 0 ? max_iter : 4000, reinterpret_cast<double*>(o),
                       reinterpret_cast<int32_t*>(o + v), c->s_qp.p, c->num_sms, st))
         return fail(SIO_ERR_INVALID, "sio_sip_step_qp: unsupported n");

@@ -120,9 +120,11 @@ void launch_chain_rows(RobotDev r, const GridDev* grids, const int32_t* link_gri
                        int normalize, double* d, double* rows, cudaStream_t st);
 // the strict QPs of one lock-step SIP iteration, one warp per problem (sio_qp.cu); returns -1 for an unsupported n
 size_t sip_qp_scratch_bytes(int num_sms);
+// rows of problem p: offs[p] .. offs[p+1] (ragged), or -- offs == NULL -- cnt[p] rows at p * stride (cnt[p] < 0: skipped)
 int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, const double* xmin, const double* xmax,
-                  const int64_t* offs, const double* rows, const double* depths, double reg, double inflation, double eps_abs,
-                  int max_iter, double* dx, int32_t* status, void* scratch, int num_sms, cudaStream_t st);
+                  const int64_t* offs, const int32_t* cnt, int32_t stride, const double* rows, const double* depths, double reg,
+                  double inflation, double eps_abs, int max_iter, double* dx, int32_t* status, void* scratch, int num_sms,
+                  cudaStream_t st);
 // mesh -> unsigned distance at every cell centre (sio_sdf.cu); tri = [nt][9] doubles
 void launch_mesh_distance(const double* tri, int32_t nt, const double bmin[3], const double h[3], const int32_t dims[3],
                           double* out, cudaStream_t st);

@@ -374,11 +374,16 @@ enum { kQpStrict = 0, kQpSlack = 1, kQpNoRows = 2, kQpToHost = 3 };
 
 template <int N>
 __device__ void solve_problem(int64_t p, const double* __restrict__ W, const double* __restrict__ xdes, const double* __restrict__ xmin,
-                              const double* __restrict__ xmax, const int64_t* __restrict__ offs, const double* __restrict__ rows,
+                              const double* __restrict__ xmax, const int64_t* __restrict__ offs, const int32_t* __restrict__ cnt,
+                              int32_t stride, const double* __restrict__ rows,
                               const double* __restrict__ depths, double reg, double inflation, double eps_abs, double eps_rel,
                               int max_iter, double* kkt, int lane, double* __restrict__ dx, int32_t* __restrict__ status) {
     constexpr double kInf = 1e20;
-    const int k = (int)(offs[p + 1] - offs[p]);
+    // ragged layout: rows of problem p at offs[p] .. offs[p+1];  padded layout (lock-step solver): cnt[p] rows at
+    // p * stride, cnt[p] < 0 = problem not taking part
+    const int k = offs ? (int)(offs[p + 1] - offs[p]) : cnt[p];
+    const int64_t base = offs ? offs[p] : p * (int64_t)stride;
+    if (k < 0) return;
     const bool box = xmin != nullptr;
     if (k == 0) {                                          // no rows: xdes, box ignored (sip.py:288)
         if (lane < N) dx[p * N + lane] = xdes[p * N + lane];
@@ -406,10 +411,10 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
 #pragma unroll
         for (int i = 0; i < N; ++i) R.a[s][i] = 0.0;
         if (r < k) {
-            const double* src = rows + (offs[p] + r) * N;
+            const double* src = rows + (base + r) * N;
 #pragma unroll
             for (int i = 0; i < N; ++i) R.a[s][i] = src[i];
-            const double b = depths[offs[p] + r];
+            const double b = depths[base + r];
             R.l[s] = -b + inflation;
             if (b < 0) { bneg2 += b * b; ++nneg; }
             bmin = fmin(bmin, b);
@@ -452,7 +457,8 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
 template <int N>
 __global__ void __launch_bounds__(kQpWarps * 32)
 k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__ xdes, const double* __restrict__ xmin,
-         const double* __restrict__ xmax, const int64_t* __restrict__ offs, const double* __restrict__ rows,
+         const double* __restrict__ xmax, const int64_t* __restrict__ offs, const int32_t* __restrict__ cnt, int32_t stride,
+         const double* __restrict__ rows,
          const double* __restrict__ depths, double reg, double inflation, double eps_abs, double eps_rel, int max_iter,
          double* __restrict__ scratch, unsigned long long* __restrict__ counter, double* __restrict__ dx, int32_t* __restrict__ status) {
     const int lane = threadIdx.x & 31;
@@ -462,7 +468,7 @@ k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__
         if (lane == 0) p = atomicAdd(counter, 1ull);
         p = __shfl_sync(0xffffffffu, p, 0);
         if (p >= (unsigned long long)nprob) return;
-        solve_problem<N>((int64_t)p, W, xdes, xmin, xmax, offs, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status);
+        solve_problem<N>((int64_t)p, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status);
     }
 }
 
@@ -471,18 +477,19 @@ size_t sip_qp_scratch_bytes(int num_sms) { return (size_t)sip_qp_grid(num_sms) *
 
 // scratch: sip_qp_scratch_bytes(num_sms) bytes; its last 64 bytes hold the work counter
 int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, const double* xmin, const double* xmax,
-                  const int64_t* offs, const double* rows, const double* depths, double reg, double inflation, double eps_abs,
-                  int max_iter, double* dx, int32_t* status, void* scratch, int num_sms, cudaStream_t st) {
+                  const int64_t* offs, const int32_t* cnt, int32_t stride, const double* rows, const double* depths, double reg,
+                  double inflation, double eps_abs, int max_iter, double* dx, int32_t* status, void* scratch, int num_sms,
+                  cudaStream_t st) {
     if (nprob <= 0) return 0;
     const int blocks = sip_qp_grid(num_sms);
     double* kkt = reinterpret_cast<double*>(scratch);
     unsigned long long* counter = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + sip_qp_scratch_bytes(num_sms) - 64);
     cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
     if (n == 6)
-        k_sip_qp<6><<<blocks, kQpWarps * 32, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, rows, depths, reg, inflation, eps_abs, 1e-5,
+        k_sip_qp<6><<<blocks, kQpWarps * 32, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, 1e-5,
                                                       max_iter, kkt, counter, dx, status);
     else if (n == 7)
-        k_sip_qp<7><<<blocks, kQpWarps * 32, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, rows, depths, reg, inflation, eps_abs, 1e-5,
+        k_sip_qp<7><<<blocks, kQpWarps * 32, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, 1e-5,
                                                       max_iter, kkt, counter, dx, status);
     else
         return -1;

@@ -116,3 +116,22 @@ def test_device_qp_equals_host_qp(ctx):
     dd2, sd2 = ctx.sip_step_qp(W[:200], xdes[:200], offs[:201], rows[:offs[200]], depths[:offs[200]], reg=1e-3)
     ok = (sh2 == 0) & (sd2 == 0)
     assert ok.sum() > 100 and np.abs(dd2[ok] - dh2[ok]).max() <= 1e-8
+
+
+def test_device_resident_driver_equals_array_driver(scene):
+    """sio_lockstep_pose_solve (all per-problem state and bookkeeping on the device) walks every problem through the same
+    iterations as optimizeCollFreeBatchFast and ends at the same poses."""
+    from semiinfiniteoptimization_b200 import batch
+    G, cube, chair = scene
+    poses = c1_poses(96, seed=31)
+    ref = batch.optimizeCollFreeBatchFast(cube, chair, poses)
+    dev = batch.optimizeCollFreeBatchDevice(cube, chair, poses)
+    assert dev.slot_overflows == 0
+    assert np.array_equal(ref.num_iterations, dev.num_iterations) and ref.status == dev.status
+    assert ref.outer_iterations == dev.outer_iterations > 400
+    assert np.abs(ref.T - dev.T).max() <= 1e-6
+    assert np.allclose(ref.gx, dev.gx, atol=1e-6) and np.allclose(ref.fx, dev.fx, atol=1e-6) and np.allclose(ref.gx0, dev.gx0, atol=1e-12)
+    for p in range(len(poses)):
+        assert len(ref.instantiated_params[p]) == len(dev.instantiated_params[p])
+        assert np.allclose(np.array(ref.instantiated_params[p]).reshape(-1), np.array(dev.instantiated_params[p]).reshape(-1), atol=1e-12)
+    assert dev.point_queries == ref.point_queries

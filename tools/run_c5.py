@@ -19,7 +19,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--problems", type=int, default=65536)
 ap.add_argument("--sip-problems", type=int, default=65536)
 ap.add_argument("--max-iters", type=int, default=10)
-ap.add_argument("--qp", default="device", help="device / host: array driver with sio_sip_step_qp / hostqp.c; scalar / batch: per-problem driver")
+ap.add_argument("--qp", default="resident", help="resident: sio_lockstep_pose_solve (everything on the device); device / host: array driver with "
+                "sio_sip_step_qp / hostqp.c; scalar / batch: per-problem driver")
 a = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -71,7 +72,9 @@ if nb == 0:
     sys.exit(0)
 st = sip.SemiInfiniteOptimizationSettings(); st.max_iters = a.max_iters
 t0 = time.time()
-if a.qp in ("device", "host"):
+if a.qp == "resident":
+    res = batch.optimizeCollFreeBatchDevice(cube, scene, mine[:nb], settings=st)
+elif a.qp in ("device", "host"):
     res = batch.optimizeCollFreeBatchFast(cube, scene, mine[:nb], settings=st, qp=a.qp)
 else:
     res = batch.optimizeCollFreeBatch(cube, scene, mine[:nb], settings=st, qp=a.qp)
@@ -87,7 +90,7 @@ if rank == 0:
                   "wall_s": wall, "iters_per_s": float(rec[0].item()) / wall, "oracle_s": float(rec[2].item()) / world,
                   "qp_s": float(rec[3].item()) / world, "point_queries": int(rec[4].item()), "feasible": int(rec[5].item()),
                   "qp_host_fallbacks": getattr(res, "qp_host_fallbacks", 0), "qp_device_s": getattr(res, "time_qp_device", 0.0), "qp_admm_iterations": getattr(res, "qp_admm_iterations", 0),
-                  "max_params": max(len(p) for p in res.instantiated_params), "mean_params": float(np.mean([len(p) for p in res.instantiated_params]))}
+                  "slot_overflows": getattr(res, "slot_overflows", 0), "max_params": max(len(p) for p in res.instantiated_params), "mean_params": float(np.mean([len(p) for p in res.instantiated_params]))}
     print(json.dumps({"config": "C5 synthetic scene %d pts, %d problems, %d GPUs" % (N, a.problems, world), **out}))
 if world > 1:
     dist.destroy_process_group()
