@@ -164,8 +164,8 @@ int sio_robot_pairs_min_distance(sio_ctx* ctx, sio_handle robot, const sio_handl
  * coordinates, caller order).  T_init / T_des / T_out are row-major 3x4 poses of the moving body.
  * Per problem: status (1 = 'local optimum', 0 = iteration limit), iterations, f(x), g(x) = min over instantiated
  * parameters, g at the start, number of instantiated parameters and (optional) the parameters themselves
- * [B*cap*3].  stats[0..3] = outer iterations, point queries resolved by the sweeps, QP ADMM iterations, parameters
- * that did not fit into `cap` slots. */
+ * [B*cap*3].  stats[0..4] = outer iterations, point queries resolved by the sweeps, device microseconds in the QP
+ * launches, parameters that did not fit into `cap` slots, device microseconds in the sweeps. */
 typedef struct {
     int32_t max_iters;                     /* sip.py:65   (50) */
     int32_t cap;                           /* parameter slots per problem (<= 58: the device QP takes 64 rows) */
@@ -182,7 +182,7 @@ typedef struct {
 int sio_lockstep_pose_solve(sio_ctx* ctx, sio_handle grid, sio_handle cloud, const double T_env[12], const double* cloud_world,
                             int64_t B, const double* T_init, const double* T_des, const sio_lockstep_settings* settings,
                             double* T_out, int32_t* status, int32_t* iterations, double* fx, double* gx, double* gx0,
-                            int32_t* n_params, double* params /* B*cap*3 or NULL */, int64_t stats[4]);
+                            int32_t* n_params, double* params /* B*cap*3 or NULL */, int64_t stats[5]);
 
 /* ---- geometry preprocessing ------------------------------------------------
  * replaces: the distance computation inside geom.convert('VolumeGrid', res) -- geometryopt.py:58-66.

@@ -261,13 +261,14 @@ class Context:
         out = {"T": np.empty((B, 12)), "status": np.empty(B, dtype=np.int32), "iterations": np.empty(B, dtype=np.int32),
                "fx": np.empty(B), "gx": np.empty(B), "gx0": np.empty(B), "n_params": np.empty(B, dtype=np.int32),
                "params": np.empty((B, cap, 3)) if want_params else None}
-        stats = np.zeros(4, dtype=np.int64)
+        stats = np.zeros(5, dtype=np.int64)
         self._ck(self.L.sio_lockstep_pose_solve(self.h, grid, cloud, Te.ctypes.data, cw.ctypes.data, B, Ti.ctypes.data, Td.ctypes.data,
                                                 C.byref(s), out["T"].ctypes.data, out["status"].ctypes.data,
                                                 out["iterations"].ctypes.data, out["fx"].ctypes.data, out["gx"].ctypes.data,
                                                 out["gx0"].ctypes.data, out["n_params"].ctypes.data, _ptr(out["params"]),
                                                 stats.ctypes.data))
-        out["stats"] = {"outer_iterations": int(stats[0]), "point_queries": int(stats[1]), "slot_overflows": int(stats[3])}
+        out["stats"] = {"outer_iterations": int(stats[0]), "point_queries": int(stats[1]), "qp_device_s": stats[2] * 1e-6,
+                        "slot_overflows": int(stats[3]), "sweep_device_s": stats[4] * 1e-6}
         return out
 
     # -- geometry preprocessing --

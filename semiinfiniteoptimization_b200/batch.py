@@ -48,13 +48,31 @@ class BatchResult:
         self.fx = np.zeros(B)
         self.gx = np.full(B, np.inf)
         self.gx0 = np.full(B, np.inf)
-        self.instantiated_params = [[] for _ in range(B)]
+        self._params = [[] for _ in range(B)]
+        self._params_arrays = None
         self.trace = None
         self.time = 0.0
         self.time_cons = 0.0
         self.time_qp = 0.0
         self.outer_iterations = 0        # sum over problems of completed outer iterations
         self.point_queries = 0           # (pose, cloud point) pairs evaluated by K2 sweeps
+
+    @property
+    def instantiated_params(self):
+        """Per problem, the list of instantiated world points (built on first use from the device arrays)."""
+        if self._params_arrays is not None:
+            P, n = self._params_arrays
+            self._params = [[list(P[p, k]) for k in range(n[p])] for p in range(len(n))]
+            self._params_arrays = None
+        return self._params
+
+    @instantiated_params.setter
+    def instantiated_params(self, v):
+        self._params, self._params_arrays = v, None
+
+    def set_params_arrays(self, P, n):
+        self._params_arrays = (P, n)
+        self.n_params = np.asarray(n)
 
     def records(self):
         """Fixed-size per-problem records for the end-of-solve gather: pose(12) gx fx iters nparams."""
@@ -64,7 +82,7 @@ class BatchResult:
         rec[:, 12] = self.gx
         rec[:, 13] = self.fx
         rec[:, 14] = self.num_iterations
-        rec[:, 15] = [len(p) for p in self.instantiated_params]
+        rec[:, 15] = self.n_params if self._params_arrays is not None else [len(p) for p in self.instantiated_params]
         return rec
 
 
@@ -581,8 +599,14 @@ def optimizeCollFreeBatchDevice(obj, env, Tinits, Tdess=None, settings=None, con
     B = len(Tinits)
     if Tdess is None:
         Tdess = Tinits
-    Ti = np.array([se3.to_rowmajor12(T) for T in Tinits]).reshape(B, 12)
-    Td = np.array([se3.to_rowmajor12(T) for T in Tdess]).reshape(B, 12)
+    def rowmajor(Ts):            # Klampt se3 (R column-major 9-list, t) -> row-major 3x4, vectorised
+        Rc = np.array([T[0] for T in Ts], dtype=np.float64).reshape(-1, 3, 3)          # [b][col][row]
+        out = np.empty((len(Ts), 3, 4))
+        out[:, :, :3] = np.transpose(Rc, (0, 2, 1))
+        out[:, :, 3] = np.array([T[1] for T in Ts], dtype=np.float64)
+        return out.reshape(-1, 12)
+    Ti = rowmajor(Tinits)
+    Td = Ti if Tdess is Tinits else rowmajor(Tdess)
     Tenv = env._T12.reshape(3, 4)
     cloud_world = env._dev.cloud32.astype(np.float64) @ Tenv[:, :3].T + Tenv[:, 3]
     t0 = time.time()
@@ -593,7 +617,8 @@ def optimizeCollFreeBatchDevice(obj, env, Tinits, Tdess=None, settings=None, con
     res.status = ['local optimum' if s == 1 else 'not converged' for s in out["status"]]
     res.num_iterations = out["iterations"].astype(np.int64)
     res.fx, res.gx, res.gx0 = out["fx"], out["gx"], out["gx0"]
-    res.instantiated_params = [[list(out["params"][p, k]) for k in range(out["n_params"][p])] for p in range(B)]
+    res.set_params_arrays(out["params"], out["n_params"])
+    res.time_qp, res.time_cons = out["stats"]["qp_device_s"], out["stats"]["sweep_device_s"]
     res.outer_iterations = out["stats"]["outer_iterations"]
     res.point_queries = out["stats"]["point_queries"]
     res.slot_overflows = out["stats"]["slot_overflows"]

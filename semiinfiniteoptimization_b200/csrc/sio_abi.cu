@@ -762,13 +762,13 @@ extern "C" {
 int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const double T_env[12], const double* cloud_world,
                             int64_t B, const double* T_init, const double* T_des, const sio_lockstep_settings* cfg,
                             double* T_out, int32_t* status, int32_t* iterations, double* fx, double* gx, double* gx0,
-                            int32_t* n_params, double* params, int64_t stats[4]) {
+                            int32_t* n_params, double* params, int64_t stats[5]) {
     if (!c || !grid_ok(c, grid) || !cloud_ok(c, cloud) || !T_env || !cloud_world || B < 0 || !cfg ||
         (B > 0 && (!T_init || !T_des || !T_out)))
         return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: bad argument");
     if (cfg->cap < 1 || cfg->cap > 58) return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: cap must be in [1, 58], got %d", cfg->cap);
     if (B >= (1LL << 31) / 64) return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: too many problems");
-    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = stats[4] = 0;
     if (B == 0) return SIO_OK;
     DeviceGuard guard(c->device);
     cudaStream_t st = c->stream;
@@ -815,6 +815,9 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     CU(c->s_qp.ensure(sip_qp_scratch_bytes(c->num_sms)));
     unsigned long long hc[4];
     int64_t queries = 0;
+    // device time of the QP launches and of the sweeps, read back at the end (events per iteration)
+    std::vector<cudaEvent_t> ev;
+    auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); };
     auto read_counters = [&]() -> cudaError_t {
         cudaError_t e = cudaMemcpyAsync(hc, S.counters, sizeof(hc), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return e;
@@ -822,8 +825,12 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     };
     auto sweep = [&](int64_t n) -> int {                   // K2 over the queued problems: minimum / arg-minimum only
         queries += n * N;
-        return sio_min_distance_dev(c, &grid, 1, nullptr, cloud, S.T_rel, S.bound, n, cfg->sweep_flags, S.dmin, S.arg, nullptr);
+        mark();
+        int rc = sio_min_distance_dev(c, &grid, 1, nullptr, cloud, S.T_rel, S.bound, n, cfg->sweep_flags, S.dmin, S.arg, nullptr);
+        mark();
+        return rc;
     };
+    std::vector<size_t> qp_marks;
     for (int it = 0; it < cfg->max_iters; ++it) {
         CU(cudaMemsetAsync(S.counters, 0, 2 * sizeof(unsigned long long), st));
         ls_launch_begin(S, it, st);
@@ -843,9 +850,12 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
             ls_launch_values(S, 0, 1, 0, st);              // rows only: the appended depths are the sweeps' exact minima
         }
         ls_launch_gx(S, L, it, st);
+        qp_marks.push_back(ev.size());
+        mark();
         if (launch_sip_qp(6, B, S.qW, S.dxdes, S.qlo, S.qhi, nullptr, S.qk, cap, S.rows, S.D, L.reg, L.inflation, 1e-5, 4000, S.dx,
                           S.qstatus, c->s_qp.p, c->num_sms, st))
             return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: QP launch failed");
+        mark();
         ls_launch_step(S, L, st);
         ls_launch_values(S, 1, 0, 1, st);
         CU(cudaMemsetAsync(S.counters, 0, sizeof(unsigned long long), st));
@@ -875,7 +885,21 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
             for (int j = 0; j < 3; ++j) T_out[12 * p + 4 * i + j] = hR[9 * p + 3 * i + j];
             T_out[12 * p + 4 * i + 3] = ht[3 * p + i];
         }
-    if (stats) { stats[0] = (int64_t)hc[2]; stats[1] = queries; stats[2] = 0; stats[3] = (int64_t)hc[3]; }
+    double qp_ms = 0.0, sweep_ms = 0.0;
+    {
+        std::vector<char> is_qp(ev.size(), 0);
+        for (size_t k : qp_marks) is_qp[k] = 1;
+        for (size_t k = 0; k + 1 < ev.size(); k += 2) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+            (is_qp[k] ? qp_ms : sweep_ms) += ms;
+        }
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+    if (stats) {
+        stats[0] = (int64_t)hc[2]; stats[1] = queries; stats[2] = (int64_t)(qp_ms * 1e3); stats[3] = (int64_t)hc[3];
+        stats[4] = (int64_t)(sweep_ms * 1e3);
+    }
     return SIO_OK;
 }
 

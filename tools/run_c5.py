@@ -90,7 +90,8 @@ if rank == 0:
                   "wall_s": wall, "iters_per_s": float(rec[0].item()) / wall, "oracle_s": float(rec[2].item()) / world,
                   "qp_s": float(rec[3].item()) / world, "point_queries": int(rec[4].item()), "feasible": int(rec[5].item()),
                   "qp_host_fallbacks": getattr(res, "qp_host_fallbacks", 0), "qp_device_s": getattr(res, "time_qp_device", 0.0), "qp_admm_iterations": getattr(res, "qp_admm_iterations", 0),
-                  "slot_overflows": getattr(res, "slot_overflows", 0), "max_params": max(len(p) for p in res.instantiated_params), "mean_params": float(np.mean([len(p) for p in res.instantiated_params]))}
+                  "slot_overflows": getattr(res, "slot_overflows", 0), "max_params": int(max(getattr(res, "n_params", [len(p) for p in res.instantiated_params]))),
+                  "mean_params": float(np.mean(getattr(res, "n_params", [len(p) for p in res.instantiated_params])))}
     print(json.dumps({"config": "C5 synthetic scene %d pts, %d problems, %d GPUs" % (N, a.problems, world), **out}))
 if world > 1:
     dist.destroy_process_group()
