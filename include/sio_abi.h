@@ -211,8 +211,9 @@ int sio_sip_step_qp(sio_ctx* ctx, int32_t n, int64_t nprob, const double* W, con
 int sio_ctx_last_bulk_ms(sio_ctx* ctx, double* ms);
 /* SIO_PRUNE bookkeeping of the LAST K2 call: (transform, sub-tile) pairs evaluated vs total. */
 int sio_ctx_last_prune_stats(sio_ctx* ctx, int64_t* evaluated, int64_t* total);
-/* ADMM iterations of the LAST sio_sip_step_qp call, summed over its problems (diagnostics). */
-int sio_ctx_last_qp_iters(sio_ctx* ctx, int64_t* iters);
+/* ADMM iterations of the LAST sio_sip_step_qp call: summed over its problems, the largest single count, and the number
+ * of solves that ran into the iteration limit (diagnostics; the last two may be NULL). */
+int sio_ctx_last_qp_iters(sio_ctx* ctx, int64_t* iters, int64_t* max_single, int64_t* n_at_limit);
 /* random 4-byte gathers over an L2-resident float array of `n_elems`: returns achieved GB/s of
  * gathered bytes (32 B sectors are NOT counted, only the 4 B used) in *gbps. */
 int sio_bench_gather(sio_ctx* ctx, int64_t n_elems, int64_t n_gathers, int iters, double* gbps);

@@ -88,7 +88,7 @@ def load_library():
     L.sio_bench_gather.argtypes = [P, I64, I64, C.c_int, C.POINTER(D)]
     L.sio_ctx_last_bulk_ms.argtypes = [P, C.POINTER(D)]
     L.sio_ctx_last_prune_stats.argtypes = [P, C.POINTER(I64), C.POINTER(I64)]
-    L.sio_ctx_last_qp_iters.argtypes = [P, C.POINTER(I64)]
+    L.sio_ctx_last_qp_iters.argtypes = [P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64)]
     _lib = L
     return L
 
@@ -302,10 +302,10 @@ class Context:
                                         float(reg), float(inflation), float(eps_abs), int(max_iter), dx.ctypes.data, status.ctypes.data))
         return dx, status
 
-    def last_qp_iters(self):
-        n = C.c_int64(0)
-        self._ck(self.L.sio_ctx_last_qp_iters(self.h, C.byref(n)))
-        return n.value
+    def last_qp_iters(self, detail=False):
+        n, mx, lim = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.sio_ctx_last_qp_iters(self.h, C.byref(n), C.byref(mx), C.byref(lim)))
+        return (n.value, mx.value, lim.value) if detail else n.value
 
     # -- K4 --
     def robot_create(self, parent, tparent, axis, jtype=None):

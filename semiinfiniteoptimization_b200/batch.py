@@ -514,7 +514,9 @@ def optimizeCollFreeBatchFast(obj, env, Tinits, Tdess=None, settings=None, conte
         if qp == 'device':
             dx, qst = ctx.sip_step_qp(Wq, dxdes, offs, rows, dep, lo_q, hi_q, reg=reg, inflation=settings.constraint_inflation)
             res.time_qp_device = getattr(res, 'time_qp_device', 0.0) + time.time() - t0
-            res.qp_admm_iterations = getattr(res, 'qp_admm_iterations', 0) + ctx.last_qp_iters()
+            qi = ctx.last_qp_iters(detail=True)
+            res.qp_admm_iterations = getattr(res, 'qp_admm_iterations', 0) + qi[0]
+            res.qp_iter_log = getattr(res, 'qp_iter_log', []) + [(len(idx), qi[0], qi[1], qi[2])]
             todo = np.nonzero(qst == 3)[0]
             if len(todo):                            # slack re-solve (sip.py:332-357) on the host
                 cn = (offs[1:] - offs[:-1])[todo]

@@ -114,7 +114,7 @@ struct sio_ctx {
     // scratch
     DevBuf s_lb, s_ub, s_items, s_icnt;
     int64_t scratch_limit = (int64_t)(256u << 20);   // bytes of sub-tile minima kept per K2 batch (sio_ctx_set_scratch_limit)
-    int64_t qp_iters_total = 0;      // ADMM iterations of the last sio_sip_step_qp call, summed over problems
+    int64_t qp_iters_total = 0, qp_iters_max = 0, qp_at_limit = 0;      // ADMM iterations of the last sio_sip_step_qp call, summed over problems
     DevBuf s_qp;                     // per-warp polish scratch + work counter of the SIP-step QP kernel
     HostBuf h_icnt;
     int n_icnt = 0;                   // batches of the last pruned call (their survivor counts sit in h_icnt)
@@ -973,8 +973,15 @@ int sio_sip_step_qp(sio_ctx* c, int32_t n, int64_t nprob, const double* W, const
     CU(cudaStreamSynchronize(st));
     std::memcpy(dx, c->h_b.p, v);
     std::memcpy(status, c->h_b.as<char>() + v, (size_t)nprob * sizeof(int32_t));
-    c->qp_iters_total = 0;
-    for (int64_t i = 0; i < nprob; ++i) { c->qp_iters_total += status[i] >> 8; status[i] &= 0xff; }
+    c->qp_iters_total = 0; c->qp_iters_max = 0; c->qp_at_limit = 0;
+    const int lim = max_iter > 0 ? max_iter : 4000;
+    for (int64_t i = 0; i < nprob; ++i) {
+        const int64_t its = status[i] >> 8;
+        c->qp_iters_total += its;
+        if (its > c->qp_iters_max) c->qp_iters_max = its;
+        if (its >= lim) c->qp_at_limit += 1;
+        status[i] &= 0xff;
+    }
     return SIO_OK;
 }
 
@@ -1137,9 +1144,11 @@ int sio_robot_min_distance(sio_ctx* c, sio_handle robot, const sio_handle* link_
 }
 
 // ---- measurement helpers --------------------------------------------------------------------------------
-int sio_ctx_last_qp_iters(sio_ctx* c, int64_t* iters) {
+int sio_ctx_last_qp_iters(sio_ctx* c, int64_t* iters, int64_t* max_single, int64_t* n_at_limit) {
     if (!c || !iters) return fail(SIO_ERR_INVALID, "sio_ctx_last_qp_iters: bad argument");
     *iters = c->qp_iters_total;
+    if (max_single) *max_single = c->qp_iters_max;
+    if (n_at_limit) *n_at_limit = c->qp_at_limit;
     return SIO_OK;
 }
 

@@ -83,6 +83,8 @@ rec = torch.tensor([res.outer_iterations, wall, res.time_cons, res.time_qp, res.
 if world > 1:
     mx = rec.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(rec, op=dist.ReduceOp.SUM)
     wall = float(mx[1].item())
+if rank == 0 and getattr(res, "qp_iter_log", None):
+    print("QP log (problems, ADMM iterations, max single, at limit):", res.qp_iter_log, file=sys.stderr)
 if rank == 0 and getattr(res, "iter_log", None):
     print("iteration log (it, live, rows, qp_s):", [(a_, b_, c_, round(d_, 4)) for a_, b_, c_, d_ in res.iter_log], file=sys.stderr)
 if rank == 0:
