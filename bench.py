@@ -28,7 +28,8 @@ NCCL once per reporting interval (the K timed steps), inside the timed total.
 
 `sip`     : BASELINE.json's second metric, SIP outer iterations/s, on configs[4] ("C5"): 65,536 independent
            cube-vs-scene optimizeCollFree problems (declared synthetic scene, 262,144 points) sharded across the
-           ranks and solved in lock step (batch.optimizeCollFreeBatchFast), with the oracle / QP / other split; at
+           ranks and solved in lock step entirely on the device (batch.optimizeCollFreeBatchDevice =
+           sio_lockstep_pose_solve), wall clock from host poses to host results, with the sweep / QP / other split; at
            N=1 also the CPU path (restated SIP loop on the CPU oracle, one process per host core, bounded sample).
 
 --impl reference times that CPU oracle port as the reference arm (the reference itself is
@@ -257,11 +258,11 @@ def sip_leg(ctx, rank, world, want_cpu):
     scene = G.PenetrationDepthGeometry(Geometry3D(PointCloud(workloads.c5_scene_cloud())), None, 0.02, context=ctx)
     poses = workloads.c5_poses(SIP_PROBLEMS, seed=3)
     lo, hi = sdist.shard_range(SIP_PROBLEMS)
-    batch.optimizeCollFreeBatchFast(cube, scene, poses[lo:lo + 64])            # warm-up (allocations, first launches)
+    batch.optimizeCollFreeBatchDevice(cube, scene, poses[lo:lo + 64])          # warm-up (allocations, first launches)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    res = batch.optimizeCollFreeBatchFast(cube, scene, poses[lo:hi])
+    res = batch.optimizeCollFreeBatchDevice(cube, scene, poses[lo:hi])         # host poses in, host results out
     wall = time.perf_counter() - t0
     rec = torch.tensor([res.outer_iterations, wall, res.time_cons, res.time_qp, res.point_queries, float((res.gx > -5e-3).sum()),
                         float((np.asarray(res.gx0) < 0).sum())], dtype=torch.float64, device="cuda")
@@ -274,9 +275,10 @@ def sip_leg(ctx, rank, world, want_cpu):
         return None
     out = {"value": float(rec[0].item()) / wall, "unit": "SIP outer iterations/s", "scaling": "strong",
            "workload": "C5: %d independent optimizeCollFree problems (cube SDF@0.05 vs synthetic 262,144-point scene, seed 2; poses "
-                       "seed 3), reference default settings (max_iters 50), sharded over %d GPU(s), lock-step array driver" % (SIP_PROBLEMS, world),
-           "outer_iterations": int(rec[0].item()), "wall_s": wall, "oracle_s_per_rank": float(rec[2].item()) / world,
-           "qp_s_per_rank": float(rec[3].item()) / world, "other_s_per_rank": wall - float(rec[2].item() + rec[3].item()) / world,
+                       "seed 3), reference default settings (max_iters 50), sharded over %d GPU(s), device-resident lock-step "
+                       "solver (sio_lockstep_pose_solve); wall clock from host poses to host results" % (SIP_PROBLEMS, world),
+           "outer_iterations": int(rec[0].item()), "wall_s": wall, "sweep_device_s_per_rank": float(rec[2].item()) / world,
+           "qp_device_s_per_rank": float(rec[3].item()) / world, "other_s_per_rank": wall - float(rec[2].item() + rec[3].item()) / world,
            "oracle_point_queries_resolved": int(rec[4].item()), "started_in_collision": int(rec[6].item()),
            "ended_feasible(g>-5e-3)": int(rec[5].item())}
     if want_cpu:
