@@ -6,17 +6,17 @@
 // Design (DESIGN.md "Kernels"): this is gather work on CUDA cores -- no tensor cores.  Each thread
 // keeps kPtsPerThread cloud points (float4, 128-bit coalesced loads of the Morton-sorted cloud) in
 // registers and walks a chunk of transforms staged in shared memory, so the cloud is read from HBM
-// once per chunk.  The grid is resident as 8-corner BRICKS (32 B per cell = one sector): a query's
-// eight trilinear corners arrive with ONE 256-bit read-only load (LDG.E.256) at one computed
-// address, instead of eight 4-byte gathers at four addresses.  The round-1 ncu profile of the
-// 8-gather version showed the kernel issue-bound (76 % issue-active, 101 instr/query, L1 hit 94 %),
-// so everything here is about instructions per query: bricks, FADD.RZ floor/fraction on the FMA
-// pipe (no F2I/I2F), 3-input FMNMX3 for the in-lattice test, a warp-uniform fast path that skips
-// the bbox-overshoot arithmetic, and one candidate test per 4 queries.
-// Minima are reduced per warp with REDUX on order-preserving keys and written as one 4-byte key
-// per (transform, 128-point sub-tile); the float64 finalize kernel (sio_fp64.cu) re-evaluates only
-// the sub-tiles within tau of the minimum, which makes the final arg-min identical to the float64
-// oracle's.
+// once per chunk.  The grid is resident as BRICKS: per cell the 8 monomial coefficients of its
+// trilinear interpolant (32 B = one sector), so a query is ONE 256-bit read-only load (LDG.E.256)
+// at one computed address + a 7-FMA Horner evaluation, instead of eight 4-byte gathers at four
+// addresses and 14 lerp operations.  History (profiles/): the 8-gather version was issue-bound at
+// 101 instr/query; corner bricks brought 57; this version runs 43 instr/query (FADD.RZ
+// floor/fraction on the FMA pipe, floor biases folded into the cell index, a bounding-sphere
+// in-lattice test per (128-point sub-tile, transform) instead of per-point range tests, one candidate
+// test per 4 queries) and is bound by the L1 data pipe: a 256-bit warp load is 8 wavefronts.
+// Minima are reduced per warp with redux.sync.min.f32 and written as one float per (transform,
+// 128-point sub-tile); the float64 finalize kernel (sio_fp64.cu) re-evaluates only the sub-tiles
+// within tau of the minimum, which makes the final arg-min identical to the float64 oracle's.
 #include "sio_common.cuh"
 #include <cstdlib>
 
