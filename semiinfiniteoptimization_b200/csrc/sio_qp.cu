@@ -163,7 +163,7 @@ enum { kAdmmSolved = 0, kAdmmMaxIter = 1, kAdmmInfeasible = 2 };
 // One instantiation serves both (a runtime flag): the unrolled body is large and two copies thrash the
 // instruction cache (ncu r01_qp: 64 % of the stall samples were instruction fetch).
 template <int N>
-__device__ __noinline__ int admm(const bool SLACK, const Rows<N>& R, const double (&Pd)[N], const double (&q)[N], double pen, int k, int m, double eps_abs,
+__device__ __forceinline__ int admm(const bool SLACK, const Rows<N>& R, const double (&Pd)[N], const double (&q)[N], double pen, int k, int m, double eps_abs,
                     double eps_rel, int max_iter, double* kkt, int lane, double (&x)[N], double (&sv)[2], int& iters) {
     constexpr double kInf = 1e20, sigma = 1e-6, alpha = 1.6;
     constexpr int check_every = 10, adapt_every = 50;
@@ -198,7 +198,7 @@ __device__ __noinline__ int admm(const bool SLACK, const Rows<N>& R, const doubl
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = 0.0;
     sv[0] = sv[1] = 0.0;
-    if (!set_rho()) return kAdmmMaxIter;
+    if (__any_sync(0xffffffffu, !set_rho())) return kAdmmMaxIter;
     int st = kAdmmMaxIter;
     for (int it = 1; it <= max_iter; ++it) {
         ++iters;
@@ -268,9 +268,9 @@ __device__ __noinline__ int admm(const bool SLACK, const Rows<N>& R, const doubl
             nd = fmax(nd, fmax(fabs(px), fmax(fabs(t), fabs(q[i]))));
         }
         r_dual = warp_max(r_dual); nd = warp_max(nd);
-        if (r_prim <= eps_abs + eps_rel * nAx && r_dual <= eps_abs + eps_rel * nd) { st = kAdmmSolved; break; }
+        if (__all_sync(0xffffffffu, r_prim <= eps_abs + eps_rel * nAx && r_dual <= eps_abs + eps_rel * nd)) { st = kAdmmSolved; break; }
         ndy = warp_max(ndy);
-        if (ndy > 1e-12) {                                 // primal infeasibility certificate
+        if (__all_sync(0xffffffffu, ndy > 1e-12)) {       // primal infeasibility certificate
             double sup = 0.0, nAt = 0.0;
             double t[N];
 #pragma unroll
@@ -287,13 +287,13 @@ __device__ __noinline__ int admm(const bool SLACK, const Rows<N>& R, const doubl
             nAt = warp_max(nAt);
 #pragma unroll
             for (int i = 0; i < N; ++i) nAt = fmax(nAt, fabs(warp_sum(t[i])));
-            if (nAt <= 1e-4 && sup < -1e-4) { st = kAdmmInfeasible; break; }
+            if (__all_sync(0xffffffffu, nAt <= 1e-4 && sup < -1e-4)) { st = kAdmmInfeasible; break; }
         }
-        if (it % adapt_every == 0 && r_prim > 0 && r_dual > 0) {
+        if (it % adapt_every == 0 && __all_sync(0xffffffffu, r_prim > 0 && r_dual > 0)) {
             const double scale = sqrt((r_prim / fmax(nAx, 1e-12)) / (r_dual / fmax(nd, 1e-12)));
-            if (scale > 5 || scale < 0.2) {
+            if (__all_sync(0xffffffffu, scale > 5 || scale < 0.2)) {
                 rho = fmin(fmax(rho * scale, 1e-6), 1e6);
-                if (!set_rho()) break;
+                if (__any_sync(0xffffffffu, !set_rho())) break;
             }
         }
     }
@@ -361,7 +361,7 @@ __device__ __noinline__ int admm(const bool SLACK, const Rows<N>& R, const doubl
     if (SLACK) { f0 += warp_sum(fs0); f1 += warp_sum(fs1); }
     bad = __any_sync(0xffffffffu, bad);
     __syncwarp();
-    if (!bad && !(f1 > f0 + 1e-9 * (1 + fabs(f0)))) {
+    if (__all_sync(0xffffffffu, !bad && !(f1 > f0 + 1e-9 * (1 + fabs(f0))))) {
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = xp[i];
         sv[0] = sp[0]; sv[1] = sp[1];
@@ -381,7 +381,9 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
     constexpr double kInf = 1e20;
     // ragged layout: rows of problem p at offs[p] .. offs[p+1];  padded layout (lock-step solver): cnt[p] rows at
     // p * stride, cnt[p] < 0 = problem not taking part
-    const int k = offs ? (int)(offs[p + 1] - offs[p]) : cnt[p];
+    // every branch below depends on warp-uniform VALUES; routing them through votes / shuffles makes them uniform for the
+    // compiler too, which otherwise wraps each of the loop's shuffles in a reconvergence sequence
+    const int k = __shfl_sync(0xffffffffu, offs ? (int)(offs[p + 1] - offs[p]) : cnt[p], 0);
     const int64_t base = offs ? offs[p] : p * (int64_t)stride;
     if (k < 0) return;
     const bool box = xmin != nullptr;
@@ -445,7 +447,7 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
         double xn = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) xn += x[i] * x[i];
-        if (!(st == kAdmmInfeasible || sqrt(xn) * reg > bnorm)) break;
+        if (__all_sync(0xffffffffu, !(st == kAdmmInfeasible || sqrt(xn) * reg > bnorm))) break;
         pen = (1.0 + nneg) / (fabs(bmin) + 1e-3);
     }
 #pragma unroll
