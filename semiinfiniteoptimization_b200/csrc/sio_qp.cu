@@ -149,11 +149,12 @@ __device__ bool warp_lu_solve(double* M, double* b, int NN, int lane) {
     return true;
 }
 
-// one lane's share of a problem: two constraint rows (and, in the slack problem, their slack variables)
-template <int N>
+// one lane's share of a problem: NR constraint rows (and, in the slack problem, their slack variables).  NR = 1 serves
+// problems with at most 32 rows (nearly all of them) at half the per-iteration work of NR = 2.
+template <int N, int NR>
 struct Rows {
-    double a[2][N], l[2], u[2];
-    bool have[2], slack[2];                 // row present; row has a slack variable (the k parameter rows)
+    double a[NR][N], l[NR], u[NR];
+    bool have[NR], slack[NR];               // row present; row has a slack variable (the k parameter rows)
 };
 
 enum { kAdmmSolved = 0, kAdmmMaxIter = 1, kAdmmInfeasible = 2 };
@@ -162,18 +163,20 @@ enum { kAdmmSolved = 0, kAdmmMaxIter = 1, kAdmmInfeasible = 2 };
 // the slack block carrying the quadratic weight `pen`.  x (and sv, the lane's slack values) hold the answer.
 // One instantiation serves both (a runtime flag): the unrolled body is large and two copies thrash the
 // instruction cache (ncu r01_qp: 64 % of the stall samples were instruction fetch).
-template <int N>
-__device__ __forceinline__ int admm(const bool SLACK, const Rows<N>& R, const double (&Pd)[N], const double (&q)[N], double pen, int k, int m, double eps_abs,
-                    double eps_rel, int max_iter, double* kkt, int lane, double (&x)[N], double (&sv)[2], int& iters) {
+template <int N, int NR>
+__device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, const double (&Pd)[N], const double (&q)[N], double pen, int k, int m, double eps_abs,
+                    double eps_rel, int max_iter, double* kkt, int lane, double (&x)[N], double (&sv)[NR], int& iters) {
     constexpr double kInf = 1e20, sigma = 1e-6, alpha = 1.6;
     constexpr int check_every = 10, adapt_every = 50;
-    double z[2] = {0.0, 0.0}, y[2] = {0.0, 0.0}, rv[2], dy[2] = {0.0, 0.0}, Ax[2] = {0.0, 0.0}, ds[2] = {1.0, 1.0};
+    double z[NR], y[NR], rv[NR], dy[NR], Ax[NR], ds[NR];
+#pragma unroll
+    for (int s = 0; s < NR; ++s) { z[s] = 0.0; y[s] = 0.0; dy[s] = 0.0; Ax[s] = 0.0; ds[s] = 1.0; }
     double rho = 0.1;
     SpdInverse<N> K;
-    double irv[2] = {1.0, 1.0}, ids[2] = {1.0, 1.0};          // reciprocals: no float64 divisions inside the loop
+    double irv[NR], ids[NR];                                  // reciprocals: no float64 divisions inside the loop
     auto set_rho = [&]() {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NR; ++s) {
             rv[s] = (R.u[s] - R.l[s] < 1e-12) ? 1e3 * rho : rho;
             ds[s] = pen + sigma + rv[s];                  // diagonal of the slack block of the system matrix
             irv[s] = 1.0 / rv[s];
@@ -185,7 +188,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N>& R, const do
             for (int j = 0; j <= i; ++j) {
                 double v = 0.0;
 #pragma unroll
-                for (int s = 0; s < 2; ++s)
+                for (int s = 0; s < NR; ++s)
                     if (R.have[s]) {
                         const double wgt = (SLACK && R.slack[s]) ? rv[s] - rv[s] * rv[s] * ids[s] : rv[s];   // Schur complement
                         v += wgt * R.a[s][i] * R.a[s][j];
@@ -197,19 +200,21 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N>& R, const do
     };
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = 0.0;
-    sv[0] = sv[1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < NR; ++s) sv[s] = 0.0;
     if (__any_sync(0xffffffffu, !set_rho())) return kAdmmMaxIter;
     int st = kAdmmMaxIter;
     for (int it = 1; it <= max_iter; ++it) {
         ++iters;
-        double xt[N], w[2], stl[2] = {0.0, 0.0};
+        double xt[N], w[NR], stl[NR];
+        const bool chk = !((it % check_every) && it != max_iter);       // residual test this iteration (qp.py: every 10)
 #pragma unroll
-        for (int s = 0; s < 2; ++s) w[s] = rv[s] * z[s] - y[s];
+        for (int s = 0; s < NR; ++s) w[s] = rv[s] * z[s] - y[s];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             double v = 0.0;
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < NR; ++s) {
                 double ws = w[s];
                 if (SLACK && R.slack[s]) ws -= rv[s] * (sigma * sv[s] + w[s]) * ids[s];     // eliminate the slack unknown
                 v += R.a[s][i] * ws;                                                       // a = 0 on absent rows
@@ -219,7 +224,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N>& R, const do
         K.apply(xt);
         double ndy = 0.0;
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NR; ++s) {
             double ax = 0.0;
 #pragma unroll
             for (int i = 0; i < N; ++i) ax += R.a[s][i] * xt[i];
@@ -232,21 +237,23 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N>& R, const do
             const double c = zr + y[s] * irv[s];
             const double zn = c < R.l[s] ? R.l[s] : (c > R.u[s] ? R.u[s] : c);
             const double yn = y[s] + rv[s] * (zr - zn);
-            dy[s] = R.have[s] ? yn - y[s] : 0.0;
-            ndy = fmax(ndy, fabs(dy[s]));
+            if (chk) {                                        // only the infeasibility certificate reads dy
+                dy[s] = R.have[s] ? yn - y[s] : 0.0;
+                ndy = fmax(ndy, fabs(dy[s]));
+            }
             if (R.have[s]) { z[s] = zn; y[s] = yn; }
             if (SLACK && R.slack[s]) sv[s] = alpha * stl[s] + (1.0 - alpha) * sv[s];
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = alpha * xt[i] + (1.0 - alpha) * x[i];
-        if ((it % check_every) && it != max_iter) continue;
+        if (!chk) continue;
         // residuals (qp.py solve_qp: every 10 iterations)
         double r_prim = 0.0, nAx = 0.0, r_dual = 0.0, nd = 0.0;
         double Aty[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) Aty[i] = 0.0;
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NR; ++s) {
             double v = 0.0;
 #pragma unroll
             for (int i = 0; i < N; ++i) { v += R.a[s][i] * x[i]; Aty[i] += R.a[s][i] * y[s]; }
@@ -276,7 +283,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N>& R, const do
 #pragma unroll
             for (int i = 0; i < N; ++i) t[i] = 0.0;
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < NR; ++s) {
                 const double d = dy[s] / ndy;
 #pragma unroll
                 for (int i = 0; i < N; ++i) t[i] += R.a[s][i] * d;
@@ -299,16 +306,16 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N>& R, const do
     }
     if (st != kAdmmSolved) return st;
     // ---- polish on the active set (qp.py _polish): KKT system over [variables | active rows] ----------------
-    int flag[2];
-    double rhs[2];
+    int flag[NR];
+    double rhs[NR];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NR; ++s) {
         const bool lo = R.have[s] && ((y[s] < -1e-9) || (Ax[s] - R.l[s] < 1e-7)) && R.l[s] > -kInf / 2;
         const bool up = R.have[s] && ((y[s] > 1e-9) || (R.u[s] - Ax[s] < 1e-7)) && R.u[s] < kInf / 2;
         flag[s] = lo || up;
         rhs[s] = lo ? R.l[s] : R.u[s];
     }
-    const unsigned m0 = __ballot_sync(0xffffffffu, flag[0]), m1 = __ballot_sync(0xffffffffu, flag[1]);
+    const unsigned m0 = __ballot_sync(0xffffffffu, flag[0]), m1 = NR > 1 ? __ballot_sync(0xffffffffu, flag[NR - 1]) : 0u;
     const int na = __popc(m0) + __popc(m1);
     if (na == 0) return kAdmmSolved;
     // Unknowns [x | multipliers of the active rows].  A slack variable s_r (weight pen + delta, one entry in its own
@@ -321,9 +328,11 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N>& R, const do
     __syncwarp();
     const double delta = 1e-7;
     if (lane < N) { M[lane * NN + lane] = Pd[lane] + delta; bb[lane] = -q[lane]; }
-    int idx[2] = {0, 0};
+    int idx[NR];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NR; ++s) idx[s] = 0;
+#pragma unroll
+    for (int s = 0; s < NR; ++s) {
         if (flag[s]) {                                     // active rows keep their row order
             idx[s] = N + ((s == 0) ? __popc(m0 & ((1u << lane) - 1u)) : __popc(m0) + __popc(m1 & ((1u << lane) - 1u)));
 #pragma unroll
@@ -334,7 +343,9 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N>& R, const do
     }
     __syncwarp();
     if (!warp_lu_solve(M, bb, NN, lane)) return kAdmmSolved;
-    double xp[N], sp[2] = {0.0, 0.0};
+    double xp[N], sp[NR];
+#pragma unroll
+    for (int s = 0; s < NR; ++s) sp[s] = 0.0;
     double f0 = 0.0, f1 = 0.0, fs0 = 0.0, fs1 = 0.0;
     int bad = 0;
 #pragma unroll
@@ -345,7 +356,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N>& R, const do
         f1 += 0.5 * Pd[i] * xp[i] * xp[i] + q[i] * xp[i];
     }
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NR; ++s) {
         double v = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) v += R.a[s][i] * xp[i];
@@ -364,7 +375,8 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N>& R, const do
     if (__all_sync(0xffffffffu, !bad && !(f1 > f0 + 1e-9 * (1 + fabs(f0))))) {
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = xp[i];
-        sv[0] = sp[0]; sv[1] = sp[1];
+#pragma unroll
+        for (int s = 0; s < NR; ++s) sv[s] = sp[s];
     }
     return kAdmmSolved;
 }
@@ -372,28 +384,13 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N>& R, const do
 // status codes written per problem (low byte; the ADMM iteration count sits above it)
 enum { kQpStrict = 0, kQpSlack = 1, kQpNoRows = 2, kQpToHost = 3 };
 
-template <int N>
-__device__ void solve_problem(int64_t p, const double* __restrict__ W, const double* __restrict__ xdes, const double* __restrict__ xmin,
-                              const double* __restrict__ xmax, const int64_t* __restrict__ offs, const int32_t* __restrict__ cnt,
-                              int32_t stride, const double* __restrict__ rows,
-                              const double* __restrict__ depths, double reg, double inflation, double eps_abs, double eps_rel,
-                              int max_iter, double* kkt, int lane, double* __restrict__ dx, int32_t* __restrict__ status) {
+template <int N, int NR>
+__device__ __forceinline__ void solve_rows(int64_t p, int k, int m, int64_t base, bool box, const double* __restrict__ W,
+                                           const double* __restrict__ xdes, const double* __restrict__ xmin, const double* __restrict__ xmax,
+                                           const double* __restrict__ rows, const double* __restrict__ depths, double reg, double inflation,
+                                           double eps_abs, double eps_rel, int max_iter, double* kkt, int lane, double* __restrict__ dx,
+                                           int32_t* __restrict__ status) {
     constexpr double kInf = 1e20;
-    // ragged layout: rows of problem p at offs[p] .. offs[p+1];  padded layout (lock-step solver): cnt[p] rows at
-    // p * stride, cnt[p] < 0 = problem not taking part
-    // every branch below depends on warp-uniform VALUES; routing them through votes / shuffles makes them uniform for the
-    // compiler too, which otherwise wraps each of the loop's shuffles in a reconvergence sequence
-    const int k = __shfl_sync(0xffffffffu, offs ? (int)(offs[p + 1] - offs[p]) : cnt[p], 0);
-    const int64_t base = offs ? offs[p] : p * (int64_t)stride;
-    if (k < 0) return;
-    const bool box = xmin != nullptr;
-    if (k == 0) {                                          // no rows: xdes, box ignored (sip.py:288)
-        if (lane < N) dx[p * N + lane] = xdes[p * N + lane];
-        if (lane == 0) status[p] = kQpNoRows;
-        return;
-    }
-    const int m = k + (box ? N : 0);
-    if (m > kQpMaxRows) { if (lane == 0) status[p] = kQpToHost; return; }
     double Pd[N], q[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -401,11 +398,11 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
         Pd[i] = w + reg;
         q[i] = -w * xdes[p * N + i];
     }
-    Rows<N> R;
+    Rows<N, NR> R;
     double bneg2 = 0.0, bmin = INFINITY;
     int nneg = 0;
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NR; ++s) {
         const int r = lane + 32 * s;
         R.have[s] = r < m;
         R.slack[s] = r < k;
@@ -432,13 +429,13 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
     nneg = __reduce_add_sync(0xffffffffu, nneg);
     bmin = -warp_max(-bmin);
     const double bnorm = nneg ? sqrt(bneg2) : 1.0;
-    double x[N], sv[2];
+    double x[N], sv[NR];
     // strict problem first; if it is infeasible or its solution out of scale, the reference's slack re-solve
     // (sip.py:332-357, slack_penalty = 'auto').  One call site in a loop: the unrolled solver body exists once.
     int iters = 0, code = kQpStrict;
     double pen = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
-        const int st = admm<N>(pass == 1, R, Pd, q, pen, k, m, eps_abs, eps_rel, max_iter, kkt, lane, x, sv, iters);
+        const int st = admm<N, NR>(pass == 1, R, Pd, q, pen, k, m, eps_abs, eps_rel, max_iter, kkt, lane, x, sv, iters);
         if (pass == 1) {
             if (st == kAdmmInfeasible) { if (lane == 0) status[p] = kQpToHost; return; }
             code = kQpSlack;
@@ -453,6 +450,34 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
 #pragma unroll
     for (int i = 0; i < N; ++i) if (lane == i) dx[p * N + i] = x[i];
     if (lane == 0) status[p] = code | (iters << 8);        // ADMM iterations spent, for diagnostics
+}
+
+template <int N>
+__device__ void solve_problem(int64_t p, const double* __restrict__ W, const double* __restrict__ xdes, const double* __restrict__ xmin,
+                              const double* __restrict__ xmax, const int64_t* __restrict__ offs, const int32_t* __restrict__ cnt,
+                              int32_t stride, const double* __restrict__ rows,
+                              const double* __restrict__ depths, double reg, double inflation, double eps_abs, double eps_rel,
+                              int max_iter, double* kkt, int lane, double* __restrict__ dx, int32_t* __restrict__ status) {
+    constexpr double kInf = 1e20;
+    // ragged layout: rows of problem p at offs[p] .. offs[p+1];  padded layout (lock-step solver): cnt[p] rows at
+    // p * stride, cnt[p] < 0 = problem not taking part
+    // every branch below depends on warp-uniform VALUES; routing them through votes / shuffles makes them uniform for the
+    // compiler too, which otherwise wraps each of the loop's shuffles in a reconvergence sequence
+    const int k = __shfl_sync(0xffffffffu, offs ? (int)(offs[p + 1] - offs[p]) : cnt[p], 0);
+    const int64_t base = offs ? offs[p] : p * (int64_t)stride;
+    if (k < 0) return;
+    const bool box = xmin != nullptr;
+    if (k == 0) {                                          // no rows: xdes, box ignored (sip.py:288)
+        if (lane < N) dx[p * N + lane] = xdes[p * N + lane];
+        if (lane == 0) status[p] = kQpNoRows;
+        return;
+    }
+    const int m = k + (box ? N : 0);
+    if (m > kQpMaxRows) { if (lane == 0) status[p] = kQpToHost; return; }
+    if (m <= 32)
+        solve_rows<N, 1>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status);
+    else
+        solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status);
 }
 
 // persistent warps: each draws the next problem from *counter (reset to 0 by the launcher)
