@@ -602,6 +602,8 @@ def optimizeCollFreeBatchDevice(obj, env, Tinits, Tdess=None, settings=None, con
     if Tdess is None:
         Tdess = Tinits
     def rowmajor(Ts):            # Klampt se3 (R column-major 9-list, t) -> row-major 3x4, vectorised
+        if isinstance(Ts, np.ndarray):                      # already row-major 3x4 per problem: (B, 12) or (B, 3, 4)
+            return np.ascontiguousarray(Ts, dtype=np.float64).reshape(len(Ts), 12)
         Rc = np.array([T[0] for T in Ts], dtype=np.float64).reshape(-1, 3, 3)          # [b][col][row]
         out = np.empty((len(Ts), 3, 4))
         out[:, :, :3] = np.transpose(Rc, (0, 2, 1))

@@ -9,6 +9,7 @@
 #include <limits>
 #include <mutex>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "../../include/sio_abi.h"
@@ -818,6 +819,16 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     // device time of the QP launches and of the sweeps, read back at the end (events per iteration)
     std::vector<cudaEvent_t> ev;
     auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); };
+    // SIO_LS_PROFILE=1: device time of every phase of the loop, printed to stderr at the end (a development aid)
+    const bool prof = getenv("SIO_LS_PROFILE") != nullptr;
+    enum { kPhPre = 0, kPhPost, kPhGx, kPhStep, kPhScore, kPhCount };
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
+    cudaEvent_t span_open = nullptr;
+    auto span_begin = [&]() { if (prof) { cudaEventCreate(&span_open); cudaEventRecord(span_open, st); } };
+    auto span_end = [&](int label) {
+        if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); spans.push_back({label, {span_open, e}}); }
+    };
+    const auto wall0 = std::chrono::steady_clock::now();
     auto read_counters = [&]() -> cudaError_t {
         cudaError_t e = cudaMemcpyAsync(hc, S.counters, sizeof(hc), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return e;
@@ -832,6 +843,7 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     };
     std::vector<size_t> qp_marks;
     for (int it = 0; it < cfg->max_iters; ++it) {
+        span_begin();
         CU(cudaMemsetAsync(S.counters, 0, 2 * sizeof(unsigned long long), st));
         ls_launch_begin(S, it, st);
         const bool maybe_upd = (it == 0) || ((it - 1) % 100 == 0);         // sip.py:855-870
@@ -841,29 +853,59 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
         } else {
             ls_launch_values(S, 0, 1, 1, st);
         }
+        span_end(kPhPre);
         CU(read_counters());
         if (hc[1] == 0) break;                             // no live problem left
         if (maybe_upd) {
             const int64_t n = (int64_t)hc[0];
             if (n > 0) { int rc = sweep(n); if (rc) return rc; }
+            span_begin();
             ls_launch_oracle_post(S, L, n, st);
             ls_launch_values(S, 0, 1, 0, st);              // rows only: the appended depths are the sweeps' exact minima
+            span_end(kPhPost);
         }
+        span_begin();
         ls_launch_gx(S, L, it, st);
+        span_end(kPhGx);
         qp_marks.push_back(ev.size());
+        if (prof) CU(cudaMemsetAsync(S.qstatus, 0, (size_t)B * 4, st));   // the kernel skips problems that are not live
         mark();
         if (launch_sip_qp(6, B, S.qW, S.dxdes, S.qlo, S.qhi, nullptr, S.qk, cap, S.rows, S.D, L.reg, L.inflation, 1e-5, 4000, S.dx,
                           S.qstatus, c->s_qp.p, c->num_sms, st))
             return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: QP launch failed");
         mark();
+        if (prof) {                                        // per-launch ADMM iteration statistics
+            static std::vector<int32_t> hprev;
+            std::vector<int32_t> hs((size_t)B), hk((size_t)B);
+            CU(cudaMemcpyAsync(hs.data(), S.qstatus, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(hk.data(), S.qk, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (hprev.size() != (size_t)B) hprev.assign((size_t)B, 0);
+            long long tot = 0, mx = 0, nz = 0, lim = 0, slow = 0, both = 0, big = 0, big_it = 0, big_mx = 0;
+            for (int64_t p = 0; p < B; ++p) {
+                const long long n = hs[p] >> 8;
+                tot += n; mx = std::max(mx, n); nz += n > 0; lim += n >= 4000;
+                if (n >= 1000) { ++slow; both += (hprev[p] >> 8) >= 1000; }
+                if (hk[p] + 6 > 32) { ++big; big_it += n; big_mx = std::max(big_mx, n); }
+            }
+            hprev = hs;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[ev.size() - 2], ev[ev.size() - 1]);
+            fprintf(stderr, "[sio lockstep] it %d: qp %.2f ms, %lld problems, %lld ADMM its (max %lld, %lld at limit, %lld slow of which %lld were slow before; "
+                            "%lld with 2 rows/lane: %lld its, max %lld)\n", it, ms, nz, tot, mx, lim, slow, both, big, big_it, big_mx);
+        }
+        span_begin();
         ls_launch_step(S, L, st);
         ls_launch_values(S, 1, 0, 1, st);
         CU(cudaMemsetAsync(S.counters, 0, sizeof(unsigned long long), st));
         ls_launch_score_pre(S, st);
+        span_end(kPhStep);
         CU(read_counters());
         const int64_t n = (int64_t)hc[0];
         if (n > 0) { int rc = sweep(n); if (rc) return rc; }
+        span_begin();
         ls_launch_score_post(S, L, n, st);
+        span_end(kPhScore);
         c->launches += 8;
         CU(cudaGetLastError());
     }
@@ -895,6 +937,18 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
             (is_qp[k] ? qp_ms : sweep_ms) += ms;
         }
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+    if (prof) {
+        double ph[kPhCount] = {0, 0, 0, 0, 0};
+        for (auto& sp : spans) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, sp.second.first, sp.second.second);
+            ph[sp.first] += ms;
+            cudaEventDestroy(sp.second.first); cudaEventDestroy(sp.second.second);
+        }
+        const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+        fprintf(stderr, "[sio lockstep] loop+readback wall %.1f ms: qp %.1f, sweeps %.1f, begin/values/oracle_pre %.1f, oracle_post/rows %.1f, gx %.1f, "
+                        "step/values/score_pre %.1f, score_post %.1f\n", wall, qp_ms, sweep_ms, ph[kPhPre], ph[kPhPost], ph[kPhGx], ph[kPhStep], ph[kPhScore]);
     }
     if (stats) {
         stats[0] = (int64_t)hc[2]; stats[1] = queries; stats[2] = (int64_t)(qp_ms * 1e3); stats[3] = (int64_t)hc[3];

@@ -7,13 +7,13 @@
 // sip.py:332-357 (one slack variable per row, penalty 'auto') -- for the 65,536 problems of BASELINE.json
 // configs[4] advancing together.  The algorithm is the one of _host/qp.py / _host/csrc/hostqp.c (OSQP's ADMM:
 // over-relaxation, adaptive rho, residual test every 10 iterations, primal-infeasibility certificate,
-// active-set polish), in float64 without FMA contraction.
+// active-set polish), in float64.
 //
 // Mapping: lane r owns constraint rows r and r+32 (the k instantiated-parameter rows, then the n box rows) and, in
 // the slack problem, the slack variables of its rows; x lives replicated in every lane.  The quadratic term is
 // diagonal and every slack variable sits in exactly one row, so the ADMM linear system reduces (Schur complement
-// over the slack block) to an n x n system whose explicit inverse every lane applies redundantly; A'(rho z - y) is n butterfly
-// reductions; everything else is lane-local.  The polish solves its KKT system (slack unknowns eliminated the same
+// over the slack block) to an n x n system whose explicit inverse K is folded into the rows once per rho (lane r keeps
+// K a_r), so that one n-value warp sum per iteration yields the whole x-update; everything else is lane-local.  The polish solves its KKT system (slack unknowns eliminated the same
 // way) with a warp-parallel Gaussian elimination in a per-warp scratch (L2-resident global memory: the ADMM loop
 // itself touches no memory).  Warps are persistent and draw problems from an atomic counter, because the ADMM
 // iteration count varies from tens to thousands between problems.
@@ -38,6 +38,68 @@ __device__ __forceinline__ double warp_max(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+
+// Sum (or maximum) over the warp of M (<= 8) doubles per lane, delivered to every lane.  A butterfly per value costs
+// 5 M 64-bit shuffles; here three halving steps (xor 16, 8, 4: a lane keeps one half of its values and ships the
+// other) leave one value per lane, two butterfly levels finish it inside each group of four lanes, and M broadcasts
+// hand every total to every lane: 6 values = 8 + 6 shuffles instead of 30.  The maximum pads with 0: for
+// non-negative values only.
+template <int M, bool MAX = false>
+struct AllRed {
+    static constexpr int H0 = (M + 1) / 2, H1 = (H0 + 1) / 2, H2 = (H1 + 1) / 2;
+    static_assert(M >= 1 && M <= 8 && H2 == 1, "three halving steps must reach one value");
+    __device__ __forceinline__ static double comb(double a, double b) { return MAX ? fmax(a, b) : a + b; }
+    __host__ __device__ static constexpr int src(int i) {   // lane (bits 1, 0 clear) that ends up with total i
+        int l = 0;
+        if (i >= H0) { l |= 16; i -= H0; }
+        if (i >= H1) { l |= 8; i -= H1; }
+        if (i >= H2) { l |= 4; }
+        return l;
+    }
+    template <int LEN, int HALF>
+    __device__ __forceinline__ static void halve(double (&v)[M], bool up, int mask) {
+#pragma unroll
+        for (int k = 0; k < HALF; ++k) {
+            const double lo = v[k], hi = (k + HALF < LEN) ? v[k + HALF] : 0.0;
+            const double send = up ? lo : hi, keep = up ? hi : lo;
+            v[k] = comb(keep, __shfl_xor_sync(0xffffffffu, send, mask));
+        }
+    }
+    __device__ __forceinline__ static void all(double (&v)[M], int lane) {
+        halve<M, H0>(v, lane & 16, 16);
+        halve<H0, H1>(v, lane & 8, 8);
+        halve<H1, H2>(v, lane & 4, 4);
+        double r = v[0];
+        r = comb(r, __shfl_xor_sync(0xffffffffu, r, 2));
+        r = comb(r, __shfl_xor_sync(0xffffffffu, r, 1));
+#pragma unroll
+        for (int i = 0; i < M; ++i) v[i] = __shfl_sync(0xffffffffu, r, src(i));
+    }
+};
+template <int M> using AllSum = AllRed<M, false>;
+template <int M> using AllMax = AllRed<M, true>;
+
+// The same sum for the ADMM loop's one reduction per iteration, without the selects: lane L keeps its 8 slots (M
+// values and zero padding) in the order slot j <-> value (L >> 2 & 7) ^ j, so that in every halving step "keep the first
+// half, ship the second" is the right thing for every lane; the lane ends with total (L >> 2 & 7).
+struct Sum8 {
+    __device__ __forceinline__ static int slot_value(int lane, int j) { return ((lane >> 2) & 7) ^ j; }
+    __device__ __forceinline__ static double scatter(double (&v)[8]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[4 + k], 16);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[2 + k], 8);
+        double r = v[0] + __shfl_xor_sync(0xffffffffu, v[1], 4);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        return r;
+    }
+    template <int M>
+    __device__ __forceinline__ static void gather(double r, double (&out)[M]) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) out[i] = __shfl_sync(0xffffffffu, r, i << 2);
+    }
+};
 
 // Symmetric positive definite N x N system matrix -> its explicit inverse (packed lower triangle, registers).
 // The ADMM loop applies the inverse as N independent dot products: a Cholesky forward/back substitution is a
@@ -172,9 +234,14 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
 #pragma unroll
     for (int s = 0; s < NR; ++s) { z[s] = 0.0; y[s] = 0.0; dy[s] = 0.0; Ax[s] = 0.0; ds[s] = 1.0; }
     double rho = 0.1;
-    SpdInverse<N> K;
     double irv[NR], ids[NR];                                  // reciprocals: no float64 divisions inside the loop
+    // The x-update is x~ = K (A'w + sigma x - q), K the inverse of the reduced system matrix.  By linearity it is
+    // sum over rows of (K a_r) w_r + K (sigma x - q): each lane keeps kb = K a_r for its rows (in Sum8's slot order), so
+    // that ONE warp sum delivers K A'w, and the lane that the sum leaves total i on keeps row i of K (krow; kq = krow . q)
+    // to add (K (sigma x - q))_i before the totals are broadcast.  K itself lives only inside set_rho.
+    double kb[NR][8], krow[N], kq = 0.0;
     auto set_rho = [&]() {
+        SpdInverse<N> K;
 #pragma unroll
         for (int s = 0; s < NR; ++s) {
             rv[s] = (R.u[s] - R.l[s] < 1e-12) ? 1e3 * rho : rho;
@@ -182,10 +249,16 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
             irv[s] = 1.0 / rv[s];
             ids[s] = 1.0 / ds[s];
         }
+        constexpr int kTri = N * (N + 1) / 2, kChunk = 7;
+        static_assert(kTri % kChunk == 0, "the packed triangle is summed seven entries at a time");
 #pragma unroll
-        for (int i = 0; i < N; ++i)
+        for (int c0 = 0; c0 < kTri; c0 += kChunk) {
+            double part[kChunk];
 #pragma unroll
-            for (int j = 0; j <= i; ++j) {
+            for (int e = 0; e < kChunk; ++e) {
+                int i = 0;                                 // (i, j) of packed entry c0 + e
+                while ((i + 1) * (i + 2) / 2 <= c0 + e) ++i;
+                const int j = c0 + e - i * (i + 1) / 2;
                 double v = 0.0;
 #pragma unroll
                 for (int s = 0; s < NR; ++s)
@@ -193,10 +266,47 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
                         const double wgt = (SLACK && R.slack[s]) ? rv[s] - rv[s] * rv[s] * ids[s] : rv[s];   // Schur complement
                         v += wgt * R.a[s][i] * R.a[s][j];
                     }
-                v = warp_sum(v);
-                K.at(i, j) = v + ((i == j) ? Pd[i] + sigma : 0.0);
+                part[e] = v;
             }
-        return K.invert();
+            AllSum<kChunk>::all(part, lane);
+#pragma unroll
+            for (int e = 0; e < kChunk; ++e) {
+                int i = 0;
+                while ((i + 1) * (i + 2) / 2 <= c0 + e) ++i;
+                const int j = c0 + e - i * (i + 1) / 2;
+                K.A[c0 + e] = part[e] + ((i == j) ? Pd[i] + sigma : 0.0);
+            }
+        }
+        if (!K.invert()) return false;
+#pragma unroll
+        for (int s = 0; s < NR; ++s) {
+            double ka[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < N; ++j) v += K.sym(i, j) * R.a[s][j];
+                ka[i] = v;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int want = Sum8::slot_value(lane, j);
+                double v = 0.0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) v = (want == i) ? ka[i] : v;
+                kb[s][j] = v;
+            }
+        }
+        kq = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double v = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) v = (((lane >> 2) & 7) == i) ? K.sym(i, j) : v;
+            krow[j] = v;
+            kq += v * q[j];
+        }
+        return true;
     };
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = 0.0;
@@ -208,34 +318,35 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
         ++iters;
         double xt[N], w[NR], stl[NR];
         const bool chk = !((it % check_every) && it != max_iter);       // residual test this iteration (qp.py: every 10)
-#pragma unroll
-        for (int s = 0; s < NR; ++s) w[s] = rv[s] * z[s] - y[s];
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            double v = 0.0;
+        {
+            double part[8];
 #pragma unroll
             for (int s = 0; s < NR; ++s) {
+                w[s] = rv[s] * z[s] - y[s];
                 double ws = w[s];
                 if (SLACK && R.slack[s]) ws -= rv[s] * (sigma * sv[s] + w[s]) * ids[s];     // eliminate the slack unknown
-                v += R.a[s][i] * ws;                                                       // a = 0 on absent rows
+#pragma unroll
+                for (int j = 0; j < 8; ++j) part[j] = (s == 0) ? kb[0][j] * ws : fma(kb[s][j], ws, part[j]);   // kb = 0 on absent rows
             }
-            xt[i] = warp_sum(v) + sigma * x[i] - q[i];
+            double kx = krow[0] * x[0];
+#pragma unroll
+            for (int j = 1; j < N; ++j) kx = fma(krow[j], x[j], kx);
+            Sum8::gather(Sum8::scatter(part) + fma(sigma, kx, -kq), xt);
         }
-        K.apply(xt);
         double ndy = 0.0;
 #pragma unroll
         for (int s = 0; s < NR; ++s) {
-            double ax = 0.0;
+            double ax = R.a[s][0] * xt[0];
 #pragma unroll
-            for (int i = 0; i < N; ++i) ax += R.a[s][i] * xt[i];
+            for (int i = 1; i < N; ++i) ax = fma(R.a[s][i], xt[i], ax);
             double zs = ax;
             if (SLACK && R.slack[s]) {
                 stl[s] = (sigma * sv[s] + w[s] - rv[s] * ax) * ids[s];
                 zs = ax + stl[s];
             }
             const double zr = alpha * zs + (1.0 - alpha) * z[s];
-            const double c = zr + y[s] * irv[s];
-            const double zn = c < R.l[s] ? R.l[s] : (c > R.u[s] ? R.u[s] : c);
+            const double cc = zr + y[s] * irv[s];
+            const double zn = fmin(fmax(cc, R.l[s]), R.u[s]);
             const double yn = y[s] + rv[s] * (zr - zn);
             if (chk) {                                        // only the infeasibility certificate reads dy
                 dy[s] = R.have[s] ? yn - y[s] : 0.0;
@@ -247,8 +358,8 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = alpha * xt[i] + (1.0 - alpha) * x[i];
         if (!chk) continue;
-        // residuals (qp.py solve_qp: every 10 iterations)
-        double r_prim = 0.0, nAx = 0.0, r_dual = 0.0, nd = 0.0;
+        // residuals (qp.py solve_qp: every 10 iterations).  The six lane-local maxima travel in one reduction.
+        double mx[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};       // r_prim, |Ax| / |z|, slack dual residual, its scale, |dy|, |dy| over slack rows
         double Aty[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) Aty[i] = 0.0;
@@ -260,41 +371,44 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
             if (SLACK && R.slack[s]) {
                 v += sv[s];
                 const double ps = pen * sv[s];                          // dual residual of the slack variable: pen s + y
-                r_dual = fmax(r_dual, fabs(ps + y[s]));
-                nd = fmax(nd, fmax(fabs(ps), fabs(y[s])));
+                mx[2] = fmax(mx[2], fabs(ps + y[s]));
+                mx[3] = fmax(mx[3], fmax(fabs(ps), fabs(y[s])));
+                mx[5] = fmax(mx[5], fabs(dy[s]));
             }
             Ax[s] = v;
-            if (R.have[s]) { r_prim = fmax(r_prim, fabs(v - z[s])); nAx = fmax(nAx, fmax(fabs(v), fabs(z[s]))); }
+            if (R.have[s]) { mx[0] = fmax(mx[0], fabs(v - z[s])); mx[1] = fmax(mx[1], fmax(fabs(v), fabs(z[s]))); }
         }
-        r_prim = warp_max(r_prim); nAx = warp_max(nAx);
+        mx[4] = ndy;
+        AllMax<6>::all(mx, lane);
+        AllSum<N>::all(Aty, lane);
+        const double r_prim = mx[0], nAx = mx[1];
+        double r_dual = mx[2], nd = mx[3];
+        ndy = mx[4];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double t = warp_sum(Aty[i]);
+            const double t = Aty[i];
             const double px = Pd[i] * x[i];
             r_dual = fmax(r_dual, fabs(px + q[i] + t));
             nd = fmax(nd, fmax(fabs(px), fmax(fabs(t), fabs(q[i]))));
         }
-        r_dual = warp_max(r_dual); nd = warp_max(nd);
         if (__all_sync(0xffffffffu, r_prim <= eps_abs + eps_rel * nAx && r_dual <= eps_abs + eps_rel * nd)) { st = kAdmmSolved; break; }
-        ndy = warp_max(ndy);
         if (__all_sync(0xffffffffu, ndy > 1e-12)) {       // primal infeasibility certificate
-            double sup = 0.0, nAt = 0.0;
-            double t[N];
+            double t[N + 1];                                // A' dy / |dy| and, last, the support term
 #pragma unroll
-            for (int i = 0; i < N; ++i) t[i] = 0.0;
+            for (int i = 0; i <= N; ++i) t[i] = 0.0;
+            const double indy = 1.0 / ndy;
 #pragma unroll
             for (int s = 0; s < NR; ++s) {
-                const double d = dy[s] / ndy;
+                const double d = dy[s] * indy;
 #pragma unroll
                 for (int i = 0; i < N; ++i) t[i] += R.a[s][i] * d;
-                if (SLACK && R.slack[s]) nAt = fmax(nAt, fabs(d));      // the slack column of A' dy
-                if (R.have[s]) sup += R.u[s] * fmax(d, 0.0) + R.l[s] * fmin(d, 0.0);
+                if (R.have[s]) t[N] += R.u[s] * fmax(d, 0.0) + R.l[s] * fmin(d, 0.0);
             }
-            sup = warp_sum(sup);
-            nAt = warp_max(nAt);
+            AllSum<N + 1>::all(t, lane);
+            double nAt = mx[5] * indy;                      // the slack columns of A' dy
 #pragma unroll
-            for (int i = 0; i < N; ++i) nAt = fmax(nAt, fabs(warp_sum(t[i])));
-            if (__all_sync(0xffffffffu, nAt <= 1e-4 && sup < -1e-4)) { st = kAdmmInfeasible; break; }
+            for (int i = 0; i < N; ++i) nAt = fmax(nAt, fabs(t[i]));
+            if (__all_sync(0xffffffffu, nAt <= 1e-4 && t[N] < -1e-4)) { st = kAdmmInfeasible; break; }
         }
         if (it % adapt_every == 0 && __all_sync(0xffffffffu, r_prim > 0 && r_dual > 0)) {
             const double scale = sqrt((r_prim / fmax(nAx, 1e-12)) / (r_dual / fmax(nd, 1e-12)));
