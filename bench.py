@@ -258,6 +258,9 @@ def sip_leg(ctx, rank, world, want_cpu):
     scene = G.PenetrationDepthGeometry(Geometry3D(PointCloud(workloads.c5_scene_cloud())), None, 0.02, context=ctx)
     poses = workloads.c5_poses(SIP_PROBLEMS, seed=3)
     lo, hi = sdist.shard_range(SIP_PROBLEMS)
+    from semiinfiniteoptimization_b200._host import se3
+    poses = np.array([se3.to_rowmajor12(T) for T in poses[lo:hi]])            # this rank's poses as a (B, 12) row-major array
+    lo, hi = 0, len(poses)
     batch.optimizeCollFreeBatchDevice(cube, scene, poses[lo:lo + 64])          # warm-up (allocations, first launches)
     if world > 1:
         dist.barrier()
@@ -276,7 +279,7 @@ def sip_leg(ctx, rank, world, want_cpu):
     out = {"value": float(rec[0].item()) / wall, "unit": "SIP outer iterations/s", "scaling": "strong",
            "workload": "C5: %d independent optimizeCollFree problems (cube SDF@0.05 vs synthetic 262,144-point scene, seed 2; poses "
                        "seed 3), reference default settings (max_iters 50), sharded over %d GPU(s), device-resident lock-step "
-                       "solver (sio_lockstep_pose_solve); wall clock from host poses to host results" % (SIP_PROBLEMS, world),
+                       "solver (sio_lockstep_pose_solve); wall clock from host poses (row-major 3x4 array) to host results" % (SIP_PROBLEMS, world),
            "outer_iterations": int(rec[0].item()), "wall_s": wall, "sweep_device_s_per_rank": float(rec[2].item()) / world,
            "qp_device_s_per_rank": float(rec[3].item()) / world, "other_s_per_rank": wall - float(rec[2].item() + rec[3].item()) / world,
            "oracle_point_queries_resolved": int(rec[4].item()), "started_in_collision": int(rec[6].item()),

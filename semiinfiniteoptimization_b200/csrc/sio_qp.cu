@@ -23,6 +23,7 @@
 namespace sio {
 
 constexpr int kQpWarps = 4;                 // warps per CTA
+constexpr int kQpCtasPerSm = 2;             // resident CTAs per SM the register budget is set for
 constexpr int kQpMaxRows = 64;              // 2 rows per lane
 constexpr int kQpMaxVars = 8;
 constexpr int kQpMaxKkt = kQpMaxVars + kQpMaxRows;     // largest polish system (x + active rows)
@@ -596,7 +597,7 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
 
 // persistent warps: each draws the next problem from *counter (reset to 0 by the launcher)
 template <int N>
-__global__ void __launch_bounds__(kQpWarps * 32, 3)
+__global__ void __launch_bounds__(kQpWarps * 32, kQpCtasPerSm)
 k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__ xdes, const double* __restrict__ xmin,
          const double* __restrict__ xmax, const int64_t* __restrict__ offs, const int32_t* __restrict__ cnt, int32_t stride,
          const double* __restrict__ rows,
@@ -613,7 +614,7 @@ k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__
     }
 }
 
-int sip_qp_grid(int num_sms) { return num_sms * 3; }                      // CTAs: 12 resident warps per SM (register-limited)
+int sip_qp_grid(int num_sms) { return num_sms * kQpCtasPerSm; }           // 8 resident warps per SM at 255 registers: measured best (3 x 168 and 4 x 128 spill and run slower alone and loaded)
 size_t sip_qp_scratch_bytes(int num_sms) { return (size_t)sip_qp_grid(num_sms) * kQpWarps * kQpScratch * sizeof(double) + 64; }
 
 // scratch: sip_qp_scratch_bytes(num_sms) bytes; its last 64 bytes hold the work counter

@@ -48,7 +48,7 @@ def one(p, reps=1):
 
 
 if a.loaded_only >= 0:
-    print(json.dumps({"loaded": one(a.loaded_only, ctx.num_sms * 12)}))
+    print(json.dumps({"loaded": one(a.loaded_only, ctx.num_sms * 8)}))
     sys.exit(0)
 recs = [one(p) for p in range(B)]
 t = np.array([r[0] for r in recs]); it = np.array([r[1] for r in recs], dtype=np.float64)
@@ -58,8 +58,12 @@ hard = int(np.argmax(it))
 out = {"problems": B, "iterations_min_med_max": [float(it.min()), float(np.median(it)), float(it.max())],
        "alone": {"fixed_us": c0 * 1e6, "ns_per_admm_iteration": c1 * 1e9},
        "hardest": {"index": hard, "rows": int(counts[hard]), "iterations": float(it[hard]), "ms": t[hard] * 1e3, "status": recs[hard][3]}}
-slots = ctx.num_sms * 12
+slots = ctx.num_sms * 8
 for reps in (slots // 12, slots // 3, slots, 4 * slots):
     dt, tot, mx, st = one(hard, reps)
     out[f"x{reps}"] = {"ms": dt * 1e3, "ns_per_iteration_per_problem": dt * 1e9 / max(it[hard], 1), "aggregate_Miter_per_s": tot / dt / 1e6}
+easy = int(np.argmin(it))
+dt, tot, mx, st = one(easy, 8 * slots)
+out["easiest_x%d" % (8 * slots)] = {"rows": int(counts[easy]), "iterations": float(it[easy]), "status": st, "ms": dt * 1e3,
+                                    "us_per_problem_per_warp_slot": dt * 1e6 / 8}
 print(json.dumps(out))

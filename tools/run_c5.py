@@ -73,7 +73,9 @@ if nb == 0:
 st = sip.SemiInfiniteOptimizationSettings(); st.max_iters = a.max_iters
 t0 = time.time()
 if a.qp == "resident":
-    res = batch.optimizeCollFreeBatchDevice(cube, scene, mine[:nb], settings=st)
+    Tm = np.array([se3.to_rowmajor12(T) for T in mine[:nb]])
+    t0 = time.time()
+    res = batch.optimizeCollFreeBatchDevice(cube, scene, Tm, settings=st)
 elif a.qp in ("device", "host"):
     res = batch.optimizeCollFreeBatchFast(cube, scene, mine[:nb], settings=st, qp=a.qp)
 else:
