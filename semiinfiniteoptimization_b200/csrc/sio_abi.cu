@@ -551,7 +551,7 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
     if (prune) {
         if ((B + Bc - 1) / Bc > max_batches) return fail(SIO_ERR_INVALID, "sio_min_distance_dev: too many batches for SIO_PRUNE");
         CU(c->s_xf.ensure((size_t)B * sizeof(XfRec)));
-        CU(c->s_lb.ensure((size_t)(Bc * nsub) * sizeof(float)));
+        CU(c->s_lb.ensure((size_t)(((Bc + 31) & ~(int64_t)31) * nsub) * sizeof(float)));      // sub-tile-major, transforms padded to whole warps
         CU(c->s_items.ensure((size_t)(Bc * nsub) * sizeof(uint32_t)));
         CU(c->s_ub.ensure((size_t)B * sizeof(uint32_t)));
         CU(c->s_icnt.ensure(sizeof(uint32_t) * max_batches));
@@ -839,6 +839,14 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
         mark();
         int rc = sio_min_distance_dev(c, &grid, 1, nullptr, cloud, S.T_rel, S.bound, n, cfg->sweep_flags, S.dmin, S.arg, nullptr);
         mark();
+        if (prof && rc == 0) {
+            int64_t evald = 0, total = 0;
+            sio_ctx_last_prune_stats(c, &evald, &total);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[ev.size() - 2], ev[ev.size() - 1]);
+            fprintf(stderr, "[sio lockstep] sweep: %lld problems, %.2f ms, %lld of %lld sub-tiles evaluated (%.2f%%), %.0f G point-queries/s resolved\n",
+                    (long long)n, ms, (long long)evald, (long long)total, total ? 100.0 * evald / total : 0.0, n * (double)N / ms * 1e-6);
+        }
         return rc;
     };
     std::vector<size_t> qp_marks;

@@ -12,7 +12,7 @@
 namespace sio {
 
 // ---- finalize: one CTA per transform (+ extra CTAs re-checking the under-bound candidates) -------------------
-constexpr int kFinThreads = 512;
+constexpr int kFinThreads = 256;
 constexpr int kSubPts = 32 * kPtsPerThread;      // points per sub-tile (128)
 constexpr int kFinSubs = kFinThreads / kSubPts;  // sub-tiles evaluated per pass (4)
 constexpr int kMaxList = 512;

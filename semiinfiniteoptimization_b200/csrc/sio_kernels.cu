@@ -345,15 +345,21 @@ void launch_min_f32(const MinArgs& a, cudaStream_t st) {
 //   k_prune_centres : lb[b][s] and ub[b]       (one query per (transform, sub-tile))
 //   k_prune_select  : survivors -> work items  (compaction)
 //   k_min_items     : one warp per surviving (transform, sub-tile), persistent grid
+// lb is kept sub-tile-major, lb[s * Bp + b] (Bp = the chunk's transforms padded to whole warps): k_prune_select walks it
+// in that order so that the survivors it appends form runs sharing their points.  The CTA's 256 sub-tiles x 32
+// transforms are transposed through shared memory so that both kernels touch lb in 128-byte rows.  Every sub-tile key
+// starts at +inf here (the finalize pass never opens a sub-tile k_min_items did not evaluate).
 __global__ void __launch_bounds__(kThreads)
 k_prune_centres(const float4* __restrict__ rep, int64_t nsub, const XfRec* __restrict__ xf, int64_t b_begin, int64_t Bc,
-                float* __restrict__ lb, uint32_t* __restrict__ ub) {
+                float* __restrict__ lb, uint32_t* __restrict__ ub, uint32_t* __restrict__ subkeys) {
     __shared__ XfRec sxf[kXfChunk];
-    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ float tile[kThreads][kXfChunk + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t ntl = (nsub + kThreads - 1) / kThreads;
     const int64_t chunk = blockIdx.x / ntl;
     const int64_t tl = blockIdx.x - chunk * ntl;
     const int64_t b0 = chunk * kXfChunk;
+    const int64_t Bp = (Bc + 31) & ~(int64_t)31;
     const int nb = (int)min((int64_t)kXfChunk, Bc - b0);
     {
         const uint4* src = reinterpret_cast<const uint4*>(xf + b_begin + b0);
@@ -376,60 +382,111 @@ k_prune_centres(const float4* __restrict__ rep, int64_t nsub, const XfRec* __res
         float my = fminf(uy + 0.5f, g.hiy + 0.5f - uy) * g.hy;
         float mz = fminf(uz + 0.5f, g.hiz + 0.5f - uz) * g.hz;
         float L = r.lip + ((min3(mx, my, mz) >= p.w) ? 0.0f : 1.0f);
-        if (ok) lb[(b0 + bl) * nsub + s] = dc - L * p.w;
+        tile[tid][bl] = dc - L * p.w;
+        if (ok) subkeys[(b0 + bl) * nsub + s] = 0x7f800000u;
         uint32_t k = __reduce_min_sync(0xffffffffu, ok ? fkey(dc) : 0xffffffffu);
         if (lane == 0) atomicMin(ub + b_begin + b0 + bl, k);
     }
-}
-
-// s-major enumeration: the threads of a warp look at ONE sub-tile under 32 consecutive transforms, so the
-// survivors they append (warp-aggregated atomic -> consecutive slots) form runs that share their points
-__global__ void k_prune_select(const float* __restrict__ lb, const uint32_t* __restrict__ ub, const double* __restrict__ bound,
-                               int64_t nsub, int64_t b_begin, int64_t Bc, float tau, uint32_t* __restrict__ subkeys,
-                               uint32_t* __restrict__ items, uint32_t* __restrict__ item_count) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t Bp = (Bc + 31) & ~(int64_t)31;            // transforms padded to whole warps
-    if (t >= Bp * nsub) return;
-    const int64_t s = t / Bp;
-    const int64_t bl = t - s * Bp;
-    if (bl >= Bc) return;
-    const int64_t b = b_begin + bl;
-    const int64_t e = bl * nsub + s;
-    float thr = fkey_inv(ub[b]);
-    if (bound) {
-        double bd = bound[b];
-        if (bd < (double)INFINITY) thr = fmaxf(thr, __double2float_ru(bd));
+    __syncthreads();
+    for (int row = warp; row < kThreads; row += kThreads / 32) {
+        const int64_t sr = tl * kThreads + row;
+        if (sr < nsub && lane < nb) lb[sr * Bp + b0 + lane] = tile[row][lane];
     }
-    if (lb[e] <= thr + 2.0f * tau) items[atomicAdd(item_count, 1u)] = (uint32_t)e;
-    else subkeys[e] = 0x7f800000u;               // +inf: the finalize pass never opens this sub-tile
 }
 
-constexpr int kItemRun = 8;      // consecutive work items taken by one warp (they mostly share a sub-tile)
+// sub-tile-major enumeration: the threads of a warp look at ONE sub-tile under 32 consecutive transforms, so the
+// survivors they append (one atomic per warp -> consecutive slots) form runs that share their points
+constexpr int kSelectRows = 16;   // sub-tiles one CTA of k_prune_select walks for its 256 transforms
+__global__ void __launch_bounds__(256)
+k_prune_select(const float* __restrict__ lb, const uint32_t* __restrict__ ub, const double* __restrict__ bound,
+               int64_t nsub, int64_t b_begin, int64_t Bc, float tau, uint32_t* __restrict__ items,
+               uint32_t* __restrict__ item_count) {
+    const int64_t Bp = (Bc + 31) & ~(int64_t)31;            // transforms padded to whole warps
+    const int64_t bl = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool valid = bl < Bc;                             // no early exit: the CTA synchronises below
+    float thr = -INFINITY;                                  // this transform's pruning threshold, once
+    if (valid) {
+        const int64_t b = b_begin + bl;
+        thr = fkey_inv(ub[b]);
+        if (bound) {
+            double bd = bound[b];
+            if (bd < (double)INFINITY) thr = fmaxf(thr, __double2float_ru(bd));
+        }
+        thr += 2.0f * tau;
+    }
+    // survivors of the CTA's 16 sub-tiles x 256 transforms go out sub-tile by sub-tile behind ONE atomic: per-warp
+    // atomics on the single counter serialise in L2 (2 M of them per chunk were the whole cost of this kernel)
+    __shared__ uint32_t cnt[kSelectRows * 8];
+    __shared__ uint32_t cta_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t s0 = blockIdx.y * (int64_t)kSelectRows;
+    uint32_t masks[kSelectRows];
+#pragma unroll
+    for (int r = 0; r < kSelectRows; ++r) {
+        const int64_t s = s0 + r;
+        const bool keep = valid && s < nsub && lb[s * Bp + bl] <= thr;
+        masks[r] = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) cnt[r * 8 + warp] = __popc(masks[r]);
+    }
+    __syncthreads();
+    if (warp == 0) {                                        // exclusive scan of the 128 counts, row-major
+        uint32_t v[4], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[j] = cnt[lane * 4 + j]; sum += v[j]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { cnt[lane * 4 + j] = run; run += v[j]; }
+        if (lane == 31) cta_base = incl ? atomicAdd(item_count, incl) : 0u;
+    }
+    __syncthreads();
+    const uint32_t base = cta_base;
+#pragma unroll
+    for (int r = 0; r < kSelectRows; ++r)
+        if (masks[r] >> lane & 1u)
+            items[base + cnt[r * 8 + warp] + __popc(masks[r] & ((1u << lane) - 1u))] = (uint32_t)(bl * nsub + (s0 + r));
+}
+
+constexpr int kItemRun = 16;     // consecutive work items taken by one warp (they mostly share a sub-tile)
 
 __global__ void __launch_bounds__(kThreads, 4)
 k_min_items(const float4* __restrict__ pts, const float4* __restrict__ rep, const XfRec* __restrict__ xf, int64_t b_begin,
             int64_t nsub, const uint32_t* __restrict__ items, const uint32_t* __restrict__ item_count,
             uint32_t* __restrict__ subkeys, Cand* __restrict__ cand, uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
-    __shared__ XfRec sxf[kThreads / 32];
+    __shared__ XfRec sxf[kThreads / 32][kItemRun];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n = *item_count;
     const uint32_t nwarps = gridDim.x * (kThreads / 32);
+    const uint32_t nsub32 = (uint32_t)nsub;
+    constexpr int kRecParts = (int)(sizeof(XfRec) / 16);
     float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
     float4 sphere = make_float4(0.f, 0.f, 0.f, 0.f);
-    int64_t have = -1;                                     // sub-tile whose points sit in registers
+    uint32_t have = 0xffffffffu;                           // sub-tile whose points sit in registers
     for (uint32_t it0 = (blockIdx.x * (kThreads / 32) + warp) * kItemRun; it0 < n; it0 += nwarps * kItemRun) {
-        const uint32_t it1 = min(n, it0 + kItemRun);
-        for (uint32_t it = it0; it < it1; ++it) {
-            const uint32_t e = __ldg(items + it);
-            const int64_t bl = e / nsub;
-            const int64_t s = e - bl * nsub;
-            const int64_t b = b_begin + bl;
-            __syncwarp();
-            if (lane < (int)(sizeof(XfRec) / 16))
-                reinterpret_cast<uint4*>(&sxf[warp])[lane] = __ldg(reinterpret_cast<const uint4*>(xf + b) + lane);
-            __syncwarp();
-            const XfRec& r = sxf[warp];
-            const int64_t base = s * (32 * kPtsPerThread);
+        // the run's items and transform records arrive together: one dependent round trip per run, not per item
+        const int cnt = (int)min(n - it0, (uint32_t)kItemRun);
+        const uint32_t e_l = lane < cnt ? __ldg(items + it0 + lane) : 0u;
+        __syncwarp();
+#pragma unroll
+        for (int q0 = 0; q0 < kItemRun * kRecParts; q0 += 32) {
+            const int q = q0 + lane, rec = q / kRecParts;
+            const uint32_t e = __shfl_sync(0xffffffffu, e_l, rec & (kItemRun - 1));
+            if (rec < cnt)
+                reinterpret_cast<uint4*>(&sxf[warp][rec])[q - rec * kRecParts] =
+                    __ldg(reinterpret_cast<const uint4*>(xf + b_begin + e / nsub32) + (q - rec * kRecParts));
+        }
+        __syncwarp();
+        for (int i = 0; i < cnt; ++i) {
+            const uint32_t e = __shfl_sync(0xffffffffu, e_l, i);
+            const uint32_t bl = e / nsub32;
+            const uint32_t s = e - bl * nsub32;
+            const XfRec& r = sxf[warp][i];
+            const int64_t base = (int64_t)s * (32 * kPtsPerThread);
             if (s != have) {
 #pragma unroll
                 for (int j = 0; j < kPtsPerThread; ++j) {
@@ -441,9 +498,9 @@ k_min_items(const float4* __restrict__ pts, const float4* __restrict__ rep, cons
             }
             float m;
             if (sphere_in_lattice(r, sphere))      // warp-uniform: every lane tests the same sphere and record
-                m = warp_subtile_min<true>(r, grid_of(r), px, py, pz, (int32_t)b, (int32_t)base, lane, cand, cand_count, cand_cap);
+                m = warp_subtile_min<true>(r, grid_of(r), px, py, pz, (int32_t)(b_begin + bl), (int32_t)base, lane, cand, cand_count, cand_cap);
             else
-                m = warp_subtile_min<false>(r, grid_of(r), px, py, pz, (int32_t)b, (int32_t)base, lane, cand, cand_count, cand_cap);
+                m = warp_subtile_min<false>(r, grid_of(r), px, py, pz, (int32_t)(b_begin + bl), (int32_t)base, lane, cand, cand_count, cand_cap);
             if (lane == 0) subkeys[e] = __float_as_uint(m);
         }
     }
@@ -454,10 +511,10 @@ void launch_min_pruned(const MinArgs& a, cudaStream_t st) {
     const int64_t nsub = (int64_t)a.ntiles * (kThreads / 32);
     const int64_t ntl = (nsub + kThreads - 1) / kThreads;
     const int64_t nchunks = (a.Bc + kXfChunk - 1) / kXfChunk;
-    k_prune_centres<<<(unsigned)(nchunks * ntl), kThreads, 0, st>>>(a.rep, nsub, a.xf, a.b_begin, a.Bc, a.lb, a.ub);
-    const int64_t ne = ((a.Bc + 31) & ~(int64_t)31) * nsub;
-    k_prune_select<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(a.lb, a.ub, a.under_bound, nsub, a.b_begin, a.Bc, (float)a.tau,
-                                                                  a.subkeys, a.items, a.item_count);
+    k_prune_centres<<<(unsigned)(nchunks * ntl), kThreads, 0, st>>>(a.rep, nsub, a.xf, a.b_begin, a.Bc, a.lb, a.ub, a.subkeys);
+    const int64_t Bp = (a.Bc + 31) & ~(int64_t)31;
+    k_prune_select<<<dim3((unsigned)((Bp + 255) / 256), (unsigned)((nsub + kSelectRows - 1) / kSelectRows)), 256, 0, st>>>(
+        a.lb, a.ub, a.under_bound, nsub, a.b_begin, a.Bc, (float)a.tau, a.items, a.item_count);
     k_min_items<<<148 * 4, kThreads, 0, st>>>(a.pts, a.rep, a.xf, a.b_begin, nsub, a.items, a.item_count, a.subkeys, a.cand,
                                               a.cand_count, a.cand_cap);
 }
