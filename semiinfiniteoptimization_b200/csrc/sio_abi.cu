@@ -347,7 +347,11 @@ int sio_cloud_create(sio_ctx* c, const float* xyz, int64_t n, sio_handle* out) {
     DeviceGuard guard(c->device);
     CloudH p;
     p.n = n;
-    // Morton order (one-off, host): warps of the bulk kernels then touch spatially coherent cells
+    // Point order (one-off, host).  Sub-tiles of 128 consecutive points are the unit of the bulk kernels (one warp) and
+    // of the culling (one bounding sphere), so they must be spatially tight: a k-d ordering -- median splits along the
+    // longest axis, left halves sized in whole sub-tiles -- down to leaves of 128, Morton order inside a leaf so that the
+    // lanes of a warp touch neighbouring cells.  (Plain Morton chunks straddle the curve's jumps: on the C5 scene 15 %
+    // of them had radii above 15 cm, up to 1.9 m, and survived every cull; k-d leaves: 3 %, at most 0.35 m.)
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int64_t i = 0; i < n; ++i)
         for (int a = 0; a < 3; ++a) {
@@ -364,7 +368,32 @@ int sio_cloud_create(sio_ctx* c, const float* xyz, int64_t n, sio_handle* out) {
         for (int a = 0; a < 3; ++a) q[a] = (uint32_t)std::min(2097151.0, std::max(0.0, (xyz[3 * i + a] - lo[a]) * sc));
         keys[i] = {morton3(q[0], q[1], q[2]), (int32_t)i};
     }
-    std::sort(keys.begin(), keys.end());
+    {
+        const int64_t leaf = 32 * kPtsPerThread;
+        std::vector<std::pair<int64_t, int64_t>> todo;
+        if (n > 0) todo.push_back({0, n});
+        while (!todo.empty()) {
+            const int64_t a0 = todo.back().first, a1 = todo.back().second;
+            todo.pop_back();
+            if (a1 - a0 <= leaf) { std::sort(keys.begin() + a0, keys.begin() + a1); continue; }
+            float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int64_t i = a0; i < a1; ++i)
+                for (int a = 0; a < 3; ++a) {
+                    const float v = xyz[3 * (int64_t)keys[i].second + a];
+                    blo[a] = std::min(blo[a], v); bhi[a] = std::max(bhi[a], v);
+                }
+            int ax = 0;
+            for (int a = 1; a < 3; ++a) if (bhi[a] - blo[a] > bhi[ax] - blo[ax]) ax = a;
+            const int64_t left = std::min(a1 - a0 - 1, ((a1 - a0) / 2 + leaf - 1) / leaf * leaf);
+            std::nth_element(keys.begin() + a0, keys.begin() + a0 + left, keys.begin() + a1,
+                             [&](const std::pair<uint64_t, int32_t>& u, const std::pair<uint64_t, int32_t>& v) {
+                                 const float fu = xyz[3 * (int64_t)u.second + ax], fv = xyz[3 * (int64_t)v.second + ax];
+                                 return fu < fv || (fu == fv && u.second < v.second);
+                             });
+            todo.push_back({a0 + left, a1});
+            todo.push_back({a0, a0 + left});
+        }
+    }
     const int64_t npad = ((n + kTile - 1) / kTile) * kTile;
     std::vector<float4> pts((size_t)std::max<int64_t>(npad, 1));
     p.perm.resize((size_t)std::max<int64_t>(npad, 1), -1);
