@@ -261,7 +261,9 @@ def sip_leg(ctx, rank, world, want_cpu):
     from semiinfiniteoptimization_b200._host import se3
     poses = np.array([se3.to_rowmajor12(T) for T in poses[lo:hi]])            # this rank's poses as a (B, 12) row-major array
     lo, hi = 0, len(poses)
-    batch.optimizeCollFreeBatchDevice(cube, scene, poses[lo:lo + 64])          # warm-up (allocations, first launches)
+    warm = sip.SemiInfiniteOptimizationSettings()
+    warm.max_iters = 1
+    batch.optimizeCollFreeBatchDevice(cube, scene, poses, settings=warm)       # warm-up: first launches, scratch sized for the shard
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()

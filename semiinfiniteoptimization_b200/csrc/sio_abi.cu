@@ -117,6 +117,7 @@ struct sio_ctx {
     int64_t scratch_limit = (int64_t)(256u << 20);   // bytes of sub-tile minima kept per K2 batch (sio_ctx_set_scratch_limit)
     int64_t qp_iters_total = 0, qp_iters_max = 0, qp_at_limit = 0;      // ADMM iterations of the last sio_sip_step_qp call, summed over problems
     DevBuf s_qp;                     // per-warp polish scratch + work counter of the SIP-step QP kernel
+    DevBuf s_ls;                     // per-problem state of the lock-step solver (sio_lockstep_pose_solve)
     HostBuf h_icnt;
     int n_icnt = 0;                   // batches of the last pruned call (their survivor counts sit in h_icnt)
     int64_t prune_total = 0;          // (transform, sub-tile) pairs of the last pruned call
@@ -208,7 +209,7 @@ int sio_ctx_destroy(sio_ctx* c) {
     for (auto& p : c->clouds) if (p.live) { cudaFree(p.d_pts); cudaFree(p.d_rep); cudaFree(p.d_perm); }
     for (auto& r : c->robots) if (r.live) { cudaFree(r.d_parent); cudaFree(r.d_jtype); cudaFree(r.d_tparent); cudaFree(r.d_axis); }
     c->s_qp.release();
-    c->s_lb.release(); c->s_ub.release(); c->s_items.release(); c->s_icnt.release(); c->h_icnt.release();
+    c->s_lb.release(); c->s_ub.release(); c->s_items.release(); c->s_icnt.release(); c->h_icnt.release(); c->s_ls.release();
     DevBuf* bufs[] = {&c->s_xf, &c->s_keys, &c->s_gridtab, &c->s_cand, &c->s_cnt, &c->s_in0, &c->s_in1, &c->s_in2, &c->s_in3,
                       &c->s_out0, &c->s_out1, &c->s_out2, &c->s_tlinks, &c->s_trel, &c->s_gob};
     for (auto* b : bufs) b->release();
@@ -759,9 +760,8 @@ int sio_pose_rows(sio_ctx* c, sio_handle grid, const double* T_pose, const int64
 }  // extern "C"
 namespace {
 // one device allocation carved into the solver's arrays; freed when it goes out of scope
-struct Arena {
+struct Arena {                                              // carves a context-owned buffer; frees nothing
     char* base = nullptr; size_t used = 0, cap = 0;
-    ~Arena() { if (base) cudaFree(base); }
     template <class T> T* take(size_t n) {
         used = (used + 255) / 256 * 256;
         T* p = reinterpret_cast<T*>(base + used);
@@ -802,6 +802,7 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     if (B == 0) return SIO_OK;
     DeviceGuard guard(c->device);
     cudaStream_t st = c->stream;
+    const auto entry0 = std::chrono::steady_clock::now();
     const int cap = cfg->cap;
     const int64_t N = c->clouds[cloud].n;
     LsState S{};
@@ -812,7 +813,8 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     {   // size pass on a null arena, then the real one
         Arena probe; LsState tmp{};
         size_t need = carve(probe, tmp, B, cap, [&] { probe.take<double>((size_t)N * 3); });
-        CU(cudaMalloc(&A.base, need + 4096));
+        CU(c->s_ls.ensure(need + 4096));                  // kept by the context: releasing ~350 MB per call cost tens of ms
+        A.base = c->s_ls.as<char>();
         A.cap = need + 4096;
     }
     carve(A, S, B, cap, [&] { d_cloud = A.take<double>((size_t)N * 3); });
@@ -858,6 +860,11 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
         if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); spans.push_back({label, {span_open, e}}); }
     };
     const auto wall0 = std::chrono::steady_clock::now();
+    if (prof) {
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[sio lockstep] setup (arena, staging, init) %.1f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - entry0).count());
+    }
     auto read_counters = [&]() -> cudaError_t {
         cudaError_t e = cudaMemcpyAsync(hc, S.counters, sizeof(hc), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return e;

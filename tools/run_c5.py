@@ -74,6 +74,8 @@ st = sip.SemiInfiniteOptimizationSettings(); st.max_iters = a.max_iters
 t0 = time.time()
 if a.qp == "resident":
     Tm = np.array([se3.to_rowmajor12(T) for T in mine[:nb]])
+    st1 = sip.SemiInfiniteOptimizationSettings(); st1.max_iters = 1
+    batch.optimizeCollFreeBatchDevice(cube, scene, Tm, settings=st1)              # first launches; scratch sized for the batch
     t0 = time.time()
     res = batch.optimizeCollFreeBatchDevice(cube, scene, Tm, settings=st)
 elif a.qp in ("device", "host"):
