@@ -284,6 +284,7 @@ def sip_leg(ctx, rank, world, want_cpu):
                        "solver (sio_lockstep_pose_solve); wall clock from host poses (row-major 3x4 array) to host results" % (SIP_PROBLEMS, world),
            "outer_iterations": int(rec[0].item()), "wall_s": wall, "sweep_device_s_per_rank": float(rec[2].item()) / world,
            "qp_device_s_per_rank": float(rec[3].item()) / world, "other_s_per_rank": wall - float(rec[2].item() + rec[3].item()) / world,
+           "library_call_s_rank0": float(res.time),
            "oracle_point_queries_resolved": int(rec[4].item()), "started_in_collision": int(rec[6].item()),
            "ended_feasible(g>-5e-3)": int(rec[5].item())}
     if want_cpu:
