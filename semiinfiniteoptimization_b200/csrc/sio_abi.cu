@@ -886,6 +886,7 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
         return rc;
     };
     std::vector<size_t> qp_marks;
+    const int qp_max_iter = getenv("SIO_QP_MAXIT") ? atoi(getenv("SIO_QP_MAXIT")) : 4000;   // diagnostic only: OSQP's limit is 4000
     for (int it = 0; it < cfg->max_iters; ++it) {
         span_begin();
         CU(cudaMemsetAsync(S.counters, 0, 2 * sizeof(unsigned long long), st));
@@ -914,7 +915,7 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
         qp_marks.push_back(ev.size());
         if (prof) CU(cudaMemsetAsync(S.qstatus, 0, (size_t)B * 4, st));   // the kernel skips problems that are not live
         mark();
-        if (launch_sip_qp(6, B, S.qW, S.dxdes, S.qlo, S.qhi, nullptr, S.qk, cap, S.rows, S.D, L.reg, L.inflation, 1e-5, 4000, S.dx,
+        if (launch_sip_qp(6, B, S.qW, S.dxdes, S.qlo, S.qhi, nullptr, S.qk, cap, S.rows, S.D, L.reg, L.inflation, 1e-5, qp_max_iter, S.dx,
                           S.qstatus, c->s_qp.p, c->num_sms, st))
             return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: QP launch failed");
         mark();

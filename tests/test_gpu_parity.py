@@ -301,6 +301,30 @@ def test_degenerate_shapes(ctx, O):
     ctx.grid_destroy(g2)
 
 
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 1025])
+def test_tiny_and_duplicate_clouds(ctx, O, n):
+    """Clouds smaller than a sub-tile, one point over a sub-tile / tile boundary, and clouds made of copies of one point
+    (every k-d split is a tie): minimum, arg-minimum (lowest caller index on ties) and under-bound counts equal the oracle's,
+    exhaustive and pruned; the caller's point order is invisible."""
+    vg = util.sphere_grid(r=0.4, n=20, half=0.8)
+    g, G = _mk(ctx, O, vg)
+    rng = np.random.default_rng(100 + n)
+    T = util.random_poses(101, 33, rot=0.7, trans=0.4)
+    bound = np.where(np.arange(len(T)) % 2 == 0, np.inf, 0.1)
+    for kind in ("random", "copies"):
+        cloud = rng.uniform(-1.0, 1.0, (n, 3)).astype(np.float32)
+        if kind == "copies":
+            cloud[:] = cloud[0]
+        c = ctx.cloud_create(cloud)
+        assert sorted(ctx.cloud_perm(c)[:n].tolist()) == list(range(n))
+        do, ao = O.min_distance(G, cloud, T, bound=bound)
+        for flags in (F32, F32 | PRUNE, F64):
+            d, a, nu = ctx.min_distance(g, c, T, bound=bound, flags=flags)
+            assert np.array_equal(a, ao) and np.abs(d - do).max() <= 1e-12, (kind, flags)
+        ctx.cloud_destroy(c)
+    ctx.grid_destroy(g)
+
+
 def test_full_size_c2_sweep_equals_oracle(ctx, O):
     """BASELINE.json configs[1] at full size: 64 poses x 2^20 points, every pose's (dmin, argmin, n_under) against the
     oracle (float64, all host threads: 67 M queries take well under a second)."""
