@@ -41,14 +41,19 @@ def _exp_so3_batch(W):
 
 
 class BatchResult:
-    def __init__(self, B):
+    def __init__(self, B, per_problem_lists=True):
+        """per_problem_lists=False (the device-resident driver): the per-problem Python lists (`status`,
+        `instantiated_params`) are built from the returned arrays on first use -- 65,536 fresh lists cost tens of
+        milliseconds of allocation and garbage-collector scans, a tenth of the whole solve."""
+        self.B = B
         self.T = None                    # (B,12) final poses, row-major 3x4
-        self.status = ['not converged'] * B
+        self._status = ['not converged'] * B if per_problem_lists else None
+        self.status_codes = None         # (B,) int32: 1 = local optimum, 0 = not converged
         self.num_iterations = np.zeros(B, dtype=np.int64)
         self.fx = np.zeros(B)
         self.gx = np.full(B, np.inf)
         self.gx0 = np.full(B, np.inf)
-        self._params = [[] for _ in range(B)]
+        self._params = [[] for _ in range(B)] if per_problem_lists else None
         self._params_arrays = None
         self.trace = None
         self.time = 0.0
@@ -56,6 +61,16 @@ class BatchResult:
         self.time_qp = 0.0
         self.outer_iterations = 0        # sum over problems of completed outer iterations
         self.point_queries = 0           # (pose, cloud point) pairs evaluated by K2 sweeps
+
+    @property
+    def status(self):
+        if self._status is None:
+            self._status = ['local optimum' if c == 1 else 'not converged' for c in self.status_codes]
+        return self._status
+
+    @status.setter
+    def status(self, v):
+        self._status = v
 
     @property
     def instantiated_params(self):
@@ -76,7 +91,7 @@ class BatchResult:
 
     def records(self):
         """Fixed-size per-problem records for the end-of-solve gather: pose(12) gx fx iters nparams."""
-        B = len(self.status)
+        B = self.B
         rec = np.zeros((B, 16))
         rec[:, :12] = self.T
         rec[:, 12] = self.gx
@@ -615,10 +630,10 @@ def optimizeCollFreeBatchDevice(obj, env, Tinits, Tdess=None, settings=None, con
     cloud_world = env._dev.cloud32.astype(np.float64) @ Tenv[:, :3].T + Tenv[:, 3]
     t0 = time.time()
     out = ctx.lockstep_pose_solve(obj._dev.grid_h, env._dev.cloud_h, env._T12, cloud_world, Ti, Td, settings, cap=cap, sweep_flags=flags)
-    res = BatchResult(B)
+    res = BatchResult(B, per_problem_lists=False)
     res.time = time.time() - t0
     res.T = out["T"]
-    res.status = ['local optimum' if s == 1 else 'not converged' for s in out["status"]]
+    res.status_codes = out["status"]
     res.num_iterations = out["iterations"].astype(np.int64)
     res.fx, res.gx, res.gx0 = out["fx"], out["gx"], out["gx0"]
     res.set_params_arrays(out["params"], out["n_params"])

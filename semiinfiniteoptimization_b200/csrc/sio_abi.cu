@@ -851,7 +851,8 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     std::vector<cudaEvent_t> ev;
     auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); };
     // SIO_LS_PROFILE=1: device time of every phase of the loop, printed to stderr at the end (a development aid)
-    const bool prof = getenv("SIO_LS_PROFILE") != nullptr;
+    const bool prof = getenv("SIO_LS_PROFILE") != nullptr && atoi(getenv("SIO_LS_PROFILE")) == 1;
+    const bool prof_total = getenv("SIO_LS_PROFILE") != nullptr && !prof;      // 2: only the call's wall time, no extra syncs
     enum { kPhPre = 0, kPhPost, kPhGx, kPhStep, kPhScore, kPhCount };
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
     cudaEvent_t span_open = nullptr;
@@ -995,6 +996,9 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
         fprintf(stderr, "[sio lockstep] loop+readback wall %.1f ms: qp %.1f, sweeps %.1f, begin/values/oracle_pre %.1f, oracle_post/rows %.1f, gx %.1f, "
                         "step/values/score_pre %.1f, score_post %.1f\n", wall, qp_ms, sweep_ms, ph[kPhPre], ph[kPhPost], ph[kPhGx], ph[kPhStep], ph[kPhScore]);
     }
+    if (prof_total)
+        fprintf(stderr, "[sio lockstep] call %.1f ms (B = %lld)\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - entry0).count(), (long long)B);
     if (stats) {
         stats[0] = (int64_t)hc[2]; stats[1] = queries; stats[2] = (int64_t)(qp_ms * 1e3); stats[3] = (int64_t)hc[3];
         stats[4] = (int64_t)(sweep_ms * 1e3);
