@@ -118,6 +118,11 @@ struct sio_ctx {
     int64_t qp_iters_total = 0, qp_iters_max = 0, qp_at_limit = 0;      // ADMM iterations of the last sio_sip_step_qp call, summed over problems
     DevBuf s_qp;                     // per-warp polish scratch + work counter of the SIP-step QP kernel
     DevBuf s_ls;                     // per-problem state of the lock-step solver (sio_lockstep_pose_solve)
+    // background QP launches of the lock-step solver (the deferred stragglers): their own streams and polish scratch
+    static constexpr int kLsBack = 3, kLsRing = 8;
+    cudaStream_t ls_stream[kLsBack] = {nullptr, nullptr, nullptr};
+    DevBuf s_qpb[kLsBack];
+    cudaEvent_t ls_evA[kLsRing] = {}, ls_evB[kLsRing] = {};
     HostBuf h_icnt;
     int n_icnt = 0;                   // batches of the last pruned call (their survivor counts sit in h_icnt)
     int64_t prune_total = 0;          // (transform, sub-tile) pairs of the last pruned call
@@ -210,6 +215,8 @@ int sio_ctx_destroy(sio_ctx* c) {
     for (auto& r : c->robots) if (r.live) { cudaFree(r.d_parent); cudaFree(r.d_jtype); cudaFree(r.d_tparent); cudaFree(r.d_axis); }
     c->s_qp.release();
     c->s_lb.release(); c->s_ub.release(); c->s_items.release(); c->s_icnt.release(); c->h_icnt.release(); c->s_ls.release();
+    for (int k = 0; k < sio_ctx::kLsBack; ++k) { c->s_qpb[k].release(); if (c->ls_stream[k]) cudaStreamDestroy(c->ls_stream[k]); }
+    for (int k = 0; k < sio_ctx::kLsRing; ++k) { if (c->ls_evA[k]) cudaEventDestroy(c->ls_evA[k]); if (c->ls_evB[k]) cudaEventDestroy(c->ls_evB[k]); }
     DevBuf* bufs[] = {&c->s_xf, &c->s_keys, &c->s_gridtab, &c->s_cand, &c->s_cnt, &c->s_in0, &c->s_in1, &c->s_in2, &c->s_in3,
                       &c->s_out0, &c->s_out1, &c->s_out2, &c->s_tlinks, &c->s_trel, &c->s_gob};
     for (auto* b : bufs) b->release();
@@ -782,6 +789,7 @@ template <class F> size_t carve(Arena& A, LsState& S, int64_t B, int cap, F&& ex
     S.qW = A.take<double>(6 * B); S.qlo = A.take<double>(6 * B); S.qhi = A.take<double>(6 * B);
     S.qk = A.take<int32_t>(B); S.qstatus = A.take<int32_t>(B);
     S.list = A.take<int32_t>(B); S.counters = A.take<unsigned long long>(8);
+    S.ph = A.take<uint8_t>(B); S.mu = A.take<uint8_t>(B); S.qdef = A.take<uint8_t>(B); S.pit = A.take<int32_t>(B); S.qdone = A.take<int32_t>(B);
     S.T_rel = A.take<double>(12 * B); S.bound = A.take<double>(B); S.dmin = A.take<double>(B); S.arg = A.take<int64_t>(B);
     extra();
     return A.used;
@@ -812,12 +820,22 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     Arena A;
     {   // size pass on a null arena, then the real one
         Arena probe; LsState tmp{};
-        size_t need = carve(probe, tmp, B, cap, [&] { probe.take<double>((size_t)N * 3); });
+        size_t need = carve(probe, tmp, B, cap, [&] {
+            probe.take<double>((size_t)N * 3);
+            for (int k = 0; k < sio_ctx::kLsRing; ++k) probe.take<int32_t>(B);
+            probe.take<uint32_t>(sio_ctx::kLsRing);
+        });
         CU(c->s_ls.ensure(need + 4096));                  // kept by the context: releasing ~350 MB per call cost tens of ms
         A.base = c->s_ls.as<char>();
         A.cap = need + 4096;
     }
-    carve(A, S, B, cap, [&] { d_cloud = A.take<double>((size_t)N * 3); });
+    int32_t* dlist[sio_ctx::kLsRing];                      // problems each of the last rounds' capped QP launches gave up on
+    uint32_t* dcount = nullptr;
+    carve(A, S, B, cap, [&] {
+        d_cloud = A.take<double>((size_t)N * 3);
+        for (int k = 0; k < sio_ctx::kLsRing; ++k) dlist[k] = A.take<int32_t>(B);
+        dcount = A.take<uint32_t>(sio_ctx::kLsRing);
+    });
     S.cloud_world = d_cloud;
     S.grid = c->grids[grid].d_meta;
     CU(cudaMemcpyAsync(d_cloud, cloud_world, (size_t)N * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -845,7 +863,7 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     CU(cudaMemsetAsync(S.key, 0, (size_t)B * cap * 3 * sizeof(long long), st));
     ls_launch_init(S, L, st);
     CU(c->s_qp.ensure(sip_qp_scratch_bytes(c->num_sms)));
-    unsigned long long hc[4];
+    unsigned long long hc[5];
     int64_t queries = 0;
     // device time of the QP launches and of the sweeps, read back at the end (events per iteration)
     std::vector<cudaEvent_t> ev;
@@ -888,57 +906,97 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     };
     std::vector<size_t> qp_marks;
     const int qp_max_iter = getenv("SIO_QP_MAXIT") ? atoi(getenv("SIO_QP_MAXIT")) : 4000;   // diagnostic only: OSQP's limit is 4000
-    for (int it = 0; it < cfg->max_iters; ++it) {
+    // Deferral of QP stragglers (SIO_LS_DEFER = ADMM iteration budget of the in-line launch, 0 = off): see k_sip_qp
+    const int defer_cap = getenv("SIO_LS_DEFER") ? atoi(getenv("SIO_LS_DEFER")) : 800;   // measured best of 150 ... 1600 at 8,192 and 65,536 problems
+    const bool defer = defer_cap > 0 && defer_cap < qp_max_iter;
+    if (defer) {
+        for (int k = 0; k < sio_ctx::kLsBack; ++k) {
+            if (!c->ls_stream[k]) {                        // lowest priority: the main stream's CTAs go first when an SM frees up
+                int lo_prio = 0, hi_prio = 0;
+                CU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+                CU(cudaStreamCreateWithPriority(&c->ls_stream[k], cudaStreamNonBlocking, lo_prio));
+            }
+            CU(c->s_qpb[k].ensure(sip_qp_scratch_bytes(c->num_sms)));
+        }
+        for (int k = 0; k < sio_ctx::kLsRing; ++k) {
+            if (!c->ls_evA[k]) CU(cudaEventCreateWithFlags(&c->ls_evA[k], cudaEventDisableTiming));
+            if (!c->ls_evB[k]) CU(cudaEventCreateWithFlags(&c->ls_evB[k], cudaEventDisableTiming));
+        }
+    }
+    const int64_t max_rounds = (int64_t)cfg->max_iters * 64 + 64;    // a problem sits a few rounds out per deferred QP
+    int64_t round = 0, rounds_with_qp = 0;
+    for (;; ++round) {
+        if (round >= max_rounds) return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: no progress after %lld rounds", (long long)round);
         span_begin();
         CU(cudaMemsetAsync(S.counters, 0, 2 * sizeof(unsigned long long), st));
-        ls_launch_begin(S, it, st);
-        const bool maybe_upd = (it == 0) || ((it - 1) % 100 == 0);         // sip.py:855-870
-        if (maybe_upd) {
-            ls_launch_values(S, 0, 0, 1, st);
-            ls_launch_oracle_pre(S, L, st);
-        } else {
-            ls_launch_values(S, 0, 1, 1, st);
-        }
+        CU(cudaMemsetAsync(S.counters + 4, 0, sizeof(unsigned long long), st));
+        ls_launch_begin(S, L, st);
+        ls_launch_values(S, 0, 1, 1, st);
+        ls_launch_oracle_pre(S, L, st);                    // only problems whose iteration refreshes the oracle at x queue up
         span_end(kPhPre);
         CU(read_counters());
         if (hc[1] == 0) break;                             // no live problem left
-        if (maybe_upd) {
+        if (hc[4] == 0) {                                  // every live problem is waiting for a background QP: wait with them
+            if (!defer) return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: live problems but none taking part");
+            for (int k = 0; k < sio_ctx::kLsBack; ++k) CU(cudaStreamSynchronize(c->ls_stream[k]));
+            continue;
+        }
+        {
             const int64_t n = (int64_t)hc[0];
-            if (n > 0) { int rc = sweep(n); if (rc) return rc; }
-            span_begin();
-            ls_launch_oracle_post(S, L, n, st);
-            ls_launch_values(S, 0, 1, 0, st);              // rows only: the appended depths are the sweeps' exact minima
-            span_end(kPhPost);
+            if (n > 0) {
+                int rc = sweep(n); if (rc) return rc;
+                span_begin();
+                ls_launch_oracle_post(S, L, n, st);
+                ls_launch_values(S, 0, 1, 0, st);          // rows only: the appended depths are the sweeps' exact minima
+                span_end(kPhPost);
+            }
         }
         span_begin();
-        ls_launch_gx(S, L, it, st);
+        ls_launch_gx(S, L, st);
         span_end(kPhGx);
         qp_marks.push_back(ev.size());
-        if (prof) CU(cudaMemsetAsync(S.qstatus, 0, (size_t)B * 4, st));   // the kernel skips problems that are not live
+        if (prof) CU(cudaMemsetAsync(S.qstatus, 0, (size_t)B * 4, st));   // the kernel skips problems that are not taking part
+        const int slot = (int)(rounds_with_qp % sio_ctx::kLsRing);
+        QpDefer dfA;
+        if (defer) {
+            if (rounds_with_qp >= sio_ctx::kLsRing) CU(cudaStreamWaitEvent(st, c->ls_evB[slot], 0));   // the slot's previous list is consumed
+            CU(cudaMemsetAsync(dcount + slot, 0, sizeof(uint32_t), st));
+            dfA.list = dlist[slot]; dfA.count = dcount + slot; dfA.done = S.qdone; dfA.mark = S.qdef; dfA.busy = S.ph;
+        }
         mark();
-        if (launch_sip_qp(6, B, S.qW, S.dxdes, S.qlo, S.qhi, nullptr, S.qk, cap, S.rows, S.D, L.reg, L.inflation, 1e-5, qp_max_iter, S.dx,
-                          S.qstatus, c->s_qp.p, c->num_sms, st))
+        if (launch_sip_qp(6, B, S.qW, S.dxdes, S.qlo, S.qhi, nullptr, S.qk, cap, S.rows, S.D, L.reg, L.inflation, 1e-5,
+                          defer ? defer_cap : qp_max_iter, S.dx, S.qstatus, c->s_qp.p, c->num_sms, st, defer ? &dfA : nullptr))
             return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: QP launch failed");
         mark();
+        if (defer) {                                       // the listed problems, in full, behind the main stream's back
+            const int k = (int)(rounds_with_qp % sio_ctx::kLsBack);
+            CU(cudaEventRecord(c->ls_evA[slot], st));
+            CU(cudaStreamWaitEvent(c->ls_stream[k], c->ls_evA[slot], 0));
+            QpDefer dfB;
+            dfB.only = dlist[slot]; dfB.only_n = dcount + slot; dfB.done = S.qdone;
+            if (launch_sip_qp(6, B, S.qW, S.dxdes, S.qlo, S.qhi, nullptr, S.qk, cap, S.rows, S.D, L.reg, L.inflation, 1e-5, qp_max_iter, S.dx,
+                              S.qstatus, c->s_qpb[k].p, c->num_sms, c->ls_stream[k], &dfB))
+                return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: QP launch failed");
+            CU(cudaEventRecord(c->ls_evB[slot], c->ls_stream[k]));
+            c->launches += 1;
+        }
+        ++rounds_with_qp;
         if (prof) {                                        // per-launch ADMM iteration statistics
-            static std::vector<int32_t> hprev;
             std::vector<int32_t> hs((size_t)B), hk((size_t)B);
             CU(cudaMemcpyAsync(hs.data(), S.qstatus, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(hk.data(), S.qk, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
-            if (hprev.size() != (size_t)B) hprev.assign((size_t)B, 0);
-            long long tot = 0, mx = 0, nz = 0, lim = 0, slow = 0, both = 0, big = 0, big_it = 0, big_mx = 0;
+            long long tot = 0, mx = 0, nz = 0, lim = 0, deferred = 0, big = 0;
             for (int64_t p = 0; p < B; ++p) {
+                if (hk[p] < 0) continue;
                 const long long n = hs[p] >> 8;
-                tot += n; mx = std::max(mx, n); nz += n > 0; lim += n >= 4000;
-                if (n >= 1000) { ++slow; both += (hprev[p] >> 8) >= 1000; }
-                if (hk[p] + 6 > 32) { ++big; big_it += n; big_mx = std::max(big_mx, n); }
+                tot += n; mx = std::max(mx, n); ++nz; lim += n >= 4000; deferred += (hs[p] & 0xff) == 4;
+                big += hk[p] + 6 > 32;
             }
-            hprev = hs;
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ev[ev.size() - 2], ev[ev.size() - 1]);
-            fprintf(stderr, "[sio lockstep] it %d: qp %.2f ms, %lld problems, %lld ADMM its (max %lld, %lld at limit, %lld slow of which %lld were slow before; "
-                            "%lld with 2 rows/lane: %lld its, max %lld)\n", it, ms, nz, tot, mx, lim, slow, both, big, big_it, big_mx);
+            fprintf(stderr, "[sio lockstep] round %lld: qp %.2f ms, %lld problems (%lld with 2 rows/lane), %lld ADMM its (max %lld, %lld at limit), %lld deferred\n",
+                    (long long)round, ms, nz, big, tot, mx, lim, deferred);
         }
         span_begin();
         ls_launch_step(S, L, st);
@@ -955,6 +1013,8 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
         c->launches += 8;
         CU(cudaGetLastError());
     }
+    if (defer)
+        for (int k = 0; k < sio_ctx::kLsBack; ++k) CU(cudaStreamSynchronize(c->ls_stream[k]));
     CU(read_counters());
     // results
     std::vector<double> hR((size_t)B * 9), ht((size_t)B * 3);

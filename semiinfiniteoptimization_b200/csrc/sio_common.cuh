@@ -121,10 +121,18 @@ void launch_chain_rows(RobotDev r, const GridDev* grids, const int32_t* link_gri
 // the strict QPs of one lock-step SIP iteration, one warp per problem (sio_qp.cu); returns -1 for an unsupported n
 size_t sip_qp_scratch_bytes(int num_sms);
 // rows of problem p: offs[p] .. offs[p+1] (ragged), or -- offs == NULL -- cnt[p] rows at p * stride (cnt[p] < 0: skipped)
+// deferral of slow problems (see k_sip_qp): list/count/done set = capped launch that lists the problems it gave up on;
+// only/only_n/done set = follow-up launch over exactly those problems
+struct QpDefer {
+    int32_t* list = nullptr; uint32_t* count = nullptr; int32_t* done = nullptr;
+    uint8_t* mark = nullptr;            // capped launch: mark[p] = 1 for every problem it lists (nobody else writes it)
+    const uint8_t* busy = nullptr;      // capped launch: problems with busy[p] == 1 are out with an earlier follow-up launch
+    const int32_t* only = nullptr; const uint32_t* only_n = nullptr;
+};
 int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, const double* xmin, const double* xmax,
                   const int64_t* offs, const int32_t* cnt, int32_t stride, const double* rows, const double* depths, double reg,
                   double inflation, double eps_abs, int max_iter, double* dx, int32_t* status, void* scratch, int num_sms,
-                  cudaStream_t st);
+                  cudaStream_t st, const QpDefer* defer = nullptr);
 // mesh -> unsigned distance at every cell centre (sio_sdf.cu); tri = [nt][9] doubles
 void launch_mesh_distance(const double* tri, int32_t nt, const double bmin[3], const double h[3], const int32_t dims[3],
                           double* out, cudaStream_t st);

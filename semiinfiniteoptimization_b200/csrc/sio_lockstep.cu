@@ -100,12 +100,24 @@ __device__ int instantiate(const LsState& S, int64_t p, const double* y, double 
 }
 
 // ---- kernels --------------------------------------------------------------------------------------------------
-__global__ void k_ls_begin(LsState S, int it) {
+// Round bookkeeping.  Problems advance through their OWN outer iterations (pit): one whose QP was handed to the
+// background launch (ph = 1) sits rounds out until the answer flag is up, then joins the next round at the step
+// phase (ph = 2); everything a problem does, and the order it does it in, is what the plain lock-step loop did.
+__global__ void k_ls_begin(LsState S, LsSettings cfg) {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= S.B || !S.live[p]) return;
+    if (S.ph[p] == 1) {
+        if (*reinterpret_cast<volatile int32_t*>(S.qdone + p)) { S.ph[p] = 2; atomicAdd(S.counters + 4, 1ull); }
+        atomicAdd(S.counters + 1, 1ull);
+        return;
+    }
+    const int it = S.pit[p];
+    if (it >= cfg.max_iters) { S.live[p] = 0; return; }    // out of iterations: stays 'not converged'
     S.niter[p] = it;
+    S.mu[p] = (it == 0) || ((it - 1) % 100 == 0);          // sip.py:855-870
     objective(S.Rdes + 9 * p, S.tdes + 3 * p, S.R + 9 * p, S.t + 3 * p, S.dxdes + 6 * p);
     atomicAdd(S.counters + 1, 1ull);
+    atomicAdd(S.counters + 4, 1ull);
 }
 
 // value (and Jacobian row) of every instantiated parameter at the current (next = 0) or proposed (next = 1) pose;
@@ -117,7 +129,7 @@ __global__ void k_ls_values(LsState S, int next, int want_rows, int write_d) {
     const int64_t p = e / S.cap;
     const int slot = (int)(e - p * S.cap);
     double* out = next ? S.Dn : S.D;
-    const bool active = next ? S.go[p] : S.live[p];
+    const bool active = next ? S.go[p] : (S.live[p] && S.ph[p] == 0 && (write_d || S.mu[p]));
     if (!active) return;
     if (slot >= S.cnt[p]) { if (write_d) out[e] = INFINITY; return; }
     double T[12], Ti[12];
@@ -145,7 +157,7 @@ __global__ void k_ls_values(LsState S, int next, int want_rows, int write_d) {
 // oracle at x, first half (sip.py:201-219): drop parameters at or above the drop value, queue the problem for a sweep
 __global__ void k_ls_oracle_pre(LsState S, LsSettings cfg) {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= S.B || !S.live[p] || !S.upd[p]) return;
+    if (p >= S.B || !S.live[p] || S.ph[p] != 0 || !S.mu[p] || !S.upd[p]) return;
     double* D = S.D + p * S.cap;
     double* P = S.P + p * S.cap * 3;
     long long* K = S.key + p * S.cap * 3;
@@ -179,10 +191,13 @@ __global__ void k_ls_oracle_post(LsState S, LsSettings cfg, int64_t count) {
 }
 
 // depths -> g(x), first-iteration bookkeeping, the oracle schedule, and the QP inputs of the problem
-__global__ void k_ls_gx(LsState S, LsSettings cfg, int it) {
+__global__ void k_ls_gx(LsState S, LsSettings cfg) {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= S.B) return;
     if (!S.live[p]) { S.qk[p] = -1; return; }
+    if (S.ph[p] != 0) { if (S.ph[p] == 2) S.qk[p] = -1; return; }     // ph = 1: the background launch still reads qk
+    S.qdef[p] = 0;
+    const int it = S.pit[p];
     const double g = row_min(S.D + p * S.cap, S.cnt[p]);
     S.gxc[p] = g;
     if (it == 0) {
@@ -199,13 +214,15 @@ __global__ void k_ls_step(LsState S, LsSettings cfg) {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= S.B) return;
     S.go[p] = 0;
-    if (!S.live[p]) return;
+    if (!S.live[p] || S.ph[p] == 1) return;
+    if (S.ph[p] == 0 && S.qdef[p]) { S.ph[p] = 1; return; }    // deferred: the answer comes from the background launch
     const double* dx = S.dx + 6 * p;
     double n2 = 0.0;
     for (int i = 0; i < 6; ++i) n2 += dx[i] * dx[i];
     if (n2 < cfg.xeps2) {
         S.status[p] = 1;
         S.live[p] = 0;
+        S.ph[p] = 0;
         S.gx[p] = S.gxc[p];
         return;
     }
@@ -264,6 +281,8 @@ __global__ void k_ls_score_post(LsState S, LsSettings cfg, int64_t count) {
     }
     const double scale = 0.75 * ((atan(S.gx[p] * 3) * 2 / 3.141592653589793 + 0.5) * 1.75 + 0.25);
     S.w[p] = fmax(S.w[p] * scale, cfg.w_min);
+    S.ph[p] = 0;
+    S.pit[p] += 1;
     atomicAdd(S.counters + 2, 1ull);
 }
 
@@ -271,6 +290,7 @@ __global__ void k_ls_init(LsState S, LsSettings cfg) {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= S.B) return;
     S.cnt[p] = 0; S.w[p] = cfg.w0; S.trs[p] = 0.5; S.upd[p] = 1; S.live[p] = 1; S.go[p] = 0;
+    S.ph[p] = 0; S.mu[p] = 1; S.qdef[p] = 0; S.pit[p] = 0; S.qdone[p] = 0; S.qstatus[p] = 0;
     S.min_cv[p] = cfg.min_cv; S.status[p] = 0; S.niter[p] = 0;
     S.gx[p] = INFINITY; S.gx0[p] = INFINITY; S.gxc[p] = INFINITY;
     S.fx[p] = objective(S.Rdes + 9 * p, S.tdes + 3 * p, S.R + 9 * p, S.t + 3 * p, nullptr);
@@ -279,7 +299,7 @@ __global__ void k_ls_init(LsState S, LsSettings cfg) {
 static unsigned grid_for(int64_t n) { return (unsigned)((n + kLsThreads - 1) / kLsThreads); }
 
 void ls_launch_init(const LsState& S, const LsSettings& c, cudaStream_t st) { k_ls_init<<<grid_for(S.B), kLsThreads, 0, st>>>(S, c); }
-void ls_launch_begin(const LsState& S, int it, cudaStream_t st) { k_ls_begin<<<grid_for(S.B), kLsThreads, 0, st>>>(S, it); }
+void ls_launch_begin(const LsState& S, const LsSettings& c, cudaStream_t st) { k_ls_begin<<<grid_for(S.B), kLsThreads, 0, st>>>(S, c); }
 void ls_launch_values(const LsState& S, int next, int want_rows, int write_d, cudaStream_t st) {
     k_ls_values<<<grid_for(S.B * S.cap), kLsThreads, 0, st>>>(S, next, want_rows, write_d);
 }
@@ -287,7 +307,7 @@ void ls_launch_oracle_pre(const LsState& S, const LsSettings& c, cudaStream_t st
 void ls_launch_oracle_post(const LsState& S, const LsSettings& c, int64_t n, cudaStream_t st) {
     if (n > 0) k_ls_oracle_post<<<grid_for(n), kLsThreads, 0, st>>>(S, c, n);
 }
-void ls_launch_gx(const LsState& S, const LsSettings& c, int it, cudaStream_t st) { k_ls_gx<<<grid_for(S.B), kLsThreads, 0, st>>>(S, c, it); }
+void ls_launch_gx(const LsState& S, const LsSettings& c, cudaStream_t st) { k_ls_gx<<<grid_for(S.B), kLsThreads, 0, st>>>(S, c); }
 void ls_launch_step(const LsState& S, const LsSettings& c, cudaStream_t st) { k_ls_step<<<grid_for(S.B), kLsThreads, 0, st>>>(S, c); }
 void ls_launch_score_pre(const LsState& S, cudaStream_t st) { k_ls_score_pre<<<grid_for(S.B), kLsThreads, 0, st>>>(S); }
 void ls_launch_score_post(const LsState& S, const LsSettings& c, int64_t n, cudaStream_t st) {

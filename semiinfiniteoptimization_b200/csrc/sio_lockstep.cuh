@@ -20,19 +20,24 @@ struct LsState {
     double *D, *Dn, *rows;
     double *w, *trs, *fx, *gx, *gx0, *min_cv, *gxc;
     uint8_t *upd, *live, *go;
+    uint8_t *ph, *mu, *qdef;                 // ph: 0 = takes part in the round, 1 = QP running in the background, 2 = its QP answer arrived (joins at the step);
+                                      // qdef: the round's capped QP launch handed the problem to the background launch;
+                                      // mu: this iteration of the problem is one that may refresh the oracle at x (sip.py:855-870)
+    int32_t *pit, *qdone;             // the problem's own outer-iteration index (a problem skips rounds while its QP is out); QP-answer flag
     int32_t *status, *niter, *ninst0;
     double *dxdes, *dx, *Rn, *tn, *fxn, *gxn, *sorig, *metric;
     double *qW, *qlo, *qhi; int32_t* qk; int32_t* qstatus;
-    int32_t* list; unsigned long long* counters;      // [0] sweep list length, [1] live problems, [2] outer iterations, [3] slot overflows
+    int32_t* list; unsigned long long* counters;      // [0] sweep list length, [1] live problems, [2] outer iterations, [3] slot overflows,
+                                                      // [4] problems doing anything this round
     double *T_rel, *bound, *dmin; int64_t* arg;
 };
 
 void ls_launch_init(const LsState& S, const LsSettings& c, cudaStream_t st);
-void ls_launch_begin(const LsState& S, int it, cudaStream_t st);
+void ls_launch_begin(const LsState& S, const LsSettings& c, cudaStream_t st);
 void ls_launch_values(const LsState& S, int next, int want_rows, int write_d, cudaStream_t st);
 void ls_launch_oracle_pre(const LsState& S, const LsSettings& c, cudaStream_t st);
 void ls_launch_oracle_post(const LsState& S, const LsSettings& c, int64_t n, cudaStream_t st);
-void ls_launch_gx(const LsState& S, const LsSettings& c, int it, cudaStream_t st);
+void ls_launch_gx(const LsState& S, const LsSettings& c, cudaStream_t st);
 void ls_launch_step(const LsState& S, const LsSettings& c, cudaStream_t st);
 void ls_launch_score_pre(const LsState& S, cudaStream_t st);
 void ls_launch_score_post(const LsState& S, const LsSettings& c, int64_t n, cudaStream_t st);

@@ -497,14 +497,14 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
 }
 
 // status codes written per problem (low byte; the ADMM iteration count sits above it)
-enum { kQpStrict = 0, kQpSlack = 1, kQpNoRows = 2, kQpToHost = 3 };
+enum { kQpStrict = 0, kQpSlack = 1, kQpNoRows = 2, kQpToHost = 3, kQpDeferred = 4 };
 
 template <int N, int NR>
 __device__ __forceinline__ void solve_rows(int64_t p, int k, int m, int64_t base, bool box, const double* __restrict__ W,
                                            const double* __restrict__ xdes, const double* __restrict__ xmin, const double* __restrict__ xmax,
                                            const double* __restrict__ rows, const double* __restrict__ depths, double reg, double inflation,
                                            double eps_abs, double eps_rel, int max_iter, double* kkt, int lane, double* __restrict__ dx,
-                                           int32_t* __restrict__ status) {
+                                           int32_t* __restrict__ status, const QpDefer& df) {
     constexpr double kInf = 1e20;
     double Pd[N], q[N];
 #pragma unroll
@@ -551,6 +551,15 @@ __device__ __forceinline__ void solve_rows(int64_t p, int k, int m, int64_t base
     double pen = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
         const int st = admm<N, NR>(pass == 1, R, Pd, q, pen, k, m, eps_abs, eps_rel, max_iter, kkt, lane, x, sv, iters);
+        if (df.list && st == kAdmmMaxIter) {              // capped launch: out of budget -> the follow-up launch solves it in full
+            if (lane == 0) {
+                status[p] = kQpDeferred;
+                df.mark[p] = 1;
+                df.done[p] = 0;
+                df.list[atomicAdd(df.count, 1u)] = (int32_t)p;
+            }
+            return;
+        }
         if (pass == 1) {
             if (st == kAdmmInfeasible) { if (lane == 0) status[p] = kQpToHost; return; }
             code = kQpSlack;
@@ -572,7 +581,8 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
                               const double* __restrict__ xmax, const int64_t* __restrict__ offs, const int32_t* __restrict__ cnt,
                               int32_t stride, const double* __restrict__ rows,
                               const double* __restrict__ depths, double reg, double inflation, double eps_abs, double eps_rel,
-                              int max_iter, double* kkt, int lane, double* __restrict__ dx, int32_t* __restrict__ status) {
+                              int max_iter, double* kkt, int lane, double* __restrict__ dx, int32_t* __restrict__ status,
+                              const QpDefer& df) {
     constexpr double kInf = 1e20;
     // ragged layout: rows of problem p at offs[p] .. offs[p+1];  padded layout (lock-step solver): cnt[p] rows at
     // p * stride, cnt[p] < 0 = problem not taking part
@@ -590,27 +600,41 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
     const int m = k + (box ? N : 0);
     if (m > kQpMaxRows) { if (lane == 0) status[p] = kQpToHost; return; }
     if (m <= 32)
-        solve_rows<N, 1>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status);
+        solve_rows<N, 1>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status, df);
     else
-        solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status);
+        solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status, df);
 }
 
-// persistent warps: each draws the next problem from *counter (reset to 0 by the launcher)
+// persistent warps: each draws the next problem from *counter (reset to 0 by the launcher).
+// Deferral (the lock-step solver, QpDefer): a launch with df.list set runs every problem under a small iteration budget
+// and lists those that exhaust it; a follow-up launch with df.only set solves exactly the listed problems from scratch
+// under the real limit -- the same arithmetic as an uncapped solve -- on another stream, and raises df.done[p] when
+// problem p's answer is in memory.  A launch lasts as long as its slowest problem; this keeps the 4000-iteration
+// stragglers (0.5 % of the problems) off the critical path of the other 99.5 %.
 template <int N>
 __global__ void __launch_bounds__(kQpWarps * 32, kQpCtasPerSm)
 k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__ xdes, const double* __restrict__ xmin,
          const double* __restrict__ xmax, const int64_t* __restrict__ offs, const int32_t* __restrict__ cnt, int32_t stride,
          const double* __restrict__ rows,
          const double* __restrict__ depths, double reg, double inflation, double eps_abs, double eps_rel, int max_iter,
-         double* __restrict__ scratch, unsigned long long* __restrict__ counter, double* __restrict__ dx, int32_t* __restrict__ status) {
+         double* __restrict__ scratch, unsigned long long* __restrict__ counter, double* __restrict__ dx, int32_t* __restrict__ status,
+         QpDefer df) {
     const int lane = threadIdx.x & 31;
-    double* kkt = scratch + ((size_t)blockIdx.x * kQpWarps + (threadIdx.x >> 5)) * kQpScratch;
+    double* kkt = scratch + (blockDim.x == 32 ? (size_t)blockIdx.x : (size_t)blockIdx.x * kQpWarps + (threadIdx.x >> 5)) * kQpScratch;
+    const unsigned long long limit = df.only ? (unsigned long long)*df.only_n : (unsigned long long)nprob;
     for (;;) {
-        unsigned long long p = 0;
-        if (lane == 0) p = atomicAdd(counter, 1ull);
-        p = __shfl_sync(0xffffffffu, p, 0);
-        if (p >= (unsigned long long)nprob) return;
-        solve_problem<N>((int64_t)p, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status);
+        unsigned long long i = 0;
+        if (lane == 0) i = atomicAdd(counter, 1ull);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= limit) return;
+        const int64_t p = df.only ? (int64_t)df.only[i] : (int64_t)i;
+        if (df.busy && df.busy[p] == 1) continue;
+        solve_problem<N>(p, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status, df);
+        if (df.only) {                                     // publish: answer first, flag second
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicExch(df.done + p, 1);
+        }
     }
 }
 
@@ -621,18 +645,22 @@ size_t sip_qp_scratch_bytes(int num_sms) { return (size_t)sip_qp_grid(num_sms) *
 int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, const double* xmin, const double* xmax,
                   const int64_t* offs, const int32_t* cnt, int32_t stride, const double* rows, const double* depths, double reg,
                   double inflation, double eps_abs, int max_iter, double* dx, int32_t* status, void* scratch, int num_sms,
-                  cudaStream_t st) {
+                  cudaStream_t st, const QpDefer* defer) {
     if (nprob <= 0) return 0;
-    const int blocks = sip_qp_grid(num_sms);
+    const QpDefer df = defer ? *defer : QpDefer{};
+    // a follow-up launch over a few hundred stragglers runs beside other kernels for milliseconds: one warp per CTA, so
+    // that each straggler holds one warp's registers on its SM and not four
+    const int threads = df.only ? 32 : kQpWarps * 32;
+    const int blocks = df.only ? sip_qp_grid(num_sms) * kQpWarps : sip_qp_grid(num_sms);
     double* kkt = reinterpret_cast<double*>(scratch);
     unsigned long long* counter = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + sip_qp_scratch_bytes(num_sms) - 64);
     cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
     if (n == 6)
-        k_sip_qp<6><<<blocks, kQpWarps * 32, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, 1e-5,
-                                                      max_iter, kkt, counter, dx, status);
+        k_sip_qp<6><<<blocks, threads, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, 1e-5,
+                                                      max_iter, kkt, counter, dx, status, df);
     else if (n == 7)
-        k_sip_qp<7><<<blocks, kQpWarps * 32, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, 1e-5,
-                                                      max_iter, kkt, counter, dx, status);
+        k_sip_qp<7><<<blocks, threads, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, 1e-5,
+                                                      max_iter, kkt, counter, dx, status, df);
     else
         return -1;
     return 0;

@@ -137,6 +137,35 @@ def test_device_resident_driver_equals_array_driver(scene):
     assert dev.point_queries == ref.point_queries
 
 
+def test_deferred_qp_stragglers_do_not_change_the_answers(ctx, monkeypatch):
+    """The resident solver hands QPs that exhaust a small ADMM budget to a background launch and lets their problems sit
+    rounds out (SIO_LS_DEFER, default 800 iterations; 0 = every QP in line).  Each problem still goes through the same
+    operations in the same order, so every output is bit-identical -- here on C5 problems, a budget small enough that
+    hundreds of QPs are deferred, several times per problem."""
+    from semiinfiniteoptimization_b200 import batch, geometryopt as G, sip, workloads as W
+    from semiinfiniteoptimization_b200._host.geometry import Geometry3D, PointCloud
+    cube = G.PenetrationDepthGeometry(W.c5_cube(), 0.05, None, context=ctx)
+    scene = G.PenetrationDepthGeometry(Geometry3D(PointCloud(W.c5_scene_cloud())), None, 0.02, context=ctx)
+    poses = W.c5_poses(1536, seed=3)
+    st = sip.SemiInfiniteOptimizationSettings()
+    st.max_iters = 12
+    outs = []
+    for cap in ("0", "60", "800"):
+        monkeypatch.setenv("SIO_LS_DEFER", cap)
+        outs.append(batch.optimizeCollFreeBatchDevice(cube, scene, poses, settings=st))
+    ref = outs[0]
+    assert ref.outer_iterations > 5000
+    for got in outs[1:]:
+        assert np.array_equal(ref.T, got.T) and np.array_equal(ref.status_codes, got.status_codes)
+        assert np.array_equal(ref.num_iterations, got.num_iterations) and ref.outer_iterations == got.outer_iterations
+        assert np.array_equal(ref.fx, got.fx) and np.array_equal(ref.gx, got.gx) and np.array_equal(ref.gx0, got.gx0)
+        assert np.array_equal(ref.n_params, got.n_params) and ref.point_queries == got.point_queries
+        P0, n0 = ref._params_arrays
+        P1, _ = got._params_arrays
+        for p in range(len(poses)):
+            assert np.array_equal(P0[p, :n0[p]], P1[p, :n0[p]])
+
+
 def test_drivers_agree_on_the_c5_workload(ctx):
     """BASELINE.json configs[4] inputs (cube vs the synthetic 262,144-point scene; two thirds of the poses start in deep
     collision, so the QP's slack re-solve is the common case): 2,048 problems through the array driver with the HOST QP and
