@@ -6,7 +6,9 @@
 // per-problem bookkeeping in numpy on the host; at 65,536 problems that host work is most of the wall time.  Here the
 // bookkeeping is kernels too (one thread per problem): objective / step (so3 log and exp maps), the oracle's drop rule
 // and exclusion hash (sip.py:203-213, 280-285), merit score, trust region and weight schedule (sip.py:1159-1215).  The
-// host only sequences launches and reads two counters per iteration (live problems, problems entering a sweep).
+// host only sequences launches and reads a few counters per round (live problems, problems entering a sweep).
+// Rounds are not outer iterations: a problem whose QP went to the background launch (see k_sip_qp) skips rounds and keeps
+// its own iteration index, so the slowest QP of a round delays one problem, not all of them.
 // Heavy lifting is the existing kernels: K2 sweeps (sio_min_distance_dev), the QPs (k_sip_qp on the padded layout),
 // and value / Jacobian-row evaluation of the instantiated parameters (same arithmetic as k_pose_rows).
 //
