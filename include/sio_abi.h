@@ -164,8 +164,10 @@ int sio_robot_pairs_min_distance(sio_ctx* ctx, sio_handle robot, const sio_handl
  * coordinates, caller order).  T_init / T_des / T_out are row-major 3x4 poses of the moving body.
  * Per problem: status (1 = 'local optimum', 0 = iteration limit), iterations, f(x), g(x) = min over instantiated
  * parameters, g at the start, number of instantiated parameters and (optional) the parameters themselves
- * [B*cap*3].  stats[0..4] = outer iterations, point queries resolved by the sweeps, device microseconds in the QP
- * launches, parameters that did not fit into `cap` slots, device microseconds in the sweeps. */
+ * [B*cap*3].  stats[0..4] = outer iterations, point queries resolved by the sweeps, device microseconds in the in-line
+ * QP launches, parameters that did not fit into `cap` slots, device microseconds in the sweeps.
+ * Problems advance independently: a QP that exhausts a small ADMM budget is finished by a background launch while
+ * its problem sits rounds out (environment SIO_LS_DEFER = budget, default 800, 0 = off); outputs do not depend on it. */
 typedef struct {
     int32_t max_iters;                     /* sip.py:65   (50) */
     int32_t cap;                           /* parameter slots per problem (<= 58: the device QP takes 64 rows) */

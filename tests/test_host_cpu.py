@@ -304,3 +304,19 @@ def test_native_batched_qp_equals_scalar_qp():
         ref = cd.solve_qp_osqp(W[p], xdes[p], list(rows[offs[p]:offs[p + 1]]), list(depths[offs[p]:offs[p + 1]]), -trs[p], trs[p],
                                regularizationFactor=1e-3)
         assert np.abs(ref - dx[p]).max() <= 1e-8
+
+
+def test_batch_result_builds_its_lists_on_first_use():
+    """The device-resident driver returns arrays; the per-problem Python lists of the reference's result format
+    (status strings, instantiated parameters) are derived from them on first use."""
+    from semiinfiniteoptimization_b200.batch import BatchResult
+    r = BatchResult(4, per_problem_lists=False)
+    r.T = np.zeros((4, 12))
+    r.status_codes = np.array([1, 0, 1, 0], dtype=np.int32)
+    P = np.arange(4 * 3 * 3, dtype=np.float64).reshape(4, 3, 3)
+    r.set_params_arrays(P, np.array([1, 0, 2, 3]))
+    assert r.records().shape == (4, 16) and list(r.records()[:, 15]) == [1, 0, 2, 3]
+    assert r.status == ['local optimum', 'not converged', 'local optimum', 'not converged']
+    assert [len(p) for p in r.instantiated_params] == [1, 0, 2, 3] and r.instantiated_params[2][1] == list(P[2, 1])
+    eager = BatchResult(2)
+    assert eager.status == ['not converged'] * 2 and eager.instantiated_params == [[], []]
