@@ -409,7 +409,12 @@ def main():
     launches = launches_per_step * args.steps
     ms_steps = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(ms_steps)) + gather_ms          # K sweeps + the one gather of the interval
+    per_rank = None
     if world > 1:
+        mine = torch.tensor([float(sum(ms_steps)), gather_ms], dtype=torch.float64, device="cuda")
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)                       # diagnostics: which rank is the maximum, and why
+        per_rank = [[round(float(v[0]), 3), round(float(v[1]), 3)] for v in allr]
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
@@ -539,6 +544,7 @@ def main():
                                                  "kernel exceeds it because Morton-ordered queries reuse bricks in L1 (hit rate 54%)"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "ms_per_step_median": float(np.median(ms_steps)), "gather_ms": gather_ms,
+                "per_rank_ms[steps_sum, gather]": per_rank,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
