@@ -541,7 +541,7 @@ def main():
                                                     "the shared-memory transform records)" % (n_sm, sm_mhz)},
                     "l2_gather": {"achieved": gathered, "peak": gather_peak, "unit": "GB/s", "frac": gathered / gather_peak,
                                   "peak_source": "sio_bench_gather: random 4 B loads over an L2-resident array of the grid's size; the "
-                                                 "kernel exceeds it because Morton-ordered queries reuse bricks in L1 (hit rate 54%)"}}
+                                                 "kernel exceeds it because spatially ordered queries reuse bricks in L1 (hit rate 65%)"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "ms_per_step_median": float(np.median(ms_steps)), "gather_ms": gather_ms,
                 "per_rank_ms[steps_sum, gather]": per_rank,
