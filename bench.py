@@ -162,6 +162,7 @@ def cpu_baseline(vg, cloud, T_rel, budget_s=12.0, native=True):
         if dt >= budget_s:
             break
     return {"value": done / dt, "unit": UNIT, "cores": int(threads), "kind": "port",
+            "minvalue_calls_per_s": done / dt / len(cloud),          # one call = one pose against the whole cloud
             "sample": "%d sweeps of %d poses x %d cloud points of the same workload, float64 brute force "
                       "(no hierarchy pruning), %.1f s" % (k, npose, len(cloud), dt)}
 
@@ -544,6 +545,7 @@ def main():
                                                  "kernel exceeds it because spatially ordered queries reuse bricks in L1 (hit rate 65%)"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "ms_per_step_median": float(np.median(ms_steps)), "gather_ms": gather_ms,
+                "minvalue_calls_per_s": value / CLOUD_N,            # one call = one pose against the whole cloud
                 "per_rank_ms[steps_sum, gather]": per_rank,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
