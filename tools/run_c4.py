@@ -12,13 +12,45 @@ import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 ap = argparse.ArgumentParser(); ap.add_argument("--levels", type=int, default=8); ap.add_argument("--no-cpu", action="store_true")
+ap.add_argument("--shard", action="store_true", help="under torchrun: time samples in blocks across the ranks (SURVEY 8e, C4); "
+                                                     "checks the agreed minimum against the unsharded dense sweep and exits")
 a = ap.parse_args()
+if a.shard:
+    import torch, torch.distributed as tdist
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    if world > 1:
+        tdist.init_process_group("nccl")
 from tests import scenes
 from semiinfiniteoptimization_b200 import sip
 
 out = {"config": "C4 tx90_geom_test2.xml, chair at %s, 67 milestones" % (scenes.CHAIR_IN_PATH,)}
 mod, robot, tc, con, traj, x = scenes.c4_scene('device')
 N = con.envs[0]._dev.ctx.cloud_size(con.envs[0]._dev.cloud_h) if hasattr(con, "envs") else None
+if a.shard:
+    from semiinfiniteoptimization_b200 import geometryopt as G
+    res = {}
+    for lv in (7, a.levels):
+        con.LEVELS = lv
+        G.LIPSCHITZ_SCHEDULE = False
+        con.shard_time_blocks = False
+        con.setx(x); ref = con.minvalue(x); con.clearx()
+        con.shard_time_blocks = True
+        con.setx(x); con.minvalue(x); con.clearx()              # warm-up (NCCL, scratch)
+        ts = []
+        for _ in range(5):
+            con.setx(x)
+            if world > 1: tdist.barrier()
+            t0 = time.perf_counter(); got = con.minvalue(x); ts.append(time.perf_counter() - t0)
+            con.clearx()
+        assert got[0] == ref[0] and tuple(got[1]) == tuple(ref[1]), (got, ref)
+        res["levels_%d" % lv] = {"minvalue_ms_sharded": 1e3 * min(ts), "dmin": got[0], "param": [float(v) for v in got[1]],
+                                 "local_queries": con.last_sweep_queries}
+    if rank == 0:
+        print(json.dumps({"config": out["config"], "ranks": world, "sharded_equals_unsharded": True, **res}))
+    if world > 1:
+        tdist.destroy_process_group()
+    sys.exit(0)
 for lv in sorted({7, a.levels}):
     con.LEVELS = lv
     con.setx(x); con.minvalue(x); con.clearx()                     # warm-up
