@@ -416,6 +416,9 @@ def main():
         allr = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)                       # diagnostics: which rank is the maximum, and why
         per_rank = [[round(float(v[0]), 3), round(float(v[1]), 3)] for v in allr]
+        allc = [None] * world
+        dist.all_gather_object(allc, {"sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons"), "power_w_max": clocks.get("power_w_max")})
+        clocks = dict(clocks, per_rank=allc)               # every rank samples its own GPU during the timed region
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
