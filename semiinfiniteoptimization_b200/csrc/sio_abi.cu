@@ -866,7 +866,11 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     unsigned long long hc[5];
     int64_t queries = 0;
     // device time of the QP launches and of the sweeps, read back at the end (events per iteration)
-    std::vector<cudaEvent_t> ev;
+    struct EventBag {                                      // destroyed on every way out of the call
+        std::vector<cudaEvent_t> v;
+        ~EventBag() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
+    } ev_bag, span_bag;
+    std::vector<cudaEvent_t>& ev = ev_bag.v;
     auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); };
     // SIO_LS_PROFILE=1: device time of every phase of the loop, printed to stderr at the end (a development aid)
     const bool prof = getenv("SIO_LS_PROFILE") != nullptr && atoi(getenv("SIO_LS_PROFILE")) == 1;
@@ -874,9 +878,9 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     enum { kPhPre = 0, kPhPost, kPhGx, kPhStep, kPhScore, kPhCount };
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
     cudaEvent_t span_open = nullptr;
-    auto span_begin = [&]() { if (prof) { cudaEventCreate(&span_open); cudaEventRecord(span_open, st); } };
+    auto span_begin = [&]() { if (prof) { cudaEventCreate(&span_open); span_bag.v.push_back(span_open); cudaEventRecord(span_open, st); } };
     auto span_end = [&](int label) {
-        if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); spans.push_back({label, {span_open, e}}); }
+        if (prof) { cudaEvent_t e; cudaEventCreate(&e); span_bag.v.push_back(e); cudaEventRecord(e, st); spans.push_back({label, {span_open, e}}); }
     };
     const auto wall0 = std::chrono::steady_clock::now();
     if (prof) {
@@ -1042,7 +1046,6 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
             cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
             (is_qp[k] ? qp_ms : sweep_ms) += ms;
         }
-        for (cudaEvent_t e : ev) cudaEventDestroy(e);
     }
     if (prof) {
         double ph[kPhCount] = {0, 0, 0, 0, 0};
@@ -1050,7 +1053,6 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
             float ms = 0.f;
             cudaEventElapsedTime(&ms, sp.second.first, sp.second.second);
             ph[sp.first] += ms;
-            cudaEventDestroy(sp.second.first); cudaEventDestroy(sp.second.second);
         }
         const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
         fprintf(stderr, "[sio lockstep] loop+readback wall %.1f ms: qp %.1f, sweeps %.1f, begin/values/oracle_pre %.1f, oracle_post/rows %.1f, gx %.1f, "
