@@ -329,11 +329,20 @@ def _solve_batch(dx, idx, rows, offs, depths, dxdes, w, trs, settings, cd_helper
                 dx[k] = x[j]
 
 
-def solve_sharded(obj, env, Tinits, Tdess=None, settings=None, qp='scalar'):
+def solve_sharded(obj, env, Tinits, Tdess=None, settings=None, qp='scalar', driver='scalar'):
     """C5 across ranks: contiguous blocks of problems per rank, no collective during the solve, one
-    gather of the fixed-size per-problem records at the end."""
+    gather of the fixed-size per-problem records at the end.  driver: 'scalar'
+    (optimizeCollFreeBatch), 'fast' (optimizeCollFreeBatchFast) or 'device' (optimizeCollFreeBatchDevice).
+    Returns (records of ALL problems [pose(12) gx fx iterations nparams], this rank's BatchResult)."""
     lo, hi = dist.shard_range(len(Tinits))
-    local = optimizeCollFreeBatch(obj, env, Tinits[lo:hi], None if Tdess is None else Tdess[lo:hi], settings, qp)
+    Ti = Tinits[lo:hi]
+    Td = None if Tdess is None else Tdess[lo:hi]
+    if driver == 'device':
+        local = optimizeCollFreeBatchDevice(obj, env, Ti, Td, settings)
+    elif driver == 'fast':
+        local = optimizeCollFreeBatchFast(obj, env, Ti, Td, settings)
+    else:
+        local = optimizeCollFreeBatch(obj, env, Ti, Td, settings, qp)
     return dist.gather_records(local.records(), n_total=len(Tinits)), local
 
 

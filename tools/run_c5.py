@@ -84,16 +84,22 @@ else:
     res = batch.optimizeCollFreeBatch(cube, scene, mine[:nb], settings=st, qp=a.qp)
 wall = time.time() - t0
 rec = torch.tensor([res.outer_iterations, wall, res.time_cons, res.time_qp, res.point_queries, float((res.gx > -5e-3).sum()), nb], dtype=torch.float64, device="cuda")
+gathered = None
 if world > 1:
     mx = rec.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(rec, op=dist.ReduceOp.SUM)
     wall = float(mx[1].item())
+    # the end-of-solve exchange of SURVEY 8e: every rank's fixed-size per-problem records, in problem order
+    t1 = time.time()
+    allrec = sdist.gather_records(res.records())
+    gathered = {"records": int(allrec.shape[0]), "s": time.time() - t1}
+    assert allrec.shape == (int(rec[6].item()), 16) and int((allrec[:, 12] > -5e-3).sum()) == int(rec[5].item())
 if rank == 0 and getattr(res, "qp_iter_log", None):
     print("QP log (problems, ADMM iterations, max single, at limit):", res.qp_iter_log, file=sys.stderr)
 if rank == 0 and getattr(res, "iter_log", None):
     print("iteration log (it, live, rows, qp_s):", [(a_, b_, c_, round(d_, 4)) for a_, b_, c_, d_ in res.iter_log], file=sys.stderr)
 if rank == 0:
     out["sip"] = {"problems": int(rec[6].item()), "max_iters": a.max_iters, "qp": a.qp, "outer_iterations": int(rec[0].item()),
-                  "wall_s": wall, "solver_s": float(getattr(res, "time", 0.0) or 0.0), "iters_per_s": float(rec[0].item()) / wall, "oracle_s": float(rec[2].item()) / world,
+                  "wall_s": wall, "gather": gathered, "solver_s": float(getattr(res, "time", 0.0) or 0.0), "iters_per_s": float(rec[0].item()) / wall, "oracle_s": float(rec[2].item()) / world,
                   "qp_s": float(rec[3].item()) / world, "point_queries": int(rec[4].item()), "feasible": int(rec[5].item()),
                   "qp_host_fallbacks": getattr(res, "qp_host_fallbacks", 0), "qp_device_s": getattr(res, "time_qp_device", 0.0), "qp_admm_iterations": getattr(res, "qp_admm_iterations", 0),
                   "slot_overflows": getattr(res, "slot_overflows", 0), "max_params": int(max(getattr(res, "n_params", [len(p) for p in res.instantiated_params]))),
