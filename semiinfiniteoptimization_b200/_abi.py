@@ -389,9 +389,10 @@ _default_ctx = {}
 
 
 def default_context(device=None):
-    """Process-wide context per device (created on first use)."""
+    """Process-wide context per device (created on first use).  device=None: the GPU of this process -- LOCAL_RANK
+    under torchrun (one process per GPU), else device 0."""
     if device is None:
-        device = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("SIO_DEVICE_FROM_RANK") else 0
+        device = int(os.environ.get("LOCAL_RANK", "0"))
     if device not in _default_ctx:
         _default_ctx[device] = Context(device)
     return _default_ctx[device]
