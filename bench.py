@@ -269,7 +269,12 @@ def sip_leg(ctx, rank, world, want_cpu):
         dist.barrier()
     t0 = time.perf_counter()
     res = batch.optimizeCollFreeBatchDevice(cube, scene, poses[lo:hi])         # host poses in, host results out
+    solve_s = time.perf_counter() - t0
+    if world > 1:                                                              # the path's one exchange: every rank's
+        allrec = sdist.gather_records(res.records())                           # per-problem records, once, at the end of the solve
+        assert allrec.shape == (SIP_PROBLEMS, 16)
     wall = time.perf_counter() - t0
+    wall_local = wall
     rec = torch.tensor([res.outer_iterations, wall, res.time_cons, res.time_qp, res.point_queries, float((res.gx > -5e-3).sum()),
                         float((np.asarray(res.gx0) < 0).sum())], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -282,10 +287,11 @@ def sip_leg(ctx, rank, world, want_cpu):
     out = {"value": float(rec[0].item()) / wall, "unit": "SIP outer iterations/s", "scaling": "strong",
            "workload": "C5: %d independent optimizeCollFree problems (cube SDF@0.05 vs synthetic 262,144-point scene, seed 2; poses "
                        "seed 3), reference default settings (max_iters 50), sharded over %d GPU(s), device-resident lock-step "
-                       "solver (sio_lockstep_pose_solve); wall clock from host poses (row-major 3x4 array) to host results" % (SIP_PROBLEMS, world),
+                       "solver (sio_lockstep_pose_solve); wall clock from host poses (row-major 3x4 array) to host results, the end-of-solve "
+                       "all-gather of the per-problem records included at N > 1" % (SIP_PROBLEMS, world),
            "outer_iterations": int(rec[0].item()), "wall_s": wall, "sweep_device_s_per_rank": float(rec[2].item()) / world,
            "qp_device_s_per_rank": float(rec[3].item()) / world, "other_s_per_rank": wall - float(rec[2].item() + rec[3].item()) / world,
-           "library_call_s_rank0": float(res.time),
+           "library_call_s_rank0": float(res.time), "gather_s_rank0": wall_local - solve_s,
            "oracle_point_queries_resolved": int(rec[4].item()), "started_in_collision": int(rec[6].item()),
            "ended_feasible(g>-5e-3)": int(rec[5].item())}
     if want_cpu:
