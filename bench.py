@@ -264,7 +264,9 @@ def sip_leg(ctx, rank, world, want_cpu):
     lo, hi = 0, len(poses)
     warm = sip.SemiInfiniteOptimizationSettings()
     warm.max_iters = 1
-    batch.optimizeCollFreeBatchDevice(cube, scene, poses, settings=warm)       # warm-up: first launches, scratch sized for the shard
+    wres = batch.optimizeCollFreeBatchDevice(cube, scene, poses, settings=warm)   # warm-up: first launches, scratch sized for the shard
+    if world > 1:
+        sdist.gather_records(wres.records())               # ... and NCCL's first all-gather of this size (it sets up buffers: 0.2 s once)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
@@ -304,7 +306,8 @@ def workload_config(ngpu):
                         "upsample (seed 1), 64 seeded poses per GPU, one K2 min/arg-min/under-bound sweep per step",
             "poses_per_gpu": POSES_PER_GPU, "cloud_points": CLOUD_N, "queries_per_step_per_gpu": POSES_PER_GPU * CLOUD_N,
             "sharding": "poses across ranks (geometry replicated), no collective inside a sweep; ONE NCCL all_gather of the per-pose "
-                        "results per reporting interval (= the K timed steps), inside the timed total" if ngpu > 1 else "single GPU",
+                        "results per reporting interval (= the K timed steps), inside the timed total (ranks are re-aligned with a "
+                        "barrier before it, so its events time the exchange, not the ranks' start skew)" if ngpu > 1 else "single GPU",
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
@@ -401,6 +404,12 @@ def main():
             ev[k][1].record(stream)
     gather_ms = 0.0
     if world > 1:
+        # ranks leave the opening barrier milliseconds apart (eight host processes on shared cores); line them up again so
+        # that the gather's events time the exchange itself and not that start skew (the steps are timed per step on the
+        # device, so the skew is in none of them either)
+        ctx.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(stream)
         gather()
