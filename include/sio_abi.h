@@ -74,6 +74,10 @@ int sio_grid_create(sio_ctx* ctx, const float* values, const int32_t dims[3],
                     const double bmin[3], const double bmax[3], sio_handle* out);
 int sio_grid_destroy(sio_ctx* ctx, sio_handle grid);
 int sio_cloud_create(sio_ctx* ctx, const float* xyz, int64_t n, sio_handle* out);
+/* the order sio_cloud_create keeps the points in (host work only, no device or context involved): a k-d ordering into
+ * leaves of 128 consecutive points -- the unit one warp evaluates and one bounding sphere culls --, Morton order inside
+ * a leaf.  order_out[internal] = caller index; sio_cloud_perm returns the same for a resident cloud. */
+int sio_cloud_order(const float* xyz, int64_t n, int32_t* order_out);
 int sio_cloud_destroy(sio_ctx* ctx, sio_handle cloud);
 int64_t sio_cloud_size(sio_ctx* ctx, sio_handle cloud);
 

@@ -24,7 +24,7 @@ ABI_SYMBOLS = (
     "sio_abi_version", "sio_last_error",
     "sio_ctx_create", "sio_ctx_destroy", "sio_ctx_sync", "sio_ctx_stream", "sio_ctx_set_tau", "sio_ctx_set_scratch_limit", "sio_ctx_num_sms",
     "sio_ctx_kernel_launches",
-    "sio_grid_create", "sio_grid_destroy", "sio_cloud_create", "sio_cloud_destroy", "sio_cloud_size",
+    "sio_grid_create", "sio_grid_destroy", "sio_cloud_create", "sio_cloud_order", "sio_cloud_destroy", "sio_cloud_size",
     "sio_query", "sio_cloud_query_dev", "sio_cloud_perm",
     "sio_min_distance", "sio_min_distance_dev", "sio_under_fetch",
     "sio_pose_rows", "sio_sip_step_qp", "sio_mesh_distance_grid", "sio_lockstep_pose_solve",
@@ -66,6 +66,7 @@ def load_library():
     L.sio_grid_create.argtypes = [P, P, P, P, P, C.POINTER(I32)]
     L.sio_grid_destroy.argtypes = [P, I32]
     L.sio_cloud_create.argtypes = [P, P, I64, C.POINTER(I32)]
+    L.sio_cloud_order.argtypes = [P, I64, P]
     L.sio_cloud_destroy.argtypes = [P, I32]
     L.sio_cloud_size.argtypes = [P, I32]
     L.sio_cloud_size.restype = I64
@@ -95,6 +96,17 @@ def load_library():
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def cloud_order(xyz):
+    """The order sio_cloud_create keeps a cloud in (host work only: usable without a GPU): internal -> caller index."""
+    L = load_library()
+    p = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    out = np.empty(len(p), dtype=np.int32)
+    rc = L.sio_cloud_order(p.ctypes.data, len(p), out.ctypes.data)
+    if rc != SIO_OK:
+        raise SioError(rc, L.sio_last_error().decode())
+    return out
 
 
 def _ptr(a):

@@ -349,12 +349,9 @@ int sio_grid_destroy(sio_ctx* c, sio_handle h) {
     return SIO_OK;
 }
 
-int sio_cloud_create(sio_ctx* c, const float* xyz, int64_t n, sio_handle* out) {
-    if (!c || !out || n < 0 || (n > 0 && !xyz)) return fail(SIO_ERR_INVALID, "sio_cloud_create: bad argument");
-    if (n >= (1LL << 31) - kTile) return fail(SIO_ERR_INVALID, "sio_cloud_create: more than 2^31 points");
-    DeviceGuard guard(c->device);
-    CloudH p;
-    p.n = n;
+// the resident order of a cloud (pure host work, no device needed): order_out[internal] = caller index
+int sio_cloud_order(const float* xyz, int64_t n, int32_t* order_out) {
+    if (n < 0 || (n > 0 && (!xyz || !order_out))) return fail(SIO_ERR_INVALID, "sio_cloud_order: bad argument");
     // Point order (one-off, host).  Sub-tiles of 128 consecutive points are the unit of the bulk kernels (one warp) and
     // of the culling (one bounding sphere), so they must be spatially tight: a k-d ordering -- median splits along the
     // longest axis, left halves sized in whole sub-tiles -- down to leaves of 128, Morton order inside a leaf so that the
@@ -402,11 +399,26 @@ int sio_cloud_create(sio_ctx* c, const float* xyz, int64_t n, sio_handle* out) {
             todo.push_back({a0, a0 + left});
         }
     }
+    for (int64_t i = 0; i < n; ++i) order_out[i] = keys[i].second;
+    return SIO_OK;
+}
+
+int sio_cloud_create(sio_ctx* c, const float* xyz, int64_t n, sio_handle* out) {
+    if (!c || !out || n < 0 || (n > 0 && !xyz)) return fail(SIO_ERR_INVALID, "sio_cloud_create: bad argument");
+    if (n >= (1LL << 31) - kTile) return fail(SIO_ERR_INVALID, "sio_cloud_create: more than 2^31 points");
+    DeviceGuard guard(c->device);
+    CloudH p;
+    p.n = n;
+    std::vector<int32_t> order((size_t)n);
+    {
+        const int rc = sio_cloud_order(xyz, n, order.data());
+        if (rc != SIO_OK) return rc;
+    }
     const int64_t npad = ((n + kTile - 1) / kTile) * kTile;
     std::vector<float4> pts((size_t)std::max<int64_t>(npad, 1));
     p.perm.resize((size_t)std::max<int64_t>(npad, 1), -1);
     for (int64_t i = 0; i < n; ++i) {
-        int32_t s = keys[i].second;
+        int32_t s = order[i];
         pts[i] = make_float4(xyz[3 * s], xyz[3 * s + 1], xyz[3 * s + 2], 0.f);
         p.perm[i] = s;
     }

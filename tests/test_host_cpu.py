@@ -320,3 +320,41 @@ def test_batch_result_builds_its_lists_on_first_use():
     assert [len(p) for p in r.instantiated_params] == [1, 0, 2, 3] and r.instantiated_params[2][1] == list(P[2, 1])
     eager = BatchResult(2)
     assert eager.status == ['not converged'] * 2 and eager.instantiated_params == [[], []]
+
+
+def _subtile_radii(P, order):
+    n = len(order) // 128 * 128
+    Q = P[order[:n]].reshape(-1, 128, 3).astype(np.float64)
+    c = Q.mean(1, keepdims=True)
+    rep = Q[np.arange(len(Q)), np.argmin(((Q - c) ** 2).sum(2), 1)][:, None, :]
+    return np.sqrt(((Q - rep) ** 2).sum(2).max(1))
+
+
+def test_cloud_order_is_a_permutation_with_tight_leaves():
+    """sio_cloud_order (host-only part of sio_cloud_create): a permutation for every size incl. ties, deterministic, and
+    -- the reason it exists -- 128-point leaves several times tighter than chunks of the plain Morton order, whose
+    outliers (chunks straddling a jump of the curve) used to survive every sub-tile cull."""
+    from semiinfiniteoptimization_b200 import _abi, workloads as W
+    rng = np.random.default_rng(7)
+    for n in (0, 1, 2, 127, 128, 129, 1000, 1025, 5000):
+        P = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+        o = _abi.cloud_order(P)
+        assert sorted(o.tolist()) == list(range(n))
+        assert np.array_equal(o, _abi.cloud_order(P))
+    same = np.tile(np.float32([0.3, -0.2, 0.9]), (777, 1))
+    assert sorted(_abi.cloud_order(same).tolist()) == list(range(777))
+    with pytest.raises(_abi.SioError):
+        _abi.cloud_order(np.float32([[0, 0, np.nan]]))
+    P = np.asarray(W.c5_scene_cloud(), dtype=np.float32)
+    r = _subtile_radii(P, _abi.cloud_order(P))
+    lo, hi = P.min(0), P.max(0)
+    q = np.minimum(2097151.0, np.maximum(0.0, (P - lo) * (2097151.0 / (hi - lo).max()))).astype(np.uint64)
+
+    def spread(v):
+        v = v & np.uint64(0x1fffff)
+        for sh, m in ((32, 0x1f00000000ffff), (16, 0x1f0000ff0000ff), (8, 0x100f00f00f00f00f), (4, 0x10c30c30c30c30c3), (2, 0x1249249249249249)):
+            v = (v | (v << np.uint64(sh))) & np.uint64(m)
+        return v
+    key = (spread(q[:, 0]) << np.uint64(2)) | (spread(q[:, 1]) << np.uint64(1)) | spread(q[:, 2])
+    rm = _subtile_radii(P, np.argsort(key, kind="stable"))
+    assert r.max() < 0.5 < rm.max() and (r > 0.15).mean() < 0.05 < (rm > 0.15).mean() and np.median(r) < np.median(rm)
