@@ -14,7 +14,8 @@ A STEP is one oracle sweep: the K2 call (transform + trilinear SDF query of ever
 every pose, minimum / arg-minimum / under-bound set with the float64 near-tie re-check) over
 64 x 2^20 = 67,108,864 point-queries per GPU.  With N > 1 every rank owns its own 64 poses (weak
 scaling; geometry replicated); sweeps need no collective, and the compact per-pose results are all-gathered with
-NCCL once per reporting interval (the K timed steps), inside the timed total.
+NCCL once per reporting interval (the K timed steps), inside the timed total (the ranks are lined up with a barrier
+before it, so that its events time the exchange and not the ranks' start skew; `per_rank_ms` shows every rank's figures).
 
 `value`  : point-queries/s, inputs resident in HBM, timed with CUDA events on the launching stream,
            max over ranks; L2 is flushed between timed steps.
@@ -29,7 +30,8 @@ NCCL once per reporting interval (the K timed steps), inside the timed total.
 `sip`     : BASELINE.json's second metric, SIP outer iterations/s, on configs[4] ("C5"): 65,536 independent
            cube-vs-scene optimizeCollFree problems (declared synthetic scene, 262,144 points) sharded across the
            ranks and solved in lock step entirely on the device (batch.optimizeCollFreeBatchDevice =
-           sio_lockstep_pose_solve), wall clock from host poses to host results, with the sweep / QP / other split; at
+           sio_lockstep_pose_solve), wall clock from host poses to host results -- at N > 1 including the end-of-solve
+           all-gather of the per-problem records --, with the sweep / in-line QP / other split; at
            N=1 also the CPU path (restated SIP loop on the CPU oracle, one process per host core, bounded sample).
 
 --impl reference times that CPU oracle port as the reference arm (the reference itself is
