@@ -81,6 +81,7 @@ def solve_qp(P, q, A, l, u, eps_abs=1e-5, eps_rel=1e-5, max_iter=4000, rho=0.1, 
 
     rho_vec = rho_vector(rho)
     solve = _kkt_solver(P, A, sigma, rho_vec, sparse)
+    At = A.T                                                # built once: the residual tests multiply by it every ten iterations
     x = np.zeros(n)
     z = np.zeros(m)
     y = np.zeros(m)
@@ -130,7 +131,7 @@ def solve_qp(P, q, A, l, u, eps_abs=1e-5, eps_rel=1e-5, max_iter=4000, rho=0.1, 
             continue
         Ax = A @ x
         Px = P @ x
-        Aty = A.T @ y
+        Aty = At @ y
         r_prim = np.abs(Ax - z).max() if m else 0.0
         r_dual = np.abs(Px + q + Aty).max()
         nAx = max(np.abs(Ax).max() if m else 0.0, np.abs(z).max() if m else 0.0)
@@ -142,7 +143,7 @@ def solve_qp(P, q, A, l, u, eps_abs=1e-5, eps_rel=1e-5, max_iter=4000, rho=0.1, 
         ndy = np.abs(dy).max() if m else 0.0
         if ndy > 1e-12:
             dyn = dy / ndy
-            if np.abs(A.T @ dyn).max() <= 1e-4 and (u @ np.maximum(dyn, 0) + l @ np.minimum(dyn, 0)) < -1e-4:
+            if np.abs(At @ dyn).max() <= 1e-4 and (u @ np.maximum(dyn, 0) + l @ np.minimum(dyn, 0)) < -1e-4:
                 status = "primal infeasible"
                 break
         if it % adapt_every == 0 and r_prim > 0 and r_dual > 0:

@@ -327,7 +327,7 @@ class RobotTrajectoryCache:
         self.tend = 1
         self.trajectory = None
         self.interMilestoneLipschitzBounds = []
-        self.linkTransforms = []
+        self._linkTransforms = []
         self.linkTransforms12 = None
         n = self.robot.numLinks()
         # K[i,j]: bound on the workspace motion of link j's geometry per unit motion of joint i
@@ -362,6 +362,14 @@ class RobotTrajectoryCache:
             self.lipschitzConstants[l, l] = Kgeom
         self.dirty = True
 
+    @property
+    def linkTransforms(self):
+        """linkTransforms[milestone][link] as Klampt se3 tuples (gopt:285-304), from the device FK result of the last set()."""
+        if self._linkTransforms is None:
+            T = self.linkTransforms12
+            self._linkTransforms = [[se3.from_rowmajor12(T[i, j]) for j in range(T.shape[1])] for i in range(T.shape[0])]
+        return self._linkTransforms
+
     def set(self, x):
         if self.dirty:
             self.trajectory = self.stateToTrajectory(x)
@@ -370,7 +378,7 @@ class RobotTrajectoryCache:
             # forward kinematics of every milestone in one device launch
             T = self.kinematics.context.fk(self.kinematics.robot_h, ms, self.robot.numLinks())
             self.linkTransforms12 = T
-            self.linkTransforms = [[se3.from_rowmajor12(T[i, j]) for j in range(T.shape[1])] for i in range(T.shape[0])]
+            self._linkTransforms = None                     # the Klampt-style list of lists is built on first use (469 conversions)
             self.dirty = False
 
     def clear(self):
