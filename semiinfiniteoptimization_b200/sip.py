@@ -219,6 +219,9 @@ class ConstraintGenerationData:
         xdes = np.asarray(xdes, dtype=np.float64)
         n = len(xdes)
         m = len(b)
+        if n <= _qp.DENSE_MAX_VARS and not scipy.sparse.issparse(W) and np.ndim(W) <= 1 \
+                and not any(scipy.sparse.issparse(r) for r in A):
+            return self._solve_qp_dense(W, xdes, A, b, xmin, xmax, regularizationFactor, slack_penalty)
         if isinstance(W, (int, float)):
             P = scipy.sparse.diags([float(W)] * n, format='csc')
         elif scipy.sparse.issparse(W):
@@ -261,6 +264,47 @@ class ConstraintGenerationData:
                 Aslack = scipy.sparse.vstack((Aslack, scipy.sparse.csc_matrix((n, m))), format='csc')
             As = scipy.sparse.hstack((Amat, Aslack), format='csc')
             results = run(Ps, qs, As)
+            if results.x is None:
+                raise RuntimeError("QP step failed even with slack variables")
+        return results.x[:n]
+
+
+    def _solve_qp_dense(self, W, xdes, A, b, xmin, xmax, regularizationFactor, slack_penalty):
+        """solve_qp_osqp for a few variables with a diagonal weight (object poses, robot configurations): the very same
+        matrices, built as numpy arrays directly.  Going through scipy.sparse (diags, vstack, bmat, toarray) cost 3 ms
+        per QP -- more than solving it -- for identical entries."""
+        n, m = len(xdes), len(b)
+        w = np.full(n, float(W)) if np.ndim(W) == 0 else np.asarray(W, dtype=np.float64)
+        q = -(w * xdes)
+        P = np.diag(w + regularizationFactor) if regularizationFactor != 0 else np.diag(w)
+        Amat = np.vstack([np.asarray(r, dtype=np.float64).reshape(1, -1) for r in A])
+        b = np.asarray(b, dtype=np.float64)
+        l = -b + np.ones(m) * self.constraint_inflation
+        u = np.full(m, np.inf)
+        if xmin is not None:
+            assert xmax is not None
+            Amat = np.vstack((Amat, np.eye(n)))
+            l = np.hstack((l, xmin))
+            u = np.hstack((u, xmax))
+        bnorm = 1
+        if any(v < 0 for v in b):
+            bnorm = np.linalg.norm([v for v in b if v < 0])
+        # column-major, as csc_matrix.toarray() hands them over: the memory order picks the BLAS kernel of A x and A'y,
+        # hence the rounding, and the traces are compared with the reference's to the last bit
+        P, Amat = np.asfortranarray(P), np.asfortranarray(Amat)
+        results = _qp.solve_qp(P, q, Amat, l, u, eps_abs=1e-5)
+        if results.x is None or np.linalg.norm(results.x) * regularizationFactor > bnorm:
+            if slack_penalty == 'auto':
+                bmin = np.min(b)
+                slack_penalty = (1 + len([v for v in b if v < 0])) / (abs(bmin) + 1e-3)
+            Ps = np.zeros((n + m, n + m), order='F')
+            Ps[:n, :n] = P
+            Ps[n:, n:] = np.diag([float(slack_penalty)] * m)
+            qs = np.hstack((q, np.zeros(m)))
+            As = np.zeros((Amat.shape[0], n + m), order='F')
+            As[:, :n] = Amat
+            As[:m, n:] = np.eye(m)
+            results = _qp.solve_qp(Ps, qs, As, l, u, eps_abs=1e-5)
             if results.x is None:
                 raise RuntimeError("QP step failed even with slack variables")
         return results.x[:n]
