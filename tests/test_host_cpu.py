@@ -358,3 +358,28 @@ def test_cloud_order_is_a_permutation_with_tight_leaves():
     key = (spread(q[:, 0]) << np.uint64(2)) | (spread(q[:, 1]) << np.uint64(1)) | spread(q[:, 2])
     rm = _subtile_radii(P, np.argsort(key, kind="stable"))
     assert r.max() < 0.5 < rm.max() and (r > 0.15).mean() < 0.05 < (rm > 0.15).mean() and np.median(r) < np.median(rm)
+
+
+def test_small_qps_dense_assembly_equals_sparse_assembly_bit_for_bit():
+    """sip.py assembles few-variable QPs as numpy arrays directly (no scipy.sparse round trip); handing the same rows over
+    as sparse matrices forces the reference-shaped assembly.  Same matrices, same memory order, same bits -- strict and
+    slack problems, with and without the box."""
+    import scipy.sparse
+    from semiinfiniteoptimization_b200 import sip
+    rng = np.random.default_rng(21)
+    cg = sip.ConstraintGenerationData([])
+    slack_cases = 0
+    for trial in range(60):
+        n = int(rng.integers(3, 8))
+        k = int(rng.integers(1, 12))
+        W = rng.uniform(0.01, 1.0, n) if trial % 2 else float(rng.uniform(0.01, 1.0))
+        xdes = rng.normal(0, 0.2, n)
+        A = [rng.normal(0, 1, n) for _ in range(k)]
+        b = list(rng.normal(0.0, 0.05, k) - (0.3 if trial % 3 == 0 else 0.0))      # deep penetrations -> slack re-solve
+        box = (np.full(n, -0.3), np.full(n, 0.3)) if trial % 4 else (None, None)
+        x_dense = cg.solve_qp_osqp(W, xdes, A, b, box[0], box[1], regularizationFactor=1e-3)
+        A_sparse = [scipy.sparse.csr_matrix(r.reshape(1, -1)) for r in A]
+        x_sparse = cg.solve_qp_osqp(W, xdes, A_sparse, b, box[0], box[1], regularizationFactor=1e-3)
+        assert np.array_equal(x_dense, x_sparse), trial
+        slack_cases += trial % 3 == 0
+    assert slack_cases >= 15
