@@ -337,3 +337,183 @@ int hqp_sip_step_batch(int64_t nprob, int n, const double* W, const double* xdes
     }
     return fail ? -2 : 0;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * One LARGE sparse problem with a banded structure (the trajectory QP of BASELINE config 4: 455 variables, a
+ * block-tridiagonal quadratic term, rows that touch two neighbouring milestones, a box on every variable):
+ *
+ *     min 1/2 x'Px + q'x (+ 1/2 pen |s|^2)   s.t.  lr <= R x (+ s) <= ur,   xmin <= x <= xmax
+ *
+ * Same ADMM as above (and as _host/qp.py solve_qp: same iterates up to rounding, same tests every 10 iterations, same
+ * rho adaptation every 50) with the x-update in its reduced form: P + sigma I + R'diag(c)R + rho_box I is banded (half
+ * bandwidth bw), so it is factorised by a banded Cholesky and solved in O(n bw) per iteration -- the interpreted loop
+ * around a sparse LU of the (n+m) x (n+m) KKT system spends 40 us per iteration in the solve alone.  The slack variables
+ * (one per general row, each in exactly one row) are eliminated in closed form as in the device kernel (sio_qp.cu).
+ * P comes as its lower band: Pb[d*n + j] = P[j+d][j], d = 0..bw.  y has mr + (has_box ? n : 0) entries, general rows
+ * first.  The polish stays with the caller.  status: 0 solved, 1 iteration limit, 2 primal infeasible, -1 not positive
+ * definite. */
+static int band_chol(double* M, int n, int bw) {              /* M[d*n + j] = M_(j+d, j); in place: L */
+    for (int j = 0; j < n; ++j) {
+        double d = M[j];
+        const int k0 = j - bw > 0 ? j - bw : 0;
+        for (int k = k0; k < j; ++k) d -= M[(j - k) * n + k] * M[(j - k) * n + k];
+        if (!(d > 0.0)) return -1;
+        d = sqrt(d);
+        M[j] = d;
+        const int i1 = j + bw < n - 1 ? j + bw : n - 1;
+        for (int i = j + 1; i <= i1; ++i) {
+            double s = M[(i - j) * n + j];
+            const int kk0 = i - bw > 0 ? i - bw : 0;
+            for (int k = kk0 > k0 ? kk0 : k0; k < j; ++k) s -= M[(i - k) * n + k] * M[(j - k) * n + k];
+            M[(i - j) * n + j] = s / d;
+        }
+    }
+    return 0;
+}
+static void band_solve(const double* L, int n, int bw, double* b) {
+    for (int i = 0; i < n; ++i) {
+        double s = b[i];
+        const int k0 = i - bw > 0 ? i - bw : 0;
+        for (int k = k0; k < i; ++k) s -= L[(i - k) * n + k] * b[k];
+        b[i] = s / L[i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        double s = b[i];
+        const int k1 = i + bw < n - 1 ? i + bw : n - 1;
+        for (int k = i + 1; k <= k1; ++k) s -= L[(k - i) * n + i] * b[k];
+        b[i] = s / L[i];
+    }
+}
+
+int hqp_admm_banded(int n, int bw, const double* Pb, const double* q, int mr, const int* rp, const int* ci, const double* rv,
+                    const double* lr, const double* ur, int has_box, const double* xmin, const double* xmax, double pen,
+                    double eps_abs, double eps_rel, int max_iter, double rho, double sigma, double alpha,
+                    double* x, double* s, double* y, int* status_out, int* iters_out, double* rp_out, double* rd_out) {
+    const int check_every = 10, adapt_every = 50;
+    const int slack = pen > 0.0;
+    const int m = mr + (has_box ? n : 0);
+    double* W = (double*)calloc((size_t)(bw + 1) * n + 12 * (size_t)(m + n) + 16, sizeof(double));
+    if (!W) return -2;
+    double* M = W;                              /* (bw+1)*n */
+    double* l = M + (size_t)(bw + 1) * n;       /* m each from here */
+    double* u = l + m; double* rho_v = u + m; double* z = rho_v + m; double* wv = z + m; double* zt = wv + m;
+    double* dy = zt + m; double* cr = dy + m; double* ds = cr + m;
+    double* xt = ds + m;                        /* n each */
+    double* tmp = xt + n; double* Aty = tmp + n;
+    for (int r = 0; r < mr; ++r) { l[r] = lr[r] < -HQP_INF ? -HQP_INF : lr[r]; u[r] = ur[r] > HQP_INF ? HQP_INF : ur[r]; }
+    for (int i = 0; i < (has_box ? n : 0); ++i) {
+        l[mr + i] = xmin[i] < -HQP_INF ? -HQP_INF : xmin[i];
+        u[mr + i] = xmax[i] > HQP_INF ? HQP_INF : xmax[i];
+    }
+    for (int i = 0; i < n; ++i) x[i] = 0.0;
+    for (int r = 0; r < mr; ++r) if (s) s[r] = 0.0;
+    for (int r = 0; r < m; ++r) { y[r] = 0.0; z[r] = 0.0; dy[r] = 0.0; }
+    int status = HQP_MAXIT, it = 0, rc = 0;
+    double r_prim = INFINITY, r_dual = INFINITY;
+#define HQP_FACTOR()                                                                                                   \
+    do {                                                                                                               \
+        for (int r = 0; r < m; ++r) rho_v[r] = (u[r] - l[r] < 1e-12) ? 1e3 * rho : rho;                                \
+        memcpy(M, Pb, sizeof(double) * (size_t)(bw + 1) * n);                                                         \
+        for (int j = 0; j < n; ++j) M[j] += sigma + (has_box ? rho_v[mr + j] : 0.0);                                   \
+        for (int r = 0; r < mr; ++r) {                                                                                 \
+            ds[r] = pen + sigma + rho_v[r];                                                                            \
+            cr[r] = slack ? rho_v[r] - rho_v[r] * rho_v[r] / ds[r] : rho_v[r];                                         \
+            for (int a = rp[r]; a < rp[r + 1]; ++a)                                                                    \
+                for (int b2 = rp[r]; b2 < rp[r + 1]; ++b2) {                                                           \
+                    const int i = ci[a], j = ci[b2];                                                                   \
+                    if (i >= j) M[(size_t)(i - j) * n + j] += cr[r] * rv[a] * rv[b2];                                   \
+                }                                                                                                      \
+        }                                                                                                              \
+        rc = band_chol(M, n, bw);                                                                                     \
+    } while (0)
+    HQP_FACTOR();
+    if (rc) { free(W); *status_out = -1; *iters_out = 0; return 0; }
+    for (it = 1; it <= max_iter; ++it) {
+        /* rhs of the reduced system */
+        for (int i = 0; i < n; ++i) xt[i] = sigma * x[i] - q[i];
+        for (int r = 0; r < m; ++r) wv[r] = rho_v[r] * z[r] - y[r];
+        for (int r = 0; r < mr; ++r) {
+            double ws = wv[r];
+            if (slack) ws -= rho_v[r] * (sigma * s[r] + wv[r]) / ds[r];
+            for (int a = rp[r]; a < rp[r + 1]; ++a) xt[ci[a]] += rv[a] * ws;
+        }
+        if (has_box) for (int i = 0; i < n; ++i) xt[i] += wv[mr + i];
+        band_solve(M, n, bw, xt);
+        /* z~ = A x~ (with the eliminated slack), relaxation, projection, dual step */
+        for (int r = 0; r < m; ++r) {
+            double ax;
+            if (r < mr) {
+                ax = 0.0;
+                for (int a = rp[r]; a < rp[r + 1]; ++a) ax += rv[a] * xt[ci[a]];
+            } else ax = xt[r - mr];
+            double zs = ax, st = 0.0;
+            if (slack && r < mr) { st = (sigma * s[r] + wv[r] - rho_v[r] * ax) / ds[r]; zs = ax + st; }
+            const double zr = alpha * zs + (1 - alpha) * z[r];
+            const double c = zr + y[r] / rho_v[r];
+            const double zn = c < l[r] ? l[r] : (c > u[r] ? u[r] : c);
+            const double yn = y[r] + rho_v[r] * (zr - zn);
+            dy[r] = yn - y[r];
+            z[r] = zn; y[r] = yn;
+            if (slack && r < mr) s[r] = alpha * st + (1 - alpha) * s[r];
+        }
+        for (int i = 0; i < n; ++i) x[i] = alpha * xt[i] + (1 - alpha) * x[i];
+        if (it % check_every && it != max_iter) continue;
+        /* residuals */
+        double nAx = 0.0, nd = 0.0;
+        r_prim = 0.0; r_dual = 0.0;
+        for (int i = 0; i < n; ++i) Aty[i] = has_box ? y[mr + i] : 0.0;
+        for (int r = 0; r < m; ++r) {
+            double ax;
+            if (r < mr) {
+                ax = 0.0;
+                for (int a = rp[r]; a < rp[r + 1]; ++a) { ax += rv[a] * x[ci[a]]; Aty[ci[a]] += rv[a] * y[r]; }
+                if (slack) {
+                    ax += s[r];
+                    const double ps = pen * s[r];
+                    r_dual = fmax(r_dual, fabs(ps + y[r]));
+                    nd = fmax(nd, fmax(fabs(ps), fabs(y[r])));
+                }
+            } else ax = x[r - mr];
+            r_prim = fmax(r_prim, fabs(ax - z[r]));
+            nAx = fmax(nAx, fmax(fabs(ax), fabs(z[r])));
+        }
+        for (int i = 0; i < n; ++i) {                       /* P x by the band */
+            double px = Pb[i] * x[i];
+            for (int d = 1; d <= bw; ++d) {
+                if (i + d < n) px += Pb[(size_t)d * n + i] * x[i + d];
+                if (i - d >= 0) px += Pb[(size_t)d * n + (i - d)] * x[i - d];
+            }
+            r_dual = fmax(r_dual, fabs(px + q[i] + Aty[i]));
+            nd = fmax(nd, fmax(fabs(px), fmax(fabs(Aty[i]), fabs(q[i]))));
+        }
+        if (r_prim <= eps_abs + eps_rel * nAx && r_dual <= eps_abs + eps_rel * nd) { status = HQP_SOLVED; break; }
+        double ndy = 0.0;
+        for (int r = 0; r < m; ++r) ndy = fmax(ndy, fabs(dy[r]));
+        if (ndy > 1e-12) {                                  /* primal infeasibility certificate */
+            double sup = 0.0, nAt = 0.0;
+            for (int i = 0; i < n; ++i) tmp[i] = has_box ? dy[mr + i] / ndy : 0.0;
+            for (int r = 0; r < m; ++r) {
+                const double d = dy[r] / ndy;
+                if (r < mr) {
+                    for (int a = rp[r]; a < rp[r + 1]; ++a) tmp[ci[a]] += rv[a] * d;
+                    if (slack) nAt = fmax(nAt, fabs(d));
+                }
+                sup += u[r] * fmax(d, 0.0) + l[r] * fmin(d, 0.0);
+            }
+            for (int i = 0; i < n; ++i) nAt = fmax(nAt, fabs(tmp[i]));
+            if (nAt <= 1e-4 && sup < -1e-4) { status = HQP_INFEASIBLE; break; }
+        }
+        if (it % adapt_every == 0 && r_prim > 0 && r_dual > 0) {
+            const double scale = sqrt((r_prim / fmax(nAx, 1e-12)) / (r_dual / fmax(nd, 1e-12)));
+            if (scale > 5 || scale < 0.2) {
+                rho = fmin(fmax(rho * scale, 1e-6), 1e6);
+                HQP_FACTOR();
+                if (rc) { status = -1; break; }
+            }
+        }
+    }
+#undef HQP_FACTOR
+    free(W);
+    *status_out = status; *iters_out = it > max_iter ? max_iter : it; *rp_out = r_prim; *rd_out = r_dual;
+    return 0;
+}

@@ -240,6 +240,73 @@ def solve_qp_batch(P, q, A, l, u, nrows, iters=400, rho=0.1, sigma=1e-6, alpha=1
 
 
 # ---------------------------------------------------------------------------------------------
+# one large banded problem natively (csrc/hostqp.c hqp_admm_banded): the trajectory QP
+# ---------------------------------------------------------------------------------------------
+# The native loop takes the x-update in its reduced, banded form, so its ADMM iterates differ from solve_qp's in the last
+# bits; the polish then lands both on the same active set and the same answer (the golden trajectory traces, compared at
+# 1e-12, are unchanged -- tests/test_golden_cpu.py runs the reference through solve_qp and this package through the native
+# loop).  A QP that stops at the iteration limit (no polish) can differ by rounding.  False = interpreted loop everywhere.
+NATIVE_BANDED = True
+MAX_BANDWIDTH = 64
+
+
+def solve_qp_structured(P, q, A, l, u, n, mr, has_box, pen, eps_abs=1e-5, eps_rel=1e-5, max_iter=4000, rho=0.1, sigma=1e-6,
+                        alpha=1.6, polish=True):
+    """The QP solve_qp(P, q, A, l, u) solves, for the structure sip.py builds: variables [x (n) | one slack per general row
+    (pen > 0 only)], P = blockdiag(Px, pen I), A = [[R, I], [I_n, 0]] with mr general rows R and, if has_box, the identity
+    rows of the box.  Returns a QPResult, or None when Px + R'R is not banded within MAX_BANDWIDTH (caller falls back)."""
+    import ctypes as C
+    P = scipy.sparse.csc_matrix(P)
+    A = scipy.sparse.csr_matrix(A)
+    Px = P[:n, :n].tocoo()
+    R = A[:mr, :n].tocsr()
+    R.sort_indices()
+    bw = int(np.abs(Px.row - Px.col).max()) if Px.nnz else 0
+    if mr:
+        counts = np.diff(R.indptr)
+        if (counts == 0).any():
+            return None
+        first = R.indices[R.indptr[:-1]]
+        last = R.indices[R.indptr[1:] - 1]
+        bw = max(bw, int((last - first).max()))
+    if bw > MAX_BANDWIDTH:
+        return None
+    Pb = np.zeros((bw + 1, n))
+    low = Px.row >= Px.col
+    np.add.at(Pb, (Px.row[low] - Px.col[low], Px.col[low]), Px.data[low])
+    q = np.asarray(q, dtype=np.float64)
+    l = np.asarray(l, dtype=np.float64)
+    u = np.asarray(u, dtype=np.float64)
+    qx = np.ascontiguousarray(q[:n])
+    lr, ur = np.ascontiguousarray(l[:mr]), np.ascontiguousarray(u[:mr])
+    xmin = np.ascontiguousarray(l[mr:mr + n]) if has_box else None
+    xmax = np.ascontiguousarray(u[mr:mr + n]) if has_box else None
+    m = mr + (n if has_box else 0)
+    x, sv, y = np.zeros(n), np.zeros(max(mr, 1)), np.zeros(max(m, 1))
+    rp = np.ascontiguousarray(R.indptr, dtype=np.int32)
+    ci = np.ascontiguousarray(R.indices, dtype=np.int32)
+    rvals = np.ascontiguousarray(R.data, dtype=np.float64)
+    status, iters = C.c_int(0), C.c_int(0)
+    r_prim, r_dual = C.c_double(0.0), C.c_double(0.0)
+    L = _native_lib()
+    rc = L.hqp_admm_banded(n, bw, Pb.ctypes.data, qx.ctypes.data, mr, rp.ctypes.data, ci.ctypes.data, rvals.ctypes.data,
+                           lr.ctypes.data, ur.ctypes.data, 1 if has_box else 0, None if xmin is None else xmin.ctypes.data,
+                           None if xmax is None else xmax.ctypes.data, float(pen), eps_abs, eps_rel, int(max_iter), rho, sigma, alpha,
+                           x.ctypes.data, sv.ctypes.data, y.ctypes.data, C.byref(status), C.byref(iters), C.byref(r_prim),
+                           C.byref(r_dual))
+    if rc != 0 or status.value < 0:
+        return None
+    xf = np.concatenate([x, sv[:mr]]) if pen > 0 else x
+    yv = y[:m]
+    name = ("solved", "max iterations", "primal infeasible")[status.value]
+    if name == "solved" and polish and m:
+        xp = _polish(P, q, scipy.sparse.csc_matrix(A), np.maximum(l, -INF), np.minimum(u, INF), xf, yv, True)
+        if xp is not None:
+            xf = xp
+    return QPResult(xf if name != "primal infeasible" else None, yv, name, iters.value, r_prim.value, r_dual.value)
+
+
+# ---------------------------------------------------------------------------------------------
 # native batched SIP step (csrc/hostqp.c): every problem's QP, slack fallback included, in one call
 # ---------------------------------------------------------------------------------------------
 _native = None
@@ -259,6 +326,9 @@ def _native_lib():
         L.hqp_sip_step_batch.argtypes = [C.c_int64, C.c_int, P, P, P, P, P, P, P, C.c_double, C.c_double, C.c_double, C.c_int, P, P, P]
         L.hqp_sip_step_batch.restype = C.c_int
         L.hqp_max_threads.restype = C.c_int
+        L.hqp_admm_banded.argtypes = [C.c_int, C.c_int, P, P, C.c_int, P, P, P, P, P, C.c_int, P, P, C.c_double, C.c_double, C.c_double,
+                                      C.c_int, C.c_double, C.c_double, C.c_double, P, P, P, P, P, P, P]
+        L.hqp_admm_banded.restype = C.c_int
         _native = L
     return _native
 

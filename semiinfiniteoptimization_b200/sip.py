@@ -244,8 +244,12 @@ class ConstraintGenerationData:
             l = np.hstack((l, xmin))
             u = np.hstack((u, xmax))
 
-        def run(Pm, qv, Am):
+        def run(Pm, qv, Am, pen=0.0):
             if Pm.shape[0] > _qp.DENSE_MAX_VARS:
+                if _qp.NATIVE_BANDED:                       # opt-in native loop for banded problems (trajectories)
+                    res = _qp.solve_qp_structured(Pm, qv, Am, l, u, n, m, xmin is not None, pen, eps_abs=1e-5)
+                    if res is not None:
+                        return res
                 return _qp.solve_qp(Pm, qv, Am, l, u, eps_abs=1e-5)
             return _qp.solve_qp(Pm.toarray(), qv, Am.toarray(), l, u, eps_abs=1e-5)
 
@@ -263,7 +267,7 @@ class ConstraintGenerationData:
             if xmin is not None:
                 Aslack = scipy.sparse.vstack((Aslack, scipy.sparse.csc_matrix((n, m))), format='csc')
             As = scipy.sparse.hstack((Amat, Aslack), format='csc')
-            results = run(Ps, qs, As)
+            results = run(Ps, qs, As, float(slack_penalty))
             if results.x is None:
                 raise RuntimeError("QP step failed even with slack variables")
         return results.x[:n]

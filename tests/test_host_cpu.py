@@ -383,3 +383,59 @@ def test_small_qps_dense_assembly_equals_sparse_assembly_bit_for_bit():
         assert np.array_equal(x_dense, x_sparse), trial
         slack_cases += trial % 3 == 0
     assert slack_cases >= 15
+
+
+def test_native_banded_qp_equals_the_interpreted_solver():
+    """hqp_admm_banded (the trajectory QP natively: reduced banded x-update) against _host/qp.py solve_qp on random
+    block-tridiagonal problems with the trajectory QP's structure -- rows spanning two neighbouring blocks, a box, strict
+    and slack forms, feasible and infeasible: same status, same iteration count to within a check interval, and the same
+    answer (after the polish the two agree to rounding because they identify the same active set)."""
+    import scipy.sparse
+    from semiinfiniteoptimization_b200._host import qp
+    rng = np.random.default_rng(33)
+    nb, k = 7, 12                                             # 12 blocks of 7 variables
+    n = nb * k
+    seen = set()
+    for trial in range(24):
+        t = np.zeros((k, k))
+        for i in range(k):
+            t[i, i] = 4 if 0 < i < k - 1 else 2
+            if i:
+                t[i, i - 1] = t[i - 1, i] = -2
+        Px = scipy.sparse.kron(scipy.sparse.csc_matrix(t), scipy.sparse.identity(nb), format="csc") + 1e-2 * scipy.sparse.identity(n, format="csc")
+        xdes = rng.normal(0, 0.3, n)
+        q = -Px.dot(xdes)
+        mr = int(rng.integers(2, 9))
+        rows = np.zeros((mr, n))
+        for r in range(mr):
+            b0 = int(rng.integers(0, k - 1)) * nb
+            rows[r, b0:b0 + 2 * nb] = rng.normal(0, 1, 2 * nb)
+        depth = rng.normal(0.0, 0.05, mr) - (0.6 if trial % 3 == 0 else 0.0)
+        lr = -depth + 1e-3
+        if trial % 6 == 4:                                    # contradictory rows (strict form): primal infeasible
+            rows[1] = -rows[0]
+            lr[0], lr[1] = 1.0, 1.0
+        lo, hi = np.full(n, -0.2), np.full(n, 0.2)
+        pen = 0.0 if trial % 2 == 0 else 50.0
+        R = scipy.sparse.csr_matrix(rows)
+        if pen > 0:
+            P = scipy.sparse.bmat([[Px, None], [None, pen * scipy.sparse.identity(mr)]], format="csc")
+            A = scipy.sparse.bmat([[R, scipy.sparse.identity(mr)], [scipy.sparse.identity(n), None]], format="csc")
+            qq = np.concatenate([q, np.zeros(mr)])
+        else:
+            P, A, qq = Px, scipy.sparse.vstack([R, scipy.sparse.identity(n)], format="csc"), q
+        l, u = np.concatenate([lr, lo]), np.concatenate([np.full(mr, np.inf), hi])
+        ref = qp.solve_qp(P, qq, A, l, u, eps_abs=1e-5)
+        got = qp.solve_qp_structured(P, qq, A, l, u, n, mr, True, pen, eps_abs=1e-5)
+        assert got is not None and got.status == ref.status, (trial, got.status, ref.status)
+        assert abs(got.iters - ref.iters) <= 10
+        seen.add((ref.status, pen > 0))
+        if ref.status == "solved":
+            assert np.abs(got.x - ref.x).max() <= 1e-7, trial
+        elif ref.status == "max iterations":
+            assert np.abs(got.x - ref.x).max() <= 1e-4
+    assert ("solved", False) in seen and ("solved", True) in seen and any(s == "primal infeasible" for s, _ in seen)
+    # a problem that is not banded is declined (the caller keeps the interpreted solver)
+    dense_rows = scipy.sparse.csr_matrix(rng.normal(0, 1, (2, n)))
+    A = scipy.sparse.vstack([dense_rows, scipy.sparse.identity(n)], format="csc")
+    assert qp.solve_qp_structured(Px, q, A, np.concatenate([[0.0, 0.0], lo]), np.concatenate([[np.inf, np.inf], hi]), n, 2, True, 0.0) is None
