@@ -517,3 +517,26 @@ int hqp_admm_banded(int n, int bw, const double* Pb, const double* q, int mr, co
     *status_out = status; *iters_out = it > max_iter ? max_iter : it; *rp_out = r_prim; *rd_out = r_dual;
     return 0;
 }
+
+/* One small dense problem with a DIAGONAL quadratic term, ADMM phase only (no polish): the interpreted solver's loop
+ * (_host/qp.py solve_qp) natively.  A is m x n row-major.  The caller polishes (numpy), so whenever both loops identify
+ * the same active set the polished answers are the same bits.  y_out[m]; returns the status (0 solved, 1 iteration limit,
+ * 2 primal infeasible) or -2 on allocation failure. */
+int hqp_admm_diag(int n, int m, const double* Pd, const double* q, const double* A, const double* l, const double* u,
+                  double eps_abs, double eps_rel, int max_iter, double rho, double sigma, double alpha,
+                  double* x, double* y_out, int* iters_out, double* rp_out, double* rd_out) {
+    hqp_opts o;
+    o.eps_abs = eps_abs; o.eps_rel = eps_rel; o.rho = rho; o.sigma = sigma; o.alpha = alpha;
+    o.max_iter = max_iter; o.check_every = 10; o.adapt_every = 50; o.polish = 0;
+    const size_t nw = (size_t)n * n + 8 * (size_t)m + 4 * (size_t)n + (size_t)(n + m) * (n + m + 1) + 16;
+    double* work = (double*)malloc(nw * sizeof(double));
+    if (!work) return -2;
+    int iters = 0;
+    double pri = 0.0, dua = 0.0;
+    const int st = admm(n, m, Pd, q, A, l, u, &o, x, &pri, &dua, &iters, work);
+    /* admm's multipliers live in its work array: K (n*n), l, u, z, then y */
+    memcpy(y_out, work + (size_t)n * n + 3 * (size_t)m, sizeof(double) * (size_t)m);
+    free(work);
+    *iters_out = iters; *rp_out = pri; *rd_out = dua;
+    return st;
+}

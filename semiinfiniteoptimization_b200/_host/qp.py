@@ -73,6 +73,12 @@ def solve_qp(P, q, A, l, u, eps_abs=1e-5, eps_rel=1e-5, max_iter=4000, rho=0.1, 
     l = np.maximum(np.asarray(l, dtype=np.float64), -INF)
     u = np.minimum(np.asarray(u, dtype=np.float64), INF)
     n, m = len(q), len(l)
+    if NATIVE_DENSE and not sparse and m and check_every == 10 and adapt_every == 50:
+        d = np.diagonal(P)
+        if not (P - np.diag(d)).any():                      # diagonal quadratic term: the native loop applies
+            res = _solve_qp_native_diag(P, d, q, A, l, u, eps_abs, eps_rel, max_iter, rho, sigma, alpha, polish)
+            if res is not None:
+                return res
     eq = (u - l) < 1e-12
 
     def rho_vector(r):
@@ -247,7 +253,31 @@ def solve_qp_batch(P, q, A, l, u, nrows, iters=400, rho=0.1, sigma=1e-6, alpha=1
 # 1e-12, are unchanged -- tests/test_golden_cpu.py runs the reference through solve_qp and this package through the native
 # loop).  A QP that stops at the iteration limit (no polish) can differ by rounding.  False = interpreted loop everywhere.
 NATIVE_BANDED = True
+# the same for small dense problems with a diagonal quadratic term (poses, configurations): ADMM natively, polish in numpy
+NATIVE_DENSE = True
 MAX_BANDWIDTH = 64
+
+
+def _solve_qp_native_diag(P, d, q, A, l, u, eps_abs, eps_rel, max_iter, rho, sigma, alpha, polish):
+    import ctypes as C
+    n, m = len(q), len(l)
+    Ac = np.ascontiguousarray(A, dtype=np.float64)
+    dd, qq = np.ascontiguousarray(d, dtype=np.float64), np.ascontiguousarray(q, dtype=np.float64)
+    ll, uu = np.ascontiguousarray(l), np.ascontiguousarray(u)
+    x, y = np.zeros(n), np.zeros(m)
+    iters = C.c_int(0)
+    r_prim, r_dual = C.c_double(0.0), C.c_double(0.0)
+    st = _native_lib().hqp_admm_diag(n, m, dd.ctypes.data, qq.ctypes.data, Ac.ctypes.data, ll.ctypes.data, uu.ctypes.data, eps_abs, eps_rel,
+                                     int(max_iter), rho, sigma, alpha, x.ctypes.data, y.ctypes.data, C.byref(iters), C.byref(r_prim),
+                                     C.byref(r_dual))
+    if st < 0:
+        return None
+    name = ("solved", "max iterations", "primal infeasible")[st]
+    if name == "solved" and polish:
+        xp = _polish(P, q, A, l, u, x, y, False)
+        if xp is not None:
+            x = xp
+    return QPResult(x if name != "primal infeasible" else None, y, name, iters.value, r_prim.value, r_dual.value)
 
 
 def solve_qp_structured(P, q, A, l, u, n, mr, has_box, pen, eps_abs=1e-5, eps_rel=1e-5, max_iter=4000, rho=0.1, sigma=1e-6,
@@ -329,6 +359,9 @@ def _native_lib():
         L.hqp_admm_banded.argtypes = [C.c_int, C.c_int, P, P, C.c_int, P, P, P, P, P, C.c_int, P, P, C.c_double, C.c_double, C.c_double,
                                       C.c_int, C.c_double, C.c_double, C.c_double, P, P, P, P, P, P, P]
         L.hqp_admm_banded.restype = C.c_int
+        L.hqp_admm_diag.argtypes = [C.c_int, C.c_int, P, P, P, P, P, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double,
+                                    P, P, P, P, P]
+        L.hqp_admm_diag.restype = C.c_int
         _native = L
     return _native
 
