@@ -95,7 +95,7 @@ static void build_K(int n, int m, const double* Pd, const double* A, const doubl
 
 /* work: doubles, at least n*n + 8*m + 4*n + (n+m)*(n+m+1) */
 static int admm(int n, int m, const double* Pd, const double* q, const double* A, const double* l0, const double* u0,
-                const hqp_opts* o, double* x, double* pri, double* dua, int* iters_out, double* work) {
+                const hqp_opts* o, double* x, double* pri, double* dua, int* iters_out, double* work, double* y_out) {
     double* K = work;               work += n * n;
     double* l = work;               work += m;
     double* u = work;               work += m;
@@ -222,6 +222,7 @@ static int admm(int n, int m, const double* Pd, const double* q, const double* A
             }
         }
     }
+    if (y_out) memcpy(y_out, y, sizeof(double) * (size_t)m);
     *pri = r_prim; *dua = r_dual; *iters_out = it;
     return status;
 }
@@ -297,7 +298,7 @@ int hqp_sip_step_batch(int64_t nprob, int n, const double* W, const double* xdes
             for (int i = 0; i < n; ++i) { Pd[i] = Wp[i] + reg; q[i] = -Wp[i] * xd[i]; }
             double pri, dua;
             int its;
-            int st = admm(n, m, Pd, q, A, l, u, &o, x, &pri, &dua, &its, work);
+            int st = admm(n, m, Pd, q, A, l, u, &o, x, &pri, &dua, &its, work, NULL);
             double bnorm = 1.0, neg2 = 0.0, bmin = INFINITY;
             int nneg = 0;
             for (int r = 0; r < k; ++r) { if (b[r] < 0) { neg2 += b[r] * b[r]; ++nneg; } if (b[r] < bmin) bmin = b[r]; }
@@ -323,7 +324,7 @@ int hqp_sip_step_batch(int64_t nprob, int n, const double* W, const double* xdes
                 for (int i = 0; i < n; ++i)
                     for (int j = 0; j < ns; ++j) A[(k + i) * ns + j] = (i == j) ? 1.0 : 0.0;
             for (int j = 0; j < k; ++j) { Pd[n + j] = pen; q[n + j] = 0.0; }
-            st = admm(ns, m, Pd, q, A, l, u, &o, x, &pri, &dua, &its, work);
+            st = admm(ns, m, Pd, q, A, l, u, &o, x, &pri, &dua, &its, work, NULL);
             if (st == HQP_INFEASIBLE) {
                 for (int i = 0; i < n; ++i) out[i] = 0.0;
                 if (status) status[p] = -1;
@@ -533,9 +534,7 @@ int hqp_admm_diag(int n, int m, const double* Pd, const double* q, const double*
     if (!work) return -2;
     int iters = 0;
     double pri = 0.0, dua = 0.0;
-    const int st = admm(n, m, Pd, q, A, l, u, &o, x, &pri, &dua, &iters, work);
-    /* admm's multipliers live in its work array: K (n*n), l, u, z, then y */
-    memcpy(y_out, work + (size_t)n * n + 3 * (size_t)m, sizeof(double) * (size_t)m);
+    const int st = admm(n, m, Pd, q, A, l, u, &o, x, &pri, &dua, &iters, work, y_out);
     free(work);
     *iters_out = iters; *rp_out = pri; *rd_out = dua;
     return st;
