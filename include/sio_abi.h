@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SIO_ABI_VERSION 1
+#define SIO_ABI_VERSION 2
 
 /* status codes */
 #define SIO_OK               0
@@ -40,7 +40,7 @@ extern "C" {
 #define SIO_ERR_CUDA        -2   /* CUDA runtime error (message has the detail) */
 #define SIO_ERR_NOMEM       -3
 #define SIO_ERR_NODEVICE    -4   /* no usable CUDA device: the product has no CPU fallback */
-#define SIO_ERR_OVERFLOW    -5   /* an output capacity was too small; counts are still exact */
+#define SIO_ERR_OVERFLOW    -5   /* an output capacity was too small (see sio_under_fetch, sio_min_distance_dev) */
 
 /* flags */
 #define SIO_F32             0x0
@@ -64,6 +64,11 @@ int   sio_ctx_set_tau(sio_ctx* ctx, double tau);    /* near-tie window (metres) 
 /* bytes of per-(transform, sub-tile) scratch a K2 call may hold at once; larger sweeps run in batches of transforms
  * (default 256 MiB; <= 0 restores it).  Results do not depend on it. */
 int   sio_ctx_set_scratch_limit(sio_ctx* ctx, int64_t bytes);
+/* under-bound candidate records a K2 call can hold (default 2^20, 16 B each; <= 0 restores it).  The host entry points
+ * (sio_min_distance, sio_robot_*_min_distance) do not need it: they size the buffer from the sweep's own count and run
+ * the sweep again, so their n_under and under-bound lists are always exact (or the call fails with SIO_ERR_NOMEM /
+ * SIO_ERR_OVERFLOW above 2^31-1 records).  Callers of sio_min_distance_dev size it themselves. */
+int   sio_ctx_set_under_capacity(sio_ctx* ctx, int64_t entries);
 int   sio_ctx_num_sms(sio_ctx* ctx);
 int64_t sio_ctx_kernel_launches(sio_ctx* ctx);      /* kernels launched by this context so far */
 
@@ -109,7 +114,11 @@ int sio_cloud_perm(sio_ctx* ctx, sio_handle cloud, int32_t* perm_out /* internal
  * gopt:411/476), n_under[b] = #{i : d(b,i) < bound[b]} (0 for an infinite bound).
  * The compact under-bound list (b, i, d) sorted by (b, i) is fetched with sio_under_fetch.
  * n_under == NULL asks for the minimum / arg-minimum only (what the reference's minvalue consumes): no
- * under-bound set is produced, sio_under_fetch then returns an empty list. */
+ * under-bound set is produced, sio_under_fetch then returns an empty list.
+ * Capacity: sio_min_distance never returns a truncated set -- when the sweep offers more candidates than the
+ * context's buffer holds it grows the buffer and sweeps again.  sio_min_distance_dev cannot wait for the count: if the
+ * buffer (sio_ctx_set_under_capacity) is too small, EVERY d_n_under[b] of the call is written as -1 (dmin / argmin
+ * stay exact) and sio_under_fetch returns SIO_ERR_OVERFLOW with the number of records needed in its message. */
 int sio_min_distance(sio_ctx* ctx, const sio_handle* grids, int32_t n_grids, const int32_t* grid_of_b,
                      sio_handle cloud, const double* T_rel, const double* bound, int64_t B, int flags,
                      double* dmin, int64_t* argmin, int32_t* n_under);
@@ -168,8 +177,10 @@ int sio_robot_pairs_min_distance(sio_ctx* ctx, sio_handle robot, const sio_handl
  * coordinates, caller order).  T_init / T_des / T_out are row-major 3x4 poses of the moving body.
  * Per problem: status (1 = 'local optimum', 0 = iteration limit), iterations, f(x), g(x) = min over instantiated
  * parameters, g at the start, number of instantiated parameters and (optional) the parameters themselves
- * [B*cap*3].  stats[0..4] = outer iterations, point queries resolved by the sweeps, device microseconds in the in-line
- * QP launches, parameters that did not fit into `cap` slots, device microseconds in the sweeps.
+ * [B*cap*3].  status 2 = the problem's QP had no solution, not even with slack variables (the reference fails there,
+ * sip.py:358-378); the problem stops at its current pose.  stats[0..5] = outer iterations, point queries resolved by
+ * the sweeps, device microseconds in the in-line QP launches, parameters that did not fit into `cap` slots, device
+ * microseconds in the sweeps, problems stopped with status 2.
  * Problems advance independently: a QP that exhausts a small ADMM budget is finished by a background launch while
  * its problem sits rounds out (environment SIO_LS_DEFER = budget, default 800, 0 = off); outputs do not depend on it. */
 typedef struct {
@@ -188,7 +199,7 @@ typedef struct {
 int sio_lockstep_pose_solve(sio_ctx* ctx, sio_handle grid, sio_handle cloud, const double T_env[12], const double* cloud_world,
                             int64_t B, const double* T_init, const double* T_des, const sio_lockstep_settings* settings,
                             double* T_out, int32_t* status, int32_t* iterations, double* fx, double* gx, double* gx0,
-                            int32_t* n_params, double* params /* B*cap*3 or NULL */, int64_t stats[5]);
+                            int32_t* n_params, double* params /* B*cap*3 or NULL */, int64_t stats[6]);
 
 /* ---- geometry preprocessing ------------------------------------------------
  * replaces: the distance computation inside geom.convert('VolumeGrid', res) -- geometryopt.py:58-66.

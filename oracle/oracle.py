@@ -62,6 +62,8 @@ def lib(prefer_native=False):
     L.orc_min_distance_1.argtypes = [P, P, I64, P, P, P]
     L.orc_under.argtypes = [P, P, P, I64, P, P, I64, I64, P, P, P]
     L.orc_under.restype = I64
+    L.orc_under_counts.argtypes = [P, P, P, I64, P, P, I64, P, P, P]
+    L.orc_under_counts.restype = I64
     L.orc_pose_rows.argtypes = [P, P, P, I64, _c.c_int, P, P]
     L.orc_fk.argtypes = [P, P, I64, P]
     L.orc_chain_rows.argtypes = [P, _c.c_int32, P, P, P, I64, _c.c_int, P, P]
@@ -184,6 +186,25 @@ def under(grids, cloud, T, bound, grid_of_b=None, cap=1 << 22):
                         bnd.ctypes.data, B, cap, ob.ctypes.data, oi.ctypes.data, od.ctypes.data)
     m = min(n, cap)
     return n, ob[:m], oi[:m], od[:m]
+
+
+def under_counts(grids, cloud, T, bound, grid_of_b=None):
+    """Per transform: #{i : d < bound}, the sum of those indices and the sum of those distances (fingerprints of the
+    under-bound set at sizes where the explicit list is too long to keep)."""
+    if isinstance(grids, Grid):
+        grids = [grids]
+    cloud = np.ascontiguousarray(cloud, dtype=np.float32).reshape(-1, 3)
+    T = _f64(T).reshape(-1, 12)
+    B = len(T)
+    bnd = _f64(np.broadcast_to(bound, (B,)))
+    cnt = np.empty(B, dtype=np.int64)
+    isum = np.empty(B, dtype=np.int64)
+    dsum = np.empty(B)
+    ga = _grid_array(grids)
+    gob = None if grid_of_b is None else np.ascontiguousarray(grid_of_b, dtype=np.int32)
+    lib().orc_under_counts(ga, None if gob is None else gob.ctypes.data, cloud.ctypes.data, len(cloud), T.ctypes.data,
+                           bnd.ctypes.data, B, cnt.ctypes.data, isum.ctypes.data, dsum.ctypes.data)
+    return cnt, isum, dsum
 
 
 def pose_rows(grid, Tpose, pts, normalize=True):

@@ -220,26 +220,62 @@ void orc_min_distance_1(const orc_grid* g, const float* cloud, int64_t N, const 
     *argmin = bi;
 }
 
-/* all (b, i) with d < bound[b], in (b, i) order.  Returns the total count; writes at most cap. */
-int64_t orc_under(const orc_grid* grids, const int32_t* grid_of_b, const float* cloud, int64_t N,
-                  const double* T, const double* bound, int64_t B, int64_t cap,
-                  int64_t* out_b, int64_t* out_i, double* out_d) {
-    int64_t cnt = 0;
+/* per transform: number of points with d < bound[b], the sum of their indices and the sum of their distances
+ * (size-independent fingerprints of the under-bound set: the full-size tests compare these for every transform and
+ * the explicit list for a few).  Any output may be NULL.  Returns the total count. */
+int64_t orc_under_counts(const orc_grid* grids, const int32_t* grid_of_b, const float* cloud, int64_t N,
+                         const double* T, const double* bound, int64_t B, int64_t* count, int64_t* idx_sum, double* d_sum) {
+    int64_t total = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
     for (int64_t b = 0; b < B; ++b) {
         const orc_grid* g = grids + (grid_of_b ? grid_of_b[b] : 0);
         const double* Tb = T + 12 * b;
-        if (!(bound[b] < INFINITY)) continue;
+        int64_t n = 0, si = 0;
+        double sd = 0.0;
+        if (bound[b] < INFINITY)
+            for (int64_t i = 0; i < N; ++i) {
+                double p[3];
+                xf_apply(Tb, (double)cloud[3 * i], (double)cloud[3 * i + 1], (double)cloud[3 * i + 2], p);
+                double d = query_local(g, p, NULL);
+                if (d < bound[b]) { ++n; si += i; sd += d; }
+            }
+        if (count) count[b] = n;
+        if (idx_sum) idx_sum[b] = si;
+        if (d_sum) d_sum[b] = sd;
+        total += n;
+    }
+    return total;
+}
+
+/* all (b, i) with d < bound[b], in (b, i) order.  Returns the total count; writes at most cap.
+ * Two passes (count per transform, then fill at the prefix offsets) so that both run on all threads. */
+int64_t orc_under(const orc_grid* grids, const int32_t* grid_of_b, const float* cloud, int64_t N,
+                  const double* T, const double* bound, int64_t B, int64_t cap,
+                  int64_t* out_b, int64_t* out_i, double* out_d) {
+    int64_t* off = (int64_t*)malloc(sizeof(int64_t) * (size_t)(B + 1));
+    if (!off) return -1;
+    orc_under_counts(grids, grid_of_b, cloud, N, T, bound, B, off + 1, NULL, NULL);
+    off[0] = 0;
+    for (int64_t b = 0; b < B; ++b) off[b + 1] += off[b];
+    const int64_t total = off[B];
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t b = 0; b < B; ++b) {
+        if (off[b + 1] == off[b]) continue;
+        const orc_grid* g = grids + (grid_of_b ? grid_of_b[b] : 0);
+        const double* Tb = T + 12 * b;
+        int64_t k = off[b];
         for (int64_t i = 0; i < N; ++i) {
             double p[3];
             xf_apply(Tb, (double)cloud[3 * i], (double)cloud[3 * i + 1], (double)cloud[3 * i + 2], p);
             double d = query_local(g, p, NULL);
             if (d < bound[b]) {
-                if (cnt < cap) { out_b[cnt] = b; out_i[cnt] = i; out_d[cnt] = d; }
-                ++cnt;
+                if (k < cap) { out_b[k] = b; out_i[k] = i; out_d[k] = d; }
+                ++k;
             }
         }
     }
-    return cnt;
+    free(off);
+    return total;
 }
 
 /* ObjectCollisionConstraint.value + df_dx (geometryopt.py:407-408, 413-418) for P world points.

@@ -22,7 +22,8 @@ SIO_PRUNE = 0x8
 # every symbol include/sio_abi.h declares (tests check the built library exports each of them)
 ABI_SYMBOLS = (
     "sio_abi_version", "sio_last_error",
-    "sio_ctx_create", "sio_ctx_destroy", "sio_ctx_sync", "sio_ctx_stream", "sio_ctx_set_tau", "sio_ctx_set_scratch_limit", "sio_ctx_num_sms",
+    "sio_ctx_create", "sio_ctx_destroy", "sio_ctx_sync", "sio_ctx_stream", "sio_ctx_set_tau", "sio_ctx_set_scratch_limit",
+    "sio_ctx_set_under_capacity", "sio_ctx_num_sms",
     "sio_ctx_kernel_launches",
     "sio_grid_create", "sio_grid_destroy", "sio_cloud_create", "sio_cloud_order", "sio_cloud_destroy", "sio_cloud_size",
     "sio_query", "sio_cloud_query_dev", "sio_cloud_perm",
@@ -60,6 +61,7 @@ def load_library():
     L.sio_ctx_stream.restype = P
     L.sio_ctx_set_tau.argtypes = [P, D]
     L.sio_ctx_set_scratch_limit.argtypes = [P, I64]
+    L.sio_ctx_set_under_capacity.argtypes = [P, I64]
     L.sio_ctx_num_sms.argtypes = [P]
     L.sio_ctx_kernel_launches.argtypes = [P]
     L.sio_ctx_kernel_launches.restype = I64
@@ -153,6 +155,10 @@ class Context:
 
     def set_scratch_limit(self, nbytes):
         self._ck(self.L.sio_ctx_set_scratch_limit(self.h, int(nbytes)))
+
+    def set_under_capacity(self, entries):
+        """Under-bound candidate records a K2 call holds (the host entry points grow it on their own)."""
+        self._ck(self.L.sio_ctx_set_under_capacity(self.h, int(entries)))
 
     @property
     def num_sms(self):
@@ -273,14 +279,14 @@ class Context:
         out = {"T": np.empty((B, 12)), "status": np.empty(B, dtype=np.int32), "iterations": np.empty(B, dtype=np.int32),
                "fx": np.empty(B), "gx": np.empty(B), "gx0": np.empty(B), "n_params": np.empty(B, dtype=np.int32),
                "params": np.empty((B, cap, 3)) if want_params else None}
-        stats = np.zeros(5, dtype=np.int64)
+        stats = np.zeros(6, dtype=np.int64)
         self._ck(self.L.sio_lockstep_pose_solve(self.h, grid, cloud, Te.ctypes.data, cw.ctypes.data, B, Ti.ctypes.data, Td.ctypes.data,
                                                 C.byref(s), out["T"].ctypes.data, out["status"].ctypes.data,
                                                 out["iterations"].ctypes.data, out["fx"].ctypes.data, out["gx"].ctypes.data,
                                                 out["gx0"].ctypes.data, out["n_params"].ctypes.data, _ptr(out["params"]),
                                                 stats.ctypes.data))
         out["stats"] = {"outer_iterations": int(stats[0]), "point_queries": int(stats[1]), "qp_device_s": stats[2] * 1e-6,
-                        "slot_overflows": int(stats[3]), "sweep_device_s": stats[4] * 1e-6}
+                        "slot_overflows": int(stats[3]), "sweep_device_s": stats[4] * 1e-6, "qp_failures": int(stats[5])}
         return out
 
     # -- geometry preprocessing --

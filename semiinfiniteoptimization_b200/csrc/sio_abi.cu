@@ -127,8 +127,8 @@ struct sio_ctx {
     int n_icnt = 0;                   // batches of the last pruned call (their survivor counts sit in h_icnt)
     int64_t prune_total = 0;          // (transform, sub-tile) pairs of the last pruned call
     DevBuf s_xf, s_keys, s_gridtab, s_cand, s_cnt, s_in0, s_in1, s_in2, s_in3, s_out0, s_out1, s_out2, s_tlinks, s_trel, s_gob;
-    HostBuf h_a, h_b, h_c;
-    uint32_t cand_cap = 1u << 20;
+    HostBuf h_a, h_b, h_c, h_cnt;
+    uint32_t cand_cap = 1u << 20;     // under-bound candidate records the buffer holds (sio_ctx_set_under_capacity; host entry points grow it)
     GridDev single_grid_host{};       // host copy handed to the single-grid bulk kernel by value
     std::vector<sio_handle> staged_grids;   // handles whose table currently sits in s_gridtab (grids are immutable)
     double staged_tau = 0.0;
@@ -138,6 +138,8 @@ struct sio_ctx {
 };
 
 namespace {
+
+constexpr unsigned long long kMaxCand = (1ull << 31) - 1;      // record slots are 32-bit in the kernels (16 B each: 34 GB)
 
 bool grid_ok(sio_ctx* c, sio_handle h) { return h >= 0 && (size_t)h < c->grids.size() && c->grids[h].live; }
 bool cloud_ok(sio_ctx* c, sio_handle h) { return h >= 0 && (size_t)h < c->clouds.size() && c->clouds[h].live; }
@@ -220,7 +222,7 @@ int sio_ctx_destroy(sio_ctx* c) {
     DevBuf* bufs[] = {&c->s_xf, &c->s_keys, &c->s_gridtab, &c->s_cand, &c->s_cnt, &c->s_in0, &c->s_in1, &c->s_in2, &c->s_in3,
                       &c->s_out0, &c->s_out1, &c->s_out2, &c->s_tlinks, &c->s_trel, &c->s_gob};
     for (auto* b : bufs) b->release();
-    c->h_a.release(); c->h_b.release(); c->h_c.release();
+    c->h_a.release(); c->h_b.release(); c->h_c.release(); c->h_cnt.release();
     cudaEventDestroy(c->ev_bulk0); cudaEventDestroy(c->ev_bulk1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -238,6 +240,12 @@ int sio_ctx_set_tau(sio_ctx* c, double tau) { if (!c) return fail(SIO_ERR_INVALI
 int sio_ctx_set_scratch_limit(sio_ctx* c, int64_t bytes) {
     if (!c) return fail(SIO_ERR_INVALID, "null context");
     c->scratch_limit = bytes > 0 ? bytes : (int64_t)(256u << 20);
+    return SIO_OK;
+}
+int sio_ctx_set_under_capacity(sio_ctx* c, int64_t entries) {
+    if (!c) return fail(SIO_ERR_INVALID, "null context");
+    if (entries > (int64_t)kMaxCand) return fail(SIO_ERR_INVALID, "sio_ctx_set_under_capacity: at most %lld entries", (long long)kMaxCand);
+    c->cand_cap = entries > 0 ? (uint32_t)entries : (1u << 20);
     return SIO_OK;
 }
 int sio_ctx_num_sms(sio_ctx* c) { return c ? c->num_sms : 0; }
@@ -575,9 +583,17 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
         maxb = std::max<int64_t>(kXfChunk, (maxb / kXfChunk) * kXfChunk);
         Bc = std::min(B, maxb);
     }
-    CU(c->s_cnt.ensure(sizeof(uint32_t)));
-    CU(c->s_cand.ensure((size_t)c->cand_cap * sizeof(Cand)));
-    CU(cudaMemsetAsync(c->s_cnt.p, 0, sizeof(uint32_t), st));
+    CU(c->s_cnt.ensure(sizeof(unsigned long long)));
+    {
+        cudaError_t e = c->s_cand.ensure((size_t)c->cand_cap * sizeof(Cand));
+        if (e != cudaSuccess) {
+            const unsigned long long asked = c->cand_cap;
+            c->cand_cap = 1u << 20;                           // the next call starts from the default again
+            cudaGetLastError();
+            return fail(SIO_ERR_NOMEM, "sio_min_distance_dev: no memory for %llu under-bound candidate records (%s)", asked, cudaGetErrorString(e));
+        }
+    }
+    CU(cudaMemsetAsync(c->s_cnt.p, 0, sizeof(unsigned long long), st));
     if (d_n_under) CU(cudaMemsetAsync(d_n_under, 0, (size_t)B * sizeof(int32_t), st));
     MinArgs a{};
     a.pts = p.d_pts; a.perm = p.d_perm; a.N = p.n; a.rep = p.d_rep;
@@ -587,7 +603,7 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
     // no counter array = the caller wants the minimum only: no candidates are produced, no re-check runs
     const bool want_under = d_bound && d_n_under;
     a.T_rel = dT_rel; a.bound = d_bound; a.under_bound = want_under ? d_bound : nullptr; a.B = B; a.tau = tau; a.ntiles = ntiles;
-    a.cand = c->s_cand.as<Cand>(); a.cand_count = c->s_cnt.as<uint32_t>(); a.cand_cap = c->cand_cap;
+    a.cand = c->s_cand.as<Cand>(); a.cand_count = c->s_cnt.as<unsigned long long>(); a.cand_cap = c->cand_cap; a.num_sms = c->num_sms;
     a.n_under = want_under ? d_n_under : nullptr;
     a.dmin = d_dmin; a.argmin = d_argmin;
     const bool prune = !f64 && (flags & SIO_PRUNE) && p.n > 0;
@@ -649,21 +665,30 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
 static int collect_under(sio_ctx* c) {
     if (c->under_valid) return SIO_OK;
     cudaStream_t st = c->stream;
-    CU(c->h_c.ensure(sizeof(uint32_t)));
-    CU(cudaMemcpyAsync(c->h_c.p, c->s_cnt.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(c->h_c.ensure(sizeof(unsigned long long)));
+    CU(cudaMemcpyAsync(c->h_c.p, c->s_cnt.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    uint32_t n = *c->h_c.as<uint32_t>();
+    const unsigned long long n = *c->h_c.as<unsigned long long>();
     if (n > c->cand_cap)
-        return fail(SIO_ERR_OVERFLOW, "under-bound candidate buffer overflow: %u candidates, capacity %u", n, c->cand_cap);
+        return fail(SIO_ERR_OVERFLOW, "under-bound candidate buffer overflow: %llu candidates, capacity %u (sio_ctx_set_under_capacity)", n, c->cand_cap);
     c->under.clear();
     if (n > 0) {
         std::vector<Cand> recs(n);
         CU(cudaMemcpy(recs.data(), c->s_cand.p, (size_t)n * sizeof(Cand), cudaMemcpyDeviceToHost));
-        c->under.reserve(n);
-        for (const Cand& r : recs) if (r.b >= 0) c->under.push_back({r.b, r.idx, r.d});
-        std::sort(c->under.begin(), c->under.end(), [](const UnderEntry& x, const UnderEntry& y) {
-            return x.b != y.b ? x.b < y.b : x.idx < y.idx;
-        });
+        // (b, idx) order: bucket by transform (a C5-scale set has tens of millions of entries), then sort each bucket
+        int32_t bmax = -1;
+        for (const Cand& r : recs) bmax = std::max(bmax, r.b);
+        std::vector<size_t> start((size_t)bmax + 2, 0);
+        for (const Cand& r : recs) if (r.b >= 0) ++start[(size_t)r.b + 1];
+        for (size_t b = 1; b < start.size(); ++b) start[b] += start[b - 1];
+        c->under.resize(start.back());
+        {
+            std::vector<size_t> fill(start.begin(), start.end() - 1);
+            for (const Cand& r : recs) if (r.b >= 0) c->under[fill[(size_t)r.b]++] = {r.b, r.idx, r.d};
+        }
+        for (size_t b = 0; b + 1 < start.size(); ++b)
+            std::sort(c->under.begin() + start[b], c->under.begin() + start[b + 1],
+                      [](const UnderEntry& x, const UnderEntry& y) { return x.idx < y.idx; });
     }
     c->under_valid = true; c->under_pending = false;
     return SIO_OK;
@@ -682,6 +707,23 @@ int sio_under_fetch(sio_ctx* c, int64_t capacity, int64_t* b_out, int64_t* idx_o
         if (d_out) d_out[i] = c->under[i].d;
     }
     return (*total > capacity && capacity > 0) ? fail(SIO_ERR_OVERFLOW, "under list has %lld entries, capacity %lld", (long long)*total, (long long)capacity) : SIO_OK;
+}
+
+// A host entry point has enqueued its sweep and its output copies: wait for them and see whether the under-bound
+// candidates fitted.  Returns 0 = done, 1 = the buffer was too small and has been re-sized: run the sweep again
+// (the float32 pass is deterministic, so the second run offers the same candidates), < 0 = error.
+static int under_settle(sio_ctx* c, bool want_under) {
+    cudaStream_t st = c->stream;
+    if (!want_under) { CU(cudaStreamSynchronize(st)); return 0; }
+    CU(c->h_cnt.ensure(sizeof(unsigned long long)));
+    CU(cudaMemcpyAsync(c->h_cnt.p, c->s_cnt.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const unsigned long long n = *c->h_cnt.as<unsigned long long>();
+    if (n <= c->cand_cap) return 0;
+    if (n > kMaxCand)
+        return fail(SIO_ERR_OVERFLOW, "%llu under-bound candidates in one call, more than the %llu the list can hold: split the batch", n, kMaxCand);
+    c->cand_cap = (uint32_t)std::min<unsigned long long>(kMaxCand, n + n / 8 + 4096);
+    return 1;
 }
 
 // host-pointer K2: inputs are packed into one pinned block and sent with ONE H2D copy; outputs come back
@@ -708,13 +750,17 @@ static int min_distance_host(sio_ctx* c, const sio_handle* grids, int32_t n_grid
     CU(cudaMemcpyAsync(c->s_in0.p, hin, in_bytes, cudaMemcpyHostToDevice, st));
     char* din = c->s_in0.as<char>();
     char* dout = c->s_out0.as<char>();
-    int rc = sio_min_distance_dev(c, grids, n_grids, grid_of_b ? reinterpret_cast<const int32_t*>(din + oG) : nullptr, cloud,
-                                  reinterpret_cast<const double*>(din + oT), bound ? reinterpret_cast<const double*>(din + oB) : nullptr,
-                                  B, flags, reinterpret_cast<double*>(dout + oD), reinterpret_cast<int64_t*>(dout + oA),
-                                  n_under ? reinterpret_cast<int32_t*>(dout + oN) : nullptr);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(c->h_b.p, dout, out_bytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    for (;;) {
+        int rc = sio_min_distance_dev(c, grids, n_grids, grid_of_b ? reinterpret_cast<const int32_t*>(din + oG) : nullptr, cloud,
+                                      reinterpret_cast<const double*>(din + oT), bound ? reinterpret_cast<const double*>(din + oB) : nullptr,
+                                      B, flags, reinterpret_cast<double*>(dout + oD), reinterpret_cast<int64_t*>(dout + oA),
+                                      n_under ? reinterpret_cast<int32_t*>(dout + oN) : nullptr);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(c->h_b.p, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+        rc = under_settle(c, bound && n_under);
+        if (rc < 0) return rc;
+        if (rc == 0) break;
+    }
     const char* hout = c->h_b.as<char>();
     std::memcpy(dmin, hout + oD, (size_t)B * 8);
     std::memcpy(argmin, hout + oA, (size_t)B * 8);
@@ -812,13 +858,13 @@ extern "C" {
 int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const double T_env[12], const double* cloud_world,
                             int64_t B, const double* T_init, const double* T_des, const sio_lockstep_settings* cfg,
                             double* T_out, int32_t* status, int32_t* iterations, double* fx, double* gx, double* gx0,
-                            int32_t* n_params, double* params, int64_t stats[5]) {
+                            int32_t* n_params, double* params, int64_t stats[6]) {
     if (!c || !grid_ok(c, grid) || !cloud_ok(c, cloud) || !T_env || !cloud_world || B < 0 || !cfg ||
         (B > 0 && (!T_init || !T_des || !T_out)))
         return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: bad argument");
     if (cfg->cap < 1 || cfg->cap > 58) return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: cap must be in [1, 58], got %d", cfg->cap);
     if (B >= (1LL << 31) / 64) return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: too many problems");
-    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = stats[4] = 0;
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = stats[4] = stats[5] = 0;
     if (B == 0) return SIO_OK;
     DeviceGuard guard(c->device);
     cudaStream_t st = c->stream;
@@ -875,7 +921,7 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     CU(cudaMemsetAsync(S.key, 0, (size_t)B * cap * 3 * sizeof(long long), st));
     ls_launch_init(S, L, st);
     CU(c->s_qp.ensure(sip_qp_scratch_bytes(c->num_sms)));
-    unsigned long long hc[5];
+    unsigned long long hc[6];
     int64_t queries = 0;
     // device time of the QP launches and of the sweeps, read back at the end (events per iteration)
     struct EventBag {                                      // destroyed on every way out of the call
@@ -1075,7 +1121,7 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - entry0).count(), (long long)B);
     if (stats) {
         stats[0] = (int64_t)hc[2]; stats[1] = queries; stats[2] = (int64_t)(qp_ms * 1e3); stats[3] = (int64_t)hc[3];
-        stats[4] = (int64_t)(sweep_ms * 1e3);
+        stats[4] = (int64_t)(sweep_ms * 1e3); stats[5] = (int64_t)hc[5];
     }
     return SIO_OK;
 }
@@ -1309,13 +1355,17 @@ int sio_robot_min_distance(sio_ctx* c, sio_handle robot, const sio_handle* link_
     CU(c->s_out0.ensure((size_t)B * sizeof(double)));
     CU(c->s_out1.ensure((size_t)B * sizeof(int64_t)));
     CU(c->s_out2.ensure((size_t)B * sizeof(int32_t)));
-    int rc = sio_min_distance_dev(c, sel.data(), n_sel, c->s_gob.as<int32_t>(), cloud, c->s_trel.as<double>(), d_bound, B, flags,
-                                  c->s_out0.as<double>(), c->s_out1.as<int64_t>(), n_under ? c->s_out2.as<int32_t>() : nullptr);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(dmin, c->s_out0.p, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(argmin, c->s_out1.p, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    if (n_under && bound) CU(cudaMemcpyAsync(n_under, c->s_out2.p, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    for (;;) {
+        int rc = sio_min_distance_dev(c, sel.data(), n_sel, c->s_gob.as<int32_t>(), cloud, c->s_trel.as<double>(), d_bound, B, flags,
+                                      c->s_out0.as<double>(), c->s_out1.as<int64_t>(), n_under ? c->s_out2.as<int32_t>() : nullptr);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(dmin, c->s_out0.p, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(argmin, c->s_out1.p, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        if (n_under && bound) CU(cudaMemcpyAsync(n_under, c->s_out2.p, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        rc = under_settle(c, bound && n_under);
+        if (rc < 0) return rc;
+        if (rc == 0) break;
+    }
     if (n_under && !bound) std::memset(n_under, 0, sizeof(int32_t) * (size_t)B);
     return SIO_OK;
 }
@@ -1385,12 +1435,16 @@ int sio_robot_pairs_min_distance(sio_ctx* c, sio_handle robot, const sio_handle*
     CU(c->s_out0.ensure(out_bytes));
     CU(c->h_b.ensure(out_bytes));
     char* o = c->s_out0.as<char>();
-    int rc = sio_min_distance_dev(c, sel.data(), (int32_t)sel.size(), c->s_gob.as<int32_t>(), cloud, c->s_trel.as<double>(),
-                                  bound ? reinterpret_cast<double*>(d + oB) : nullptr, P, flags, reinterpret_cast<double*>(o + oD),
-                                  reinterpret_cast<int64_t*>(o + oA), n_under ? reinterpret_cast<int32_t*>(o + oN) : nullptr);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(c->h_b.p, o, out_bytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    for (;;) {
+        int rc = sio_min_distance_dev(c, sel.data(), (int32_t)sel.size(), c->s_gob.as<int32_t>(), cloud, c->s_trel.as<double>(),
+                                      bound ? reinterpret_cast<double*>(d + oB) : nullptr, P, flags, reinterpret_cast<double*>(o + oD),
+                                      reinterpret_cast<int64_t*>(o + oA), n_under ? reinterpret_cast<int32_t*>(o + oN) : nullptr);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(c->h_b.p, o, out_bytes, cudaMemcpyDeviceToHost, st));
+        rc = under_settle(c, bound && n_under);
+        if (rc < 0) return rc;
+        if (rc == 0) break;
+    }
     const char* ho = c->h_b.as<char>();
     std::memcpy(dmin, ho + oD, (size_t)P * 8);
     std::memcpy(argmin, ho + oA, (size_t)P * 8);

@@ -82,13 +82,14 @@ struct MinArgs {
     double tau;
     uint32_t* subkeys; int32_t ntiles;                  // scratch [Bc * ntiles*8]: float32 min (raw bits) per 128-point sub-tile
     XfRec* xf;                                          // scratch [B]
-    Cand* cand; uint32_t* cand_count; uint32_t cand_cap;
+    Cand* cand; unsigned long long* cand_count; uint32_t cand_cap;   // 64-bit counter: a C5-scale sweep can offer > 2^32 candidates
     int32_t* n_under;                                   // device [B] counters of the exact under-bound set, or null
     const float4* rep;                                  // bounding sphere (a cloud point + radius) per 128-point sub-tile
     // sub-tile culling (SIO_PRUNE): lower bounds, upper bounds, work list
     float* lb; uint32_t* ub; uint32_t* items; uint32_t* item_count;
     double* dmin; int64_t* argmin;                      // device outputs
     int normalize;
+    int num_sms;                                        // persistent grids are sized from it
 };
 void launch_prep_xf(const MinArgs& a, cudaStream_t st);
 void launch_min_f32(const MinArgs& a, cudaStream_t st);

@@ -22,13 +22,22 @@ __device__ __forceinline__ bool lex_less(double d1, int64_t i1, double d2, int64
 }
 
 // exact re-evaluation of the fp32 pass's under-bound candidates, strided over the `nthreads` threads of the
-// re-check CTAs; kept entries are counted per transform in n_under
+// re-check CTAs; kept entries are counted per transform in n_under.
+// More candidates than the buffer holds: the list is incomplete, so no count can be exact -- every n_under[b] of the
+// call is set to -1 (never a silently low count).  The host entry points see the counter, grow the buffer and run the
+// sweep again; a caller of the _dev entry point sees the -1s (and SIO_ERR_OVERFLOW from sio_under_fetch).
 __device__ void recheck_candidates(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int64_t N,
                                    const GridDev* __restrict__ grids, const int32_t* __restrict__ grid_of_b,
                                    const double* __restrict__ T_rel, const double* __restrict__ bound,
-                                   Cand* __restrict__ cand, const uint32_t* __restrict__ cand_count, uint32_t cand_cap,
-                                   int32_t* __restrict__ n_under, uint32_t first, uint32_t nthreads) {
-    const uint32_t n = min(*cand_count, cand_cap);
+                                   Cand* __restrict__ cand, const unsigned long long* __restrict__ cand_count, uint32_t cand_cap,
+                                   int32_t* __restrict__ n_under, int64_t B, uint32_t first, uint32_t nthreads) {
+    const unsigned long long offered = *cand_count;
+    if (offered > (unsigned long long)cand_cap) {
+        if (n_under)
+            for (int64_t b = first; b < B; b += nthreads) n_under[b] = -1;
+        return;
+    }
+    const uint32_t n = (uint32_t)offered;
     for (uint32_t c = first; c < n; c += nthreads) {
         Cand r = cand[c];
         if (r.idx >= N) { r.b = -1; cand[c] = r; continue; }        // a padding copy of the last point
@@ -53,11 +62,11 @@ k_finalize(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int
            const GridDev* __restrict__ grids, const int32_t* __restrict__ grid_of_b,
            const double* __restrict__ T_rel, const double* __restrict__ bound, double tau, int64_t b_begin, int64_t Bc,
            const uint32_t* __restrict__ subkeys, int64_t nsub, int all_tiles, int emit_under,
-           Cand* __restrict__ cand, uint32_t* __restrict__ cand_count, uint32_t cand_cap,
+           Cand* __restrict__ cand, unsigned long long* __restrict__ cand_count, uint32_t cand_cap,
            int32_t* __restrict__ n_under, double* __restrict__ dmin, int64_t* __restrict__ argmin) {
     const int tid = threadIdx.x;
     if ((int64_t)blockIdx.x >= Bc) {
-        recheck_candidates(pts, perm, N, grids, grid_of_b, T_rel, bound, cand, cand_count, cand_cap, n_under,
+        recheck_candidates(pts, perm, N, grids, grid_of_b, T_rel, bound, cand, cand_count, cand_cap, n_under, b_begin + Bc,
                            (uint32_t)((blockIdx.x - Bc) * kFinThreads + tid), (uint32_t)((gridDim.x - Bc) * kFinThreads));
         return;
     }
@@ -115,8 +124,8 @@ k_finalize(const float4* __restrict__ pts, const int32_t* __restrict__ perm, int
             int64_t oi = perm[i];
             if (lex_less(d, oi, best, besti)) { best = d; besti = oi; }
             if (d < bnd && bnd < (double)INFINITY) {        // fp64 mode: final under-bound entries
-                uint32_t slot = atomicAdd(cand_count, 1u);
-                if (slot < cand_cap) { Cand c; c.b = (int32_t)b; c.idx = (int32_t)oi; c.d = d; cand[slot] = c; }
+                const unsigned long long slot = atomicAdd(cand_count, 1ull);      // n_under stays exact past the capacity
+                if (slot < (unsigned long long)cand_cap) { Cand c; c.b = (int32_t)b; c.idx = (int32_t)oi; c.d = d; cand[slot] = c; }
                 if (n_under) atomicAdd(n_under + b, 1);
             }
         }

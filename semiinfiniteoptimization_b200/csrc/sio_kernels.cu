@@ -213,7 +213,7 @@ template <bool kInside>
 __device__ __forceinline__ float warp_subtile_min(const XfRec& r, const GridK& g, const float (&px)[kPtsPerThread],
                                                   const float (&py)[kPtsPerThread], const float (&pz)[kPtsPerThread],
                                                   int32_t b, int32_t base, int lane, Cand* __restrict__ cand,
-                                                  uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
+                                                  unsigned long long* __restrict__ cand_count, uint32_t cand_cap) {
     float d[kPtsPerThread];
 #pragma unroll
     for (int j = 0; j < kPtsPerThread; ++j) {
@@ -228,8 +228,9 @@ __device__ __forceinline__ float warp_subtile_min(const XfRec& r, const GridK& g
 #pragma unroll
         for (int j = 0; j < kPtsPerThread; ++j) {
             if (d[j] < r.thr) {
-                uint32_t slot = atomicAdd(cand_count, 1u);
-                if (slot < cand_cap) {
+                // the counter keeps counting past the capacity: the host entry points read it, grow the buffer and re-run
+                const unsigned long long slot = atomicAdd(cand_count, 1ull);
+                if (slot < (unsigned long long)cand_cap) {
                     Cand c; c.b = b; c.idx = base + j * 32 + lane; c.d = (double)d[j];
                     cand[slot] = c;
                 }
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 k_min_f32(const float4* __restrict__ pts, const float4* __restrict__ rep, const GridDev* __restrict__ grids,
           const int32_t* __restrict__ grid_of_b, const double* __restrict__ T_rel, const double* __restrict__ bound, double tau,
           int64_t b_begin, int64_t Bc, int32_t ntiles, int32_t xfchunk, uint32_t* __restrict__ subkeys, Cand* __restrict__ cand,
-          uint32_t* __restrict__ cand_count, uint32_t cand_cap, GridK gk) {
+          unsigned long long* __restrict__ cand_count, uint32_t cand_cap, GridK gk) {
     __shared__ XfRec sxf[kXfChunk];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t chunk = blockIdx.x / ntiles;
@@ -457,7 +458,7 @@ constexpr int kItemRun = 16;     // consecutive work items taken by one warp (th
 __global__ void __launch_bounds__(kThreads, 4)
 k_min_items(const float4* __restrict__ pts, const float4* __restrict__ rep, const XfRec* __restrict__ xf, int64_t b_begin,
             int64_t nsub, const uint32_t* __restrict__ items, const uint32_t* __restrict__ item_count,
-            uint32_t* __restrict__ subkeys, Cand* __restrict__ cand, uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
+            uint32_t* __restrict__ subkeys, Cand* __restrict__ cand, unsigned long long* __restrict__ cand_count, uint32_t cand_cap) {
     __shared__ XfRec sxf[kThreads / 32][kItemRun];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n = *item_count;
@@ -515,7 +516,7 @@ void launch_min_pruned(const MinArgs& a, cudaStream_t st) {
     const int64_t Bp = (a.Bc + 31) & ~(int64_t)31;
     k_prune_select<<<dim3((unsigned)((Bp + 255) / 256), (unsigned)((nsub + kSelectRows - 1) / kSelectRows)), 256, 0, st>>>(
         a.lb, a.ub, a.under_bound, nsub, a.b_begin, a.Bc, (float)a.tau, a.items, a.item_count);
-    k_min_items<<<148 * 4, kThreads, 0, st>>>(a.pts, a.rep, a.xf, a.b_begin, nsub, a.items, a.item_count, a.subkeys, a.cand,
+    k_min_items<<<(a.num_sms > 0 ? a.num_sms : 148) * 4, kThreads, 0, st>>>(a.pts, a.rep, a.xf, a.b_begin, nsub, a.items, a.item_count, a.subkeys, a.cand,
                                               a.cand_count, a.cand_cap);
 }
 

@@ -218,6 +218,17 @@ __global__ void k_ls_step(LsState S, LsSettings cfg) {
     S.go[p] = 0;
     if (!S.live[p] || S.ph[p] == 1) return;
     if (S.ph[p] == 0 && S.qdef[p]) { S.ph[p] = 1; return; }    // deferred: the answer comes from the background launch
+    if ((S.qstatus[p] & 0xff) == 3) {
+        // the QP kernel produced no step (its slack re-solve was infeasible too): the reference raises here
+        // (results.x is None, sip.py:358-378).  The problem stops with its own status instead of stepping along
+        // whatever S.dx holds.
+        S.status[p] = 2;
+        S.live[p] = 0;
+        S.ph[p] = 0;
+        S.gx[p] = S.gxc[p];
+        atomicAdd(S.counters + 5, 1ull);
+        return;
+    }
     const double* dx = S.dx + 6 * p;
     double n2 = 0.0;
     for (int i = 0; i < 6; ++i) n2 += dx[i] * dx[i];
@@ -296,6 +307,7 @@ __global__ void k_ls_init(LsState S, LsSettings cfg) {
     S.min_cv[p] = cfg.min_cv; S.status[p] = 0; S.niter[p] = 0;
     S.gx[p] = INFINITY; S.gx0[p] = INFINITY; S.gxc[p] = INFINITY;
     S.fx[p] = objective(S.Rdes + 9 * p, S.tdes + 3 * p, S.R + 9 * p, S.t + 3 * p, nullptr);
+    for (int i = 0; i < 6; ++i) S.dx[6 * p + i] = 0.0;     // the arena is reused across calls
 }
 
 static unsigned grid_for(int64_t n) { return (unsigned)((n + kLsThreads - 1) / kLsThreads); }

@@ -28,7 +28,7 @@ struct LsState {
     double *dxdes, *dx, *Rn, *tn, *fxn, *gxn, *sorig, *metric;
     double *qW, *qlo, *qhi; int32_t* qk; int32_t* qstatus;
     int32_t* list; unsigned long long* counters;      // [0] sweep list length, [1] live problems, [2] outer iterations, [3] slot overflows,
-                                                      // [4] problems doing anything this round
+                                                      // [4] problems doing anything this round, [5] problems stopped because their QP had no solution
     double *T_rel, *bound, *dmin; int64_t* arg;
 };
 

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(built):
     lib = ctypes.CDLL(_abi.LIB_PATH)
     for name in sorted(declared):
         assert hasattr(lib, name), "libsio_b200.so does not export %s" % name
-    assert lib.sio_abi_version() == 1
+    assert lib.sio_abi_version() == int(re.search(r"#define SIO_ABI_VERSION (\d+)", hdr).group(1))
 
 
 def test_no_cpu_fallback_without_device(built):
@@ -125,6 +125,30 @@ def test_oracle_min_distance_and_value_consistency(O):
     bound = np.full(len(T), np.median(dmin))
     d2, a2 = O.min_distance(G, cloud, T, bound=bound)
     assert np.array_equal(a2 >= 0, dmin < bound) and np.array_equal(d2, dmin)
+
+
+def test_oracle_under_set_and_its_fingerprints(O):
+    """The under-bound list (two-pass, all threads) against the numpy restatement, and the per-transform fingerprints
+    the full-size GPU test compares instead of the explicit list."""
+    vg = util.fixture_geometry("cube").convert("VolumeGrid", 0.05).getVolumeGrid()
+    G = O.Grid(vg.values, vg.bmin, vg.bmax)
+    cloud = (util.fixture_geometry("m797").convert("PointCloud", 0.02).getPointCloud().points + [0.3, 0, 0]).astype(np.float32)
+    T = util.invert12(util.random_poses(10, 7, rot=0.3, trans=0.3, center=(0.2, 0.2, 0.2)))
+    bound = np.array([0.01, np.inf, -0.02, 0.0, 0.05, -1.0, 0.02])
+    n, ob, oi, od = O.under(G, cloud, T, bound)
+    want_b, want_i, want_d = [], [], []
+    for b in range(len(T)):
+        d = O.cloud_query(G, cloud, T[b], want_grad=False)[0]
+        sel = np.nonzero(d < bound[b])[0] if np.isfinite(bound[b]) else np.zeros(0, dtype=np.int64)
+        want_b += [b] * len(sel); want_i += list(sel); want_d += list(d[sel])
+    assert n == len(want_b) > 0
+    assert np.array_equal(ob, want_b) and np.array_equal(oi, want_i) and np.array_equal(od, want_d)
+    cnt, isum, dsum = O.under_counts(G, cloud, T, bound)
+    assert np.array_equal(cnt, np.bincount(ob, minlength=len(T)))
+    assert np.array_equal(isum, np.bincount(ob, weights=oi.astype(float), minlength=len(T)).astype(np.int64))
+    assert np.abs(dsum - np.bincount(ob, weights=od, minlength=len(T))).max() < 1e-12
+    n2, b2, _, _ = O.under(G, cloud, T, bound, cap=5)            # a capacity below the count: count exact, list truncated
+    assert n2 == n and len(b2) == 5
 
 
 def test_oracle_fk_and_chain_rows_vs_host_model(O):
