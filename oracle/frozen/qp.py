@@ -168,17 +168,15 @@ def solve_qp(P, q, A, l, u, eps_abs=1e-5, eps_rel=None, max_iter=4000, rho=0.1, 
     return QPResult(x if status != "primal infeasible" else None, y, status, it, r_prim, r_dual)
 
 
-def _polish(P, q, A, l, u, x, y, sparse, delta=1e-7, tol=1e-7):
+def _polish(P, q, A, l, u, x, y, sparse, delta=1e-10, tol=1e-7):
     """Solve the equality-constrained QP on the active set the ADMM iterate identifies; keep the
-    result only if it is feasible and no worse."""
+    result only if it is feasible and its multipliers have the signs of a minimiser (then it IS the minimiser)."""
     Ax = A @ x
     lo = (y < -1e-9) | (Ax - l < 1e-7)
     up = (y > 1e-9) | (u - Ax < 1e-7)
     lo &= l > -INF / 2
     up &= u < INF / 2
-    act = np.nonzero(lo | up)[0]
-    if len(act) == 0:
-        return None
+    act = np.nonzero(lo | up)[0]          # may be empty: the candidate is then the unconstrained minimiser
     rhs_c = np.where(lo[act], l[act], u[act])
     n = len(q)
     try:
@@ -199,13 +197,20 @@ def _polish(P, q, A, l, u, x, y, sparse, delta=1e-7, tol=1e-7):
     except Exception:
         return None
     xp = sol[:n]
-    if not np.all(np.isfinite(xp)):
+    lam = sol[n:]
+    if not np.all(np.isfinite(sol)):
         return None
     Axp = A @ xp
     if np.any(Axp < l - tol) or np.any(Axp > u + tol):
         return None
-    f = lambda v: 0.5 * v @ (P @ v) + q @ v
-    if f(xp) > f(x) + 1e-9 * (1 + abs(f(x))):
+    # KKT test instead of an objective comparison (the ADMM iterate is slightly infeasible, so its objective is LOWER than
+    # the minimiser's and the comparison used to reject most polishes): stationarity holds by construction
+    # (P xp + q + Aa' lam = 0), xp is feasible, so xp is the minimiser iff no multiplier has the wrong sign --
+    # lam <= 0 on a row held at its lower bound, lam >= 0 at its upper bound
+    lamtol = 1e-9 * (1.0 + (np.abs(lam).max() if len(lam) else 0.0))
+    only_lo = lo[act] & ~up[act]
+    only_up = up[act] & ~lo[act]
+    if np.any(lam[only_lo] > lamtol) or np.any(lam[only_up] < -lamtol):
         return None
     return xp
 

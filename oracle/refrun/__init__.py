@@ -9,11 +9,11 @@ objective.py logic rather than from a restatement:
                  applies the mechanical py2 -> py3 source fixes in memory (xrange, iteritems,
                  raw_input, one print statement, one implicit relative import) and executes them as
                  the package `semiinfinite_ref`
-  klampt_shim.py stand-in `klampt` modules: the data model is the host substrate of this repository
-                 (_host/), the geometric queries (distance_point / distance_ext) are the CPU oracle
+  klampt_shim.py stand-in `klampt` modules: geometry containers from the host substrate (_host/geometry.py),
+                 kinematics / so3 / se3 / trajectories from the frozen copies (oracle/frozen/), the geometric queries (distance_point / distance_ext) are the CPU oracle
                  (oracle/oracle.py) -- so the Klampt-side arithmetic is still a
                  restatement ("parity unpinned" for that layer), while everything above it is pinned
-  osqp_shim.py   stand-in `osqp` module on the host ADMM solver (_host/qp.py)
+  osqp_shim.py   stand-in `osqp` module on the frozen ADMM solver (oracle/frozen/qp.py)
 
 Only tools/make_golden.py and tests/ import this; it needs /root/reference and therefore only runs
 in the build container, never on the GPU box.

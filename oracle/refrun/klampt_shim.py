@@ -1,7 +1,9 @@
 """Stand-in `klampt` package for running the reference's own Python (see oracle/refrun/__init__.py).
 
-Data model = this repository's host substrate (`_host/`: Geometry3D, PointCloud, VolumeGrid,
-RobotModel, Trajectory, so3/se3/vectorops with Klampt's conventions).  The two geometric queries the
+Data model: geometry containers and file loaders come from this repository's host substrate
+(`_host/geometry.py`: Geometry3D, PointCloud, VolumeGrid -- inputs, identical on both sides of every
+comparison); the MATH (RobotModel FK and Jacobians, Trajectory, so3/se3/vectorops with Klampt's
+conventions) comes from the frozen copies under oracle/frozen/.  The two geometric queries the
 reference issues (geometryopt.py:104-108, 124-127, 139, 153) are answered by the CPU oracle:
 
     Geometry3D.distance_point(pt[, settings])   -> oracle.query      
@@ -16,9 +18,9 @@ import types
 import numpy as np
 
 from oracle import oracle as O
-from semiinfiniteoptimization_b200._host import geometry as _hg
-from semiinfiniteoptimization_b200._host import robot as _hr
-from semiinfiniteoptimization_b200._host import se3, so3, trajectory as _ht, vectorops
+from semiinfiniteoptimization_b200._host import geometry as _hg       # data containers + file loaders only (inputs)
+from oracle.frozen import robot as _hr                                 # FK / Jacobians / so3 / se3 / trajectories: frozen copies,
+from oracle.frozen import se3, so3, trajectory as _ht, vectorops       # so product changes cannot move the goldens
 
 
 class DistanceQuerySettings:

@@ -1,12 +1,14 @@
-"""Stand-in `osqp` module (OSQP is absent from this image) on the host ADMM solver `_host/qp.py` --
-the same solver the product's sip.py calls, so the reference run and the product see identical QP
-answers for identical QP data.  Interface used by the reference: sip.py:302, 327-331, 355-357."""
+"""Stand-in `osqp` module (OSQP is absent from this image) on the FROZEN solver oracle/frozen/qp.py -- a
+restatement of OSQP's published algorithm that no longer follows the product's solvers (round-1 verdict:
+"goldens move with the product").  The product's QP paths (host numpy, native hostqp.c, device k_sip_qp)
+are tested against the goldens this produces, at a stated tolerance.
+Interface used by the reference: sip.py:302, 327-331, 355-357."""
 import sys
 import types
 
 import numpy as np
 
-from semiinfiniteoptimization_b200._host import qp as _qp
+from oracle.frozen import qp as _qp
 
 
 class _Info:
@@ -29,7 +31,7 @@ class OSQP:
         if "eps_abs" in self.settings:
             kw["eps_abs"] = self.settings["eps_abs"]
         P, A = self.P, self.A
-        if P.shape[0] <= _qp.DENSE_MAX_VARS:          # the same dense/sparse rule as the product's sip.py
+        if P.shape[0] <= _qp.DENSE_MAX_VARS:          # dense KKT factorisation for the small problems, sparse LU above
             P, A = P.toarray(), A.toarray()
         r = _qp.solve_qp(P, self.q, A, self.l, self.u, **kw)
         n = len(self.q)

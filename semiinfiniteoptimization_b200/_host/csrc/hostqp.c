@@ -196,8 +196,8 @@ static int admm(int n, int m, const double* Pd, const double* q, const double* A
             int up = ((y[r] > 1e-9) || (u[r] - Ax[r] < 1e-7)) && u[r] < HQP_INF / 2;
             if (lo || up) { act[na] = r; rhs_c[na] = lo ? l[r] : u[r]; ++na; }
         }
-        if (na > 0) {
-            const double delta = 1e-7, tol = 1e-7;
+        {                                        /* na == 0: the candidate is the unconstrained minimiser */
+            const double delta = 1e-10, tol = 1e-7;
             int N = n + na;
             double* M = kkt;
             double* b = kkt + (size_t)N * N;
@@ -211,14 +211,24 @@ static int admm(int n, int m, const double* Pd, const double* q, const double* A
             if (lu_solve(M, b, N) == 0) {
                 int ok = 1;
                 for (int i = 0; i < n; ++i) if (!isfinite(b[i])) ok = 0;
-                double f0 = 0.0, f1 = 0.0;
-                for (int i = 0; i < n && ok; ++i) { f0 += 0.5 * Pd[i] * x[i] * x[i] + q[i] * x[i]; f1 += 0.5 * Pd[i] * b[i] * b[i] + q[i] * b[i]; }
                 for (int r = 0; r < m && ok; ++r) {
                     double s = 0.0;
                     for (int i = 0; i < n; ++i) s += A[r * n + i] * b[i];
                     if (s < l[r] - tol || s > u[r] + tol) ok = 0;
                 }
-                if (ok && !(f1 > f0 + 1e-9 * (1 + fabs(f0)))) for (int i = 0; i < n; ++i) x[i] = b[i];
+                /* KKT test (qp.py _polish): feasible + stationary by construction, so it is the minimiser iff no
+                 * multiplier has the wrong sign (<= 0 at a lower bound, >= 0 at an upper bound) */
+                double lmax = 0.0;
+                for (int a = 0; a < na && ok; ++a) { if (!isfinite(b[n + a])) ok = 0; else if (fabs(b[n + a]) > lmax) lmax = fabs(b[n + a]); }
+                const double lamtol = 1e-9 * (1.0 + lmax);
+                for (int a = 0; a < na && ok; ++a) {
+                    const int r = act[a];
+                    const int lo = ((y[r] < -1e-9) || (Ax[r] - l[r] < 1e-7)) && l[r] > -HQP_INF / 2;
+                    const int up = ((y[r] > 1e-9) || (u[r] - Ax[r] < 1e-7)) && u[r] < HQP_INF / 2;
+                    if (lo && !up && b[n + a] > lamtol) ok = 0;
+                    if (up && !lo && b[n + a] < -lamtol) ok = 0;
+                }
+                if (ok) for (int i = 0; i < n; ++i) x[i] = b[i];
             }
         }
     }

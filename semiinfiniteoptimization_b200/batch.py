@@ -48,7 +48,7 @@ class BatchResult:
         self.B = B
         self.T = None                    # (B,12) final poses, row-major 3x4
         self._status = ['not converged'] * B if per_problem_lists else None
-        self.status_codes = None         # (B,) int32: 1 = local optimum, 0 = not converged
+        self.status_codes = None         # (B,) int32: 1 = local optimum, 0 = not converged, 2 = QP without a solution
         self.num_iterations = np.zeros(B, dtype=np.int64)
         self.fx = np.zeros(B)
         self.gx = np.full(B, np.inf)
@@ -65,7 +65,8 @@ class BatchResult:
     @property
     def status(self):
         if self._status is None:
-            self._status = ['local optimum' if c == 1 else 'not converged' for c in self.status_codes]
+            names = {1: 'local optimum', 0: 'not converged', 2: 'qp failed'}          # 2: the reference raises there (sip.py:358-378)
+            self._status = [names.get(int(c), 'not converged') for c in self.status_codes]
         return self._status
 
     @status.setter

@@ -421,18 +421,19 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
     }
     if (st != kAdmmSolved) return st;
     // ---- polish on the active set (qp.py _polish): KKT system over [variables | active rows] ----------------
-    int flag[NR];
+    int flag[NR], side[NR];                                // side: -1 held at the lower bound only, +1 upper only, 0 both / none
     double rhs[NR];
 #pragma unroll
     for (int s = 0; s < NR; ++s) {
         const bool lo = R.have[s] && ((y[s] < -1e-9) || (Ax[s] - R.l[s] < 1e-7)) && R.l[s] > -kInf / 2;
         const bool up = R.have[s] && ((y[s] > 1e-9) || (R.u[s] - Ax[s] < 1e-7)) && R.u[s] < kInf / 2;
         flag[s] = lo || up;
+        side[s] = (lo && !up) ? -1 : ((up && !lo) ? 1 : 0);
         rhs[s] = lo ? R.l[s] : R.u[s];
     }
     const unsigned m0 = __ballot_sync(0xffffffffu, flag[0]), m1 = NR > 1 ? __ballot_sync(0xffffffffu, flag[NR - 1]) : 0u;
     const int na = __popc(m0) + __popc(m1);
-    if (na == 0) return kAdmmSolved;
+    // na == 0: the candidate is the unconstrained minimiser (the system below is then diagonal)
     // Unknowns [x | multipliers of the active rows].  A slack variable s_r (weight pen + delta, one entry in its own
     // row) is eliminated in closed form: s_r = -lambda_r / (pen + delta), which adds 1 / (pen + delta) to that row's
     // -delta diagonal; slack variables of inactive rows are zero.
@@ -441,7 +442,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
     double* bb = M + NN * NN;
     for (int e = lane; e < NN * (NN + 1); e += 32) M[e] = 0.0;
     __syncwarp();
-    const double delta = 1e-7;
+    const double delta = 1e-10;
     if (lane < N) { M[lane * NN + lane] = Pd[lane] + delta; bb[lane] = -q[lane]; }
     int idx[NR];
 #pragma unroll
@@ -461,33 +462,39 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
     double xp[N], sp[NR];
 #pragma unroll
     for (int s = 0; s < NR; ++s) sp[s] = 0.0;
-    double f0 = 0.0, f1 = 0.0, fs0 = 0.0, fs1 = 0.0;
     int bad = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         xp[i] = bb[i];
         if (!isfinite(xp[i])) bad = 1;
-        f0 += 0.5 * Pd[i] * x[i] * x[i] + q[i] * x[i];
-        f1 += 0.5 * Pd[i] * xp[i] * xp[i] + q[i] * xp[i];
     }
+    // KKT test (qp.py _polish): xp is stationary by construction; feasible + multipliers of the right sign
+    // (<= 0 on a row held at its lower bound, >= 0 at its upper bound) = the minimiser
+    double lam[NR], lmax = 0.0;
+#pragma unroll
+    for (int s = 0; s < NR; ++s) {
+        lam[s] = flag[s] ? bb[idx[s]] : 0.0;
+        if (!isfinite(lam[s])) bad = 1;
+        lmax = fmax(lmax, fabs(lam[s]));
+    }
+    lmax = warp_max(lmax);
+    const double lamtol = 1e-9 * (1.0 + lmax);
 #pragma unroll
     for (int s = 0; s < NR; ++s) {
         double v = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) v += R.a[s][i] * xp[i];
         if (SLACK && R.slack[s]) {
-            sp[s] = flag[s] ? -bb[idx[s]] / (pen + delta) : 0.0;
+            sp[s] = flag[s] ? -lam[s] / (pen + delta) : 0.0;
             if (!isfinite(sp[s])) bad = 1;
             v += sp[s];
-            fs0 += 0.5 * pen * sv[s] * sv[s];
-            fs1 += 0.5 * pen * sp[s] * sp[s];
         }
         if (R.have[s] && (v < R.l[s] - 1e-7 || v > R.u[s] + 1e-7)) bad = 1;
+        if ((side[s] < 0 && lam[s] > lamtol) || (side[s] > 0 && lam[s] < -lamtol)) bad = 1;
     }
-    if (SLACK) { f0 += warp_sum(fs0); f1 += warp_sum(fs1); }
     bad = __any_sync(0xffffffffu, bad);
     __syncwarp();
-    if (__all_sync(0xffffffffu, !bad && !(f1 > f0 + 1e-9 * (1 + fabs(f0))))) {
+    if (!bad) {
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = xp[i];
 #pragma unroll

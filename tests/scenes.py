@@ -24,6 +24,18 @@ def family(kind):
     return geometryopt
 
 
+def _robot_modules(kind):
+    """The reference's code runs on the FROZEN kinematics (oracle/frozen), the restatement and the product on the
+    product's host substrate: the goldens pin the latter against the former."""
+    if kind == 'reference':
+        from oracle.frozen.robot import WorldModel
+        from oracle.frozen.trajectory import RobotTrajectory
+    else:
+        from semiinfiniteoptimization_b200._host.robot import WorldModel
+        from semiinfiniteoptimization_b200._host.trajectory import RobotTrajectory
+    return WorldModel, RobotTrajectory
+
+
 def _names(kind):
     if kind == 'restated':
         return dict(PDG='RefPDG', Obj='RefObjectCollisionConstraint', Kin='RefRobotKinematicsCache',
@@ -33,7 +45,7 @@ def _names(kind):
 
 
 def c1_poses(n, seed=0):
-    from semiinfiniteoptimization_b200._host import so3
+    from oracle.frozen import so3          # inputs are generated with the frozen helpers: goldens do not move with the product
     rng = np.random.default_rng(seed)
     return [(so3.from_rotation_vector(rng.uniform(-0.3, 0.3, 3)),
              [float(rng.uniform(0.4, 1.0)), float(rng.uniform(-0.3, 0.5)), float(rng.uniform(-0.3, 0.5))]) for _ in range(n)]
@@ -41,7 +53,7 @@ def c1_poses(n, seed=0):
 
 def c1_scene(kind):
     """C1: cube SDF@0.05 (moving) vs m797 cloud@0.02 at (I,[1.2,0,0]) (geomopt.py:14-15, 43)."""
-    from semiinfiniteoptimization_b200._host import so3
+    from oracle.frozen import so3          # inputs are generated with the frozen helpers: goldens do not move with the product
     from semiinfiniteoptimization_b200._host.geometry import fixture_geometry
     mod, nm = family(kind), _names(kind)
     PDG = getattr(mod, nm['PDG'])
@@ -56,7 +68,7 @@ TREE_INTERIOR = (0.41, 0.06, 0.42)       # deepest interior sample of the m1062 
 def c2_scene(kind, gridres=0.01):
     """C2 as shipped: m1062 SDF@gridres (moving) vs the 397-point bunny cloud; the cloud's centroid is placed at the
     deepest interior point of the tree so the poses below start in contact."""
-    from semiinfiniteoptimization_b200._host import so3
+    from oracle.frozen import so3          # inputs are generated with the frozen helpers: goldens do not move with the product
     from semiinfiniteoptimization_b200._host.geometry import fixture_geometry
     mod, nm = family(kind), _names(kind)
     PDG = getattr(mod, nm['PDG'])
@@ -69,7 +81,7 @@ def c2_scene(kind, gridres=0.01):
 
 def c2_poses(n, seed=0):
     """Poses of the tree: rotation w ~ U(-0.3,0.3)^3 about TREE_INTERIOR, then a shift t ~ U(-0.03,0.03)^3."""
-    from semiinfiniteoptimization_b200._host import so3
+    from oracle.frozen import so3          # inputs are generated with the frozen helpers: goldens do not move with the product
     rng = np.random.default_rng(seed)
     c = np.asarray(TREE_INTERIOR)
     out = []
@@ -82,7 +94,7 @@ def c2_poses(n, seed=0):
 
 def c3_scene(kind):
     """C3: tx90_geom_test3.xml, declared synthetic link boxes, tree = m1062 x2 rotated; gridres = pcres = 0.02."""
-    from semiinfiniteoptimization_b200._host.robot import WorldModel
+    WorldModel, _ = _robot_modules(kind)
     mod, nm = family(kind), _names(kind)
     w = WorldModel()
     w.readFile("tx90_geom_test3.xml")
@@ -106,8 +118,7 @@ def c3_configs(robot, n, seed=3):
 def c4_scene(kind, chair_pos=CHAIR_IN_PATH):
     """C4: tx90_geom_test2.xml, robottrajopt_initial.path remeshed x6 -> 67 milestones (65 free, x in R^455), chair
     cloud only (gridres=None), link grids/clouds at 0.02 (robottrajopt.py:13-17, 70-71, 101-131)."""
-    from semiinfiniteoptimization_b200._host.robot import WorldModel
-    from semiinfiniteoptimization_b200._host.trajectory import RobotTrajectory
+    WorldModel, RobotTrajectory = _robot_modules(kind)
     mod, nm = family(kind), _names(kind)
     p0 = json.load(open(os.path.join(ROOT, "semiinfiniteoptimization_b200", "data", "paths.json")))["resources/robottrajopt_initial.path"]
     w = WorldModel()
@@ -130,6 +141,24 @@ def c4_scene(kind, chair_pos=CHAIR_IN_PATH):
     tc.tstart, tc.tend = traj.times[0], traj.times[-1]
     x = [float(v) for q in traj.milestones[1:-1] for v in q]
     return mod, robot, tc, con, traj, x
+
+
+def c5_scene(kind, context=None):
+    """C5: cube SDF@0.05 (moving) vs the declared synthetic 262,144-point scene cloud (scene2_1.pcd is missing from the
+    reference checkout), scene at the identity -- the geometry of BASELINE.json configs[4]."""
+    from semiinfiniteoptimization_b200 import workloads as W
+    from semiinfiniteoptimization_b200._host.geometry import Geometry3D, PointCloud
+    mod, nm = family(kind), _names(kind)
+    PDG = getattr(mod, nm['PDG'])
+    kw = {"context": context} if (kind == 'device' and context is not None) else {}
+    cube = PDG(W.c5_cube(), 0.05, None, **kw)
+    scene = PDG(Geometry3D(PointCloud(W.c5_scene_cloud())), None, 0.02, **kw)
+    return mod, cube, scene, getattr(mod, nm['Obj'])(cube, scene)
+
+
+def c5_sample_indices(n=64, total=65536):
+    """Every (total / n)-th of the 65,536 C5 problems (seed 3)."""
+    return list(range(0, total, total // n))[:n]
 
 
 def load_golden(name):

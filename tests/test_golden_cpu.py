@@ -68,7 +68,28 @@ def test_linear_field_is_reproduced_exactly(O):
     assert np.abs(d2 - ((lat @ a + c) + np.linalg.norm(out - inside, axis=1))).max() <= 2e-7
 
 
-def _run_pose_cases(golden, scene_fn, settings_kw=None):
+# Two comparisons against every golden (the goldens' QP answers come from the FROZEN solver
+# oracle/frozen/qp.py and no longer follow the product):
+#   'frozen'  : the restated host logic (sip.py, objectives, constraint classes) with the frozen solver plugged in
+#               -> pins the LOGIC, 1e-12 (observed: identical bits)
+#   'product' : the same with the product's own QP paths (native hqp_admm_diag / hqp_admm_banded + numpy polish)
+#               -> pins the product's SOLVERS against the frozen one, 1e-8 on whole SIP traces (observed <= 4e-11)
+QP_KINDS = [("frozen", 1e-12), ("product", 1e-8)]
+
+
+@pytest.fixture(params=QP_KINDS, ids=[k for k, _ in QP_KINDS])
+def qp_kind(request, monkeypatch):
+    kind, tol = request.param
+    if kind == "frozen":
+        import types
+        from oracle.frozen import qp as fq
+        from semiinfiniteoptimization_b200 import sip
+        monkeypatch.setattr(sip, "_qp", types.SimpleNamespace(solve_qp=fq.solve_qp, DENSE_MAX_VARS=fq.DENSE_MAX_VARS,
+                                                               NATIVE_BANDED=False, NATIVE_DENSE=False))
+    return tol
+
+
+def _run_pose_cases(golden, scene_fn, settings_kw=None, tol=1e-12):
     from semiinfiniteoptimization_b200 import geometryopt as G
     from semiinfiniteoptimization_b200 import sip
     mod, g1, g2, con = scene_fn('restated')
@@ -81,24 +102,43 @@ def _run_pose_cases(golden, scene_fn, settings_kw=None):
         res = sip.optimizeSemiInfinite(G.ObjectPoseObjective(T), [con], T, settings=st, verbose=0)
         assert len(res.trace) == len(case["trace"])
         for a, b in zip(res.trace, case["trace"]):
-            assert _pose_close(a, b, 1e-12)
-        assert _pose_close(res.x, case["T"], 1e-12)
+            assert _pose_close(a, b, tol)
+        assert _pose_close(res.x, case["T"], tol)
         assert len(res.instantiated_params[0]) == len(case["params"])
         for ya, yb in zip(res.instantiated_params[0], case["params"]):
-            assert np.allclose(ya, yb, atol=1e-12, rtol=0)
+            assert np.allclose(ya, yb, atol=1e-12, rtol=0)          # parameters are cloud points: identical or different
         nontrivial += len(case["trace"]) > 3
     return nontrivial
 
 
-def test_c1_restated_sip_reproduces_the_reference():
-    assert _run_pose_cases(scenes.load_golden("c1_pose.json"), scenes.c1_scene) >= 5
+def test_c1_restated_sip_reproduces_the_reference(qp_kind):
+    assert _run_pose_cases(scenes.load_golden("c1_pose.json"), scenes.c1_scene, tol=qp_kind) >= 5
 
 
-def test_c2_restated_sip_reproduces_the_reference():
-    assert _run_pose_cases(scenes.load_golden("c2_pose.json"), scenes.c2_scene, {"max_iters": 20}) >= 4
+def test_c2_restated_sip_reproduces_the_reference(qp_kind):
+    assert _run_pose_cases(scenes.load_golden("c2_pose.json"), scenes.c2_scene, {"max_iters": 20}, tol=qp_kind) >= 4
 
 
-def test_c3_restated_sip_reproduces_the_reference():
+def test_c5_restated_sip_reproduces_the_reference(qp_kind):
+    """Six of the 64 sampled C5 problems (the 262,144-point scene makes each oracle call 5 ms on one core)."""
+    from semiinfiniteoptimization_b200 import geometryopt as G
+    from semiinfiniteoptimization_b200 import sip
+    golden = scenes.load_golden("c5_pose.json")
+    mod, cube, scene, con = scenes.c5_scene('restated')
+    picked = [c for c in golden["cases"] if 5 <= c["iterations"] <= 30][:5] + [c for c in golden["cases"] if c["iterations"] == 0][:1]
+    assert len(picked) == 6
+    for case in picked:
+        T = (case["Tinit"][0], case["Tinit"][1])
+        res = sip.optimizeSemiInfinite(G.ObjectPoseObjective(T), [con], T, settings=sip.SemiInfiniteOptimizationSettings(), verbose=0)
+        assert res.status == case["status"] and res.num_iterations == case["num_iterations"] and len(res.trace) - 1 == case["iterations"]
+        assert _pose_close(res.x, case["T"], qp_kind)
+        assert abs(res.fx - case["fx"]) <= qp_kind
+        assert len(res.instantiated_params[0]) == len(case["params"])
+        for ya, yb in zip(res.instantiated_params[0], case["params"]):
+            assert np.allclose(ya, yb, atol=1e-12, rtol=0)
+
+
+def test_c3_restated_sip_reproduces_the_reference(qp_kind):
     from semiinfiniteoptimization_b200 import geometryopt as G
     from semiinfiniteoptimization_b200 import sip
     golden = scenes.load_golden("c3_robot.json")
@@ -110,13 +150,13 @@ def test_c3_restated_sip_reproduces_the_reference():
         res = sip.optimizeSemiInfinite(G.RobotConfigObjective(robot, case["qdes"]), cons, [0.0] * 7, np.asarray(qmin), np.asarray(qmax),
                                        settings=st, verbose=0)
         assert len(res.trace) == len(case["trace"])
-        assert np.allclose(np.array(res.trace), np.array(case["trace"]), atol=1e-12, rtol=0)
+        assert np.allclose(np.array(res.trace), np.array(case["trace"]), atol=qp_kind, rtol=0)
         assert [len(p) for p in res.instantiated_params] == [len(p) for p in case["params"]]
         for pa, pb in zip(res.instantiated_params, case["params"]):
             assert np.allclose(np.array(pa).reshape(-1), np.array(pb).reshape(-1), atol=1e-12, rtol=0)
 
 
-def test_c4_restated_trajectory_constraint_reproduces_the_reference():
+def test_c4_restated_trajectory_constraint_reproduces_the_reference(qp_kind):
     from semiinfiniteoptimization_b200 import geometryopt as G
     from semiinfiniteoptimization_b200 import sip
     golden = scenes.load_golden("c4_traj.json")
@@ -138,8 +178,8 @@ def test_c4_restated_trajectory_constraint_reproduces_the_reference():
     res = sip.optimizeSemiInfinite(G.TrajectoryLengthObjective(tc), [con], np.asarray(x), np.hstack([qmin] * 65), np.hstack([qmax] * 65),
                                    settings=st, verbose=0)
     assert len(res.trace) == len(golden["trace"]) >= 4
-    assert np.allclose(np.array(res.trace), np.array(golden["trace"]), atol=1e-12, rtol=0)
-    assert np.allclose(np.array(res.instantiated_params[0]), np.array(golden["params"][0]), atol=1e-12, rtol=0)
+    assert np.allclose(np.array(res.trace), np.array(golden["trace"]), atol=qp_kind, rtol=0)
+    assert np.allclose(np.array(res.instantiated_params[0]), np.array(golden["params"][0]), atol=qp_kind, rtol=0)
 
 
 def test_class_level_goldens_on_the_restatement():

@@ -320,6 +320,77 @@ def test_c4_solutions_match(G, R, c4):
     assert res.gx0[0] < -0.01 and len(res.trace) >= 3          # it really started in collision and moved
 
 
+def _brute_dense_sweep(R, robot2, tc2, con2, xa, levels):
+    """The idea of the reference's commented brute-force check (gopt:865-888), at the benchmark's sampling density:
+    every milestone and every interior sample k / 2^levels of every edge x every active link, each a brute-force
+    cloud-vs-grid minimum on the CPU oracle (oracle.fk for the link frames, oracle.min_distance for the minima; the
+    visiting order -- time-major, then link -- with a strict '<' decides ties, as in the reference's loops).
+    Independent of the product: no device, no scheduler."""
+    from oracle import oracle as O
+    tc2.set(list(xa))
+    traj = tc2.trajectory
+    ms = np.asarray(traj.milestones, dtype=np.float64)
+    times = np.asarray(traj.times, dtype=np.float64)
+    K = 1 << levels
+    us = np.arange(K) / K
+    q = np.vstack([(ms[:-1, None, :] + us[None, :, None] * (ms[1:, None, :] - ms[:-1, None, :])).reshape(-1, ms.shape[1]), ms[-1:]])
+    t = np.concatenate([(times[:-1, None] + us[None, :] * (times[1:, None] - times[:-1, None])).reshape(-1), times[-1:]])
+    links = list(con2.activeLinks) if hasattr(con2, "activeLinks") else [l for l in range(1, robot2.numLinks())]
+    orob = O.Robot([robot2.link(i).getParent() for i in range(robot2.numLinks())],
+                   [se3_to12(robot2.link(i).getParentTransform()) for i in range(robot2.numLinks())],
+                   [robot2.link(i).getAxis() for i in range(robot2.numLinks())])
+    TL = O.fk(orob, q)                                     # (S, n_links, 12)
+    best = (np.inf, None)
+    for j, env in enumerate(con2.envs):
+        Tenv = np.asarray(env.T12(), dtype=np.float64).reshape(3, 4)
+        grids = [tc2.kinematics.geometry[l].G for l in links]
+        T = TL[:, links, :].reshape(-1, 3, 4)
+        Ti = np.empty_like(T)
+        Ti[:, :, :3] = np.transpose(T[:, :, :3], (0, 2, 1))
+        Ti[:, :, 3] = -np.einsum('bji,bj->bi', T[:, :, :3], T[:, :, 3])
+        Trel = np.empty_like(T)
+        Trel[:, :, :3] = Ti[:, :, :3] @ Tenv[:, :3]
+        Trel[:, :, 3] = Ti[:, :, :3] @ Tenv[:, 3] + Ti[:, :, 3]
+        gob = np.tile(np.arange(len(links), dtype=np.int32), len(q))
+        dmin, arg = O.min_distance(grids, env.cloud32, Trel.reshape(-1, 12), grid_of_b=gob)
+        flat = int(np.argmin(dmin))                        # first occurrence = time-major, then link
+        if dmin[flat] < best[0]:
+            s, k = divmod(flat, len(links))
+            p = env.cloud32[int(arg[flat])].astype(np.float64)
+            best = (float(dmin[flat]), (links[k], j, float(t[s])) + tuple(float(v) for v in Tenv[:, :3] @ p + Tenv[:, 3]))
+    tc2.clear()
+    return best
+
+
+def se3_to12(T):
+    R, t = np.asarray(T[0], dtype=float).reshape(3, 3).T, np.asarray(T[1], dtype=float)
+    return np.column_stack([R, t]).reshape(-1)
+
+
+@pytest.mark.parametrize("chair_pos", [None, CHAIR_IN_PATH])
+def test_trajectory_minvalue_256_samples_per_edge_equals_brute_dense_oracle_sweep(G, R, c4, chair_pos):
+    """BASELINE.json configs[3] as the benchmark states it -- 256 time samples per edge (LEVELS = 8): the device sweep
+    (Lipschitz-scheduled and dense) against a brute dense sweep on the CPU oracle.  VERDICT r1 weak #3."""
+    (robot, tc, con, traj, x), (robot2, tc2, con2, traj2, x2) = c4(G, False, chair_pos), c4(R, True, chair_pos)
+    rng = np.random.default_rng(11)
+    con.LEVELS = 8
+    try:
+        for trial in range(3):
+            xa = np.asarray(x) + (rng.normal(0, 0.05, len(x)) if trial else 0)
+            want = _brute_dense_sweep(R, robot2, tc2, con2, xa, 8)
+            for sched in (True, False):
+                G.LIPSCHITZ_SCHEDULE = sched
+                con.setx(list(xa))
+                got = con.minvalue(list(xa))
+                con.clearx()
+                assert abs(got[0] - want[0]) <= 1e-9, (got, want)
+                assert got[1][0] == want[1][0] and got[1][1] == want[1][1] and abs(got[1][2] - want[1][2]) <= 1e-12
+                assert np.allclose(got[1][3:], want[1][3:], atol=1e-9)
+    finally:
+        G.LIPSCHITZ_SCHEDULE = True
+        con.LEVELS = 7
+
+
 @pytest.mark.parametrize("chair_pos", [None, CHAIR_IN_PATH])
 def test_lipschitz_scheduled_sweep_equals_dense_sweep(G, R, c4, chair_pos):
     """Row f2: milestones first, interior samples only for (edge, link) pairs whose Lipschitz lower bound can still win

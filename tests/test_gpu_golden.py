@@ -1,5 +1,5 @@
 """Device-backed drop-in classes against the committed golden vectors (tests/golden/: outputs of the
-REFERENCE's own Python, see tools/make_golden.py) on BASELINE.json's configurations C1-C4.
+REFERENCE's own Python, see tools/make_golden.py) on BASELINE.json's configurations C1-C5.
 
 Tolerances: single oracle calls agree with the float64 goldens to 1e-9 (the device's float64
 re-check makes minima and arg-min points exact; the value kernels differ only in operation order);
@@ -43,6 +43,56 @@ def test_c1_solutions_equal_the_reference(ctx):
 
 def test_c2_solutions_equal_the_reference(ctx):
     assert _pose_cases(ctx, scenes.load_golden("c2_pose.json"), scenes.c2_scene, {"max_iters": 20}) >= 4
+
+
+def _se3_to12(T):
+    R, t = np.asarray(T[0], dtype=float), np.asarray(T[1], dtype=float)
+    return np.concatenate([np.column_stack([R.reshape(3, 3).T, t]).reshape(-1)])       # Klampt R is column-major
+
+
+def test_c5_solutions_equal_the_reference(ctx):
+    """BASELINE.json configs[4]: 64 of the 65,536 problems, reference's own optimizeCollFree (tests/golden/c5_pose.json)
+    against (a) the drop-in optimizeCollFree on the device-backed classes, one problem at a time, and (b) the
+    device-resident lock-step solver optimizeCollFreeBatchDevice: status, outer iterations, final pose <= 1e-6,
+    instantiated parameters identical."""
+    from semiinfiniteoptimization_b200 import batch, sip
+    golden = scenes.load_golden("c5_pose.json")
+    cases = golden["cases"]
+    assert len(cases) >= 64 and sum(c["iterations"] >= 5 for c in cases) >= 20
+    mod, cube, scene, con = scenes.c5_scene('device', context=ctx)
+    poses = [(c["Tinit"][0], c["Tinit"][1]) for c in cases]
+    # (a) the reference's call shape, problem by problem (every 4th case: each is up to 50 x 2 sweeps of 262,144 points)
+    for case in cases[::4]:
+        T = (case["Tinit"][0], case["Tinit"][1])
+        out = mod.optimizeCollFree(cube, scene, T, settings=sip.SemiInfiniteOptimizationSettings(), verbose=0)
+        assert len(out[1]) - 1 == case["iterations"]
+        assert _pose_close(out[0], case["T"], 1e-6)
+        assert len(out[3]) == len(case["params"])
+        for ya, yb in zip(out[3], case["params"]):
+            assert np.allclose(ya, yb, atol=1e-9, rtol=0)
+        if "trace" in case:
+            for a, b in zip(out[1], case["trace"]):
+                assert _pose_close(a, b, 1e-6)
+    # (b) all 64 at once on the device
+    res = batch.optimizeCollFreeBatchDevice(cube, scene, poses, settings=sip.SemiInfiniteOptimizationSettings(), context=ctx)
+    assert res.slot_overflows == 0
+    want_T = np.array([_se3_to12(c["T"]) for c in cases])
+    want_it = np.array([c["num_iterations"] for c in cases])          # res.num_iterations of the reference (sip.py:847, 1217)
+    want_status = [c["status"] for c in cases]
+    same_status = np.array([a == b for a, b in zip(res.status, want_status)])
+    same_it = np.asarray(res.num_iterations) == want_it
+    close = np.abs(res.T - want_T).max(1) <= 1e-6
+    assert same_status.all(), [(i, res.status[i], want_status[i]) for i in np.nonzero(~same_status)[0]]
+    assert same_it.all(), [(i, int(res.num_iterations[i]), int(want_it[i])) for i in np.nonzero(~same_it)[0]]
+    assert close.all(), np.abs(res.T - want_T).max(1)[~close]
+    n_par = np.array([len(c["params"]) for c in cases])
+    assert np.array_equal(np.asarray(res.n_params), n_par)
+    for p, c in enumerate(cases):
+        if n_par[p]:
+            assert np.allclose(np.array(res.instantiated_params[p]), np.array(c["params"]), atol=1e-9, rtol=0)
+    gx = np.array([min(c["gx"]) if isinstance(c["gx"], list) else c["gx"] for c in cases], dtype=float)
+    fin = np.isfinite(gx)
+    assert np.allclose(np.asarray(res.gx)[fin], gx[fin], atol=1e-6, rtol=0)
 
 
 def test_c3_solutions_equal_the_reference(ctx):

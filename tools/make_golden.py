@@ -6,7 +6,7 @@ modules) on BASELINE.json's configurations.  The Klampt-side queries underneath 
 the reference's.  Needs /root/reference, so it runs in the build container only; the fixtures it writes
 are committed and are what the tests on the GPU box compare against.
 
-    python tools/make_golden.py [--only c1,c2,c3,c4,classes,oracle]
+    python tools/make_golden.py [--only c1,c2,c3,c4,c5,classes,oracle]
 """
 import argparse
 import json
@@ -131,6 +131,31 @@ def gen_c4():
                            "x0": x, "minvalue_probes": probes, "trace": trace, "params": _f(out[3])})
 
 
+def gen_c5():
+    """64 of the 65,536 C5 problems through the reference's own optimizeCollFree (gopt:1039-1081 -> sip.py:795-1241),
+    default settings (max_iters 50).  Per problem: final pose, outer iterations, status, f, g, instantiated parameters;
+    the full pose trace for the first 8."""
+    from semiinfiniteoptimization_b200 import workloads as W
+    mod, cube, scene, con = scenes.c5_scene('reference')
+    sip = sys.modules[mod.__name__.rsplit('.', 1)[0] + '.sip']
+    allposes = W.c5_poses(65536, seed=3)
+    cases = []
+    for k, idx in enumerate(scenes.c5_sample_indices(64)):
+        T = allposes[idx]
+        out = _quiet(mod.optimizeCollFree, cube, scene, T, settings=sip.SemiInfiniteOptimizationSettings(), verbose=0)
+        # the same run once more through optimizeSemiInfinite itself, for the fields the front-end drops (status, f, g)
+        res = _quiet(sip.optimizeSemiInfinite, mod.ObjectPoseObjective(T), [con], T, settings=sip.SemiInfiniteOptimizationSettings(), verbose=0)
+        assert len(res.trace) == len(out[1]) and np.array_equal(np.array(res.x[1]), np.array(out[0][1]))
+        rec = {"index": idx, "Tinit": _f(T), "T": _f(out[0]), "iterations": len(out[1]) - 1, "num_iterations": int(res.num_iterations), "status": res.status,
+               "fx": float(res.fx), "gx": _f(res.gx), "fx0": float(res.fx0), "gx0": _f(res.gx0), "params": _f(out[3])}
+        if k < 8:
+            rec["trace"] = _f(out[1])
+        cases.append(rec)
+    write("c5_pose.json", {"config": "C5: cube SDF@0.05 vs synthetic 262,144-point scene (seed 2), problems %s of the 65,536 (poses seed 3), "
+                                     "optimizeCollFree defaults (max_iters 50)" % (scenes.c5_sample_indices(64)[:3] + ["..."],),
+                           "cases": cases})
+
+
 def gen_classes():
     """Single calls of the reference's constraint classes: value / minvalue / df_dx (gopt:394-420, 457-484)."""
     out = {}
@@ -189,7 +214,7 @@ def gen_oracle():
     write("oracle_kat.json", out)
 
 
-GENERATORS = {"c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "classes": gen_classes, "oracle": gen_oracle}
+GENERATORS = {"c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "c5": gen_c5, "classes": gen_classes, "oracle": gen_oracle}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
