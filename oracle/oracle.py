@@ -68,6 +68,14 @@ def lib(prefer_native=False):
     L.orc_fk.argtypes = [P, P, I64, P]
     L.orc_chain_rows.argtypes = [P, _c.c_int32, P, P, P, I64, _c.c_int, P, P]
     L.orc_min_distance_f32.argtypes = [P, P, I64, P, I64, P, P]
+    L.orc_tree_build.argtypes = [P, I64]
+    L.orc_tree_build.restype = P
+    L.orc_tree_free.argtypes = [P]
+    L.orc_tree_free.restype = None
+    L.orc_grid_lipschitz.argtypes = [P]
+    L.orc_grid_lipschitz.restype = _c.c_double
+    L.orc_min_distance_pruned.argtypes = [P, _c.c_double, P, P, P, I64, _c.c_int, P, P, P]
+    L.orc_min_distance_pruned.restype = None
     if not prefer_native:
         _lib = L
     return L
@@ -248,6 +256,48 @@ def min_distance_f32(grid, cloud, T, L=None):
     s = grid.struct()
     L.orc_min_distance_f32(_c.byref(s), cloud.ctypes.data, len(cloud), T.ctypes.data, B, dmin.ctypes.data, arg.ctypes.data)
     return dmin, arg
+
+
+class CloudTree:
+    """k-d leaves of 128 points with bounding spheres: the hierarchy of the pruned CPU arm (orc_min_distance_pruned)."""
+
+    def __init__(self, cloud, L=None):
+        self.L = L or lib()
+        self.cloud = np.ascontiguousarray(cloud, dtype=np.float32).reshape(-1, 3)
+        self.h = self.L.orc_tree_build(self.cloud.ctypes.data, len(self.cloud))
+        if not self.h:
+            raise MemoryError("orc_tree_build failed")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.orc_tree_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def grid_lipschitz(grid, L=None):
+    s = grid.struct()
+    return float((L or lib()).orc_grid_lipschitz(_c.byref(s)))
+
+
+def min_distance_pruned(grid, tree, T, bound=None, use_bound=False, lip=None, L=None):
+    """The hierarchy-pruned CPU arm ("pruning on"): same (dmin, argmin) as min_distance, plus the point queries spent per
+    transform.  use_bound=True lets the caller's bound prune too (Klampt's upperBound): dmin is then exact only below it."""
+    L = L or tree.L
+    T = _f64(T).reshape(-1, 12)
+    B = len(T)
+    dmin = np.empty(B)
+    arg = np.empty(B, dtype=np.int64)
+    ev = np.empty(B, dtype=np.int64)
+    bnd = None if bound is None else _f64(np.broadcast_to(bound, (B,)))
+    s = grid.struct()
+    if lip is None:
+        lip = grid_lipschitz(grid, L)
+    L.orc_min_distance_pruned(_c.byref(s), float(lip), tree.h, T.ctypes.data, None if bnd is None else bnd.ctypes.data, B,
+                              int(bool(use_bound)), dmin.ctypes.data, arg.ctypes.data, ev.ctypes.data)
+    return dmin, arg, ev
 
 
 # ---------------------------------------------------------------------------------------------

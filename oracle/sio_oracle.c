@@ -449,3 +449,185 @@ void orc_min_distance_f32(const orc_grid* g, const float* cloud, int64_t N, cons
         argmin[b] = bi;
     }
 }
+
+/* ---- hierarchy-pruned cloud-vs-grid minimum: the CPU arm with "pruning on" ---------------------------------------
+ * Klampt's distance_ext does not test every point: it descends a bounding hierarchy of the cloud and discards
+ * branches whose lower bound cannot beat the best distance found so far (or the caller's upperBound).  This is the
+ * host restatement of that idea at the granularity the device uses (leaves of 128 points, SIO_PRUNE), written
+ * independently of the product: a k-d ordering of the cloud into leaves, one bounding sphere (a cloud point + radius)
+ * per leaf, a Lipschitz constant L of the trilinear field taken from the grid's own samples, and per transform a
+ * BEST-FIRST visit of the leaves by lower bound d(rep) - L r, stopping at the first leaf whose bound exceeds
+ * min(best so far, upperBound).  Results equal orc_min_distance's (same float64 query; lowest index on exact ties).
+ * Used by tests (equality with the brute-force sweep) and by bench.py's pruned cpu_baseline leg. */
+typedef struct {
+    int64_t n, nleaf;
+    int32_t* order;        /* [n]  leaf-ordered position -> caller index */
+    float* pts;            /* [n*3] points in leaf order */
+    double* rep;           /* [nleaf*4] representative point (a cloud point) + radius */
+} orc_cloud_tree;
+
+#define ORC_LEAF 128
+
+static void kd_select(int32_t* idx, int64_t lo, int64_t hi, int64_t k, const float* xyz, int ax) {
+    /* quickselect: after the call idx[lo..k) <= idx[k] <= idx(k..hi) along axis ax (ties by index) */
+    while (hi - lo > 1) {
+        int64_t mid = lo + (hi - lo) / 2;
+        int32_t pv = idx[mid];
+        float pvv = xyz[3 * (int64_t)pv + ax];
+        int32_t t = idx[mid]; idx[mid] = idx[hi - 1]; idx[hi - 1] = t;
+        int64_t s = lo;
+        for (int64_t i = lo; i < hi - 1; ++i) {
+            float v = xyz[3 * (int64_t)idx[i] + ax];
+            if (v < pvv || (v == pvv && idx[i] < pv)) { t = idx[i]; idx[i] = idx[s]; idx[s] = t; ++s; }
+        }
+        t = idx[s]; idx[s] = idx[hi - 1]; idx[hi - 1] = t;
+        if (s == k) return;
+        if (k < s) hi = s; else lo = s + 1;
+    }
+}
+
+static void kd_build(int32_t* idx, int64_t lo, int64_t hi, const float* xyz) {
+    if (hi - lo <= ORC_LEAF) return;
+    float bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = lo; i < hi; ++i)
+        for (int a = 0; a < 3; ++a) {
+            float v = xyz[3 * (int64_t)idx[i] + a];
+            if (v < bl[a]) bl[a] = v;
+            if (v > bh[a]) bh[a] = v;
+        }
+    int ax = 0;
+    for (int a = 1; a < 3; ++a) if (bh[a] - bl[a] > bh[ax] - bl[ax]) ax = a;
+    int64_t half = ((hi - lo) / 2 + ORC_LEAF - 1) / ORC_LEAF * ORC_LEAF;      /* left side in whole leaves */
+    if (half >= hi - lo) half = hi - lo - 1;
+    kd_select(idx, lo, hi, lo + half, xyz, ax);
+    kd_build(idx, lo, lo + half, xyz);
+    kd_build(idx, lo + half, hi, xyz);
+}
+
+orc_cloud_tree* orc_tree_build(const float* cloud, int64_t n) {
+    orc_cloud_tree* t = (orc_cloud_tree*)calloc(1, sizeof(orc_cloud_tree));
+    if (!t) return NULL;
+    t->n = n;
+    t->nleaf = (n + ORC_LEAF - 1) / ORC_LEAF;
+    t->order = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    t->pts = (float*)malloc(sizeof(float) * 3 * (size_t)(n > 0 ? n : 1));
+    t->rep = (double*)malloc(sizeof(double) * 4 * (size_t)(t->nleaf > 0 ? t->nleaf : 1));
+    for (int64_t i = 0; i < n; ++i) t->order[i] = (int32_t)i;
+    kd_build(t->order, 0, n, cloud);
+    for (int64_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) t->pts[3 * i + a] = cloud[3 * (int64_t)t->order[i] + a];
+    for (int64_t s = 0; s < t->nleaf; ++s) {
+        const int64_t a0 = s * ORC_LEAF, a1 = (a0 + ORC_LEAF < n) ? a0 + ORC_LEAF : n;
+        double c[3] = {0, 0, 0};
+        for (int64_t i = a0; i < a1; ++i) for (int a = 0; a < 3; ++a) c[a] += t->pts[3 * i + a];
+        for (int a = 0; a < 3; ++a) c[a] /= (double)(a1 - a0);
+        int64_t best = a0;
+        double bd = INFINITY;
+        for (int64_t i = a0; i < a1; ++i) {
+            double d2 = 0;
+            for (int a = 0; a < 3; ++a) { double e = t->pts[3 * i + a] - c[a]; d2 += e * e; }
+            if (d2 < bd) { bd = d2; best = i; }
+        }
+        double r2 = 0;
+        for (int64_t i = a0; i < a1; ++i) {
+            double d2 = 0;
+            for (int a = 0; a < 3; ++a) { double e = (double)t->pts[3 * i + a] - (double)t->pts[3 * best + a]; d2 += e * e; }
+            if (d2 > r2) r2 = d2;
+        }
+        for (int a = 0; a < 3; ++a) t->rep[4 * s + a] = t->pts[3 * best + a];
+        t->rep[4 * s + 3] = sqrt(r2) * (1.0 + 1e-12);
+    }
+    return t;
+}
+
+void orc_tree_free(orc_cloud_tree* t) {
+    if (!t) return;
+    free(t->order); free(t->pts); free(t->rep); free(t);
+}
+
+/* Lipschitz constant of the trilinear interpolant w.r.t. the grid-local position: inside a cell |dv/dx| <= the largest
+ * |difference| over its four x-edges / hx (likewise y, z); the maximum over cells of the norm of that vector. */
+double orc_grid_lipschitz(const orc_grid* g) {
+    const int nx = g->nx, ny = g->ny, nz = g->nz;
+    const double h[3] = {(g->bmax[0] - g->bmin[0]) / nx, (g->bmax[1] - g->bmin[1]) / ny, (g->bmax[2] - g->bmin[2]) / nz};
+    const size_t sy = (size_t)nz, sx = (size_t)ny * nz;
+    double lip = 0.0;
+#pragma omp parallel for reduction(max : lip) schedule(static)
+    for (int i = 0; i < nx; ++i)
+        for (int j = 0; j < ny; ++j)
+            for (int k = 0; k < nz; ++k) {
+                const int i1 = i + 1 < nx ? i + 1 : i, j1 = j + 1 < ny ? j + 1 : j, k1 = k + 1 < nz ? k + 1 : k;
+                double e[3] = {0, 0, 0};
+                const int I[2] = {i, i1}, J[2] = {j, j1}, K[2] = {k, k1};
+                for (int b = 0; b < 2; ++b)
+                    for (int c = 0; c < 2; ++c) {
+                        double dx = fabs((double)g->v[I[1] * sx + J[b] * sy + K[c]] - (double)g->v[I[0] * sx + J[b] * sy + K[c]]);
+                        double dy = fabs((double)g->v[I[b] * sx + J[1] * sy + K[c]] - (double)g->v[I[b] * sx + J[0] * sy + K[c]]);
+                        double dz = fabs((double)g->v[I[b] * sx + J[c] * sy + K[1]] - (double)g->v[I[b] * sx + J[c] * sy + K[0]]);
+                        if (dx > e[0]) e[0] = dx;
+                        if (dy > e[1]) e[1] = dy;
+                        if (dz > e[2]) e[2] = dz;
+                    }
+                double n2 = 0;
+                for (int a = 0; a < 3; ++a) { e[a] /= h[a]; n2 += e[a] * e[a]; }
+                double l = sqrt(n2);
+                if (l > lip) lip = l;
+            }
+    return lip * (1.0 + 1e-9);
+}
+
+typedef struct { double lb; int64_t leaf; } orc_heap_item;
+static int heap_cmp(const void* a, const void* b) {
+    const orc_heap_item* x = (const orc_heap_item*)a; const orc_heap_item* y = (const orc_heap_item*)b;
+    return (x->lb > y->lb) - (x->lb < y->lb);
+}
+
+/* dmin / argmin as orc_min_distance (caller indices, lowest index on exact ties, argmin = -1 when a finite bound is
+ * not beaten).  `lip` from orc_grid_lipschitz of the same grid.  evaluated[b] (optional) = point queries spent.
+ * use_bound != 0: the caller's upperBound prunes as well (what Klampt does with settings.upperBound): dmin[b] is then
+ * exact only when it is below the bound -- all that PenetrationDepthGeometry.distance reads (gopt:128-130). */
+void orc_min_distance_pruned(const orc_grid* g, double lip, const orc_cloud_tree* t, const double* T, const double* bound,
+                             int64_t B, int use_bound, double* dmin, int64_t* argmin, int64_t* evaluated) {
+#pragma omp parallel
+    {
+        orc_heap_item* items = (orc_heap_item*)malloc(sizeof(orc_heap_item) * (size_t)(t->nleaf > 0 ? t->nleaf : 1));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t b = 0; b < B; ++b) {
+            const double* Tb = T + 12 * b;
+            int64_t spent = 0;
+            double best = INFINITY;
+            int64_t bi = -1;
+            for (int64_t s = 0; s < t->nleaf; ++s) {
+                double p[3];
+                xf_apply(Tb, t->rep[4 * s], t->rep[4 * s + 1], t->rep[4 * s + 2], p);
+                double d = query_local(g, p, NULL);
+                /* +1 where the sphere can leave the bbox: the overshoot distance added outside is 1-Lipschitz */
+                double L = lip;
+                for (int a = 0; a < 3; ++a)
+                    if (p[a] - t->rep[4 * s + 3] < g->bmin[a] || p[a] + t->rep[4 * s + 3] > g->bmax[a]) { L = lip + 1.0; break; }
+                items[s].lb = d - L * t->rep[4 * s + 3];
+                items[s].leaf = s;
+            }
+            spent += t->nleaf;
+            qsort(items, (size_t)t->nleaf, sizeof(orc_heap_item), heap_cmp);
+            const double ub = (use_bound && bound && bound[b] < INFINITY) ? bound[b] : INFINITY;     /* Klampt's upperBound */
+            for (int64_t k = 0; k < t->nleaf; ++k) {
+                const double thr = best < ub ? best : ub;
+                if (items[k].lb > thr) break;                /* no later leaf can hold a point at or below thr */
+                const int64_t s = items[k].leaf, a0 = s * ORC_LEAF, a1 = (a0 + ORC_LEAF < t->n) ? a0 + ORC_LEAF : t->n;
+                for (int64_t i = a0; i < a1; ++i) {
+                    double p[3];
+                    xf_apply(Tb, (double)t->pts[3 * i], (double)t->pts[3 * i + 1], (double)t->pts[3 * i + 2], p);
+                    double d = query_local(g, p, NULL);
+                    const int64_t ci = t->order[i];
+                    if (d < best || (d == best && ci < bi)) { best = d; bi = ci; }
+                }
+                spent += a1 - a0;
+            }
+            dmin[b] = best;
+            argmin[b] = (bound && !(best < bound[b])) ? -1 : bi;
+            if (evaluated) evaluated[b] = spent;
+        }
+        free(items);
+    }
+}

@@ -84,3 +84,76 @@ def c5_poses(n, seed=3):
 def c5_cube():
     """The moving body of C5: cube.off (unit cube), converted to an SDF at gridres 0.05 by the caller."""
     return fixture_geometry("cube")
+
+
+# ---- single-problem configurations (C1, C3, C4) for bench.py's latency legs ------------------------------------------
+# `family` is a module with the reference's class names (this package's geometryopt) or the CPU restatement's
+# (`names` maps the roles); the builders only assemble inputs, they do not import either.
+DEVICE_NAMES = dict(PDG='PenetrationDepthGeometry', Obj='ObjectCollisionConstraint', Kin='RobotKinematicsCache',
+                    Link='RobotLinkCollisionConstraint', TC='RobotTrajectoryCache', Traj='RobotTrajectoryCollisionConstraint')
+CHAIR_IN_PATH = (-0.68, -0.38, 0.5)       # puts the chair across the initial TX90 path (the shipped placement never touches it)
+
+
+def c1_poses(n, seed=0):
+    """C1's headless poses: w ~ U(-0.3,0.3)^3, t in a box overlapping the chair."""
+    rng = np.random.default_rng(seed)
+    return [(so3.from_rotation_vector(rng.uniform(-0.3, 0.3, 3)),
+             [float(rng.uniform(0.4, 1.0)), float(rng.uniform(-0.3, 0.5)), float(rng.uniform(-0.3, 0.5))]) for _ in range(n)]
+
+
+def c1_scene(family, names=DEVICE_NAMES):
+    """cube SDF@0.05 (moving) vs m797 cloud@0.02 at (I,[1.2,0,0]) (geomopt.py:14-15, 43)."""
+    PDG = getattr(family, names['PDG'])
+    g1, g2 = PDG(fixture_geometry("cube"), 0.05, 0.02), PDG(fixture_geometry("m797"), 0.05, 0.02)
+    g2.setTransform((so3.identity(), [1.2, 0, 0]))
+    return g1, g2, getattr(family, names['Obj'])(g1, g2)
+
+
+def c3_scene(family, names=DEVICE_NAMES):
+    """tx90_geom_test3.xml, declared synthetic link boxes, tree = m1062 x2 rotated; gridres = pcres = 0.02."""
+    from ._host.robot import WorldModel
+    w = WorldModel()
+    w.readFile("tx90_geom_test3.xml")
+    robot, tree = w.robot(0), w.rigidObject(0)
+    cache = getattr(family, names['Kin'])(robot, 0.02, 0.02)
+    env = getattr(family, names['PDG'])(tree.geometry(), 0.02, 0.02)
+    cons = [getattr(family, names['Link'])(robot.link(i), env, cache) for i in range(robot.numLinks())
+            if not robot.link(i).geometry().empty()]
+    return robot, cons
+
+
+def c3_configs(robot, n, seed=3):
+    rng = np.random.default_rng(seed)
+    qmin, qmax = robot.getJointLimits()
+    return [[float(lo + rng.uniform(0.2, 0.8) * (hi - lo)) for lo, hi in zip(qmin, qmax)] for _ in range(n)]
+
+
+def c4_scene(family, names=DEVICE_NAMES, chair_pos=CHAIR_IN_PATH):
+    """tx90_geom_test2.xml, robottrajopt_initial.path remeshed x6 -> 67 milestones (65 free, x in R^455), chair cloud
+    only (gridres=None), link grids/clouds at 0.02 (robottrajopt.py:13-17, 70-71, 101-131)."""
+    import json
+    import os
+    from ._host.robot import WorldModel
+    from ._host.trajectory import RobotTrajectory
+    here = os.path.dirname(os.path.abspath(__file__))
+    p0 = json.load(open(os.path.join(here, "data", "paths.json")))["resources/robottrajopt_initial.path"]
+    w = WorldModel()
+    w.readFile("tx90_geom_test2.xml")
+    robot, chair = w.robot(0), w.rigidObject(0)
+    if chair_pos is not None:
+        chair.setTransform(chair.getTransform()[0], list(chair_pos))
+    traj = RobotTrajectory(robot, p0["times"], p0["milestones"])
+    times = []
+    for i in range(len(traj.times) - 1):
+        for k in range(6):
+            times.append(traj.times[i] + k / 6.0 * (traj.times[i + 1] - traj.times[i]))
+    times.append(traj.times[-1])
+    traj = traj.remesh(times)[0]
+    kin = getattr(family, names['Kin'])(robot, 0.02, 0.02)
+    tc = getattr(family, names['TC'])(kin, 10 * 6 + 6 - 1)
+    env = getattr(family, names['PDG'])(chair.geometry(), None, 0.02)
+    con = getattr(family, names['Traj'])([env], tc)
+    tc.qstart, tc.qend = traj.milestones[0][:], traj.milestones[-1][:]
+    tc.tstart, tc.tend = traj.times[0], traj.times[-1]
+    x = [float(v) for q in traj.milestones[1:-1] for v in q]
+    return robot, tc, con, traj, x

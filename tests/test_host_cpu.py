@@ -151,6 +151,38 @@ def test_oracle_under_set_and_its_fingerprints(O):
     assert n2 == n and len(b2) == 5
 
 
+@pytest.mark.parametrize("scene", ["cube_chair", "random_grid", "tiny"])
+def test_oracle_pruned_min_distance_equals_brute_force(O, scene):
+    """The hierarchy-pruned CPU arm (bench.py's "pruning on" baseline) returns what the brute-force sweep returns:
+    same minimum, same lowest index, same "[]" decisions -- with fewer point queries."""
+    rng = np.random.default_rng(5)
+    if scene == "cube_chair":
+        vg = util.fixture_geometry("cube").convert("VolumeGrid", 0.05).getVolumeGrid()
+        cloud = (util.fixture_geometry("m797").convert("PointCloud", 0.02).getPointCloud().points + [0.3, 0, 0]).astype(np.float32)
+        T = util.invert12(util.random_poses(4, 12, rot=0.5, trans=0.4, center=(0.2, 0.2, 0.2)))
+    elif scene == "random_grid":
+        vg = util.random_grid(3)
+        cloud = rng.uniform(-0.6, 1.6, (5000, 3)).astype(np.float32)
+        T = util.random_poses(6, 8, rot=0.5, trans=0.2)
+    else:
+        vg = util.sphere_grid()
+        cloud = np.repeat(rng.uniform(-1.5, 1.5, (37, 3)), 3, axis=0).astype(np.float32)      # duplicates: exact ties
+        T = util.random_poses(7, 5, rot=1.0, trans=0.5)
+    G = O.Grid(vg.values, vg.bmin, vg.bmax)
+    tree = O.CloudTree(cloud)
+    d0, a0 = O.min_distance(G, cloud, T)
+    d1, a1, ev = O.min_distance_pruned(G, tree, T)
+    assert np.array_equal(a0, a1) and np.array_equal(d0, d1)
+    if scene == "cube_chair":
+        assert ev.mean() < 0.5 * len(cloud)
+    bound = np.where(np.arange(len(T)) % 2 == 0, np.median(d0), np.inf)
+    d2, a2 = O.min_distance(G, cloud, T, bound=bound)
+    d3, a3, _ = O.min_distance_pruned(G, tree, T, bound=bound)
+    assert np.array_equal(a2, a3) and np.array_equal(d2, d3)
+    d4, a4, ev4 = O.min_distance_pruned(G, tree, T, bound=bound, use_bound=True)
+    assert np.array_equal(a2, a4) and np.array_equal(d2[a2 >= 0], d4[a2 >= 0]) and ev4.sum() <= ev.sum()
+
+
 def test_oracle_fk_and_chain_rows_vs_host_model(O):
     from semiinfiniteoptimization_b200._host.robot import load_arc_robot
     robot = load_arc_robot()
