@@ -66,6 +66,12 @@ class Trajectory:
         Trajectory.__init__(self, times, milestones)
         return self
 
+    def length(self, metric=None):
+        """Klampt's Trajectory.length (added for the reference's planopt.py, which the round-1 copy did not run)."""
+        if metric is None:
+            metric = lambda a, b: sum((x - y) ** 2 for x, y in zip(a, b)) ** 0.5
+        return sum(metric(a, b) for a, b in zip(self.milestones[:-1], self.milestones[1:]))
+
 
 class RobotTrajectory(Trajectory):
     def __init__(self, robot, times=None, milestones=None):
@@ -74,6 +80,9 @@ class RobotTrajectory(Trajectory):
 
     def interpolate(self, a, b, u, dt=None):
         return self.robot.interpolate(a, b, u)
+
+    def length(self, metric=None):
+        return Trajectory.length(self, metric or self.robot.distance)
 
     def _init_like(self, other, times, milestones):
         RobotTrajectory.__init__(self, other.robot, times, milestones)

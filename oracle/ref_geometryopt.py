@@ -256,6 +256,18 @@ class RefRobotTrajectoryCache:
         times = [self.tstart + float(i) / (M - 1) * (self.tend - self.tstart) for i in range(M)]
         return RobotTrajectory(self.robot, times, milestones)
 
+    def trajectoryToState(self, traj):
+        """gopt:343-356 (times is False here)."""
+        if self.qstart is not None:
+            assert list(traj.milestones[0]) == list(self.qstart), "Trajectory needs to match the start configuration"
+        if self.qend is not None:
+            assert list(traj.milestones[-1]) == list(self.qend), "Trajectory needs to match the end configuration"
+        sshift = 1 if self.qstart is not None else 0
+        eshift = 1 if self.qend is not None else 0
+        assert len(traj.milestones) == self.numPoints + sshift + eshift
+        assert traj.times[0] == self.tstart and traj.times[-1] == self.tend
+        return [v for q in traj.milestones[sshift:len(traj.milestones) - eshift] for v in q]
+
     def straightLineState(self):
         """gopt:357-366."""
         assert self.qstart is not None, "Need a start config for a straight line state"

@@ -131,6 +131,7 @@ def distance_ext(self, other, settings=None):
 
 
 Geometry3D = _hg.Geometry3D
+PLANNER_FACTORY = None          # callable(world, robot, target, **settings) -> object with planMore(n) / getPath()
 
 
 def install():
@@ -159,5 +160,19 @@ def install():
     ktraj.Trajectory, ktraj.RobotTrajectory = _ht.Trajectory, _ht.RobotTrajectory
     kmodel.trajectory = ktraj
     k.math, k.model = km, kmodel
+    # klampt.plan.robotplanning.planToConfig (planopt.py:2, 114): Klampt's planners are absent; the reference's
+    # planner / optimiser alternation is run with whatever stand-in the caller puts into PLANNER_FACTORY
+    kplan = types.ModuleType("klampt.plan")
+    kplan.__path__ = []
+    krp = types.ModuleType("klampt.plan.robotplanning")
+
+    def planToConfig(world, robot, target, **settings):
+        if PLANNER_FACTORY is None:
+            raise RuntimeError("klampt.plan.robotplanning is a stand-in: set oracle.refrun.klampt_shim.PLANNER_FACTORY")
+        return PLANNER_FACTORY(world, robot, target, **settings)
+    krp.planToConfig = planToConfig
+    kplan.robotplanning = krp
+    k.plan = kplan
+    sys.modules.update({"klampt.plan": kplan, "klampt.plan.robotplanning": krp})
     sys.modules.update({"klampt": k, "klampt.math": km, "klampt.math.vectorops": vectorops, "klampt.math.so3": so3,
                         "klampt.math.se3": se3, "klampt.model": kmodel, "klampt.model.trajectory": ktraj})

@@ -8,7 +8,7 @@ import types
 
 REFERENCE_ROOT = os.environ.get("SIO_REFERENCE_ROOT", "/root/reference")
 PKG = "semiinfinite_ref"
-MODULES = ["utils", "objective", "constraint", "sip", "geometryopt"]     # planopt needs Klampt's planners
+MODULES = ["utils", "objective", "constraint", "sip", "geometryopt", "planopt"]     # planopt: Klampt's planners are a stand-in hook (klampt_shim.PLANNER_FACTORY)
 
 
 def available():

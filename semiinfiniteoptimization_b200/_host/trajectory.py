@@ -58,6 +58,21 @@ class Trajectory:
         Trajectory.__init__(self, times, milestones)
         return self
 
+    # klampt.model.trajectory.Trajectory.load / save (robottrajopt.py:71, 396): the `.path` wire format
+    def load(self, fn):
+        from . import pathio
+        self.times, self.milestones = pathio.load_path(fn)
+
+    def save(self, fn, precise=False):
+        from . import pathio
+        pathio.save_path(fn, self.times, self.milestones, precise)
+
+    def length(self, metric=None):
+        """Sum of the distances between consecutive milestones (Klampt's Trajectory.length)."""
+        if metric is None:
+            metric = lambda a, b: sum((x - y) ** 2 for x, y in zip(a, b)) ** 0.5
+        return sum(metric(a, b) for a, b in zip(self.milestones[:-1], self.milestones[1:]))
+
 
 class RobotTrajectory(Trajectory):
     def __init__(self, robot, times=None, milestones=None):
@@ -67,25 +82,20 @@ class RobotTrajectory(Trajectory):
     def interpolate(self, a, b, u, dt=None):
         return self.robot.interpolate(a, b, u)
 
+    def length(self, metric=None):
+        return Trajectory.length(self, metric or self.robot.distance)
+
     def _init_like(self, other, times, milestones):
         RobotTrajectory.__init__(self, other.robot, times, milestones)
         return self
 
 
 def load_path(fn):
-    """Klampt linear path format: one `time<TAB>n q1 ... qn` line per milestone."""
-    times, ms = [], []
-    for line in open(fn).read().splitlines():
-        t = line.split()
-        if not t:
-            continue
-        n = int(t[1])
-        times.append(float(t[0]))
-        ms.append([float(v) for v in t[2:2 + n]])
-    return Trajectory(times, ms)
+    """Klampt linear path format: one `time<TAB>n q1 ... qn` line per milestone (see pathio.py)."""
+    from . import pathio
+    return Trajectory(*pathio.load_path(fn))
 
 
-def save_path(traj, fn):
-    with open(fn, "w") as f:
-        for t, m in zip(traj.times, traj.milestones):
-            f.write("%f\t%d %s\n" % (t, len(m), " ".join(repr(float(v)) for v in m)))
+def save_path(traj, fn, precise=False):
+    from . import pathio
+    pathio.save_path(fn, traj.times, traj.milestones, precise)

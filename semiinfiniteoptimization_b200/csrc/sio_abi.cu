@@ -320,7 +320,9 @@ int sio_grid_create(sio_ctx* c, const float* values, const int32_t dims[3], cons
         for (int bit = 1; bit < 8; bit <<= 1)
             for (int k = 0; k < 8; ++k)
                 if (k & bit) m[k] -= m[k ^ bit];
-        for (int k = 0; k < 8; ++k) q[k] = (float)m[k];
+        // stored as the register pairs of the packed Horner evaluation: [c6 c2 | c7 c3 | c4 c0 | c5 c1] (sio_kernels.cu)
+        static const int pos[8] = {5, 7, 1, 3, 4, 6, 0, 2};
+        for (int k = 0; k < 8; ++k) q[pos[k]] = (float)m[k];
     }
     GridH g;
     g.meta.lip = (float)(lip * (1.0 + 1e-6)) + 1e-6f;

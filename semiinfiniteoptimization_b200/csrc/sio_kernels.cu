@@ -50,13 +50,37 @@ __device__ __forceinline__ float warp_min_f32(float v) {
 // (f = offset from the cell's low corner in cell units), 32 bytes = one sector, fetched with ONE
 // 256-bit read-only load.  Horner evaluation is 7 FMAs (the corner form needs 7 FMAs + 7 subtractions)
 // and the analytic gradient reuses its partial sums.  Coefficients are formed in float64 on the host.
+// Storage order inside the 32 bytes: [c6 c2 | c7 c3 | c4 c0 | c5 c1] -- the four register PAIRS the packed Horner evaluation
+// (fma.rn.f32x2, SASS FFMA2) consumes directly: (a,c) = fz (c7,c3) + (c6,c2); (b,d) = fz (c5,c1) + (c4,c0);
+// (e,f) = fy (a,c) + (b,d); v = e fx + f.  kPos[m] = position of coefficient m.
 struct Cell { float c[8]; };
+__host__ __device__ constexpr int brick_pos(int m) { return m == 0 ? 5 : m == 1 ? 7 : m == 2 ? 1 : m == 3 ? 3 : m == 4 ? 4 : m == 5 ? 6 : m == 6 ? 0 : 2; }
 __device__ __forceinline__ Cell load_cell(const float* __restrict__ brick, uint32_t cell) {
     Cell q;
     const float* p = brick + (size_t)cell * 8;
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(q.c[0]), "=f"(q.c[1]), "=f"(q.c[2]), "=f"(q.c[3]), "=f"(q.c[4]), "=f"(q.c[5]), "=f"(q.c[6]), "=f"(q.c[7])
         : "l"(p));
+    return q;
+}
+
+// ---- packed float32 pairs (sm_100a: fma/add .f32x2 -> SASS FFMA2 / FADD2, one issue slot for two lanes of work) -------
+// A pair lives in a 64-bit register (two adjacent 32-bit registers).  Every operand of FFMA2 / FADD2 may also be a
+// single register broadcast to both halves (SASS `R.F32`), which ptxas selects when both halves of a packed operand
+// are the same register -- so a matrix entry, a fraction or a constant multiplies a pair without any duplication.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b) { f32x2 r; asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// one cell as four register pairs [c6 c2 | c7 c3 | c4 c0 | c5 c1], one 256-bit read-only load
+struct Cell2 { f32x2 p62, p73, p40, p51; };
+__device__ __forceinline__ Cell2 load_cell2(const float* __restrict__ brick, uint32_t cell) {
+    Cell2 q;
+    const float* p = brick + (size_t)cell * 8;
+    asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(q.p62), "=l"(q.p73), "=l"(q.p40), "=l"(q.p51) : "l"(p));
     return q;
 }
 
@@ -74,10 +98,10 @@ __device__ __forceinline__ float lattice_value(const GridK& g, float cx, float c
     uint32_t bx, by, bz; float fx, fy, fz;
     split_rz(cx, bx, fx); split_rz(cy, by, fy); split_rz(cz, bz, fz);
     Cell q = load_cell(g.brick, bx * g.cx + (by * g.cz + (bz + g.nbias)));
-    float a = fmaf(q.c[7], fz, q.c[6]);          // coefficient of fx fy
-    float b = fmaf(q.c[5], fz, q.c[4]);          // coefficient of fx
-    float c = fmaf(q.c[3], fz, q.c[2]);          // coefficient of fy
-    float d = fmaf(q.c[1], fz, q.c[0]);
+    float a = fmaf(q.c[2], fz, q.c[0]);          // coefficient of fx fy
+    float b = fmaf(q.c[6], fz, q.c[4]);          // coefficient of fx
+    float c = fmaf(q.c[3], fz, q.c[1]);          // coefficient of fy
+    float d = fmaf(q.c[7], fz, q.c[5]);
     return fmaf(fmaf(a, fy, b), fx, fmaf(c, fy, d));
 }
 
@@ -138,16 +162,16 @@ __device__ __forceinline__ float eval32_grad(const XfRec& r, float px, float py,
     split_rz(cx, bx_, fx); split_rz(cy, by_, fy); split_rz(cz, bz_, fz);
     const uint32_t sx = (uint32_t)r.sx, sy = (uint32_t)r.sy;
     Cell q = load_cell(r.v, bx_ * sx + (by_ * sy + (bz_ + (0u - kFloorBias * (sx + sy + 1u)))));
-    float a = fmaf(q.c[7], fz, q.c[6]);          // coefficient of fx fy
-    float b = fmaf(q.c[5], fz, q.c[4]);          // coefficient of fx
-    float c = fmaf(q.c[3], fz, q.c[2]);          // coefficient of fy
-    float d = fmaf(q.c[1], fz, q.c[0]);
+    float a = fmaf(q.c[2], fz, q.c[0]);          // coefficient of fx fy
+    float b = fmaf(q.c[6], fz, q.c[4]);          // coefficient of fx
+    float c = fmaf(q.c[3], fz, q.c[1]);          // coefficient of fy
+    float d = fmaf(q.c[7], fz, q.c[5]);
     float dx = fmaf(a, fy, b);                   // dv/dfx
     float val = fmaf(dx, fx, fmaf(c, fy, d));
     // derivative w.r.t. the cell coordinate, zero on clamped axes (Appendix A.2 step 3/5)
     float gfx = (ux > 0.0f && ux < r.hix) ? dx : 0.0f;
     float gfy = (uy > 0.0f && uy < r.hiy) ? fmaf(a, fx, c) : 0.0f;
-    float gfz = (uz > 0.0f && uz < r.hiz) ? fmaf(fmaf(q.c[7], fy, q.c[5]), fx, fmaf(q.c[3], fy, q.c[1])) : 0.0f;
+    float gfz = (uz > 0.0f && uz < r.hiz) ? fmaf(fmaf(q.c[2], fy, q.c[6]), fx, fmaf(q.c[3], fy, q.c[7])) : 0.0f;
     float dout = sqrtf(dout2);
     if (dout2 > 0.0f) {
         float inv = 1.0f / dout;
@@ -240,6 +264,57 @@ __device__ __forceinline__ float warp_subtile_min(const XfRec& r, const GridK& g
     return warp_min_f32(best);
 }
 
+// The same for a sub-tile known to lie inside the sample lattice, two points per instruction: the transform of a point
+// PAIR is 9 FFMA2 (matrix entries broadcast), floor / fraction 3 x (FADD2.RZ, FADD2, FADD2), and each point's Horner
+// evaluation 3 FFMA2 + 1 FFMA on the brick's register pairs -- 13 floating-point instructions per query instead of 25,
+// with bit-identical results (each half is the same IEEE fma / add as the scalar path).
+__device__ __forceinline__ float warp_subtile_min_packed(const XfRec& r, const GridK& g, const f32x2 (&PX)[kPtsPerThread / 2],
+                                                         const f32x2 (&PY)[kPtsPerThread / 2], const f32x2 (&PZ)[kPtsPerThread / 2],
+                                                         int32_t b, int32_t base, int lane, Cand* __restrict__ cand,
+                                                         unsigned long long* __restrict__ cand_count, uint32_t cand_cap) {
+    float d[kPtsPerThread];
+    const float big = 8388608.0f;
+    const f32x2 BIG = pk2(big, big);
+#pragma unroll
+    for (int h = 0; h < kPtsPerThread / 2; ++h) {
+        const f32x2 UX = fma2(pk2(r.m[0], r.m[0]), PX[h], fma2(pk2(r.m[1], r.m[1]), PY[h], fma2(pk2(r.m[2], r.m[2]), PZ[h], pk2(r.m[3], r.m[3]))));
+        const f32x2 UY = fma2(pk2(r.m[4], r.m[4]), PX[h], fma2(pk2(r.m[5], r.m[5]), PY[h], fma2(pk2(r.m[6], r.m[6]), PZ[h], pk2(r.m[7], r.m[7]))));
+        const f32x2 UZ = fma2(pk2(r.m[8], r.m[8]), PX[h], fma2(pk2(r.m[9], r.m[9]), PY[h], fma2(pk2(r.m[10], r.m[10]), PZ[h], pk2(r.m[11], r.m[11]))));
+        const f32x2 TX = add2_rz(UX, BIG), TY = add2_rz(UY, BIG), TZ = add2_rz(UZ, BIG);
+        const f32x2 FX = sub2(UX, sub2(TX, BIG)), FY = sub2(UY, sub2(TY, BIG)), FZ = sub2(UZ, sub2(TZ, BIG));
+        float tx[2], ty[2], tz[2], fx[2], fy[2], fz[2];
+        upk2(TX, tx[0], tx[1]); upk2(TY, ty[0], ty[1]); upk2(TZ, tz[0], tz[1]);
+        upk2(FX, fx[0], fx[1]); upk2(FY, fy[0], fy[1]); upk2(FZ, fz[0], fz[1]);
+        Cell2 q[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+            q[e] = load_cell2(g.brick, __float_as_uint(tx[e]) * g.cx + (__float_as_uint(ty[e]) * g.cz + (__float_as_uint(tz[e]) + g.nbias)));
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const f32x2 FZs = pk2(fz[e], fz[e]), FYs = pk2(fy[e], fy[e]);
+            const f32x2 AC = fma2(FZs, q[e].p73, q[e].p62);          // (a, c): coefficients of fx fy and of fy
+            const f32x2 BD = fma2(FZs, q[e].p51, q[e].p40);          // (b, d): coefficient of fx and the constant
+            float ee, ff;
+            upk2(fma2(FYs, AC, BD), ee, ff);                          // (a fy + b, c fy + d)
+            d[2 * h + e] = fmaf(ee, fx[e], ff);
+        }
+    }
+    float best = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
+    if (best < r.thr) {                                    // rare: candidates for the under-bound set
+#pragma unroll
+        for (int j = 0; j < kPtsPerThread; ++j) {
+            if (d[j] < r.thr) {
+                const unsigned long long slot = atomicAdd(cand_count, 1ull);
+                if (slot < (unsigned long long)cand_cap) {
+                    Cand c; c.b = b; c.idx = base + j * 32 + lane; c.d = (double)d[j];
+                    cand[slot] = c;
+                }
+            }
+        }
+    }
+    return warp_min_f32(best);
+}
+
 // ---- K2 bulk pass ---------------------------------------------------------------------------------
 // grid  = nchunks * ntiles CTAs (chunk-major: consecutive CTAs share the transform chunk); a chunk is
 //         `xfchunk` <= 32 transforms, chosen by the launcher so that the CTA count is many waves
@@ -281,6 +356,11 @@ k_min_f32(const float4* __restrict__ pts, const float4* __restrict__ rep, const 
         float4 p = __ldg(pts + base + j * 32 + lane);
         px[j] = p.x; py[j] = p.y; pz[j] = p.z;
     }
+    f32x2 PX[kPtsPerThread / 2], PY[kPtsPerThread / 2], PZ[kPtsPerThread / 2];
+#pragma unroll
+    for (int h = 0; h < kPtsPerThread / 2; ++h) {
+        PX[h] = pk2(px[2 * h], px[2 * h + 1]); PY[h] = pk2(py[2 * h], py[2 * h + 1]); PZ[h] = pk2(pz[2 * h], pz[2 * h + 1]);
+    }
     const float4 sphere = __ldg(rep + sub);
     __syncthreads();
     const uint32_t inmask = __ballot_sync(0xffffffffu, lane < nb && sphere_in_lattice(sxf[lane < nb ? lane : 0], sphere));
@@ -291,7 +371,7 @@ k_min_f32(const float4* __restrict__ pts, const float4* __restrict__ rep, const 
         const GridK g = kMulti ? grid_of(r) : gk;
         const int32_t b = (int32_t)(b_begin + b0 + bl);
         float m;
-        if ((inmask >> bl) & 1u) m = warp_subtile_min<true>(r, g, px, py, pz, b, (int32_t)base, lane, cand, cand_count, cand_cap);
+        if ((inmask >> bl) & 1u) m = warp_subtile_min_packed(r, g, PX, PY, PZ, b, (int32_t)base, lane, cand, cand_count, cand_cap);
         else m = warp_subtile_min<false>(r, g, px, py, pz, b, (int32_t)base, lane, cand, cand_count, cand_cap);
         mine = (lane == bl) ? m : mine;
     }
@@ -466,6 +546,7 @@ k_min_items(const float4* __restrict__ pts, const float4* __restrict__ rep, cons
     const uint32_t nsub32 = (uint32_t)nsub;
     constexpr int kRecParts = (int)(sizeof(XfRec) / 16);
     float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
+    f32x2 PX[kPtsPerThread / 2], PY[kPtsPerThread / 2], PZ[kPtsPerThread / 2];      // the same points as register pairs
     float4 sphere = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t have = 0xffffffffu;                           // sub-tile whose points sit in registers
     for (uint32_t it0 = (blockIdx.x * (kThreads / 32) + warp) * kItemRun; it0 < n; it0 += nwarps * kItemRun) {
@@ -494,12 +575,16 @@ k_min_items(const float4* __restrict__ pts, const float4* __restrict__ rep, cons
                     float4 p = __ldg(pts + base + j * 32 + lane);
                     px[j] = p.x; py[j] = p.y; pz[j] = p.z;
                 }
+#pragma unroll
+                for (int h = 0; h < kPtsPerThread / 2; ++h) {
+                    PX[h] = pk2(px[2 * h], px[2 * h + 1]); PY[h] = pk2(py[2 * h], py[2 * h + 1]); PZ[h] = pk2(pz[2 * h], pz[2 * h + 1]);
+                }
                 sphere = __ldg(rep + s);
                 have = s;
             }
             float m;
             if (sphere_in_lattice(r, sphere))      // warp-uniform: every lane tests the same sphere and record
-                m = warp_subtile_min<true>(r, grid_of(r), px, py, pz, (int32_t)(b_begin + bl), (int32_t)base, lane, cand, cand_count, cand_cap);
+                m = warp_subtile_min_packed(r, grid_of(r), PX, PY, PZ, (int32_t)(b_begin + bl), (int32_t)base, lane, cand, cand_count, cand_cap);
             else
                 m = warp_subtile_min<false>(r, grid_of(r), px, py, pz, (int32_t)(b_begin + bl), (int32_t)base, lane, cand, cand_count, cand_cap);
             if (lane == 0) subkeys[e] = __float_as_uint(m);
@@ -531,14 +616,14 @@ __device__ __forceinline__ float lattice_value_grad(const XfRec& r, const GridK&
     uint32_t bx, by, bz; float fx, fy, fz;
     split_rz(ux, bx, fx); split_rz(uy, by, fy); split_rz(uz, bz, fz);
     Cell q = load_cell(g.brick, bx * g.cx + (by * g.cz + (bz + g.nbias)));
-    float a = fmaf(q.c[7], fz, q.c[6]);
-    float b = fmaf(q.c[5], fz, q.c[4]);
-    float c = fmaf(q.c[3], fz, q.c[2]);
-    float d = fmaf(q.c[1], fz, q.c[0]);
+    float a = fmaf(q.c[2], fz, q.c[0]);
+    float b = fmaf(q.c[6], fz, q.c[4]);
+    float c = fmaf(q.c[3], fz, q.c[1]);
+    float d = fmaf(q.c[7], fz, q.c[5]);
     float gfx = fmaf(a, fy, b);                                               // dv/dfx
     float val = fmaf(gfx, fx, fmaf(c, fy, d));
     float gfy = fmaf(a, fx, c);
-    float gfz = fmaf(fmaf(q.c[7], fy, q.c[5]), fx, fmaf(q.c[3], fy, q.c[1]));
+    float gfz = fmaf(fmaf(q.c[2], fy, q.c[6]), fx, fmaf(q.c[3], fy, q.c[7]));
     // strictly inside the lattice: no clamped axis, no bbox term.  g_in = M' gf
     gx = fmaf(r.m[0], gfx, fmaf(r.m[4], gfy, r.m[8] * gfz));
     gy = fmaf(r.m[1], gfx, fmaf(r.m[5], gfy, r.m[9] * gfz));

@@ -156,6 +156,68 @@ def gen_c5():
                            "cases": cases})
 
 
+class ScriptedPlanner:
+    """Stand-in planner for the planopt golden: 'finds' a fixed path on its first slice (Klampt's planners are absent)."""
+
+    def __init__(self, path):
+        self._path, self._found = [list(q) for q in path], False
+
+    def planMore(self, n):
+        self._found = True
+
+    def getPath(self):
+        return self._path if self._found else None
+
+
+def planopt_inputs(WorldModel):
+    """tx90_geom_test2.xml as shipped (chair clear of the arm), start / goal / planner path from robottrajopt_initial.path."""
+    p0 = json.load(open(os.path.join(ROOT, "semiinfiniteoptimization_b200", "data", "paths.json")))["resources/robottrajopt_initial.path"]
+    w = WorldModel()
+    w.readFile("tx90_geom_test2.xml")
+    robot = w.robot(0)
+    robot.setConfig(p0["milestones"][0])
+    return w, robot, p0
+
+
+def gen_planopt():
+    """The reference's planopt.py (arc_length_refine 8-33, planOptimizedTrajectory 36-245) executed with a scripted
+    stand-in planner: refined trajectory, returned best path and the CSV log (time column dropped)."""
+    import io
+    from oracle.refrun import klampt_shim, load
+    mods = load.load()
+    planopt = mods["planopt"]
+    from oracle.frozen.robot import WorldModel
+    from oracle.frozen.trajectory import RobotTrajectory, Trajectory
+    w, robot, p0 = planopt_inputs(WorldModel)
+    out = {}
+    rt = RobotTrajectory(robot, list(range(len(p0["milestones"]))), p0["milestones"])
+    refined = planopt.arc_length_refine(rt, 12)
+    plain = planopt.arc_length_refine(Trajectory(p0["times"], p0["milestones"]), 5)
+    out["arc_length_refine"] = {"robot_12": {"times": _f(refined.times), "milestones": _f(refined.milestones)},
+                                "plain_5": {"times": _f(plain.times), "milestones": _f(plain.milestones)}}
+    klampt_shim.PLANNER_FACTORY = lambda world, rob, target, **kw: ScriptedPlanner(p0["milestones"])
+    log = io.StringIO()
+    robot.setConfig(p0["milestones"][0])
+    best = _quiet(planopt.planOptimizedTrajectory, w, robot, p0["milestones"][-1], numRestarts=2, optimizationMaxIters=8, logFile=log)
+    rows = [l.split(",") for l in log.getvalue().splitlines()]
+    out["plan_optimize"] = {"args": {"numRestarts": 2, "optimizationMaxIters": 8}, "times": _f(best.times), "milestones": _f(best.milestones),
+                            "length": float(best.length()),
+                            "log_header": [",".join(r) for r in rows[:3]],
+                            "log_rows": [[int(r[0]), int(r[1]), r[3], float(r[4])] for r in rows[3:]]}
+    write("planopt.json", out)
+
+
+def gen_paths():
+    """The shipped `.path` / `.configs` files verbatim (data, not source) for the byte-exact round-trip test."""
+    ref = os.environ.get("SIO_REFERENCE_ROOT", "/root/reference")
+    files = {}
+    for sub in ("resources", "output"):
+        for fn in sorted(os.listdir(os.path.join(ref, sub))):
+            if fn.endswith((".path", ".configs")):
+                files[sub + "/" + fn] = open(os.path.join(ref, sub, fn)).read()
+    write("path_files.json", {"files": files})
+
+
 def gen_classes():
     """Single calls of the reference's constraint classes: value / minvalue / df_dx (gopt:394-420, 457-484)."""
     out = {}
@@ -214,7 +276,8 @@ def gen_oracle():
     write("oracle_kat.json", out)
 
 
-GENERATORS = {"c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "c5": gen_c5, "classes": gen_classes, "oracle": gen_oracle}
+GENERATORS = {"c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "c5": gen_c5, "classes": gen_classes, "oracle": gen_oracle,
+              "planopt": gen_planopt, "paths": gen_paths}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
