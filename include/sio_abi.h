@@ -48,6 +48,8 @@ extern "C" {
 #define SIO_NO_NORMALIZE    0x2   /* return the raw analytic gradient instead of the unit one */
 #define SIO_WANT_GRAD       0x4
 #define SIO_PRUNE           0x8   /* K2: skip 128-point sub-tiles whose Lipschitz lower bound rules them out (results identical) */
+#define SIO_SMEM_GRID       0x10  /* K2, one grid of <= 200 KB of samples: bulk pass from a TMA-staged shared-memory copy of the grid
+                                     (a measured alternative, slower than the default brick kernel; minimum / arg-minimum only) */
 
 typedef struct sio_ctx sio_ctx;
 typedef int32_t sio_handle;

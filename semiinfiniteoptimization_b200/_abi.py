@@ -18,6 +18,7 @@ SIO_F32 = 0x0
 SIO_F64 = 0x1
 SIO_NO_NORMALIZE = 0x2
 SIO_PRUNE = 0x8
+SIO_SMEM_GRID = 0x10
 
 # every symbol include/sio_abi.h declares (tests check the built library exports each of them)
 ABI_SYMBOLS = (

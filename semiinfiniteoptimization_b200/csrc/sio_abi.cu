@@ -631,6 +631,14 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
         c->launches += 1;
         c->prune_total = B * nsub;
     }
+    const bool smem_variant = !f64 && !prune && (flags & SIO_SMEM_GRID) != 0;
+    if (smem_variant) {
+        if (want_under) return fail(SIO_ERR_INVALID, "SIO_SMEM_GRID computes minima only: pass n_under = NULL");
+        CU(c->s_xf.ensure((size_t)B * sizeof(XfRec)));
+        a.xf = c->s_xf.as<XfRec>();
+        launch_prep_xf(a, st);
+        c->launches += 1;
+    }
     c->bulk_timed = false;
     // the bulk launch is bracketed by timing events unless the caller is capturing the call into a CUDA graph
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -645,6 +653,11 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
             if (one_batch) { cudaEventRecord(c->ev_bulk1, st); c->bulk_timed = true; }
             c->n_icnt += 1;
             c->launches += 3;
+        } else if (!f64 && smem_variant) {
+            if (one_batch) cudaEventRecord(c->ev_bulk0, st);
+            if (!launch_min_smem(a, st)) return fail(SIO_ERR_INVALID, "SIO_SMEM_GRID: needs one grid whose padded samples fit 200 KB");
+            if (one_batch) { cudaEventRecord(c->ev_bulk1, st); c->bulk_timed = true; }
+            c->launches += 1;
         } else if (!f64) {
             if (one_batch) cudaEventRecord(c->ev_bulk0, st);
             launch_min_f32(a, st);

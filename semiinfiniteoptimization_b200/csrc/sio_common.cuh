@@ -94,6 +94,7 @@ struct MinArgs {
 void launch_prep_xf(const MinArgs& a, cudaStream_t st);
 void launch_min_f32(const MinArgs& a, cudaStream_t st);
 void launch_min_pruned(const MinArgs& a, cudaStream_t st);
+bool launch_min_smem(const MinArgs& a, cudaStream_t st);      // TMA-staged shared-memory variant (needs a.xf); false = not applicable
 void launch_finalize(const MinArgs& a, bool all_tiles, bool emit_under, int n_recheck, cudaStream_t st);
 
 void launch_cloud_query_f32(const float4* pts, const float4* rep, int64_t N, const XfRec* xf, int64_t B, int normalize,

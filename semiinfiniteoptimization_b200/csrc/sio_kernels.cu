@@ -413,6 +413,113 @@ void launch_min_f32(const MinArgs& a, cudaStream_t st) {
     }
 }
 
+// ---- K2 bulk pass, grid staged in shared memory by TMA (SIO_SMEM_GRID; measured alternative, not the default) --------------
+// BASELINE.json's north_star names "TMA or shared-memory staging of grid bricks".  The 32-byte bricks of even the small
+// grids (C1 / C5 cube at 0.05: 27,000 cells = 864 KB) do not fit a CTA's 227 KB, but the plain padded sample array does
+// (31^3 floats = 119 KB).  This variant therefore stages THAT array with one bulk asynchronous copy
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx: the TMA engine, SASS UBLKCP) per persistent CTA and
+// evaluates every query from its 8 corner samples with shared-memory loads.  Same decomposition and the same sub-tile
+// minima as k_min_f32 (the finalize pass is shared), general clamped path for every point.
+// Result (profiles/r02_smem_vs_brick.md): slower than the brick kernel -- a query costs 8 LDS (each at least one
+// data-stage wavefront, more under bank conflicts) against one 256-bit LDG, through the SAME L1 data pipe that binds.
+constexpr int kSmemThreads = 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kSmemThreads, 1)
+k_min_smem(const float4* __restrict__ pts, const XfRec* __restrict__ xf, int64_t b_begin, int64_t Bc, int64_t nsub, int32_t xfchunk,
+           uint32_t* __restrict__ subkeys, const float* __restrict__ gv, uint32_t n_floats, int32_t sx, int32_t sy) {
+    extern __shared__ __align__(128) float sv[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t bulk_bytes = (n_floats * 4u) & ~15u;            // bulk copies move multiples of 16 bytes
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bulk_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sv)), "l"(gv), "r"(bulk_bytes), "r"(smem_u32(&mbar)) : "memory");
+    }
+    for (uint32_t i = bulk_bytes / 4 + tid; i < n_floats; i += kSmemThreads) sv[i] = __ldg(gv + i);     // the < 16-byte tail
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+    }
+    __syncthreads();
+    const int64_t nchunks = (Bc + xfchunk - 1) / xfchunk;
+    const int64_t nitems = nchunks * nsub;                          // one item = (transform chunk, 128-point sub-tile), one warp
+    for (int64_t item = (int64_t)blockIdx.x * (kSmemThreads / 32) + warp; item < nitems; item += (int64_t)gridDim.x * (kSmemThreads / 32)) {
+        const int64_t chunk = item / nsub, sub = item - chunk * nsub;
+        const int64_t b0 = chunk * xfchunk;
+        const int nb = (int)min((int64_t)xfchunk, Bc - b0);
+        const int64_t base = sub * (32 * kPtsPerThread);
+        float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
+#pragma unroll
+        for (int j = 0; j < kPtsPerThread; ++j) {
+            float4 p = __ldg(pts + base + j * 32 + lane);
+            px[j] = p.x; py[j] = p.y; pz[j] = p.z;
+        }
+        float mine = INFINITY;
+        for (int bl = 0; bl < nb; ++bl) {
+            const XfRec* r = xf + b_begin + b0 + bl;                // warp-uniform address: one broadcast load per field
+            float m[12];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(r->m) + q);
+                m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
+            }
+            const float4 h4 = __ldg(reinterpret_cast<const float4*>(&r->hx));      // hx hy hz thr
+            const float4 d4 = __ldg(reinterpret_cast<const float4*>(&r->hix));     // hix hiy hiz (sx)
+            float best = INFINITY;
+#pragma unroll
+            for (int j = 0; j < kPtsPerThread; ++j) {
+                const float ux = fmaf(m[0], px[j], fmaf(m[1], py[j], fmaf(m[2], pz[j], m[3])));
+                const float uy = fmaf(m[4], px[j], fmaf(m[5], py[j], fmaf(m[6], pz[j], m[7])));
+                const float uz = fmaf(m[8], px[j], fmaf(m[9], py[j], fmaf(m[10], pz[j], m[11])));
+                const float bx = fminf(fmaxf(ux, -0.5f), d4.x + 0.5f), by = fminf(fmaxf(uy, -0.5f), d4.y + 0.5f), bz = fminf(fmaxf(uz, -0.5f), d4.z + 0.5f);
+                const float ox = (ux - bx) * h4.x, oy = (uy - by) * h4.y, oz = (uz - bz) * h4.z;
+                const float dout2 = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
+                const float cx = fminf(fmaxf(ux, 0.0f), d4.x), cy = fminf(fmaxf(uy, 0.0f), d4.y), cz = fminf(fmaxf(uz, 0.0f), d4.z);
+                uint32_t ix, iy, iz; float fx, fy, fz;
+                split_rz(cx, ix, fx); split_rz(cy, iy, fy); split_rz(cz, iz, fz);
+                const float* c = sv + ((ix - kFloorBias) * (uint32_t)sx + (iy - kFloorBias) * (uint32_t)sy + (iz - kFloorBias));
+                // the padded copy makes corner +1 addressable on every axis (its last layer repeats the one before)
+                const float v000 = c[0], v001 = c[1], v010 = c[sy], v011 = c[sy + 1];
+                const float v100 = c[sx], v101 = c[sx + 1], v110 = c[sx + sy], v111 = c[sx + sy + 1];
+                const float a00 = fmaf(fz, v001 - v000, v000), a01 = fmaf(fz, v011 - v010, v010);
+                const float a10 = fmaf(fz, v101 - v100, v100), a11 = fmaf(fz, v111 - v110, v110);
+                const float b0v = fmaf(fy, a01 - a00, a00), b1v = fmaf(fy, a11 - a10, a10);
+                float dout;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(dout) : "f"(dout2));
+                best = fminf(best, fmaf(fx, b1v - b0v, b0v) + dout);
+            }
+            const float mw = warp_min_f32(best);
+            mine = (lane == bl) ? mw : mine;
+        }
+        if (lane < nb) subkeys[(b0 + lane) * nsub + sub] = __float_as_uint(mine);
+    }
+}
+
+// returns false when the variant does not apply (more than one grid, or the padded sample array exceeds the shared memory)
+bool launch_min_smem(const MinArgs& a, cudaStream_t st) {
+    if (!a.single_grid || a.Bc <= 0 || a.N <= 0) return false;
+    const GridDev& g = *a.single_grid;
+    const size_t n_floats = (size_t)(g.nx + 1) * (g.ny + 1) * (g.nz + 1);
+    const size_t bytes = ((n_floats * 4 + 127) / 128) * 128;
+    if (bytes > 200 * 1024) return false;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_min_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    const int64_t nsub = (int64_t)a.ntiles * (kThreads / 32);
+    k_min_smem<<<a.num_sms > 0 ? a.num_sms : 148, kSmemThreads, bytes, st>>>(a.pts, a.xf, a.b_begin, a.Bc, nsub, kXfChunk, a.subkeys, g.v,
+                                                                             (uint32_t)n_floats, g.sx, g.sy);
+    return true;
+}
+
 // ---- K2 with sub-tile culling (SIO_PRUNE) -----------------------------------------------------------
 // The GPU counterpart of the bounding-hierarchy branch-and-bound inside Klampt's distance_ext: each
 // 128-point sub-tile has a representative cloud point and a bounding radius (built once with the

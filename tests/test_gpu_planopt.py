@@ -22,12 +22,12 @@ def test_plan_optimize_alternation_on_the_device_equals_the_reference(ctx):
 
 
 def test_rrt_stand_in_plans_through_the_oracle_and_the_optimiser_shortens_its_path(ctx):
-    """Chair across the arm's initial path: the straight segment is infeasible, the seeded RRT finds a way around it with
+    """Chair across the straight joint-space segment from start to goal: the segment is infeasible, the seeded RRT finds a way around it with
     batched oracle feasibility checks, and planOptimizedTrajectory returns a shorter, still collision-free trajectory."""
     from semiinfiniteoptimization_b200 import geometryopt as G, planopt
     w, robot, p0 = _inputs()
     chair = w.rigidObject(0)
-    chair.setTransform(chair.getTransform()[0], list(scenes.CHAIR_IN_PATH))
+    chair.setTransform(chair.getTransform()[0], [0.59, -0.22, 0.54])      # endpoints clear by 0.18 m, the straight segment cuts the chair
     start, goal = p0["milestones"][0], p0["milestones"][-1]
     kin = G.RobotKinematicsCache(robot)
     feas = planopt.OracleFeasibility(robot, [chair], kin)
