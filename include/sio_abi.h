@@ -211,6 +211,19 @@ int sio_lockstep_pose_solve(sio_ctx* ctx, sio_handle grid, sio_handle cloud, con
 int sio_mesh_distance_grid(sio_ctx* ctx, const double* verts, int32_t nv, const int32_t* tris, int32_t nt,
                            const double bmin[3], const double h[3], const int32_t dims[3], double* out_dist);
 
+/* The whole conversion on the device: distances as above, then the side of every cell -- the generalised winding number
+ * (> 1/2 = inside; robust to the open / self-intersecting benchmark meshes) for the first cell of each z-column and for
+ * every cell within one cell size of the surface, inherited from the z-predecessor elsewhere -- and the float32 samples
+ * out_sdf[(i*ny + j)*nz + k] that sio_grid_create takes.  Equal to the host builder's grid (tests). */
+int sio_mesh_sdf_grid(sio_ctx* ctx, const double* verts, int32_t nv, const int32_t* tris, int32_t nt,
+                      const double bmin[3], const double h[3], const int32_t dims[3], float* out_sdf);
+/* replaces: geom.convert('PointCloud', pcres) -- geometryopt.py:65.  The mesh vertices plus, per triangle, the lattice
+ * spanned by its two shorter edges with ceil(edge / res) subdivisions (no surface point farther than ~res from a
+ * sample), points shared between triangles merged (quantised to 1e-9 m, first occurrence kept, order preserved).
+ * out_pts [capacity*3] float64 (NULL: count only); *n_out = number of points. */
+int sio_mesh_surface_sample(sio_ctx* ctx, const double* verts, int32_t nv, const int32_t* tris, int32_t nt, double res,
+                            double* out_pts, int64_t capacity, int64_t* n_out);
+
 /* ---- the QPs of one lock-step SIP iteration ------------------------------------
  * replaces: ConstraintGenerationData.solve_qp_osqp -> osqp.OSQP().setup/solve -- sip.py:294-331, one
  * call per problem per outer iteration (sip.py:964), here for `nprob` problems at once, one warp each:

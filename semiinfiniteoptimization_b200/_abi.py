@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "sio_grid_create", "sio_grid_destroy", "sio_cloud_create", "sio_cloud_order", "sio_cloud_destroy", "sio_cloud_size",
     "sio_query", "sio_cloud_query_dev", "sio_cloud_perm",
     "sio_min_distance", "sio_min_distance_dev", "sio_under_fetch",
-    "sio_pose_rows", "sio_sip_step_qp", "sio_mesh_distance_grid", "sio_lockstep_pose_solve",
+    "sio_pose_rows", "sio_sip_step_qp", "sio_mesh_distance_grid", "sio_mesh_sdf_grid", "sio_mesh_surface_sample", "sio_lockstep_pose_solve",
     "sio_robot_create", "sio_robot_destroy", "sio_fk", "sio_chain_rows", "sio_robot_min_distance", "sio_robot_pairs_min_distance",
     "sio_bench_gather", "sio_ctx_last_bulk_ms", "sio_ctx_last_prune_stats", "sio_ctx_last_qp_iters",
 )
@@ -82,6 +82,8 @@ def load_library():
     L.sio_pose_rows.argtypes = [P, I32, P, P, I64, P, C.c_int, P, P]
     L.sio_sip_step_qp.argtypes = [P, I32, I64, P, P, P, P, P, P, P, D, D, D, I32, P, P]
     L.sio_mesh_distance_grid.argtypes = [P, P, I32, P, I32, P, P, P, P]
+    L.sio_mesh_sdf_grid.argtypes = [P, P, I32, P, I32, P, P, P, P]
+    L.sio_mesh_surface_sample.argtypes = [P, P, I32, P, I32, D, P, I64, C.POINTER(I64)]
     L.sio_lockstep_pose_solve.argtypes = [P, I32, I32, P, P, I64, P, P, P, P, P, P, P, P, P, P, P, P]
     L.sio_robot_create.argtypes = [P, I32, P, P, P, P, C.POINTER(I32)]
     L.sio_robot_destroy.argtypes = [P, I32]
@@ -300,6 +302,29 @@ class Context:
         out = np.empty(tuple(int(v) for v in d3))
         self._ck(self.L.sio_mesh_distance_grid(self.h, V.ctypes.data, len(V), T.ctypes.data, len(T), b.ctypes.data, hh.ctypes.data,
                                                d3.ctypes.data, out.ctypes.data))
+        return out
+
+    def mesh_sdf_grid(self, verts, tris, bmin, h, dims):
+        """Signed distance samples float32 (nx, ny, nz) at the cell centres: distances AND sides on the device."""
+        V = _f64(verts).reshape(-1, 3)
+        T = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1, 3)
+        b, hh = _f64(bmin).reshape(3), _f64(h).reshape(3)
+        d3 = np.ascontiguousarray(dims, dtype=np.int32).reshape(3)
+        out = np.empty(tuple(int(v) for v in d3), dtype=np.float32)
+        self._ck(self.L.sio_mesh_sdf_grid(self.h, V.ctypes.data, len(V), T.ctypes.data, len(T), b.ctypes.data, hh.ctypes.data,
+                                          d3.ctypes.data, out.ctypes.data))
+        return out
+
+    def mesh_surface_sample(self, verts, tris, res):
+        """Surface point cloud (n, 3) float64 at resolution `res` (vertices + per-triangle lattices, duplicates merged)."""
+        V = _f64(verts).reshape(-1, 3)
+        T = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1, 3)
+        n = C.c_int64(0)
+        self._ck(self.L.sio_mesh_surface_sample(self.h, V.ctypes.data, len(V), T.ctypes.data if len(T) else None, len(T), float(res),
+                                                None, 0, C.byref(n)))
+        out = np.empty((n.value, 3))
+        self._ck(self.L.sio_mesh_surface_sample(self.h, V.ctypes.data, len(V), T.ctypes.data if len(T) else None, len(T), float(res),
+                                                out.ctypes.data, n.value, C.byref(n)))
         return out
 
     # -- SIP-step QPs --

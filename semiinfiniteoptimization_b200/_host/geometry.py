@@ -161,6 +161,18 @@ def set_distance_grid_builder(fn):
     _distance_grid_fn = fn
 
 
+# the whole conversion on the device (row f3): fn(verts, tris, bmin, h, dims) -> float32 (nx,ny,nz) SIGNED samples
+# (sio_mesh_sdf_grid) and fn(verts, tris, res) -> float64 (n,3) surface points (sio_mesh_surface_sample).  geometryopt
+# installs both; the host implementations below remain what the CPU-only tests and the golden generator run.
+_sdf_grid_fn = None
+_surface_sample_fn = None
+
+
+def set_device_converters(sdf_fn, sample_fn):
+    global _sdf_grid_fn, _surface_sample_fn
+    _sdf_grid_fn, _surface_sample_fn = sdf_fn, sample_fn
+
+
 def mesh_to_sdf(mesh, res, pad_cells=SDF_PAD_CELLS):
     lo, hi = mesh.bbox()
     dims = np.maximum(1, np.ceil((hi - lo) / res - 1e-9).astype(np.int64)) + 2 * pad_cells
@@ -170,6 +182,8 @@ def mesh_to_sdf(mesh, res, pad_cells=SDF_PAD_CELLS):
     out = np.empty(tuple(int(d) for d in dims), dtype=np.float32)
     dims32 = np.ascontiguousarray(dims, dtype=np.int32)
     bmin_c = np.ascontiguousarray(bmin)
+    if _sdf_grid_fn is not None:
+        return VolumeGrid(np.ascontiguousarray(_sdf_grid_fn(mesh.verts, mesh.tris, bmin_c, h, dims32), dtype=np.float32), bmin, bmax)
     if _distance_grid_fn is not None:
         dist = np.ascontiguousarray(_distance_grid_fn(mesh.verts, mesh.tris, bmin_c, h, dims32), dtype=np.float64)
         rc = _lib().hg_sdf_sign_pass(mesh.verts.ctypes.data, mesh.tris.ctypes.data, len(mesh.tris), bmin_c.ctypes.data,
@@ -296,7 +310,10 @@ class Geometry3D:
                 out = Geometry3D(self.data)      # an existing cloud is not densified
             elif isinstance(self.data, TriangleMesh):
                 res = float(param) if param and param > 0 else span / AUTO_PC_DIVS
-                out = Geometry3D(PointCloud(sample_mesh_surface(self.data, res)))
+                if _surface_sample_fn is not None and np.isfinite(res):
+                    out = Geometry3D(PointCloud(np.asarray(_surface_sample_fn(self.data.verts, self.data.tris, res), dtype=np.float64)))
+                else:
+                    out = Geometry3D(PointCloud(sample_mesh_surface(self.data, res)))
             else:
                 raise ValueError("cannot convert a %s to a PointCloud" % self.type())
         else:

@@ -1168,6 +1168,120 @@ int sio_mesh_distance_grid(sio_ctx* c, const double* verts, int32_t nv, const in
     return SIO_OK;
 }
 
+// mesh -> SIGNED distance grid, distances and sides on the device
+int sio_mesh_sdf_grid(sio_ctx* c, const double* verts, int32_t nv, const int32_t* tris, int32_t nt,
+                      const double bmin[3], const double h[3], const int32_t dims[3], float* out_sdf) {
+    if (!c || !verts || !tris || !bmin || !h || !dims || !out_sdf || nv <= 0 || nt <= 0)
+        return fail(SIO_ERR_INVALID, "sio_mesh_sdf_grid: bad argument");
+    const int64_t ncell = (int64_t)dims[0] * dims[1] * dims[2];
+    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || ncell >= (1LL << 31)) return fail(SIO_ERR_INVALID, "sio_mesh_sdf_grid: bad dims");
+    std::vector<double> tri((size_t)nt * 9);
+    for (int t = 0; t < nt; ++t)
+        for (int v = 0; v < 3; ++v) {
+            const int32_t idx = tris[3 * t + v];
+            if (idx < 0 || idx >= nv) return fail(SIO_ERR_INVALID, "sio_mesh_sdf_grid: triangle %d refers to vertex %d", t, idx);
+            for (int a = 0; a < 3; ++a) tri[(size_t)t * 9 + v * 3 + a] = verts[3 * (size_t)idx + a];
+        }
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    CU(c->s_in0.ensure(tri.size() * sizeof(double)));
+    CU(c->s_out0.ensure((size_t)ncell * sizeof(double)));
+    CU(c->s_out1.ensure((size_t)ncell * sizeof(float)));
+    CU(c->s_out2.ensure((size_t)ncell));
+    CU(cudaMemcpyAsync(c->s_in0.p, tri.data(), tri.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_mesh_distance(c->s_in0.as<double>(), nt, bmin, h, dims, c->s_out0.as<double>(), st);
+    launch_sdf_sign(c->s_in0.as<double>(), nt, bmin, h, dims, c->s_out0.as<double>(), c->s_out2.as<int8_t>(), c->s_out1.as<float>(), st);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_sdf, c->s_out1.p, (size_t)ncell * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SIO_OK;
+}
+
+// mesh -> surface point cloud at resolution `res`
+int sio_mesh_surface_sample(sio_ctx* c, const double* verts, int32_t nv, const int32_t* tris, int32_t nt, double res,
+                            double* out_pts, int64_t capacity, int64_t* n_out) {
+    if (!c || !verts || !n_out || nv <= 0 || nt < 0 || (nt > 0 && !tris)) return fail(SIO_ERR_INVALID, "sio_mesh_surface_sample: bad argument");
+    // layout (host, O(triangles)): the vertices first, then one block per triangle, triangles grouped by their (m1, m2)
+    // in lexicographic order, ascending triangle index inside a group -- the order the host builder emits
+    std::vector<LatticeTriHost> recs;
+    int64_t total = nv;
+    if (res > 0 && std::isfinite(res) && nt > 0) {
+        struct Item { int32_t m1, m2, t; };
+        std::vector<Item> items;
+        std::vector<LatticeTriHost> tmp((size_t)nt);
+        for (int t = 0; t < nt; ++t) {
+            const double* P[3];
+            for (int v = 0; v < 3; ++v) {
+                const int32_t idx = tris[3 * t + v];
+                if (idx < 0 || idx >= nv) return fail(SIO_ERR_INVALID, "sio_mesh_surface_sample: triangle %d refers to vertex %d", t, idx);
+                P[v] = verts + 3 * (size_t)idx;
+            }
+            auto dist = [](const double* x, const double* y) {
+                const double d0 = x[0] - y[0], d1 = x[1] - y[1], d2 = x[2] - y[2];
+                return std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            };
+            const double e[3] = {dist(P[2], P[1]), dist(P[0], P[2]), dist(P[1], P[0])};       // edge opposite vertex v
+            int apex = 0;
+            if (e[1] > e[apex]) apex = 1;
+            if (e[2] > e[apex]) apex = 2;
+            const double *A = P[apex], *Bp = P[(apex + 1) % 3], *Cp = P[(apex + 2) % 3];
+            LatticeTriHost r;
+            for (int a = 0; a < 3; ++a) { r.a[a] = A[a]; r.b[a] = Bp[a]; r.c[a] = Cp[a]; }
+            r.m1 = (int32_t)std::max(1.0, std::ceil(dist(Bp, A) / res - 1e-9));
+            r.m2 = (int32_t)std::max(1.0, std::ceil(dist(Cp, A) / res - 1e-9));
+            r.base = 0;
+            tmp[t] = r;
+            if (!(r.m1 == 1 && r.m2 == 1)) items.push_back({r.m1, r.m2, t});
+        }
+        std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.m1 != y.m1 ? x.m1 < y.m1 : x.m2 < y.m2; });
+        recs.reserve(items.size());
+        for (const Item& it : items) {
+            LatticeTriHost r = tmp[it.t];
+            int64_t cnt = 0;
+            for (int i = 0; i <= r.m1; ++i) {
+                const double u = (double)i / (double)r.m1;
+                for (int j = 0; j <= r.m2; ++j) {
+                    const double v = (double)j / (double)r.m2;
+                    if ((u + v) <= 1.0 + 1e-12 && !((i == 0 && j == 0) || (i == r.m1 && j == 0) || (i == 0 && j == r.m2))) ++cnt;
+                }
+            }
+            r.base = total;
+            total += cnt;
+            recs.push_back(r);
+        }
+    }
+    if (total >= (1LL << 31)) return fail(SIO_ERR_INVALID, "sio_mesh_surface_sample: %lld lattice points: too many", (long long)total);
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    uint64_t slots = 1024;
+    while (slots < 2 * (uint64_t)total) slots <<= 1;
+    const int64_t nb = (total + 1023) / 1024;
+    CU(c->s_in0.ensure(std::max<size_t>(recs.size(), 1) * sizeof(LatticeTriHost)));
+    CU(c->s_in1.ensure((size_t)total * 3 * sizeof(double)));          // all lattice points
+    CU(c->s_out0.ensure((size_t)total * 3 * sizeof(double)));         // compacted
+    CU(c->s_in2.ensure((size_t)slots * sizeof(uint32_t)));
+    CU(c->s_out2.ensure((size_t)total));
+    CU(c->s_in3.ensure((size_t)(nb + 1) * sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(c->s_in1.p, verts, (size_t)nv * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (!recs.empty()) {
+        CU(cudaMemcpyAsync(c->s_in0.p, recs.data(), recs.size() * sizeof(LatticeTriHost), cudaMemcpyHostToDevice, st));
+        launch_lattice_fill(c->s_in0.p, (int32_t)recs.size(), c->s_in1.as<double>(), st);
+    }
+    launch_dedup(c->s_in1.as<double>(), total, c->s_in2.as<uint32_t>(), slots, c->s_out2.as<uint8_t>(), c->s_in3.as<uint32_t>(),
+                 c->s_out0.as<double>(), st);
+    c->launches += 6 + (recs.empty() ? 0 : 1);
+    CU(cudaGetLastError());
+    uint32_t kept = 0;
+    CU(cudaMemcpyAsync(&kept, c->s_in3.as<uint32_t>() + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_out = (int64_t)kept;
+    if (!out_pts) return SIO_OK;                                      // count only
+    if ((int64_t)kept > capacity) return fail(SIO_ERR_OVERFLOW, "sio_mesh_surface_sample: %u points, capacity %lld", kept, (long long)capacity);
+    CU(cudaMemcpy(out_pts, c->s_out0.p, (size_t)kept * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    return SIO_OK;
+}
+
 // ---- SIP-step QPs ----------------------------------------------------------------------------------------
 int sio_sip_step_qp(sio_ctx* c, int32_t n, int64_t nprob, const double* W, const double* xdes, const double* xmin,
                     const double* xmax, const int64_t* offsets, const double* rows, const double* depths, double reg,

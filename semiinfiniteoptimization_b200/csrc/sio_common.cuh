@@ -138,6 +138,14 @@ int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, con
 // mesh -> unsigned distance at every cell centre (sio_sdf.cu); tri = [nt][9] doubles
 void launch_mesh_distance(const double* tri, int32_t nt, const double bmin[3], const double h[3], const int32_t dims[3],
                           double* out, cudaStream_t st);
+// inside/outside sign of a distance grid (winding number near the surface, inherited along z elsewhere) -> float32 SDF
+void launch_sdf_sign(const double* tri, int32_t nt, const double bmin[3], const double h[3], const int32_t dims[3],
+                     const double* dist, int8_t* side, float* out, cudaStream_t st);
+// surface sampler: lattice points of every triangle (host-built layout records), then order-preserving de-duplication
+struct LatticeTriHost { double a[3], b[3], c[3]; int32_t m1, m2; int64_t base; };
+void launch_lattice_fill(const void* tris, int32_t nt, double* pts, cudaStream_t st);
+void launch_dedup(const double* pts, int64_t n, uint32_t* table, uint64_t table_slots, uint8_t* keep, uint32_t* counts, double* out,
+                  cudaStream_t st);
 void launch_gather_bench(const float* arr, int64_t n_elems, const uint32_t* idx, int64_t n_gathers,
                          float* sink, cudaStream_t st);
 

@@ -59,6 +59,9 @@ PRUNE_SWEEPS = False        # C4 (8k-point chair cloud, 65 coarse sub-tiles): me
 # trajectory sweeps: evaluate interior time samples only where the Lipschitz lower bound of an (edge, link) pair allows a
 # new minimum (the reference's own pruning rule, gopt:761-797); False = every sample of every edge (one device call)
 LIPSCHITZ_SCHEDULE = True
+# Geometry3D.convert('VolumeGrid' | 'PointCloud') of a mesh runs on the device (False: distances on the device, sign pass
+# and surface sampler on the host, as in round 1)
+DEVICE_CONVERSION = True
 
 
 def _sweep_flags():
@@ -131,10 +134,14 @@ class PenetrationDepthGeometry:
             self.polyhedron = None
             self._dev = _DeviceGeometry(context or _abi.default_context())
             self._T12 = se3.to_rowmajor12(geom.getCurrentTransform())
-            if gridres is not None:
-                # mesh -> SDF: distances on the device (sio_mesh_distance_grid), signs on the host; same grid as the
-                # host-only builder, bit for bit
+            # mesh -> SDF and mesh -> surface cloud on the device (row f3: sio_mesh_sdf_grid, sio_mesh_surface_sample); the
+            # results equal the host builder's (tests/test_gpu_parity.py)
+            if DEVICE_CONVERSION:
+                _hostgeometry.set_device_converters(self._dev.ctx.mesh_sdf_grid, self._dev.ctx.mesh_surface_sample)
+            else:
+                _hostgeometry.set_device_converters(None, None)
                 _hostgeometry.set_distance_grid_builder(self._dev.ctx.mesh_distance_grid)
+            if gridres is not None:
                 try:
                     self.grid = geom.convert('VolumeGrid', gridres)
                 except Exception as e:

@@ -476,6 +476,31 @@ def test_c5_scale_under_bound_set_is_exact(ctx, O):
     ctx.grid_destroy(g)
 
 
+def test_smem_variant_equals_brick_kernel(ctx, O):
+    """SIO_SMEM_GRID: the bulk pass from a TMA-staged shared-memory copy of the grid (a measured alternative, see
+    profiles/r02_kmin_evidence.md) returns the default kernel's minima / arg-minima, which equal the oracle's; grids that
+    do not fit a CTA's shared memory are refused."""
+    from semiinfiniteoptimization_b200 import _abi
+    g, G, cloud, T = _c1_scene(ctx, O)
+    c = ctx.cloud_create(cloud)
+    d0, a0 = O.min_distance(G, cloud, T)
+    d1, a1, _ = ctx.min_distance(g, c, T, flags=F32 | _abi.SIO_SMEM_GRID, want_under=False)
+    assert np.array_equal(a1, a0) and np.abs(d1 - d0).max() <= 1e-12
+    bound = np.full(len(T), float(np.median(d0)))
+    d2, a2, _ = ctx.min_distance(g, c, T, bound=bound, flags=F32 | _abi.SIO_SMEM_GRID, want_under=False)
+    d3, a3 = O.min_distance(G, cloud, T, bound=bound)
+    assert np.array_equal(a2, a3) and np.abs(d2 - d3).max() <= 1e-12
+    with pytest.raises(_abi.SioError):                      # the under-bound set is not produced by this variant
+        ctx.min_distance(g, c, T, bound=bound, flags=F32 | _abi.SIO_SMEM_GRID)
+    big = util.fixture_geometry("m1062").convert("VolumeGrid", 0.02).getVolumeGrid()
+    gb = ctx.grid_create(big.values, big.bmin, big.bmax)
+    with pytest.raises(_abi.SioError):
+        ctx.min_distance(gb, c, T, flags=F32 | _abi.SIO_SMEM_GRID, want_under=False)
+    ctx.grid_destroy(gb)
+    ctx.cloud_destroy(c)
+    ctx.grid_destroy(g)
+
+
 # ---- row f3: mesh -> SDF, distances on the device ------------------------------------------------------------------
 @pytest.mark.parametrize("name,res", [("cube", 0.05), ("m797", 0.05), ("m1062", 0.02), ("sphere", 0.1)])
 def test_device_sdf_builder_equals_host_builder(ctx, name, res):
@@ -495,6 +520,57 @@ def test_device_sdf_builder_equals_host_builder(ctx, name, res):
 
 
 # ---- error behaviour at the boundary (status codes + message, the shim raises) ----------------------
+@pytest.mark.parametrize("name,res,pcres", [("cube", 0.05, 0.02), ("sphere", 0.1, 0.05), ("m797", 0.08, 0.05)])
+def test_device_mesh_conversions_equal_the_independent_restatement(ctx, name, res, pcres):
+    """Row f3 complete: distances, inside/outside sides (winding number) and the surface sampler as kernels
+    (sio_mesh_sdf_grid, sio_mesh_surface_sample) against oracle/ref_meshconv.py -- numpy code that shares nothing with the
+    product's builders.  Identical float32 samples; identical points in identical order."""
+    from oracle import ref_meshconv as RM
+    from semiinfiniteoptimization_b200._host import geometry as HG
+    g = util.fixture_geometry(name)
+    lo, hi = g.data.bbox()
+    dims = np.maximum(1, np.ceil((hi - lo) / res - 1e-9).astype(np.int64)) + 2 * HG.SDF_PAD_CELLS
+    bmin = lo - HG.SDF_PAD_CELLS * res
+    h = np.array([res] * 3)
+    got = ctx.mesh_sdf_grid(g.data.verts, g.data.tris, bmin, h, dims)
+    ref = RM.mesh_sdf(g.data.verts, g.data.tris, bmin, h, dims)
+    assert got.dtype == np.float32 and got.shape == ref.shape
+    assert np.array_equal(np.sign(got), np.sign(ref))
+    assert np.array_equal(got, ref)
+    pts = ctx.mesh_surface_sample(g.data.verts, g.data.tris, pcres)
+    assert np.array_equal(pts, RM.surface_sample(g.data.verts, g.data.tris, pcres))
+
+
+def test_device_mesh_conversions_equal_the_host_builders_at_full_size(ctx):
+    """The benchmark's own geometry: m1062 at gridres 0.01 (700 k cells x 692 triangles) and fine surface clouds -- too
+    large for the numpy restatement, so the host builders (themselves pinned to it on the CPU) are the comparison; and
+    the drop-in class builds its grid and cloud on the device by default."""
+    from semiinfiniteoptimization_b200 import geometryopt as G
+    from semiinfiniteoptimization_b200._host import geometry as HG
+    try:
+        HG.set_device_converters(None, None)
+        HG.set_distance_grid_builder(None)
+        g = util.fixture_geometry("m1062")
+        host_grid = g.convert("VolumeGrid", 0.01).getVolumeGrid()
+        host_pc = {(n, r): util.fixture_geometry(n).convert("PointCloud", r).getPointCloud().points
+                   for n, r in (("m1062", 0.005), ("m797", 0.004), ("cube", 0.003))}
+        HG.set_device_converters(ctx.mesh_sdf_grid, ctx.mesh_surface_sample)
+        dev_grid = util.fixture_geometry("m1062").convert("VolumeGrid", 0.01).getVolumeGrid()
+        assert np.array_equal(dev_grid.values, host_grid.values) and np.array_equal(dev_grid.bmin, host_grid.bmin)
+        for (n, r), want in host_pc.items():
+            got = util.fixture_geometry(n).convert("PointCloud", r).getPointCloud().points
+            assert len(got) > 10000 and np.array_equal(got, want), (n, r, got.shape, want.shape)
+    finally:
+        HG.set_device_converters(None, None)
+    assert G.DEVICE_CONVERSION
+    pdg = G.PenetrationDepthGeometry(util.fixture_geometry("m797"), 0.05, 0.02, context=ctx)
+    assert HG._sdf_grid_fn is not None and HG._surface_sample_fn is not None
+    HG.set_device_converters(None, None)
+    ref = util.fixture_geometry("m797")
+    assert np.array_equal(pdg.grid.getVolumeGrid().values, ref.convert("VolumeGrid", 0.05).getVolumeGrid().values)
+    assert np.array_equal(pdg.pcdata.points, ref.convert("PointCloud", 0.02).getPointCloud().points)
+
+
 def test_error_paths(ctx, O):
     from semiinfiniteoptimization_b200 import _abi
     vg = util.random_grid(95)

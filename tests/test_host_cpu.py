@@ -265,6 +265,24 @@ def test_mesh_conversions_are_deterministic_and_sane():
 
 
 # ---- QP -------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,res,pcres", [("cube", 0.05, 0.02), ("m797", 0.08, 0.05)])
+def test_host_mesh_conversions_equal_the_independent_restatement(name, res, pcres):
+    """Row f3's definition of mesh -> SDF and mesh -> surface cloud, host builders (hostgeom.c / geometry.py) against
+    oracle/ref_meshconv.py (numpy, shares no code with them): identical samples, identical points in identical order."""
+    from oracle import ref_meshconv as RM
+    from semiinfiniteoptimization_b200._host import geometry as HG
+    HG.set_device_converters(None, None)
+    HG.set_distance_grid_builder(None)
+    g = util.fixture_geometry(name)
+    vg = g.convert("VolumeGrid", res).getVolumeGrid()
+    h = (vg.bmax - vg.bmin) / np.array(vg.dims)
+    ref = RM.mesh_sdf(g.data.verts, g.data.tris, vg.bmin, h, vg.dims)
+    assert np.array_equal(ref, vg.values)
+    assert (ref < 0).any() and (ref > 0).any()
+    pc = g.convert("PointCloud", pcres).getPointCloud().points
+    assert np.array_equal(pc, RM.surface_sample(g.data.verts, g.data.tris, pcres))
+
+
 def test_qp_matches_kkt_on_random_problems():
     from semiinfiniteoptimization_b200._host import qp
     rng = np.random.default_rng(7)
