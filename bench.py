@@ -13,9 +13,9 @@ centroid) + centre(bbox(m1062)) + N(0, 0.005^2 I), numpy default_rng(1)); 64 see
 A STEP is one oracle sweep: the K2 call (transform + trilinear SDF query of every cloud point for
 every pose, minimum / arg-minimum / under-bound set with the float64 near-tie re-check) over
 64 x 2^20 = 67,108,864 point-queries per GPU.  With N > 1 every rank owns its own 64 poses (weak
-scaling; geometry replicated); sweeps need no collective, and the compact per-pose results are all-gathered with
-NCCL once per reporting interval (the K timed steps), inside the timed total (the ranks are lined up with a barrier
-before it, so that its events time the exchange and not the ranks' start skew; `per_rank_ms` shows every rank's figures).
+scaling; geometry replicated); sweeps need no collective, and the compact per-pose results reach every rank once per
+reporting interval (the K timed steps) as peer stores over NVLink issued by the interval's last sweep (result boards,
+include/sio_abi.h), inside that step's timed span; an NCCL all-gather of the same records verifies them after the timing.
 
 `value`  : point-queries/s, inputs resident in HBM, timed with CUDA events on the launching stream,
            max over ranks; L2 is flushed between timed steps.
@@ -464,9 +464,9 @@ def workload_config(ngpu):
     return {"workload": "C2 bunny-vs-m1062 fine grid: m1062 SDF gridres 0.01 (68x98x105 f32), synthetic 2^20-point bunny "
                         "upsample (seed 1), 64 seeded poses per GPU, one K2 min/arg-min/under-bound sweep per step",
             "poses_per_gpu": POSES_PER_GPU, "cloud_points": CLOUD_N, "queries_per_step_per_gpu": POSES_PER_GPU * CLOUD_N,
-            "sharding": "poses across ranks (geometry replicated), no collective inside a sweep; ONE NCCL all_gather of the per-pose "
-                        "results per reporting interval (= the K timed steps), inside the timed total (ranks are re-aligned with a "
-                        "barrier before it, so its events time the exchange, not the ranks' start skew)" if ngpu > 1 else "single GPU",
+            "sharding": "poses across ranks (geometry replicated), no collective inside a sweep; the per-pose results reach every "
+                        "rank once per reporting interval (= the K timed steps) as peer stores over NVLink issued by the last sweep "
+                        "(inside its timed step)" if ngpu > 1 else "single GPU",
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
@@ -515,13 +515,21 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
 
-    def step():
-        ctx.min_distance_dev([g], c, dT.data_ptr(), dbound.data_ptr(), B, _abi.SIO_F32, ddmin.data_ptr(), darg.data_ptr(),
-                             d_n_under_ptr=dnu.data_ptr())
+    # The path's only exchange: the compact per-pose results (20 B per pose) of every rank, once per reporting
+    # interval (= the K timed steps).  It is done WITHOUT a collective launch: the interval's last sweep is issued with
+    # SIO_PUSH_BOARDS and its tail stores this rank's records into every rank's result board over NVLink (peer memory
+    # mapped through CUDA IPC, dist.ResultBoards); the barrier that ends the timed region is all the synchronisation it
+    # needs.  An NCCL all-gather of the same records runs AFTER the timed region, only to verify the boards.
+    boards = None
+    if world > 1:
+        from semiinfiniteoptimization_b200 import dist as sdist
+        boards = sdist.ResultBoards(ctx, B)
+
+    def step(push=False):
+        ctx.min_distance_dev([g], c, dT.data_ptr(), dbound.data_ptr(), B, _abi.SIO_F32 | (_abi.SIO_PUSH_BOARDS if push else 0),
+                             ddmin.data_ptr(), darg.data_ptr(), d_n_under_ptr=dnu.data_ptr())
 
     def gather():
-        """The path's only exchange: the compact per-pose results (24 B per pose) of every rank, once per reporting
-        interval -- here once per K timed steps, as batch.solve_sharded gathers once per solve."""
         with torch.cuda.stream(stream):
             dist.all_gather_into_tensor(gathered, packed)
 
@@ -548,8 +556,15 @@ def main():
     with torch.cuda.graph(graph, stream=stream):
         step()
     launches_per_step = ctx.kernel_launches - launches_per_step
+    graph_push = None
+    if world > 1:                                       # the interval's last step: the same sweep + the peer stores
+        graph_push = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_push, stream=stream):
+            step(push=True)
     with torch.cuda.stream(stream):
         graph.replay()
+        if graph_push is not None:
+            graph_push.replay()
     ctx.sync()
     torch.cuda.synchronize()
     if world > 1:
@@ -562,34 +577,35 @@ def main():
         with torch.cuda.stream(stream):
             flush.zero_()                       # evict L2 (126 MB) between timed steps
             ev[k][0].record(stream)
-            graph.replay()
+            (graph_push if (graph_push is not None and k == args.steps - 1) else graph).replay()
             ev[k][1].record(stream)
-    gather_ms = 0.0
-    if world > 1:
-        # ranks leave the opening barrier milliseconds apart (eight host processes on shared cores); line them up again so
-        # that the gather's events time the exchange itself and not that start skew (the steps are timed per step on the
-        # device, so the skew is in none of them either)
-        ctx.sync()
-        torch.cuda.synchronize()
-        dist.barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        gather()
-        g1.record(stream)
-        g1.synchronize()
-        gather_ms = g0.elapsed_time(g1)
     ctx.sync()
     torch.cuda.synchronize()
     if world > 1:
-        dist.barrier()
+        dist.barrier()                                  # every rank's peer stores have landed on every board
     t_wall = time.perf_counter() - t_wall0
+    exchange = None
+    if world > 1:
+        bd, ba, bn = boards.read()
+        gather()                                        # verification only, outside the timed region
+        torch.cuda.synchronize()
+        ref = gathered.cpu().numpy().reshape(world, 3 * B)
+        ok = (np.array_equal(bd, ref[:, :B]) and np.array_equal(ba, ref[:, B:2 * B].view(np.int64))
+              and np.array_equal(bn, ref[:, 2 * B:].view(np.int32)[:, :B]))
+        flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange = {"how": "peer stores over NVLink into every rank's result board (CUDA IPC mapped), issued by the interval's "
+                           "last sweep (SIO_PUSH_BOARDS); no collective launch in the timed region",
+                    "bytes_per_rank_pair": 20 * B, "verified_against_nccl_all_gather_on_every_rank": bool(flag.item() == 1.0)}
+        if not ok:
+            raise SystemExit("result boards differ from the NCCL all-gather of the same records")
     clocks = sampler.stop()
     launches = launches_per_step * args.steps
     ms_steps = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(ms_steps)) + gather_ms          # K sweeps + the one gather of the interval
+    total_ms = float(sum(ms_steps))                      # K sweeps, the last one carrying the exchange
     per_rank = None
     if world > 1:
-        mine = torch.tensor([float(sum(ms_steps)), gather_ms], dtype=torch.float64, device="cuda")
+        mine = torch.tensor([float(sum(ms_steps)), float(ms_steps[-1])], dtype=torch.float64, device="cuda")
         allr = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)                       # diagnostics: which rank is the maximum, and why
         per_rank = [[round(float(v[0]), 3), round(float(v[1]), 3)] for v in allr]
@@ -763,9 +779,9 @@ def main():
                                     "are served by L1/L2, not DRAM: `dram_fraction_measured` = ncu DRAM bytes per launch / time / peak"},
                     "l2_gather_peak_gbs": gather_peak}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "ms_per_step_median": float(np.median(ms_steps)), "gather_ms": gather_ms,
+                "ms_per_step": total_ms / args.steps, "ms_per_step_median": float(np.median(ms_steps)), "exchange": exchange,
                 "minvalue_calls_per_s": value / CLOUD_N,            # one call = one pose against the whole cloud
-                "per_rank_ms[steps_sum, gather]": per_rank,
+                "per_rank_ms[steps_sum, last_step_with_push]": per_rank,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
@@ -781,6 +797,8 @@ def main():
                                if pruned else None,
                                "exhaustive_e2e_over_cpu_pruned": e2e["value"] / cb["pruned"]["effective_queries_per_s"]}
         print(json.dumps(line))
+    if boards is not None:
+        boards.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -48,6 +48,7 @@ extern "C" {
 #define SIO_NO_NORMALIZE    0x2   /* return the raw analytic gradient instead of the unit one */
 #define SIO_WANT_GRAD       0x4
 #define SIO_PRUNE           0x8   /* K2: skip 128-point sub-tiles whose Lipschitz lower bound rules them out (results identical) */
+#define SIO_PUSH_BOARDS     0x20  /* K2 (_dev): after the call's kernels, store its results into every rank's result board (sio_ctx_set_boards) */
 #define SIO_SMEM_GRID       0x10  /* K2, one grid of <= 200 KB of samples: bulk pass from a TMA-staged shared-memory copy of the grid
                                      (a measured alternative, slower than the default brick kernel; minimum / arg-minimum only) */
 
@@ -73,6 +74,21 @@ int   sio_ctx_set_scratch_limit(sio_ctx* ctx, int64_t bytes);
 int   sio_ctx_set_under_capacity(sio_ctx* ctx, int64_t entries);
 int   sio_ctx_num_sms(sio_ctx* ctx);
 int64_t sio_ctx_kernel_launches(sio_ctx* ctx);      /* kernels launched by this context so far */
+
+/* ---- result boards: the multi-GPU exchange of the compact K2 results as peer stores over NVLink --------
+ * The path has no data-path collective; what crosses the links are the per-transform records (20 bytes each).  Instead
+ * of a collective launch per reporting interval, every rank owns a BOARD of nranks slots; after sio_ctx_set_boards,
+ * the tail of every sio_min_distance_dev call made with SIO_PUSH_BOARDS stores this rank's records [dmin f64 x B | argmin i64 x B | n_under i32 x B]
+ * into slot `rank` of EVERY rank's board (the peers' boards are mapped here through CUDA IPC), with a system-scope
+ * fence.  Once the ranks' streams have drained and the ranks have met at a host barrier, every board holds every
+ * rank's latest results; sio_board_read copies the local one out.  One process per GPU:
+ *     sio_board_create (local board + its 64-byte IPC handle)  ->  exchange the handles (torch.distributed)
+ *     ->  sio_board_open per peer  ->  sio_ctx_set_boards(rank, nranks, pointers, slot_bytes). */
+int sio_board_create(sio_ctx* ctx, int64_t bytes, void** dptr, unsigned char ipc_handle[64]);
+int sio_board_open(sio_ctx* ctx, const unsigned char ipc_handle[64], void** dptr);
+int sio_board_close(sio_ctx* ctx, void* dptr, int is_local);
+int sio_ctx_set_boards(sio_ctx* ctx, int32_t rank, int32_t nranks, void* const* boards, int64_t slot_bytes);   /* nranks <= 0: off */
+int sio_board_read(sio_ctx* ctx, void* host_out, int64_t bytes);
 
 /* ---- resident geometry ----------------------------------------------------------------------
  * replaces: Geometry3D.convert(...) results being handed to Klampt's collision data structures,

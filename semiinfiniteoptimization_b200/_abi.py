@@ -19,12 +19,14 @@ SIO_F64 = 0x1
 SIO_NO_NORMALIZE = 0x2
 SIO_PRUNE = 0x8
 SIO_SMEM_GRID = 0x10
+SIO_PUSH_BOARDS = 0x20
 
 # every symbol include/sio_abi.h declares (tests check the built library exports each of them)
 ABI_SYMBOLS = (
     "sio_abi_version", "sio_last_error",
     "sio_ctx_create", "sio_ctx_destroy", "sio_ctx_sync", "sio_ctx_stream", "sio_ctx_set_tau", "sio_ctx_set_scratch_limit",
     "sio_ctx_set_under_capacity", "sio_ctx_num_sms",
+    "sio_board_create", "sio_board_open", "sio_board_close", "sio_ctx_set_boards", "sio_board_read",
     "sio_ctx_kernel_launches",
     "sio_grid_create", "sio_grid_destroy", "sio_cloud_create", "sio_cloud_order", "sio_cloud_destroy", "sio_cloud_size",
     "sio_query", "sio_cloud_query_dev", "sio_cloud_perm",
@@ -63,6 +65,11 @@ def load_library():
     L.sio_ctx_set_tau.argtypes = [P, D]
     L.sio_ctx_set_scratch_limit.argtypes = [P, I64]
     L.sio_ctx_set_under_capacity.argtypes = [P, I64]
+    L.sio_board_create.argtypes = [P, I64, C.POINTER(P), P]
+    L.sio_board_open.argtypes = [P, P, C.POINTER(P)]
+    L.sio_board_close.argtypes = [P, P, C.c_int]
+    L.sio_ctx_set_boards.argtypes = [P, I32, I32, P, I64]
+    L.sio_board_read.argtypes = [P, P, I64]
     L.sio_ctx_num_sms.argtypes = [P]
     L.sio_ctx_kernel_launches.argtypes = [P]
     L.sio_ctx_kernel_launches.restype = I64
@@ -162,6 +169,40 @@ class Context:
     def set_under_capacity(self, entries):
         """Under-bound candidate records a K2 call holds (the host entry points grow it on their own)."""
         self._ck(self.L.sio_ctx_set_under_capacity(self.h, int(entries)))
+
+    # -- result boards (multi-GPU exchange by peer stores) --
+    def board_create(self, nbytes):
+        """(device pointer, 64-byte IPC handle) of a zeroed local board."""
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64)()
+        self._ck(self.L.sio_board_create(self.h, int(nbytes), C.byref(p), h))
+        return p.value, bytes(h)
+
+    def board_open(self, handle):
+        p = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._ck(self.L.sio_board_open(self.h, buf, C.byref(p)))
+        return p.value
+
+    def board_close(self, ptr, is_local):
+        self._ck(self.L.sio_board_close(self.h, C.c_void_p(ptr), 1 if is_local else 0))
+
+    def set_boards(self, rank, ptrs, slot_bytes):
+        if not ptrs:
+            self._ck(self.L.sio_ctx_set_boards(self.h, 0, 0, None, 0))
+            return
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self._ck(self.L.sio_ctx_set_boards(self.h, int(rank), len(ptrs), arr, int(slot_bytes)))
+
+    def board_read(self, nranks, slot_bytes, B):
+        """The local board as (dmin[nranks,B], argmin[nranks,B], n_under[nranks,B])."""
+        raw = np.empty(nranks * slot_bytes, dtype=np.uint8)
+        self._ck(self.L.sio_board_read(self.h, raw.ctypes.data, raw.nbytes))
+        raw = raw.reshape(nranks, slot_bytes)
+        d = np.ascontiguousarray(raw[:, :8 * B]).view(np.float64)
+        a = np.ascontiguousarray(raw[:, 8 * B:16 * B]).view(np.int64)
+        n = np.ascontiguousarray(raw[:, 16 * B:20 * B]).view(np.int32)
+        return d, a, n
 
     @property
     def num_sms(self):

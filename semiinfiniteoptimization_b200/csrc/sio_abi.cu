@@ -132,6 +132,11 @@ struct sio_ctx {
     GridDev single_grid_host{};       // host copy handed to the single-grid bulk kernel by value
     std::vector<sio_handle> staged_grids;   // handles whose table currently sits in s_gridtab (grids are immutable)
     double staged_tau = 0.0;
+    // result boards (multi-GPU exchange by peer stores): this rank, the boards of all ranks as device pointers
+    int board_rank = -1, board_n = 0;
+    int64_t board_slot = 0;
+    void* board_local = nullptr;
+    DevBuf s_boards;
     // state of the last min-distance call (for sio_under_fetch)
     bool under_valid = false, under_pending = false, under_final = false;
     std::vector<UnderEntry> under;
@@ -216,6 +221,7 @@ int sio_ctx_destroy(sio_ctx* c) {
     for (auto& p : c->clouds) if (p.live) { cudaFree(p.d_pts); cudaFree(p.d_rep); cudaFree(p.d_perm); }
     for (auto& r : c->robots) if (r.live) { cudaFree(r.d_parent); cudaFree(r.d_jtype); cudaFree(r.d_tparent); cudaFree(r.d_axis); }
     c->s_qp.release();
+    c->s_boards.release();
     c->s_lb.release(); c->s_ub.release(); c->s_items.release(); c->s_icnt.release(); c->h_icnt.release(); c->s_ls.release();
     for (int k = 0; k < sio_ctx::kLsBack; ++k) { c->s_qpb[k].release(); if (c->ls_stream[k]) cudaStreamDestroy(c->ls_stream[k]); }
     for (int k = 0; k < sio_ctx::kLsRing; ++k) { if (c->ls_evA[k]) cudaEventDestroy(c->ls_evA[k]); if (c->ls_evB[k]) cudaEventDestroy(c->ls_evB[k]); }
@@ -249,6 +255,59 @@ int sio_ctx_set_under_capacity(sio_ctx* c, int64_t entries) {
     return SIO_OK;
 }
 int sio_ctx_num_sms(sio_ctx* c) { return c ? c->num_sms : 0; }
+
+// ---- result boards ---------------------------------------------------------------------------------------------------
+int sio_board_create(sio_ctx* c, int64_t bytes, void** dptr, unsigned char ipc_handle[64]) {
+    if (!c || bytes <= 0 || !dptr) return fail(SIO_ERR_INVALID, "sio_board_create: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard guard(c->device);
+    void* p = nullptr;
+    CU(cudaMalloc(&p, (size_t)bytes));
+    CU(cudaMemset(p, 0, (size_t)bytes));
+    if (ipc_handle) {
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, p);
+        if (e != cudaSuccess) { cudaFree(p); return fail(SIO_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+        std::memcpy(ipc_handle, &h, 64);
+    }
+    *dptr = p;
+    return SIO_OK;
+}
+int sio_board_open(sio_ctx* c, const unsigned char ipc_handle[64], void** dptr) {
+    if (!c || !ipc_handle || !dptr) return fail(SIO_ERR_INVALID, "sio_board_open: bad argument");
+    DeviceGuard guard(c->device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handle, 64);
+    CU(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SIO_OK;
+}
+int sio_board_close(sio_ctx* c, void* dptr, int is_local) {
+    if (!c || !dptr) return fail(SIO_ERR_INVALID, "sio_board_close: bad argument");
+    DeviceGuard guard(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (is_local) { if (c->board_local == dptr) { c->board_n = 0; c->board_local = nullptr; } CU(cudaFree(dptr)); }
+    else CU(cudaIpcCloseMemHandle(dptr));
+    return SIO_OK;
+}
+int sio_ctx_set_boards(sio_ctx* c, int32_t rank, int32_t nranks, void* const* boards, int64_t slot_bytes) {
+    if (!c) return fail(SIO_ERR_INVALID, "null context");
+    if (nranks <= 0) { c->board_n = 0; c->board_rank = -1; c->board_local = nullptr; return SIO_OK; }
+    if (!boards || rank < 0 || rank >= nranks || slot_bytes <= 0 || slot_bytes % 8) return fail(SIO_ERR_INVALID, "sio_ctx_set_boards: bad argument");
+    DeviceGuard guard(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(c->s_boards.ensure((size_t)nranks * sizeof(void*)));
+    CU(cudaMemcpy(c->s_boards.p, boards, (size_t)nranks * sizeof(void*), cudaMemcpyHostToDevice));
+    c->board_rank = rank; c->board_n = nranks; c->board_slot = slot_bytes; c->board_local = boards[rank];
+    return SIO_OK;
+}
+int sio_board_read(sio_ctx* c, void* host_out, int64_t bytes) {
+    if (!c || !host_out || bytes <= 0 || !c->board_local) return fail(SIO_ERR_INVALID, "sio_board_read: no board set");
+    if (bytes > c->board_slot * c->board_n) return fail(SIO_ERR_INVALID, "sio_board_read: %lld bytes asked, the board has %lld", (long long)bytes, (long long)(c->board_slot * c->board_n));
+    DeviceGuard guard(c->device);
+    CU(cudaMemcpyAsync(host_out, c->board_local, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SIO_OK;
+}
 int64_t sio_ctx_kernel_launches(sio_ctx* c) { return c ? c->launches : 0; }
 
 // ---- geometry --------------------------------------------------------------------------------------
@@ -667,6 +726,11 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
         // the last batch's launch also carries the CTAs that re-check the float32 pass's under-bound candidates
         const bool last = b0 + Bc >= B;
         launch_finalize(a, /*all_tiles=*/f64, /*emit_under=*/f64 && want_under, (!f64 && want_under && last) ? c->num_sms : 0, st);
+        c->launches += 1;
+    }
+    if (c->board_n > 0 && (flags & SIO_PUSH_BOARDS)) {      // the results also go to every rank's board, over NVLink
+        if (B * 20 > c->board_slot) return fail(SIO_ERR_INVALID, "sio_min_distance_dev: %lld results do not fit a board slot of %lld bytes", (long long)B, (long long)c->board_slot);
+        launch_push_results(c->s_boards.as<void*>(), c->board_n, c->board_rank, c->board_slot, d_dmin, d_argmin, want_under ? d_n_under : nullptr, B, st);
         c->launches += 1;
     }
     CU(cudaGetLastError());

@@ -96,6 +96,8 @@ void launch_min_f32(const MinArgs& a, cudaStream_t st);
 void launch_min_pruned(const MinArgs& a, cudaStream_t st);
 bool launch_min_smem(const MinArgs& a, cudaStream_t st);      // TMA-staged shared-memory variant (needs a.xf); false = not applicable
 void launch_finalize(const MinArgs& a, bool all_tiles, bool emit_under, int n_recheck, cudaStream_t st);
+void launch_push_results(void* const* d_boards, int nranks, int rank, int64_t slot_bytes, const double* dmin, const int64_t* argmin,
+                         const int32_t* n_under, int64_t B, cudaStream_t st);
 
 void launch_cloud_query_f32(const float4* pts, const float4* rep, int64_t N, const XfRec* xf, int64_t B, int normalize,
                             float* out_d, float4* out_g, cudaStream_t st);

@@ -159,6 +159,33 @@ void launch_finalize(const MinArgs& a, bool all_tiles, bool emit_under, int n_re
                                                                       a.dmin, a.argmin);
 }
 
+// ---- result boards: the compact per-transform results stored straight into every rank's memory over NVLink ------------
+// One CTA per destination rank.  A board is nranks slots of slot_bytes; slot r of EVERY board receives rank r's records
+// [dmin f64 x B | argmin i64 x B | n_under i32 x B].  boards[] are device pointers valid on THIS device: the local board
+// and the peers' boards mapped through CUDA IPC (other processes) or peer access (same process).  The stores are plain
+// 8-byte writes over NVLink / NVSwitch; __threadfence_system() orders them before the kernel's completion, so that a
+// host-side barrier after the ranks' streams have drained (what bench.py and batch.solve_sharded do anyway) is all the
+// synchronisation the exchange needs -- no collective launch, no staging, no host copies.
+__global__ void k_push_results(void* const* __restrict__ boards, int rank, int64_t slot_bytes, const double* __restrict__ dmin,
+                               const int64_t* __restrict__ argmin, const int32_t* __restrict__ n_under, int64_t B) {
+    char* slot = reinterpret_cast<char*>(boards[blockIdx.x]) + (int64_t)rank * slot_bytes;
+    double* o_d = reinterpret_cast<double*>(slot);
+    int64_t* o_a = reinterpret_cast<int64_t*>(slot + 8 * B);
+    int32_t* o_n = reinterpret_cast<int32_t*>(slot + 16 * B);
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
+        o_d[b] = dmin[b];
+        o_a[b] = argmin[b];
+        o_n[b] = n_under ? n_under[b] : 0;
+    }
+    __threadfence_system();
+}
+
+void launch_push_results(void* const* d_boards, int nranks, int rank, int64_t slot_bytes, const double* dmin, const int64_t* argmin,
+                         const int32_t* n_under, int64_t B, cudaStream_t st) {
+    if (nranks <= 0 || B <= 0) return;
+    k_push_results<<<nranks, 128, 0, st>>>(d_boards, rank, slot_bytes, dmin, argmin, n_under, B);
+}
+
 // ---- K1 float64 ---------------------------------------------------------------------------------------
 __global__ void k_query_f64(const GridDev* __restrict__ grid, const double* __restrict__ T,
                             const double* __restrict__ pts, int64_t P, int normalize,

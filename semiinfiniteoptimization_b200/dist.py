@@ -109,6 +109,44 @@ def gather_records(local, n_total=None):
     return res
 
 
+class ResultBoards:
+    """The exchange of the compact K2 results as peer stores over NVLink (include/sio_abi.h "result boards"): every rank
+    owns a board of `world` slots; K2 calls made with SIO_PUSH_BOARDS store this rank's (dmin, argmin, n_under) records
+    into slot `rank` of every rank's board.  After the ranks' streams have drained and a barrier, `read()` returns every
+    rank's latest results from the LOCAL board -- no collective launch in between.  Single process: one slot."""
+
+    def __init__(self, ctx, B):
+        self.ctx, self.B = ctx, int(B)
+        self.rank, self.world = world()
+        self.slot_bytes = ((20 * self.B + 63) // 64) * 64
+        self.local, handle = ctx.board_create(self.slot_bytes * self.world)
+        self.ptrs = [None] * self.world
+        self.ptrs[self.rank] = self.local
+        d = _dist()
+        if d is not None and self.world > 1:
+            handles = [None] * self.world
+            d.all_gather_object(handles, handle)
+            for r, h in enumerate(handles):
+                if r != self.rank:
+                    self.ptrs[r] = ctx.board_open(h)
+        ctx.set_boards(self.rank, self.ptrs, self.slot_bytes)
+
+    def read(self):
+        return self.ctx.board_read(self.world, self.slot_bytes, self.B)
+
+    def close(self):
+        if self.local is None:
+            return
+        self.ctx.set_boards(0, [], 0)
+        barrier()                                  # nobody may still be storing into a board that is about to go
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank and p is not None:
+                self.ctx.board_close(p, False)
+        barrier()
+        self.ctx.board_close(self.local, True)
+        self.local = None
+
+
 def argmin_allreduce(value, payload):
     """Global minimum over ranks of (value, payload): returns the winning (value, payload) on every
     rank.  `payload` is a fixed-length sequence of floats (ids, time, point ...).  A rank with

@@ -571,6 +571,59 @@ def test_device_mesh_conversions_equal_the_host_builders_at_full_size(ctx):
     assert np.array_equal(pdg.pcdata.points, ref.convert("PointCloud", 0.02).getPointCloud().points)
 
 
+def test_result_boards_receive_every_ranks_records(ctx, O):
+    """The peer-store exchange (SIO_PUSH_BOARDS) with two 'ranks' emulated as two contexts of one process on one GPU:
+    after both streams have drained, BOTH boards hold both ranks' (dmin, argmin, n_under) records -- and these equal the
+    oracle's.  (Across processes the peers' boards are mapped through CUDA IPC: bench.py --gpus N verifies that path
+    against an NCCL all-gather of the same records.)"""
+    import torch
+    from semiinfiniteoptimization_b200 import _abi
+    ctxs = [ctx, _abi.Context(0)]
+    vg = util.fixture_geometry("cube").convert("VolumeGrid", 0.05).getVolumeGrid()
+    G = O.Grid(vg.values, vg.bmin, vg.bmax)
+    cloud = (util.fixture_geometry("m797").convert("PointCloud", 0.02).getPointCloud().points + [0.3, 0, 0]).astype(np.float32)
+    B = 12
+    slot = ((20 * B + 63) // 64) * 64
+    made = [c.board_create(slot * 2) for c in ctxs]
+    ptrs = [m[0] for m in made]
+    assert all(len(m[1]) == 64 for m in made)
+    outs, want = [], []
+    dev = torch.device("cuda:0")
+    for r, c in enumerate(ctxs):
+        c.set_boards(r, ptrs, slot)
+        g, cl = c.grid_create(vg.values, vg.bmin, vg.bmax), c.cloud_create(cloud)
+        T = util.invert12(util.random_poses(30 + r, B, rot=0.3, trans=0.3, center=(0.2, 0.2, 0.2)))
+        bound = np.full(B, 0.01)
+        dT, db = torch.from_numpy(T).to(dev), torch.from_numpy(bound).to(dev)
+        dd = torch.empty(B, dtype=torch.float64, device=dev)
+        da = torch.empty(B, dtype=torch.int64, device=dev)
+        dn = torch.zeros(B, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        c.min_distance_dev([g], cl, dT.data_ptr(), db.data_ptr(), B, _abi.SIO_F32, dd.data_ptr(), da.data_ptr(), d_n_under_ptr=dn.data_ptr())
+        c.sync()
+        assert not c.board_read(2, slot, B)[0].any()                       # no SIO_PUSH_BOARDS: the boards stay untouched
+        c.min_distance_dev([g], cl, dT.data_ptr(), db.data_ptr(), B, _abi.SIO_F32 | _abi.SIO_PUSH_BOARDS, dd.data_ptr(), da.data_ptr(),
+                           d_n_under_ptr=dn.data_ptr())
+        outs.append((dd, da, dn))
+        d0, a0 = O.min_distance(G, cloud, T, bound=bound)
+        want.append((d0, a0, O.under_counts(G, cloud, T, bound)[0]))
+    for c in ctxs:
+        c.sync()
+    for c in ctxs:
+        d, a, n = c.board_read(2, slot, B)
+        for r in range(2):
+            assert np.array_equal(a[r], want[r][1]) and np.abs(d[r] - want[r][0]).max() <= 1e-12 and np.array_equal(n[r], want[r][2])
+    with pytest.raises(_abi.SioError):                                     # more results than a slot holds
+        ctxs[0].set_boards(0, ptrs, 64)
+        g2, c2 = ctxs[0].grid_create(vg.values, vg.bmin, vg.bmax), ctxs[0].cloud_create(cloud)
+        ctxs[0].min_distance_dev([g2], c2, dT.data_ptr(), db.data_ptr(), B, _abi.SIO_F32 | _abi.SIO_PUSH_BOARDS, dd.data_ptr(), da.data_ptr())
+    for r, c in enumerate(ctxs):
+        c.set_boards(0, [], 0)
+    for r, c in enumerate(ctxs):
+        c.board_close(ptrs[r], True)
+    ctxs[1].close()
+
+
 def test_error_paths(ctx, O):
     from semiinfiniteoptimization_b200 import _abi
     vg = util.random_grid(95)
