@@ -150,6 +150,19 @@ bool grid_ok(sio_ctx* c, sio_handle h) { return h >= 0 && (size_t)h < c->grids.s
 bool cloud_ok(sio_ctx* c, sio_handle h) { return h >= 0 && (size_t)h < c->clouds.size() && c->clouds[h].live; }
 bool robot_ok(sio_ctx* c, sio_handle h) { return h >= 0 && (size_t)h < c->robots.size() && c->robots[h].live; }
 
+// Wait for a stream the way a latency-bound caller wants it: the single-problem paths (PenetrationDepthGeometry.distance,
+// value / df_dx batches of a few points) wait for ~10-100 us of device work per call, and a blocking
+// cudaStreamSynchronize costs 10-20 us of wake-up latency on top.  Poll for up to ~0.5 ms, then block.
+inline cudaError_t wait_stream(cudaStream_t st) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        const cudaError_t e = cudaStreamQuery(st);
+        if (e != cudaErrorNotReady) return e;
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(500)) break;
+    }
+    return cudaStreamSynchronize(st);
+}
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
@@ -570,7 +583,7 @@ int sio_query(sio_ctx* c, sio_handle grid, const double T[12], const double* pts
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(d, c->s_out0.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (grad) CU(cudaMemcpyAsync(grad, c->s_out1.p, (size_t)P * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(wait_stream(st));
     return SIO_OK;
 }
 
@@ -793,10 +806,10 @@ int sio_under_fetch(sio_ctx* c, int64_t capacity, int64_t* b_out, int64_t* idx_o
 // (the float32 pass is deterministic, so the second run offers the same candidates), < 0 = error.
 static int under_settle(sio_ctx* c, bool want_under) {
     cudaStream_t st = c->stream;
-    if (!want_under) { CU(cudaStreamSynchronize(st)); return 0; }
+    if (!want_under) { CU(wait_stream(st)); return 0; }
     CU(c->h_cnt.ensure(sizeof(unsigned long long)));
     CU(cudaMemcpyAsync(c->h_cnt.p, c->s_cnt.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(wait_stream(st));
     const unsigned long long n = *c->h_cnt.as<unsigned long long>();
     if (n <= c->cand_cap) return 0;
     if (n > kMaxCand)
@@ -894,7 +907,7 @@ int sio_pose_rows(sio_ctx* c, sio_handle grid, const double* T_pose, const int64
     c->launches += 1;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_b.p, dout, out_bytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(wait_stream(st));
     std::memcpy(d, c->h_b.as<char>() + oD, (size_t)total * sizeof(double));
     if (rows) std::memcpy(rows, c->h_b.as<char>() + oR, (size_t)total * 6 * sizeof(double));
     return SIO_OK;
@@ -1449,7 +1462,7 @@ int sio_fk(sio_ctx* c, sio_handle robot, const double* q, int64_t B, double* T_o
     c->launches += 1;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(T_out, c->s_tlinks.p, (size_t)B * r.n * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(wait_stream(st));
     return SIO_OK;
 }
 
@@ -1504,7 +1517,7 @@ int sio_chain_rows(sio_ctx* c, sio_handle robot, const sio_handle* link_grids, c
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(d, c->s_out0.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (rows) CU(cudaMemcpyAsync(rows, c->s_out1.p, (size_t)P * r.n * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(wait_stream(st));
     return SIO_OK;
 }
 

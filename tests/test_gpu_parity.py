@@ -601,7 +601,7 @@ def test_result_boards_receive_every_ranks_records(ctx, O):
         torch.cuda.synchronize()
         c.min_distance_dev([g], cl, dT.data_ptr(), db.data_ptr(), B, _abi.SIO_F32, dd.data_ptr(), da.data_ptr(), d_n_under_ptr=dn.data_ptr())
         c.sync()
-        assert not c.board_read(2, slot, B)[0].any()                       # no SIO_PUSH_BOARDS: the boards stay untouched
+        assert not c.board_read(2, slot, B)[0][r].any()                    # no SIO_PUSH_BOARDS: this rank's slot stays untouched
         c.min_distance_dev([g], cl, dT.data_ptr(), db.data_ptr(), B, _abi.SIO_F32 | _abi.SIO_PUSH_BOARDS, dd.data_ptr(), da.data_ptr(),
                            d_n_under_ptr=dn.data_ptr())
         outs.append((dd, da, dn))
