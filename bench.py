@@ -452,7 +452,13 @@ def cpu_single_problem_legs():
     from oracle import oracle as O, ref_geometryopt as R
     O.lib().orc_set_threads(1)
     try:
+        R.RefPDG.PRUNED = True                          # "pruning on": the stronger CPU arm for single problems
+        try:
+            pruned = single_problem_legs(R, REF_NAMES, device=False, n_c1=4, n_c3=4, c4_iters=2, reps=1)
+        finally:
+            R.RefPDG.PRUNED = False
         out = single_problem_legs(R, REF_NAMES, device=False, n_c1=4, n_c3=4, c4_iters=2, reps=1)
+        out["pruned"] = pruned
         # C4 at the benchmark's density on the CPU: brute dense sweep, every host thread (the reference algorithm above
         # bisects down to k/128 only)
         O.lib().orc_set_threads(0)

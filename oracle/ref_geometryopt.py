@@ -50,6 +50,8 @@ def _mul12(A12, B12):
 class RefPDG:
     """gopt:38-168 on the CPU oracle.  Shares nothing with the device."""
 
+    PRUNED = False        # True: cloud-vs-grid minima by the hierarchy-pruned search (bench.py's "pruning on" CPU legs)
+
     def __init__(self, geom, gridres=0, pcres=0):
         if isinstance(geom, RefPDG):
             self.geom, self.grid, self.pc, self.pcdata = geom.geom, geom.grid, geom.pc, geom.pcdata
@@ -87,7 +89,19 @@ class RefPDG:
             return d, [pt[k] - g[0, k] * d for k in range(3)], pt
         assert isinstance(other, RefPDG) and other.G is not None
         T_rel = _mul12(_inv12(other.T12()), self.T12())
-        dmin, arg = O.min_distance(other.G, self.cloud32, T_rel, bound=None if bound is None else [bound])
+        if RefPDG.PRUNED:
+            # the hierarchy-pruned CPU arm (what Klampt's distance_ext does in spirit): same answer wherever it is below the
+            # bound, which is all this method reads
+            tree = getattr(self, "_tree", None)
+            if tree is None:
+                tree = self._tree = O.CloudTree(self.cloud32)
+            lip = getattr(other, "_lip", None)
+            if lip is None:
+                lip = other._lip = O.grid_lipschitz(other.G)
+            dmin, arg, _ = O.min_distance_pruned(other.G, tree, T_rel, bound=None if bound is None else [bound],
+                                                 use_bound=bound is not None, lip=lip)
+        else:
+            dmin, arg = O.min_distance(other.G, self.cloud32, T_rel, bound=None if bound is None else [bound])
         d = float(dmin[0])
         if arg[0] < 0 or (bound is not None and d >= bound):
             return d, [0.0] * 3, [0.0] * 3

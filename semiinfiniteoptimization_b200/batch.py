@@ -651,4 +651,5 @@ def optimizeCollFreeBatchDevice(obj, env, Tinits, Tdess=None, settings=None, con
     res.outer_iterations = out["stats"]["outer_iterations"]
     res.point_queries = out["stats"]["point_queries"]
     res.slot_overflows = out["stats"]["slot_overflows"]
+    res.qp_failures = out["stats"]["qp_failures"]          # problems stopped with status 2 ('qp failed')
     return res

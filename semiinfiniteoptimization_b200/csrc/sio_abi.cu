@@ -88,6 +88,7 @@ struct CloudH {
     float4* d_rep = nullptr;       // per 128-point sub-tile: representative cloud point (xyz) + bounding radius (w)
     int32_t* d_perm = nullptr;     // internal -> caller index
     std::vector<int32_t> perm;
+    double max_abs = 0.0;          // largest |coordinate|: the float32 transform error grows with it
 };
 struct RobotH {
     bool live = false;
@@ -230,6 +231,7 @@ int sio_ctx_destroy(sio_ctx* c) {
     if (!c) return SIO_OK;
     DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < sio_ctx::kLsBack; ++k) if (c->ls_stream[k]) cudaStreamSynchronize(c->ls_stream[k]);
     for (auto& g : c->grids) if (g.live) { cudaFree(g.d_v); cudaFree(g.d_brick); cudaFree(g.d_meta); }
     for (auto& p : c->clouds) if (p.live) { cudaFree(p.d_pts); cudaFree(p.d_rep); cudaFree(p.d_perm); }
     for (auto& r : c->robots) if (r.live) { cudaFree(r.d_parent); cudaFree(r.d_jtype); cudaFree(r.d_tparent); cudaFree(r.d_axis); }
@@ -503,6 +505,7 @@ int sio_cloud_create(sio_ctx* c, const float* xyz, int64_t n, sio_handle* out) {
         int32_t s = order[i];
         pts[i] = make_float4(xyz[3 * s], xyz[3 * s + 1], xyz[3 * s + 2], 0.f);
         p.perm[i] = s;
+        for (int a = 0; a < 3; ++a) p.max_abs = std::max(p.max_abs, (double)std::fabs(xyz[3 * s + a]));
     }
     // pad to a whole tile with copies of the last point: the bulk kernel needs no bounds test, a duplicate
     // cannot lower a minimum, and the fp64 stages only ever look at indices < n
@@ -567,23 +570,32 @@ int sio_query(sio_ctx* c, sio_handle grid, const double T[12], const double* pts
     if (P == 0) return SIO_OK;
     DeviceGuard guard(c->device);
     cudaStream_t st = c->stream;
-    CU(c->s_in0.ensure(12 * sizeof(double)));
-    CU(c->s_in1.ensure((size_t)P * 3 * sizeof(double)));
-    CU(c->s_out0.ensure((size_t)P * sizeof(double)));
-    CU(c->s_out1.ensure((size_t)P * 3 * sizeof(double)));
-    CU(cudaMemcpyAsync(c->s_in0.p, T, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->s_in1.p, pts, (size_t)P * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    // one pinned block each way: [T | pts] -> device, [d | grad] <- device (a point query is latency, not bandwidth)
+    const size_t in_bytes = (12 + (size_t)P * 3) * sizeof(double);
+    const size_t out_bytes = ((size_t)P + (grad ? (size_t)P * 3 : 0)) * sizeof(double);
+    CU(c->h_a.ensure(in_bytes));
+    CU(c->h_b.ensure(out_bytes));
+    CU(c->s_in0.ensure(in_bytes));
+    CU(c->s_out0.ensure(out_bytes));
+    double* hin = c->h_a.as<double>();
+    std::memcpy(hin, T, 12 * sizeof(double));
+    std::memcpy(hin + 12, pts, (size_t)P * 3 * sizeof(double));
+    CU(cudaMemcpyAsync(c->s_in0.p, hin, in_bytes, cudaMemcpyHostToDevice, st));
+    const double* dT = c->s_in0.as<double>();
+    const double* dpts = dT + 12;
+    double* dd = c->s_out0.as<double>();
+    double* dg = grad ? dd + P : nullptr;
     const int normalize = (flags & SIO_NO_NORMALIZE) ? 0 : 1;
-    double* dg = grad ? c->s_out1.as<double>() : nullptr;
     if (flags & SIO_F64)
-        launch_query_f64(c->grids[grid].d_meta, c->s_in0.as<double>(), c->s_in1.as<double>(), P, normalize, c->s_out0.as<double>(), dg, st);
+        launch_query_f64(c->grids[grid].d_meta, dT, dpts, P, normalize, dd, dg, st);
     else
-        launch_query_f32(c->grids[grid].d_meta, c->s_in0.as<double>(), c->s_in1.as<double>(), P, normalize, c->s_out0.as<double>(), dg, st);
+        launch_query_f32(c->grids[grid].d_meta, dT, dpts, P, normalize, dd, dg, st);
     c->launches += 1;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(d, c->s_out0.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (grad) CU(cudaMemcpyAsync(grad, c->s_out1.p, (size_t)P * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_b.p, dd, out_bytes, cudaMemcpyDeviceToHost, st));
     CU(wait_stream(st));
+    std::memcpy(d, c->h_b.p, (size_t)P * sizeof(double));
+    if (grad) std::memcpy(grad, c->h_b.as<double>() + P, (size_t)P * 3 * sizeof(double));
     return SIO_OK;
 }
 
@@ -647,6 +659,10 @@ int sio_min_distance_dev(sio_ctx* c, const sio_handle* grids, int32_t n_grids, c
     if (rc) return rc;
     cudaStream_t st = c->stream;
     const CloudH& p = c->clouds[cloud];
+    // the automatic near-tie window also has to cover the float32 error of the transform itself, ~2e-7 x the magnitude of
+    // the cloud-local coordinates (cancellation in M p + t): a cloud stored hundreds of metres from its origin widens it.
+    // (A T_rel whose translation is far larger than both geometries is the caller's to cover with sio_ctx_set_tau.)
+    if (!(c->tau > 0)) tau = std::max(tau, 1e-5 * p.max_abs);
     const bool f64 = (flags & SIO_F64) != 0;
     const int32_t ntiles = (int32_t)((p.n + kTile - 1) / kTile);
     const int64_t nsub = (int64_t)ntiles * (kThreads / 32);
@@ -960,6 +976,12 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     if (B == 0) return SIO_OK;
     DeviceGuard guard(c->device);
     cudaStream_t st = c->stream;
+    // every way out of this call -- errors included -- first waits for the background QP launches: they read and write
+    // the context-owned arena that the next call re-carves
+    struct BackgroundDrain {
+        sio_ctx* c;
+        ~BackgroundDrain() { for (int k = 0; k < sio_ctx::kLsBack; ++k) if (c->ls_stream[k]) cudaStreamSynchronize(c->ls_stream[k]); }
+    } drain{c};
     const auto entry0 = std::chrono::steady_clock::now();
     const int cap = cfg->cap;
     const int64_t N = c->clouds[cloud].n;
@@ -1077,6 +1099,8 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
             if (!c->ls_evB[k]) CU(cudaEventCreateWithFlags(&c->ls_evB[k], cudaEventDisableTiming));
         }
     }
+    // SIO_LS_INJECT_QPFAIL=<problem>: fault injection for the tests of the "QP without a solution" path (status 2)
+    const int64_t inject_fail = getenv("SIO_LS_INJECT_QPFAIL") ? atoll(getenv("SIO_LS_INJECT_QPFAIL")) : -1;
     const int64_t max_rounds = (int64_t)cfg->max_iters * 64 + 64;    // a problem sits a few rounds out per deferred QP
     int64_t round = 0, rounds_with_qp = 0;
     for (;; ++round) {
@@ -1133,6 +1157,11 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
                 return fail(SIO_ERR_INVALID, "sio_lockstep_pose_solve: QP launch failed");
             CU(cudaEventRecord(c->ls_evB[slot], c->ls_stream[k]));
             c->launches += 1;
+        }
+        if (inject_fail >= 0 && inject_fail < B && round == 0) {   // test aid: pretend problem p's QP had no solution
+            const int32_t code = 3;
+            CU(cudaMemcpyAsync(S.qstatus + inject_fail, &code, sizeof(code), cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
         }
         ++rounds_with_qp;
         if (prof) {                                        // per-launch ADMM iteration statistics

@@ -166,6 +166,31 @@ def test_deferred_qp_stragglers_do_not_change_the_answers(ctx, monkeypatch):
             assert np.array_equal(P0[p, :n0[p]], P1[p, :n0[p]])
 
 
+def test_a_qp_without_a_solution_stops_its_problem_only(ctx, monkeypatch):
+    """when the device QP reports that it produced no step (its slack re-solve infeasible too -- the
+    reference fails there, sip.py:358-378), the lock-step solver must stop THAT problem with its own status instead of
+    stepping along stale memory, count it, and leave every other problem's answer untouched.  The condition cannot be
+    produced by valid inputs (a trust-region box with slack rows is always feasible), so it is injected."""
+    from semiinfiniteoptimization_b200 import batch, geometryopt as G, sip, workloads as W
+    from semiinfiniteoptimization_b200._host.geometry import Geometry3D, PointCloud
+    cube = G.PenetrationDepthGeometry(W.c5_cube(), 0.05, None, context=ctx)
+    scene = G.PenetrationDepthGeometry(Geometry3D(PointCloud(W.c5_scene_cloud())), None, 0.02, context=ctx)
+    poses = W.c5_poses(256, seed=3)
+    st = sip.SemiInfiniteOptimizationSettings()
+    st.max_iters = 10
+    ref = batch.optimizeCollFreeBatchDevice(cube, scene, poses, settings=st)
+    victim = int(np.nonzero(np.asarray(ref.num_iterations) >= 3)[0][0])
+    monkeypatch.setenv("SIO_LS_INJECT_QPFAIL", str(victim))
+    got = batch.optimizeCollFreeBatchDevice(cube, scene, poses, settings=st)
+    monkeypatch.delenv("SIO_LS_INJECT_QPFAIL")
+    assert got.status[victim] == 'qp failed' and got.status_codes[victim] == 2 and got.num_iterations[victim] == 0
+    Tinit = np.array([np.column_stack([np.asarray(T[0]).reshape(3, 3).T, T[1]]).reshape(-1) for T in poses])
+    assert np.array_equal(got.T[victim], Tinit[victim])                    # it stayed where it was
+    others = np.arange(len(poses)) != victim
+    assert np.array_equal(got.T[others], ref.T[others]) and np.array_equal(np.asarray(got.status_codes)[others], np.asarray(ref.status_codes)[others])
+    assert 'qp failed' not in ref.status and ref.qp_failures == 0 and got.qp_failures == 1
+
+
 def test_drivers_agree_on_the_c5_workload(ctx):
     """BASELINE.json configs[4] inputs (cube vs the synthetic 262,144-point scene; two thirds of the poses start in deep
     collision, so the QP's slack re-solve is the common case): 2,048 problems through the array driver with the HOST QP and

@@ -624,6 +624,31 @@ def test_result_boards_receive_every_ranks_records(ctx, O):
     ctxs[1].close()
 
 
+@pytest.mark.parametrize("flags", [F32, F32 | PRUNE])
+def test_cloud_stored_far_from_its_origin_keeps_exact_results(ctx, O, flags):
+    """the float32 error of the bulk pass grows with the magnitude of the cloud-local coordinates
+    (cancellation in M p + t); a cloud stored 400 m from its origin under a compensating transform must still give
+    the float64 oracle's minima, arg-minima and under-bound sets (the automatic near-tie window scales with it)."""
+    vg = util.fixture_geometry("cube").convert("VolumeGrid", 0.05).getVolumeGrid()
+    g, G = _mk(ctx, O, vg)
+    env = util.fixture_geometry("m797").convert("PointCloud", 0.02).getPointCloud().points
+    shift = np.array([400.0, -250.0, 120.0])
+    cloud = (env + np.array([0.3, 0.0, 0.0]) + shift).astype(np.float32)        # float32 spacing at 400 m: 3e-5 m
+    c = ctx.cloud_create(cloud)
+    T = util.invert12(util.random_poses(10, 16, rot=0.3, trans=0.3, center=(0.2, 0.2, 0.2))).reshape(-1, 3, 4)
+    T[:, :, 3] -= T[:, :, :3] @ shift                                            # T'(p + shift) = T p
+    T = T.reshape(-1, 12)
+    bound = np.full(len(T), 0.0)
+    dmin, arg, nu = ctx.min_distance(g, c, T, bound=bound, flags=flags)
+    ub, ui, ud = ctx.under_fetch(1 << 22)
+    d0, a0 = O.min_distance(G, cloud, T, bound=bound)
+    n0, ob, oi, od = O.under(G, cloud, T, bound)
+    assert np.array_equal(arg, a0) and np.abs(dmin - d0).max() <= 1e-9
+    assert n0 == len(ub) and np.array_equal(ub, ob) and np.array_equal(ui, oi)
+    ctx.cloud_destroy(c)
+    ctx.grid_destroy(g)
+
+
 def test_error_paths(ctx, O):
     from semiinfiniteoptimization_b200 import _abi
     vg = util.random_grid(95)
