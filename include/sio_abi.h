@@ -72,6 +72,9 @@ int   sio_ctx_set_scratch_limit(sio_ctx* ctx, int64_t bytes);
  * the sweep again, so their n_under and under-bound lists are always exact (or the call fails with SIO_ERR_NOMEM /
  * SIO_ERR_OVERFLOW above 2^31-1 records).  Callers of sio_min_distance_dev size it themselves. */
 int   sio_ctx_set_under_capacity(sio_ctx* ctx, int64_t entries);
+/* host-pointer K2 calls that repeat the previous call's signature are replayed as one CUDA graph (default on; results
+ * do not depend on it; sio_ctx_last_bulk_ms is not available for a replayed call) */
+int   sio_ctx_set_host_graphs(sio_ctx* ctx, int on);
 int   sio_ctx_num_sms(sio_ctx* ctx);
 int64_t sio_ctx_kernel_launches(sio_ctx* ctx);      /* kernels launched by this context so far */
 

@@ -25,7 +25,7 @@ SIO_PUSH_BOARDS = 0x20
 ABI_SYMBOLS = (
     "sio_abi_version", "sio_last_error",
     "sio_ctx_create", "sio_ctx_destroy", "sio_ctx_sync", "sio_ctx_stream", "sio_ctx_set_tau", "sio_ctx_set_scratch_limit",
-    "sio_ctx_set_under_capacity", "sio_ctx_num_sms",
+    "sio_ctx_set_under_capacity", "sio_ctx_set_host_graphs", "sio_ctx_num_sms",
     "sio_board_create", "sio_board_open", "sio_board_close", "sio_ctx_set_boards", "sio_board_read",
     "sio_ctx_kernel_launches",
     "sio_grid_create", "sio_grid_destroy", "sio_cloud_create", "sio_cloud_order", "sio_cloud_destroy", "sio_cloud_size",
@@ -65,6 +65,7 @@ def load_library():
     L.sio_ctx_set_tau.argtypes = [P, D]
     L.sio_ctx_set_scratch_limit.argtypes = [P, I64]
     L.sio_ctx_set_under_capacity.argtypes = [P, I64]
+    L.sio_ctx_set_host_graphs.argtypes = [P, C.c_int]
     L.sio_board_create.argtypes = [P, I64, C.POINTER(P), P]
     L.sio_board_open.argtypes = [P, P, C.POINTER(P)]
     L.sio_board_close.argtypes = [P, P, C.c_int]
@@ -169,6 +170,10 @@ class Context:
     def set_under_capacity(self, entries):
         """Under-bound candidate records a K2 call holds (the host entry points grow it on their own)."""
         self._ck(self.L.sio_ctx_set_under_capacity(self.h, int(entries)))
+
+    def set_host_graphs(self, on):
+        """Replay repeated host-pointer K2 calls as one CUDA graph (default on)."""
+        self._ck(self.L.sio_ctx_set_host_graphs(self.h, 1 if on else 0))
 
     # -- result boards (multi-GPU exchange by peer stores) --
     def board_create(self, nbytes):

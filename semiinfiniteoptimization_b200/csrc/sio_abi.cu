@@ -2,6 +2,7 @@
 // scratch arenas and the launch sequences of the oracle calls.  No CPU implementation of any query
 // exists here: without a CUDA device sio_ctx_create fails with SIO_ERR_NODEVICE.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -43,19 +44,25 @@ int fail(int code, const char* fmt, ...) {
 // grow-only device / pinned-host buffers; growth is geometric (a lock-step SIP run asks for a little more
 // every iteration, and cudaFree / cudaMalloc / cudaMallocHost each cost a device synchronisation and milliseconds)
 inline size_t grown(size_t bytes, size_t cap) { return std::max(std::max(bytes, (size_t)256), cap + cap / 2); }
+// bumped by every re-allocation of a scratch buffer: a captured CUDA graph holds the buffers' addresses AND the
+// driver's registration of the pinned ones, so a graph captured before any re-allocation must never be replayed
+// (freeing a pinned buffer and getting the same address back is not "the same buffer" to the driver: replaying a
+// graph with such a copy node crashed inside cudaGraphLaunch)
+std::atomic<uint64_t> g_realloc_gen{0};
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         size_t want = grown(bytes, cap);
+        g_realloc_gen.fetch_add(1);
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) { g_realloc_gen.fetch_add(1); cudaFree(p); } p = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 struct HostBuf {
@@ -64,13 +71,14 @@ struct HostBuf {
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         size_t want = grown(bytes, cap);
+        g_realloc_gen.fetch_add(1);
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
     }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    void release() { if (p) { g_realloc_gen.fetch_add(1); cudaFreeHost(p); } p = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -133,6 +141,14 @@ struct sio_ctx {
     GridDev single_grid_host{};       // host copy handed to the single-grid bulk kernel by value
     std::vector<sio_handle> staged_grids;   // handles whose table currently sits in s_gridtab (grids are immutable)
     double staged_tau = 0.0;
+    // host-pointer K2 calls repeated with the same signature are replayed as ONE CUDA graph (H2D, memsets, kernels, D2H)
+    struct HostGraph {
+        std::vector<int64_t> key;        // everything the captured launch sequence depends on (see host_graph_key)
+        cudaGraphExec_t exec = nullptr;
+        int n_icnt = 0; int64_t prune_total = 0; int64_t launches = 0; bool f64 = false;
+    } hgraph;
+    std::vector<int64_t> last_host_key;  // signature of the previous host-pointer K2 call (a repeat is what gets captured)
+    bool host_graphs = true;
     // result boards (multi-GPU exchange by peer stores): this rank, the boards of all ranks as device pointers
     int board_rank = -1, board_n = 0;
     int64_t board_slot = 0;
@@ -223,6 +239,7 @@ int sio_ctx_create(int device, sio_ctx** out) {
     if (e != cudaSuccess) { delete c; return fail(SIO_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     cudaEventCreate(&c->ev_bulk0);
     cudaEventCreate(&c->ev_bulk1);
+    if (getenv("SIO_HOST_GRAPHS")) c->host_graphs = atoi(getenv("SIO_HOST_GRAPHS")) != 0;
     *out = c;
     return SIO_OK;
 }
@@ -236,6 +253,7 @@ int sio_ctx_destroy(sio_ctx* c) {
     for (auto& p : c->clouds) if (p.live) { cudaFree(p.d_pts); cudaFree(p.d_rep); cudaFree(p.d_perm); }
     for (auto& r : c->robots) if (r.live) { cudaFree(r.d_parent); cudaFree(r.d_jtype); cudaFree(r.d_tparent); cudaFree(r.d_axis); }
     c->s_qp.release();
+    if (c->hgraph.exec) cudaGraphExecDestroy(c->hgraph.exec);
     c->s_boards.release();
     c->s_lb.release(); c->s_ub.release(); c->s_items.release(); c->s_icnt.release(); c->h_icnt.release(); c->s_ls.release();
     for (int k = 0; k < sio_ctx::kLsBack; ++k) { c->s_qpb[k].release(); if (c->ls_stream[k]) cudaStreamDestroy(c->ls_stream[k]); }
@@ -270,6 +288,12 @@ int sio_ctx_set_under_capacity(sio_ctx* c, int64_t entries) {
     return SIO_OK;
 }
 int sio_ctx_num_sms(sio_ctx* c) { return c ? c->num_sms : 0; }
+int sio_ctx_set_host_graphs(sio_ctx* c, int on) {
+    if (!c) return fail(SIO_ERR_INVALID, "null context");
+    c->host_graphs = on != 0;
+    if (!on && c->hgraph.exec) { cudaGraphExecDestroy(c->hgraph.exec); c->hgraph.exec = nullptr; c->hgraph.key.clear(); }
+    return SIO_OK;
+}
 
 // ---- result boards ---------------------------------------------------------------------------------------------------
 int sio_board_create(sio_ctx* c, int64_t bytes, void** dptr, unsigned char ipc_handle[64]) {
@@ -427,6 +451,7 @@ int sio_grid_destroy(sio_ctx* c, sio_handle h) {
     if (!c || !grid_ok(c, h)) return fail(SIO_ERR_INVALID, "sio_grid_destroy: bad handle %d", h);
     DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
+    g_realloc_gen.fetch_add(1);
     cudaFree(c->grids[h].d_v); cudaFree(c->grids[h].d_brick); cudaFree(c->grids[h].d_meta);
     c->grids[h] = GridH();
     c->staged_grids.clear();
@@ -549,6 +574,7 @@ int sio_cloud_destroy(sio_ctx* c, sio_handle h) {
     if (!c || !cloud_ok(c, h)) return fail(SIO_ERR_INVALID, "sio_cloud_destroy: bad handle %d", h);
     DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
+    g_realloc_gen.fetch_add(1);
     cudaFree(c->clouds[h].d_pts); cudaFree(c->clouds[h].d_rep); cudaFree(c->clouds[h].d_perm);
     c->clouds[h] = CloudH();
     return SIO_OK;
@@ -837,6 +863,32 @@ static int under_settle(sio_ctx* c, bool want_under) {
 // host-pointer K2: inputs are packed into one pinned block and sent with ONE H2D copy; outputs come back
 // with ONE D2H copy:   in  = [T_rel B*12 f64 | bound B f64 | grid_of_b B i32]
 //                      out = [dmin B f64 | argmin B i64 | n_under B i32]
+// everything the launch sequence of a host-pointer K2 call depends on: arguments' shapes, settings, and the addresses
+// of every buffer it touches (they are grow-only, so equal addresses = nothing was re-allocated)
+static std::vector<int64_t> host_graph_key(sio_ctx* c, const sio_handle* grids, int32_t n_grids, bool has_gob, sio_handle cloud,
+                                           bool has_bound, int64_t B, int flags, bool want_n) {
+    std::vector<int64_t> k;
+    k.reserve(32 + n_grids);
+    k.push_back(n_grids);
+    for (int i = 0; i < n_grids; ++i) k.push_back(grids[i]);
+    const int64_t scalars[] = {cloud, B, flags, has_gob, has_bound, want_n, (int64_t)c->cand_cap, c->scratch_limit, c->board_n, c->board_rank};
+    k.insert(k.end(), std::begin(scalars), std::end(scalars));
+    int64_t taubits;
+    std::memcpy(&taubits, &c->tau, 8);
+    k.push_back(taubits);
+    k.push_back((int64_t)g_realloc_gen.load());
+    const void* bufs[] = {c->h_a.p, c->h_b.p, c->h_cnt.p, c->s_in0.p, c->s_out0.p, c->s_cand.p, c->s_cnt.p, c->s_keys.p, c->s_xf.p, c->s_lb.p,
+                          c->s_ub.p, c->s_items.p, c->s_icnt.p, c->s_gridtab.p, c->s_boards.p};
+    for (const void* p : bufs) k.push_back((int64_t)(intptr_t)p);
+    return k;
+}
+
+// host-pointer K2: inputs are packed into one pinned block and sent with ONE H2D copy; outputs come back
+// with ONE D2H copy:   in  = [T_rel B*12 f64 | bound B f64 | grid_of_b B i32]
+//                      out = [dmin B f64 | argmin B i64 | n_under B i32]
+// A call that repeats the previous call's signature is captured into a CUDA graph (copies, memsets, kernels) and every
+// further repeat replays it with one launch: the SIP loop issues the same call thousands of times, and at 64 poses the
+// seven driver calls of the plain sequence cost as much as a fifth of the sweep itself.
 static int min_distance_host(sio_ctx* c, const sio_handle* grids, int32_t n_grids, const int32_t* grid_of_b, sio_handle cloud,
                              const double* T_rel, const double* bound, int64_t B, int flags, double* dmin, int64_t* argmin,
                              int32_t* n_under) {
@@ -845,6 +897,7 @@ static int min_distance_host(sio_ctx* c, const sio_handle* grids, int32_t n_grid
     const size_t oD = 0, oA = (size_t)B * 8, oN = oA + (size_t)B * 8, out_bytes = oN + (size_t)B * 4;
     CU(c->h_a.ensure(in_bytes));
     CU(c->h_b.ensure(out_bytes));
+    CU(c->h_cnt.ensure(sizeof(unsigned long long)));
     CU(c->s_in0.ensure(in_bytes));
     CU(c->s_out0.ensure(out_bytes));
     char* hin = c->h_a.as<char>();
@@ -855,20 +908,64 @@ static int min_distance_host(sio_ctx* c, const sio_handle* grids, int32_t n_grid
             if (grid_of_b[b] < 0 || grid_of_b[b] >= n_grids) return fail(SIO_ERR_INVALID, "grid_of_b[%lld]=%d out of range", (long long)b, grid_of_b[b]);
         std::memcpy(hin + oG, grid_of_b, (size_t)B * 4);
     }
-    CU(cudaMemcpyAsync(c->s_in0.p, hin, in_bytes, cudaMemcpyHostToDevice, st));
+    const bool want_under = bound && n_under;
     char* din = c->s_in0.as<char>();
     char* dout = c->s_out0.as<char>();
-    for (;;) {
+    auto enqueue = [&]() -> int {                           // the call's whole device-side sequence, on the context's stream
+        CU(cudaMemcpyAsync(c->s_in0.p, hin, in_bytes, cudaMemcpyHostToDevice, st));
         int rc = sio_min_distance_dev(c, grids, n_grids, grid_of_b ? reinterpret_cast<const int32_t*>(din + oG) : nullptr, cloud,
                                       reinterpret_cast<const double*>(din + oT), bound ? reinterpret_cast<const double*>(din + oB) : nullptr,
                                       B, flags, reinterpret_cast<double*>(dout + oD), reinterpret_cast<int64_t*>(dout + oA),
                                       n_under ? reinterpret_cast<int32_t*>(dout + oN) : nullptr);
         if (rc) return rc;
         CU(cudaMemcpyAsync(c->h_b.p, dout, out_bytes, cudaMemcpyDeviceToHost, st));
-        rc = under_settle(c, bound && n_under);
-        if (rc < 0) return rc;
-        if (rc == 0) break;
+        if (want_under) CU(cudaMemcpyAsync(c->h_cnt.p, c->s_cnt.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        return SIO_OK;
+    };
+    auto overflowed = [&]() { return want_under && *c->h_cnt.as<unsigned long long>() > c->cand_cap; };
+    bool done = false;
+    const std::vector<int64_t> key = c->host_graphs ? host_graph_key(c, grids, n_grids, grid_of_b != nullptr, cloud, bound != nullptr, B, flags, n_under != nullptr)
+                                                    : std::vector<int64_t>();
+    if (c->host_graphs && c->hgraph.exec && c->hgraph.key == key) {            // replay
+        CU(cudaGraphLaunch(c->hgraph.exec, st));
+        CU(wait_stream(st));
+        c->under.clear();
+        c->under_pending = want_under; c->under_valid = !want_under; c->under_final = c->hgraph.f64;
+        c->bulk_timed = false; c->n_icnt = c->hgraph.n_icnt; c->prune_total = c->hgraph.prune_total;
+        c->launches += c->hgraph.launches;
+        done = !overflowed();                               // an overflow falls through to the plain path, which re-sizes
+    } else if (c->host_graphs && !key.empty() && key == c->last_host_key) {    // second identical call in a row: capture it
+        if (c->hgraph.exec) { cudaGraphExecDestroy(c->hgraph.exec); c->hgraph.exec = nullptr; c->hgraph.key.clear(); }
+        const int64_t launches0 = c->launches;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc = enqueue();
+            const cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (rc == SIO_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&c->hgraph.exec, graph, 0) == cudaSuccess) {
+                c->hgraph.key = key;
+                c->hgraph.n_icnt = c->n_icnt; c->hgraph.prune_total = c->prune_total; c->hgraph.f64 = (flags & SIO_F64) != 0;
+                c->hgraph.launches = c->launches - launches0;
+                if (graph) cudaGraphDestroy(graph);
+                CU(cudaGraphLaunch(c->hgraph.exec, st));
+                CU(wait_stream(st));
+                done = !overflowed();
+            } else {                                        // capture refused something: stay on the plain path for good
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                c->hgraph.exec = nullptr; c->hgraph.key.clear();
+                c->host_graphs = false;
+            }
+        }
     }
+    while (!done) {
+        int rc = enqueue();
+        if (rc) return rc;
+        rc = under_settle(c, want_under);
+        if (rc < 0) return rc;
+        if (rc == 0) done = true;
+    }
+    c->last_host_key = c->host_graphs ? host_graph_key(c, grids, n_grids, grid_of_b != nullptr, cloud, bound != nullptr, B, flags, n_under != nullptr)
+                                      : std::vector<int64_t>();
     const char* hout = c->h_b.as<char>();
     std::memcpy(dmin, hout + oD, (size_t)B * 8);
     std::memcpy(argmin, hout + oA, (size_t)B * 8);

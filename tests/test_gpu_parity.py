@@ -649,6 +649,40 @@ def test_cloud_stored_far_from_its_origin_keeps_exact_results(ctx, O, flags):
     ctx.grid_destroy(g)
 
 
+@pytest.mark.parametrize("flags", [F32, F32 | PRUNE, F64])
+def test_repeated_host_calls_replayed_as_a_graph_stay_exact(ctx, O, flags):
+    """sio_min_distance replays a repeated call signature as one CUDA graph (H2D, memsets, kernels, D2H).  The replays
+    must answer NEW poses and bounds exactly, hand the under-bound list over, and fall back to the plain path -- which
+    re-sizes the candidate buffer -- when a replayed sweep offers more candidates than the buffer holds."""
+    g, G, cloud, T0 = _c1_scene(ctx, O)
+    c = ctx.cloud_create(cloud)
+    ctx.set_host_graphs(True)
+    ctx.set_under_capacity(4096)
+    try:
+        for rep in range(6):
+            T = util.invert12(util.random_poses(100 + rep, len(T0), rot=0.3, trans=0.3, center=(0.2, 0.2, 0.2)))
+            bound = np.full(len(T), 0.001 if rep < 4 else 0.05)          # rep 4: far more candidates than 4096
+            dmin, arg, nu = ctx.min_distance(g, c, T, bound=bound, flags=flags)
+            ub, ui, ud = ctx.under_fetch(1 << 22)
+            d0, a0 = O.min_distance(G, cloud, T, bound=bound)
+            n0, ob, oi, od = O.under(G, cloud, T, bound)
+            assert np.array_equal(arg, a0) and np.abs(dmin - d0).max() <= 1e-12, rep
+            assert n0 == len(ub) and np.array_equal(ub, ob) and np.array_equal(ui, oi) and np.abs(ud - od).max() <= 1e-12, rep
+            assert np.array_equal(nu, np.bincount(ob, minlength=len(T))), rep
+            if rep == 4:
+                assert n0 > 4096
+        # minimum-only calls (what minvalue issues), one pose per call, as the SIP loop does
+        for rep in range(5):
+            T = util.invert12(util.random_poses(200 + rep, 1, rot=0.3, trans=0.3, center=(0.2, 0.2, 0.2)))
+            dmin, arg, _ = ctx.min_distance(g, c, T, bound=[0.0], flags=flags, want_under=False)
+            d0, a0 = O.min_distance(G, cloud, T, bound=[0.0])
+            assert np.array_equal(arg, a0) and np.abs(dmin - d0).max() <= 1e-12
+    finally:
+        ctx.set_under_capacity(0)
+    ctx.cloud_destroy(c)
+    ctx.grid_destroy(g)
+
+
 def test_error_paths(ctx, O):
     from semiinfiniteoptimization_b200 import _abi
     vg = util.random_grid(95)

@@ -13,6 +13,7 @@ from semiinfiniteoptimization_b200._host.geometry import fixture_geometry
 ap = argparse.ArgumentParser(); ap.add_argument("--poses", type=int, default=2048); ap.add_argument("--iters", type=int, default=5)
 a = ap.parse_args()
 ctx = _abi.Context(0)
+ctx.set_host_graphs(False)          # every call is timed by the events around its bulk launch
 vg = fixture_geometry("cube").convert("VolumeGrid", 0.05).getVolumeGrid()
 g = ctx.grid_create(vg.values, vg.bmin, vg.bmax)
 cloud = W.c5_scene_cloud()
