@@ -538,7 +538,7 @@ bool launch_min_smem(const MinArgs& a, cudaStream_t st) {
 // transforms are transposed through shared memory so that both kernels touch lb in 128-byte rows.  Every sub-tile key
 // starts at +inf here (the finalize pass never opens a sub-tile k_min_items did not evaluate).
 __global__ void __launch_bounds__(kThreads)
-k_prune_centres(const float4* __restrict__ rep, int64_t nsub, const XfRec* __restrict__ xf, int64_t b_begin, int64_t Bc,
+k_prune_centres(const float4* __restrict__ rep, int64_t nsub, const XfRec* __restrict__ xf, int64_t b_begin, int64_t Bc, int32_t xfchunk,
                 float* __restrict__ lb, uint32_t* __restrict__ ub, uint32_t* __restrict__ subkeys) {
     __shared__ XfRec sxf[kXfChunk];
     __shared__ float tile[kThreads][kXfChunk + 1];
@@ -546,9 +546,9 @@ k_prune_centres(const float4* __restrict__ rep, int64_t nsub, const XfRec* __res
     const int64_t ntl = (nsub + kThreads - 1) / kThreads;
     const int64_t chunk = blockIdx.x / ntl;
     const int64_t tl = blockIdx.x - chunk * ntl;
-    const int64_t b0 = chunk * kXfChunk;
+    const int64_t b0 = chunk * xfchunk;                    // xfchunk <= kXfChunk transforms per CTA (fewer when the sweep is small)
     const int64_t Bp = (Bc + 31) & ~(int64_t)31;
-    const int nb = (int)min((int64_t)kXfChunk, Bc - b0);
+    const int nb = (int)min((int64_t)xfchunk, Bc - b0);
     {
         const uint4* src = reinterpret_cast<const uint4*>(xf + b_begin + b0);
         uint4* dst = reinterpret_cast<uint4*>(sxf);
@@ -703,8 +703,13 @@ void launch_min_pruned(const MinArgs& a, cudaStream_t st) {
     if (a.Bc <= 0 || a.N <= 0) return;
     const int64_t nsub = (int64_t)a.ntiles * (kThreads / 32);
     const int64_t ntl = (nsub + kThreads - 1) / kThreads;
-    const int64_t nchunks = (a.Bc + kXfChunk - 1) / kXfChunk;
-    k_prune_centres<<<(unsigned)(nchunks * ntl), kThreads, 0, st>>>(a.rep, nsub, a.xf, a.b_begin, a.Bc, a.lb, a.ub, a.subkeys);
+    // transforms per CTA: the full chunk when the sweep is large; a small sweep (C2: 64 poses x 8,192 sub-tiles = 64 CTAs
+    // at 32 per CTA, 25 us of latency for 0.8 % of the bulk pass's queries) is cut finer until it fills the machine
+    int xfchunk = kXfChunk;
+    const int sms = a.num_sms > 0 ? a.num_sms : 148;
+    while (xfchunk > 4 && ((a.Bc + xfchunk - 1) / xfchunk) * ntl < 4 * (int64_t)sms) xfchunk >>= 1;
+    const int64_t nchunks = (a.Bc + xfchunk - 1) / xfchunk;
+    k_prune_centres<<<(unsigned)(nchunks * ntl), kThreads, 0, st>>>(a.rep, nsub, a.xf, a.b_begin, a.Bc, xfchunk, a.lb, a.ub, a.subkeys);
     const int64_t Bp = (a.Bc + 31) & ~(int64_t)31;
     k_prune_select<<<dim3((unsigned)((Bp + 255) / 256), (unsigned)((nsub + kSelectRows - 1) / kSelectRows)), 256, 0, st>>>(
         a.lb, a.ub, a.under_bound, nsub, a.b_begin, a.Bc, (float)a.tau, a.items, a.item_count);
