@@ -532,7 +532,19 @@ def main():
     boards = None
     if world > 1:
         from semiinfiniteoptimization_b200 import dist as sdist
-        boards = sdist.ResultBoards(ctx, B)
+        try:
+            boards = sdist.ResultBoards(ctx, B)
+        except Exception as e:                         # no peer access / IPC on this box: fall back to the NCCL exchange
+            sys.stderr.write("rank %d: result boards unavailable (%s); using all_gather_into_tensor\n" % (rank, e))
+            boards = None
+        okf = torch.tensor([1.0 if boards is not None else 0.0], device="cuda")
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        if okf.item() != 1.0 and boards is not None:
+            dist.barrier()                             # the ranks that did map this board are past their last store (none yet)
+            boards.close(collective=False)
+            boards = None
+        elif okf.item() != 1.0:
+            dist.barrier()
 
     def step(push=False):
         ctx.min_distance_dev([g], c, dT.data_ptr(), dbound.data_ptr(), B, _abi.SIO_F32 | (_abi.SIO_PUSH_BOARDS if push else 0),
@@ -566,7 +578,7 @@ def main():
         step()
     launches_per_step = ctx.kernel_launches - launches_per_step
     graph_push = None
-    if world > 1:                                       # the interval's last step: the same sweep + the peer stores
+    if boards is not None:                              # the interval's last step: the same sweep + the peer stores
         graph_push = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph_push, stream=stream):
             step(push=True)
@@ -588,13 +600,27 @@ def main():
             ev[k][0].record(stream)
             (graph_push if (graph_push is not None and k == args.steps - 1) else graph).replay()
             ev[k][1].record(stream)
+    gather_ms = 0.0
+    if world > 1 and boards is None:                    # fallback exchange: one NCCL all-gather of the packed records, timed
+        ctx.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        gather()
+        g1.record(stream)
+        g1.synchronize()
+        gather_ms = g0.elapsed_time(g1)
     ctx.sync()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()                                  # every rank's peer stores have landed on every board
     t_wall = time.perf_counter() - t_wall0
     exchange = None
-    if world > 1:
+    if world > 1 and boards is None:
+        exchange = {"how": "NCCL all_gather_into_tensor of the packed per-rank records, once per interval (result boards unavailable)",
+                    "ms": gather_ms}
+    if boards is not None:
         bd, ba, bn = boards.read()
         gather()                                        # verification only, outside the timed region
         torch.cuda.synchronize()
@@ -611,7 +637,7 @@ def main():
     clocks = sampler.stop()
     launches = launches_per_step * args.steps
     ms_steps = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(ms_steps))                      # K sweeps, the last one carrying the exchange
+    total_ms = float(sum(ms_steps)) + gather_ms          # K sweeps, the last one carrying the exchange (or + the fallback gather)
     per_rank = None
     if world > 1:
         mine = torch.tensor([float(sum(ms_steps)), float(ms_steps[-1])], dtype=torch.float64, device="cuda")

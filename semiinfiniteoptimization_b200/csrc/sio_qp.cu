@@ -28,6 +28,11 @@ constexpr int kQpMaxRows = 64;              // 2 rows per lane
 constexpr int kQpMaxVars = 8;
 constexpr int kQpMaxKkt = kQpMaxVars + kQpMaxRows;     // largest polish system (x + active rows)
 constexpr int kQpScratch = kQpMaxKkt * (kQpMaxKkt + 1);   // doubles per warp
+// Polish systems of up to kQpSmemKkt unknowns (x + active rows: nearly all of them) are factorised in shared memory:
+// the elimination is a chain of dependent loads and stores with two __syncwarp per column, 15-20 us per problem at
+// L2 latency (a quarter of a typical solve), a few at shared-memory latency.  Larger systems use the global scratch.
+constexpr int kQpSmemKkt = 24;
+constexpr int kQpSmemScratch = kQpSmemKkt * (kQpSmemKkt + 1);
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -228,7 +233,7 @@ enum { kAdmmSolved = 0, kAdmmMaxIter = 1, kAdmmInfeasible = 2 };
 // instruction cache (ncu r01_qp: 64 % of the stall samples were instruction fetch).
 template <int N, int NR>
 __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, const double (&Pd)[N], const double (&q)[N], double pen, int k, int m, double eps_abs,
-                    double eps_rel, int max_iter, double* kkt, int lane, double (&x)[N], double (&sv)[NR], int& iters) {
+                    double eps_rel, int max_iter, double* kkt, double* skkt, int lane, double (&x)[N], double (&sv)[NR], int& iters) {
     constexpr double kInf = 1e20, sigma = 1e-6, alpha = 1.6;
     constexpr int check_every = 10, adapt_every = 50;
     double z[NR], y[NR], rv[NR], dy[NR], Ax[NR], ds[NR];
@@ -438,7 +443,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
     // row) is eliminated in closed form: s_r = -lambda_r / (pen + delta), which adds 1 / (pen + delta) to that row's
     // -delta diagonal; slack variables of inactive rows are zero.
     const int NN = N + na;
-    double* M = kkt;
+    double* M = (NN <= kQpSmemKkt) ? skkt : kkt;
     double* bb = M + NN * NN;
     for (int e = lane; e < NN * (NN + 1); e += 32) M[e] = 0.0;
     __syncwarp();
@@ -510,7 +515,7 @@ template <int N, int NR>
 __device__ __forceinline__ void solve_rows(int64_t p, int k, int m, int64_t base, bool box, const double* __restrict__ W,
                                            const double* __restrict__ xdes, const double* __restrict__ xmin, const double* __restrict__ xmax,
                                            const double* __restrict__ rows, const double* __restrict__ depths, double reg, double inflation,
-                                           double eps_abs, double eps_rel, int max_iter, double* kkt, int lane, double* __restrict__ dx,
+                                           double eps_abs, double eps_rel, int max_iter, double* kkt, double* skkt, int lane, double* __restrict__ dx,
                                            int32_t* __restrict__ status, const QpDefer& df) {
     constexpr double kInf = 1e20;
     double Pd[N], q[N];
@@ -557,7 +562,7 @@ __device__ __forceinline__ void solve_rows(int64_t p, int k, int m, int64_t base
     int iters = 0, code = kQpStrict;
     double pen = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
-        const int st = admm<N, NR>(pass == 1, R, Pd, q, pen, k, m, eps_abs, eps_rel, max_iter, kkt, lane, x, sv, iters);
+        const int st = admm<N, NR>(pass == 1, R, Pd, q, pen, k, m, eps_abs, eps_rel, max_iter, kkt, skkt, lane, x, sv, iters);
         if (df.list && st == kAdmmMaxIter) {              // capped launch: out of budget -> the follow-up launch solves it in full
             if (lane == 0) {
                 status[p] = kQpDeferred;
@@ -588,7 +593,7 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
                               const double* __restrict__ xmax, const int64_t* __restrict__ offs, const int32_t* __restrict__ cnt,
                               int32_t stride, const double* __restrict__ rows,
                               const double* __restrict__ depths, double reg, double inflation, double eps_abs, double eps_rel,
-                              int max_iter, double* kkt, int lane, double* __restrict__ dx, int32_t* __restrict__ status,
+                              int max_iter, double* kkt, double* skkt, int lane, double* __restrict__ dx, int32_t* __restrict__ status,
                               const QpDefer& df) {
     constexpr double kInf = 1e20;
     // ragged layout: rows of problem p at offs[p] .. offs[p+1];  padded layout (lock-step solver): cnt[p] rows at
@@ -607,9 +612,9 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
     const int m = k + (box ? N : 0);
     if (m > kQpMaxRows) { if (lane == 0) status[p] = kQpToHost; return; }
     if (m <= 32)
-        solve_rows<N, 1>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status, df);
+        solve_rows<N, 1>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
     else
-        solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status, df);
+        solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
 }
 
 // persistent warps: each draws the next problem from *counter (reset to 0 by the launcher).
@@ -628,6 +633,8 @@ k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__
          QpDefer df) {
     const int lane = threadIdx.x & 31;
     double* kkt = scratch + (blockDim.x == 32 ? (size_t)blockIdx.x : (size_t)blockIdx.x * kQpWarps + (threadIdx.x >> 5)) * kQpScratch;
+    __shared__ double s_kkt[kQpWarps][kQpSmemScratch];
+    double* skkt = s_kkt[threadIdx.x >> 5];
     const unsigned long long limit = df.only ? (unsigned long long)*df.only_n : (unsigned long long)nprob;
     for (;;) {
         unsigned long long i = 0;
@@ -636,7 +643,7 @@ k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__
         if (i >= limit) return;
         const int64_t p = df.only ? (int64_t)df.only[i] : (int64_t)i;
         if (df.busy && df.busy[p] == 1) continue;
-        solve_problem<N>(p, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, lane, dx, status, df);
+        solve_problem<N>(p, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
         if (df.only) {                                     // publish: answer first, flag second
             __threadfence();
             __syncwarp();

@@ -134,15 +134,18 @@ class ResultBoards:
     def read(self):
         return self.ctx.board_read(self.world, self.slot_bytes, self.B)
 
-    def close(self):
+    def close(self, collective=True):
+        """collective=False: this rank alone gives its boards up (another rank failed to set its own up), no barriers."""
         if self.local is None:
             return
         self.ctx.set_boards(0, [], 0)
-        barrier()                                  # nobody may still be storing into a board that is about to go
+        if collective:
+            barrier()                              # nobody may still be storing into a board that is about to go
         for r, p in enumerate(self.ptrs):
             if r != self.rank and p is not None:
                 self.ctx.board_close(p, False)
-        barrier()
+        if collective:
+            barrier()
         self.ctx.board_close(self.local, True)
         self.local = None
 
