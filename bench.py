@@ -78,7 +78,7 @@ class ClockSampler:
     because an nvidia-smi subprocess polling every 100 ms was seen to stall CUDA calls."""
     REASONS = {0x08: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x04: "sw_power_cap"}
 
-    def __init__(self, device, period_s=0.005):
+    def __init__(self, device, period_s=0.001):
         self.device, self.period = device, period_s
         self.sm, self.reasons, self.smax, self.power = [], set(), None, []
         self._stop = threading.Event()

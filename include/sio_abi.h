@@ -239,7 +239,9 @@ int sio_mesh_sdf_grid(sio_ctx* ctx, const double* verts, int32_t nv, const int32
 /* replaces: geom.convert('PointCloud', pcres) -- geometryopt.py:65.  The mesh vertices plus, per triangle, the lattice
  * spanned by its two shorter edges with ceil(edge / res) subdivisions (no surface point farther than ~res from a
  * sample), points shared between triangles merged (quantised to 1e-9 m, first occurrence kept, order preserved).
- * out_pts [capacity*3] float64 (NULL: count only); *n_out = number of points. */
+ * out_pts [capacity*3] float64 (NULL: count only); *n_out = number of points.  sio_mesh_surface_sample_bound (host work
+ * only, no device) returns the number of points before merging: an upper bound to size out_pts with. */
+int64_t sio_mesh_surface_sample_bound(const double* verts, int32_t nv, const int32_t* tris, int32_t nt, double res);
 int sio_mesh_surface_sample(sio_ctx* ctx, const double* verts, int32_t nv, const int32_t* tris, int32_t nt, double res,
                             double* out_pts, int64_t capacity, int64_t* n_out);
 

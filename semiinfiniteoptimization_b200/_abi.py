@@ -31,7 +31,7 @@ ABI_SYMBOLS = (
     "sio_grid_create", "sio_grid_destroy", "sio_cloud_create", "sio_cloud_order", "sio_cloud_destroy", "sio_cloud_size",
     "sio_query", "sio_cloud_query_dev", "sio_cloud_perm",
     "sio_min_distance", "sio_min_distance_dev", "sio_under_fetch",
-    "sio_pose_rows", "sio_sip_step_qp", "sio_mesh_distance_grid", "sio_mesh_sdf_grid", "sio_mesh_surface_sample", "sio_lockstep_pose_solve",
+    "sio_pose_rows", "sio_sip_step_qp", "sio_mesh_distance_grid", "sio_mesh_sdf_grid", "sio_mesh_surface_sample", "sio_mesh_surface_sample_bound", "sio_lockstep_pose_solve",
     "sio_robot_create", "sio_robot_destroy", "sio_fk", "sio_chain_rows", "sio_robot_min_distance", "sio_robot_pairs_min_distance",
     "sio_bench_gather", "sio_ctx_last_bulk_ms", "sio_ctx_last_prune_stats", "sio_ctx_last_qp_iters",
 )
@@ -92,6 +92,8 @@ def load_library():
     L.sio_mesh_distance_grid.argtypes = [P, P, I32, P, I32, P, P, P, P]
     L.sio_mesh_sdf_grid.argtypes = [P, P, I32, P, I32, P, P, P, P]
     L.sio_mesh_surface_sample.argtypes = [P, P, I32, P, I32, D, P, I64, C.POINTER(I64)]
+    L.sio_mesh_surface_sample_bound.argtypes = [P, I32, P, I32, D]
+    L.sio_mesh_surface_sample_bound.restype = I64
     L.sio_lockstep_pose_solve.argtypes = [P, I32, I32, P, P, I64, P, P, P, P, P, P, P, P, P, P, P, P]
     L.sio_robot_create.argtypes = [P, I32, P, P, P, P, C.POINTER(I32)]
     L.sio_robot_destroy.argtypes = [P, I32]
@@ -365,13 +367,14 @@ class Context:
         """Surface point cloud (n, 3) float64 at resolution `res` (vertices + per-triangle lattices, duplicates merged)."""
         V = _f64(verts).reshape(-1, 3)
         T = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1, 3)
+        tp = T.ctypes.data if len(T) else None
+        bound = self.L.sio_mesh_surface_sample_bound(V.ctypes.data, len(V), tp, len(T), float(res))     # host only: points before merging
+        if bound < 0:
+            raise SioError(-1, self.L.sio_last_error().decode())
+        out = np.empty((bound, 3))
         n = C.c_int64(0)
-        self._ck(self.L.sio_mesh_surface_sample(self.h, V.ctypes.data, len(V), T.ctypes.data if len(T) else None, len(T), float(res),
-                                                None, 0, C.byref(n)))
-        out = np.empty((n.value, 3))
-        self._ck(self.L.sio_mesh_surface_sample(self.h, V.ctypes.data, len(V), T.ctypes.data if len(T) else None, len(T), float(res),
-                                                out.ctypes.data, n.value, C.byref(n)))
-        return out
+        self._ck(self.L.sio_mesh_surface_sample(self.h, V.ctypes.data, len(V), tp, len(T), float(res), out.ctypes.data, bound, C.byref(n)))
+        return out[:n.value].copy()
 
     # -- SIP-step QPs --
     def sip_step_qp(self, W, xdes, offs, rows, depths, xmin=None, xmax=None, reg=1e-2, inflation=1e-3, eps_abs=1e-5, max_iter=4000):

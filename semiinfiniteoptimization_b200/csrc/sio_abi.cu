@@ -1401,59 +1401,71 @@ int sio_mesh_sdf_grid(sio_ctx* c, const double* verts, int32_t nv, const int32_t
     return SIO_OK;
 }
 
+// layout of the surface sampler's output (host, O(triangles)): the vertices first, then one block per triangle,
+// triangles grouped by their (m1, m2) in lexicographic order, ascending triangle index inside a group -- the order the
+// host builder emits.  Returns the number of points BEFORE duplicates are merged, or -1 (message set).
+static int64_t surface_layout(const double* verts, int32_t nv, const int32_t* tris, int32_t nt, double res, std::vector<LatticeTriHost>* recs) {
+    int64_t total = nv;
+    if (!(res > 0 && std::isfinite(res) && nt > 0)) return total;
+    struct Item { int32_t m1, m2, t; };
+    std::vector<Item> items;
+    std::vector<LatticeTriHost> tmp((size_t)nt);
+    for (int t = 0; t < nt; ++t) {
+        const double* P[3];
+        for (int v = 0; v < 3; ++v) {
+            const int32_t idx = tris[3 * t + v];
+            if (idx < 0 || idx >= nv) { fail(SIO_ERR_INVALID, "sio_mesh_surface_sample: triangle %d refers to vertex %d", t, idx); return -1; }
+            P[v] = verts + 3 * (size_t)idx;
+        }
+        auto dist = [](const double* x, const double* y) {
+            const double d0 = x[0] - y[0], d1 = x[1] - y[1], d2 = x[2] - y[2];
+            return std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        };
+        const double e[3] = {dist(P[2], P[1]), dist(P[0], P[2]), dist(P[1], P[0])};       // edge opposite vertex v
+        int apex = 0;
+        if (e[1] > e[apex]) apex = 1;
+        if (e[2] > e[apex]) apex = 2;
+        const double *A = P[apex], *Bp = P[(apex + 1) % 3], *Cp = P[(apex + 2) % 3];
+        LatticeTriHost r;
+        for (int a = 0; a < 3; ++a) { r.a[a] = A[a]; r.b[a] = Bp[a]; r.c[a] = Cp[a]; }
+        r.m1 = (int32_t)std::max(1.0, std::ceil(dist(Bp, A) / res - 1e-9));
+        r.m2 = (int32_t)std::max(1.0, std::ceil(dist(Cp, A) / res - 1e-9));
+        r.base = 0;
+        tmp[t] = r;
+        if (!(r.m1 == 1 && r.m2 == 1)) items.push_back({r.m1, r.m2, t});
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.m1 != y.m1 ? x.m1 < y.m1 : x.m2 < y.m2; });
+    if (recs) recs->reserve(items.size());
+    for (const Item& it : items) {
+        LatticeTriHost r = tmp[it.t];
+        int64_t cnt = 0;
+        for (int i = 0; i <= r.m1; ++i) {
+            const double u = (double)i / (double)r.m1;
+            for (int j = 0; j <= r.m2; ++j) {
+                const double v = (double)j / (double)r.m2;
+                if ((u + v) <= 1.0 + 1e-12 && !((i == 0 && j == 0) || (i == r.m1 && j == 0) || (i == 0 && j == r.m2))) ++cnt;
+            }
+        }
+        r.base = total;
+        total += cnt;
+        if (recs) recs->push_back(r);
+    }
+    return total;
+}
+
+// upper bound of the sampler's output (host work only): what a caller sizes out_pts with
+int64_t sio_mesh_surface_sample_bound(const double* verts, int32_t nv, const int32_t* tris, int32_t nt, double res) {
+    if (!verts || nv <= 0 || nt < 0 || (nt > 0 && !tris)) { fail(SIO_ERR_INVALID, "sio_mesh_surface_sample_bound: bad argument"); return -1; }
+    return surface_layout(verts, nv, tris, nt, res, nullptr);
+}
+
 // mesh -> surface point cloud at resolution `res`
 int sio_mesh_surface_sample(sio_ctx* c, const double* verts, int32_t nv, const int32_t* tris, int32_t nt, double res,
                             double* out_pts, int64_t capacity, int64_t* n_out) {
     if (!c || !verts || !n_out || nv <= 0 || nt < 0 || (nt > 0 && !tris)) return fail(SIO_ERR_INVALID, "sio_mesh_surface_sample: bad argument");
-    // layout (host, O(triangles)): the vertices first, then one block per triangle, triangles grouped by their (m1, m2)
-    // in lexicographic order, ascending triangle index inside a group -- the order the host builder emits
     std::vector<LatticeTriHost> recs;
-    int64_t total = nv;
-    if (res > 0 && std::isfinite(res) && nt > 0) {
-        struct Item { int32_t m1, m2, t; };
-        std::vector<Item> items;
-        std::vector<LatticeTriHost> tmp((size_t)nt);
-        for (int t = 0; t < nt; ++t) {
-            const double* P[3];
-            for (int v = 0; v < 3; ++v) {
-                const int32_t idx = tris[3 * t + v];
-                if (idx < 0 || idx >= nv) return fail(SIO_ERR_INVALID, "sio_mesh_surface_sample: triangle %d refers to vertex %d", t, idx);
-                P[v] = verts + 3 * (size_t)idx;
-            }
-            auto dist = [](const double* x, const double* y) {
-                const double d0 = x[0] - y[0], d1 = x[1] - y[1], d2 = x[2] - y[2];
-                return std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-            };
-            const double e[3] = {dist(P[2], P[1]), dist(P[0], P[2]), dist(P[1], P[0])};       // edge opposite vertex v
-            int apex = 0;
-            if (e[1] > e[apex]) apex = 1;
-            if (e[2] > e[apex]) apex = 2;
-            const double *A = P[apex], *Bp = P[(apex + 1) % 3], *Cp = P[(apex + 2) % 3];
-            LatticeTriHost r;
-            for (int a = 0; a < 3; ++a) { r.a[a] = A[a]; r.b[a] = Bp[a]; r.c[a] = Cp[a]; }
-            r.m1 = (int32_t)std::max(1.0, std::ceil(dist(Bp, A) / res - 1e-9));
-            r.m2 = (int32_t)std::max(1.0, std::ceil(dist(Cp, A) / res - 1e-9));
-            r.base = 0;
-            tmp[t] = r;
-            if (!(r.m1 == 1 && r.m2 == 1)) items.push_back({r.m1, r.m2, t});
-        }
-        std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.m1 != y.m1 ? x.m1 < y.m1 : x.m2 < y.m2; });
-        recs.reserve(items.size());
-        for (const Item& it : items) {
-            LatticeTriHost r = tmp[it.t];
-            int64_t cnt = 0;
-            for (int i = 0; i <= r.m1; ++i) {
-                const double u = (double)i / (double)r.m1;
-                for (int j = 0; j <= r.m2; ++j) {
-                    const double v = (double)j / (double)r.m2;
-                    if ((u + v) <= 1.0 + 1e-12 && !((i == 0 && j == 0) || (i == r.m1 && j == 0) || (i == 0 && j == r.m2))) ++cnt;
-                }
-            }
-            r.base = total;
-            total += cnt;
-            recs.push_back(r);
-        }
-    }
+    const int64_t total = surface_layout(verts, nv, tris, nt, res, &recs);
+    if (total < 0) return SIO_ERR_INVALID;
     if (total >= (1LL << 31)) return fail(SIO_ERR_INVALID, "sio_mesh_surface_sample: %lld lattice points: too many", (long long)total);
     DeviceGuard guard(c->device);
     cudaStream_t st = c->stream;

@@ -512,8 +512,8 @@ bool launch_min_smem(const MinArgs& a, cudaStream_t st) {
     const size_t n_floats = (size_t)(g.nx + 1) * (g.ny + 1) * (g.nz + 1);
     const size_t bytes = ((n_floats * 4 + 127) / 128) * 128;
     if (bytes > 200 * 1024) return false;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_min_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    // per device and cheap: set on every launch rather than remembered (a process may drive several devices)
+    if (cudaFuncSetAttribute(k_min_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return false;
     const int64_t nsub = (int64_t)a.ntiles * (kThreads / 32);
     k_min_smem<<<a.num_sms > 0 ? a.num_sms : 148, kSmemThreads, bytes, st>>>(a.pts, a.xf, a.b_begin, a.Bc, nsub, kXfChunk, a.subkeys, g.v,
                                                                              (uint32_t)n_floats, g.sx, g.sy);
