@@ -195,7 +195,8 @@ int sio_robot_pairs_min_distance(sio_ctx* ctx, sio_handle robot, const sio_handl
  * replaces: B runs of optimizeCollFree (geometryopt.py:1039-1081) = optimizeSemiInfinite (sip.py:795-1241, default
  * flags) with one ObjectCollisionConstraint (gopt:394-420) each -- BASELINE.json configs[4].  The moving body owns
  * `grid`, the environment owns `cloud` (pose T_env = world <- cloud; cloud_world [N*3] = its points in world
- * coordinates, caller order).  T_init / T_des / T_out are row-major 3x4 poses of the moving body.
+ * coordinates, caller order -- a function of (cloud, T_env): the library keeps its device copy and re-uploads it only
+ * when either differs from the previous call's).  T_init / T_des / T_out are row-major 3x4 poses of the moving body.
  * Per problem: status (1 = 'local optimum', 0 = iteration limit), iterations, f(x), g(x) = min over instantiated
  * parameters, g at the start, number of instantiated parameters and (optional) the parameters themselves
  * [B*cap*3].  status 2 = the problem's QP had no solution, not even with slack variables (the reference fails there,

@@ -127,6 +127,9 @@ struct sio_ctx {
     int64_t qp_iters_total = 0, qp_iters_max = 0, qp_at_limit = 0;      // ADMM iterations of the last sio_sip_step_qp call, summed over problems
     DevBuf s_qp;                     // per-warp polish scratch + work counter of the SIP-step QP kernel
     DevBuf s_ls;                     // per-problem state of the lock-step solver (sio_lockstep_pose_solve)
+    DevBuf s_ls_cloud;               // the environment cloud in world coordinates (float64), kept between calls:
+    sio_handle ls_cloud_h = -1;      //   by contract it is a function of (cloud, T_env), so the 6 MB upload is skipped when
+    double ls_cloud_T[12] = {0};     //   both are those of the previous call
     // background QP launches of the lock-step solver (the deferred stragglers): their own streams and polish scratch
     static constexpr int kLsBack = 3, kLsRing = 8;
     cudaStream_t ls_stream[kLsBack] = {nullptr, nullptr, nullptr};
@@ -255,7 +258,7 @@ int sio_ctx_destroy(sio_ctx* c) {
     c->s_qp.release();
     if (c->hgraph.exec) cudaGraphExecDestroy(c->hgraph.exec);
     c->s_boards.release();
-    c->s_lb.release(); c->s_ub.release(); c->s_items.release(); c->s_icnt.release(); c->h_icnt.release(); c->s_ls.release();
+    c->s_lb.release(); c->s_ub.release(); c->s_items.release(); c->s_icnt.release(); c->h_icnt.release(); c->s_ls.release(); c->s_ls_cloud.release();
     for (int k = 0; k < sio_ctx::kLsBack; ++k) { c->s_qpb[k].release(); if (c->ls_stream[k]) cudaStreamDestroy(c->ls_stream[k]); }
     for (int k = 0; k < sio_ctx::kLsRing; ++k) { if (c->ls_evA[k]) cudaEventDestroy(c->ls_evA[k]); if (c->ls_evB[k]) cudaEventDestroy(c->ls_evB[k]); }
     DevBuf* bufs[] = {&c->s_xf, &c->s_keys, &c->s_gridtab, &c->s_cand, &c->s_cnt, &c->s_in0, &c->s_in1, &c->s_in2, &c->s_in3,
@@ -1090,7 +1093,6 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     {   // size pass on a null arena, then the real one
         Arena probe; LsState tmp{};
         size_t need = carve(probe, tmp, B, cap, [&] {
-            probe.take<double>((size_t)N * 3);
             for (int k = 0; k < sio_ctx::kLsRing; ++k) probe.take<int32_t>(B);
             probe.take<uint32_t>(sio_ctx::kLsRing);
         });
@@ -1101,13 +1103,22 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     int32_t* dlist[sio_ctx::kLsRing];                      // problems each of the last rounds' capped QP launches gave up on
     uint32_t* dcount = nullptr;
     carve(A, S, B, cap, [&] {
-        d_cloud = A.take<double>((size_t)N * 3);
         for (int k = 0; k < sio_ctx::kLsRing; ++k) dlist[k] = A.take<int32_t>(B);
         dcount = A.take<uint32_t>(sio_ctx::kLsRing);
     });
+    {
+        const bool same = c->ls_cloud_h == cloud && c->s_ls_cloud.p && std::memcmp(c->ls_cloud_T, T_env, sizeof(c->ls_cloud_T)) == 0;
+        if (!same) {
+            c->ls_cloud_h = -1;
+            CU(c->s_ls_cloud.ensure((size_t)std::max<int64_t>(N, 1) * 3 * sizeof(double)));
+            CU(cudaMemcpyAsync(c->s_ls_cloud.p, cloud_world, (size_t)N * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+            c->ls_cloud_h = cloud;
+            std::memcpy(c->ls_cloud_T, T_env, sizeof(c->ls_cloud_T));
+        }
+        d_cloud = c->s_ls_cloud.as<double>();
+    }
     S.cloud_world = d_cloud;
     S.grid = c->grids[grid].d_meta;
-    CU(cudaMemcpyAsync(d_cloud, cloud_world, (size_t)N * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     // poses: row-major 3x4 -> R (3x3) and t
     {
         std::vector<double> hR((size_t)B * 9), ht((size_t)B * 3), hRd((size_t)B * 9), htd((size_t)B * 3);
