@@ -231,3 +231,24 @@ def test_committed_goldens_are_what_the_reference_produces_now():
             assert len(out[1]) == len(case["trace"])
             for a, b in zip(out[1], case["trace"]):
                 assert _pose_close(a, b, 0.0)
+        # C5: one sampled problem with a real trajectory (gopt:1039-1081 on the 262,144-point scene)
+        g5 = scenes.load_golden("c5_pose.json")
+        case = next(c for c in g5["cases"] if 5 <= c["iterations"] <= 20)
+        mod5, cube, scene, con5 = scenes.c5_scene('reference')
+        T = (case["Tinit"][0], case["Tinit"][1])
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = mod5.optimizeCollFree(cube, scene, T, verbose=0)
+        assert len(out[1]) - 1 == case["iterations"] and _pose_close(out[0], case["T"], 0.0)
+        # f4: the reference's own arc_length_refine on the shipped initial path
+        from oracle.frozen.robot import WorldModel
+        from oracle.frozen.trajectory import RobotTrajectory
+        from tools.make_golden import planopt_inputs
+        planopt = load.load()["planopt"]
+        w, robot, p0 = planopt_inputs(WorldModel)
+        refined = planopt.arc_length_refine(RobotTrajectory(robot, list(range(len(p0["milestones"]))), p0["milestones"]), 12)
+        want = scenes.load_golden("planopt.json")["arc_length_refine"]["robot_12"]
+        assert np.array_equal(np.array(refined.milestones), np.array(want["milestones"])) and np.array_equal(refined.times, want["times"])
+        # the shipped .path / .configs files are what path_files.json holds
+        files = scenes.load_golden("path_files.json")["files"]
+        for name, text in files.items():
+            assert open(os.path.join(load.REFERENCE_ROOT, name)).read() == text
