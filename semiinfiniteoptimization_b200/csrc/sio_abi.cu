@@ -1095,6 +1095,8 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
         size_t need = carve(probe, tmp, B, cap, [&] {
             for (int k = 0; k < sio_ctx::kLsRing; ++k) probe.take<int32_t>(B);
             probe.take<uint32_t>(sio_ctx::kLsRing);
+            probe.take<int32_t>(B);
+            probe.take<uint32_t>(1);
         });
         CU(c->s_ls.ensure(need + 4096));                  // kept by the context: releasing ~350 MB per call cost tens of ms
         A.base = c->s_ls.as<char>();
@@ -1102,9 +1104,13 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     }
     int32_t* dlist[sio_ctx::kLsRing];                      // problems each of the last rounds' capped QP launches gave up on
     uint32_t* dcount = nullptr;
+    int32_t* wlist = nullptr;                              // problems of the current round with more than 32 QP rows
+    uint32_t* wcount = nullptr;
     carve(A, S, B, cap, [&] {
         for (int k = 0; k < sio_ctx::kLsRing; ++k) dlist[k] = A.take<int32_t>(B);
         dcount = A.take<uint32_t>(sio_ctx::kLsRing);
+        wlist = A.take<int32_t>(B);
+        wcount = A.take<uint32_t>(1);
     });
     {
         const bool same = c->ls_cloud_h == cloud && c->s_ls_cloud.p && std::memcmp(c->ls_cloud_T, T_env, sizeof(c->ls_cloud_T)) == 0;
@@ -1248,6 +1254,7 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
             if (rounds_with_qp >= sio_ctx::kLsRing) CU(cudaStreamWaitEvent(st, c->ls_evB[slot], 0));   // the slot's previous list is consumed
             CU(cudaMemsetAsync(dcount + slot, 0, sizeof(uint32_t), st));
             dfA.list = dlist[slot]; dfA.count = dcount + slot; dfA.done = S.qdone; dfA.mark = S.qdef; dfA.busy = S.ph;
+            dfA.wide = wlist; dfA.wide_n = wcount;
         }
         mark();
         if (launch_sip_qp(6, B, S.qW, S.dxdes, S.qlo, S.qhi, nullptr, S.qk, cap, S.rows, S.D, L.reg, L.inflation, 1e-5,

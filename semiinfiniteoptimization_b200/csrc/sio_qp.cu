@@ -588,7 +588,15 @@ __device__ __forceinline__ void solve_rows(int64_t p, int k, int m, int64_t base
     if (lane == 0) status[p] = code | (iters << 8);        // ADMM iterations spent, for diagnostics
 }
 
-template <int N>
+// Three builds of the kernel.  kQpFull serves any problem (plain calls, and the follow-up launches over the stragglers).
+// The capped launch of the lock-step solver is split in two, back to back on one stream: kQpNarrow compiles in only the
+// one-row-per-lane solver and lists the problems with more than 32 rows in df.wide; kQpWide then solves exactly those with
+// the two-row solver.  In one kernel the two-row instantiation (70 % of the instructions) sets the register allocation
+// and the one-row loop -- where the launch spends its time -- runs with spills; apart it has 222 registers and none
+// (profiles/r02_qp_phases.md: in-line QP time of BASELINE configs[4] 0.217 -> 0.16 s).
+enum { kQpFull = 0, kQpNarrow = 1, kQpWide = 2 };
+
+template <int N, int MODE>
 __device__ void solve_problem(int64_t p, const double* __restrict__ W, const double* __restrict__ xdes, const double* __restrict__ xmin,
                               const double* __restrict__ xmax, const int64_t* __restrict__ offs, const int32_t* __restrict__ cnt,
                               int32_t stride, const double* __restrict__ rows,
@@ -611,10 +619,15 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
     }
     const int m = k + (box ? N : 0);
     if (m > kQpMaxRows) { if (lane == 0) status[p] = kQpToHost; return; }
-    if (m <= 32)
-        solve_rows<N, 1>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
-    else
+    if constexpr (MODE == kQpWide) {                       // the narrow launch listed it: two rows per lane
         solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
+    } else if (m <= 32) {
+        solve_rows<N, 1>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
+    } else if constexpr (MODE == kQpNarrow) {
+        if (lane == 0) df.wide[atomicAdd(df.wide_n, 1u)] = (int32_t)p;
+    } else {
+        solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
+    }
 }
 
 // persistent warps: each draws the next problem from *counter (reset to 0 by the launcher).
@@ -623,7 +636,7 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
 // under the real limit -- the same arithmetic as an uncapped solve -- on another stream, and raises df.done[p] when
 // problem p's answer is in memory.  A launch lasts as long as its slowest problem; this keeps the 4000-iteration
 // stragglers (0.5 % of the problems) off the critical path of the other 99.5 %.
-template <int N>
+template <int N, int MODE>
 __global__ void __launch_bounds__(kQpWarps * 32, kQpCtasPerSm)
 k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__ xdes, const double* __restrict__ xmin,
          const double* __restrict__ xmax, const int64_t* __restrict__ offs, const int32_t* __restrict__ cnt, int32_t stride,
@@ -635,15 +648,16 @@ k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__
     double* kkt = scratch + (blockDim.x == 32 ? (size_t)blockIdx.x : (size_t)blockIdx.x * kQpWarps + (threadIdx.x >> 5)) * kQpScratch;
     __shared__ double s_kkt[kQpWarps][kQpSmemScratch];
     double* skkt = s_kkt[threadIdx.x >> 5];
-    const unsigned long long limit = df.only ? (unsigned long long)*df.only_n : (unsigned long long)nprob;
+    const unsigned long long limit = MODE == kQpWide ? (unsigned long long)*df.wide_n
+                                                     : (df.only ? (unsigned long long)*df.only_n : (unsigned long long)nprob);
     for (;;) {
         unsigned long long i = 0;
         if (lane == 0) i = atomicAdd(counter, 1ull);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= limit) return;
-        const int64_t p = df.only ? (int64_t)df.only[i] : (int64_t)i;
-        if (df.busy && df.busy[p] == 1) continue;
-        solve_problem<N>(p, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
+        const int64_t p = MODE == kQpWide ? (int64_t)df.wide[i] : (df.only ? (int64_t)df.only[i] : (int64_t)i);
+        if (MODE != kQpWide && df.busy && df.busy[p] == 1) continue;
+        solve_problem<N, MODE>(p, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
         if (df.only) {                                     // publish: answer first, flag second
             __threadfence();
             __syncwarp();
@@ -669,14 +683,19 @@ int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, con
     double* kkt = reinterpret_cast<double*>(scratch);
     unsigned long long* counter = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + sip_qp_scratch_bytes(num_sms) - 64);
     cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
-    if (n == 6)
-        k_sip_qp<6><<<blocks, threads, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, 1e-5,
-                                                      max_iter, kkt, counter, dx, status, df);
-    else if (n == 7)
-        k_sip_qp<7><<<blocks, threads, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, 1e-5,
-                                                      max_iter, kkt, counter, dx, status, df);
-    else
-        return -1;
+#define SIO_QP_LAUNCH(N, MODE)                                                                                                   \
+    k_sip_qp<N, MODE><<<blocks, threads, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, \
+                                                  1e-5, max_iter, kkt, counter, dx, status, df)
+    if (n != 6 && n != 7) return -1;
+    if (df.wide) {                                         // capped launch: narrow problems, then the ones it listed
+        cudaMemsetAsync(df.wide_n, 0, sizeof(uint32_t), st);
+        if (n == 6) SIO_QP_LAUNCH(6, kQpNarrow); else SIO_QP_LAUNCH(7, kQpNarrow);
+        cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+        if (n == 6) SIO_QP_LAUNCH(6, kQpWide); else SIO_QP_LAUNCH(7, kQpWide);
+    } else {
+        if (n == 6) SIO_QP_LAUNCH(6, kQpFull); else SIO_QP_LAUNCH(7, kQpFull);
+    }
+#undef SIO_QP_LAUNCH
     return 0;
 }
 
