@@ -24,6 +24,7 @@ namespace sio {
 
 constexpr int kQpWarps = 4;                 // warps per CTA
 constexpr int kQpCtasPerSm = 2;             // resident CTAs per SM the register budget is set for
+constexpr int kQpCtasNarrow = 3;            // the same for the one-row-per-lane build (168 registers)
 constexpr int kQpMaxRows = 64;              // 2 rows per lane
 constexpr int kQpMaxVars = 8;
 constexpr int kQpMaxKkt = kQpMaxVars + kQpMaxRows;     // largest polish system (x + active rows)
@@ -175,41 +176,57 @@ struct SpdInverse {
     }
 };
 
-// Gaussian elimination with partial pivoting on the NN x NN row-major system M x = b in the warp's scratch, rows
-// spread over the lanes.  Pivot choice (first largest |entry|) and the per-row arithmetic are those of the
-// host's serial routine, so the answer is the same.  Returns false on a zero pivot.  Result in b.
+// Gaussian elimination with partial pivoting on the NN x NN row-major system M x = b in the warp's scratch.  The pivot of
+// a column is its first largest |entry|, as in the host's serial routine (hostqp.c lu_solve), and each entry sees the same
+// operations in the same order, so the answer is the same.  Returns false on a zero pivot.  Result in b.
+// Every step is spread over the whole warp: the pivot search is two integer warp maxima over the bit patterns of the
+// (non-negative) magnitudes and an integer minimum over the rows that hold it; the elimination of column c runs over (row, column) pairs, lane = 8 * row
+// group + column group, with the multiplier of a row kept in the entry it annihilates; only the back substitution is
+// serial.  (One row per lane with a serial column loop left three lanes in four idle on a typical 12 x 12 system and
+// cost a sixth of the kernel's time: profiles/r02_qp_phases.md.)
 __device__ bool warp_lu_solve(double* M, double* b, int NN, int lane) {
+    const int lr = lane >> 3, lk = lane & 7;
     for (int c = 0; c < NN; ++c) {
-        double best = -1.0;
-        int pv = NN;
+        double v = -1.0;                                   // a NaN never wins, as in the host's comparison
+        int pr = NN;
         for (int r = c + lane; r < NN; r += 32) {
-            const double v = fabs(M[r * NN + c]);
-            if (v > best) { best = v; pv = r; }
+            const double a = fabs(M[r * NN + c]);
+            if (a > v) { v = a; pr = r; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int op = __shfl_xor_sync(0xffffffffu, pv, o);
-            if (ob > best || (ob == best && op < pv)) { best = ob; pv = op; }
-        }
-        if (!(best > 0.0)) return false;
+        const int hi = __double2hiint(v);
+        const int mhi = __reduce_max_sync(0xffffffffu, hi);
+        if (mhi < 0) return false;
+        const unsigned lo = (hi == mhi) ? (unsigned)__double2loint(v) : 0u;
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
+        if (mhi == 0 && mlo == 0u) return false;           // zero pivot
+        const int pv = __reduce_min_sync(0xffffffffu, (hi == mhi && lo == mlo) ? pr : 0x7fffffff);
         if (pv != c) {
-            for (int kk = lane; kk < NN; kk += 32) { const double t = M[c * NN + kk]; M[c * NN + kk] = M[pv * NN + kk]; M[pv * NN + kk] = t; }
-            if (lane == 0) { const double t = b[c]; b[c] = b[pv]; b[pv] = t; }
+            for (int kk = lane; kk <= NN; kk += 32) {
+                double* pc = kk < NN ? M + c * NN + kk : b + c;
+                double* pp = kk < NN ? M + pv * NN + kk : b + pv;
+                const double t = *pc; *pc = *pp; *pp = t;
+            }
         }
         __syncwarp();
-        const double piv = M[c * NN + c], bc = b[c];
-        for (int r = c + 1 + lane; r < NN; r += 32) {
-            const double f = M[r * NN + c] / piv;
+        const double piv = M[c * NN + c];
+        for (int r = c + 1 + lane; r < NN; r += 32) M[r * NN + c] = M[r * NN + c] / piv;     // the row's multiplier, in place
+        __syncwarp();
+        for (int r = c + 1 + lr; r < NN; r += 4) {
+            const double f = M[r * NN + c];
             if (f == 0.0) continue;
-            for (int kk = c; kk < NN; ++kk) M[r * NN + kk] -= f * M[c * NN + kk];
-            b[r] -= f * bc;
+#pragma unroll 2
+            for (int kk = c + 1 + lk; kk <= NN; kk += 8) {
+                double* dst = kk < NN ? M + r * NN + kk : b + r;
+                const double src = kk < NN ? M[c * NN + kk] : b[c];
+                *dst -= f * src;
+            }
         }
         __syncwarp();
     }
     if (lane == 0)
         for (int r = NN - 1; r >= 0; --r) {
             double s = b[r];
+#pragma unroll 4
             for (int kk = r + 1; kk < NN; ++kk) s -= M[r * NN + kk] * b[kk];
             b[r] = s / M[r * NN + r];
         }
@@ -637,7 +654,7 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
 // problem p's answer is in memory.  A launch lasts as long as its slowest problem; this keeps the 4000-iteration
 // stragglers (0.5 % of the problems) off the critical path of the other 99.5 %.
 template <int N, int MODE>
-__global__ void __launch_bounds__(kQpWarps * 32, kQpCtasPerSm)
+__global__ void __launch_bounds__(kQpWarps * 32, MODE == kQpNarrow ? kQpCtasNarrow : kQpCtasPerSm)
 k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__ xdes, const double* __restrict__ xmin,
          const double* __restrict__ xmax, const int64_t* __restrict__ offs, const int32_t* __restrict__ cnt, int32_t stride,
          const double* __restrict__ rows,
@@ -667,7 +684,7 @@ k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__
 }
 
 int sip_qp_grid(int num_sms) { return num_sms * kQpCtasPerSm; }           // 8 resident warps per SM at 255 registers: measured best (3 x 168 and 4 x 128 spill and run slower alone and loaded)
-size_t sip_qp_scratch_bytes(int num_sms) { return (size_t)sip_qp_grid(num_sms) * kQpWarps * kQpScratch * sizeof(double) + 64; }
+size_t sip_qp_scratch_bytes(int num_sms) { return (size_t)num_sms * kQpCtasNarrow * kQpWarps * kQpScratch * sizeof(double) + 64; }
 
 // scratch: sip_qp_scratch_bytes(num_sms) bytes; its last 64 bytes hold the work counter
 int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, const double* xmin, const double* xmax,
@@ -689,7 +706,10 @@ int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, con
     if (n != 6 && n != 7) return -1;
     if (df.wide) {                                         // capped launch: narrow problems, then the ones it listed
         cudaMemsetAsync(df.wide_n, 0, sizeof(uint32_t), st);
-        if (n == 6) SIO_QP_LAUNCH(6, kQpNarrow); else SIO_QP_LAUNCH(7, kQpNarrow);
+        {
+            const int blocks = num_sms * kQpCtasNarrow;
+            if (n == 6) SIO_QP_LAUNCH(6, kQpNarrow); else SIO_QP_LAUNCH(7, kQpNarrow);
+        }
         cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
         if (n == 6) SIO_QP_LAUNCH(6, kQpWide); else SIO_QP_LAUNCH(7, kQpWide);
     } else {
