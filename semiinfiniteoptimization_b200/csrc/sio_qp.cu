@@ -46,6 +46,20 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// Maxima of NON-NEGATIVE doubles through their bit patterns, which order like the values: three or four integer
+// instructions where fmax's NaN handling costs seven, and a warp maximum in two integer warp reductions (high words, then
+// low words among the lanes that hold the largest high word) where a shuffle butterfly takes five dependent levels.  A
+// NaN orders above everything here (fmax drops it): the residual tests then fail and the solve runs to its iteration limit.
+__device__ __forceinline__ double max_nn(double a, double b) {
+    return __longlong_as_double(max(__double_as_longlong(a), __double_as_longlong(b)));
+}
+__device__ __forceinline__ double warp_max_nn(double v) {
+    const int hi = __double2hiint(v);
+    const int mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, (hi == mhi) ? (unsigned)__double2loint(v) : 0u);
+    return __hiloint2double(mhi, (int)mlo);
+}
+
 // Sum (or maximum) over the warp of M (<= 8) doubles per lane, delivered to every lane.  A butterfly per value costs
 // 5 M 64-bit shuffles; here three halving steps (xor 16, 8, 4: a lane keeps one half of its values and ships the
 // other) leave one value per lane, two butterfly levels finish it inside each group of four lanes, and M broadcasts
@@ -337,10 +351,12 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
     for (int s = 0; s < NR; ++s) sv[s] = 0.0;
     if (__any_sync(0xffffffffu, !set_rho())) return kAdmmMaxIter;
     int st = kAdmmMaxIter;
+    int to_check = check_every;                              // iterations to the next multiple of check_every
     for (int it = 1; it <= max_iter; ++it) {
         ++iters;
-        double xt[N], w[NR], stl[NR];
-        const bool chk = !((it % check_every) && it != max_iter);       // residual test this iteration (qp.py: every 10)
+        double xt[N], w[NR], stl[NR], yold[NR];
+        const bool chk = --to_check == 0 || it == max_iter;             // residual test this iteration (qp.py: every 10)
+        if (to_check == 0) to_check = check_every;
         {
             double part[8];
 #pragma unroll
@@ -369,19 +385,21 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
             }
             const double zr = alpha * zs + (1.0 - alpha) * z[s];
             const double cc = zr + y[s] * irv[s];
-            const double zn = fmin(fmax(cc, R.l[s]), R.u[s]);
+            const double zn = cc < R.l[s] ? R.l[s] : (cc > R.u[s] ? R.u[s] : cc);     // l <= u
             const double yn = y[s] + rv[s] * (zr - zn);
-            if (chk) {                                        // only the infeasibility certificate reads dy
-                dy[s] = R.have[s] ? yn - y[s] : 0.0;
-                ndy = fmax(ndy, fabs(dy[s]));
-            }
+            yold[s] = y[s];
             if (R.have[s]) { z[s] = zn; y[s] = yn; }
             if (SLACK && R.slack[s]) sv[s] = alpha * stl[s] + (1.0 - alpha) * sv[s];
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = alpha * xt[i] + (1.0 - alpha) * x[i];
         if (!chk) continue;
-        // residuals (qp.py solve_qp: every 10 iterations).  The six lane-local maxima travel in one reduction.
+#pragma unroll
+        for (int s = 0; s < NR; ++s) {                       // only the infeasibility certificate reads dy
+            dy[s] = y[s] - yold[s];                          // 0 on absent rows: their y never moves
+            ndy = max_nn(ndy, fabs(dy[s]));
+        }
+        // residuals (qp.py solve_qp: every 10 iterations)
         double mx[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};       // r_prim, |Ax| / |z|, slack dual residual, its scale, |dy|, |dy| over slack rows
         double Aty[N];
 #pragma unroll
@@ -394,15 +412,16 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
             if (SLACK && R.slack[s]) {
                 v += sv[s];
                 const double ps = pen * sv[s];                          // dual residual of the slack variable: pen s + y
-                mx[2] = fmax(mx[2], fabs(ps + y[s]));
-                mx[3] = fmax(mx[3], fmax(fabs(ps), fabs(y[s])));
-                mx[5] = fmax(mx[5], fabs(dy[s]));
+                mx[2] = max_nn(mx[2], fabs(ps + y[s]));
+                mx[3] = max_nn(mx[3], max_nn(fabs(ps), fabs(y[s])));
+                mx[5] = max_nn(mx[5], fabs(dy[s]));
             }
             Ax[s] = v;
-            if (R.have[s]) { mx[0] = fmax(mx[0], fabs(v - z[s])); mx[1] = fmax(mx[1], fmax(fabs(v), fabs(z[s]))); }
+            if (R.have[s]) { mx[0] = max_nn(mx[0], fabs(v - z[s])); mx[1] = max_nn(mx[1], max_nn(fabs(v), fabs(z[s]))); }
         }
         mx[4] = ndy;
-        AllMax<6>::all(mx, lane);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) mx[i] = warp_max_nn(mx[i]);
         AllSum<N>::all(Aty, lane);
         const double r_prim = mx[0], nAx = mx[1];
         double r_dual = mx[2], nd = mx[3];
@@ -411,8 +430,8 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
         for (int i = 0; i < N; ++i) {
             const double t = Aty[i];
             const double px = Pd[i] * x[i];
-            r_dual = fmax(r_dual, fabs(px + q[i] + t));
-            nd = fmax(nd, fmax(fabs(px), fmax(fabs(t), fabs(q[i]))));
+            r_dual = max_nn(r_dual, fabs(px + q[i] + t));
+            nd = max_nn(nd, max_nn(fabs(px), max_nn(fabs(t), fabs(q[i]))));
         }
         if (__all_sync(0xffffffffu, r_prim <= eps_abs + eps_rel * nAx && r_dual <= eps_abs + eps_rel * nd)) { st = kAdmmSolved; break; }
         if (__all_sync(0xffffffffu, ndy > 1e-12)) {       // primal infeasibility certificate
@@ -430,7 +449,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
             AllSum<N + 1>::all(t, lane);
             double nAt = mx[5] * indy;                      // the slack columns of A' dy
 #pragma unroll
-            for (int i = 0; i < N; ++i) nAt = fmax(nAt, fabs(t[i]));
+            for (int i = 0; i < N; ++i) nAt = max_nn(nAt, fabs(t[i]));
             if (__all_sync(0xffffffffu, nAt <= 1e-4 && t[N] < -1e-4)) { st = kAdmmInfeasible; break; }
         }
         if (it % adapt_every == 0 && __all_sync(0xffffffffu, r_prim > 0 && r_dual > 0)) {
