@@ -331,7 +331,8 @@ def sip_leg(ctx, rank, world, want_cpu):
            "qp_device_s_per_rank": float(rec[3].item()) / world, "other_s_per_rank": wall - float(rec[2].item() + rec[3].item()) / world,
            "library_call_s_rank0": float(res.time), "gather_s_rank0": wall_local - solve_s,
            "limiting_term": "in-line QP launches (k_sip_qp): a launch lasts as long as its slowest problem under the 800-iteration "
-                            "budget (0.34 ms) plus ~(problems per rank / 1,184 resident warps) x 77 us of ADMM per problem, so it shrinks "
+                            "budget (0.34 ms) plus ~(problems per rank / 1,776 resident warps) x 160 us of ADMM + polish per problem (12 warps share "
+                            "an SM; profiles/r02_qp_phases.md), so it shrinks "
                             "less than linearly with the shard; then the fixed per-round host sequencing (2 counter read-backs, ~12 launches)",
            "oracle_point_queries_resolved": int(rec[4].item()), "started_in_collision": int(rec[6].item()),
            "ended_feasible(g>-5e-3)": int(rec[5].item())}
