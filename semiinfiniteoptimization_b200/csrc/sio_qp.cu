@@ -349,10 +349,39 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
     for (int i = 0; i < N; ++i) x[i] = 0.0;
 #pragma unroll
     for (int s = 0; s < NR; ++s) sv[s] = 0.0;
-    if (__any_sync(0xffffffffu, !set_rho())) return kAdmmMaxIter;
+    // set_rho's unrolled body is a quarter of the solver's instructions and the kernel is bound by instruction fetch
+    // outside its iteration loop (profiles/r02_qp_phases.md), so it exists ONCE: an outer loop per value of rho, the
+    // iteration loop inside.  The iterate is parked in the warp's (otherwise idle) polish scratch across the call --
+    // left to the compiler it stays live in registers and every problem's first refactorisation pays the spills.
+    static_assert((5 * NR + N) * 32 <= kQpSmemScratch, "the parked iterate fits the polish scratch");
+    double* const nook = skkt + lane;
+    auto park = [&]() {
+#pragma unroll
+        for (int s = 0; s < NR; ++s) {
+            nook[(5 * s + 0) * 32] = z[s]; nook[(5 * s + 1) * 32] = y[s]; nook[(5 * s + 2) * 32] = sv[s];
+            nook[(5 * s + 3) * 32] = dy[s]; nook[(5 * s + 4) * 32] = Ax[s];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) nook[(5 * NR + i) * 32] = x[i];
+    };
+    auto unpark = [&]() {
+#pragma unroll
+        for (int s = 0; s < NR; ++s) {
+            z[s] = nook[(5 * s + 0) * 32]; y[s] = nook[(5 * s + 1) * 32]; sv[s] = nook[(5 * s + 2) * 32];
+            dy[s] = nook[(5 * s + 3) * 32]; Ax[s] = nook[(5 * s + 4) * 32];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = nook[(5 * NR + i) * 32];
+    };
+    park();
     int st = kAdmmMaxIter;
     int to_check = check_every;                              // iterations to the next multiple of check_every
-    for (int it = 1; it <= max_iter; ++it) {
+    for (int it = 1;;) {
+    const bool refactored = !__any_sync(0xffffffffu, !set_rho());
+    unpark();
+    if (!refactored) break;
+    bool new_rho = false;
+    for (; it <= max_iter; ++it) {
         ++iters;
         double xt[N], w[NR], stl[NR], yold[NR];
         const bool chk = --to_check == 0 || it == max_iter;             // residual test this iteration (qp.py: every 10)
@@ -456,9 +485,14 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
             const double scale = sqrt((r_prim / fmax(nAx, 1e-12)) / (r_dual / fmax(nd, 1e-12)));
             if (__all_sync(0xffffffffu, scale > 5 || scale < 0.2)) {
                 rho = fmin(fmax(rho * scale, 1e-6), 1e6);
-                if (__any_sync(0xffffffffu, !set_rho())) break;
+                park();
+                new_rho = true;
+                ++it;
+                break;
             }
         }
+    }
+    if (!new_rho) break;
     }
     if (st != kAdmmSolved) return st;
     // ---- polish on the active set (qp.py _polish): KKT system over [variables | active rows] ----------------
