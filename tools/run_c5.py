@@ -83,6 +83,8 @@ elif a.qp in ("device", "host"):
 else:
     res = batch.optimizeCollFreeBatch(cube, scene, mine[:nb], settings=st, qp=a.qp)
 wall = time.time() - t0
+if os.environ.get("SIO_C5_DUMP"):                         # development aid: the per-problem records, for A/B comparisons
+    np.save(os.environ["SIO_C5_DUMP"], np.asarray(res.records()))
 rec = torch.tensor([res.outer_iterations, wall, res.time_cons, res.time_qp, res.point_queries, float((res.gx > -5e-3).sum()), nb], dtype=torch.float64, device="cuda")
 gathered = None
 if world > 1:
