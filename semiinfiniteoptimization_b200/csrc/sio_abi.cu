@@ -86,6 +86,7 @@ struct GridH {
     bool live = false;
     float* d_v = nullptr;
     float* d_brick = nullptr;
+    uint8_t* d_lipd = nullptr;
     GridDev meta{};
     GridDev* d_meta = nullptr;     // single-element device copy (K1 kernels take a pointer)
 };
@@ -252,7 +253,7 @@ int sio_ctx_destroy(sio_ctx* c) {
     DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
     for (int k = 0; k < sio_ctx::kLsBack; ++k) if (c->ls_stream[k]) cudaStreamSynchronize(c->ls_stream[k]);
-    for (auto& g : c->grids) if (g.live) { cudaFree(g.d_v); cudaFree(g.d_brick); cudaFree(g.d_meta); }
+    for (auto& g : c->grids) if (g.live) { cudaFree(g.d_v); cudaFree(g.d_brick); cudaFree(g.d_lipd); cudaFree(g.d_meta); }
     for (auto& p : c->clouds) if (p.live) { cudaFree(p.d_pts); cudaFree(p.d_rep); cudaFree(p.d_perm); }
     for (auto& r : c->robots) if (r.live) { cudaFree(r.d_parent); cudaFree(r.d_jtype); cudaFree(r.d_tparent); cudaFree(r.d_axis); }
     c->s_qp.release();
@@ -399,6 +400,7 @@ int sio_grid_create(sio_ctx* c, const float* values, const int32_t dims[3], cons
     // |difference| / hx (likewise y, z), so sqrt of the sum of squares bounds the gradient norm there; take the
     // maximum over cells.  Used only by the sub-tile culling (a valid bound keeps pruned results exact).
     double lip = 0.0;
+    std::vector<uint8_t> lipq((size_t)kLipLevels * nx * ny * nz);       // local constants, see GridDev::lipd
     {
         const double hx = (bmax[0] - bmin[0]) / nx, hy = (bmax[1] - bmin[1]) / ny, hz = (bmax[2] - bmin[2]) / nz;
         for (size_t cidx = 0, nc = (size_t)nx * ny * nz; cidx < nc; ++cidx) {
@@ -410,7 +412,28 @@ int sio_grid_create(sio_ctx* c, const float* values, const int32_t dims[3], cons
                 ez = std::max(ez, (double)std::fabs(q[2 * m + 1] - q[2 * m]));               // z-edges
             }
             ex /= hx; ey /= hy; ez /= hz;
-            lip = std::max(lip, std::sqrt(ex * ex + ey * ey + ez * ez));
+            const double lc = std::sqrt(ex * ex + ey * ey + ez * ez);
+            lip = std::max(lip, lc);
+            const double q64 = std::ceil(lc * (1.0 + 1e-6) * 64.0 + 1e-4);        // rounded up: stays a bound
+            lipq[cidx] = (uint8_t)(q64 < 255.0 ? q64 : 255.0);                    // 255 = fall back to the global constant
+        }
+        // level D = the maximum over the cells within D cells (Chebyshev): D dilations by one cell, each separable
+        const size_t nc = (size_t)nx * ny * nz;
+        std::vector<uint8_t> cur(lipq.begin(), lipq.begin() + nc), tmp(nc);
+        const int dims[3] = {nx, ny, nz};
+        const size_t strides[3] = {(size_t)ny * nz, (size_t)nz, 1};
+        for (int D = 1; D <= kLipLevels; ++D) {
+            for (int ax = 0; ax < 3; ++ax) {
+                for (size_t i = 0; i < nc; ++i) {
+                    const int pos = (int)((i / strides[ax]) % dims[ax]);
+                    uint8_t m = cur[i];
+                    if (pos > 0) m = std::max(m, cur[i - strides[ax]]);
+                    if (pos + 1 < dims[ax]) m = std::max(m, cur[i + strides[ax]]);
+                    tmp[i] = m;
+                }
+                cur.swap(tmp);
+            }
+            std::copy(cur.begin(), cur.end(), lipq.begin() + (size_t)(D - 1) * nc);
         }
     }
     // corner samples -> monomial coefficients (Moebius transform per axis bit, in float64)
@@ -429,6 +452,9 @@ int sio_grid_create(sio_ctx* c, const float* values, const int32_t dims[3], cons
     g.meta.lip = (float)(lip * (1.0 + 1e-6)) + 1e-6f;
     CU(cudaMalloc(&g.d_v, pad.size() * sizeof(float)));
     CU(cudaMemcpyAsync(g.d_v, pad.data(), pad.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMalloc(&g.d_lipd, lipq.size()));
+    CU(cudaMemcpyAsync(g.d_lipd, lipq.data(), lipq.size(), cudaMemcpyHostToDevice, c->stream));
+    g.meta.lipd = g.d_lipd;
     CU(cudaMalloc(&g.d_brick, brick.size() * sizeof(float)));
     CU(cudaMemcpyAsync(g.d_brick, brick.data(), brick.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     g.meta.v = g.d_v;
@@ -455,7 +481,7 @@ int sio_grid_destroy(sio_ctx* c, sio_handle h) {
     DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
     g_realloc_gen.fetch_add(1);
-    cudaFree(c->grids[h].d_v); cudaFree(c->grids[h].d_brick); cudaFree(c->grids[h].d_meta);
+    cudaFree(c->grids[h].d_v); cudaFree(c->grids[h].d_brick); cudaFree(c->grids[h].d_lipd); cudaFree(c->grids[h].d_meta);
     c->grids[h] = GridH();
     c->staged_grids.clear();
     return SIO_OK;

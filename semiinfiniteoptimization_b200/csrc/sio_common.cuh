@@ -26,7 +26,11 @@ struct GridDev {
     double bmin[3], bmax[3], h[3], ih[3];   // ih = 1/h (host-computed: no fp64 divides on the device)
     float vmin, vmax;            // range of the samples
     float lip;                   // Lipschitz constant of the trilinear interpolant w.r.t. local position
+    // LOCAL Lipschitz constants for the sub-tile culling: lipd[(D-1) * ncell + cell] = ceil(64 * the largest per-cell
+    // constant among the cells within D cells (Chebyshev, D = 1 .. kLipLevels) of `cell`), 255 = use `lip`
+    const uint8_t* lipd;
 };
+constexpr int kLipLevels = 8;
 
 // fp32 transform record of one query b: cloud-local point -> dual-lattice cell coordinates
 // u = M p + t  (grid affine (p - bmin)/h - 1/2 folded in), plus what the inner loop needs.
@@ -39,8 +43,11 @@ struct __align__(16) XfRec {
     const float* v;              // the grid's bricks (monomial coefficients)
     int32_t sy;                  // cell stride in y: nz
     float lip;                   // Lipschitz constant of the grid's interpolant (sub-tile culling)
+    const uint8_t* lipd;         // the grid's local constants (GridDev::lipd), or null
+    int32_t ncell;               // cells per level of lipd
+    float ihmin;                 // 1 / (smallest cell size), rounded up
 };
-static_assert(sizeof(XfRec) == 96, "XfRec layout");
+static_assert(sizeof(XfRec) == 112, "XfRec layout");
 
 // candidate / under-bound record.  The fp32 pass writes (b, internal index, float d); the fp64
 // re-check rewrites it in place to (b or -1, caller index, exact d).

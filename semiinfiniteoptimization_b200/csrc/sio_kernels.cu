@@ -129,6 +129,25 @@ __device__ __forceinline__ GridK grid_of(const XfRec& r) {
     return g;
 }
 
+// Lipschitz constant of the interpolant over a sphere (centre at lattice coordinates u, radius rad in metres): the
+// largest per-cell constant among the cells the sphere can touch.  Along an axis the sphere spans rad / h cells either
+// way, so those cells lie within D = ceil(rad / min h) cells of the centre's cell (clamping the coordinates into the
+// lattice is monotone and 1-Lipschitz, so this also holds for spheres that leave it; 1/256 cell of slack covers the
+// float32 rounding of u, ~1e-5 cells); the grid carries the maxima over such neighbourhoods for D = 1 .. kLipLevels.
+// On an SDF the global constant is set by a few cells on the medial axis (sqrt 3 for a box) while the field is
+// 1-Lipschitz almost everywhere: on BASELINE configs[1] (the chair) the cull keeps 3.5 % of the sub-tiles with the local
+// bound where the global one kept 17 %.
+__device__ __forceinline__ float local_lipschitz(const XfRec& r, const GridK& g, float ux, float uy, float uz, float rad) {
+    if (!r.lipd) return r.lip;
+    const float rho = __fmul_ru(rad, r.ihmin) + 0.00390625f;
+    if (!(rho <= (float)kLipLevels)) return r.lip;
+    const int D = max(1, (int)ceilf(rho));
+    const uint32_t ix = (uint32_t)fminf(fmaxf(ux, 0.0f), g.hix), iy = (uint32_t)fminf(fmaxf(uy, 0.0f), g.hiy),
+                   iz = (uint32_t)fminf(fmaxf(uz, 0.0f), g.hiz);
+    const uint32_t q = __ldg(r.lipd + (size_t)(D - 1) * (uint32_t)r.ncell + (ix * g.cx + iy * g.cz + iz));
+    return q == 255u ? r.lip : (float)q * (1.0f / 64.0f);
+}
+
 // Is the bounding sphere (centre p, radius p.w, cloud-local) of a group of points, mapped by the
 // transform of record r, entirely inside the sample lattice [0, dim-1]^3?  Then every point of the
 // group takes the unclamped path.  Row a of M has norm 1/h_a, so the sphere spans r/h_a cells on axis a;
@@ -203,7 +222,7 @@ __device__ __forceinline__ XfRec make_xf(const GridDev& g, const double* T, floa
     }
     r.hx = (float)g.h[0]; r.hy = (float)g.h[1]; r.hz = (float)g.h[2];
     r.hix = (float)(g.nx - 1); r.hiy = (float)(g.ny - 1); r.hiz = (float)(g.nz - 1);
-    r.sx = g.ny * g.nz; r.sy = g.nz; r.v = g.brick; r.lip = g.lip;
+    r.sx = g.ny * g.nz; r.sy = g.nz; r.v = g.brick; r.lip = g.lip; r.lipd = g.lipd; r.ncell = g.nx * g.ny * g.nz; r.ihmin = __frcp_ru(fminf(r.hx, fminf(r.hy, r.hz)));
     r.thr = thr;
     return r;
 }
@@ -569,7 +588,7 @@ k_prune_centres(const float4* __restrict__ rep, int64_t nsub, const XfRec* __res
         float mx = fminf(ux + 0.5f, g.hix + 0.5f - ux) * g.hx;
         float my = fminf(uy + 0.5f, g.hiy + 0.5f - uy) * g.hy;
         float mz = fminf(uz + 0.5f, g.hiz + 0.5f - uz) * g.hz;
-        float L = r.lip + ((min3(mx, my, mz) >= p.w) ? 0.0f : 1.0f);
+        float L = local_lipschitz(r, g, ux, uy, uz, p.w) + ((min3(mx, my, mz) >= p.w) ? 0.0f : 1.0f);
         tile[tid][bl] = dc - L * p.w;
         if (ok) subkeys[(b0 + bl) * nsub + s] = 0x7f800000u;
         uint32_t k = __reduce_min_sync(0xffffffffu, ok ? fkey(dc) : 0xffffffffu);
