@@ -675,13 +675,17 @@ k_min_items(const float4* __restrict__ pts, const float4* __restrict__ rep, cons
     f32x2 PX[kPtsPerThread / 2], PY[kPtsPerThread / 2], PZ[kPtsPerThread / 2];      // the same points as register pairs
     float4 sphere = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t have = 0xffffffffu;                           // sub-tile whose points sit in registers
-    for (uint32_t it0 = (blockIdx.x * (kThreads / 32) + warp) * kItemRun; it0 < n; it0 += nwarps * kItemRun) {
+    // runs of up to kItemRun items; shorter when there are few items per warp (a 64-pose sweep leaves 4 per warp: at
+    // 16 to a run three warps in four would idle while the fourth walks its run one dependent item after the other)
+    const uint32_t run = max(1u, min((uint32_t)kItemRun, (n + nwarps - 1) / nwarps));
+    for (uint32_t it0 = (blockIdx.x * (kThreads / 32) + warp) * run; it0 < n; it0 += nwarps * run) {
         // the run's items and transform records arrive together: one dependent round trip per run, not per item
-        const int cnt = (int)min(n - it0, (uint32_t)kItemRun);
+        const int cnt = (int)min(n - it0, run);
         const uint32_t e_l = lane < cnt ? __ldg(items + it0 + lane) : 0u;
         __syncwarp();
 #pragma unroll
         for (int q0 = 0; q0 < kItemRun * kRecParts; q0 += 32) {
+            if (q0 >= cnt * kRecParts) break;              // warp-uniform
             const int q = q0 + lane, rec = q / kRecParts;
             const uint32_t e = __shfl_sync(0xffffffffu, e_l, rec & (kItemRun - 1));
             if (rec < cnt)
