@@ -199,7 +199,7 @@ int sio_robot_pairs_min_distance(sio_ctx* ctx, sio_handle robot, const sio_handl
  * when either differs from the previous call's).  T_init / T_des / T_out are row-major 3x4 poses of the moving body.
  * Per problem: status (1 = 'local optimum', 0 = iteration limit), iterations, f(x), g(x) = min over instantiated
  * parameters, g at the start, number of instantiated parameters and (optional) the parameters themselves
- * [B*cap*3].  status 2 = the problem's QP had no solution, not even with slack variables (the reference fails there,
+ * [B*cap*3]: the first n_params[p] points of row p are written, the rest of the row is left as it was.  status 2 = the problem's QP had no solution, not even with slack variables (the reference fails there,
  * sip.py:358-378); the problem stops at its current pose.  stats[0..5] = outer iterations, point queries resolved by
  * the sweeps, device microseconds in the in-line QP launches, parameters that did not fit into `cap` slots, device
  * microseconds in the sweeps, problems stopped with status 2.

@@ -11,6 +11,7 @@
 #include <mutex>
 #include <string>
 #include <chrono>
+#include <thread>
 #include <vector>
 
 #include "../../include/sio_abi.h"
@@ -140,7 +141,8 @@ struct sio_ctx {
     int n_icnt = 0;                   // batches of the last pruned call (their survivor counts sit in h_icnt)
     int64_t prune_total = 0;          // (transform, sub-tile) pairs of the last pruned call
     DevBuf s_xf, s_keys, s_gridtab, s_cand, s_cnt, s_in0, s_in1, s_in2, s_in3, s_out0, s_out1, s_out2, s_tlinks, s_trel, s_gob;
-    HostBuf h_a, h_b, h_c, h_cnt;
+    HostBuf h_a, h_b, h_c, h_cnt, h_ls, h_ls_out, h_ls_pack;
+    DevBuf s_ls_pack;
     uint32_t cand_cap = 1u << 20;     // under-bound candidate records the buffer holds (sio_ctx_set_under_capacity; host entry points grow it)
     GridDev single_grid_host{};       // host copy handed to the single-grid bulk kernel by value
     std::vector<sio_handle> staged_grids;   // handles whose table currently sits in s_gridtab (grids are immutable)
@@ -174,6 +176,16 @@ bool robot_ok(sio_ctx* c, sio_handle h) { return h >= 0 && (size_t)h < c->robots
 // Wait for a stream the way a latency-bound caller wants it: the single-problem paths (PenetrationDepthGeometry.distance,
 // value / df_dx batches of a few points) wait for ~10-100 us of device work per call, and a blocking
 // cudaStreamSynchronize costs 10-20 us of wake-up latency on top.  Poll for up to ~0.5 ms, then block.
+// the same without giving up: for loops that wait for milliseconds of device work many times over (the lock-step solver)
+inline cudaError_t spin_stream(cudaStream_t st) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        const cudaError_t e = cudaStreamQuery(st);
+        if (e != cudaErrorNotReady) return e;
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(200)) break;    // something is wrong or huge: block
+    }
+    return cudaStreamSynchronize(st);
+}
 inline cudaError_t wait_stream(cudaStream_t st) {
     const auto t0 = std::chrono::steady_clock::now();
     for (;;) {
@@ -265,7 +277,7 @@ int sio_ctx_destroy(sio_ctx* c) {
     DevBuf* bufs[] = {&c->s_xf, &c->s_keys, &c->s_gridtab, &c->s_cand, &c->s_cnt, &c->s_in0, &c->s_in1, &c->s_in2, &c->s_in3,
                       &c->s_out0, &c->s_out1, &c->s_out2, &c->s_tlinks, &c->s_trel, &c->s_gob};
     for (auto* b : bufs) b->release();
-    c->h_a.release(); c->h_b.release(); c->h_c.release(); c->h_cnt.release();
+    c->h_a.release(); c->h_b.release(); c->h_c.release(); c->h_cnt.release(); c->h_ls.release(); c->h_ls_out.release(); c->h_ls_pack.release(); c->s_ls_pack.release();
     cudaEventDestroy(c->ev_bulk0); cudaEventDestroy(c->ev_bulk1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1123,6 +1135,7 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
             probe.take<uint32_t>(sio_ctx::kLsRing);
             probe.take<int32_t>(B);
             probe.take<uint32_t>(1);
+            probe.take<double>(24 * B);
         });
         CU(c->s_ls.ensure(need + 4096));                  // kept by the context: releasing ~350 MB per call cost tens of ms
         A.base = c->s_ls.as<char>();
@@ -1132,11 +1145,13 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     uint32_t* dcount = nullptr;
     int32_t* wlist = nullptr;                              // problems of the current round with more than 32 QP rows
     uint32_t* wcount = nullptr;
+    double* raw_poses = nullptr;                           // T_init, T_des as handed over; unpacked on the device
     carve(A, S, B, cap, [&] {
         for (int k = 0; k < sio_ctx::kLsRing; ++k) dlist[k] = A.take<int32_t>(B);
         dcount = A.take<uint32_t>(sio_ctx::kLsRing);
         wlist = A.take<int32_t>(B);
         wcount = A.take<uint32_t>(1);
+        raw_poses = A.take<double>(24 * B);
     });
     {
         const bool same = c->ls_cloud_h == cloud && c->s_ls_cloud.p && std::memcmp(c->ls_cloud_T, T_env, sizeof(c->ls_cloud_T)) == 0;
@@ -1151,20 +1166,9 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     }
     S.cloud_world = d_cloud;
     S.grid = c->grids[grid].d_meta;
-    // poses: row-major 3x4 -> R (3x3) and t
-    {
-        std::vector<double> hR((size_t)B * 9), ht((size_t)B * 3), hRd((size_t)B * 9), htd((size_t)B * 3);
-        for (int64_t p = 0; p < B; ++p)
-            for (int i = 0; i < 3; ++i) {
-                for (int j = 0; j < 3; ++j) { hR[9 * p + 3 * i + j] = T_init[12 * p + 4 * i + j]; hRd[9 * p + 3 * i + j] = T_des[12 * p + 4 * i + j]; }
-                ht[3 * p + i] = T_init[12 * p + 4 * i + 3]; htd[3 * p + i] = T_des[12 * p + 4 * i + 3];
-            }
-        CU(cudaMemcpyAsync(S.R, hR.data(), hR.size() * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(S.t, ht.data(), ht.size() * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(S.Rdes, hRd.data(), hRd.size() * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(S.tdes, htd.data(), htd.size() * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));                     // the staging vectors die here
-    }
+    // poses: two copies as they are (row-major 3x4); R (3x3) and t are split out on the device
+    CU(cudaMemcpyAsync(raw_poses, T_init, (size_t)B * 12 * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(raw_poses + 12 * B, T_des, (size_t)B * 12 * 8, cudaMemcpyHostToDevice, st));
     LsSettings L{};
     L.max_iters = cfg->max_iters; L.cap = cap;
     L.xeps2 = cfg->xepsilon * cfg->xepsilon * 2;           // len((R,t)) == 2 in the reference (sip.py:836-837)     quirk
@@ -1173,9 +1177,14 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     L.excl = cfg->parameter_exclusion_distance; L.reg = cfg->qp_regularization;
     CU(cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long), st));
     CU(cudaMemsetAsync(S.key, 0, (size_t)B * cap * 3 * sizeof(long long), st));
+    ls_launch_unpack_poses(S, raw_poses, st);
     ls_launch_init(S, L, st);
     CU(c->s_qp.ensure(sip_qp_scratch_bytes(c->num_sms)));
-    unsigned long long hc[6];
+    // the loop's counters come back twice per round into pinned memory (a pageable destination makes the "async" copy a
+    // staged, synchronous one), and the host SPINS on the stream for them: a blocking synchronise adds tens of
+    // microseconds of wake-up latency per read-back, 128 of them per solve, with the device idle meanwhile
+    CU(c->h_ls.ensure(8 * sizeof(unsigned long long)));
+    unsigned long long* const hc = c->h_ls.as<unsigned long long>();
     int64_t queries = 0;
     // device time of the QP launches and of the sweeps, read back at the end (events per iteration)
     struct EventBag {                                      // destroyed on every way out of the call
@@ -1201,9 +1210,9 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - entry0).count());
     }
     auto read_counters = [&]() -> cudaError_t {
-        cudaError_t e = cudaMemcpyAsync(hc, S.counters, sizeof(hc), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaMemcpyAsync(hc, S.counters, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return e;
-        return cudaStreamSynchronize(st);
+        return spin_stream(st);
     };
     auto sweep = [&](int64_t n) -> int {                   // K2 over the queued problems: minimum / arg-minimum only
         queries += n * N;
@@ -1340,23 +1349,71 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     if (defer)
         for (int k = 0; k < sio_ctx::kLsBack; ++k) CU(cudaStreamSynchronize(c->ls_stream[k]));
     CU(read_counters());
-    // results
-    std::vector<double> hR((size_t)B * 9), ht((size_t)B * 3);
-    CU(cudaMemcpyAsync(hR.data(), S.R, hR.size() * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(ht.data(), S.t, ht.size() * 8, cudaMemcpyDeviceToHost, st));
-    if (status) CU(cudaMemcpyAsync(status, S.status, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-    if (iterations) CU(cudaMemcpyAsync(iterations, S.niter, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-    if (fx) CU(cudaMemcpyAsync(fx, S.fx, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-    if (gx) CU(cudaMemcpyAsync(gx, S.gx, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-    if (gx0) CU(cudaMemcpyAsync(gx0, S.gx0, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-    if (n_params) CU(cudaMemcpyAsync(n_params, S.cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-    if (params) CU(cudaMemcpyAsync(params, S.P, (size_t)B * cap * 3 * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    for (int64_t p = 0; p < B; ++p)
-        for (int i = 0; i < 3; ++i) {
-            for (int j = 0; j < 3; ++j) T_out[12 * p + 4 * i + j] = hR[9 * p + 3 * i + j];
-            T_out[12 * p + 4 * i + 3] = ht[3 * p + i];
+    const auto loop1 = std::chrono::steady_clock::now();
+    // results.  Everything comes back through ONE pinned block kept by the context, and the instantiated parameters
+    // PACKED (a device gather of the cnt[p] points per problem: a quarter of the B * cap * 3 dense array on BASELINE
+    // configs[4]); worker threads then spread the rows over the caller's arrays.  Copying the dense array straight into
+    // the caller's freshly allocated memory took 24 ms of a 260 ms solve -- page faults, mostly.
+    {
+        const size_t oR = 0, ot = oR + (size_t)B * 9 * 8, ofx = ot + (size_t)B * 3 * 8, ogx = ofx + (size_t)B * 8, og0 = ogx + (size_t)B * 8;
+        const size_t ost = og0 + (size_t)B * 8, oit = ost + (size_t)B * 4, ocn = oit + (size_t)B * 4, small = ocn + (size_t)B * 4;
+        CU(c->h_ls_out.ensure(small));
+        char* hb = c->h_ls_out.as<char>();
+        CU(cudaMemcpyAsync(hb + oR, S.R, (size_t)B * 9 * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hb + ot, S.t, (size_t)B * 3 * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hb + ofx, S.fx, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hb + ogx, S.gx, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hb + og0, S.gx0, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hb + ost, S.status, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hb + oit, S.niter, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hb + ocn, S.cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+        CU(spin_stream(st));
+        const double* hR = reinterpret_cast<const double*>(hb + oR);
+        const double* ht = reinterpret_cast<const double*>(hb + ot);
+        const int32_t* hcnt = reinterpret_cast<const int32_t*>(hb + ocn);
+        std::vector<int64_t> offs;
+        int64_t total = 0;
+        const double* hpk = nullptr;
+        if (params) {
+            offs.resize((size_t)B + 1);
+            for (int64_t p = 0; p < B; ++p) { offs[p] = total; total += std::max(0, std::min<int32_t>(hcnt[p], cap)); }
+            offs[B] = total;
+            // sized for full rows: a second solve of the same batch never re-allocates (pinned allocations cost milliseconds)
+            CU(c->s_ls_pack.ensure((size_t)B * 8 + (size_t)B * cap * 24));
+            CU(c->h_ls_pack.ensure((size_t)B * cap * 24));
+            int64_t* d_offs = c->s_ls_pack.as<int64_t>();
+            double* d_pk = reinterpret_cast<double*>(c->s_ls_pack.as<char>() + (size_t)B * 8);
+            CU(cudaMemcpyAsync(d_offs, offs.data(), (size_t)B * 8, cudaMemcpyHostToDevice, st));
+            ls_launch_pack_params(S, d_offs, d_pk, st);
+            CU(cudaMemcpyAsync(c->h_ls_pack.p, d_pk, (size_t)total * 24, cudaMemcpyDeviceToHost, st));
+            hpk = c->h_ls_pack.as<double>();
         }
+        auto spread = [&](int64_t p0, int64_t p1, bool with_params) {
+            for (int64_t p = p0; p < p1; ++p) {
+                for (int i = 0; i < 3; ++i) {
+                    for (int j = 0; j < 3; ++j) T_out[12 * p + 4 * i + j] = hR[9 * p + 3 * i + j];
+                    T_out[12 * p + 4 * i + 3] = ht[3 * p + i];
+                }
+                if (with_params) std::memcpy(params + p * (int64_t)cap * 3, hpk + 3 * offs[p], (size_t)(offs[p + 1] - offs[p]) * 24);
+            }
+        };
+        // the small arrays while the packed parameters are still in flight
+        if (fx) std::memcpy(fx, hb + ofx, (size_t)B * 8);
+        if (gx) std::memcpy(gx, hb + ogx, (size_t)B * 8);
+        if (gx0) std::memcpy(gx0, hb + og0, (size_t)B * 8);
+        if (status) std::memcpy(status, hb + ost, (size_t)B * 4);
+        if (iterations) std::memcpy(iterations, hb + oit, (size_t)B * 4);
+        if (n_params) std::memcpy(n_params, hb + ocn, (size_t)B * 4);
+        if (params) CU(spin_stream(st));
+        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)std::thread::hardware_concurrency(), B / 2048}));
+        if (nthr <= 1) {
+            spread(0, B, params != nullptr);
+        } else {
+            std::vector<std::thread> pool;
+            for (int k = 0; k < nthr; ++k) pool.emplace_back(spread, B * k / nthr, B * (k + 1) / nthr, params != nullptr);
+            for (auto& th : pool) th.join();
+        }
+    }
     double qp_ms = 0.0, sweep_ms = 0.0;
     {
         std::vector<char> is_qp(ev.size(), 0);
@@ -1379,8 +1436,11 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
                         "step/values/score_pre %.1f, score_post %.1f\n", wall, qp_ms, sweep_ms, ph[kPhPre], ph[kPhPost], ph[kPhGx], ph[kPhStep], ph[kPhScore]);
     }
     if (prof_total)
-        fprintf(stderr, "[sio lockstep] call %.1f ms (B = %lld)\n",
-                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - entry0).count(), (long long)B);
+        fprintf(stderr, "[sio lockstep] call %.1f ms (B = %lld): set-up %.1f, loop %.1f, read-back %.1f\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - entry0).count(), (long long)B,
+                std::chrono::duration<double, std::milli>(wall0 - entry0).count(),
+                std::chrono::duration<double, std::milli>(loop1 - wall0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - loop1).count());
     if (stats) {
         stats[0] = (int64_t)hc[2]; stats[1] = queries; stats[2] = (int64_t)(qp_ms * 1e3); stats[3] = (int64_t)hc[3];
         stats[4] = (int64_t)(sweep_ms * 1e3); stats[5] = (int64_t)hc[5];

@@ -310,6 +310,30 @@ __global__ void k_ls_init(LsState S, LsSettings cfg) {
     for (int i = 0; i < 6; ++i) S.dx[6 * p + i] = 0.0;     // the arena is reused across calls
 }
 
+// poses as the caller hands them over (row-major 3x4, initial then desired) -> R (3x3), t, Rdes, tdes
+__global__ void __launch_bounds__(kLsThreads)
+k_ls_unpack_poses(LsState S, const double* __restrict__ raw) {
+    const int64_t p = (int64_t)blockIdx.x * kLsThreads + threadIdx.x;
+    if (p >= S.B) return;
+    const double* Ti = raw + 12 * p;
+    const double* Td = raw + 12 * (S.B + p);
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) { S.R[9 * p + 3 * i + j] = Ti[4 * i + j]; S.Rdes[9 * p + 3 * i + j] = Td[4 * i + j]; }
+        S.t[3 * p + i] = Ti[4 * i + 3]; S.tdes[3 * p + i] = Td[4 * i + 3];
+    }
+}
+
+// the instantiated parameters, packed: problem p's cnt[p] points go to packed[3 * offs[p] ...] (one warp per problem)
+__global__ void __launch_bounds__(kLsThreads)
+k_ls_pack_params(LsState S, const int64_t* __restrict__ offs, double* __restrict__ packed) {
+    const int64_t p = ((int64_t)blockIdx.x * kLsThreads + threadIdx.x) >> 5;
+    if (p >= S.B) return;
+    const int n3 = 3 * S.cnt[p];
+    const double* src = S.P + p * (int64_t)S.cap * 3;
+    double* dst = packed + 3 * offs[p];
+    for (int i = threadIdx.x & 31; i < n3; i += 32) dst[i] = src[i];
+}
+
 static unsigned grid_for(int64_t n) { return (unsigned)((n + kLsThreads - 1) / kLsThreads); }
 
 void ls_launch_init(const LsState& S, const LsSettings& c, cudaStream_t st) { k_ls_init<<<grid_for(S.B), kLsThreads, 0, st>>>(S, c); }
@@ -326,6 +350,11 @@ void ls_launch_step(const LsState& S, const LsSettings& c, cudaStream_t st) { k_
 void ls_launch_score_pre(const LsState& S, cudaStream_t st) { k_ls_score_pre<<<grid_for(S.B), kLsThreads, 0, st>>>(S); }
 void ls_launch_score_post(const LsState& S, const LsSettings& c, int64_t n, cudaStream_t st) {
     if (n > 0) k_ls_score_post<<<grid_for(n), kLsThreads, 0, st>>>(S, c, n);
+}
+
+void ls_launch_unpack_poses(const LsState& S, const double* raw, cudaStream_t st) { k_ls_unpack_poses<<<grid_for(S.B), kLsThreads, 0, st>>>(S, raw); }
+void ls_launch_pack_params(const LsState& S, const int64_t* offs, double* packed, cudaStream_t st) {
+    k_ls_pack_params<<<grid_for(S.B * 32), kLsThreads, 0, st>>>(S, offs, packed);
 }
 
 }  // namespace sio

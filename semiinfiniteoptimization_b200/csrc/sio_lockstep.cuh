@@ -41,5 +41,7 @@ void ls_launch_gx(const LsState& S, const LsSettings& c, cudaStream_t st);
 void ls_launch_step(const LsState& S, const LsSettings& c, cudaStream_t st);
 void ls_launch_score_pre(const LsState& S, cudaStream_t st);
 void ls_launch_score_post(const LsState& S, const LsSettings& c, int64_t n, cudaStream_t st);
+void ls_launch_unpack_poses(const LsState& S, const double* raw /* [2][B][12] device: initial, desired */, cudaStream_t st);
+void ls_launch_pack_params(const LsState& S, const int64_t* offs /* [B] device */, double* packed, cudaStream_t st);
 
 }  // namespace sio
