@@ -308,11 +308,22 @@ def sip_leg(ctx, rank, world, want_cpu):
     t0 = time.perf_counter()
     res = batch.optimizeCollFreeBatchDevice(cube, scene, poses[lo:hi])         # host poses in, host results out
     solve_s = time.perf_counter() - t0
+    t_rec = t_gat = 0.0
     if world > 1:                                                              # the path's one exchange: every rank's
-        allrec = sdist.gather_records(res.records(), n_total=SIP_PROBLEMS)     # per-problem records, once, at the end of the solve
+        t1 = time.perf_counter()
+        recs = res.records()
+        t_rec = time.perf_counter() - t1
+        allrec = sdist.gather_records(recs, n_total=SIP_PROBLEMS)              # per-problem records, once, at the end of the solve
+        t_gat = time.perf_counter() - t1 - t_rec
         assert allrec.shape == (SIP_PROBLEMS, 16)
     wall = time.perf_counter() - t0
     wall_local = wall
+    per_rank = None
+    if world > 1:                                                              # after the timed region: who waited for whom
+        mine = torch.tensor([solve_s, t_rec, t_gat], dtype=torch.float64, device="cuda")
+        every = torch.empty((world, 3), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(every, mine)
+        per_rank = every.cpu().numpy()
     rec = torch.tensor([res.outer_iterations, wall, res.time_cons, res.time_qp, res.point_queries, float((res.gx > -5e-3).sum()),
                         float((np.asarray(res.gx0) < 0).sum())], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -320,9 +331,24 @@ def sip_leg(ctx, rank, world, want_cpu):
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(rec, op=dist.ReduceOp.SUM)
         wall = float(mx[1].item())
+    weak = None
+    if world > 1:
+        # the same solver with the shard held FIXED (65,536 problems on every GPU, rank r's poses from seed 3 + r): what the
+        # strong-scaling figure above loses is per-round latency on an 8,192-problem shard, not anything between the GPUs
+        wposes = np.array([se3.to_rowmajor12(T) for T in workloads.c5_poses(SIP_PROBLEMS, seed=3 + rank)])
+        dist.barrier()
+        t0 = time.perf_counter()
+        wres = batch.optimizeCollFreeBatchDevice(cube, scene, wposes)
+        wrec = torch.tensor([wres.outer_iterations, time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        wmx = wrec.clone()
+        dist.all_reduce(wmx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(wrec, op=dist.ReduceOp.SUM)
+        weak = {"value": float(wrec[0].item()) / float(wmx[1].item()), "unit": "SIP outer iterations/s", "scaling": "weak",
+                "problems_per_gpu": SIP_PROBLEMS, "outer_iterations": int(wrec[0].item()), "wall_s_max_over_ranks": float(wmx[1].item()),
+                "note": "65,536 problems per GPU (seed 3 + rank), no exchange; host poses in, host results out"}
     if rank != 0:
         return None
-    out = {"value": float(rec[0].item()) / wall, "unit": "SIP outer iterations/s", "scaling": "strong",
+    out = {"value": float(rec[0].item()) / wall, "unit": "SIP outer iterations/s", "scaling": "strong", "weak_scaling": weak,
            "workload": "C5: %d independent optimizeCollFree problems (cube SDF@0.05 vs synthetic 262,144-point scene, seed 2; poses "
                        "seed 3), reference default settings (max_iters 50), sharded over %d GPU(s), device-resident lock-step "
                        "solver (sio_lockstep_pose_solve); wall clock from host poses (row-major 3x4 array) to host results, the end-of-solve "
@@ -330,6 +356,9 @@ def sip_leg(ctx, rank, world, want_cpu):
            "outer_iterations": int(rec[0].item()), "wall_s": wall, "sweep_device_s_per_rank": float(rec[2].item()) / world,
            "qp_device_s_per_rank": float(rec[3].item()) / world, "other_s_per_rank": wall - float(rec[2].item() + rec[3].item()) / world,
            "library_call_s_rank0": float(res.time), "gather_s_rank0": wall_local - solve_s,
+           "solve_s_per_rank": None if per_rank is None else [round(float(v), 6) for v in per_rank[:, 0]],
+           "records_s_per_rank": None if per_rank is None else [round(float(v), 6) for v in per_rank[:, 1]],
+           "gather_incl_wait_s_per_rank": None if per_rank is None else [round(float(v), 6) for v in per_rank[:, 2]],
            "limiting_term": "in-line QP launches (k_sip_qp): a launch lasts as long as its slowest problem under the 800-iteration "
                             "budget (0.34 ms) plus ~(problems per rank / 1,776 resident warps) x 160 us of ADMM + polish per problem (12 warps share "
                             "an SM; profiles/r02_qp_phases.md), so it shrinks "
