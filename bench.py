@@ -56,6 +56,7 @@ GRIDRES = 0.01
 BYTES_PER_QUERY = 48          # 16 B float4 point + 8 x 4 B corners
 GATHER_BYTES_PER_QUERY = 32
 SIP_PROBLEMS = 65536
+SIP_GROUPS = 2            # concurrent slices per GPU in the C5 leg (tools/run_c5_groups.py: 1 -> 2 slices = -7 % wall at 65,536 problems, -9 % at 8,192)
 METRIC = "sdf_oracle_point_queries_per_s"
 UNIT = "queries/s"
 
@@ -291,8 +292,9 @@ def sip_leg(ctx, rank, world, want_cpu):
     from semiinfiniteoptimization_b200 import batch, geometryopt as G, sip, workloads
     from semiinfiniteoptimization_b200 import dist as sdist
     from semiinfiniteoptimization_b200._host.geometry import Geometry3D, PointCloud
-    cube = G.PenetrationDepthGeometry(workloads.c5_cube(), 0.05, None, context=ctx)
-    scene = G.PenetrationDepthGeometry(Geometry3D(PointCloud(workloads.c5_scene_cloud())), None, 0.02, context=ctx)
+    # two concurrent slices of the shard (one context + host thread each, same GPU): one slice's QP launches overlap the
+    # other's sweeps and bookkeeping launches; same answers problem by problem (tests/test_gpu_batch.py)
+    solver = batch.GroupedPoseSolver(workloads.c5_cube(), 0.05, workloads.c5_scene_cloud(), pcres=0.02, groups=SIP_GROUPS, context=ctx)
     poses = workloads.c5_poses(SIP_PROBLEMS, seed=3)
     lo, hi = sdist.shard_range(SIP_PROBLEMS)
     from semiinfiniteoptimization_b200._host import se3
@@ -300,20 +302,20 @@ def sip_leg(ctx, rank, world, want_cpu):
     lo, hi = 0, len(poses)
     warm = sip.SemiInfiniteOptimizationSettings()
     warm.max_iters = 1
-    wres = batch.optimizeCollFreeBatchDevice(cube, scene, poses, settings=warm)   # warm-up: first launches, scratch sized for the shard
+    wres = solver.solve(poses, settings=warm)                                  # warm-up: first launches, scratch sized for the shard
     if world > 1:
         sdist.gather_records(wres.records(), n_total=SIP_PROBLEMS)   # ... and NCCL's first all-gather of this size (it sets up buffers: 0.2 s once)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    res = batch.optimizeCollFreeBatchDevice(cube, scene, poses[lo:hi])         # host poses in, host results out
+    res = solver.solve(poses[lo:hi])                                           # host poses in, host results out
     solve_s = time.perf_counter() - t0
     t_rec = t_gat = 0.0
     if world > 1:                                                              # the path's one exchange: every rank's
         t1 = time.perf_counter()
         recs = res.records()
         t_rec = time.perf_counter() - t1
-        allrec = sdist.gather_records(recs, n_total=SIP_PROBLEMS)              # per-problem records, once, at the end of the solve
+        allrec = sdist.gather_records(recs, n_total=SIP_PROBLEMS, copy=False)  # per-problem records, once, at the end of the solve
         t_gat = time.perf_counter() - t1 - t_rec
         assert allrec.shape == (SIP_PROBLEMS, 16)
     wall = time.perf_counter() - t0
@@ -336,9 +338,10 @@ def sip_leg(ctx, rank, world, want_cpu):
         # the same solver with the shard held FIXED (65,536 problems on every GPU, rank r's poses from seed 3 + r): what the
         # strong-scaling figure above loses is per-round latency on an 8,192-problem shard, not anything between the GPUs
         wposes = np.array([se3.to_rowmajor12(T) for T in workloads.c5_poses(SIP_PROBLEMS, seed=3 + rank)])
+        solver.solve(wposes, settings=warm)                                     # scratch re-sized for the larger shard, untimed
         dist.barrier()
         t0 = time.perf_counter()
-        wres = batch.optimizeCollFreeBatchDevice(cube, scene, wposes)
+        wres = solver.solve(wposes)
         wrec = torch.tensor([wres.outer_iterations, time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         wmx = wrec.clone()
         dist.all_reduce(wmx, op=dist.ReduceOp.MAX)
@@ -351,10 +354,13 @@ def sip_leg(ctx, rank, world, want_cpu):
     out = {"value": float(rec[0].item()) / wall, "unit": "SIP outer iterations/s", "scaling": "strong", "weak_scaling": weak,
            "workload": "C5: %d independent optimizeCollFree problems (cube SDF@0.05 vs synthetic 262,144-point scene, seed 2; poses "
                        "seed 3), reference default settings (max_iters 50), sharded over %d GPU(s), device-resident lock-step "
-                       "solver (sio_lockstep_pose_solve); wall clock from host poses (row-major 3x4 array) to host results, the end-of-solve "
-                       "all-gather of the per-problem records included at N > 1" % (SIP_PROBLEMS, world),
+                       "solver (sio_lockstep_pose_solve), each shard solved as %d concurrent slices (batch.GroupedPoseSolver); wall clock from host poses (row-major 3x4 array) to host results, the end-of-solve "
+                       "all-gather of the per-problem records included at N > 1" % (SIP_PROBLEMS, world, SIP_GROUPS),
            "outer_iterations": int(rec[0].item()), "wall_s": wall, "sweep_device_s_per_rank": float(rec[2].item()) / world,
            "qp_device_s_per_rank": float(rec[3].item()) / world, "other_s_per_rank": wall - float(rec[2].item() + rec[3].item()) / world,
+           "slices_per_gpu": SIP_GROUPS,
+           "device_s_note": "sweep / qp device seconds are those of the slower slice; with more than one slice per GPU the slices' "
+                            "launches overlap in time, so sweep + qp + other no longer partition the wall clock exactly",
            "library_call_s_rank0": float(res.time), "gather_s_rank0": wall_local - solve_s,
            "solve_s_per_rank": None if per_rank is None else [round(float(v), 6) for v in per_rank[:, 0]],
            "records_s_per_rank": None if per_rank is None else [round(float(v), 6) for v in per_rank[:, 1]],

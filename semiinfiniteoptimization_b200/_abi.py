@@ -128,6 +128,13 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
+def lockstep_outputs(B, cap=48, want_params=True):
+    """The per-problem result arrays of Context.lockstep_pose_solve for B problems."""
+    return {"T": np.empty((B, 12)), "status": np.empty(B, dtype=np.int32), "iterations": np.empty(B, dtype=np.int32),
+            "fx": np.empty(B), "gx": np.empty(B), "gx0": np.empty(B), "n_params": np.empty(B, dtype=np.int32),
+            "params": np.empty((B, cap, 3)) if want_params else None}
+
+
 class Context:
     """One device context (stream + scratch + resident handles).  Calls are serialised on its stream."""
 
@@ -308,9 +315,10 @@ class Context:
 
     # -- lock-step pose solver (device resident) --
     def lockstep_pose_solve(self, grid, cloud, T_env, cloud_world, T_init, T_des, settings, cap=48, sweep_flags=SIO_F32 | SIO_PRUNE,
-                            want_params=True):
+                            want_params=True, out=None):
         """B object-pose SIP problems in lock step on the device (sio_lockstep_pose_solve).  `settings`: a
-        SemiInfiniteOptimizationSettings.  Returns a dict of per-problem arrays and the stats."""
+        SemiInfiniteOptimizationSettings.  Returns a dict of per-problem arrays and the stats.  `out`: the same dict
+        with caller-owned C-contiguous arrays of B rows (slices of a larger batch's arrays) to be filled in place."""
         class _S(C.Structure):
             _fields_ = [("max_iters", C.c_int32), ("cap", C.c_int32), ("xepsilon", C.c_double), ("constraint_inflation", C.c_double),
                         ("constraint_drop_value", C.c_double), ("minimum_constraint_value", C.c_double),
@@ -327,9 +335,16 @@ class Context:
                float(settings.initial_objective_score_weight), float(settings.minimum_objective_score_weight),
                float(settings.parameter_exclusion_distance), float(settings.qp_solver_params.get('regularizationFactor', 1e-2)),
                int(sweep_flags))
-        out = {"T": np.empty((B, 12)), "status": np.empty(B, dtype=np.int32), "iterations": np.empty(B, dtype=np.int32),
-               "fx": np.empty(B), "gx": np.empty(B), "gx0": np.empty(B), "n_params": np.empty(B, dtype=np.int32),
-               "params": np.empty((B, cap, 3)) if want_params else None}
+        if out is None:
+            out = lockstep_outputs(B, cap, want_params)
+        else:
+            shapes = lockstep_outputs(0, cap, want_params)
+            for k, ref in shapes.items():
+                a = out[k]
+                if ref is None:
+                    assert a is None
+                    continue
+                assert a.dtype == ref.dtype and a.shape == (B,) + ref.shape[1:] and a.flags.c_contiguous, k
         stats = np.zeros(6, dtype=np.int64)
         self._ck(self.L.sio_lockstep_pose_solve(self.h, grid, cloud, Te.ctypes.data, cw.ctypes.data, B, Ti.ctypes.data, Td.ctypes.data,
                                                 C.byref(s), out["T"].ctypes.data, out["status"].ctypes.data,

@@ -612,7 +612,7 @@ def optimizeCollFreeBatchFast(obj, env, Tinits, Tdess=None, settings=None, conte
     return res
 
 
-def optimizeCollFreeBatchDevice(obj, env, Tinits, Tdess=None, settings=None, context=None, flags=None, cap=48):
+def optimizeCollFreeBatchDevice(obj, env, Tinits, Tdess=None, settings=None, context=None, flags=None, cap=48, _out=None):
     """The lock-step algorithm with ALL per-problem state on the device (sio_lockstep_pose_solve, csrc/sio_lockstep.cu):
     the host sequences kernel launches and reads two counters per outer iteration.  Same iterations per problem as
     optimizeCollFreeBatchFast (tests compare them); `cap` = parameter slots per problem (parameters beyond it are
@@ -646,7 +646,7 @@ def optimizeCollFreeBatchDevice(obj, env, Tinits, Tdess=None, settings=None, con
         env._cloud_world_cache = cached
     cloud_world = cached[2]
     t0 = time.time()
-    out = ctx.lockstep_pose_solve(obj._dev.grid_h, env._dev.cloud_h, env._T12, cloud_world, Ti, Td, settings, cap=cap, sweep_flags=flags)
+    out = ctx.lockstep_pose_solve(obj._dev.grid_h, env._dev.cloud_h, env._T12, cloud_world, Ti, Td, settings, cap=cap, sweep_flags=flags, out=_out)
     res = BatchResult(B, per_problem_lists=False)
     res.time = time.time() - t0
     res.T = out["T"]
@@ -660,3 +660,81 @@ def optimizeCollFreeBatchDevice(obj, env, Tinits, Tdess=None, settings=None, con
     res.slot_overflows = out["stats"]["slot_overflows"]
     res.qp_failures = out["stats"]["qp_failures"]          # problems stopped with status 2 ('qp failed')
     return res
+
+
+class GroupedPoseSolver:
+    """optimizeCollFreeBatchDevice over `groups` concurrent slices of the batch: one device context (stream, scratch,
+    resident copy of the two geometries) and one host thread per slice, all on the same GPU.
+
+    Why: a round of the lock-step solver is a chain of dependent launches; with few problems per GPU (8,192 = one rank of
+    an 8-GPU C5 run) every QP launch lasts as long as its slowest problem and the small bookkeeping launches run one
+    after the other on a mostly idle device.  Independent slices have no such dependence on each other, so their chains
+    interleave on the SMs.  The problems are independent (each keeps its own iteration index, no quantity is shared
+    between problems), so the answers are those of the single-context solve, problem by problem (tests).
+
+    obj / env: Geometry3D (as PenetrationDepthGeometry takes them) -- obj converted to an SDF at `gridres`, env to a
+    cloud at `pcres`; env_T: the environment's pose (Klampt se3), default as loaded."""
+
+    def __init__(self, obj, gridres, env, pcres=0.02, groups=2, context=None, env_T=None):
+        from ._host.geometry import Geometry3D, PointCloud
+        first = context or _abi.default_context()
+        device = first.device
+        if isinstance(env, np.ndarray):
+            env = Geometry3D(PointCloud(env))
+        self.groups = max(1, int(groups))
+        self.ctxs, self.objs, self.envs = [], [], []
+        for k in range(self.groups):
+            ctx = first if k == 0 else _abi.Context(device)
+            self.ctxs.append(ctx)
+            self.objs.append(PenetrationDepthGeometry(obj, gridres, None, context=ctx))
+            e = PenetrationDepthGeometry(env, None, pcres, context=ctx)
+            if env_T is not None:
+                e.setTransform(env_T)
+            self.envs.append(e)
+
+    def solve(self, Tinits, Tdess=None, settings=None, cap=48):
+        import threading
+        B = len(Tinits)
+        k = min(self.groups, max(1, B))
+        if k == 1:
+            return optimizeCollFreeBatchDevice(self.objs[0], self.envs[0], Tinits, Tdess, settings=settings, context=self.ctxs[0], cap=cap)
+        cuts = [(B * g) // k for g in range(k + 1)]
+        parts, errs = [None] * k, [None] * k
+        whole = _abi.lockstep_outputs(B, cap)                 # every slice fills its rows of the same arrays: nothing is merged afterwards
+
+        def run(g):
+            try:
+                lo, hi = cuts[g], cuts[g + 1]
+                parts[g] = optimizeCollFreeBatchDevice(self.objs[g], self.envs[g], Tinits[lo:hi], None if Tdess is None else Tdess[lo:hi],
+                                                       settings=settings, context=self.ctxs[g], cap=cap,
+                                                       _out={n: (a[lo:hi] if a is not None else None) for n, a in whole.items()})
+            except BaseException as e:                        # re-raised on the calling thread
+                errs[g] = e
+        t0 = time.time()
+        threads = [threading.Thread(target=run, args=(g,)) for g in range(1, k)]
+        for t in threads:
+            t.start()
+        run(0)
+        for t in threads:
+            t.join()
+        for e in errs:
+            if e is not None:
+                raise e
+        res = BatchResult(B, per_problem_lists=False)
+        res.time = time.time() - t0
+        res.T, res.status_codes = whole["T"], whole["status"]
+        res.num_iterations = whole["iterations"].astype(np.int64)
+        res.fx, res.gx, res.gx0 = whole["fx"], whole["gx"], whole["gx0"]
+        res.set_params_arrays(whole["params"], whole["n_params"])
+        # device seconds of the slices overlap in time: the per-slice maxima are what a wall clock can see
+        res.time_qp, res.time_cons = max(p.time_qp for p in parts), max(p.time_cons for p in parts)
+        res.outer_iterations = sum(p.outer_iterations for p in parts)
+        res.point_queries = sum(p.point_queries for p in parts)
+        res.slot_overflows = sum(p.slot_overflows for p in parts)
+        res.qp_failures = sum(p.qp_failures for p in parts)
+        return res
+
+    def close(self):
+        for ctx in self.ctxs[1:]:
+            ctx.close()
+        self.ctxs, self.objs, self.envs = [], [], []

@@ -63,12 +63,14 @@ def _buffers(dev, ws, nmax, k):
     return b
 
 
-def gather_records(local, n_total=None):
+def gather_records(local, n_total=None, copy=True):
     """All-gather a (n_local, k) float64 array of per-unit records from every rank, in rank order (= unit order for
     `shard_range` blocks).  ONE collective (all_gather_into_tensor into a preallocated buffer) and one copy each way
     through pinned memory; with `n_total` given the per-rank counts follow from shard_range and nothing else is
-    exchanged (8 ranks x 8,192 records x 16 doubles: 8 ms with a count all-reduce + list all-gather + per-rank .cpu(),
-    now well under a millisecond).  Ranks may own different counts (blocks are padded to the largest)."""
+    exchanged.  Ranks may own different counts (blocks are padded to the largest).
+    copy=False returns a view of the pinned landing buffer when every rank owns the same count -- valid until the next
+    gather of the same shape; the default hands out fresh memory (measured at 2 ranks x 32,768 records x 16 doubles:
+    3.0 ms, most of it first-touch page faults of that 8 MB copy)."""
     import torch
     local = np.ascontiguousarray(local, dtype=np.float64)
     if local.ndim == 1:
@@ -101,7 +103,9 @@ def gather_records(local, n_total=None):
         torch.cuda.current_stream().synchronize()
     allr = h_recv.numpy().reshape(ws, nmax, k)
     if all(cn == nmax for cn in counts):
-        res = allr.reshape(ws * nmax, k).copy()
+        res = allr.reshape(ws * nmax, k)
+        if copy:
+            res = res.copy()
     else:
         res = np.concatenate([allr[r, :cn] for r, cn in enumerate(counts)], axis=0)
     if n_total is not None:

@@ -215,3 +215,30 @@ def test_drivers_agree_on_the_c5_workload(ctx):
     feas_ref, feas_dev = (ref.gx > -5e-3).sum(), (dev.gx > -5e-3).sum()
     assert abs(int(feas_ref) - int(feas_dev)) <= 0.01 * len(poses)
     assert (np.asarray(ref.gx0) < 0).mean() > 0.5
+
+
+@pytest.mark.gpu
+def test_concurrent_slices_give_the_single_context_answers(ctx):
+    """GroupedPoseSolver: the batch cut into slices solved concurrently (own context, stream and host thread each) ends
+    every problem exactly where the one-context solve does -- problems share nothing -- including a slice count that
+    does not divide the batch and a batch smaller than the slice count."""
+    from semiinfiniteoptimization_b200 import batch, sip, workloads as W
+    from semiinfiniteoptimization_b200._host import se3
+    poses = np.array([se3.to_rowmajor12(T) for T in W.c5_poses(1537, seed=3)])
+    st = sip.SemiInfiniteOptimizationSettings()
+    st.max_iters = 12
+    one = batch.GroupedPoseSolver(W.c5_cube(), 0.05, W.c5_scene_cloud(), groups=1, context=ctx)
+    ref = one.solve(poses, settings=st)
+    for k in (2, 3):
+        many = batch.GroupedPoseSolver(W.c5_cube(), 0.05, W.c5_scene_cloud(), groups=k, context=ctx)
+        res = many.solve(poses, settings=st)
+        assert np.array_equal(res.T, ref.T) and np.array_equal(res.num_iterations, ref.num_iterations)
+        assert np.array_equal(res.status_codes, ref.status_codes) and np.array_equal(res.gx, ref.gx)
+        assert np.array_equal(res.n_params, ref.n_params)
+        for p in (0, 700, 1536):
+            assert res.instantiated_params[p] == ref.instantiated_params[p]
+        assert res.outer_iterations == ref.outer_iterations and res.point_queries == ref.point_queries
+        assert np.array_equal(res.records(), ref.records())
+        tiny = many.solve(poses[:1], settings=st)
+        assert np.array_equal(tiny.T, ref.T[:1])
+        many.close()
