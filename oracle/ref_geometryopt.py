@@ -139,6 +139,23 @@ class RefObjectCollisionConstraint(SemiInfiniteConstraintInterface):
         cporiented = so3.apply(T[0], vectorops.sub(pt[:3], T[1]))     # R (pt - t), as written (gopt:415)
         return np.array(list(vectorops.cross(cporiented, worlddir)) + list(worlddir))
 
+    def domain(self):
+        return RefPenetrationGeometryDomain(self.env)
+
+
+class RefPenetrationGeometryDomain:
+    """gopt:171-183: the world positions of a geometry's cloud points."""
+
+    def __init__(self, g):
+        self.g = g
+
+    def sample(self):
+        import random
+        return se3.apply(self.g.getTransform(), self.g.pcdata.getPoint(random.randint(0, self.g.pcdata.numPoints() - 1)))
+
+    def extrema(self):
+        return [se3.apply(self.g.getTransform(), self.g.pcdata.getPoint(i)) for i in range(self.g.pcdata.numPoints())]
+
 
 class RefRobotKinematicsCache:
     """gopt:187-207."""

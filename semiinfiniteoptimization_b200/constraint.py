@@ -205,3 +205,83 @@ class SemiInfiniteConstraintAdaptor(SemiInfiniteConstraintInterface):
 
     def domain(self):
         return SetDomain([(0,)])
+
+
+class MultiSemiInfiniteConstraint(SemiInfiniteConstraintInterface):
+    """Several scalar semi-infinite constraints c_0 .. c_{n-1} presented as one:
+        min_y f(x, y) = min_i min_{y_i} c_i(x, y_i),      y = (i, y_i, zero padding to a common length)
+    (constraint.py:174-256).  all_negative=True: `minvalue` hands back every pair its members report under
+    min(bound, 0) -- with members that answer with their whole active set (ObjectCollisionConstraint.all_under) one
+    oracle call instantiates all violated points at once; False: the single deepest pair.
+    The reference sizes the padding with `sampleDomain(c.domain())`, a name it never imports; here the length of a
+    co-parameter comes from `c.domain().sample()`."""
+
+    def __init__(self, constraints, all_negative=True):
+        self.constraints = list(constraints)
+        self.all_negative = all_negative
+        self.num_co_parameters = []
+        for c in self.constraints:
+            assert c.dims() == 0
+            self.num_co_parameters.append(len(np.atleast_1d(c.domain().sample())))
+        self.max_co_parameters = max(self.num_co_parameters)
+
+    def _member(self, y):
+        index = int(y[0])
+        assert 0 <= index < len(self.constraints)
+        return index, self.constraints[index], y[1:1 + self.num_co_parameters[index]]
+
+    def _pad(self, i, yi):
+        return np.hstack(([i], yi, [0] * (self.max_co_parameters - len(yi))))
+
+    def __call__(self, x, y):
+        _, c, yi = self._member(y)
+        c.setx(x)
+        res = c.value(x, yi)
+        c.clearx()
+        return res
+
+    def setx(self, x):
+        for c in self.constraints:
+            c.setx(x)
+
+    def clearx(self):
+        for c in self.constraints:
+            c.clearx()
+
+    def value(self, x, y):
+        _, c, yi = self._member(y)
+        return c.value(x, yi)
+
+    @staticmethod
+    def _pairs(mv):
+        return [mv] if len(mv) > 0 and not hasattr(mv[0], '__iter__') else mv
+
+    def minvalue(self, x, bound=None):
+        if self.all_negative:
+            res = []
+            if bound is not None and bound < 0:              # members are asked for everything below zero  (constraint.py:226-227)
+                bound = 0
+            for i, c in enumerate(self.constraints):
+                for (fi, yi) in self._pairs(c.minvalue(x, bound)):
+                    res.append((fi, self._pad(i, yi)))
+            return res
+        best = None
+        for i, c in enumerate(self.constraints):
+            for (fi, yi) in self._pairs(c.minvalue(x, bound)):
+                if bound is None or fi < bound:
+                    bound = fi
+                    best = self._pad(i, yi)
+        if best is None:
+            return []
+        return (bound, best)
+
+    def df_dx(self, x, y):
+        _, c, yi = self._member(y)
+        return c.df_dx(x, yi)
+
+    def df_dy(self, x, y):
+        _, c, yi = self._member(y)
+        return np.hstack(([0], c.df_dy(x, yi)))
+
+    def domain(self):
+        raise NotImplementedError("TODO: Can't inspect domain of a MultiSemiInfiniteConstraint yet")

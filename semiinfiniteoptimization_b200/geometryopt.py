@@ -227,6 +227,29 @@ class PenetrationDepthGeometry:
         cp2 = other.distance(cp1)[1] if want_cp2 else [0.0] * 3
         return d, cp1, cp2
 
+    def under(self, other, bound):
+        """The ACTIVE SET of the cloud-vs-grid query (BASELINE.json north_star: "global minimum plus all points under the
+        bound, with compacted index output"; protocol: constraint.py:141-151 lets `minvalue` return a list of pairs):
+        every point i of THIS geometry's cloud with SDF_other(T_other^-1 T_self p_i) < bound.
+        Returns (d[K], index[K], world points[K,3]) in index order; d is the float64 value of the reference's
+        per-point query (the float32 bulk pass only nominates candidates, k_finalize re-evaluates them exactly), so the
+        set equals the CPU oracle's.  The list is compacted on the device; its size is not limited (the candidate
+        buffer is re-sized and the sweep repeated when it overflows)."""
+        assert isinstance(other, PenetrationDepthGeometry)
+        assert self.pc is not None, "Need a PointCloud for geometry-geometry distance"
+        assert other.grid is not None, "Need a VolumeGrid for geometry-geometry distance"
+        ctx = self._dev.ctx
+        T_rel = _mul12(_inv12(other._T12), self._T12)
+        _, _, n_under = ctx.min_distance(other._dev.grid_h, self._dev.cloud_h, T_rel, bound=[float(bound)], flags=BULK_FLAGS,
+                                         want_under=True)
+        n = int(n_under[0])
+        if n == 0:
+            return np.zeros(0), np.zeros(0, dtype=np.int64), np.zeros((0, 3))
+        _, idx, d = ctx.under_fetch(capacity=n)
+        assert len(idx) == n
+        T = self._T12.reshape(3, 4)
+        return d, idx, self._dev.cloud32[idx].astype(np.float64) @ T[:, :3].T + T[:, 3]
+
     def normal(self, pt):
         """grad1 of the SDF at the world point: d(distance)/d(translation of this geometry)
         (gopt:148-168)."""
@@ -565,11 +588,26 @@ class ObjectCollisionConstraint(SemiInfiniteConstraintInterface):
     def value(self, T, pt):
         return self.objgeom.distance(pt)[0]
 
+    # all_under = True: `minvalue(x, bound)` answers with EVERY environment point under the bound as a list of
+    # (value, point) pairs, deepest first -- what constraint.py:141-151 allows and MultiSemiInfiniteConstraint's
+    # all_negative mode asks of its members.  Off by default: the reference's class returns one pair (gopt:409-412), and
+    # solutions only match in that mode (SURVEY A.6).
+    all_under = False
+
     def minvalue(self, T, bound=None):
+        if self.all_under and bound is not None:
+            return self.minvalue_all(T, bound)
         dmin, cp1, cp2 = self.env._cloud_vs_grid(self.objgeom, bound, want_cp2=False)
         if bound is not None and dmin >= bound:
             return []
         return dmin, cp1
+
+    def minvalue_all(self, T, bound):
+        """[(value, world point), ...] for all points of the environment cloud below `bound` at the pose given to
+        setx, deepest first (ties: lowest point index first)."""
+        d, idx, pts = self.env.under(self.objgeom, bound)
+        order = np.lexsort((idx, d))
+        return [(float(d[i]), [float(v) for v in pts[i]]) for i in order]
 
     def df_dx(self, T, pt):
         return self.df_dx_batch(T, [pt])[0]
@@ -617,6 +655,13 @@ class RobotLinkCollisionConstraint(SemiInfiniteConstraintInterface):
         p = self.env._dev.cloud32[idx].astype(np.float64)
         T = self.env._T12.reshape(3, 4)
         return dmin, [float(v) for v in T[:, :3] @ p + T[:, 3]]
+
+    def minvalue_all(self, q, bound):
+        """[(value, world point), ...] for all points of the environment cloud below `bound` of THIS link's SDF at the
+        configuration given to setx, deepest first (the active set; see ObjectCollisionConstraint.minvalue_all)."""
+        d, idx, pts = self.env.under(self.robot.geometry[self.link.index], bound)
+        order = np.lexsort((idx, d))
+        return [(float(d[i]), [float(v) for v in pts[i]]) for i in order]
 
     def df_dx(self, q, pt):
         return self.df_dx_batch(q, [pt])[0]

@@ -417,3 +417,74 @@ def test_lipschitz_scheduled_sweep_equals_dense_sweep(G, R, c4, chair_pos):
             assert con.minvalue(xa, a[0] - 1e-6) == [] and con.minvalue(xa, a[0] + 1e-6) == a
             con.clearx()
     con.LEVELS = 7
+
+
+def test_active_set_through_the_python_api(G, c1):
+    """north_star: "global minimum plus all points under the bound, with compacted index output" -- through the drop-in
+    classes: PenetrationDepthGeometry.under and ObjectCollisionConstraint.minvalue_all give the oracle's under-bound set
+    (indices identical, float64 values), deepest first; all_under makes `minvalue` itself answer with the list."""
+    from oracle import oracle as O
+    g1, g2, r1, r2 = c1
+    grid = O.Grid(g1.grid.getVolumeGrid().values, g1.grid.getVolumeGrid().bmin, g1.grid.getVolumeGrid().bmax)
+    c = G.ObjectCollisionConstraint(g1, g2)
+    sizes = []
+    for T in c1_poses(5, seed=11):
+        c.setx(T)
+        dmin = c.minvalue(T)[0]
+        for bound in (dmin - 1e-3, dmin + 1e-6, dmin + 0.02, 0.0, 0.1):
+            d, idx, pts = g2.under(g1, bound)
+            T_rel = (np.linalg.inv(mat4(T)) @ mat4(g2.getTransform()))[:3].reshape(1, 12)      # grid-local <- cloud-local
+            n_u, ub, ui, ud = O.under(grid, g2._dev.cloud32, T_rel, np.array([bound]))
+            assert n_u == len(ui)
+            assert np.array_equal(idx, ui) and np.abs(d - ud).max(initial=0.0) <= 1e-12
+            sizes.append(len(idx))
+            pairs = c.minvalue_all(T, bound)
+            assert len(pairs) == len(ui)
+            assert [p[0] for p in pairs] == sorted(p[0] for p in pairs)
+            if len(pairs):
+                assert abs(pairs[0][0] - dmin) <= 1e-12 and np.allclose(pairs[0][1], c.minvalue(T)[1], atol=1e-12)
+                k = int(np.argmin(ud))
+                assert np.allclose(pairs[0][1], pts[k], atol=0)
+                for f, y in pairs[:: max(1, len(pairs) // 7)]:
+                    assert abs(c.value(T, y) - f) <= 1e-9
+            c.all_under = True
+            try:
+                assert c.minvalue(T, bound) == pairs
+                one = c.minvalue(T)                              # no bound: the single deepest pair, as always
+                assert not hasattr(one[0], '__iter__')
+            finally:
+                c.all_under = False
+    assert max(sizes) > 500 and min(sizes) == 0
+
+
+def mat4(T):
+    """Klampt se3 (R column-major 9-list, t) as a 4x4 matrix."""
+    A = np.eye(4)
+    A[:3, :3] = np.asarray(T[0], dtype=np.float64).reshape(3, 3).T
+    A[:3, 3] = T[1]
+    return A
+
+
+def test_multi_constraint_over_device_members_equals_the_reference_class():
+    from tests.test_multi_cpu import check_against_golden
+    check_against_golden('device', 1e-9)
+
+
+def test_sip_with_all_under_members_reaches_feasibility(G, c1):
+    """The batched extension of SURVEY A.6 end to end: a MultiSemiInfiniteConstraint whose member answers every oracle
+    call with its whole active set (capped by the solver's bound) still drives optimizeSemiInfinite to a collision-free
+    pose, in no more outer iterations than the one-pair mode."""
+    from semiinfiniteoptimization_b200 import sip
+    g1, g2, r1, r2 = c1
+    T0 = c1_poses(1, seed=0)[0]
+    iters = {}
+    for mode in (False, True):
+        c = G.ObjectCollisionConstraint(g1, g2)
+        c.all_under = mode
+        M = G.MultiSemiInfiniteConstraint([c], all_negative=True)
+        st = sip.SemiInfiniteOptimizationSettings()
+        res = sip.optimizeSemiInfinite(G.ObjectPoseObjective(T0), [M], T0, settings=st, verbose=0)
+        c.setx(res.x)
+        assert c.minvalue(res.x)[0] > -5e-3
+        iters[mode] = res.num_iterations
+    assert iters[True] <= iters[False]

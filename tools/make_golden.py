@@ -276,7 +276,46 @@ def gen_oracle():
     write("oracle_kat.json", out)
 
 
-GENERATORS = {"c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "c5": gen_c5, "classes": gen_classes, "oracle": gen_oracle,
+def multi_inputs(kind):
+    """Two member constraints over the same pose variable: C1's cube-vs-chair pair and the same cube against the chair
+    moved to (I, [1.0, 0.3, 0.1]); poses from c1_poses (seed 5); bounds None / 0.05 / -0.5 (the last prunes everything)."""
+    from oracle.frozen import so3
+    from semiinfiniteoptimization_b200._host.geometry import fixture_geometry
+    mod, g1, g2, con_a = scenes.c1_scene(kind)
+    nm = scenes._names(kind)
+    g3 = getattr(mod, nm['PDG'])(fixture_geometry("m797"), 0.05, 0.02)
+    g3.setTransform((so3.identity(), [1.0, 0.3, 0.1]))
+    con_b = getattr(mod, nm['Obj'])(g1, g3)
+    return mod, [con_a, con_b], scenes.c1_poses(4, seed=5), [None, 0.05, -0.5]
+
+
+def gen_multi():
+    """The reference's MultiSemiInfiniteConstraint (con:174-256) over two ObjectCollisionConstraints.  Its __init__ calls
+    `sampleDomain`, a name constraint.py never imports: the loader's namespace gets
+    sampleDomain = lambda d: d.sample() -- the only reading the call site allows -- and nothing else is touched."""
+    mod, cons, poses, bounds = multi_inputs('reference')
+    cmod = sys.modules[mod.__name__.rsplit('.', 1)[0] + '.constraint']
+    cmod.sampleDomain = lambda d: d.sample()
+    cases = []
+    for all_negative in (True, False):
+        M = cmod.MultiSemiInfiniteConstraint(cons, all_negative=all_negative)
+        for T in poses:
+            for bound in bounds:
+                M.setx(T)
+                mv = M.minvalue(T, bound)
+                pairs = [mv] if len(mv) > 0 and not hasattr(mv[0], '__iter__') else mv
+                rec = {"all_negative": all_negative, "T": _f(T), "bound": bound, "single": not (len(mv) == 0 or hasattr(mv[0], '__iter__')),
+                       "pairs": [[float(f), _f(y)] for (f, y) in pairs],
+                       # co-parameters handed back as lists: the reference's point queries accept list / tuple only (gopt:97-100)
+                       "value": [float(M.value(T, [float(v) for v in y])) for (f, y) in pairs],
+                       "df_dx": [_f(np.asarray(M.df_dx(T, [float(v) for v in y]))) for (f, y) in pairs]}
+                M.clearx()
+                cases.append(rec)
+    write("multi_constraint.json", {"config": "MultiSemiInfiniteConstraint([cube vs chair@(1.2,0,0), cube vs chair@(1.0,0.3,0.1)]) (con:174-256)",
+                                    "num_co_parameters": M.num_co_parameters, "cases": cases})
+
+
+GENERATORS = {"multi": gen_multi, "c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "c5": gen_c5, "classes": gen_classes, "oracle": gen_oracle,
               "planopt": gen_planopt, "paths": gen_paths}
 
 if __name__ == "__main__":
