@@ -64,6 +64,18 @@ LIPSCHITZ_SCHEDULE = True
 DEVICE_CONVERSION = True
 
 
+def grid_to_numpy(grid):
+    """The samples of a VolumeGrid geometry as a float64 (m, n, p) array, z fastest (gopt:21-29)."""
+    return np.array(grid.getVolumeGrid().values, dtype=np.float64)
+
+
+def dump_grid_mat(grid, fn='grid.mat'):
+    """One variable `slice_<i>` per x-slice of the grid, as utils/SDF Plotting.ipynb reads them (gopt:31-36)."""
+    import scipy.io
+    arr = grid_to_numpy(grid)
+    scipy.io.savemat(fn, {"slice_%d" % i: arr[i, :, :] for i in range(arr.shape[0])})
+
+
 def _sweep_flags():
     return BULK_FLAGS | (_abi.SIO_PRUNE if PRUNE_SWEEPS else 0)
 

@@ -513,3 +513,22 @@ def test_native_banded_qp_equals_the_interpreted_solver():
     dense_rows = scipy.sparse.csr_matrix(rng.normal(0, 1, (2, n)))
     A = scipy.sparse.vstack([dense_rows, scipy.sparse.identity(n)], format="csc")
     assert qp.solve_qp_structured(Px, q, A, np.concatenate([[0.0, 0.0], lo]), np.concatenate([[np.inf, np.inf], hi]), n, 2, True, 0.0) is None
+
+
+def test_grid_export_formats(tmp_path):
+    """grid_to_numpy / dump_grid_mat (gopt:21-36): the (m, n, p) sample array and the per-x-slice .mat file the
+    reference's demo drivers write (robotposeopt.py:78)."""
+    import scipy.io
+    from semiinfiniteoptimization_b200 import geometryopt as G
+    from semiinfiniteoptimization_b200._host.geometry import fixture_geometry
+    ns = {"grid_to_numpy": G.grid_to_numpy, "dump_grid_mat": G.dump_grid_mat}
+    grid = fixture_geometry("cube").convert("VolumeGrid", 0.1)
+    vg = grid.getVolumeGrid()
+    arr = ns["grid_to_numpy"](grid)
+    assert arr.shape == tuple(vg.dims) and arr.dtype == np.float64
+    assert arr[1, 2, 3] == vg.get(1, 2, 3) and arr[-1, 0, 5] == vg.get(vg.dims[0] - 1, 0, 5)
+    fn = str(tmp_path / "grid.mat")
+    ns["dump_grid_mat"](grid, fn)
+    mat = scipy.io.loadmat(fn)
+    assert sorted(k for k in mat if k.startswith("slice_")) == sorted("slice_%d" % i for i in range(vg.dims[0]))
+    assert np.array_equal(mat["slice_2"], arr[2])
