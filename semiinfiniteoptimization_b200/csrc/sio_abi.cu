@@ -137,6 +137,8 @@ struct sio_ctx {
     cudaStream_t ls_stream[kLsBack] = {nullptr, nullptr, nullptr};
     DevBuf s_qpb[kLsBack];
     cudaEvent_t ls_evA[kLsRing] = {}, ls_evB[kLsRing] = {};
+    cudaStream_t qp_side = nullptr;   // the two-row QP launch of a round runs here, beside the one-row launch on the main stream
+    cudaEvent_t qp_fork = nullptr, qp_join = nullptr;
     HostBuf h_icnt;
     int n_icnt = 0;                   // batches of the last pruned call (their survivor counts sit in h_icnt)
     int64_t prune_total = 0;          // (transform, sub-tile) pairs of the last pruned call
@@ -265,6 +267,7 @@ int sio_ctx_destroy(sio_ctx* c) {
     DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
     for (int k = 0; k < sio_ctx::kLsBack; ++k) if (c->ls_stream[k]) cudaStreamSynchronize(c->ls_stream[k]);
+    if (c->qp_side) { cudaStreamSynchronize(c->qp_side); cudaStreamDestroy(c->qp_side); cudaEventDestroy(c->qp_fork); cudaEventDestroy(c->qp_join); }
     for (auto& g : c->grids) if (g.live) { cudaFree(g.d_v); cudaFree(g.d_brick); cudaFree(g.d_lipd); cudaFree(g.d_meta); }
     for (auto& p : c->clouds) if (p.live) { cudaFree(p.d_pts); cudaFree(p.d_rep); cudaFree(p.d_perm); }
     for (auto& r : c->robots) if (r.live) { cudaFree(r.d_parent); cudaFree(r.d_jtype); cudaFree(r.d_tparent); cudaFree(r.d_axis); }
@@ -1118,7 +1121,10 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     // the context-owned arena that the next call re-carves
     struct BackgroundDrain {
         sio_ctx* c;
-        ~BackgroundDrain() { for (int k = 0; k < sio_ctx::kLsBack; ++k) if (c->ls_stream[k]) cudaStreamSynchronize(c->ls_stream[k]); }
+        ~BackgroundDrain() {
+            for (int k = 0; k < sio_ctx::kLsBack; ++k) if (c->ls_stream[k]) cudaStreamSynchronize(c->ls_stream[k]);
+            if (c->qp_side) cudaStreamSynchronize(c->qp_side);
+        }
     } drain{c};
     const auto entry0 = std::chrono::steady_clock::now();
     const int cap = cfg->cap;
@@ -1234,6 +1240,7 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
     // Deferral of QP stragglers (SIO_LS_DEFER = ADMM iteration budget of the in-line launch, 0 = off): see k_sip_qp
     const int defer_cap = getenv("SIO_LS_DEFER") ? atoi(getenv("SIO_LS_DEFER")) : 800;   // measured best of 150 ... 1600 at 8,192 and 65,536 problems
     const bool defer = defer_cap > 0 && defer_cap < qp_max_iter;
+    const bool qp_beside = !(getenv("SIO_QP_BESIDE") && atoi(getenv("SIO_QP_BESIDE")) == 0);   // 0: the two-row launch after the one-row launch
     if (defer) {
         for (int k = 0; k < sio_ctx::kLsBack; ++k) {
             if (!c->ls_stream[k]) {                        // lowest priority: the main stream's CTAs go first when an SM frees up
@@ -1242,6 +1249,11 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
                 CU(cudaStreamCreateWithPriority(&c->ls_stream[k], cudaStreamNonBlocking, lo_prio));
             }
             CU(c->s_qpb[k].ensure(sip_qp_scratch_bytes(c->num_sms)));
+        }
+        if (!c->qp_side) {
+            CU(cudaStreamCreateWithFlags(&c->qp_side, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&c->qp_fork, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->qp_join, cudaEventDisableTiming));
         }
         for (int k = 0; k < sio_ctx::kLsRing; ++k) {
             if (!c->ls_evA[k]) CU(cudaEventCreateWithFlags(&c->ls_evA[k], cudaEventDisableTiming));
@@ -1290,6 +1302,11 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
             CU(cudaMemsetAsync(dcount + slot, 0, sizeof(uint32_t), st));
             dfA.list = dlist[slot]; dfA.count = dcount + slot; dfA.done = S.qdone; dfA.mark = S.qdef; dfA.busy = S.ph;
             dfA.wide = wlist; dfA.wide_n = wcount;
+            // side by side only while the round is latency-bound (fewer problems than ~4 per resident one-row warp): there
+            // each launch lasts as long as its slowest problem and the two overlap; a throughput-bound round (65,536
+            // problems: 17 k still live at the end) is served best by each build's full grid, one after the other
+            // (measured: 8,192 problems 58.9 -> 56.0 ms, 65,536 problems 237 -> 247 ms when forced everywhere)
+            if (qp_beside && (int64_t)hc[4] <= 4 * 12 * (int64_t)c->num_sms) { dfA.side = c->qp_side; dfA.fork = c->qp_fork; dfA.join = c->qp_join; }
         }
         mark();
         if (launch_sip_qp(6, B, S.qW, S.dxdes, S.qlo, S.qhi, nullptr, S.qk, cap, S.rows, S.D, L.reg, L.inflation, 1e-5,

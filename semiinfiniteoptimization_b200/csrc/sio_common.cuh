@@ -140,6 +140,9 @@ struct QpDefer {
     const uint8_t* busy = nullptr;      // capped launch: problems with busy[p] == 1 are out with an earlier follow-up launch
     const int32_t* only = nullptr; const uint32_t* only_n = nullptr;
     int32_t* wide = nullptr; uint32_t* wide_n = nullptr;   // capped launch: room for the problems with two rows per lane (sio_qp.cu)
+    // host side only: with these set the two-row launch runs BESIDE the one-row launch on `side` (fork / join by the two
+    // events) instead of after it
+    cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr;
 };
 int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, const double* xmin, const double* xmax,
                   const int64_t* offs, const int32_t* cnt, int32_t stride, const double* rows, const double* depths, double reg,

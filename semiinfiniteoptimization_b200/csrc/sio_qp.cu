@@ -694,7 +694,7 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
     } else if (m <= 32) {
         solve_rows<N, 1>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
     } else if constexpr (MODE == kQpNarrow) {
-        if (lane == 0) df.wide[atomicAdd(df.wide_n, 1u)] = (int32_t)p;
+        // k_qp_list_wide listed it for the two-row launch
     } else {
         solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
     }
@@ -736,10 +736,25 @@ k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__
     }
 }
 
-int sip_qp_grid(int num_sms) { return num_sms * kQpCtasPerSm; }           // 8 resident warps per SM at 255 registers: measured best (3 x 168 and 4 x 128 spill and run slower alone and loaded)
-size_t sip_qp_scratch_bytes(int num_sms) { return (size_t)num_sms * kQpCtasNarrow * kQpWarps * kQpScratch * sizeof(double) + 64; }
+// The problems of a capped launch that need two rows per lane (32 < rows <= 64), listed BEFORE either solver kernel runs
+// so that the one-row and the two-row launch can share the device: late in a BASELINE configs[4] solve half of the live
+// problems are of this kind, and run one after the other each launch lasts as long as its own slowest problem.
+__global__ void k_qp_list_wide(int64_t nprob, const int32_t* __restrict__ cnt, int nbox, QpDefer df) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= nprob) return;
+    if (df.busy && df.busy[p] == 1) return;
+    const int k = cnt[p];
+    if (k <= 0) return;
+    const int m = k + nbox;
+    if (m > 32 && m <= kQpMaxRows) df.wide[atomicAdd(df.wide_n, 1u)] = (int32_t)p;
+}
 
-// scratch: sip_qp_scratch_bytes(num_sms) bytes; its last 64 bytes hold the work counter
+int sip_qp_grid(int num_sms) { return num_sms * kQpCtasPerSm; }           // 8 resident warps per SM at 255 registers: measured best (3 x 168 and 4 x 128 spill and run slower alone and loaded)
+// polish scratch of the one-row launch's warps, then of the two-row launch's (they run side by side), then the two work counters
+static size_t qp_narrow_doubles(int num_sms) { return (size_t)num_sms * kQpCtasNarrow * kQpWarps * kQpScratch; }
+size_t sip_qp_scratch_bytes(int num_sms) { return (qp_narrow_doubles(num_sms) + (size_t)num_sms * kQpCtasPerSm * kQpWarps * kQpScratch) * sizeof(double) + 128; }
+
+// scratch: sip_qp_scratch_bytes(num_sms) bytes; its last 128 bytes hold the work counters
 int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, const double* xmin, const double* xmax,
                   const int64_t* offs, const int32_t* cnt, int32_t stride, const double* rows, const double* depths, double reg,
                   double inflation, double eps_abs, int max_iter, double* dx, int32_t* status, void* scratch, int num_sms,
@@ -751,20 +766,41 @@ int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, con
     const int threads = df.only ? 32 : kQpWarps * 32;
     const int blocks = df.only ? sip_qp_grid(num_sms) * kQpWarps : sip_qp_grid(num_sms);
     double* kkt = reinterpret_cast<double*>(scratch);
-    unsigned long long* counter = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + sip_qp_scratch_bytes(num_sms) - 64);
-    cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + sip_qp_scratch_bytes(num_sms) - 128);
+    unsigned long long* counter2 = counter + 8;
+    cudaMemsetAsync(counter, 0, 128, st);
 #define SIO_QP_LAUNCH(N, MODE)                                                                                                   \
     k_sip_qp<N, MODE><<<blocks, threads, 0, st>>>(nprob, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, \
                                                   1e-5, max_iter, kkt, counter, dx, status, df)
     if (n != 6 && n != 7) return -1;
-    if (df.wide) {                                         // capped launch: narrow problems, then the ones it listed
+    if (df.wide) {                                         // capped launch: the two-row problems listed first, then both solvers
+        if (offs) return -1;                               // padded layout only (the lock-step solver's)
         cudaMemsetAsync(df.wide_n, 0, sizeof(uint32_t), st);
-        {
+        k_qp_list_wide<<<(unsigned)((nprob + 255) / 256), 256, 0, st>>>(nprob, cnt, xmin ? n : 0, df);
+        const bool beside = df.side && df.fork && df.join;
+        cudaStream_t wst = beside ? df.side : st;
+        if (beside) { cudaEventRecord(df.fork, st); cudaStreamWaitEvent(wst, df.fork, 0); }
+        if (!beside) {
             const int blocks = num_sms * kQpCtasNarrow;
             if (n == 6) SIO_QP_LAUNCH(6, kQpNarrow); else SIO_QP_LAUNCH(7, kQpNarrow);
         }
-        cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
-        if (n == 6) SIO_QP_LAUNCH(6, kQpWide); else SIO_QP_LAUNCH(7, kQpWide);
+        {
+            double* kkt_n = kkt;
+            double* kkt = kkt_n + qp_narrow_doubles(num_sms);
+            unsigned long long* counter = counter2;
+            cudaStream_t st = wst;
+            // beside the one-row launch: ONE two-row CTA per SM (255 registers x 128 threads = half the register file), which
+            // leaves room for a one-row CTA (168 x 128) next to it; alone, two per SM
+            const int blocks = beside ? num_sms : sip_qp_grid(num_sms);
+            if (n == 6) SIO_QP_LAUNCH(6, kQpWide); else SIO_QP_LAUNCH(7, kQpWide);
+        }
+        if (beside) {
+            // the two-row launch goes first: it has the fewer, longer problems, and the one-row CTAs fill the SMs around it
+            cudaEventRecord(df.join, wst);
+            const int blocks = num_sms * kQpCtasNarrow;
+            if (n == 6) SIO_QP_LAUNCH(6, kQpNarrow); else SIO_QP_LAUNCH(7, kQpNarrow);
+            cudaStreamWaitEvent(st, df.join, 0);
+        }
     } else {
         if (n == 6) SIO_QP_LAUNCH(6, kQpFull); else SIO_QP_LAUNCH(7, kQpFull);
     }
