@@ -1306,7 +1306,7 @@ int sio_lockstep_pose_solve(sio_ctx* c, sio_handle grid, sio_handle cloud, const
             // each launch lasts as long as its slowest problem and the two overlap; a throughput-bound round (65,536
             // problems: 17 k still live at the end) is served best by each build's full grid, one after the other
             // (measured: 8,192 problems 58.9 -> 56.0 ms, 65,536 problems 237 -> 247 ms when forced everywhere)
-            if (qp_beside && (int64_t)hc[4] <= 4 * 12 * (int64_t)c->num_sms) { dfA.side = c->qp_side; dfA.fork = c->qp_fork; dfA.join = c->qp_join; }
+            if (qp_beside && (int64_t)hc[4] <= 4 * 16 * (int64_t)c->num_sms) { dfA.side = c->qp_side; dfA.fork = c->qp_fork; dfA.join = c->qp_join; }
         }
         mark();
         if (launch_sip_qp(6, B, S.qW, S.dxdes, S.qlo, S.qhi, nullptr, S.qk, cap, S.rows, S.D, L.reg, L.inflation, 1e-5,

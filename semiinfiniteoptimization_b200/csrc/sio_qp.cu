@@ -19,12 +19,14 @@
 // iteration count varies from tens to thousands between problems.
 // Problems with more than 64 rows are flagged for the host solver.
 #include "sio_common.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace sio {
 
 constexpr int kQpWarps = 4;                 // warps per CTA
 constexpr int kQpCtasPerSm = 2;             // resident CTAs per SM the register budget is set for
-constexpr int kQpCtasNarrow = 3;            // the same for the one-row-per-lane build (168 registers)
+constexpr int kQpCtasNarrow = 4;            // the same for the one-row-per-lane build (128 registers: its loop-invariant operands sit in shared memory)
 constexpr int kQpMaxRows = 64;              // 2 rows per lane
 constexpr int kQpMaxVars = 8;
 constexpr int kQpMaxKkt = kQpMaxVars + kQpMaxRows;     // largest polish system (x + active rows)
@@ -250,10 +252,22 @@ __device__ bool warp_lu_solve(double* M, double* b, int NN, int lane) {
 
 // one lane's share of a problem: NR constraint rows (and, in the slack problem, their slack variables).  NR = 1 serves
 // problems with at most 32 rows (nearly all of them) at half the per-iteration work of NR = 2.
-template <int N, int NR>
+// SM (the one-row build of the lock-step solver's capped launch): everything the iteration loop only READS -- the lane's
+// row a_r, its K a_r (kb), its row of K (krow), and the problem's P, q -- lives in a per-warp block of shared memory instead
+// of registers, column `lane` of a [value][32] array each (P and q once, broadcast).  That is 64 registers less across the
+// loop, which lets the build fit 128 registers = 4 CTAs x 4 warps per SM with no spill inside the loop: the kernel is
+// bound by the latency of one dependent chain per warp, so resident warps are throughput.  The loads do not sit on that
+// chain (their addresses never change), and the arithmetic is the same operations on the same values.
+template <int N> __host__ __device__ constexpr int qp_ops_doubles() { return (N + 8 + N) * 32 + 2 * N; }
+template <int N, int NR, bool SM>
 struct Rows {
-    double a[NR][N], l[NR], u[NR];
+    double areg[SM ? 1 : NR][SM ? 1 : N], l[NR], u[NR];
     bool have[NR], slack[NR];               // row present; row has a slack variable (the k parameter rows)
+    double* op;                             // SM: the warp's operand block + lane
+    __device__ __forceinline__ double a(int s, int i) const { return SM ? op[i * 32] : areg[s][i]; }
+    __device__ __forceinline__ void set_a(int s, int i, double v) { if (SM) op[i * 32] = v; else areg[s][i] = v; }
+    __device__ __forceinline__ double kb(int j) const { return op[(N + j) * 32]; }
+    __device__ __forceinline__ double krow(int j) const { return op[(N + 8 + j) * 32]; }
 };
 
 enum { kAdmmSolved = 0, kAdmmMaxIter = 1, kAdmmInfeasible = 2 };
@@ -262,10 +276,15 @@ enum { kAdmmSolved = 0, kAdmmMaxIter = 1, kAdmmInfeasible = 2 };
 // the slack block carrying the quadratic weight `pen`.  x (and sv, the lane's slack values) hold the answer.
 // One instantiation serves both (a runtime flag): the unrolled body is large and two copies thrash the
 // instruction cache (ncu r01_qp: 64 % of the stall samples were instruction fetch).
-template <int N, int NR>
-__device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, const double (&Pd)[N], const double (&q)[N], double pen, int k, int m, double eps_abs,
+template <int N, int NR, bool SM>
+__device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR, SM>& R, const double (&Pd_)[SM ? 1 : N], const double (&q_)[SM ? 1 : N], double pen, int k, int m, double eps_abs,
                     double eps_rel, int max_iter, double* kkt, double* skkt, int lane, double (&x)[N], double (&sv)[NR], int& iters) {
+    static_assert(!SM || NR == 1, "shared-memory operands: one row per lane");
     constexpr double kInf = 1e20, sigma = 1e-6, alpha = 1.6;
+    // P and q: registers, or (SM) the broadcast tail of the warp's operand block
+    const double* const pq = SM ? R.op - lane + (N + 8 + N) * 32 : nullptr;
+    auto Pd = [&](int i) -> double { return SM ? pq[i] : Pd_[SM ? 0 : i]; };
+    auto q = [&](int i) -> double { return SM ? pq[N + i] : q_[SM ? 0 : i]; };
     constexpr int check_every = 10, adapt_every = 50;
     double z[NR], y[NR], rv[NR], dy[NR], Ax[NR], ds[NR];
 #pragma unroll
@@ -276,7 +295,9 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
     // sum over rows of (K a_r) w_r + K (sigma x - q): each lane keeps kb = K a_r for its rows (in Sum8's slot order), so
     // that ONE warp sum delivers K A'w, and the lane that the sum leaves total i on keeps row i of K (krow; kq = krow . q)
     // to add (K (sigma x - q))_i before the totals are broadcast.  K itself lives only inside set_rho.
-    double kb[NR][8], krow[N], kq = 0.0;
+    double kb_[SM ? 1 : NR][SM ? 1 : 8], krow_[SM ? 1 : N], kq = 0.0;
+    auto KB = [&](int s, int j) -> double { return SM ? R.kb(j) : kb_[SM ? 0 : s][SM ? 0 : j]; };
+    auto KROW = [&](int j) -> double { return SM ? R.krow(j) : krow_[SM ? 0 : j]; };
     auto set_rho = [&]() {
         SpdInverse<N> K;
 #pragma unroll
@@ -301,7 +322,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
                 for (int s = 0; s < NR; ++s)
                     if (R.have[s]) {
                         const double wgt = (SLACK && R.slack[s]) ? rv[s] - rv[s] * rv[s] * ids[s] : rv[s];   // Schur complement
-                        v += wgt * R.a[s][i] * R.a[s][j];
+                        v += wgt * R.a(s, i) * R.a(s, j);
                     }
                 part[e] = v;
             }
@@ -311,7 +332,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
                 int i = 0;
                 while ((i + 1) * (i + 2) / 2 <= c0 + e) ++i;
                 const int j = c0 + e - i * (i + 1) / 2;
-                K.A[c0 + e] = part[e] + ((i == j) ? Pd[i] + sigma : 0.0);
+                K.A[c0 + e] = part[e] + ((i == j) ? Pd(i) + sigma : 0.0);
             }
         }
         if (!K.invert()) return false;
@@ -322,7 +343,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
             for (int i = 0; i < N; ++i) {
                 double v = 0.0;
 #pragma unroll
-                for (int j = 0; j < N; ++j) v += K.sym(i, j) * R.a[s][j];
+                for (int j = 0; j < N; ++j) v += K.sym(i, j) * R.a(s, j);
                 ka[i] = v;
             }
 #pragma unroll
@@ -331,7 +352,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
                 double v = 0.0;
 #pragma unroll
                 for (int i = 0; i < N; ++i) v = (want == i) ? ka[i] : v;
-                kb[s][j] = v;
+                if (SM) R.op[(N + j) * 32] = v; else kb_[SM ? 0 : s][SM ? 0 : j] = v;
             }
         }
         kq = 0.0;
@@ -340,8 +361,8 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
             double v = 0.0;
 #pragma unroll
             for (int i = 0; i < N; ++i) v = (((lane >> 2) & 7) == i) ? K.sym(i, j) : v;
-            krow[j] = v;
-            kq += v * q[j];
+            if (SM) R.op[(N + 8 + j) * 32] = v; else krow_[SM ? 0 : j] = v;
+            kq += v * q(j);
         }
         return true;
     };
@@ -394,19 +415,19 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
                 double ws = w[s];
                 if (SLACK && R.slack[s]) ws -= rv[s] * (sigma * sv[s] + w[s]) * ids[s];     // eliminate the slack unknown
 #pragma unroll
-                for (int j = 0; j < 8; ++j) part[j] = (s == 0) ? kb[0][j] * ws : fma(kb[s][j], ws, part[j]);   // kb = 0 on absent rows
+                for (int j = 0; j < 8; ++j) part[j] = (s == 0) ? KB(0, j) * ws : fma(KB(s, j), ws, part[j]);   // kb = 0 on absent rows
             }
-            double kx = krow[0] * x[0];
+            double kx = KROW(0) * x[0];
 #pragma unroll
-            for (int j = 1; j < N; ++j) kx = fma(krow[j], x[j], kx);
+            for (int j = 1; j < N; ++j) kx = fma(KROW(j), x[j], kx);
             Sum8::gather(Sum8::scatter(part) + fma(sigma, kx, -kq), xt);
         }
         double ndy = 0.0;
 #pragma unroll
         for (int s = 0; s < NR; ++s) {
-            double ax = R.a[s][0] * xt[0];
+            double ax = R.a(s, 0) * xt[0];
 #pragma unroll
-            for (int i = 1; i < N; ++i) ax = fma(R.a[s][i], xt[i], ax);
+            for (int i = 1; i < N; ++i) ax = fma(R.a(s, i), xt[i], ax);
             double zs = ax;
             if (SLACK && R.slack[s]) {
                 stl[s] = (sigma * sv[s] + w[s] - rv[s] * ax) * ids[s];
@@ -437,7 +458,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
         for (int s = 0; s < NR; ++s) {
             double v = 0.0;
 #pragma unroll
-            for (int i = 0; i < N; ++i) { v += R.a[s][i] * x[i]; Aty[i] += R.a[s][i] * y[s]; }
+            for (int i = 0; i < N; ++i) { const double ai = R.a(s, i); v += ai * x[i]; Aty[i] += ai * y[s]; }
             if (SLACK && R.slack[s]) {
                 v += sv[s];
                 const double ps = pen * sv[s];                          // dual residual of the slack variable: pen s + y
@@ -458,9 +479,9 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const double t = Aty[i];
-            const double px = Pd[i] * x[i];
-            r_dual = max_nn(r_dual, fabs(px + q[i] + t));
-            nd = max_nn(nd, max_nn(fabs(px), max_nn(fabs(t), fabs(q[i]))));
+            const double px = Pd(i) * x[i];
+            r_dual = max_nn(r_dual, fabs(px + q(i) + t));
+            nd = max_nn(nd, max_nn(fabs(px), max_nn(fabs(t), fabs(q(i)))));
         }
         if (__all_sync(0xffffffffu, r_prim <= eps_abs + eps_rel * nAx && r_dual <= eps_abs + eps_rel * nd)) { st = kAdmmSolved; break; }
         if (__all_sync(0xffffffffu, ndy > 1e-12)) {       // primal infeasibility certificate
@@ -472,7 +493,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
             for (int s = 0; s < NR; ++s) {
                 const double d = dy[s] * indy;
 #pragma unroll
-                for (int i = 0; i < N; ++i) t[i] += R.a[s][i] * d;
+                for (int i = 0; i < N; ++i) t[i] += R.a(s, i) * d;
                 if (R.have[s]) t[N] += R.u[s] * fmax(d, 0.0) + R.l[s] * fmin(d, 0.0);
             }
             AllSum<N + 1>::all(t, lane);
@@ -518,7 +539,9 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
     for (int e = lane; e < NN * (NN + 1); e += 32) M[e] = 0.0;
     __syncwarp();
     const double delta = 1e-10;
-    if (lane < N) { M[lane * NN + lane] = Pd[lane] + delta; bb[lane] = -q[lane]; }
+    #pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (lane == i) { M[i * NN + i] = Pd(i) + delta; bb[i] = -q(i); }
     int idx[NR];
 #pragma unroll
     for (int s = 0; s < NR; ++s) idx[s] = 0;
@@ -527,7 +550,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
         if (flag[s]) {                                     // active rows keep their row order
             idx[s] = N + ((s == 0) ? __popc(m0 & ((1u << lane) - 1u)) : __popc(m0) + __popc(m1 & ((1u << lane) - 1u)));
 #pragma unroll
-            for (int i = 0; i < N; ++i) { M[i * NN + idx[s]] = R.a[s][i]; M[idx[s] * NN + i] = R.a[s][i]; }
+            for (int i = 0; i < N; ++i) { const double ai = R.a(s, i); M[i * NN + idx[s]] = ai; M[idx[s] * NN + i] = ai; }
             M[idx[s] * NN + idx[s]] = -delta - ((SLACK && R.slack[s]) ? 1.0 / (pen + delta) : 0.0);
             bb[idx[s]] = rhs[s];
         }
@@ -558,7 +581,7 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
     for (int s = 0; s < NR; ++s) {
         double v = 0.0;
 #pragma unroll
-        for (int i = 0; i < N; ++i) v += R.a[s][i] * xp[i];
+        for (int i = 0; i < N; ++i) v += R.a(s, i) * xp[i];
         if (SLACK && R.slack[s]) {
             sp[s] = flag[s] ? -lam[s] / (pen + delta) : 0.0;
             if (!isfinite(sp[s])) bad = 1;
@@ -581,21 +604,32 @@ __device__ __forceinline__ int admm(const bool SLACK, const Rows<N, NR>& R, cons
 // status codes written per problem (low byte; the ADMM iteration count sits above it)
 enum { kQpStrict = 0, kQpSlack = 1, kQpNoRows = 2, kQpToHost = 3, kQpDeferred = 4 };
 
-template <int N, int NR>
+template <int N, int NR, bool SM = false>
 __device__ __forceinline__ void solve_rows(int64_t p, int k, int m, int64_t base, bool box, const double* __restrict__ W,
                                            const double* __restrict__ xdes, const double* __restrict__ xmin, const double* __restrict__ xmax,
                                            const double* __restrict__ rows, const double* __restrict__ depths, double reg, double inflation,
-                                           double eps_abs, double eps_rel, int max_iter, double* kkt, double* skkt, int lane, double* __restrict__ dx,
+                                           double eps_abs, double eps_rel, int max_iter, double* kkt, double* skkt, double* sop, int lane, double* __restrict__ dx,
                                            int32_t* __restrict__ status, const QpDefer& df) {
     constexpr double kInf = 1e20;
-    double Pd[N], q[N];
+    double Pd[SM ? 1 : N], q[SM ? 1 : N];
+    Rows<N, NR, SM> R;
+    R.op = SM ? sop + lane : nullptr;
+    if (SM) {
+        __syncwarp();                                          // the previous problem's readers are done with the block
+        if (lane < N) {
+            const double w = W[p * N + lane];
+            sop[(N + 8 + N) * 32 + lane] = w + reg;
+            sop[(N + 8 + N) * 32 + N + lane] = -w * xdes[p * N + lane];
+        }
+        __syncwarp();
+    } else {
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const double w = W[p * N + i];
-        Pd[i] = w + reg;
-        q[i] = -w * xdes[p * N + i];
+        for (int i = 0; i < N; ++i) {
+            const double w = W[p * N + i];
+            Pd[SM ? 0 : i] = w + reg;
+            q[SM ? 0 : i] = -w * xdes[p * N + i];
+        }
     }
-    Rows<N, NR> R;
     double bneg2 = 0.0, bmin = INFINITY;
     int nneg = 0;
 #pragma unroll
@@ -605,18 +639,18 @@ __device__ __forceinline__ void solve_rows(int64_t p, int k, int m, int64_t base
         R.slack[s] = r < k;
         R.l[s] = -kInf; R.u[s] = kInf;
 #pragma unroll
-        for (int i = 0; i < N; ++i) R.a[s][i] = 0.0;
+        for (int i = 0; i < N; ++i) R.set_a(s, i, 0.0);
         if (r < k) {
             const double* src = rows + (base + r) * N;
 #pragma unroll
-            for (int i = 0; i < N; ++i) R.a[s][i] = src[i];
+            for (int i = 0; i < N; ++i) R.set_a(s, i, src[i]);
             const double b = depths[base + r];
             R.l[s] = -b + inflation;
             if (b < 0) { bneg2 += b * b; ++nneg; }
             bmin = fmin(bmin, b);
         } else if (r < m) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) R.a[s][i] = (i == r - k) ? 1.0 : 0.0;
+            for (int i = 0; i < N; ++i) R.set_a(s, i, (i == r - k) ? 1.0 : 0.0);
             R.l[s] = fmax(xmin[p * N + (r - k)], -kInf);
             R.u[s] = fmin(xmax[p * N + (r - k)], kInf);
         }
@@ -632,7 +666,7 @@ __device__ __forceinline__ void solve_rows(int64_t p, int k, int m, int64_t base
     int iters = 0, code = kQpStrict;
     double pen = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
-        const int st = admm<N, NR>(pass == 1, R, Pd, q, pen, k, m, eps_abs, eps_rel, max_iter, kkt, skkt, lane, x, sv, iters);
+        const int st = admm<N, NR, SM>(pass == 1, R, Pd, q, pen, k, m, eps_abs, eps_rel, max_iter, kkt, skkt, lane, x, sv, iters);
         if (df.list && st == kAdmmMaxIter) {              // capped launch: out of budget -> the follow-up launch solves it in full
             if (lane == 0) {
                 status[p] = kQpDeferred;
@@ -671,7 +705,7 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
                               const double* __restrict__ xmax, const int64_t* __restrict__ offs, const int32_t* __restrict__ cnt,
                               int32_t stride, const double* __restrict__ rows,
                               const double* __restrict__ depths, double reg, double inflation, double eps_abs, double eps_rel,
-                              int max_iter, double* kkt, double* skkt, int lane, double* __restrict__ dx, int32_t* __restrict__ status,
+                              int max_iter, double* kkt, double* skkt, double* sop, int lane, double* __restrict__ dx, int32_t* __restrict__ status,
                               const QpDefer& df) {
     constexpr double kInf = 1e20;
     // ragged layout: rows of problem p at offs[p] .. offs[p+1];  padded layout (lock-step solver): cnt[p] rows at
@@ -690,13 +724,13 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
     const int m = k + (box ? N : 0);
     if (m > kQpMaxRows) { if (lane == 0) status[p] = kQpToHost; return; }
     if constexpr (MODE == kQpWide) {                       // the narrow launch listed it: two rows per lane
-        solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
+        solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, sop, lane, dx, status, df);
     } else if (m <= 32) {
-        solve_rows<N, 1>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
+        solve_rows<N, 1, MODE == kQpNarrow>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, sop, lane, dx, status, df);
     } else if constexpr (MODE == kQpNarrow) {
         // k_qp_list_wide listed it for the two-row launch
     } else {
-        solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
+        solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, sop, lane, dx, status, df);
     }
 }
 
@@ -718,6 +752,8 @@ k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__
     double* kkt = scratch + (blockDim.x == 32 ? (size_t)blockIdx.x : (size_t)blockIdx.x * kQpWarps + (threadIdx.x >> 5)) * kQpScratch;
     __shared__ double s_kkt[kQpWarps][kQpSmemScratch];
     double* skkt = s_kkt[threadIdx.x >> 5];
+    __shared__ double s_op[MODE == kQpNarrow ? kQpWarps : 1][MODE == kQpNarrow ? qp_ops_doubles<N>() : 1];   // Rows<.., SM>
+    double* sop = s_op[MODE == kQpNarrow ? (threadIdx.x >> 5) : 0];
     const unsigned long long limit = MODE == kQpWide ? (unsigned long long)*df.wide_n
                                                      : (df.only ? (unsigned long long)*df.only_n : (unsigned long long)nprob);
     for (;;) {
@@ -727,7 +763,7 @@ k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__
         if (i >= limit) return;
         const int64_t p = MODE == kQpWide ? (int64_t)df.wide[i] : (df.only ? (int64_t)df.only[i] : (int64_t)i);
         if (MODE != kQpWide && df.busy && df.busy[p] == 1) continue;
-        solve_problem<N, MODE>(p, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, lane, dx, status, df);
+        solve_problem<N, MODE>(p, W, xdes, xmin, xmax, offs, cnt, stride, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, sop, lane, dx, status, df);
         if (df.only) {                                     // publish: answer first, flag second
             __threadfence();
             __syncwarp();
@@ -775,6 +811,16 @@ int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, con
     if (n != 6 && n != 7) return -1;
     if (df.wide) {                                         // capped launch: the two-row problems listed first, then both solvers
         if (offs) return -1;                               // padded layout only (the lock-step solver's)
+        static const bool once = [] {                      // SIO_LS_PROFILE: resident CTAs per SM the driver grants each build
+            if (getenv("SIO_LS_PROFILE")) {
+                int a = 0, b = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_sip_qp<6, kQpNarrow>, kQpWarps * 32, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_sip_qp<6, kQpWide>, kQpWarps * 32, 0);
+                fprintf(stderr, "[sio qp] resident CTAs per SM: one-row build %d, two-row build %d\n", a, b);
+            }
+            return true;
+        }();
+        (void)once;
         cudaMemsetAsync(df.wide_n, 0, sizeof(uint32_t), st);
         k_qp_list_wide<<<(unsigned)((nprob + 255) / 256), 256, 0, st>>>(nprob, cnt, xmin ? n : 0, df);
         const bool beside = df.side && df.fork && df.join;
