@@ -698,7 +698,7 @@ __device__ __forceinline__ void solve_rows(int64_t p, int k, int m, int64_t base
 // the two-row solver.  In one kernel the two-row instantiation (70 % of the instructions) sets the register allocation
 // and the one-row loop -- where the launch spends its time -- runs with spills; apart it has 222 registers and none
 // (profiles/r02_qp_phases.md: in-line QP time of BASELINE configs[4] 0.217 -> 0.16 s).
-enum { kQpFull = 0, kQpNarrow = 1, kQpWide = 2 };
+enum { kQpFull = 0, kQpNarrow = 1, kQpWide = 2, kQpNarrowReg = 3 };   // kQpNarrowReg: the one-row build with every operand in registers (168, 3 CTAs per SM)
 
 template <int N, int MODE>
 __device__ void solve_problem(int64_t p, const double* __restrict__ W, const double* __restrict__ xdes, const double* __restrict__ xmin,
@@ -727,7 +727,7 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
         solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, sop, lane, dx, status, df);
     } else if (m <= 32) {
         solve_rows<N, 1, MODE == kQpNarrow>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, sop, lane, dx, status, df);
-    } else if constexpr (MODE == kQpNarrow) {
+    } else if constexpr (MODE == kQpNarrow || MODE == kQpNarrowReg) {
         // k_qp_list_wide listed it for the two-row launch
     } else {
         solve_rows<N, 2>(p, k, m, base, box, W, xdes, xmin, xmax, rows, depths, reg, inflation, eps_abs, eps_rel, max_iter, kkt, skkt, sop, lane, dx, status, df);
@@ -741,7 +741,7 @@ __device__ void solve_problem(int64_t p, const double* __restrict__ W, const dou
 // problem p's answer is in memory.  A launch lasts as long as its slowest problem; this keeps the 4000-iteration
 // stragglers (0.5 % of the problems) off the critical path of the other 99.5 %.
 template <int N, int MODE>
-__global__ void __launch_bounds__(kQpWarps * 32, MODE == kQpNarrow ? kQpCtasNarrow : kQpCtasPerSm)
+__global__ void __launch_bounds__(kQpWarps * 32, MODE == kQpNarrow ? kQpCtasNarrow : (MODE == kQpNarrowReg ? 3 : kQpCtasPerSm))
 k_sip_qp(int64_t nprob, const double* __restrict__ W, const double* __restrict__ xdes, const double* __restrict__ xmin,
          const double* __restrict__ xmax, const int64_t* __restrict__ offs, const int32_t* __restrict__ cnt, int32_t stride,
          const double* __restrict__ rows,
@@ -826,10 +826,17 @@ int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, con
         const bool beside = df.side && df.fork && df.join;
         cudaStream_t wst = beside ? df.side : st;
         if (beside) { cudaEventRecord(df.fork, st); cudaStreamWaitEvent(wst, df.fork, 0); }
-        if (!beside) {
-            const int blocks = num_sms * kQpCtasNarrow;
-            if (n == 6) SIO_QP_LAUNCH(6, kQpNarrow); else SIO_QP_LAUNCH(7, kQpNarrow);
-        }
+        static const bool reg_build = getenv("SIO_QP_REGS") && atoi(getenv("SIO_QP_REGS")) != 0;   // A/B aid: operands in registers
+        auto launch_narrow = [&]() {
+            if (reg_build) {
+                const int blocks = num_sms * 3;
+                if (n == 6) SIO_QP_LAUNCH(6, kQpNarrowReg); else SIO_QP_LAUNCH(7, kQpNarrowReg);
+            } else {
+                const int blocks = num_sms * kQpCtasNarrow;
+                if (n == 6) SIO_QP_LAUNCH(6, kQpNarrow); else SIO_QP_LAUNCH(7, kQpNarrow);
+            }
+        };
+        if (!beside) launch_narrow();
         {
             double* kkt_n = kkt;
             double* kkt = kkt_n + qp_narrow_doubles(num_sms);
@@ -843,8 +850,7 @@ int launch_sip_qp(int n, int64_t nprob, const double* W, const double* xdes, con
         if (beside) {
             // the two-row launch goes first: it has the fewer, longer problems, and the one-row CTAs fill the SMs around it
             cudaEventRecord(df.join, wst);
-            const int blocks = num_sms * kQpCtasNarrow;
-            if (n == 6) SIO_QP_LAUNCH(6, kQpNarrow); else SIO_QP_LAUNCH(7, kQpNarrow);
+            launch_narrow();
             cudaStreamWaitEvent(st, df.join, 0);
         }
     } else {
