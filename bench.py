@@ -366,9 +366,11 @@ def sip_leg(ctx, rank, world, want_cpu):
            "records_s_per_rank": None if per_rank is None else [round(float(v), 6) for v in per_rank[:, 1]],
            "gather_incl_wait_s_per_rank": None if per_rank is None else [round(float(v), 6) for v in per_rank[:, 2]],
            "limiting_term": "in-line QP launches (k_sip_qp): a launch lasts as long as its slowest problem under the 800-iteration "
-                            "budget (0.34 ms) plus ~(problems per rank / 1,776 resident warps) x 160 us of ADMM + polish per problem (12 warps share "
-                            "an SM; profiles/r02_qp_phases.md), so it shrinks "
-                            "less than linearly with the shard; then the fixed per-round host sequencing (2 counter read-backs, ~12 launches)",
+                            "budget (0.34 ms) plus ~(problems per rank / 2,368 resident warps) x 160 us of ADMM + polish per problem (16 warps share "
+                            "an SM and its L1 data pipe; profiles/r02_qp_phases.md, r02_qp_smem_operands_full.txt), so it shrinks "
+                            "less than linearly with the shard: a rank of an 8-GPU run spends ~56 rounds x 0.9 ms of mostly latency "
+                            "(QP 0.5, two sweeps 0.3, ~14 bookkeeping launches and 2 counter read-backs 0.1); two concurrent slices per GPU "
+                            "overlap one slice's QP with the other's sweeps",
            "oracle_point_queries_resolved": int(rec[4].item()), "started_in_collision": int(rec[6].item()),
            "ended_feasible(g>-5e-3)": int(rec[5].item())}
     if want_cpu:
