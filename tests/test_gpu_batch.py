@@ -242,3 +242,29 @@ def test_concurrent_slices_give_the_single_context_answers(ctx):
         tiny = many.solve(poses[:1], settings=st)
         assert np.array_equal(tiny.T, ref.T[:1])
         many.close()
+
+
+@pytest.mark.gpu
+def test_concurrent_slices_with_targets_and_a_moved_environment(ctx):
+    """GroupedPoseSolver with separate target poses and the environment placed by env_T: the same answers as
+    optimizeCollFreeBatchDevice on PenetrationDepthGeometry objects set up by hand."""
+    from semiinfiniteoptimization_b200 import batch, geometryopt as G, sip
+    from semiinfiniteoptimization_b200._host import se3, so3
+    cube, chair = util.fixture_geometry("cube"), util.fixture_geometry("m797")
+    env_T = (so3.identity(), [1.2, 0.0, 0.0])
+    Tinit = c1_poses(96, seed=21)
+    Tdes = c1_poses(96, seed=22)
+    st = sip.SemiInfiniteOptimizationSettings()
+    st.max_iters = 15
+    g1 = G.PenetrationDepthGeometry(cube, 0.05, None, context=ctx)
+    g2 = G.PenetrationDepthGeometry(chair, None, 0.02, context=ctx)
+    g2.setTransform(env_T)
+    ref = batch.optimizeCollFreeBatchDevice(g1, g2, Tinit, Tdes, settings=st, context=ctx)
+    solver = batch.GroupedPoseSolver(cube, 0.05, chair, pcres=0.02, groups=2, context=ctx, env_T=env_T)
+    res = solver.solve(Tinit, Tdes, settings=st)
+    solver.close()
+    assert np.array_equal(res.T, ref.T) and np.array_equal(res.num_iterations, ref.num_iterations)
+    assert np.array_equal(res.status_codes, ref.status_codes)
+    assert (ref.num_iterations > 1).sum() > 10                       # the targets differ from the starts: real work was done
+    moved = np.abs(ref.T - np.array([se3.to_rowmajor12(T) for T in Tinit])).max(1)
+    assert (moved > 1e-3).mean() > 0.5
