@@ -260,6 +260,10 @@ def solve_qp_batch(P, q, A, l, u, nrows, iters=400, rho=0.1, sigma=1e-6, alpha=1
 NATIVE_BANDED = True
 # the same for small dense problems with a diagonal quadratic term (poses, configurations): ADMM natively, polish in numpy
 NATIVE_DENSE = True
+# ... and their polish too (hostqp.c's own Gaussian elimination instead of numpy's block matrix + LAPACK solve: the same
+# rule and the same system, answers equal to rounding -- 1e-15 relative on the polished x; the golden traces, compared at
+# 1e-8, do not move).  C1: 24 of 147 ms of eight optimizeCollFree runs were this numpy code.
+NATIVE_POLISH = True
 MAX_BANDWIDTH = 64
 
 
@@ -272,13 +276,18 @@ def _solve_qp_native_diag(P, d, q, A, l, u, eps_abs, eps_rel, max_iter, rho, sig
     x, y = np.zeros(n), np.zeros(m)
     iters = C.c_int(0)
     r_prim, r_dual = C.c_double(0.0), C.c_double(0.0)
-    st = _native_lib().hqp_admm_diag(n, m, dd.ctypes.data, qq.ctypes.data, Ac.ctypes.data, ll.ctypes.data, uu.ctypes.data, eps_abs, eps_rel,
-                                     int(max_iter), rho, sigma, alpha, x.ctypes.data, y.ctypes.data, C.byref(iters), C.byref(r_prim),
-                                     C.byref(r_dual))
+    if NATIVE_POLISH:
+        st = _native_lib().hqp_solve_diag(n, m, dd.ctypes.data, qq.ctypes.data, Ac.ctypes.data, ll.ctypes.data, uu.ctypes.data, eps_abs, eps_rel,
+                                          int(max_iter), rho, sigma, alpha, 1 if polish else 0, x.ctypes.data, y.ctypes.data, C.byref(iters),
+                                          C.byref(r_prim), C.byref(r_dual))
+    else:
+        st = _native_lib().hqp_admm_diag(n, m, dd.ctypes.data, qq.ctypes.data, Ac.ctypes.data, ll.ctypes.data, uu.ctypes.data, eps_abs, eps_rel,
+                                         int(max_iter), rho, sigma, alpha, x.ctypes.data, y.ctypes.data, C.byref(iters), C.byref(r_prim),
+                                         C.byref(r_dual))
     if st < 0:
         return None
     name = ("solved", "max iterations", "primal infeasible")[st]
-    if name == "solved" and polish:
+    if name == "solved" and polish and not NATIVE_POLISH:
         xp = _polish(P, q, A, l, u, x, y, False)
         if xp is not None:
             x = xp
@@ -367,6 +376,9 @@ def _native_lib():
         L.hqp_admm_diag.argtypes = [C.c_int, C.c_int, P, P, P, P, P, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double,
                                     P, P, P, P, P]
         L.hqp_admm_diag.restype = C.c_int
+        L.hqp_solve_diag.argtypes = [C.c_int, C.c_int, P, P, P, P, P, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double,
+                                     C.c_int, P, P, P, P, P]
+        L.hqp_solve_diag.restype = C.c_int
         _native = L
     return _native
 

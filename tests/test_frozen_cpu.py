@@ -107,6 +107,8 @@ def test_osqp_default_settings_are_switchable_and_land_within_their_tolerance():
 
 def test_real_osqp_if_importable():
     osqp = pytest.importorskip("osqp")
+    if getattr(osqp, "_sio_shim", False):                   # oracle/refrun's stand-in, installed by an earlier test of this process
+        pytest.skip("only the stand-in osqp module is present")
     import scipy.sparse
     from oracle.frozen import qp as fq
     for w, xdes, rows, depths, trs in _sip_shaped_qps(5, 20):
@@ -182,6 +184,8 @@ def test_real_klampt_if_importable():
     oracle.query / oracle.min_distance on the same VolumeGrid samples.  This is the test that can correct the oracle's
     named Klampt-side choices (cell-centred samples, outside-bbox rule, gradient convention) by evidence."""
     klampt = pytest.importorskip("klampt")
+    if getattr(klampt, "_sio_shim", False):                 # oracle/refrun's stand-in, installed by an earlier test of this process
+        pytest.skip("only the stand-in klampt module is present")
     from oracle import oracle as O
     vg0 = util.sphere_grid(r=0.7, n=32)
     vg = klampt.VolumeGrid()
