@@ -850,7 +850,12 @@ def main():
                             "dram_fraction_measured": (traffic / (bulk * 1e-3) / 1e9 / hbm_peak) if traffic else None,
                             "note": "SURVEY 8d's algorithmic 48 B/query x queries / kernel time exceeds the HBM peak because those bytes "
                                     "are served by L1/L2, not DRAM: `dram_fraction_measured` = ncu DRAM bytes per launch / time / peak"},
-                    "l2_gather_peak_gbs": gather_peak}
+                    "l2_gather_peak_gbs": gather_peak,
+                    # what ncu's own counter says of the same pipe, all of its traffic included (bricks + cloud tiles + the
+                    # transform records read from shared memory + lane groups that straddle cache lines): a committed capture
+                    # of this kernel on this workload, not a live measurement
+                    "pipe_busy_ncu": {"l1tex__throughput_pct_of_peak": 75.4, "binding_sub_unit": "l1tex__data_pipe_lsu_wavefronts", "issue_active_pct": 46.6,
+                                      "source": "profiles/r02_ffma2_kmin_full.txt, profiles/r02_kmin_evidence.md (ncu --set full, 64 poses x 2^20 points)"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "ms_per_step_median": float(np.median(ms_steps)), "exchange": exchange,
                 "minvalue_calls_per_s": value / CLOUD_N,            # one call = one pose against the whole cloud
