@@ -741,8 +741,9 @@ def main():
                   "note": "SIO_PRUNE: Lipschitz lower bound per 128-point sub-tile (the GPU analogue of Klampt's bounding-hierarchy "
                           "search inside distance_ext); effective = all (pose, point) pairs resolved / time"}
 
-    # SURVEY.md 8d also asks for the per-point output modes of the same sweep (value-only, value+gradient); these ARE
-    # HBM-bound (4 B / 16 B written per query), so the HBM roofline means something for them
+    # SURVEY.md 8d also asks for the per-point output modes of the same sweep (value-only, value+gradient); they write
+    # 4 B / 16 B per query to HBM, so an HBM fraction means something for them (the gradient mode reaches 0.71 of the copy
+    # peak) -- what binds them is still the L1 data pipe (ncu: profiles/r02_k1_modes_full.txt)
     modes = None
     if rank == 0:
         N_ = CLOUD_N
@@ -768,7 +769,10 @@ def main():
             gbs = B * N_ * (wbytes + 16.0 / 32) / (t_m * 1e-3) / 1e9          # written bytes + the cloud read once per 32-pose chunk
             modes[name] = {"queries_per_s": B * N_ / (t_m * 1e-3), "ms": t_m,
                            "hbm": {"achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
-                                   "bytes_per_query": wbytes + 0.5}}
+                                   "bytes_per_query": wbytes + 0.5},
+                           # ncu (profiles/r02_k1_modes_full.txt): like the K2 bulk kernel, both modes keep the L1 data pipe 75 %
+                           # busy (brick loads + the stores themselves); DRAM is 19 % / 55 % busy
+                           "bound": "l1_data_pipe"}
         del outg
 
     sip_rec = None
