@@ -287,11 +287,9 @@ __device__ __forceinline__ float warp_subtile_min(const XfRec& r, const GridK& g
 // PAIR is 9 FFMA2 (matrix entries broadcast), floor / fraction 3 x (FADD2.RZ, FADD2, FADD2), and each point's Horner
 // evaluation 3 FFMA2 + 1 FFMA on the brick's register pairs -- 13 floating-point instructions per query instead of 25,
 // with bit-identical results (each half is the same IEEE fma / add as the scalar path).
-__device__ __forceinline__ float warp_subtile_min_packed(const XfRec& r, const GridK& g, const f32x2 (&PX)[kPtsPerThread / 2],
-                                                         const f32x2 (&PY)[kPtsPerThread / 2], const f32x2 (&PZ)[kPtsPerThread / 2],
-                                                         int32_t b, int32_t base, int lane, Cand* __restrict__ cand,
-                                                         unsigned long long* __restrict__ cand_count, uint32_t cand_cap) {
-    float d[kPtsPerThread];
+__device__ __forceinline__ void subtile_values_packed(const XfRec& r, const GridK& g, const f32x2 (&PX)[kPtsPerThread / 2],
+                                                      const f32x2 (&PY)[kPtsPerThread / 2], const f32x2 (&PZ)[kPtsPerThread / 2],
+                                                      float (&d)[kPtsPerThread]) {
     const float big = 8388608.0f;
     const f32x2 BIG = pk2(big, big);
 #pragma unroll
@@ -318,6 +316,14 @@ __device__ __forceinline__ float warp_subtile_min_packed(const XfRec& r, const G
             d[2 * h + e] = fmaf(ee, fx[e], ff);
         }
     }
+}
+
+__device__ __forceinline__ float warp_subtile_min_packed(const XfRec& r, const GridK& g, const f32x2 (&PX)[kPtsPerThread / 2],
+                                                         const f32x2 (&PY)[kPtsPerThread / 2], const f32x2 (&PZ)[kPtsPerThread / 2],
+                                                         int32_t b, int32_t base, int lane, Cand* __restrict__ cand,
+                                                         unsigned long long* __restrict__ cand_count, uint32_t cand_cap) {
+    float d[kPtsPerThread];
+    subtile_values_packed(r, g, PX, PY, PZ, d);
     float best = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
     if (best < r.thr) {                                    // rare: candidates for the under-bound set
 #pragma unroll
@@ -794,6 +800,11 @@ k_cloud_query_f32(const float4* __restrict__ pts, const float4* __restrict__ rep
         float4 p = __ldg(pts + base + j * 32 + lane);
         px[j] = p.x; py[j] = p.y; pz[j] = p.z;
     }
+    f32x2 PX[kPtsPerThread / 2], PY[kPtsPerThread / 2], PZ[kPtsPerThread / 2];      // the same points as register pairs (value-only mode)
+#pragma unroll
+    for (int h = 0; h < kPtsPerThread / 2; ++h) {
+        PX[h] = pk2(px[2 * h], px[2 * h + 1]); PY[h] = pk2(py[2 * h], py[2 * h + 1]); PZ[h] = pk2(pz[2 * h], pz[2 * h + 1]);
+    }
     const float4 sphere = __ldg(rep + sub);
     __syncthreads();
     const uint32_t inmask = __ballot_sync(0xffffffffu, lane < nb && sphere_in_lattice(sxf[lane < nb ? lane : 0], sphere));
@@ -802,6 +813,16 @@ k_cloud_query_f32(const float4* __restrict__ pts, const float4* __restrict__ rep
         const GridK g = grid_of(r);
         const bool inside = (inmask >> bl) & 1u;
         const int64_t row = (b0 + bl) * N;
+        if (!kGrad && inside) {                            // the K2 bulk kernel's packed evaluation (two points per FFMA2), same values
+            float d4[kPtsPerThread];
+            subtile_values_packed(r, g, PX, PY, PZ, d4);
+#pragma unroll
+            for (int j = 0; j < kPtsPerThread; ++j) {
+                const int64_t i = base + j * 32 + lane;
+                if (i < N) __stcs(out_d + row + i, d4[j]);
+            }
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < kPtsPerThread; ++j) {
             const int64_t i = base + j * 32 + lane;
