@@ -455,6 +455,16 @@ def test_active_set_through_the_python_api(G, c1):
             finally:
                 c.all_under = False
     assert max(sizes) > 500 and min(sizes) == 0
+    # the float64 validation mode of the north_star answers with the same set
+    T = c1_poses(1, seed=11)[0]
+    c.setx(T)
+    want = g2.under(g1, 0.0)
+    G.set_validation_mode(True)
+    try:
+        got = g2.under(g1, 0.0)
+    finally:
+        G.set_validation_mode(False)
+    assert np.array_equal(got[1], want[1]) and np.abs(got[0] - want[0]).max(initial=0.0) <= 1e-12 and len(want[1]) > 100
 
 
 def mat4(T):
