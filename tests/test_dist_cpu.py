@@ -45,6 +45,16 @@ WORKER = textwrap.dedent("""
     local = np.stack([np.arange(lo, hi) * 1.0, np.arange(lo, hi) ** 2.0], axis=1)
     allrec = sd.gather_records(local, n_total=n)
     assert np.array_equal(allrec[:, 0], np.arange(n)) and np.array_equal(allrec[:, 1], np.arange(n) ** 2.0)
+    # equal shards, result handed out as a view of the landing buffer (copy=False): right values, and the next gather of
+    # the same shape overwrites it -- the documented lifetime
+    mine = np.full((4, 3), float(rank))
+    view = sd.gather_records(mine, n_total=8, copy=False)
+    assert view.shape == (8, 3) and np.array_equal(view[:4], np.zeros((4, 3))) and np.array_equal(view[4:], np.ones((4, 3)))
+    kept = view.copy()
+    again = sd.gather_records(mine + 10.0, n_total=8, copy=False)
+    assert np.array_equal(again, kept + 10.0) and np.array_equal(view, again)
+    fresh = sd.gather_records(mine, n_total=8)
+    assert np.array_equal(fresh, kept) and not np.shares_memory(fresh, again)
     # empty shard on one rank
     e = sd.gather_records(np.zeros((0, 2)) if rank == 1 else np.ones((3, 2)))
     assert e.shape == (3, 2)
