@@ -73,6 +73,7 @@ __device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64
 __device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b) { f32x2 r; asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
 // one cell as four register pairs [c6 c2 | c7 c3 | c4 c0 | c5 c1], one 256-bit read-only load
@@ -776,6 +777,63 @@ __device__ __forceinline__ float lattice_value_grad(const XfRec& r, const GridK&
     return val;
 }
 
+// lattice_value_grad for a sub-tile inside the sample lattice, two points per instruction where the operands allow: the
+// transform and floor / fraction of a point PAIR as in subtile_values_packed; per point the brick's register pairs give
+// (a, c), (b, d), (a fy + b, c fy + d) and (c2 fy + c6, c3 fy + c7) in four FFMA2, then value, dv/dfy and dv/dfz in three
+// FFMA; M' gf and the normalisation again per pair.  Each half is the IEEE operation of the scalar routine, in its order.
+__device__ __forceinline__ void subtile_grad_packed(const XfRec& r, const GridK& g, const f32x2 (&PX)[kPtsPerThread / 2],
+                                                    const f32x2 (&PY)[kPtsPerThread / 2], const f32x2 (&PZ)[kPtsPerThread / 2],
+                                                    int normalize, float4 (&out)[kPtsPerThread]) {
+    const float big = 8388608.0f;
+    const f32x2 BIG = pk2(big, big);
+#pragma unroll
+    for (int h = 0; h < kPtsPerThread / 2; ++h) {
+        const f32x2 UX = fma2(pk2(r.m[0], r.m[0]), PX[h], fma2(pk2(r.m[1], r.m[1]), PY[h], fma2(pk2(r.m[2], r.m[2]), PZ[h], pk2(r.m[3], r.m[3]))));
+        const f32x2 UY = fma2(pk2(r.m[4], r.m[4]), PX[h], fma2(pk2(r.m[5], r.m[5]), PY[h], fma2(pk2(r.m[6], r.m[6]), PZ[h], pk2(r.m[7], r.m[7]))));
+        const f32x2 UZ = fma2(pk2(r.m[8], r.m[8]), PX[h], fma2(pk2(r.m[9], r.m[9]), PY[h], fma2(pk2(r.m[10], r.m[10]), PZ[h], pk2(r.m[11], r.m[11]))));
+        const f32x2 TX = add2_rz(UX, BIG), TY = add2_rz(UY, BIG), TZ = add2_rz(UZ, BIG);
+        const f32x2 FX = sub2(UX, sub2(TX, BIG)), FY = sub2(UY, sub2(TY, BIG)), FZ = sub2(UZ, sub2(TZ, BIG));
+        float tx[2], ty[2], tz[2], fx[2], fy[2], fz[2];
+        upk2(TX, tx[0], tx[1]); upk2(TY, ty[0], ty[1]); upk2(TZ, tz[0], tz[1]);
+        upk2(FX, fx[0], fx[1]); upk2(FY, fy[0], fy[1]); upk2(FZ, fz[0], fz[1]);
+        Cell2 q[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+            q[e] = load_cell2(g.brick, __float_as_uint(tx[e]) * g.cx + (__float_as_uint(ty[e]) * g.cz + (__float_as_uint(tz[e]) + g.nbias)));
+        float val[2], gfx[2], gfy[2], gfz[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const f32x2 FZs = pk2(fz[e], fz[e]), FYs = pk2(fy[e], fy[e]);
+            const f32x2 AC = fma2(FZs, q[e].p73, q[e].p62);          // (a, c)
+            const f32x2 BD = fma2(FZs, q[e].p51, q[e].p40);          // (b, d)
+            float a, c, ff, u, v;
+            upk2(AC, a, c);
+            upk2(fma2(FYs, AC, BD), gfx[e], ff);                      // (dv/dfx = a fy + b, c fy + d)
+            upk2(fma2(FYs, q[e].p73, q[e].p51), u, v);                // (c2 fy + c6, c3 fy + c7) in the scalar routine's naming
+            val[e] = fmaf(gfx[e], fx[e], ff);
+            gfy[e] = fmaf(a, fx[e], c);
+            gfz[e] = fmaf(u, fx[e], v);
+        }
+        const f32x2 GFX = pk2(gfx[0], gfx[1]), GFY = pk2(gfy[0], gfy[1]), GFZ = pk2(gfz[0], gfz[1]);
+        f32x2 GX = fma2(pk2(r.m[0], r.m[0]), GFX, fma2(pk2(r.m[4], r.m[4]), GFY, mul2(pk2(r.m[8], r.m[8]), GFZ)));
+        f32x2 GY = fma2(pk2(r.m[1], r.m[1]), GFX, fma2(pk2(r.m[5], r.m[5]), GFY, mul2(pk2(r.m[9], r.m[9]), GFZ)));
+        f32x2 GZ = fma2(pk2(r.m[2], r.m[2]), GFX, fma2(pk2(r.m[6], r.m[6]), GFY, mul2(pk2(r.m[10], r.m[10]), GFZ)));
+        float gx[2], gy[2], gz[2];
+        if (normalize) {
+            const f32x2 N2 = fma2(GX, GX, fma2(GY, GY, mul2(GZ, GZ)));
+            float n2[2], sc[2];
+            upk2(N2, n2[0], n2[1]);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) sc[e] = n2[e] > 0.0f ? rsqrtf(n2[e]) : 1.0f;     // x * 1.0f == x: the scalar routine leaves a zero gradient alone
+            const f32x2 S = pk2(sc[0], sc[1]);
+            GX = mul2(GX, S); GY = mul2(GY, S); GZ = mul2(GZ, S);
+        }
+        upk2(GX, gx[0], gx[1]); upk2(GY, gy[0], gy[1]); upk2(GZ, gz[0], gz[1]);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) out[2 * h + e] = make_float4(gx[e], gy[e], gz[e], val[e]);
+    }
+}
+
 template <bool kGrad>
 __global__ void __launch_bounds__(kThreads, 4)
 k_cloud_query_f32(const float4* __restrict__ pts, const float4* __restrict__ rep, int64_t N, int32_t ntiles,
@@ -800,7 +858,7 @@ k_cloud_query_f32(const float4* __restrict__ pts, const float4* __restrict__ rep
         float4 p = __ldg(pts + base + j * 32 + lane);
         px[j] = p.x; py[j] = p.y; pz[j] = p.z;
     }
-    f32x2 PX[kPtsPerThread / 2], PY[kPtsPerThread / 2], PZ[kPtsPerThread / 2];      // the same points as register pairs (value-only mode)
+    f32x2 PX[kPtsPerThread / 2], PY[kPtsPerThread / 2], PZ[kPtsPerThread / 2];      // the same points as register pairs (sub-tiles inside the lattice)
 #pragma unroll
     for (int h = 0; h < kPtsPerThread / 2; ++h) {
         PX[h] = pk2(px[2 * h], px[2 * h + 1]); PY[h] = pk2(py[2 * h], py[2 * h + 1]); PZ[h] = pk2(pz[2 * h], pz[2 * h + 1]);
@@ -813,6 +871,16 @@ k_cloud_query_f32(const float4* __restrict__ pts, const float4* __restrict__ rep
         const GridK g = grid_of(r);
         const bool inside = (inmask >> bl) & 1u;
         const int64_t row = (b0 + bl) * N;
+        if (kGrad && inside) {                             // packed value + gradient
+            float4 o4[kPtsPerThread];
+            subtile_grad_packed(r, g, PX, PY, PZ, normalize, o4);
+#pragma unroll
+            for (int j = 0; j < kPtsPerThread; ++j) {
+                const int64_t i = base + j * 32 + lane;
+                if (i < N) __stcs(out_g + row + i, o4[j]);
+            }
+            continue;
+        }
         if (!kGrad && inside) {                            // the K2 bulk kernel's packed evaluation (two points per FFMA2), same values
             float d4[kPtsPerThread];
             subtile_values_packed(r, g, PX, PY, PZ, d4);
