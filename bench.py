@@ -742,7 +742,7 @@ def main():
                           "search inside distance_ext); effective = all (pose, point) pairs resolved / time"}
 
     # SURVEY.md 8d also asks for the per-point output modes of the same sweep (value-only, value+gradient); they write
-    # 4 B / 16 B per query to HBM, so an HBM fraction means something for them (the gradient mode reaches 0.71 of the copy
+    # 4 B / 16 B per query to HBM, so an HBM fraction means something for them (the gradient mode reaches 0.77 of the copy
     # peak) -- what binds them is still the L1 data pipe (ncu: profiles/r02_k1_modes_full.txt)
     modes = None
     if rank == 0:
