@@ -132,12 +132,18 @@ def test_product_so3_se3_kinematics_equal_the_frozen_copies():
         wv = rng.uniform(-3, 3, 3)
         Rp, Rf = pso3.from_rotation_vector(wv), fso3.from_rotation_vector(wv)
         assert np.abs(np.array(Rp) - np.array(Rf)).max() <= 1e-14
-        assert np.abs(np.array(pso3.rotation_vector(Rp)) - np.array(fso3.rotation_vector(Rf))).max() <= 1e-14
+        # the log map w = v theta / (2 sin theta), v the antisymmetric part (|v| = 2 sin theta), is ill-conditioned towards
+        # pi: a last-bit difference between the product's scalar arithmetic and the frozen copy's numpy round trip comes
+        # out amplified by ~ theta / sin^2 theta (these draws reach theta = 3.137: 2.6e-11)
+        wf_ = np.array(fso3.rotation_vector(Rf))
+        logtol = 1e-14 / max(np.sin(np.linalg.norm(wf_)) ** 2, 1e-6)
+        assert np.abs(np.array(pso3.rotation_vector(Rp)) - wf_).max() <= logtol
         T1 = (Rp, list(rng.normal(size=3)))
         T2 = (pso3.from_rotation_vector(rng.uniform(-1, 1, 3)), list(rng.normal(size=3)))
         for a, b in zip(pse3.mul(T1, pse3.inv(T2)), fse3.mul(T1, fse3.inv(T2))):
             assert np.abs(np.array(a) - np.array(b)).max() <= 1e-14
-        assert np.abs(np.array(pse3.error(T1, T2)) - np.array(fse3.error(T1, T2))).max() <= 1e-14
+        ef_ = np.array(fse3.error(T1, T2))
+        assert np.abs(np.array(pse3.error(T1, T2)) - ef_).max() <= 1e-14 / max(np.sin(np.linalg.norm(ef_[:3])) ** 2, 1e-6)
     wp, wf = probot.WorldModel(), frobot.WorldModel()
     wp.readFile("tx90_geom_test3.xml")
     wf.readFile("tx90_geom_test3.xml")
