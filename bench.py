@@ -697,14 +697,24 @@ def main():
     value = queries_per_step * args.steps / (total_ms * 1e-3)
 
     # end to end through the host-pointer call (what PenetrationDepthGeometry.distance(other) issues)
+    # ... through a prebound call (Context.min_distance_plan: the same sio_min_distance entry point with host pointers, the
+    # interpreter's per-call glue done once) and, for comparison, through the plain wrapper
     for _ in range(2):
         ctx.min_distance(g, c, T_rel, bound=bound)
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.min_distance(g, c, T_rel, bound=bound)
+    plain_s = time.perf_counter() - t0
+    plan = ctx.min_distance_plan(g, c, B)
+    for _ in range(2):
+        plan(T_rel, bound)
     ctx.sync()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        dmin_h, arg_h, nu_h = ctx.min_distance(g, c, T_rel, bound=bound)
+        dmin_h, arg_h, nu_h = plan(T_rel, bound)
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -713,7 +723,8 @@ def main():
     n_under = int(nu_h.sum())
     e2e = {"value": queries_per_step * args.steps / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": int(B * (96 + 8)), "d2h_bytes_per_step": int(B * (8 + 8 + 4)),
-           "call": "sio_min_distance (host pointers): poses+bounds H2D from a pinned block, dmin/argmin/n_under D2H; geometry "
+           "plain_wrapper_value_this_rank": B * CLOUD_N * args.steps / plain_s,
+           "call": "Context.min_distance_plan(...)(T_rel, bound) -> sio_min_distance (host pointers): poses+bounds H2D from a pinned block, dmin/argmin/n_under D2H; geometry "
                    "resident as in the reference API (PenetrationDepthGeometry builds grid+cloud once); the sorted under-bound "
                    "list itself stays on the device until sio_under_fetch asks for it"}
 

@@ -722,3 +722,25 @@ def test_error_paths(ctx, O):
     ctx.grid_destroy(g)
     with pytest.raises(_abi.SioError):
         ctx.min_distance(g, c, T)                                     # destroyed handles
+
+
+def test_prebound_call_plan_equals_the_plain_wrapper(ctx, O):
+    """Context.min_distance_plan: same entry point, same answers as Context.min_distance, call after call (the plan owns
+    its output arrays and overwrites them), with and without a bound / the under-bound counts."""
+    vg = util.sphere_grid(r=0.7, n=32)
+    g = ctx.grid_create(vg.values, vg.bmin, vg.bmax)
+    cloud = np.random.default_rng(5).uniform(-0.9, 0.9, (5000, 3)).astype(np.float32)
+    c = ctx.cloud_create(cloud)
+    plan = ctx.min_distance_plan(g, c, 7)
+    plan_nb = ctx.min_distance_plan(g, c, 7, with_bound=False, want_under=False)
+    for seed in range(4):
+        T = util.random_poses(seed, 7, rot=0.5, trans=0.2)
+        bound = np.linspace(-0.1, 0.2, 7) + 0.01 * seed
+        d0, a0, n0 = ctx.min_distance(g, c, T, bound=bound)
+        d1, a1, n1 = plan(T, bound)
+        assert np.array_equal(d0, d1) and np.array_equal(a0, a1) and np.array_equal(n0, n1)
+        d2, a2, _ = ctx.min_distance(g, c, T, want_under=False)
+        d3, a3, n3 = plan_nb(T)
+        assert np.array_equal(d2, d3) and np.array_equal(a2, a3) and n3 is None
+    with pytest.raises(ValueError):
+        plan(util.random_poses(0, 6), np.zeros(7))           # a different batch size does not fit the plan
