@@ -306,7 +306,25 @@ class Context:
         return b[:n], i[:n], d[:n]
 
     # -- K3 --
+    _POSE_ROWS_CAP = 256
+
     def pose_rows(self, grid, T_pose, offsets, pts, flags=SIO_F64, want_rows=True):
+        if len(offsets) == 2 and len(pts) <= self._POSE_ROWS_CAP:
+            # ONE pose and a handful of points -- the call a single-problem SIP run makes three times per iteration: inputs
+            # go into arrays this context keeps (their addresses fetched once), outputs come back as copies
+            sc = getattr(self, "_pr", None)
+            if sc is None:
+                cap = self._POSE_ROWS_CAP
+                arrs = (np.empty(12), np.zeros(2, dtype=np.int64), np.empty((cap, 3)), np.empty(cap), np.empty((cap, 6)))
+                sc = self._pr = arrs + tuple(a.ctypes.data for a in arrs)
+            T, off, p, d, rows, pT, poff, pp, pd, prows = sc
+            P = len(pts)
+            T[...] = np.reshape(T_pose, 12)
+            off[1] = P
+            if P:
+                p[:P] = pts
+            self._ck(self.L.sio_pose_rows(self.h, grid, pT, poff, 1, pp, int(flags), pd, prows if want_rows else None))
+            return d[:P].copy(), (rows[:P].copy() if want_rows else None)
         T = _f64(T_pose).reshape(-1, 12)
         off = np.ascontiguousarray(offsets, dtype=np.int64)
         p = _f64(pts).reshape(-1, 3)
