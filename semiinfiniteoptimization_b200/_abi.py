@@ -458,6 +458,24 @@ class Context:
         return out
 
     def chain_rows(self, robot, n_links, link_grids, q, link_of_pt, pts, cfg_of_pt=None, flags=SIO_F64, want_rows=True):
+        if cfg_of_pt is None and np.isscalar(link_of_pt) and len(pts) <= self._POSE_ROWS_CAP and len(q) == 1 and n_links <= 16:
+            # ONE configuration, one link, a handful of points (what a link constraint of a robot-pose problem asks three
+            # times per iteration): inputs into arrays this context keeps, their addresses fetched once (see pose_rows)
+            key = (int(robot), int(n_links), tuple(int(g) for g in link_grids))
+            sc = getattr(self, "_cr", None)
+            if sc is None or sc[0] != key:
+                cap = self._POSE_ROWS_CAP
+                arrs = (np.array(key[2], dtype=np.int32), np.empty((1, n_links)), np.zeros(cap, dtype=np.int32), np.empty((cap, 3)),
+                        np.empty(cap), np.empty((cap, n_links)))
+                sc = self._cr = (key,) + arrs + tuple(a.ctypes.data for a in arrs)
+            _, lg, qq, lop, p, d, rows, plg, pq, plop, pp, pd, prows = sc
+            P = len(pts)
+            qq[0, :] = q[0]
+            lop[:P] = int(link_of_pt)
+            if P:
+                p[:P] = pts
+            self._ck(self.L.sio_chain_rows(self.h, robot, plg, pq, 1, None, plop, pp, P, int(flags), pd, prows if want_rows else None))
+            return d[:P].copy(), (rows[:P].copy() if want_rows else None)
         lg = np.ascontiguousarray(link_grids, dtype=np.int32)
         q = _f64(q).reshape(-1, n_links)
         p = _f64(pts).reshape(-1, 3)
