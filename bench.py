@@ -20,19 +20,24 @@ include/sio_abi.h), inside that step's timed span; an NCCL all-gather of the sam
 `value`  : point-queries/s, inputs resident in HBM, timed with CUDA events on the launching stream,
            max over ranks; L2 is flushed between timed steps.
 `e2e`    : the same sweep through the host-pointer C-ABI call a user of the Python API makes
-           (poses + bounds H2D, results D2H inside the timed region, wall clock).
-`roofline`: the dominant kernel k_min_f32 against the measured HBM copy peak using the
-           ALGORITHMIC 48 B/query of SURVEY.md 8d, and (extra key `gather`) its 32 B/query of corner
-           gathers against an L2 gather peak measured here.
+           (poses + bounds H2D, results D2H inside the timed region, wall clock), issued through a prebound call
+           (Context.min_distance_plan); the plain wrapper's figure is reported beside it.
+`roofline`: the dominant kernel k_min_f32 against the unit that binds it, the L1 data pipe (32 B brick per query
+           delivered to registers / 148 SMs x 128 B/clk x the sampled SM clock), with ncu's own utilisation of that pipe
+           from the committed capture; the contract's ALGORITHMIC 48 B/query of SURVEY.md 8d against the measured HBM
+           copy peak and the measured DRAM fraction are kept under `roofline.hbm`.
+`modes`  : the per-point output modes of the same sweep (value only, value + gradient) with their HBM fractions.
 `cpu_baseline`: the CPU oracle (oracle/, float64 brute force, all host threads) on a bounded
            sample of the same sweep, rank 0 / N=1 only.
 
 `sip`     : BASELINE.json's second metric, SIP outer iterations/s, on configs[4] ("C5"): 65,536 independent
            cube-vs-scene optimizeCollFree problems (declared synthetic scene, 262,144 points) sharded across the
-           ranks and solved in lock step entirely on the device (batch.optimizeCollFreeBatchDevice =
-           sio_lockstep_pose_solve), wall clock from host poses to host results -- at N > 1 including the end-of-solve
-           all-gather of the per-problem records --, with the sweep / in-line QP / other split; at
+           ranks and solved in lock step entirely on the device (batch.GroupedPoseSolver: every shard as two concurrent
+           slices of sio_lockstep_pose_solve), wall clock from host poses to host results -- at N > 1 including the
+           end-of-solve all-gather of the per-problem records --, with the sweep / in-line QP / other split, every
+           rank's solve / gather times and (`weak_scaling`) the same solve with 65,536 problems on EVERY GPU; at
            N=1 also the CPU path (restated SIP loop on the CPU oracle, one process per host core, bounded sample).
+`single_problems`: C1 / C3 latency per problem, C4 minvalue and SIP iterations/s, API call latency, GPU beside CPU.
 
 --impl reference times that CPU oracle port as the reference arm (the reference itself is
 Python 2 on absent Klampt/OSQP and cannot run).
