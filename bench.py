@@ -299,7 +299,14 @@ def sip_leg(ctx, rank, world, want_cpu):
     from semiinfiniteoptimization_b200._host.geometry import Geometry3D, PointCloud
     # two concurrent slices of the shard (one context + host thread each, same GPU): one slice's QP launches overlap the
     # other's sweeps and bookkeeping launches; same answers problem by problem (tests/test_gpu_batch.py)
-    solver = batch.GroupedPoseSolver(workloads.c5_cube(), 0.05, workloads.c5_scene_cloud(), pcres=0.02, groups=SIP_GROUPS, context=ctx)
+    # (every slice has a host thread that polls its stream: on a box with fewer host cores than 2 x ranks the slices would
+    # fight over them, so such a box solves each shard in one piece)
+    try:
+        host_cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        host_cores = os.cpu_count() or 1
+    groups = SIP_GROUPS if host_cores >= SIP_GROUPS * world else 1
+    solver = batch.GroupedPoseSolver(workloads.c5_cube(), 0.05, workloads.c5_scene_cloud(), pcres=0.02, groups=groups, context=ctx)
     poses = workloads.c5_poses(SIP_PROBLEMS, seed=3)
     lo, hi = sdist.shard_range(SIP_PROBLEMS)
     from semiinfiniteoptimization_b200._host import se3
@@ -360,10 +367,10 @@ def sip_leg(ctx, rank, world, want_cpu):
            "workload": "C5: %d independent optimizeCollFree problems (cube SDF@0.05 vs synthetic 262,144-point scene, seed 2; poses "
                        "seed 3), reference default settings (max_iters 50), sharded over %d GPU(s), device-resident lock-step "
                        "solver (sio_lockstep_pose_solve), each shard solved as %d concurrent slices (batch.GroupedPoseSolver); wall clock from host poses (row-major 3x4 array) to host results, the end-of-solve "
-                       "all-gather of the per-problem records included at N > 1" % (SIP_PROBLEMS, world, SIP_GROUPS),
+                       "all-gather of the per-problem records included at N > 1" % (SIP_PROBLEMS, world, groups),
            "outer_iterations": int(rec[0].item()), "wall_s": wall, "sweep_device_s_per_rank": float(rec[2].item()) / world,
            "qp_device_s_per_rank": float(rec[3].item()) / world, "other_s_per_rank": wall - float(rec[2].item() + rec[3].item()) / world,
-           "slices_per_gpu": SIP_GROUPS,
+           "slices_per_gpu": groups, "host_cores": host_cores,
            "device_s_note": "sweep / qp device seconds are those of the slower slice; with more than one slice per GPU the slices' "
                             "launches overlap in time, so sweep + qp + other no longer partition the wall clock exactly",
            "library_call_s_rank0": float(res.time), "gather_s_rank0": wall_local - solve_s,
