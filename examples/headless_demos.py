@@ -11,7 +11,7 @@ bundled fixtures, Klampt being absent from this image):
   robottrajopt   robottrajopt.py:13-17, 70-71, 101-131, 197: the initial path remeshed x 6, chair as a cloud only,
                  RobotTrajectoryCollisionConstraint + optimizeCollFreeTrajectory.  (With the chair moved across the path the
                  reference's own optimiser, run through oracle/refrun, stops after 14 iterations at a deepest penetration of
-                 -0.0484 with |x - x0| = 0.005 and one instantiated parameter; so does this one.)
+                 -0.0484 with |x - x0| = 0.005 and 12 instantiated parameters; so does this one: tests/golden/c4_traj_long.json.)
   robotplanopt   robotplanopt.py:67-143: planner / optimiser alternation (planOptimizedTrajectory) with the declared
                  stand-in planner
 
@@ -91,7 +91,7 @@ def robottrajopt():
     print("robottrajopt: deepest penetration along the path %.4f -> %s, |x - x0| = %.3f, %d iterations, %.1f ms, %d milestones, "
           "%d instantiated (link, env, t, point) parameters"
           % (d0, "%.4f" % mv[0] if len(mv) else "none", float(np.linalg.norm(np.asarray(xs) - np.asarray(x))), len(trace) - 1, dt * 1e3,
-             len(trajsolved.milestones), len(params)))
+             len(trajsolved.milestones), sum(len(p) for p in params)))
     if len(mv):
         link, env, t = mv[1][:3]
         first = trajsolved.times[1]

@@ -182,6 +182,31 @@ def test_c4_restated_trajectory_constraint_reproduces_the_reference(qp_kind):
     assert np.allclose(np.array(res.instantiated_params[0]), np.array(golden["params"][0]), atol=qp_kind, rtol=0)
 
 
+def test_c4_run_to_its_end_reproduces_the_reference(qp_kind):
+    """tests/golden/c4_traj_long.json: the reference's optimizeCollFreeTrajectory (max_iters 30) stops by itself after 14
+    outer iterations on this scene; the restated loop stops at the same iteration, trajectory and deepest point."""
+    from semiinfiniteoptimization_b200 import geometryopt as G
+    from semiinfiniteoptimization_b200 import sip
+    golden = scenes.load_golden("c4_traj_long.json")
+    mod, robot, tc, con, traj, x = scenes.c4_scene('restated')
+    assert np.array_equal(np.array(x), np.array(golden["x0"]))
+    st = sip.SemiInfiniteOptimizationSettings()
+    st.max_iters, st.minimum_constraint_value = 30, -0.02
+    qmin, qmax = robot.getJointLimits()
+    res = sip.optimizeSemiInfinite(G.TrajectoryLengthObjective(tc), [con], np.asarray(x), np.hstack([qmin] * 65), np.hstack([qmax] * 65),
+                                   settings=st, verbose=0)
+    tol = max(qp_kind, 1e-10)
+    assert res.num_iterations == golden["iterations"] == 14
+    assert np.abs(np.asarray(res.x) - np.array(golden["x"])).max() <= tol
+    xs = [float(v) for v in res.x]
+    con.setx(xs)
+    mv = con.minvalue(xs)
+    con.clearx()
+    assert abs(mv[0] - golden["dmin"]) <= tol and np.allclose(mv[1], golden["param"], atol=max(tol, 1e-9), rtol=0)
+    assert len(res.instantiated_params[0]) == len(golden["params"][0]) == 12
+    assert np.allclose(np.array(res.instantiated_params[0]), np.array(golden["params"][0]), atol=max(tol, 1e-9), rtol=0)
+
+
 def test_class_level_goldens_on_the_restatement():
     g = scenes.load_golden("classes.json")
     mod, g1, g2, con = scenes.c1_scene('restated')

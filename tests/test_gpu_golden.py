@@ -153,6 +153,27 @@ def test_c4_trajectory_constraint_and_solution_equal_the_reference(ctx):
     assert len(out[0].milestones) == 67
 
 
+def test_c4_run_to_its_end_equals_the_reference(ctx):
+    """tests/golden/c4_traj_long.json: optimizeCollFreeTrajectory with max_iters 30 on the device classes stops where the
+    reference's own run stops -- 14 outer iterations, the same trajectory (1e-6) and the same deepest (link, env, t, point)."""
+    from semiinfiniteoptimization_b200 import sip
+    golden = scenes.load_golden("c4_traj_long.json")
+    mod, robot, tc, con, traj, x = scenes.c4_scene('device')
+    st = sip.SemiInfiniteOptimizationSettings()
+    st.max_iters, st.minimum_constraint_value = 30, -0.02
+    out = mod.optimizeCollFreeTrajectory(tc, traj, env=None, constraints=[con], settings=st, verbose=0)
+    res = mod.optimizeCollFreeTrajectory.last_result
+    assert res.num_iterations == golden["iterations"]
+    xs = [float(v) for q in out[0].milestones[1:-1] for v in q]
+    assert np.abs(np.array(xs) - np.array(golden["x"])).max() <= 1e-6
+    con.setx(xs)
+    mv = con.minvalue(xs)
+    con.clearx()
+    assert abs(mv[0] - golden["dmin"]) <= 1e-6 and int(mv[1][0]) == golden["param"][0] and abs(mv[1][2] - golden["param"][2]) <= 1e-6
+    assert len(out[3][0]) == len(golden["params"][0]) == 12
+    assert np.allclose(np.array(out[3][0]), np.array(golden["params"][0]), atol=1e-6, rtol=0)
+
+
 def test_class_level_goldens(ctx):
     g = scenes.load_golden("classes.json")
     mod, g1, g2, con = scenes.c1_scene('device')

@@ -315,7 +315,23 @@ def gen_multi():
                                     "num_co_parameters": M.num_co_parameters, "cases": cases})
 
 
-GENERATORS = {"multi": gen_multi, "c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "c5": gen_c5, "classes": gen_classes, "oracle": gen_oracle,
+def gen_c4_long():
+    """C4 run to its end: the reference's optimizeCollFreeTrajectory with max_iters 30 stops by itself after 14 outer
+    iterations on this scene (chair across the path): final trajectory, its deepest penetration, the instantiated parameters."""
+    mod, robot, tc, con, traj, x = _quiet(scenes.c4_scene, 'reference')
+    sip = sys.modules[mod.__name__.rsplit('.', 1)[0] + '.sip']
+    st = sip.SemiInfiniteOptimizationSettings()
+    st.max_iters, st.minimum_constraint_value = 30, -0.02
+    out = _quiet(mod.optimizeCollFreeTrajectory, tc, traj, env=None, constraints=[con], settings=st, verbose=0)
+    xs = [float(v) for q in out[0].milestones[1:-1] for v in q]
+    con.setx(xs)
+    mv = _quiet(con.minvalue, xs)
+    con.clearx()
+    write("c4_traj_long.json", {"config": "C4 as in c4_traj.json, max_iters 30, minimum_constraint_value -0.02", "x0": x, "x": xs,
+                                "iterations": len(out[1]) - 1, "dmin": float(mv[0]), "param": _f(mv[1]), "params": _f(out[3])})
+
+
+GENERATORS = {"c4long": gen_c4_long, "multi": gen_multi, "c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "c5": gen_c5, "classes": gen_classes, "oracle": gen_oracle,
               "planopt": gen_planopt, "paths": gen_paths}
 
 if __name__ == "__main__":
