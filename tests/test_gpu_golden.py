@@ -112,6 +112,26 @@ def test_c3_solutions_equal_the_reference(ctx):
             assert np.allclose(np.array(pa).reshape(-1), np.array(pb).reshape(-1), atol=1e-9, rtol=0)
 
 
+def test_c3_sampled_start_equals_the_reference(ctx):
+    """optimizeCollFreeRobot(qinit='random-collision-free' | 'random') (gopt:1172-1207) against the reference's own run with
+    the same `random.seed`: same number of draws (the generator's next value agrees), same start, same solution."""
+    import random
+    from semiinfiniteoptimization_b200 import sip
+    golden = scenes.load_golden("c3_random_init.json")
+    mod, robot, cons = scenes.c3_scene('device')
+    took_several = 0
+    for case in golden["cases"]:
+        st = sip.SemiInfiniteOptimizationSettings()
+        st.max_iters, st.minimum_constraint_value = 5, -0.02
+        random.seed(case["seed"])
+        out = mod.optimizeCollFreeRobot(robot, None, qdes=case["qdes"], qinit=case["qinit"], constraints=cons, settings=st, verbose=0)
+        assert random.random() == case["draws_after"]
+        assert len(out[1]) == len(case["trace"])
+        assert np.allclose(np.array(out[1]), np.array(case["trace"]), atol=1e-7, rtol=0) and np.allclose(out[0], case["q"], atol=1e-7, rtol=0)
+        took_several += len(case["trace"]) > 1
+    assert took_several >= 2
+
+
 def test_c4_trajectory_constraint_and_solution_equal_the_reference(ctx):
     from semiinfiniteoptimization_b200 import sip
     golden = scenes.load_golden("c4_traj.json")

@@ -331,7 +331,28 @@ def gen_c4_long():
                                 "iterations": len(out[1]) - 1, "dmin": float(mv[0]), "param": _f(mv[1]), "params": _f(out[3])})
 
 
-GENERATORS = {"c4long": gen_c4_long, "multi": gen_multi, "c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "c5": gen_c5, "classes": gen_classes, "oracle": gen_oracle,
+def gen_c3_random():
+    """optimizeCollFreeRobot with qinit = 'random-collision-free' / 'random' (gopt:1172-1207): up to 50 samples in a box growing
+    from qdes to the joint limits, drawn with Python's `random` (seeded here), the first one whose constraints' minima reach
+    the lower bound starts the solve.  Pins the draw order and the accept rule."""
+    import random
+    mod, robot, cons = _quiet(scenes.c3_scene, 'reference')
+    sip = sys.modules[mod.__name__.rsplit('.', 1)[0] + '.sip']
+    cases = []
+    for k, qdes in enumerate(scenes.c3_configs(robot, 6, seed=3)):
+        for mode in ('random-collision-free', 'random'):
+            st = sip.SemiInfiniteOptimizationSettings()
+            st.max_iters, st.minimum_constraint_value = 5, -0.02
+            random.seed(100 + k)
+            out = _quiet(mod.optimizeCollFreeRobot, robot, None, qdes=qdes, qinit=mode, constraints=cons, settings=st, verbose=0)
+            q, trace = out[0], out[1]
+            cases.append({"qdes": _f(qdes), "qinit": mode, "seed": 100 + k, "q": _f(q), "trace": _f(trace),
+                          "draws_after": random.random()})      # the generator's state after the call: how many draws it took
+    write("c3_random_init.json", {"config": "C3, optimizeCollFreeRobot with a sampled start (gopt:1172-1207), max_iters 5, "
+                                            "minimum_constraint_value -0.02, random.seed(seed) before each call", "cases": cases})
+
+
+GENERATORS = {"c3random": gen_c3_random, "c4long": gen_c4_long, "multi": gen_multi, "c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "c5": gen_c5, "classes": gen_classes, "oracle": gen_oracle,
               "planopt": gen_planopt, "paths": gen_paths}
 
 if __name__ == "__main__":
