@@ -5,6 +5,7 @@ class restatement oracle/ref_geometryopt.py).  No GPU.  When /root/reference is 
 container) the goldens are also regenerated in memory and compared with the committed files."""
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -273,6 +274,27 @@ def test_committed_goldens_are_what_the_reference_produces_now():
         refined = planopt.arc_length_refine(RobotTrajectory(robot, list(range(len(p0["milestones"]))), p0["milestones"]), 12)
         want = scenes.load_golden("planopt.json")["arc_length_refine"]["robot_12"]
         assert np.array_equal(np.array(refined.milestones), np.array(want["milestones"])) and np.array_equal(refined.times, want["times"])
+        # the sampled start of optimizeCollFreeRobot (gopt:1172-1207), first case (the target in collision)
+        import random
+        g3 = scenes.load_golden("c3_random_init.json")
+        mod3, robot3, cons3 = scenes.c3_scene('reference')
+        sip3 = sys.modules[mod3.__name__.rsplit('.', 1)[0] + '.sip']
+        case = g3["cases"][0]
+        st = sip3.SemiInfiniteOptimizationSettings()
+        st.max_iters, st.minimum_constraint_value = 5, -0.02
+        random.seed(case["seed"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = mod3.optimizeCollFreeRobot(robot3, None, qdes=case["qdes"], qinit=case["qinit"], constraints=cons3, settings=st, verbose=0)
+        assert random.random() == case["draws_after"] and np.array_equal(np.array(out[0]), np.array(case["q"]))
+        # C4 run to its end (tools/make_golden.py gen_c4_long)
+        g4 = scenes.load_golden("c4_traj_long.json")
+        mod4, robot4, tc4, con4, traj4, x4 = scenes.c4_scene('reference')
+        st = sip3.SemiInfiniteOptimizationSettings()
+        st.max_iters, st.minimum_constraint_value = 30, -0.02
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = mod4.optimizeCollFreeTrajectory(tc4, traj4, env=None, constraints=[con4], settings=st, verbose=0)
+        assert len(out[1]) - 1 == g4["iterations"]
+        assert np.array_equal(np.array([float(v) for q in out[0].milestones[1:-1] for v in q]), np.array(g4["x"]))
         # the shipped .path / .configs files are what path_files.json holds
         files = scenes.load_golden("path_files.json")["files"]
         for name, text in files.items():
