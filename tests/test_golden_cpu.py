@@ -97,10 +97,11 @@ def _run_pose_cases(golden, scene_fn, settings_kw=None, tol=1e-12):
     nontrivial = 0
     for case in golden["cases"]:
         T = (case["Tinit"][0], case["Tinit"][1])
+        Td = (case["Tdes"][0], case["Tdes"][1]) if "Tdes" in case else T
         st = sip.SemiInfiniteOptimizationSettings()
         for k, v in (settings_kw or {}).items():
             setattr(st, k, v)
-        res = sip.optimizeSemiInfinite(G.ObjectPoseObjective(T), [con], T, settings=st, verbose=0)
+        res = sip.optimizeSemiInfinite(G.ObjectPoseObjective(Td), [con], T, settings=st, verbose=0)
         assert len(res.trace) == len(case["trace"])
         for a, b in zip(res.trace, case["trace"]):
             assert _pose_close(a, b, tol)
@@ -110,6 +111,12 @@ def _run_pose_cases(golden, scene_fn, settings_kw=None, tol=1e-12):
             assert np.allclose(ya, yb, atol=1e-12, rtol=0)          # parameters are cloud points: identical or different
         nontrivial += len(case["trace"]) > 3
     return nontrivial
+
+
+def test_c1_with_separate_targets_reproduces_the_reference(qp_kind):
+    """tests/golden/c1_pose_targets.json: optimizeCollFree(obj, env, Tinit, Tdes) with Tdes inside the chair and Tinit
+    clear of it -- the objective's minstep / value and the QP's xdes are non-zero from the first iteration."""
+    assert _run_pose_cases(scenes.load_golden("c1_pose_targets.json"), scenes.c1_scene, tol=qp_kind) >= 10
 
 
 def test_c1_restated_sip_reproduces_the_reference(qp_kind):

@@ -22,10 +22,11 @@ def _pose_cases(ctx, golden, scene_fn, settings_kw=None):
     nontrivial = 0
     for case in golden["cases"]:
         T = (case["Tinit"][0], case["Tinit"][1])
+        Td = (case["Tdes"][0], case["Tdes"][1]) if "Tdes" in case else None
         st = sip.SemiInfiniteOptimizationSettings()
         for k, v in (settings_kw or {}).items():
             setattr(st, k, v)
-        out = mod.optimizeCollFree(g1, g2, T, settings=st, verbose=0)
+        out = mod.optimizeCollFree(g1, g2, T, Td, settings=st, verbose=0)
         assert len(out) == 4 and len(out[1]) == len(case["trace"])
         for a, b in zip(out[1], case["trace"]):
             assert _pose_close(a, b, 1e-7)
@@ -39,6 +40,25 @@ def _pose_cases(ctx, golden, scene_fn, settings_kw=None):
 
 def test_c1_solutions_equal_the_reference(ctx):
     assert _pose_cases(ctx, scenes.load_golden("c1_pose.json"), scenes.c1_scene) >= 5
+
+
+def test_c1_with_separate_targets_equals_the_reference(ctx):
+    """optimizeCollFree(obj, env, Tinit, Tdes), Tdes != Tinit (tests/golden/c1_pose_targets.json), on the device classes one
+    problem at a time AND through the device-resident lock-step solver with its separate target array."""
+    from semiinfiniteoptimization_b200 import batch, sip
+    golden = scenes.load_golden("c1_pose_targets.json")
+    assert _pose_cases(ctx, golden, scenes.c1_scene) >= 10
+    cases = golden["cases"]
+    mod, g1, g2, con = scenes.c1_scene('device')
+    res = batch.optimizeCollFreeBatchDevice(g1, g2, [(c["Tinit"][0], c["Tinit"][1]) for c in cases],
+                                            [(c["Tdes"][0], c["Tdes"][1]) for c in cases], settings=sip.SemiInfiniteOptimizationSettings())
+    want_T = np.array([_se3_to12(c["T"]) for c in cases])
+    assert [s for s in res.status] == [c["status"] for c in cases]
+    assert np.array_equal(np.asarray(res.num_iterations), np.array([c["num_iterations"] for c in cases]))
+    assert np.abs(res.T - want_T).max() <= 1e-6
+    assert np.allclose(res.fx, [c["fx"] for c in cases], atol=1e-6, rtol=0)
+    for p, c in enumerate(cases):
+        assert np.allclose(np.array(res.instantiated_params[p]), np.array(c["params"]), atol=1e-9, rtol=0)
 
 
 def test_c2_solutions_equal_the_reference(ctx):

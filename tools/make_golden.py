@@ -352,7 +352,33 @@ def gen_c3_random():
                                             "minimum_constraint_value -0.02, random.seed(seed) before each call", "cases": cases})
 
 
-GENERATORS = {"c3random": gen_c3_random, "c4long": gen_c4_long, "multi": gen_multi, "c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "c5": gen_c5, "classes": gen_classes, "oracle": gen_oracle,
+def target_cases():
+    """Start poses clear of the chair (x in [0, 0.3]) with targets inside it (c1_poses): the objective pulls the cube into
+    contact, which is where Tdes != Tinit matters (minstep / value / the QP's xdes are all non-zero from the first iteration)."""
+    from oracle.frozen import so3
+    rng = np.random.default_rng(17)
+    starts = [(so3.from_rotation_vector(rng.uniform(-0.3, 0.3, 3)), [float(rng.uniform(0.0, 0.3)), float(rng.uniform(-0.3, 0.5)),
+                                                                     float(rng.uniform(-0.3, 0.5))]) for _ in range(12)]
+    return starts, scenes.c1_poses(12, seed=23)
+
+
+def gen_c1_targets():
+    """optimizeCollFree(obj, env, Tinit, Tdes) with Tdes != Tinit on the C1 scene (gopt:1039-1081), reference defaults."""
+    mod, g1, g2, con = scenes.c1_scene('reference')
+    sip = sys.modules[mod.__name__.rsplit('.', 1)[0] + '.sip']
+    starts, targets = target_cases()
+    cases = []
+    for T0, Td in zip(starts, targets):
+        out = _quiet(mod.optimizeCollFree, g1, g2, T0, Td, settings=sip.SemiInfiniteOptimizationSettings(), verbose=0)
+        res = _quiet(sip.optimizeSemiInfinite, mod.ObjectPoseObjective(Td), [con], T0, settings=sip.SemiInfiniteOptimizationSettings(), verbose=0)
+        assert len(res.trace) == len(out[1])
+        cases.append({"Tinit": _f(T0), "Tdes": _f(Td), "T": _f(out[0]), "iterations": len(out[1]) - 1, "num_iterations": int(res.num_iterations),
+                      "status": res.status, "fx": float(res.fx), "gx": _f(res.gx), "trace": _f(out[1]), "params": _f(out[3])})
+    write("c1_pose_targets.json", {"config": "C1 scene, optimizeCollFree with separate start and target poses, defaults (max_iters 50)",
+                                   "cases": cases})
+
+
+GENERATORS = {"c1targets": gen_c1_targets, "c3random": gen_c3_random, "c4long": gen_c4_long, "multi": gen_multi, "c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "c5": gen_c5, "classes": gen_classes, "oracle": gen_oracle,
               "planopt": gen_planopt, "paths": gen_paths}
 
 if __name__ == "__main__":
