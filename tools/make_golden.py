@@ -6,7 +6,10 @@ modules) on BASELINE.json's configurations.  The Klampt-side queries underneath 
 the reference's.  Needs /root/reference, so it runs in the build container only; the fixtures it writes
 are committed and are what the tests on the GPU box compare against.
 
-    python tools/make_golden.py [--only c1,c2,c3,c4,c5,classes,oracle]
+    python tools/make_golden.py [--only c1,c2,c3,c4,c5,classes,oracle,planopt,paths,multi,c1targets,c3random,c4long]
+
+Generators are deterministic: re-running one rewrites its file byte for byte (tests/test_golden_cpu.py re-runs a case of
+each against the committed file whenever the reference sources are present).
 """
 import argparse
 import json
