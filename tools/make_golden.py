@@ -141,7 +141,7 @@ def gen_c5():
     from semiinfiniteoptimization_b200 import workloads as W
     mod, cube, scene, con = scenes.c5_scene('reference')
     sip = sys.modules[mod.__name__.rsplit('.', 1)[0] + '.sip']
-    allposes = W.c5_poses(65536, seed=3)
+    allposes = frozen_c5_poses(65536, seed=3)
     cases = []
     for k, idx in enumerate(scenes.c5_sample_indices(64)):
         T = allposes[idx]
@@ -254,6 +254,31 @@ def gen_classes():
     write("classes.json", out)
 
 
+def frozen_random_poses(seed, n, rot=0.3, trans=0.1, center=(0, 0, 0)):
+    """tests/util.random_poses with the FROZEN so3 / se3 helpers: golden inputs must not move when the product's helpers are
+    rewritten (they did, by one unit in the last place, when _host/so3.py went from numpy round trips to scalar arithmetic)."""
+    from oracle.frozen import se3, so3
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, 12))
+    for i in range(n):
+        w = rng.uniform(-rot, rot, 3)
+        t = np.asarray(center) + rng.uniform(-trans, trans, 3)
+        out[i] = se3.to_rowmajor12((so3.from_rotation_vector(w), list(t)))
+    return out
+
+
+def frozen_c5_poses(n, seed=3):
+    """workloads.c5_poses with the frozen so3 (same draws, same order)."""
+    from oracle.frozen import so3
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        R = so3.from_rotation_vector(rng.uniform(-np.pi / 2, np.pi / 2, 3))
+        t = [float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)), float(rng.uniform(0.0, 1.0))]
+        out.append((R, t))
+    return out
+
+
 def gen_oracle():
     """Known answers of the oracle itself on seeded arrays (regression pin for oracle/sio_oracle.c and for the
     CUDA kernels): analytic linear field (trilinear interpolation is exact on it) + seeded random grid."""
@@ -262,7 +287,7 @@ def gen_oracle():
     rng = np.random.default_rng(123)
     vg = util.random_grid(7)
     G = O.Grid(vg.values, vg.bmin, vg.bmax)
-    T = util.random_poses(8, 6, rot=0.5, trans=0.2)
+    T = frozen_random_poses(8, 6, rot=0.5, trans=0.2)
     pts = rng.uniform(-0.6, 1.6, (40, 3))
     d, g = O.query(G, T[0], pts)
     cloud = rng.uniform(-0.5, 1.5, (5000, 3)).astype(np.float32)
