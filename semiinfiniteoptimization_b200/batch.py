@@ -691,6 +691,11 @@ class GroupedPoseSolver:
             if env_T is not None:
                 e.setTransform(env_T)
             self.envs.append(e)
+        # constructing a PenetrationDepthGeometry points the host substrate's mesh converters at ITS context; leave them on
+        # the caller's, which outlives close()
+        from . import geometryopt as _G
+        if self.groups > 1 and _G.DEVICE_CONVERSION:
+            _G._hostgeometry.set_device_converters(first.mesh_sdf_grid, first.mesh_surface_sample)
 
     def solve(self, Tinits, Tdess=None, settings=None, cap=48):
         import threading
