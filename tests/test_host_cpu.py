@@ -532,3 +532,84 @@ def test_grid_export_formats(tmp_path):
     mat = scipy.io.loadmat(fn)
     assert sorted(k for k in mat if k.startswith("slice_")) == sorted("slice_%d" % i for i in range(vg.dims[0]))
     assert np.array_equal(mat["slice_2"], arr[2])
+
+
+def test_prebound_and_fast_path_wrappers_wire_their_buffers_correctly():
+    """No GPU: Context.min_distance_plan and the single-pose / single-configuration fast paths of pose_rows / chain_rows
+    against a stand-in library that reads the inputs and fills the outputs THROUGH THE RAW POINTERS it is handed -- what the
+    real entry points do.  Checks addresses, counts, flags, that outputs are copies where the scratch is reused, and that
+    the plan's arrays are overwritten in place."""
+    import ctypes as C
+    from semiinfiniteoptimization_b200 import _abi
+
+    def dbl(ptr, n):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,))
+
+    class Lib:
+        calls = []
+
+        def sio_min_distance(self, h, ga, n_g, gob, cloud, T, bound, B, flags, dmin, arg, nu):
+            g = np.ctypeslib.as_array(C.cast(ga, C.POINTER(C.c_int32)), shape=(n_g,))
+            t = dbl(T, 12 * B)
+            dbl(dmin, B)[:] = t.reshape(B, 12)[:, 3] + (dbl(bound, B) if bound else 0.0)       # something to recognise
+            np.ctypeslib.as_array(C.cast(arg, C.POINTER(C.c_int64)), shape=(B,))[:] = np.arange(B) + int(g[0]) * 100 + cloud
+            if nu:
+                np.ctypeslib.as_array(C.cast(nu, C.POINTER(C.c_int32)), shape=(B,))[:] = flags
+            self.calls.append(("min", B, flags))
+            return 0
+
+        def sio_pose_rows(self, h, grid, T, off, nT, pts, flags, d, rows):
+            o = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_int64)), shape=(nT + 1,))
+            P = int(o[-1])
+            p = dbl(pts, 3 * P).reshape(P, 3)
+            dbl(d, P)[:] = p.sum(1) + dbl(T, 12)[3]
+            if rows:
+                dbl(rows, 6 * P).reshape(P, 6)[:] = np.arange(6) + p[:, :1]
+            self.calls.append(("rows", nT, P, grid))
+            return 0
+
+        def sio_chain_rows(self, h, robot, lg, q, nq, cop, lop, pts, P, flags, d, rows):
+            links = np.ctypeslib.as_array(C.cast(lop, C.POINTER(C.c_int32)), shape=(max(P, 1),))[:P]
+            dbl(d, P)[:] = dbl(pts, 3 * P).reshape(P, 3)[:, 0] + links + dbl(q, 7)[6]
+            if rows:
+                dbl(rows, 7 * P).reshape(P, 7)[:] = dbl(q, 7)
+            self.calls.append(("chain", nq, P, cop))
+            return 0
+
+    ctx = _abi.Context.__new__(_abi.Context)
+    ctx.L, ctx.h = Lib(), None
+    # the prebound K2 call
+    plan = ctx.min_distance_plan(3, 4, 5, flags=9)
+    T = np.arange(60.0).reshape(5, 12)
+    d, a, n = plan(T, np.full(5, 0.5))
+    assert np.array_equal(d, T[:, 3] + 0.5) and np.array_equal(a, np.arange(5) + 304) and np.array_equal(n, np.full(5, 9))
+    d2, a2, n2 = plan(T + 1.0, np.zeros(5))
+    assert d2 is d and np.array_equal(d, T[:, 3] + 1.0)                    # the plan's own arrays, overwritten in place
+    nb = ctx.min_distance_plan([7, 8], 1, 2, with_bound=False, want_under=False)
+    d3, a3, n3 = nb(T[:2])
+    assert n3 is None and np.array_equal(d3, T[:2, 3]) and np.array_equal(a3, np.arange(2) + 701)
+    with pytest.raises(ValueError):
+        plan(T[:4], np.zeros(5))
+    # pose_rows: fast path (one pose, few points) and general path agree; the fast path hands out copies
+    pts = [[0.1, 0.2, 0.3], [1.0, 2.0, 3.0], [4.0, 5.0, 6.0]]
+    T1 = np.arange(12.0)
+    d_f, r_f = ctx.pose_rows(11, T1, [0, 3], pts)
+    d_k, _ = ctx.pose_rows(11, T1, [0, 2], pts[:2], want_rows=False)
+    assert np.allclose(d_f, [0.6 + 3, 6 + 3, 15 + 3]) and r_f.shape == (3, 6) and np.allclose(r_f[:, 0], [0.1, 1.0, 4.0])
+    assert np.allclose(d_k, d_f[:2]) and _ is None and np.allclose(d_f, [3.6, 9.0, 18.0])      # d_f survived the second call
+    ctx._POSE_ROWS_CAP = 1                                                 # force the general path
+    d_g, r_g = ctx.pose_rows(11, T1, [0, 3], pts)
+    assert np.array_equal(d_g, d_f) and np.array_equal(r_g, r_f)
+    d_e, r_e = _abi.Context.pose_rows(ctx, 11, T1, [0, 0], np.zeros((0, 3)))
+    assert d_e.shape == (0,) and r_e.shape == (0, 6)
+    # chain_rows likewise
+    ctx._POSE_ROWS_CAP = 256
+    q = [[0.0, 1.0, 2.0, 3.0, 4.0, 5.0, 6.0]]
+    lg = [1, 2, 3, 4, 5, 6, 7]
+    d_c, r_c = ctx.chain_rows(0, 7, lg, q, 4, pts)
+    assert np.allclose(d_c, [0.1 + 4 + 6, 1 + 4 + 6, 4 + 4 + 6]) and np.array_equal(r_c, np.tile(np.arange(7.0), (3, 1)))
+    ctx._POSE_ROWS_CAP = -1
+    d_cg, r_cg = ctx.chain_rows(0, 7, lg, q, 4, pts)
+    assert np.array_equal(d_cg, d_c) and np.array_equal(r_cg, r_c)
+    kinds = [c[0] for c in Lib.calls]
+    assert kinds.count("min") == 3 and kinds.count("rows") == 4 and kinds.count("chain") == 2
