@@ -613,3 +613,50 @@ def test_prebound_and_fast_path_wrappers_wire_their_buffers_correctly():
     assert np.array_equal(d_cg, d_c) and np.array_equal(r_cg, r_c)
     kinds = [c[0] for c in Lib.calls]
     assert kinds.count("min") == 3 and kinds.count("rows") == 4 and kinds.count("chain") == 2
+
+
+def test_grouped_solver_slices_fill_one_set_of_arrays_and_errors_propagate(monkeypatch):
+    """No GPU: GroupedPoseSolver.solve with the per-slice driver replaced by a stand-in -- contiguous slices whose sizes
+    differ by at most one, every slice writing its rows of the SAME output arrays from its own thread, the totals summed,
+    the device seconds the slowest slice's, and an exception raised in a worker thread re-raised by solve()."""
+    import threading
+    from semiinfiniteoptimization_b200 import batch
+    seen = []
+
+    def fake(obj, env, Tinits, Tdess=None, settings=None, context=None, flags=None, cap=48, _out=None):
+        n = len(Tinits)
+        seen.append((obj, context, n, threading.get_ident(), None if Tdess is None else len(Tdess)))
+        if obj == "bad":
+            raise RuntimeError("slice failed")
+        _out["T"][:] = np.asarray(Tinits) + 1.0
+        _out["status"][:] = 1
+        _out["iterations"][:] = obj
+        for k in ("fx", "gx", "gx0"):
+            _out[k][:] = obj
+        _out["n_params"][:] = 2
+        _out["params"][:] = obj
+        r = batch.BatchResult(n, per_problem_lists=False)
+        r.time_qp, r.time_cons, r.outer_iterations, r.point_queries, r.slot_overflows, r.qp_failures = 0.1 * obj, 0.2 * obj, n, 10 * n, 0, 0
+        return r
+
+    monkeypatch.setattr(batch, "optimizeCollFreeBatchDevice", fake)
+    s = batch.GroupedPoseSolver.__new__(batch.GroupedPoseSolver)
+    s.groups, s.objs, s.envs, s.ctxs = 3, [1, 2, 3], ["e"] * 3, ["c1", "c2", "c3"]
+    T = np.arange(10 * 12, dtype=np.float64).reshape(10, 12)
+    res = s.solve(T, Tdess=T + 5.0, cap=4)
+    sizes = sorted(c[2] for c in seen)
+    assert sizes == [3, 3, 4] and sum(sizes) == 10 and all(c[4] == c[2] for c in seen)
+    assert len({c[3] for c in seen}) == 3                                  # three threads
+    assert np.array_equal(res.T, T + 1.0)
+    assert list(res.num_iterations) == [1] * 3 + [2] * 3 + [3] * 4          # slice g owns a contiguous block, in order
+    assert res.outer_iterations == 10 and res.point_queries == 100
+    assert abs(res.time_qp - 0.3) < 1e-12 and abs(res.time_cons - 0.6) < 1e-12
+    assert res.instantiated_params[9] == [[3.0, 3.0, 3.0]] * 2 and res.status[0] == 'local optimum'
+    # fewer problems than slices: one slice per problem at most
+    seen.clear()
+    res = s.solve(T[:2], cap=4)
+    assert sorted(c[2] for c in seen) == [1, 1]
+    # a failing slice
+    s.objs = [1, "bad", 3]
+    with pytest.raises(RuntimeError, match="slice failed"):
+        s.solve(T, cap=4)
