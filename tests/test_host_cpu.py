@@ -622,10 +622,13 @@ def test_grouped_solver_slices_fill_one_set_of_arrays_and_errors_propagate(monke
     import threading
     from semiinfiniteoptimization_b200 import batch
     seen = []
+    gate = {"barrier": None}
 
     def fake(obj, env, Tinits, Tdess=None, settings=None, context=None, flags=None, cap=48, _out=None):
         n = len(Tinits)
         seen.append((obj, context, n, threading.get_ident(), None if Tdess is None else len(Tdess)))
+        if gate["barrier"] is not None:
+            gate["barrier"].wait(timeout=30)                # all slices are in flight at the same time, or this times out
         if obj == "bad":
             raise RuntimeError("slice failed")
         _out["T"][:] = np.asarray(Tinits) + 1.0
@@ -643,7 +646,9 @@ def test_grouped_solver_slices_fill_one_set_of_arrays_and_errors_propagate(monke
     s = batch.GroupedPoseSolver.__new__(batch.GroupedPoseSolver)
     s.groups, s.objs, s.envs, s.ctxs = 3, [1, 2, 3], ["e"] * 3, ["c1", "c2", "c3"]
     T = np.arange(10 * 12, dtype=np.float64).reshape(10, 12)
+    gate["barrier"] = threading.Barrier(3)
     res = s.solve(T, Tdess=T + 5.0, cap=4)
+    gate["barrier"] = None
     sizes = sorted(c[2] for c in seen)
     assert sizes == [3, 3, 4] and sum(sizes) == 10 and all(c[4] == c[2] for c in seen)
     assert len({c[3] for c in seen}) == 3                                  # three threads
