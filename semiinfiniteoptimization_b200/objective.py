@@ -1,7 +1,7 @@
 """Objective-function protocol of the SIP solver -- same method names and meaning as the
 reference's semiinfinite/objective.py:5-76: value / minstep / gradient / hessian / integrate.
-Objectives are O(n) host arithmetic and stay on the host (SURVEY.md component 7); only the
-protocol and the combinators the collision front-ends need are provided."""
+Objectives are O(n) host arithmetic and stay on the host (SURVEY.md component 7).  The arithmetic combinators carry the
+reference's class names (objective.py:112-199) and semantics, checked against its own classes (tests/test_host_cpu.py)."""
 import numpy as np
 import scipy.sparse
 
@@ -28,23 +28,36 @@ class ObjectiveFunctionInterface:
         return np.asarray(x) + np.asarray(dx)
 
     def __add__(self, rhs):
-        return _Sum(self, _as_objective(rhs), 1.0)
+        return AddObjectiveFunction(self, _as_objective(rhs))
 
     def __radd__(self, lhs):
-        return _Sum(_as_objective(lhs), self, 1.0)
+        return AddObjectiveFunction(_as_objective(lhs), self)
 
     def __sub__(self, rhs):
-        return _Sum(self, _as_objective(rhs), -1.0)
+        return SubObjectiveFunction(self, _as_objective(rhs))
 
-    def __mul__(self, s):
-        if isinstance(s, ObjectiveFunctionInterface):
-            raise NotImplementedError("products of objectives are outside the collision hot path")
-        return _Scaled(self, float(s))
+    def __rsub__(self, lhs):
+        return SubObjectiveFunction(_as_objective(lhs), self)
 
-    __rmul__ = __mul__
+    def __mul__(self, rhs):
+        if isinstance(rhs, ObjectiveFunctionInterface):
+            return MulObjectiveFunction(self, rhs)
+        return MulConstObjectiveFunction(self, rhs)        # the reference forgets the factor here (objective.py:58): TypeError
 
-    def __truediv__(self, s):
-        return _Scaled(self, 1.0 / float(s))
+    def __rmul__(self, lhs):
+        return MulConstObjectiveFunction(self, lhs)
+
+    def __truediv__(self, rhs):
+        if isinstance(rhs, ObjectiveFunctionInterface):
+            return DivObjectiveFunction(self, rhs)
+        return MulConstObjectiveFunction(self, 1.0 / rhs)
+
+    __div__ = __truediv__                                  # the reference is Python 2
+
+    def __pow__(self, rhs):
+        if isinstance(rhs, ObjectiveFunctionInterface):
+            raise NotImplementedError("Can't raise a function to a function power")
+        return PowConstObjectiveFunction(self, rhs)
 
 
 class ConstantObjectiveFunction(ObjectiveFunctionInterface):
@@ -109,38 +122,115 @@ def _as_objective(v):
     return v if isinstance(v, ObjectiveFunctionInterface) else ConstantObjectiveFunction(v)
 
 
-class _Sum(ObjectiveFunctionInterface):
-    def __init__(self, g, h, sign):
-        self.g, self.h, self.sign = g, h, sign
+class AddObjectiveFunction(ObjectiveFunctionInterface):
+    """f(x) = g(x) + h(x); integrates like g (objective.py:112-123)."""
+
+    def __init__(self, g, h):
+        self.g, self.h = g, h
 
     def value(self, x):
-        return self.g.value(x) + self.sign * self.h.value(x)
+        return self.g.value(x) + self.h.value(x)
 
     def gradient(self, x):
-        return self.g.gradient(x) + self.sign * self.h.gradient(x)
+        return self.g.gradient(x) + self.h.gradient(x)
 
     def hessian(self, x):
-        return self.g.hessian(x) + self.sign * self.h.hessian(x)
+        return self.g.hessian(x) + self.h.hessian(x)
 
     def integrate(self, x, dx):
         return self.g.integrate(x, dx)
 
 
-class _Scaled(ObjectiveFunctionInterface):
-    def __init__(self, g, s):
-        self.g, self.s = g, s
+class SubObjectiveFunction(AddObjectiveFunction):
+    """f(x) = g(x) - h(x) (objective.py:126-137)."""
 
     def value(self, x):
-        return self.g.value(x) * self.s
+        return self.g.value(x) - self.h.value(x)
 
     def gradient(self, x):
-        return self.g.gradient(x) * self.s
+        return self.g.gradient(x) - self.h.gradient(x)
 
     def hessian(self, x):
-        return self.g.hessian(x) * self.s
+        return self.g.hessian(x) - self.h.hessian(x)
+
+
+class MulConstObjectiveFunction(ObjectiveFunctionInterface):
+    """f(x) = g(x) * h with h a number; the minimising step is g's (objective.py:140-153)."""
+
+    def __init__(self, g, h):
+        self.g, self.h = g, h
+
+    def value(self, x):
+        return self.g.value(x) * self.h
+
+    def gradient(self, x):
+        return self.g.gradient(x) * self.h
+
+    def hessian(self, x):
+        return self.g.hessian(x) * self.h
 
     def minstep(self, x):
         return self.g.minstep(x)
+
+    def integrate(self, x, dx):
+        return self.g.integrate(x, dx)
+
+
+class MulObjectiveFunction(ObjectiveFunctionInterface):
+    """f(x) = g(x) * h(x), product rule to second order (objective.py:156-167)."""
+
+    def __init__(self, g, h):
+        self.g, self.h = g, h
+
+    def value(self, x):
+        return self.g.value(x) * self.h.value(x)
+
+    def gradient(self, x):
+        return self.g.gradient(x) * self.h.value(x) + self.g.value(x) * self.h.gradient(x)
+
+    def hessian(self, x):
+        gg, hg = self.g.gradient(x), self.h.gradient(x)
+        return self.g.hessian(x) * self.h.value(x) + np.outer(gg, hg) + self.g.value(x) * self.h.hessian(x) + np.outer(hg, gg)
+
+    def integrate(self, x, dx):
+        return self.g.integrate(x, dx)
+
+
+class DivObjectiveFunction(ObjectiveFunctionInterface):
+    """f(x) = g(x) / h(x) (objective.py:170-182)."""
+
+    def __init__(self, g, h):
+        self.g, self.h = g, h
+
+    def value(self, x):
+        return self.g.value(x) / self.h.value(x)
+
+    def gradient(self, x):
+        hval = self.h.value(x)
+        return (self.g.gradient(x) * hval + self.g.value(x) * self.h.gradient(x)) / (hval * hval)   # quirk: '+' as in the reference (the quotient rule has '-')
+
+    def hessian(self, x):
+        raise NotImplementedError("Can't do hessian of function/function division yet")
+
+    def integrate(self, x, dx):
+        return self.g.integrate(x, dx)
+
+
+class PowConstObjectiveFunction(ObjectiveFunctionInterface):
+    """f(x) = g(x) ** h with h a number (objective.py:185-199)."""
+
+    def __init__(self, g, h):
+        self.g, self.h = g, h
+
+    def value(self, x):
+        return pow(self.g.value(x), self.h)
+
+    def gradient(self, x):
+        return self.h * pow(self.g.value(x), self.h - 1) * self.g.gradient(x)
+
+    def hessian(self, x):
+        gval, ggrad = self.g.value(x), self.g.gradient(x)
+        return self.h * (self.h - 1) * pow(gval, self.h - 2) * np.outer(ggrad, ggrad) + self.h * pow(gval, self.h - 1) * self.g.hessian(x)
 
     def integrate(self, x, dx):
         return self.g.integrate(x, dx)

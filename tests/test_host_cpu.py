@@ -665,3 +665,76 @@ def test_grouped_solver_slices_fill_one_set_of_arrays_and_errors_propagate(monke
     s.objs = [1, "bad", 3]
     with pytest.raises(RuntimeError, match="slice failed"):
         s.solve(T, cap=4)
+
+
+def test_objective_combinators_equal_the_reference_classes():
+    """objective.py:112-199: Add / Sub / MulConst / Mul / Div / PowConst on the same leaf objectives through this package's
+    classes and through the reference's own (oracle/refrun; build container only), at random points: value, gradient,
+    Hessian, minstep / integrate where the reference defines them -- including Div's '+' in the quotient rule, as is."""
+    from oracle.refrun import load
+    if not load.available():
+        pytest.skip("reference sources are not present on this machine")
+    from semiinfiniteoptimization_b200 import objective as mine
+    ref = load.load()["objective"]
+
+    class Leaf:                                             # duck-typed leaf usable by both families
+        def __init__(self, A, b, c):
+            self.A, self.b, self.c = A, b, c
+
+        def value(self, x):
+            return float(0.5 * x @ self.A @ x + self.b @ x + self.c)
+
+        def gradient(self, x):
+            return self.A @ x + self.b
+
+        def hessian(self, x):
+            return self.A
+
+        def minstep(self, x):
+            return -np.linalg.solve(self.A, self.gradient(x))
+
+        def integrate(self, x, dx):
+            return x + 2.0 * dx                             # recognisable: combinators integrate like their first operand
+
+    rng = np.random.default_rng(4)
+    n = 4
+
+    def leaf():
+        M = rng.normal(size=(n, n))
+        return Leaf(M @ M.T + n * np.eye(n), rng.normal(size=n), 3.0 + rng.uniform())
+
+    g, h = leaf(), leaf()
+    pairs = [(mine.AddObjectiveFunction(g, h), ref.AddObjectiveFunction(g, h)),
+             (mine.SubObjectiveFunction(g, h), ref.SubObjectiveFunction(g, h)),
+             (mine.MulConstObjectiveFunction(g, 2.5), ref.MulConstObjectiveFunction(g, 2.5)),
+             (mine.MulObjectiveFunction(g, h), ref.MulObjectiveFunction(g, h)),
+             (mine.DivObjectiveFunction(g, h), ref.DivObjectiveFunction(g, h)),
+             (mine.PowConstObjectiveFunction(g, 3), ref.PowConstObjectiveFunction(g, 3)),
+             (mine.PowConstObjectiveFunction(g, 0.5), ref.PowConstObjectiveFunction(g, 0.5))]
+    for a, b in pairs:
+        assert type(a).__name__ == type(b).__name__
+        for _ in range(5):
+            x, dx = rng.normal(size=n), rng.normal(size=n)
+            assert a.value(x) == b.value(x)
+            assert np.array_equal(a.gradient(x), b.gradient(x))
+            assert np.array_equal(a.integrate(x, dx), b.integrate(x, dx)) and np.array_equal(a.integrate(x, dx), x + 2.0 * dx)
+            if isinstance(a, mine.DivObjectiveFunction):
+                with pytest.raises(NotImplementedError):
+                    a.hessian(x)
+                with pytest.raises(NotImplementedError):
+                    b.hessian(x)
+            else:
+                assert np.array_equal(a.hessian(x), b.hessian(x))
+            if isinstance(a, mine.MulConstObjectiveFunction):
+                assert np.array_equal(a.minstep(x), b.minstep(x))
+    # the operators build the same classes (the reference's own `f * 2.0` forgets the factor and raises TypeError)
+    q = mine.QuadraticObjectiveFunction(np.ones(n))
+    assert isinstance(q + 1.0, mine.AddObjectiveFunction) and isinstance(1.0 + q, mine.AddObjectiveFunction)
+    assert isinstance(q - q, mine.SubObjectiveFunction) and isinstance(2.0 - q, mine.SubObjectiveFunction)
+    assert isinstance(q * 2.0, mine.MulConstObjectiveFunction) and isinstance(2.0 * q, mine.MulConstObjectiveFunction)
+    assert isinstance(q * q, mine.MulObjectiveFunction) and isinstance(q / q, mine.DivObjectiveFunction)
+    assert isinstance(q / 4.0, mine.MulConstObjectiveFunction) and (q / 4.0).h == 0.25 and isinstance(q ** 2, mine.PowConstObjectiveFunction)
+    x = rng.normal(size=n)
+    assert ((q + 1.0) * 2.0).value(x) == (q.value(x) + 1.0) * 2.0 and (2.0 - q).value(x) == 2.0 - q.value(x)
+    with pytest.raises(NotImplementedError):
+        q ** q
