@@ -738,3 +738,35 @@ def test_objective_combinators_equal_the_reference_classes():
     assert ((q + 1.0) * 2.0).value(x) == (q.value(x) + 1.0) * 2.0 and (2.0 - q).value(x) == 2.0 - q.value(x)
     with pytest.raises(NotImplementedError):
         q ** q
+
+
+def test_gradient_checking_aids_equal_the_reference_functions(capsys):
+    """utils.py:3-51 (numeric_gradient in its three methods, test_gradient) against the reference's own functions through
+    oracle/refrun, on a smooth function of five variables -- including the one-sided methods' cumulative step, as is."""
+    from oracle.refrun import load
+    if not load.available():
+        pytest.skip("reference sources are not present on this machine")
+    from semiinfinite import utils as mine
+    ref = load.load()["utils"]
+    rng = np.random.default_rng(6)
+    A = rng.normal(size=(5, 5))
+
+    def f(x):
+        return float(np.sin(x @ A @ x) + x[0] * x[3])
+
+    def grad(x):
+        return np.cos(x @ A @ x) * ((A + A.T) @ x) + np.array([x[3], 0, 0, x[0], 0])
+
+    for _ in range(4):
+        x = rng.normal(size=5) * 0.3
+        for method in ("centered", "forward", "backward"):
+            assert np.array_equal(mine.numeric_gradient(f, x, 1e-4, method), ref.numeric_gradient(f, x, 1e-4, method))
+        assert np.abs(mine.numeric_gradient(f, x) - grad(x)).max() < 1e-6
+        assert mine.test_gradient(f, grad, x) is True and ref.test_gradient(f, grad, x) is True
+        wrong = lambda v: grad(v) + np.array([0, 0.01, 0, 0, 0])
+        assert mine.test_gradient(f, wrong, x, name="w") is False
+        out_mine = capsys.readouterr().out
+        assert ref.test_gradient(f, wrong, x, name="w") is False
+        assert out_mine == capsys.readouterr().out and "errorneous value 1" in out_mine
+    with pytest.raises(ValueError):
+        mine.numeric_gradient(f, np.zeros(5), method="sideways")
