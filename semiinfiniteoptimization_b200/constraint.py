@@ -207,6 +207,38 @@ class SemiInfiniteConstraintAdaptor(SemiInfiniteConstraintInterface):
         return SetDomain([(0,)])
 
 
+class MinimumConstraintAdaptor(ConstraintInterface):
+    """The plain constraint f(x) = min_y f(x, y) >= 0 of a semi-infinite one (constraint.py:259-277): value = the oracle's
+    minimum at x, gradient = df/dx at the minimising parameter -- the classical "minimum distance" formulation the
+    reference's optimizeCollFreeMinDist compares the exchange method with.
+    The reference's class cannot run as written (`self.f.setx()` without its argument, an undefined `self.minvalue`,
+    `df_dy` where the x-gradient is meant); this is what its docstring and call site (gopt:1108-1110) describe."""
+
+    def __init__(self, semi_infinite_constraint):
+        self.f = semi_infinite_constraint
+        self.minval = None
+        self.minparam = None
+
+    def dims(self):
+        return self.f.dims()
+
+    def setx(self, x):
+        self.f.setx(x)
+        res = self.f.minvalue(x)
+        if len(res) > 0 and hasattr(res[0], '__iter__'):   # a list of pairs: the deepest one
+            res = min(res, key=lambda pair: pair[0])
+        self.minval, self.minparam = res
+
+    def clearx(self):
+        self.f.clearx()
+
+    def value(self, x):
+        return self.minval
+
+    def df_dx(self, x):
+        return self.f.df_dx(x, self.minparam)
+
+
 class MultiSemiInfiniteConstraint(SemiInfiniteConstraintInterface):
     """Several scalar semi-infinite constraints c_0 .. c_{n-1} presented as one:
         min_y f(x, y) = min_i min_{y_i} c_i(x, y_i),      y = (i, y_i, zero padding to a common length)

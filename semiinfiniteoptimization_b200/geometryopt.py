@@ -1049,6 +1049,21 @@ def optimizeCollFree(obj, env, Tinit, Tdes=None, settings=None, verbose=1,
     return _format(res.x, res, want_trace, want_times, want_constraints, params=res.instantiated_params[0])
 
 
+def optimizeCollFreeMinDist(obj, env, Tinit, Tdes=None, settings=None, verbose=1,
+                            want_trace=True, want_times=True, want_constraints=True):
+    """The same pose problem through ONE plain constraint min_y distance(T, y) >= 0 (MinimumConstraintAdaptor) and the
+    generic loop (gopt:1083-1122): every evaluation is a whole cloud-vs-grid sweep, every step sees only the deepest
+    point.  Returns T or [T, trace, times, []] like optimizeCollFree (the constraints entry is empty by design).
+    The reference's function stops at its first line for want of a working adaptor (constraint.py:259-277) and names
+    an undefined `want_constraint_pts`; arguments and return shape are as written there."""
+    if Tdes is None:
+        Tdes = Tinit
+    constraint = MinimumConstraintAdaptor(ObjectCollisionConstraint(obj, env))
+    res = optimizeStandard(ObjectPoseObjective(Tdes), [constraint], Tinit, verbose=verbose, settings=settings)
+    optimizeCollFreeMinDist.last_result = res
+    return _format(res.x, res, want_trace, want_times, want_constraints, params=[])
+
+
 def optimizeCollFreeRobot(robot, env, qdes=None, qinit=None, objective=None, constraints=None,
                           settings=None, verbose=1, want_trace=True, want_times=True, want_constraints=True):
     """Robot configuration closest to qdes that keeps every link collision-free (gopt:1125-1225)."""

@@ -498,3 +498,19 @@ def test_sip_with_all_under_members_reaches_feasibility(G, c1):
         assert c.minvalue(res.x)[0] > -5e-3
         iters[mode] = res.num_iterations
     assert iters[True] <= iters[False]
+
+
+def test_min_dist_front_end_runs_on_the_device_classes(G, c1):
+    """optimizeCollFreeMinDist (gopt:1083-1122): one plain constraint min_y distance >= 0 through the generic loop, every
+    evaluation a K2 sweep; ends collision-free from a pose in collision and returns optimizeCollFree's shape with an
+    empty constraint list."""
+    g1, g2, r1, r2 = c1
+    T = c1_poses(6, seed=0)[1]
+    g1.setTransform(T)
+    d0 = g2.distance(g1)[0]
+    assert d0 < -0.05
+    out = G.optimizeCollFreeMinDist(g1, g2, T, verbose=0)
+    assert len(out) == 4 and out[3] == [] and len(out[1]) == len(out[2]) >= 2
+    g1.setTransform(out[0])
+    assert g2.distance(g1)[0] > -5e-3
+    assert G.optimizeCollFreeMinDist(g1, g2, T, verbose=0, want_trace=False, want_times=False, want_constraints=False)[1] is not None

@@ -87,3 +87,31 @@ def test_multi_golden_is_what_the_reference_produces_now():
     mv = M.minvalue(T, rec["bound"])
     assert [float(f) for f, _ in mv] == [p[0] for p in rec["pairs"]]
     assert all(np.array_equal(np.asarray(y), np.asarray(p[1])) for (_, y), p in zip(mv, rec["pairs"]))
+
+
+def test_minimum_constraint_adaptor_drives_the_generic_loop_to_a_collision_free_pose():
+    """MinimumConstraintAdaptor (constraint.py:259-277, made to run) + optimizeStandard, the body of optimizeCollFreeMinDist
+    (gopt:1083-1122), on the CPU restatement of the object constraint: value = the oracle's minimum, gradient = the row at
+    the minimising point; from poses in collision the loop ends collision-free, and agrees with minvalue / df_dx of the
+    constraint it wraps."""
+    from semiinfiniteoptimization_b200 import sip
+    from semiinfiniteoptimization_b200.constraint import MinimumConstraintAdaptor
+    from semiinfiniteoptimization_b200.geometryopt import ObjectPoseObjective
+    mod, g1, g2, con = scenes.c1_scene('restated')
+    ad = MinimumConstraintAdaptor(con)
+    solved = 0
+    for T in scenes.c1_poses(6, seed=0):
+        ad.setx(T)
+        d0, y0 = con.minvalue(T)
+        assert ad.value(T) == d0 and np.array_equal(ad.df_dx(T), con.df_dx(T, y0)) and list(ad.minparam) == list(y0)
+        ad.clearx()
+        assert ad(T) == d0                                  # __call__ brackets value with setx / clearx
+        if d0 > -0.01:
+            continue
+        res = sip.optimizeStandard(ObjectPoseObjective(T), [ad], T, settings=sip.SemiInfiniteOptimizationSettings(), verbose=0)
+        con.setx(res.x)
+        d1 = con.minvalue(res.x)[0]
+        con.clearx()
+        assert d1 > -5e-3 and d1 > d0 + 0.005, (d0, d1)
+        solved += 1
+    assert solved >= 3
